@@ -69,3 +69,107 @@ def sponge16_hash_rows(rows):
                                       ctypes.c_size_t(r.shape[1]), out.ctypes.data_as(ctypes.c_void_p))
     assert rc == 0
     return out
+
+
+# ---- Lair executor / traces (oracle/lair.h) -----------------------------------------------------
+def _vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _err():
+    lib().orc_last_error.restype = ctypes.c_char_p
+    return lib().orc_last_error().decode()
+
+
+class OracleToplevel:
+    def __init__(self, program_words):
+        L = lib()
+        L.orc_toplevel_new.restype = ctypes.c_void_p
+        w = _u32(program_words)
+        self.h = L.orc_toplevel_new(_vp(w), ctypes.c_size_t(len(w)))
+        if not self.h:
+            raise RuntimeError(_err())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_toplevel_free(ctypes.c_void_p(self.h))
+
+    def width(self, func):
+        return lib().orc_func_width(ctypes.c_void_p(self.h), func)
+
+
+class OracleRecord:
+    """QueryRecord (src/lair/execute.rs:67-75) held by the oracle."""
+
+    def __init__(self, top: OracleToplevel):
+        L = lib()
+        L.orc_record_new.restype = ctypes.c_void_p
+        for f in ("orc_num_queries", "orc_num_mem", "orc_public_values", "orc_func_trace_height", "orc_mem_trace_height"):
+            getattr(L, f).restype = ctypes.c_size_t
+        self.top = top
+        self.h = L.orc_record_new(ctypes.c_void_p(top.h))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_record_free(ctypes.c_void_p(self.h))
+
+    def execute(self, func, args, nout):
+        a = _u32(args)
+        out = np.zeros(nout, dtype=np.uint32)
+        rc = lib().orc_execute(ctypes.c_void_p(self.top.h), ctypes.c_void_p(self.h), func, _vp(a),
+                               ctypes.c_size_t(len(a)), _vp(out), ctypes.c_size_t(nout))
+        if rc:
+            raise RuntimeError(_err())
+        return out
+
+    def inject_inv_queries(self, func, inps, outs):
+        i, o = _u32(inps), _u32(outs)
+        rc = lib().orc_inject_inv_queries(ctypes.c_void_p(self.top.h), ctypes.c_void_p(self.h), func, _vp(i), _vp(o),
+                                          ctypes.c_size_t(len(i)))
+        if rc:
+            raise RuntimeError(_err())
+
+    def num_queries(self, func):
+        return lib().orc_num_queries(ctypes.c_void_p(self.h), func)
+
+    def num_mem(self, mem_idx):
+        return lib().orc_num_mem(ctypes.c_void_p(self.h), mem_idx)
+
+    def num_shards(self, shard_size):
+        return lib().orc_num_shards(ctypes.c_void_p(self.h), shard_size)
+
+    def public_values(self):
+        out = np.zeros(64, dtype=np.uint32)
+        n = lib().orc_public_values(ctypes.c_void_p(self.h), _vp(out), ctypes.c_size_t(64))
+        return out[:n].copy()
+
+    def func_trace(self, func, shard=0, shard_size=1 << 22):
+        h = lib().orc_func_trace_height(ctypes.c_void_p(self.h), func, shard, shard_size)
+        w = self.top.width(func)
+        out = np.zeros((h, w), dtype=np.uint32)
+        rc = lib().orc_func_trace(ctypes.c_void_p(self.top.h), ctypes.c_void_p(self.h), func, shard, shard_size, _vp(out))
+        if rc:
+            raise RuntimeError(_err())
+        return out
+
+    def mem_trace(self, mem_idx):
+        h = lib().orc_mem_trace_height(ctypes.c_void_p(self.h), mem_idx)
+        w = 4 + [2, 3, 4, 5, 6, 8][mem_idx]
+        out = np.zeros((h, w), dtype=np.uint32)
+        rc = lib().orc_mem_trace(ctypes.c_void_p(self.h), mem_idx, _vp(out))
+        if rc:
+            raise RuntimeError(_err())
+        return out
+
+    def bytes_trace(self, shard=0):
+        out = np.zeros((1 << 16, 13), dtype=np.uint32)
+        rc = lib().orc_bytes_trace(ctypes.c_void_p(self.h), shard, _vp(out))
+        if rc:
+            raise RuntimeError(_err())
+        return out
+
+
+def bytes_preprocessed():
+    out = np.zeros((1 << 16, 6), dtype=np.uint32)
+    lib().orc_bytes_preprocessed(_vp(out))
+    return out

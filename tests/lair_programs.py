@@ -1,0 +1,123 @@
+"""Lair programs used by the reference's own tests, re-expressed with the lurk_b200.lair builder.
+Each cites the `func!` it mirrors."""
+from lurk_b200.lair import (Toplevel, add, array, assert_eq, assert_ne, call, const, contains, eq, func, if_, load,
+                            match, match_many, mul, not_, range_u8, ret, store, sub)
+
+
+def match_toplevel():
+    """src/lair/trace.rs:517-543 (lair_match_trace_test)"""
+    f = func("test", ["n", "m"], 1, [
+        const("one", 1),
+        match("n", [
+            (0, [ret("one")]),
+            (1, [ret("m")]),
+            (2, [mul("res", "m", "m"), ret("res")]),
+            (3, [mul("res", "m", "m"), mul("res2", "res", "res"), ret("res2")]),
+        ]),
+        sub("pred", "n", "one"),
+        call(["res"], "test", ["pred", "m"]),
+        ret("res"),
+    ])
+    return Toplevel.new_pure([f])
+
+
+def inner_match_toplevel():
+    """src/lair/trace.rs:580-610 (lair_inner_match_trace_test)"""
+    f = func("test", ["n", "m"], 1, [
+        const("zero", 0), const("one", 1), const("two", 2), const("three", 3),
+        match("n", [
+            (0, [match("m", [(0, [ret("zero")]), (1, [ret("one")])], exhaustive=True)]),
+            (1, [match("m", [(0, [ret("two")]), (1, [ret("three")])], exhaustive=True)]),
+        ], exhaustive=True),
+    ])
+    return Toplevel.new_pure([f])
+
+
+def not_eq_toplevel():
+    """src/lair/air.rs:627-637 (lair_not_eq_test); note the order [eq, not]"""
+    not_f = func("not", ["a"], 1, [not_("x", "a"), ret("x")])
+    eq_f = func("eq", ["a", "b"], 1, [eq("x", "a", "b"), ret("x")])
+    return Toplevel.new_pure([eq_f, not_f])
+
+
+def if_many_toplevel():
+    """src/lair/air.rs:716-725"""
+    f = func("if_many", [("a", 4)], 1, [
+        if_("a", [const("one", 1), ret("one")]),
+        const("zero", 0),
+        ret("zero"),
+    ])
+    return Toplevel.new_pure([f])
+
+
+def match_many_toplevel():
+    """src/lair/air.rs:771-794"""
+    f = func("match_many", [("a", 2)], 2, [
+        match_many("a", [
+            ([0, 0], [array("res", [1, 0]), ret("res")]),
+            ([0, 1], [array("res", [1, 1]), ret("res")]),
+            ([1, 0], [array("res", [1, 2]), ret("res")]),
+            ([1, 1], [array("res", [1, 3]), ret("res")]),
+        ]),
+        array("fail", [0, 0]),
+        ret("fail"),
+    ])
+    return Toplevel.new_pure([f])
+
+
+def assert_toplevel():
+    """src/lair/air.rs:849-861"""
+    f = func("assert", [("a", 4)], 4, [
+        array("arr1", [2, 4, 5, 8]),
+        array("arr2", [2, 4, 6, 8]),
+        assert_ne("a", "arr1"),
+        const("two", 2),
+        const("four", 4),
+        contains("a", "two"),
+        contains("a", "four"),
+        assert_eq("a", "arr2"),
+        ret("a"),
+    ])
+    return Toplevel.new_pure([f])
+
+
+def equal_branch_toplevel():
+    """src/lair/air.rs:888-898"""
+    f = func("test", ["a"], 1, [
+        match("a", [((2, 3, 4), [const("one", 1), ret("one")])]),
+        ret("a"),
+    ])
+    return Toplevel.new_pure([f])
+
+
+def range_toplevel():
+    """src/lair/air.rs:943-948"""
+    f = func("range_test", [("x", 3)], 0, [range_u8(["x"]), ret()])
+    return Toplevel.new_pure([f])
+
+
+def memory_toplevel():
+    """src/lair/memory.rs:133-142"""
+    f = func("test", [], 2, [
+        const("one", 1), const("two", 2), const("three", 3),
+        store("ptr1", ["one", "two", "three"]),
+        store("ptr2", ["one", "one", "one"]),
+        load(["_x", "y", "_z"], "ptr1"),
+        ret("ptr2", "y"),
+    ])
+    return Toplevel.new_pure([f])
+
+
+def ackermann_toplevel():
+    """src/lair/trace.rs:659-680 (lair_shard_test)"""
+    f = func("ackermann", ["m", "n"], 1, [
+        const("one", 1),
+        match("m", [(0, [add("ret", "n", "one"), ret("ret")])]),
+        sub("m_minus_one", "m", "one"),
+        match("n", [(0, [call(["ret"], "ackermann", ["m_minus_one", "one"]), ret("ret")])]),
+        sub("n_minus_one", "n", "one"),
+        call(["inner"], "ackermann", ["m", "n_minus_one"]),
+        call(["ret"], "ackermann", ["m_minus_one", "inner"]),
+        ret("ret"),
+    ])
+    return Toplevel.new_pure([f])

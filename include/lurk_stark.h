@@ -1,0 +1,99 @@
+/* lurk_stark.h -- C ABI of liblurkstark, the B200-native proving hot path for Lurk.
+ *
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * argumentcomputer/lurk tree).  Conventions:
+ *   - return 0 on success, negative on error; never throws or aborts across the boundary;
+ *     lsk_last_error() gives the message (thread-local, valid until the next call on this thread);
+ *   - field elements cross the boundary as canonical u32 residues of BabyBear
+ *     (from_canonical_u32 / as_canonical_u32); Montgomery form is internal;
+ *   - matrices cross the boundary row-major exactly as RowMajorMatrix.values;
+ *   - `const uint32_t*` arguments are HOST pointers unless the name says `_dev`;
+ *   - an lsk_ctx owns one CUDA device + stream; it is stream-ordered and not re-entrant;
+ *     distinct contexts are independent (one process per GPU).
+ *   - there is NO CPU fallback: every compute entry point fails with LSK_ERR_CUDA when no
+ *     device is usable.
+ */
+#ifndef LURK_STARK_H
+#define LURK_STARK_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSK_OK 0
+#define LSK_ERR_ARG (-1)
+#define LSK_ERR_CUDA (-2)
+#define LSK_ERR_EXEC (-3)   /* Lair execution error (the reference panics / bails) */
+#define LSK_ERR_VERIFY (-4)
+
+typedef struct lsk_ctx lsk_ctx;
+typedef struct lsk_program lsk_program;   /* a loaded Toplevel (src/lair/toplevel.rs:25-56) */
+typedef struct lsk_record lsk_record;     /* a flattened QueryRecord (src/lair/execute.rs:67-75) */
+typedef struct lsk_machine lsk_machine;   /* StarkMachine + pk/vk (src/core/stark_machine.rs:20-30) */
+
+const char* lsk_last_error(void);
+int lsk_version(void);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int lsk_ctx_create(int device, lsk_ctx** out);
+void lsk_ctx_destroy(lsk_ctx* ctx);
+/* cudaStream_t of the context (so callers can bracket work with their own CUDA events) */
+void* lsk_ctx_stream(lsk_ctx* ctx);
+int lsk_ctx_sync(lsk_ctx* ctx);
+
+/* ---- A1: Poseidon2 hashing of content-addressed data ------------------------------------------
+ * replaces PoseidonChipset::hash / execute_simple, src/core/poseidon.rs:29-39,61-63 as called from
+ * ZStore::hash3/4/5, src/core/zstore.rs:305-333.  width in {24, 32, 40} (also 16: the commitment
+ * permutation); `in` is n rows of `width` words, `out8` n rows of 8 words. */
+int lsk_poseidon2_hash(lsk_ctx* ctx, int width, const uint32_t* in, size_t n, uint32_t* out8);
+int lsk_poseidon2_hash_dev(lsk_ctx* ctx, int width, const uint32_t* in_dev, size_t n, uint32_t* out8_dev);
+/* full permutation (p3 Poseidon2::permute, hasher() in src/poseidon/config.rs:77-95) */
+int lsk_poseidon2_permute(lsk_ctx* ctx, int width, const uint32_t* in, size_t n, uint32_t* out);
+/* replaces PoseidonChipset::populate_witness, src/core/poseidon.rs:65-72 (+ Poseidon2Cols::populate,
+ * src/poseidon/wide/trace.rs:12-82): out row = digest[8] ++ wide witness; lsk_poseidon2_witness_cols
+ * gives the row length (457 / 611 / 763). */
+int lsk_poseidon2_witness_cols(int width);
+int lsk_poseidon2_witness(lsk_ctx* ctx, int width, const uint32_t* in, size_t n, uint32_t* out);
+
+/* ---- A2/A3: program + flattened record ------------------------------------------------------
+ * `words` is the flat Toplevel image produced by the host layer (lurk_b200/lair.py::serialize;
+ * format documented in DESIGN.md).  The executor is the host-side producer of the hot path's
+ * input (Toplevel::execute, src/lair/execute.rs:375-783) re-designed to emit GPU-ready SoA tables
+ * with resolved callee / pointer row indices. */
+int lsk_program_load(const uint32_t* words, size_t n, lsk_program** out);
+void lsk_program_free(lsk_program* p);
+int lsk_program_num_funcs(const lsk_program* p);
+int lsk_program_func_width(const lsk_program* p, uint32_t func);   /* BaseAir::width, func_chip.rs:83-87 */
+
+int lsk_record_new(const lsk_program* p, lsk_record** out);        /* QueryRecord::new, execute.rs:263-284 */
+void lsk_record_free(lsk_record* r);
+int lsk_execute(const lsk_program* p, lsk_record* r, uint32_t func, const uint32_t* args, size_t nargs,
+                uint32_t* out, size_t nout);                        /* Toplevel::execute, execute.rs:376-392 */
+int lsk_inject_inv_queries(const lsk_program* p, lsk_record* r, uint32_t func, const uint32_t* inps,
+                           const uint32_t* outs, size_t n);         /* execute.rs:299-319 */
+size_t lsk_record_num_queries(const lsk_record* r, uint32_t func);
+size_t lsk_record_num_mem(const lsk_record* r, uint32_t mem_idx);
+size_t lsk_record_public_values(const lsk_record* r, uint32_t* out, size_t cap);
+uint32_t lsk_record_num_shards(const lsk_record* r, uint32_t shard_size);  /* Shard::shard, execute.rs:186-216 */
+/* bytes a prove call moves host->device for this record (for end-to-end accounting) */
+size_t lsk_record_device_bytes(const lsk_record* r);
+
+/* ---- A4/A5: trace generation -------------------------------------------------------------------
+ * replaces FuncChip::generate_trace (src/lair/trace.rs:72-135), MemChip::generate_trace
+ * (src/lair/memory.rs:30-68), BytesChip::generate_trace / preprocessed_trace
+ * (src/gadgets/bytes/trace.rs:49-101).  Output: row-major canonical, height x width, where
+ * height is given by the *_height call (next power of two; >= 4 for Mem; 65536 for Bytes). */
+size_t lsk_func_trace_height(const lsk_record* r, uint32_t func, uint32_t shard, uint32_t shard_size);
+int lsk_func_trace(lsk_ctx* ctx, const lsk_program* p, const lsk_record* r, uint32_t func, uint32_t shard,
+                   uint32_t shard_size, uint32_t* out_row_major);
+size_t lsk_mem_trace_height(const lsk_record* r, uint32_t mem_idx);
+int lsk_mem_trace(lsk_ctx* ctx, const lsk_record* r, uint32_t mem_idx, uint32_t* out_row_major);
+int lsk_bytes_trace(lsk_ctx* ctx, const lsk_record* r, uint32_t shard, uint32_t* out_row_major /* 65536 x 13 */);
+int lsk_bytes_preprocessed(lsk_ctx* ctx, uint32_t* out_row_major /* 65536 x 6 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

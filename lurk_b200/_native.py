@@ -1,0 +1,103 @@
+"""ctypes binding of liblurkstark.so (the C ABI in include/lurk_stark.h).
+
+There is no CPU fallback: if the library is missing, or no CUDA device is usable when a context
+is created, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "liblurkstark.so")
+HEADER = os.path.join(os.path.dirname(_PKG), "include", "lurk_stark.h")
+_lib = None
+
+
+class LurkStarkError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"liblurkstark error {code}: {msg}")
+        self.code = code
+
+
+def build(jobs: int = 8):
+    """Compile the CUDA library in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    subprocess.check_call(["make", "-s", f"-j{jobs}", "-C", os.path.join(_PKG, "csrc")])
+
+
+def declared_symbols():
+    """Every `lsk_*` function declared in include/lurk_stark.h."""
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lsk_[a-z0-9_]+)\s*\(", src)))
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(liblurkstark has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        L.lsk_last_error.restype = ctypes.c_char_p
+        L.lsk_ctx_stream.restype = ctypes.c_void_p
+        for f in ("lsk_record_num_queries", "lsk_record_num_mem", "lsk_record_public_values",
+                  "lsk_func_trace_height", "lsk_mem_trace_height", "lsk_record_device_bytes"):
+            getattr(L, f).restype = ctypes.c_size_t
+        L.lsk_record_num_shards.restype = ctypes.c_uint32
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise LurkStarkError(rc, lib().lsk_last_error().decode())
+
+
+def u32(a):
+    return np.ascontiguousarray(a, dtype=np.uint32)
+
+
+def vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """lsk_ctx: one CUDA device + stream."""
+
+    def __init__(self, device: int = 0):
+        self.h = ctypes.c_void_p()
+        check(lib().lsk_ctx_create(int(device), ctypes.byref(self.h)))
+        self.device = device
+
+    def close(self):
+        if self.h:
+            lib().lsk_ctx_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return lib().lsk_ctx_stream(self.h)
+
+    def sync(self):
+        check(lib().lsk_ctx_sync(self.h))
+
+
+_default_ctx = None
+
+
+def default_context() -> Context:
+    global _default_ctx
+    if _default_ctx is None:
+        _default_ctx = Context(int(os.environ.get("LOCAL_RANK", "0")))
+    return _default_ctx

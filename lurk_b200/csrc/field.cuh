@@ -1,0 +1,186 @@
+// BabyBear (p = 2^31 - 2^27 + 1) and its quartic extension F[x]/(x^4 - 11) for sm_100a.
+//
+// Device representation: Montgomery form (x * 2^32 mod p), always reduced to [0, p).  Field
+// elements cross the C ABI in canonical form (the reference's from_canonical_u32 /
+// as_canonical_u32 view, e.g. src/lair/mod.rs:33-46); conversion happens in the first/last kernel
+// that touches boundary data.  The arithmetic itself lives in the third-party p3-baby-bear /
+// p3-field crates in the reference, so this is a from-scratch implementation of
+// the published field, not a translation.
+//
+// A Montgomery product costs 1 IMAD.WIDE + 1 IMAD (lo) + 1 IMAD.HI + sub/compare/select on the
+// fma/alu pipes; there are no tensor-core shaped operations anywhere on this path.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LSK_HD __host__ __device__ __forceinline__
+#define LSK_D __device__ __forceinline__
+#else
+#define LSK_HD inline
+#define LSK_D inline
+#endif
+
+namespace lsk {
+
+constexpr uint32_t P = 0x78000001u;
+constexpr uint32_t PINV = 0x88000001u;      // P * PINV == 1 (mod 2^32)
+constexpr uint32_t R1 = 268435454u;         // 2^32 mod P  (Montgomery one)
+constexpr uint32_t R2 = 1172168163u;        // 2^64 mod P
+constexpr uint32_t GEN = 31u;               // multiplicative generator (coset shift)
+constexpr uint32_t TWO_ADIC_GEN_27 = 0x1a427a41u;  // 31^((p-1)/2^27)
+
+LSK_HD uint32_t mont_reduce(uint64_t x) {
+  uint32_t t = (uint32_t)x * PINV;
+#if defined(__CUDA_ARCH__)
+  uint32_t hu = __umulhi(t, P);
+#else
+  uint32_t hu = (uint32_t)(((uint64_t)t * P) >> 32);
+#endif
+  uint32_t hx = (uint32_t)(x >> 32);
+  uint32_t r = hx - hu;
+  return hx < hu ? r + P : r;
+}
+LSK_HD uint32_t fmul(uint32_t a, uint32_t b) { return mont_reduce((uint64_t)a * b); }
+LSK_HD uint32_t fadd(uint32_t a, uint32_t b) {
+  uint32_t s = a + b;
+  return s >= P ? s - P : s;
+}
+LSK_HD uint32_t fsub(uint32_t a, uint32_t b) {
+  uint32_t s = a - b;
+  return a < b ? s + P : s;
+}
+LSK_HD uint32_t fneg(uint32_t a) { return a ? P - a : 0u; }
+LSK_HD uint32_t fdbl(uint32_t a) { return fadd(a, a); }
+LSK_HD uint32_t to_mont(uint32_t canonical) { return fmul(canonical, R2); }
+LSK_HD uint32_t from_mont(uint32_t m) { return mont_reduce((uint64_t)m); }
+LSK_HD uint32_t fsqr(uint32_t a) { return fmul(a, a); }
+
+// a^(p-2): p - 2 = 7 * 2^28 + (2^27 - 1).  ~62 products.  Returns 0 for 0.
+LSK_HD uint32_t finv(uint32_t a) {
+  uint32_t x1 = a;
+  uint32_t x2 = fmul(fsqr(x1), x1);
+  uint32_t x3 = fmul(fsqr(x2), x1);
+  uint32_t t = x3;
+  for (int i = 0; i < 3; i++) t = fsqr(t);
+  uint32_t x6 = fmul(t, x3);
+  t = x6;
+  for (int i = 0; i < 6; i++) t = fsqr(t);
+  uint32_t x12 = fmul(t, x6);
+  t = x12;
+  for (int i = 0; i < 12; i++) t = fsqr(t);
+  uint32_t x24 = fmul(t, x12);
+  t = x24;
+  for (int i = 0; i < 3; i++) t = fsqr(t);
+  uint32_t x27 = fmul(t, x3);  // a^(2^27 - 1)
+  t = x3;                      // a^7
+  for (int i = 0; i < 28; i++) t = fsqr(t);
+  return fmul(t, x27);
+}
+LSK_HD uint32_t fpow(uint32_t b, uint64_t e) {
+  uint32_t r = R1;
+  while (e) {
+    if (e & 1) r = fmul(r, b);
+    b = fsqr(b);
+    e >>= 1;
+  }
+  return r;
+}
+// generator of the subgroup of order 2^bits, Montgomery form
+LSK_HD uint32_t two_adic_generator(unsigned bits) {
+  uint32_t g = to_mont(TWO_ADIC_GEN_27);
+  for (unsigned i = bits; i < 27; i++) g = fsqr(g);
+  return g;
+}
+LSK_HD uint32_t fmul11(uint32_t a) {
+  uint32_t a2 = fdbl(a), a4 = fdbl(a2), a8 = fdbl(a4);
+  return fadd(fadd(a8, a2), a);
+}
+
+// ---- quartic extension ------------------------------------------------------------------------
+struct __align__(16) Ext {
+  uint32_t c[4];
+};
+LSK_HD Ext ext_zero() { return Ext{{0, 0, 0, 0}}; }
+LSK_HD Ext ext_one() { return Ext{{R1, 0, 0, 0}}; }
+LSK_HD Ext ext_from_base(uint32_t a) { return Ext{{a, 0, 0, 0}}; }
+LSK_HD bool ext_eq(const Ext& a, const Ext& b) {
+  return a.c[0] == b.c[0] && a.c[1] == b.c[1] && a.c[2] == b.c[2] && a.c[3] == b.c[3];
+}
+LSK_HD Ext eadd(const Ext& a, const Ext& b) {
+  return Ext{{fadd(a.c[0], b.c[0]), fadd(a.c[1], b.c[1]), fadd(a.c[2], b.c[2]), fadd(a.c[3], b.c[3])}};
+}
+LSK_HD Ext esub(const Ext& a, const Ext& b) {
+  return Ext{{fsub(a.c[0], b.c[0]), fsub(a.c[1], b.c[1]), fsub(a.c[2], b.c[2]), fsub(a.c[3], b.c[3])}};
+}
+LSK_HD Ext eneg(const Ext& a) { return Ext{{fneg(a.c[0]), fneg(a.c[1]), fneg(a.c[2]), fneg(a.c[3])}}; }
+LSK_HD Ext emul_base(const Ext& a, uint32_t b) {
+  return Ext{{fmul(a.c[0], b), fmul(a.c[1], b), fmul(a.c[2], b), fmul(a.c[3], b)}};
+}
+LSK_HD Ext eadd_base(const Ext& a, uint32_t b) { return Ext{{fadd(a.c[0], b), a.c[1], a.c[2], a.c[3]}}; }
+LSK_HD Ext esub_base(const Ext& a, uint32_t b) { return Ext{{fsub(a.c[0], b), a.c[1], a.c[2], a.c[3]}}; }
+
+// Schoolbook product with the 64-bit partial sums reduced once per coefficient: each a_i*b_j is
+// < 2^62, so up to four of them (pre-scaled where x^4 = 11 folds back) are accumulated modulo
+// P*2^32 before a single Montgomery reduction.
+LSK_HD uint64_t acc_reduce64(uint64_t x) {  // keep x < P * 2^32 so mont_reduce stays in range
+  const uint64_t M = (uint64_t)P << 32;
+  return x >= M ? x - M : x;
+}
+LSK_HD Ext emul(const Ext& a, const Ext& b) {
+  // high part folded with W = 11: compute t_k = sum_{i+j=k+4} a_i b_j as field elements first
+  uint32_t h0 = mont_reduce(acc_reduce64(acc_reduce64((uint64_t)a.c[1] * b.c[3] + (uint64_t)a.c[2] * b.c[2]) +
+                                         (uint64_t)a.c[3] * b.c[1]));
+  uint32_t h1 = mont_reduce(acc_reduce64((uint64_t)a.c[2] * b.c[3] + (uint64_t)a.c[3] * b.c[2]));
+  uint32_t h2 = fmul(a.c[3], b.c[3]);
+  uint32_t l0 = fmul(a.c[0], b.c[0]);
+  uint32_t l1 = mont_reduce(acc_reduce64((uint64_t)a.c[0] * b.c[1] + (uint64_t)a.c[1] * b.c[0]));
+  uint32_t l2 = mont_reduce(acc_reduce64(acc_reduce64((uint64_t)a.c[0] * b.c[2] + (uint64_t)a.c[1] * b.c[1]) +
+                                         (uint64_t)a.c[2] * b.c[0]));
+  uint32_t l3 = mont_reduce(acc_reduce64(
+      acc_reduce64(acc_reduce64((uint64_t)a.c[0] * b.c[3] + (uint64_t)a.c[1] * b.c[2]) + (uint64_t)a.c[2] * b.c[1]) +
+      (uint64_t)a.c[3] * b.c[0]));
+  return Ext{{fadd(l0, fmul11(h0)), fadd(l1, fmul11(h1)), fadd(l2, fmul11(h2)), l3}};
+}
+LSK_HD Ext esqr(const Ext& a) { return emul(a, a); }
+
+// 1/a via the tower F[y]/(y^2-11) -> F[x]/(x^2-y): a = A + xB, 1/a = (A - xB)/(A^2 - yB^2).
+LSK_HD Ext einv(const Ext& a) {
+  uint32_t a0 = a.c[0], a1 = a.c[1], a2 = a.c[2], a3 = a.c[3];
+  uint32_t a1a3 = fmul(a1, a3), a0a2 = fmul(a0, a2);
+  uint32_t d0 = fsub(fadd(fsqr(a0), fmul11(fsqr(a2))), fmul11(fdbl(a1a3)));
+  uint32_t d1 = fsub(fsub(fdbl(a0a2), fsqr(a1)), fmul11(fsqr(a3)));
+  uint32_t n = fsub(fsqr(d0), fmul11(fsqr(d1)));
+  uint32_t ni = finv(n);
+  uint32_t e0 = fmul(d0, ni), e1 = fneg(fmul(d1, ni));
+  uint32_t r0 = fadd(fmul(a0, e0), fmul11(fmul(a2, e1)));
+  uint32_t r2 = fadd(fmul(a0, e1), fmul(a2, e0));
+  uint32_t r1 = fneg(fadd(fmul(a1, e0), fmul11(fmul(a3, e1))));
+  uint32_t r3 = fneg(fadd(fmul(a1, e1), fmul(a3, e0)));
+  return Ext{{r0, r1, r2, r3}};
+}
+LSK_HD Ext epow(Ext b, uint64_t e) {
+  Ext r = ext_one();
+  while (e) {
+    if (e & 1) r = emul(r, b);
+    b = esqr(b);
+    e >>= 1;
+  }
+  return r;
+}
+
+LSK_HD uint32_t bitrev32(uint32_t x, unsigned bits) {
+#if defined(__CUDA_ARCH__)
+  return bits ? (__brev(x) >> (32 - bits)) : 0u;
+#else
+  uint32_t r = 0;
+  for (unsigned i = 0; i < bits; i++) r |= ((x >> i) & 1u) << (bits - 1 - i);
+  return r;
+#endif
+}
+LSK_HD unsigned log2_exact(uint64_t n) {
+  unsigned l = 0;
+  while ((1ull << l) < n) l++;
+  return l;
+}
+
+}  // namespace lsk

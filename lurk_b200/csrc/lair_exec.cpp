@@ -1,0 +1,465 @@
+// Host-side Lair executor that emits the flattened, GPU-ready QueryRecord (record.h).
+//
+// Mirrors the behaviour of Toplevel::execute / Func::execute (src/lair/execute.rs:375-783):
+// memoised evaluation where every distinct (func, args) becomes one row whose index is its
+// insertion order (the nonce), `provide`/`require` bookkeeping through Record::new_lookup
+// (src/air/builder.rs:141-148), the pre-seeded `provide.count = 1` of the entry query
+// (execute.rs:444-447), memory tables by length class (:641-664) and byte range checks (:673-682).
+// Re-designed rather than transliterated: it walks the flat program image with a program counter
+// and three shared stacks (values, require records, hints) instead of cloning per-call vectors,
+// and it records callee / slot row indices so no hashing is needed at trace time.
+//
+// This is the producer of the hot path's input; it is sequential by construction (memo table +
+// nonce order) and stays on the CPU exactly like the reference's.
+#include <cstring>
+
+#include "common.h"
+#include "poseidon2_constants.h"
+#include "record.h"
+
+namespace lsk {
+
+static const uint64_t Pq = 0x78000001ull;
+static inline uint32_t hadd(uint32_t a, uint32_t b) { uint32_t s = a + b; return s >= Pq ? s - Pq : s; }
+static inline uint32_t hsub(uint32_t a, uint32_t b) { return a >= b ? a - b : a + (uint32_t)Pq - b; }
+static inline uint32_t hmul(uint32_t a, uint32_t b) { return (uint32_t)((uint64_t)a * b % Pq); }
+static inline uint32_t hpow(uint32_t b, uint64_t e) {
+  uint32_t r = 1;
+  while (e) { if (e & 1) r = hmul(r, b); b = hmul(b, b); e >>= 1; }
+  return r;
+}
+static inline uint32_t hinv(uint32_t a) { return hpow(a, Pq - 2); }
+
+// Host Poseidon2 (canonical arithmetic) for ExternCall hashers: PoseidonChipset::execute_simple,
+// src/core/poseidon.rs:61-63.  Only used by the executor; the proving path hashes on the GPU.
+static void host_external_linear(uint32_t* s, int t) {
+  for (int i = 0; i < t; i += 4) {
+    uint64_t x0 = s[i], x1 = s[i + 1], x2 = s[i + 2], x3 = s[i + 3];
+    s[i] = (uint32_t)((2 * x0 + 3 * x1 + x2 + x3) % Pq);
+    s[i + 1] = (uint32_t)((x0 + 2 * x1 + 3 * x2 + x3) % Pq);
+    s[i + 2] = (uint32_t)((x0 + x1 + 2 * x2 + 3 * x3) % Pq);
+    s[i + 3] = (uint32_t)((3 * x0 + x1 + x2 + 2 * x3) % Pq);
+  }
+  uint64_t sums[4] = {0, 0, 0, 0};
+  for (int i = 0; i < t; i++) sums[i & 3] += s[i];
+  for (int i = 0; i < t; i++) s[i] = (uint32_t)((s[i] + sums[i & 3]) % Pq);
+}
+static inline uint32_t host_sbox(uint32_t x) {
+  uint32_t x3 = hmul(hmul(x, x), x);
+  return hmul(x, hmul(x3, x3));
+}
+static void host_poseidon2(uint32_t* s, int t) {
+  const uint32_t *diag, *full, *part;
+  int rp;
+  switch (t) {
+    case 24: diag = P2_DIAG_24; full = P2_FULL_RC_24; part = P2_PART_RC_24; rp = P2_RP_24; break;
+    case 32: diag = P2_DIAG_32; full = P2_FULL_RC_32; part = P2_PART_RC_32; rp = P2_RP_32; break;
+    case 40: diag = P2_DIAG_40; full = P2_FULL_RC_40; part = P2_PART_RC_40; rp = P2_RP_40; break;
+    default: fail(LSK_ERR_EXEC, "unknown extern chip width %d", t);
+  }
+  host_external_linear(s, t);
+  auto full_round = [&](int r) {
+    for (int i = 0; i < t; i++) s[i] = host_sbox(hadd(s[i], full[r * t + i]));
+    host_external_linear(s, t);
+  };
+  for (int r = 0; r < 4; r++) full_round(r);
+  for (int r = 0; r < rp; r++) {
+    s[0] = host_sbox(hadd(s[0], part[r]));
+    uint64_t sum = 0;
+    for (int i = 0; i < t; i++) sum += s[i];
+    sum %= Pq;
+    for (int i = 0; i < t; i++) s[i] = (uint32_t)(((uint64_t)s[i] * diag[i] + sum) % Pq);
+  }
+  for (int r = 4; r < 8; r++) full_round(r);
+}
+static inline int chip_width(uint32_t kind) { return kind == 1 ? 24 : kind == 2 ? 32 : kind == 3 ? 40 : 0; }
+
+struct Frame {
+  uint32_t func, nonce, pc, ops_left;
+  size_t map_base, req_base, hint_base;
+  bool preimg;  // this frame was entered through PreImg: the caller receives the inputs
+};
+
+struct Executor {
+  const lsk_program& prog;
+  lsk_record& rec;
+  const uint32_t* w;
+  std::vector<uint32_t> vals, req_stack, hint_stack;
+  std::vector<Frame> frames;
+  Executor(const lsk_program& p, lsk_record& r) : prog(p), rec(r), w(p.words.data()) {}
+
+  static void new_lookup(uint32_t* provide, uint32_t nonce, std::vector<uint32_t>& reqs) {
+    reqs.push_back(provide[0]);
+    reqs.push_back(provide[1]);
+    provide[0] = nonce;
+    provide[1] += 1;
+  }
+  uint32_t insert_query(uint32_t f, const uint32_t* args, uint32_t seed_count) {
+    FuncTable& t = rec.funcs[f];
+    uint32_t row = (uint32_t)t.rows();
+    t.args.insert(t.args.end(), args, args + t.in);
+    t.outs.resize(t.outs.size() + t.out, 0);
+    t.done.push_back(0);
+    t.provide.push_back(0);
+    t.provide.push_back(seed_count);
+    t.req_off.push_back(0);
+    t.hint_off.push_back(0);
+    t.index.insert_new(t.args.data(), t.in, row);
+    return row;
+  }
+  void enter_block(Frame& f, uint32_t block) {
+    f.ops_left = w[block + 1];
+    f.pc = block + 2;
+  }
+  void push_frame(uint32_t func, uint32_t nonce, const uint32_t* inp, uint32_t n, bool preimg) {
+    Frame f{func, nonce, 0, 0, vals.size(), req_stack.size(), hint_stack.size(), preimg};
+    // NB `inp` may point into `vals`; copy before growing
+    std::vector<uint32_t> tmp(inp, inp + n);
+    vals.insert(vals.end(), tmp.begin(), tmp.end());
+    enter_block(f, prog.body(func));
+    frames.push_back(f);
+  }
+  // a memoised or just-finished callee row is consumed by the frame on top of the stack
+  void consume(uint32_t callee, uint32_t row, bool preimg) {
+    Frame& f = frames.back();
+    FuncTable& t = rec.funcs[callee];
+    const uint32_t* src = preimg ? &t.args[(size_t)row * t.in] : &t.outs[(size_t)row * t.out];
+    uint32_t n = preimg ? t.in : t.out;
+    std::vector<uint32_t> tmp(src, src + n);
+    vals.insert(vals.end(), tmp.begin(), tmp.end());
+    new_lookup(&t.provide[(size_t)row * 2], f.nonce, req_stack);
+    hint_stack.push_back(row);
+  }
+
+  void run(uint32_t entry, const uint32_t* args, uint32_t nargs, std::vector<uint32_t>& out) {
+    FuncTable& et = rec.funcs[entry];
+    if (nargs != et.in) fail(LSK_ERR_EXEC, "Argument mismatch");
+    long existing = et.index.find(et.args.data(), et.in, args);
+    uint32_t row;
+    if (existing >= 0) {
+      // IndexMap::insert_full overwrites the value of an existing key (execute.rs:446-447)
+      row = (uint32_t)existing;
+      et.done[row] = 0;
+      et.provide[(size_t)row * 2] = 0;
+      et.provide[(size_t)row * 2 + 1] = 1;
+    } else {
+      row = insert_query(entry, args, 1);
+    }
+    push_frame(entry, row, args, nargs, false);
+    while (!frames.empty()) step(out);
+    rec.public_values.assign(args, args + nargs);
+    rec.public_values.insert(rec.public_values.end(), out.begin(), out.end());
+  }
+
+  void step(std::vector<uint32_t>& final_out) {
+    Frame& f = frames.back();
+    uint32_t* m = vals.data() + f.map_base;
+    if (f.ops_left) {
+      const uint32_t* op = w + f.pc;
+      f.pc += op_words(op);
+      f.ops_left--;
+      switch (op[0]) {
+        case OP_CONST: vals.push_back(op[1]); break;
+        case OP_ADD: vals.push_back(hadd(m[op[1]], m[op[2]])); break;
+        case OP_SUB: vals.push_back(hsub(m[op[1]], m[op[2]])); break;
+        case OP_MUL: vals.push_back(hmul(m[op[1]], m[op[2]])); break;
+        case OP_INV:
+          if (!m[op[1]]) fail(LSK_ERR_EXEC, "inverse of zero");
+          vals.push_back(hinv(m[op[1]]));
+          break;
+        case OP_NOT: vals.push_back(m[op[1]] == 0 ? 1u : 0u); break;
+        case OP_ASSERT_EQ: {
+          uint32_t n = op[1];
+          for (uint32_t i = 0; i < n; i++)
+            if (m[op[2 + i]] != m[op[2 + n + i]]) fail(LSK_ERR_EXEC, "AssertEq failed");
+        } break;
+        case OP_ASSERT_NE: {
+          uint32_t n = op[1];
+          bool ne = false;
+          for (uint32_t i = 0; i < n; i++) ne |= m[op[2 + i]] != m[op[2 + n + i]];
+          if (!ne) fail(LSK_ERR_EXEC, "AssertNe failed");
+        } break;
+        case OP_CONTAINS: {
+          uint32_t n = op[1], b = m[op[2 + n]];
+          bool found = false;
+          for (uint32_t i = 0; i < n; i++) found |= m[op[2 + i]] == b;
+          if (!found) fail(LSK_ERR_EXEC, "Contains failed");
+        } break;
+        case OP_CALL: {
+          uint32_t callee = op[1], n = op[2];
+          FuncTable& t = rec.funcs[callee];
+          uint32_t inp[64];
+          if (n > 64) fail(LSK_ERR_EXEC, "call arity too large");
+          for (uint32_t i = 0; i < n; i++) inp[i] = m[op[3 + i]];
+          long row = t.index.find(t.args.data(), t.in, inp);
+          if (row >= 0) {
+            if (!t.done[row]) fail(LSK_ERR_EXEC, "Loop detected");
+            consume(callee, (uint32_t)row, false);
+          } else {
+            uint32_t r = insert_query(callee, inp, 0);
+            push_frame(callee, r, inp, n, false);
+          }
+        } break;
+        case OP_PREIMG: {
+          uint32_t callee = op[1], n = op[2];
+          FuncTable& t = rec.funcs[callee];
+          if (!t.invertible) fail(LSK_ERR_EXEC, "Missing inverse map");
+          uint32_t outv[64];
+          if (n > 64) fail(LSK_ERR_EXEC, "preimg arity too large");
+          for (uint32_t i = 0; i < n; i++) outv[i] = m[op[3 + i]];
+          long iv = t.inv_index.find(t.inv_outs.data(), t.out, outv);
+          if (iv < 0) fail(LSK_ERR_EXEC, "Preimg not found");
+          std::vector<uint32_t> inp(t.inv_inps.begin() + (size_t)iv * t.in, t.inv_inps.begin() + (size_t)(iv + 1) * t.in);
+          long row = t.index.find(t.args.data(), t.in, inp.data());
+          if (row >= 0) {
+            if (!t.done[row]) fail(LSK_ERR_EXEC, "Loop detected");
+            if (memcmp(&t.outs[(size_t)row * t.out], outv, t.out * 4)) fail(LSK_ERR_EXEC, "preimage output mismatch");
+            consume(callee, (uint32_t)row, true);
+          } else {
+            uint32_t r = insert_query(callee, inp.data(), 0);
+            push_frame(callee, r, inp.data(), t.in, true);
+          }
+        } break;
+        case OP_STORE: {
+          uint32_t n = op[1];
+          int mi = mem_index_from_len((int)n);
+          if (mi < 0) fail(LSK_ERR_EXEC, "There are no mem tables of size %u", n);
+          MemTable& mt = rec.mems[mi];
+          uint32_t v[8];
+          for (uint32_t i = 0; i < n; i++) v[i] = m[op[2 + i]];
+          long row = mt.index.find(mt.vals.data(), n, v);
+          if (row < 0) {
+            row = (long)mt.rows();
+            mt.vals.insert(mt.vals.end(), v, v + n);
+            mt.provide.push_back(0);
+            mt.provide.push_back(0);
+            mt.index.insert_new(mt.vals.data(), n, (uint32_t)row);
+          }
+          vals.push_back((uint32_t)row + 1);
+          new_lookup(&mt.provide[(size_t)row * 2], f.nonce, req_stack);
+          hint_stack.push_back((uint32_t)row);
+        } break;
+        case OP_LOAD: {
+          uint32_t len = op[1], ptr = m[op[2]];
+          int mi = mem_index_from_len((int)len);
+          if (mi < 0) fail(LSK_ERR_EXEC, "There are no mem tables of size %u", len);
+          MemTable& mt = rec.mems[mi];
+          if (ptr == 0 || ptr > mt.rows()) fail(LSK_ERR_EXEC, "Unbound pointer");
+          uint32_t v[8];
+          memcpy(v, &mt.vals[(size_t)(ptr - 1) * len], len * 4);
+          vals.insert(vals.end(), v, v + len);
+          new_lookup(&mt.provide[(size_t)(ptr - 1) * 2], f.nonce, req_stack);
+        } break;
+        case OP_EXTERN: {
+          const uint32_t* chip = prog.chip(op[1]);
+          int t = chip_width(chip[0]);
+          if (!t || op[2] != (uint32_t)t) fail(LSK_ERR_EXEC, "bad extern chip call");
+          uint32_t st[40];
+          for (int i = 0; i < t; i++) st[i] = m[op[3 + i]];
+          host_poseidon2(st, t);
+          vals.insert(vals.end(), st, st + 8);
+        } break;
+        case OP_RANGE_U8: {
+          uint32_t n = op[1];
+          if (rec.bytes.empty()) rec.bytes.assign((size_t)65536 * 12, 0);
+          rec.bytes_used = true;
+          for (uint32_t i = 0; i < n; i += 2) {
+            uint32_t i1 = m[op[2 + i]], i2 = i + 1 < n ? m[op[3 + i]] : 0;
+            if (i1 > 255 || i2 > 255) fail(LSK_ERR_EXEC, "Variable not in u8 range");
+            size_t key = i1 | (i2 << 8);
+            new_lookup(&rec.bytes[key * 12 + 0], f.nonce, req_stack);  // slot 0 = range_u8 pair
+          }
+        } break;
+        default: fail(LSK_ERR_EXEC, "bad opcode %u", op[0]);
+      }
+      return;
+    }
+    // control node
+    const uint32_t* c = w + f.pc;
+    if (c[0] == CTRL_RETURN) {
+      uint32_t n = c[2];
+      FuncTable& t = rec.funcs[f.func];
+      if (n != t.out) fail(LSK_ERR_EXEC, "return arity mismatch");
+      if (t.done[f.nonce]) fail(LSK_ERR_EXEC, "output already set");
+      uint32_t outv[64];
+      for (uint32_t i = 0; i < n; i++) outv[i] = m[c[3 + i]];
+      memcpy(&t.outs[(size_t)f.nonce * t.out], outv, n * 4);
+      t.done[f.nonce] = 1;
+      if (t.invertible) {  // execute.rs:690-692: inv_map.insert(out, inp) (later insert wins)
+        long iv = t.inv_index.find(t.inv_outs.data(), t.out, outv);
+        if (iv >= 0) {
+          memcpy(&t.inv_inps[(size_t)iv * t.in], &t.args[(size_t)f.nonce * t.in], t.in * 4);
+        } else {
+          uint32_t slot = (uint32_t)t.inv_index.used;
+          t.inv_outs.insert(t.inv_outs.end(), outv, outv + t.out);
+          t.inv_inps.insert(t.inv_inps.end(), t.args.begin() + (size_t)f.nonce * t.in,
+                            t.args.begin() + (size_t)(f.nonce + 1) * t.in);
+          t.inv_index.insert_new(t.inv_outs.data(), t.out, slot);
+        }
+      }
+      t.req_off[f.nonce] = (uint32_t)(t.reqs.size() / 2);
+      t.reqs.insert(t.reqs.end(), req_stack.begin() + f.req_base, req_stack.end());
+      t.hint_off[f.nonce] = (uint32_t)t.hints.size();
+      t.hints.insert(t.hints.end(), hint_stack.begin() + f.hint_base, hint_stack.end());
+      req_stack.resize(f.req_base);
+      hint_stack.resize(f.hint_base);
+      vals.resize(f.map_base);
+      Frame done = f;
+      frames.pop_back();
+      if (frames.empty()) {
+        final_out.assign(outv, outv + n);
+      } else {
+        consume(done.func, done.nonce, done.preimg);
+      }
+      return;
+    }
+    if (c[0] == CTRL_CHOOSE || c[0] == CTRL_CHOOSE_MANY) {
+      uint32_t nv = c[1];
+      const uint32_t* vars = c + 2;
+      uint32_t nb = c[2 + nv], has_d = c[3 + nv];
+      uint32_t p = f.pc + 4 + nv;
+      long chosen = -1;
+      for (uint32_t b = 0; b < nb; b++) {
+        uint32_t nk = w[p++];
+        bool hit = false;
+        if (c[0] == CTRL_CHOOSE) {
+          for (uint32_t k = 0; k < nk; k++) hit |= w[p + k] == m[vars[0]];
+          p += nk;
+        } else {
+          hit = true;
+          for (uint32_t k = 0; k < nv; k++) hit &= w[p + k] == m[vars[k]];
+          p += nv * nk;
+        }
+        if (hit && chosen < 0) chosen = p;
+        p += w[p];  // skip the block
+      }
+      if (chosen < 0 && has_d) chosen = p;
+      if (chosen < 0) fail(LSK_ERR_EXEC, "No match");
+      enter_block(f, (uint32_t)chosen);
+      return;
+    }
+    fail(LSK_ERR_EXEC, "bad control word %u", c[0]);
+  }
+};
+
+}  // namespace lsk
+
+using namespace lsk;
+
+extern "C" {
+
+int lsk_program_load(const uint32_t* words, size_t n, lsk_program** out) {
+  LSK_API_BEGIN
+  if (!words || n < 3 || words[0] != PROGRAM_MAGIC) fail(LSK_ERR_ARG, "bad program image");
+  auto* p = new lsk_program;
+  p->words.assign(words, words + n);
+  p->nfuncs = words[1];
+  p->nchips = words[2];
+  if (3 + (size_t)p->nchips * CHIP_WORDS + p->nfuncs > n) {
+    delete p;
+    fail(LSK_ERR_ARG, "truncated program image");
+  }
+  for (uint32_t f = 0; f < p->nfuncs; f++) {
+    if (p->func_offset(f) + FUNC_HEADER_WORDS + 2 > n) { delete p; fail(LSK_ERR_ARG, "bad func offset"); }
+    if (p->header(f).partial) { delete p; fail(LSK_ERR_ARG, "partial funcs (depth provenance) are not supported yet"); }
+  }
+  *out = p;
+  return LSK_OK;
+  LSK_API_END
+}
+void lsk_program_free(lsk_program* p) { delete p; }
+int lsk_program_num_funcs(const lsk_program* p) { return p ? (int)p->nfuncs : LSK_ERR_ARG; }
+int lsk_program_func_width(const lsk_program* p, uint32_t func) {
+  return p && func < p->nfuncs ? (int)p->width(func) : LSK_ERR_ARG;
+}
+
+int lsk_record_new(const lsk_program* p, lsk_record** out) {
+  LSK_API_BEGIN
+  if (!p || !out) fail(LSK_ERR_ARG, "null argument");
+  auto* r = new lsk_record;
+  r->funcs.resize(p->nfuncs);
+  for (uint32_t f = 0; f < p->nfuncs; f++) {
+    auto h = p->header(f);
+    r->funcs[f].in = h.in;
+    r->funcs[f].out = h.out;
+    r->funcs[f].invertible = h.invertible != 0;
+  }
+  for (int i = 0; i < NUM_MEM_TABLES; i++) r->mems[i].len = (uint32_t)mem_table_len(i);
+  *out = r;
+  return LSK_OK;
+  LSK_API_END
+}
+void lsk_record_free(lsk_record* r) { delete r; }
+
+int lsk_execute(const lsk_program* p, lsk_record* r, uint32_t func, const uint32_t* args, size_t nargs, uint32_t* out,
+                size_t nout) {
+  LSK_API_BEGIN
+  if (!p || !r || func >= p->nfuncs) fail(LSK_ERR_ARG, "bad argument");
+  for (size_t i = 0; i < nargs; i++)
+    if (args[i] >= Pq) fail(LSK_ERR_ARG, "argument not canonical");
+  Executor ex(*p, *r);
+  std::vector<uint32_t> o;
+  ex.run(func, args, (uint32_t)nargs, o);
+  if (o.size() != nout) fail(LSK_ERR_ARG, "output size mismatch");
+  for (size_t i = 0; i < nout; i++) out[i] = o[i];
+  return LSK_OK;
+  LSK_API_END
+}
+
+int lsk_inject_inv_queries(const lsk_program* p, lsk_record* r, uint32_t func, const uint32_t* inps,
+                           const uint32_t* outs, size_t n) {
+  LSK_API_BEGIN
+  if (!p || !r || func >= p->nfuncs) fail(LSK_ERR_ARG, "bad argument");
+  FuncTable& t = r->funcs[func];
+  if (!t.invertible) fail(LSK_ERR_ARG, "Inverse query map not found");
+  for (size_t i = 0; i < n; i++) {
+    const uint32_t* o = outs + i * t.out;
+    long iv = t.inv_index.find(t.inv_outs.data(), t.out, o);
+    if (iv >= 0) {
+      memcpy(&t.inv_inps[(size_t)iv * t.in], inps + i * t.in, t.in * 4);
+    } else {
+      uint32_t slot = (uint32_t)t.inv_index.used;
+      t.inv_outs.insert(t.inv_outs.end(), o, o + t.out);
+      t.inv_inps.insert(t.inv_inps.end(), inps + i * t.in, inps + (i + 1) * t.in);
+      t.inv_index.insert_new(t.inv_outs.data(), t.out, slot);
+    }
+  }
+  return LSK_OK;
+  LSK_API_END
+}
+
+size_t lsk_record_num_queries(const lsk_record* r, uint32_t func) { return func < r->funcs.size() ? r->funcs[func].rows() : 0; }
+size_t lsk_record_num_mem(const lsk_record* r, uint32_t mem_idx) { return mem_idx < NUM_MEM_TABLES ? r->mems[mem_idx].rows() : 0; }
+size_t lsk_record_public_values(const lsk_record* r, uint32_t* out, size_t cap) {
+  for (size_t i = 0; i < r->public_values.size() && i < cap; i++) out[i] = r->public_values[i];
+  return r->public_values.size();
+}
+uint32_t lsk_record_num_shards(const lsk_record* r, uint32_t shard_size) {
+  size_t mx = 0;
+  for (auto& t : r->funcs) mx = std::max(mx, t.rows());
+  if (!shard_size) return 0;
+  return (uint32_t)(mx / shard_size + (mx % shard_size ? 1 : 0));
+}
+size_t lsk_func_trace_height(const lsk_record* r, uint32_t func, uint32_t shard, uint32_t shard_size) {
+  size_t n = r->funcs[func].rows();
+  size_t s = (size_t)shard * shard_size, e = std::min<size_t>((size_t)(shard + 1) * shard_size, n);
+  size_t real = e > s ? e - s : 0, h = 1;
+  while (h < real) h <<= 1;
+  return h;
+}
+size_t lsk_mem_trace_height(const lsk_record* r, uint32_t mem_idx) {
+  size_t n = r->mems[mem_idx].rows(), h = 4;
+  while (h < n) h <<= 1;
+  return h;
+}
+size_t lsk_record_device_bytes(const lsk_record* r) {
+  size_t b = 0;
+  for (auto& t : r->funcs)
+    b += 4 * (t.args.size() + t.outs.size() + t.provide.size() + t.req_off.size() + t.reqs.size() + t.hint_off.size() +
+              t.hints.size());
+  for (auto& m : r->mems) b += 4 * (m.vals.size() + m.provide.size());
+  b += 4 * r->bytes.size();
+  return b;
+}
+
+}  // extern "C"

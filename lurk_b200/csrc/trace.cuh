@@ -1,0 +1,48 @@
+// A4/A5 device-side declarations: the uploaded (device-resident) flattened record and the trace
+// generation launchers shared by the boundary API (row-major canonical output) and the prover
+// pipeline (column-major, bit-reversed rows, Montgomery form).
+#pragma once
+#include <vector>
+
+#include "device.cuh"
+#include "record.h"
+
+namespace lsk {
+
+struct DevFuncTable {
+  const uint32_t *args, *outs, *provide, *req_off, *reqs, *hint_off, *hints;
+  uint32_t in, out, rows;
+};
+struct DevMemTable {
+  const uint32_t *vals, *provide;
+  uint32_t len, rows;
+};
+
+// Owns the device copies of a record's tables (uploaded once per prove call; this is the
+// host->device traffic of the end-to-end path).
+struct DeviceRecord {
+  std::vector<DevBuf<uint32_t>> bufs;
+  DevBuf<DevFuncTable> funcs;
+  DevBuf<DevMemTable> mems;
+  DevBuf<uint32_t> program;
+  DevBuf<uint32_t> bytes;  // [65536][12] or empty
+  std::vector<DevFuncTable> h_funcs;
+  std::vector<DevMemTable> h_mems;
+  size_t h2d_bytes = 0;
+  void upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_record& rec);
+};
+
+// Output layouts
+enum class TraceLayout { RowMajorCanonical, ColMajorBitrevMont };
+
+// d_out must be zero-filled by the callee: the launchers do it.
+void func_trace_dev(lsk_ctx* ctx, const lsk_program& prog, const DeviceRecord& drec, uint32_t func, uint32_t row_start,
+                    uint32_t real_rows, uint32_t height, TraceLayout layout, uint32_t* d_out);
+void mem_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, uint32_t mem_idx, uint32_t height, TraceLayout layout,
+                   uint32_t* d_out);
+void bytes_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, bool real, TraceLayout layout, uint32_t* d_out);
+void bytes_preprocessed_dev(lsk_ctx* ctx, TraceLayout layout, uint32_t* d_out);
+// single-row Entrypoint trace = public values (src/lair/lair_chip.rs:112-118)
+void init_trace_kernels();
+
+}  // namespace lsk

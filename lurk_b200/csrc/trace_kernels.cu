@@ -1,0 +1,388 @@
+// A4/A5: witness-trace generation on the GPU.
+//
+// Replaces FuncChip::generate_trace + Func::populate_row (src/lair/trace.rs:72-135,145-418),
+// MemChip::generate_trace (src/lair/memory.rs:30-68), BytesChip::generate_trace /
+// preprocessed_trace (src/gadgets/bytes/trace.rs:49-101).
+//
+// One thread per trace row interprets the func's flat bytecode (program.h).  Everything the
+// reference looks up through hash maps at this point (callee outputs, memory slots) arrives as
+// row indices in the flattened record, so the kernel only gathers.  Field inversions (AssertNe /
+// Inv / Not witnesses and the 1/(count+1) of every require triple) are done in-thread with a
+// 62-product Fermat chain.  Output is written either row-major canonical (C-ABI parity view) or
+// column-major with bit-reversed rows in Montgomery form (the layout the LDE/commit kernels eat:
+// thread i writes row brev(i) of every column, the inverse NTT then needs no reordering pass).
+// HBM-bound by design: 4*N*w bytes written + the record tables read once.
+#include "poseidon2.cuh"
+#include "trace.cuh"
+
+namespace lsk {
+
+struct StoreRowMajor {
+  uint32_t* out;
+  uint32_t width, row;
+  LSK_D void operator()(uint32_t col, uint32_t v_mont) const { out[(size_t)row * width + col] = from_mont(v_mont); }
+};
+struct StoreColBitrev {
+  uint32_t* out;
+  uint32_t height, brow;  // brow = bitrev(row)
+  LSK_D void operator()(uint32_t col, uint32_t v_mont) const { out[(size_t)col * height + brow] = v_mont; }
+};
+
+template <class Store>
+struct AuxWitness {  // sink for the wide Poseidon2 witness inside a func row
+  const Store& st;
+  uint32_t base;  // column of the first Poseidon2Cols entry
+  int t, rp;
+  LSK_D void ext_state(int r, int i, uint32_t v) { st(base + r * t + i, v); }
+  LSK_D void ext_sbox(int r, int i, uint32_t v) { st(base + 8 * t + r * t + i, v); }
+  LSK_D void int_init(int i, uint32_t v) { st(base + 16 * t + i, v); }
+  LSK_D void int_state0(int r, uint32_t v) { st(base + 17 * t + r, v); }
+  LSK_D void int_sbox(int r, uint32_t v) { st(base + 17 * t + (rp - 1) + r, v); }
+};
+
+template <int T, class Store>
+__device__ __noinline__ void extern_poseidon(const uint32_t* op, uint32_t* map, uint32_t& map_len, uint32_t& aux,
+                                              const Store& st) {
+  uint32_t s[T];
+#pragma unroll
+  for (int i = 0; i < T; i++) s[i] = map[op[3 + i]];
+  AuxWitness<Store> wit{st, aux + 8, T, P2Rounds<T>::RP};
+  p2_permute<T, AuxWitness<Store>>(s, wit);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    map[map_len++] = s[i];
+    st(aux + i, s[i]);
+  }
+  aux += 8 + 17 * T + 2 * P2Rounds<T>::RP - 1;
+}
+
+template <int MAP_CAP, class Store>
+__device__ void populate_row(const uint32_t* __restrict__ w, uint32_t body, FuncHeader hdr, const uint32_t* chips,
+                             const DevFuncTable* __restrict__ funcs, const DevMemTable* __restrict__ mems,
+                             const DevFuncTable& self, uint32_t q, const Store& st) {
+  uint32_t map[MAP_CAP];
+  uint32_t map_len = 0;
+  const uint32_t col_in = 1, col_out = 1 + hdr.in, col_aux = 1 + hdr.in + hdr.out;
+  const uint32_t col_sel = col_aux + hdr.aux;
+  for (uint32_t j = 0; j < hdr.in; j++) {
+    uint32_t v = to_mont(self.args[(size_t)q * hdr.in + j]);
+    map[map_len++] = v;
+    st(col_in + j, v);
+  }
+  for (uint32_t j = 0; j < hdr.out; j++) st(col_out + j, to_mont(self.outs[(size_t)q * hdr.out + j]));
+  uint32_t aux = col_aux;
+  st(aux++, to_mont(self.provide[(size_t)q * 2]));
+  st(aux++, to_mont(self.provide[(size_t)q * 2 + 1]));
+  const uint32_t* reqs = self.reqs + (size_t)self.req_off[q] * 2;
+  const uint32_t* hints = self.hints + self.hint_off[q];
+  auto push_require = [&]() {  // Record::into_require, src/air/builder.rs:159-168
+    uint32_t pn = reqs[0], pc = reqs[1];
+    reqs += 2;
+    st(aux++, to_mont(pn));
+    st(aux++, to_mont(pc));
+    st(aux++, finv(to_mont(pc + 1)));
+  };
+  uint32_t pc = body;
+  for (;;) {
+    uint32_t nops = w[pc + 1];
+    pc += 2;
+    for (uint32_t k = 0; k < nops; k++) {
+      const uint32_t* op = w + pc;
+      pc += op_words(op);
+      switch (op[0]) {
+        case OP_CONST: map[map_len++] = to_mont(op[1]); break;
+        case OP_ADD: map[map_len] = fadd(map[op[1]], map[op[2]]); map_len++; break;
+        case OP_SUB: map[map_len] = fsub(map[op[1]], map[op[2]]); map_len++; break;
+        case OP_MUL: {
+          uint32_t v = fmul(map[op[1]], map[op[2]]);
+          map[map_len++] = v;
+          if (op[3]) st(aux++, v);
+        } break;
+        case OP_INV: {
+          uint32_t v = finv(map[op[1]]);
+          map[map_len++] = v;
+          if (op[2]) st(aux++, v);
+        } break;
+        case OP_NOT: {
+          uint32_t a = map[op[1]];
+          uint32_t x = a == 0 ? R1 : 0u;
+          map[map_len++] = x;
+          if (op[2]) {
+            st(aux++, finv(a));  // finv(0) == 0
+            st(aux++, x);
+          }
+        } break;
+        case OP_ASSERT_EQ: break;
+        case OP_ASSERT_NE: {  // push_inequality_witness, trace.rs:218-233
+          uint32_t n = op[1];
+          bool found = false;
+          for (uint32_t i = 0; i < n; i++) {
+            uint32_t d = fsub(map[op[2 + i]], map[op[2 + n + i]]);
+            uint32_t c = 0;
+            if (!found && d != 0) {
+              c = finv(d);
+              found = true;
+            }
+            st(aux++, c);
+          }
+        } break;
+        case OP_CONTAINS: {
+          uint32_t n = op[1], b = map[op[2 + n]];
+          uint32_t acc = fsub(map[op[2]], b);
+          for (uint32_t i = 1; i < n; i++) {
+            acc = fmul(acc, fsub(map[op[2 + i]], b));
+            st(aux++, acc);
+          }
+        } break;
+        case OP_CALL: {
+          const DevFuncTable& callee = funcs[op[1]];
+          uint32_t row = *hints++;
+          for (uint32_t j = 0; j < callee.out; j++) {
+            uint32_t v = to_mont(callee.outs[(size_t)row * callee.out + j]);
+            map[map_len++] = v;
+            st(aux++, v);
+          }
+          push_require();
+        } break;
+        case OP_PREIMG: {
+          const DevFuncTable& callee = funcs[op[1]];
+          uint32_t row = *hints++;
+          for (uint32_t j = 0; j < callee.in; j++) {
+            uint32_t v = to_mont(callee.args[(size_t)row * callee.in + j]);
+            map[map_len++] = v;
+            st(aux++, v);
+          }
+          push_require();
+        } break;
+        case OP_STORE: {
+          uint32_t row = *hints++;
+          uint32_t v = to_mont(row + 1);
+          map[map_len++] = v;
+          st(aux++, v);
+          push_require();
+        } break;
+        case OP_LOAD: {
+          uint32_t len = op[1];
+          const DevMemTable& mt = mems[mem_index_from_len((int)len)];
+          uint32_t ptr = from_mont(map[op[2]]);
+          for (uint32_t j = 0; j < len; j++) {
+            uint32_t v = to_mont(mt.vals[(size_t)(ptr - 1) * len + j]);
+            map[map_len++] = v;
+            st(aux++, v);
+          }
+          push_require();
+        } break;
+        case OP_EXTERN: {
+          uint32_t kind = chips[op[1] * CHIP_WORDS];
+          if (kind == 1) extern_poseidon<24, Store>(op, map, map_len, aux, st);
+          else if (kind == 2) extern_poseidon<32, Store>(op, map, map_len, aux, st);
+          else if (kind == 3) extern_poseidon<40, Store>(op, map, map_len, aux, st);
+        } break;
+        case OP_RANGE_U8: {
+          uint32_t n = (op[1] + 1) / 2;
+          for (uint32_t i = 0; i < n; i++) push_require();
+        } break;
+        default: break;
+      }
+    }
+    const uint32_t* c = w + pc;
+    if (c[0] == CTRL_RETURN) {
+      st(col_sel + c[1], R1);
+      return;
+    }
+    // CHOOSE / CHOOSE_MANY
+    uint32_t nv = c[1];
+    const uint32_t* vars = c + 2;
+    uint32_t nb = c[2 + nv], has_d = c[3 + nv];
+    uint32_t p = pc + 4 + nv;
+    uint32_t chosen = 0;
+    for (uint32_t b = 0; b < nb; b++) {
+      uint32_t nk = w[p++];
+      bool hit = false;
+      if (c[0] == CTRL_CHOOSE) {
+        uint32_t v = from_mont(map[vars[0]]);
+        for (uint32_t k = 0; k < nk; k++) hit |= w[p + k] == v;
+        p += nk;
+      } else {
+        hit = true;
+        for (uint32_t k = 0; k < nv; k++) hit &= w[p + k] == from_mont(map[vars[k]]);
+        p += nv * nk;
+      }
+      if (hit && !chosen) chosen = p;
+      p += w[p];
+    }
+    if (!chosen && has_d) chosen = p;
+    if (!chosen) return;  // unreachable for records produced by the executor
+    pc = chosen;
+  }
+}
+
+template <int MAP_CAP, bool COLMAJOR>
+__global__ void __launch_bounds__(128) func_trace_kernel(const uint32_t* __restrict__ w, uint32_t body, FuncHeader hdr,
+                                                          const uint32_t* chips, uint32_t func,
+                                                          const DevFuncTable* __restrict__ funcs,
+                                                          const DevMemTable* __restrict__ mems, uint32_t row_start,
+                                                          uint32_t real_rows, uint32_t height, uint32_t log_h,
+                                                          uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= height) return;
+  uint32_t width = 1 + hdr.in + hdr.out + hdr.aux + hdr.sel;
+  const DevFuncTable self = funcs[func];
+  if (COLMAJOR) {
+    StoreColBitrev st{out, height, bitrev32(i, log_h)};
+    st(0, to_mont(row_start + i));  // nonces are unique even on padding rows (trace.rs:82-84)
+    if (i < real_rows) populate_row<MAP_CAP>(w, body, hdr, chips, funcs, mems, self, row_start + i, st);
+  } else {
+    StoreRowMajor st{out, width, i};
+    st(0, to_mont(row_start + i));
+    if (i < real_rows) populate_row<MAP_CAP>(w, body, hdr, chips, funcs, mems, self, row_start + i, st);
+  }
+}
+
+// MemChip: [is_real, ptr = i + 1, last_nonce, last_count, values...]
+template <bool COLMAJOR>
+__global__ void mem_trace_kernel(DevMemTable mt, uint32_t height, uint32_t log_h, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mt.rows) return;
+  uint32_t width = 4 + mt.len;
+  auto put = [&](uint32_t col, uint32_t canonical) {
+    if (COLMAJOR) out[(size_t)col * height + bitrev32(i, log_h)] = to_mont(canonical);
+    else out[(size_t)i * width + col] = canonical;
+  };
+  put(0, 1);
+  put(1, i + 1);
+  put(2, mt.provide[(size_t)i * 2]);
+  put(3, mt.provide[(size_t)i * 2 + 1]);
+  for (uint32_t j = 0; j < mt.len; j++) put(4 + j, mt.vals[(size_t)i * mt.len + j]);
+}
+
+// BytesChip main: [is_real, 6 x (last_nonce, last_count)] for the 2^16 byte pairs
+template <bool COLMAJOR>
+__global__ void bytes_trace_kernel(const uint32_t* __restrict__ rec, uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 65536) return;
+  auto put = [&](uint32_t col, uint32_t canonical) {
+    if (COLMAJOR) out[(size_t)col * 65536 + bitrev32(i, 16)] = to_mont(canonical);
+    else out[(size_t)i * 13 + col] = canonical;
+  };
+  put(0, 1);
+  for (int k = 0; k < 12; k++) put(1 + k, rec[(size_t)i * 12 + k]);
+}
+// BytesChip preprocessed: (b1, b2, b1 < b2, and, xor, or), index = b1 | b2 << 8
+template <bool COLMAJOR>
+__global__ void bytes_prep_kernel(uint32_t* __restrict__ out) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 65536) return;
+  uint32_t b1 = i & 255, b2 = i >> 8;
+  uint32_t v[6] = {b1, b2, b1 < b2 ? 1u : 0u, b1 & b2, b1 ^ b2, b1 | b2};
+  for (int k = 0; k < 6; k++) {
+    if (COLMAJOR) out[(size_t)k * 65536 + bitrev32(i, 16)] = to_mont(v[k]);
+    else out[(size_t)i * 6 + k] = v[k];
+  }
+}
+
+void init_trace_kernels() { LSK_CUDA(p2_upload_constants()); }
+
+void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_record& rec) {
+  bufs.clear();
+  h2d_bytes = 0;
+  auto up = [&](const std::vector<uint32_t>& v) -> const uint32_t* {
+    if (v.empty()) return nullptr;
+    bufs.emplace_back(ctx, v.size());
+    bufs.back().upload(v.data(), v.size());
+    h2d_bytes += v.size() * 4;
+    return bufs.back().p;
+  };
+  h_funcs.clear();
+  for (const FuncTable& t : rec.funcs) {
+    DevFuncTable d{};
+    d.args = up(t.args); d.outs = up(t.outs); d.provide = up(t.provide);
+    d.req_off = up(t.req_off); d.reqs = up(t.reqs); d.hint_off = up(t.hint_off); d.hints = up(t.hints);
+    d.in = t.in; d.out = t.out; d.rows = (uint32_t)t.rows();
+    h_funcs.push_back(d);
+  }
+  h_mems.clear();
+  for (const MemTable& m : rec.mems) {
+    DevMemTable d{};
+    d.vals = up(m.vals); d.provide = up(m.provide);
+    d.len = m.len; d.rows = (uint32_t)m.rows();
+    h_mems.push_back(d);
+  }
+  funcs.alloc(ctx, h_funcs.size());
+  if (!h_funcs.empty()) funcs.upload(h_funcs.data(), h_funcs.size());
+  mems.alloc(ctx, h_mems.size());
+  mems.upload(h_mems.data(), h_mems.size());
+  program.alloc(ctx, prog.words.size());
+  program.upload(prog.words.data(), prog.words.size());
+  if (rec.bytes_used) {
+    bytes.alloc(ctx, rec.bytes.size());
+    bytes.upload(rec.bytes.data(), rec.bytes.size());
+    h2d_bytes += rec.bytes.size() * 4;
+  } else {
+    bytes.release();
+  }
+}
+
+void func_trace_dev(lsk_ctx* ctx, const lsk_program& prog, const DeviceRecord& drec, uint32_t func, uint32_t row_start,
+                    uint32_t real_rows, uint32_t height, TraceLayout layout, uint32_t* d_out) {
+  FuncHeader hdr = prog.header(func);
+  uint32_t width = prog.width(func);
+  LSK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)height * width * 4, ctx->stream));
+  if (!height) return;
+  uint32_t log_h = log2_exact(height);
+  unsigned grid = div_up(height, 128);
+  const uint32_t* w = drec.program.p;
+  const uint32_t* chips = w + 3;
+  uint32_t body = prog.body(func);
+  bool col = layout == TraceLayout::ColMajorBitrevMont;
+#define LAUNCH(CAP)                                                                                                  \
+  do {                                                                                                               \
+    if (col)                                                                                                         \
+      func_trace_kernel<CAP, true><<<grid, 128, 0, ctx->stream>>>(w, body, hdr, chips, func, drec.funcs.p,          \
+                                                                  drec.mems.p, row_start, real_rows, height, log_h, \
+                                                                  d_out);                                            \
+    else                                                                                                             \
+      func_trace_kernel<CAP, false><<<grid, 128, 0, ctx->stream>>>(w, body, hdr, chips, func, drec.funcs.p,         \
+                                                                   drec.mems.p, row_start, real_rows, height, log_h, \
+                                                                   d_out);                                           \
+  } while (0)
+  if (hdr.max_map <= 32) LAUNCH(32);
+  else if (hdr.max_map <= 128) LAUNCH(128);
+  else if (hdr.max_map <= 512) LAUNCH(512);
+  else fail(LSK_ERR_ARG, "func %u needs a value stack of %u entries (> 512)", func, hdr.max_map);
+#undef LAUNCH
+  LSK_CUDA(cudaGetLastError());
+}
+
+void mem_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, uint32_t mem_idx, uint32_t height, TraceLayout layout,
+                   uint32_t* d_out) {
+  const DevMemTable& mt = drec.h_mems[mem_idx];
+  LSK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)height * (4 + mt.len) * 4, ctx->stream));
+  if (!mt.rows) return;
+  uint32_t log_h = log2_exact(height);
+  if (layout == TraceLayout::ColMajorBitrevMont)
+    mem_trace_kernel<true><<<div_up(mt.rows, 128), 128, 0, ctx->stream>>>(mt, height, log_h, d_out);
+  else
+    mem_trace_kernel<false><<<div_up(mt.rows, 128), 128, 0, ctx->stream>>>(mt, height, log_h, d_out);
+  LSK_CUDA(cudaGetLastError());
+}
+
+void bytes_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, bool real, TraceLayout layout, uint32_t* d_out) {
+  LSK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)65536 * 13 * 4, ctx->stream));
+  if (!real || !drec.bytes.p) return;
+  if (layout == TraceLayout::ColMajorBitrevMont)
+    bytes_trace_kernel<true><<<65536 / 256, 256, 0, ctx->stream>>>(drec.bytes.p, d_out);
+  else
+    bytes_trace_kernel<false><<<65536 / 256, 256, 0, ctx->stream>>>(drec.bytes.p, d_out);
+  LSK_CUDA(cudaGetLastError());
+}
+
+void bytes_preprocessed_dev(lsk_ctx* ctx, TraceLayout layout, uint32_t* d_out) {
+  if (layout == TraceLayout::ColMajorBitrevMont)
+    bytes_prep_kernel<true><<<65536 / 256, 256, 0, ctx->stream>>>(d_out);
+  else
+    bytes_prep_kernel<false><<<65536 / 256, 256, 0, ctx->stream>>>(d_out);
+  LSK_CUDA(cudaGetLastError());
+}
+
+}  // namespace lsk

@@ -1,0 +1,95 @@
+"""GPU parity: witness-trace generation through the C ABI vs the reference's golden matrices and
+vs the oracle on larger / multi-shard inputs."""
+import numpy as np
+import pytest
+
+import goldens
+from lurk_b200.execute import (BytesChip, MemChip, QueryRecord, Shard, ShardingConfig, execute_by_name)
+from lurk_b200.lair import FuncChip, demo_toplevel
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case", goldens.CASES, ids=[c[0] + ":" + c[1] for c in goldens.CASES])
+def test_golden_func_trace(case):
+    tname, fname, arg_list, golden = case
+    top = goldens.toplevel_for(tname)
+    q = QueryRecord.new(top)
+    for args in arg_list:
+        execute_by_name(top, fname, args, q)
+    trace = FuncChip.from_name(fname, top).generate_trace(Shard.new(q))
+    assert trace.shape == golden.shape
+    assert np.array_equal(trace, golden)
+
+
+def test_golden_mem_trace():
+    top = goldens.toplevel_for("memory")
+    q = QueryRecord.new(top)
+    execute_by_name(top, "test", [], q)
+    assert np.array_equal(MemChip(3).generate_trace(Shard.new(q)), goldens.MEMORY_MEM3)
+    t = MemChip(8).generate_trace(Shard.new(q))
+    assert t.shape == (4, 12) and not t.any()
+
+
+def _oracle_rec(oracle, top, fname, args):
+    ot = oracle.OracleToplevel(top.serialize())
+    rec = oracle.OracleRecord(ot)
+    f = top.func_by_name(fname)
+    rec.execute(f.index, list(args), f.output_size)
+    return rec
+
+
+def test_fib_2pow16_matches_oracle(oracle):
+    top = demo_toplevel()
+    n = (1 << 16) - 1
+    q = QueryRecord.new(top)
+    execute_by_name(top, "fib", [n], q)
+    trace = FuncChip.from_name("fib", top).generate_trace(Shard.new(q))
+    want = _oracle_rec(oracle, top, "fib", [n]).func_trace(1)
+    assert trace.shape == (1 << 16, 18)
+    assert np.array_equal(trace, want)
+
+
+def test_sharded_traces_match_oracle(oracle):
+    # reference tests multi-shard with tiny shard sizes (src/air/debug.rs:119-158); ragged last shard
+    top = goldens.toplevel_for("ackermann")
+    q = QueryRecord.new(top)
+    execute_by_name(top, "ackermann", [2, 7], q)
+    rec = _oracle_rec(oracle, top, "ackermann", [2, 7])
+    cfg = ShardingConfig(64)
+    shards = Shard.new(q).shard(cfg)
+    assert len(shards) == rec.num_shards(64) and len(shards) > 2
+    chip = FuncChip.from_name("ackermann", top)
+    for s in shards:
+        assert np.array_equal(chip.generate_trace(s), rec.func_trace(0, shard=s.index, shard_size=64))
+
+
+def test_bytes_traces_match_oracle(oracle):
+    top = goldens.toplevel_for("range")
+    q = QueryRecord.new(top)
+    execute_by_name(top, "range_test", [100, 12, 64], q)
+    rec = _oracle_rec(oracle, top, "range_test", [100, 12, 64])
+    chip = BytesChip()
+    assert np.array_equal(chip.generate_trace(Shard.new(q)), rec.bytes_trace(0))
+    assert not chip.generate_trace(Shard(q, 1)).any()
+    assert np.array_equal(chip.generate_preprocessed_trace(), oracle.bytes_preprocessed())
+
+
+def test_hash_chip_trace_matches_oracle(oracle):
+    # a func wrapping the hash4 extern chip: width 1 + 32 + 8 + (2 + 611) + 1 = 655 (eval_direct.rs:2053-2055)
+    from lurk_b200.lair import ChipInfo, Toplevel, extern_call, func, ret
+    chips = [ChipInfo("hasher4", 32, 8, 611, 0, kind=2)]
+    f = func("hash4", [("preimg", 32)], 8, [extern_call([("img", 8)], "hasher4", ["preimg"]), ret("img")])
+    top = Toplevel([f], chips)
+    chip = FuncChip.from_name("hash4", top)
+    assert chip.width() == 655
+    q = QueryRecord.new(top)
+    rng = np.random.default_rng(3)
+    ot = oracle.OracleToplevel(top.serialize())
+    rec = oracle.OracleRecord(ot)
+    for _ in range(5):
+        pre = rng.integers(0, 2013265921, size=32, dtype=np.uint32)
+        a = execute_by_name(top, "hash4", pre, q)
+        b = rec.execute(0, pre, 8)
+        assert np.array_equal(a, b)
+    assert np.array_equal(chip.generate_trace(Shard.new(q)), rec.func_trace(0))

@@ -1,0 +1,83 @@
+"""CPU-side tests of the native host logic: the C-ABI library loads and exports every declared
+symbol, and the flattening executor agrees with the oracle's restatement of execute.rs (no GPU
+compute is called here)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import goldens
+from lurk_b200 import _native as N
+from lurk_b200.execute import QueryRecord, Shard, ShardingConfig, execute_by_name
+from lurk_b200.lair import demo_toplevel
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    N.build()
+
+
+def test_library_exports_every_declared_symbol():
+    L = N.lib()
+    syms = N.declared_symbols()
+    assert len(syms) >= 25
+    missing = [s for s in syms if not hasattr(L, s)]
+    assert not missing, missing
+
+
+def test_ctx_create_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(N.LurkStarkError) as ei:
+        N.Context(0)
+    assert "no CPU fallback" in str(ei.value)
+
+
+@pytest.mark.parametrize("case", goldens.CASES, ids=[c[0] + ":" + c[1] for c in goldens.CASES])
+def test_executor_matches_oracle(oracle, case):
+    tname, fname, arg_list, golden = case
+    top = goldens.toplevel_for(tname)
+    f = top.func_by_name(fname)
+    q = QueryRecord.new(top)
+    ot = oracle.OracleToplevel(top.serialize())
+    orec = oracle.OracleRecord(ot)
+    for args in arg_list:
+        got = execute_by_name(top, fname, args, q)
+        want = orec.execute(f.index, list(args), f.output_size)
+        assert np.array_equal(got, want)
+    for fi in range(top.num_funcs()):
+        assert q.num_queries(fi) == orec.num_queries(fi)
+    for mi in range(6):
+        assert q.num_mem(mi) == orec.num_mem(mi)
+    assert np.array_equal(q.expect_public_values(), orec.public_values())
+    # outputs column of the golden equals what the executor memoised
+    assert q.num_queries(f.index) <= golden.shape[0]
+
+
+def test_executor_fib_100000():
+    # src/lair/execute.rs:826-834
+    top = demo_toplevel()
+    q = QueryRecord.new(top)
+    out = execute_by_name(top, "fib", [100000], q)
+    assert int(out[0]) == 1123328132
+    assert q.num_queries(1) == 100001
+    assert list(q.expect_public_values()) == [100000, 1123328132]
+
+
+def test_executor_errors_are_reported_not_thrown():
+    top = goldens.toplevel_for("assert")
+    q = QueryRecord.new(top)
+    with pytest.raises(N.LurkStarkError):
+        execute_by_name(top, "assert", [2, 4, 5, 8], q)   # assert_ne!(a, arr1) fails
+
+
+def test_sharding_policy():
+    # src/lair/execute.rs:106-111,186-216
+    top = demo_toplevel()
+    q = QueryRecord.new(top)
+    execute_by_name(top, "fib", [9], q)
+    shards = Shard.new(q).shard(ShardingConfig(4))
+    assert len(shards) == 3
+    assert [len(s.get_func_range(1)) for s in shards] == [4, 4, 2]
+    assert len(Shard.new(q).shard(ShardingConfig.default())) == 1

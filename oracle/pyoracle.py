@@ -173,3 +173,65 @@ def bytes_preprocessed():
     out = np.zeros((1 << 16, 6), dtype=np.uint32)
     lib().orc_bytes_preprocessed(_vp(out))
     return out
+
+
+# ---- STARK machine (oracle/stark.h, oracle/stark_prove.h) ---------------------------------------
+class OracleMachine:
+    """CPU restatement of sphinx's StarkMachine for a Lair chip vector (parity unpinned, see stark.h)."""
+
+    def __init__(self, top: OracleToplevel, entry_func: int, machine_blob, num_queries=100, pow_bits=16):
+        L = lib()
+        L.orc_machine_new.restype = ctypes.c_void_p
+        L.orc_stark_last_error.restype = ctypes.c_char_p
+        blob = _u32(machine_blob)
+        self.top = top
+        self.h = L.orc_machine_new(ctypes.c_void_p(top.h), entry_func, _vp(blob), ctypes.c_size_t(len(blob)),
+                                   num_queries, pow_bits)
+        if not self.h:
+            raise RuntimeError(L.orc_stark_last_error().decode())
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_machine_free(ctypes.c_void_p(self.h))
+
+    def prep_commit(self):
+        out = np.zeros(8, dtype=np.uint32)
+        lib().orc_machine_prep_commit(ctypes.c_void_p(self.h), _vp(out))
+        return out
+
+    def prove(self, rec: OracleRecord, shard_size=1 << 22) -> np.ndarray:
+        L = lib()
+        out = ctypes.POINTER(ctypes.c_uint32)()
+        n = ctypes.c_size_t()
+        rc = L.orc_prove(ctypes.c_void_p(self.h), ctypes.c_void_p(rec.h), shard_size, ctypes.byref(out), ctypes.byref(n))
+        if rc:
+            raise RuntimeError(L.orc_stark_last_error().decode())
+        arr = np.ctypeslib.as_array(out, shape=(n.value,)).copy()
+        L.orc_free(out)
+        return arr
+
+    def verify(self, proof) -> bool:
+        p = _u32(proof)
+        rc = lib().orc_verify(ctypes.c_void_p(self.h), _vp(p), ctypes.c_size_t(len(p)))
+        self.last_error = lib().orc_stark_last_error().decode() if rc else ""
+        return rc == 0
+
+
+def coset_lde(rows, in_shift=1):
+    r = _u32(rows)
+    out = np.zeros((2 * r.shape[0], r.shape[1]), dtype=np.uint32)
+    rc = lib().orc_coset_lde(_vp(r), ctypes.c_size_t(r.shape[0]), ctypes.c_size_t(r.shape[1]), in_shift, _vp(out))
+    assert rc == 0
+    return out
+
+
+def merkle_root(mats):
+    ms = [_u32(m) for m in mats]
+    n = len(ms)
+    ptrs = (ctypes.c_void_p * n)(*[m.ctypes.data for m in ms])
+    hs = (ctypes.c_size_t * n)(*[m.shape[0] for m in ms])
+    ws = (ctypes.c_size_t * n)(*[m.shape[1] for m in ms])
+    out = np.zeros(8, dtype=np.uint32)
+    rc = lib().orc_merkle_root(ptrs, hs, ws, ctypes.c_size_t(n), _vp(out))
+    assert rc == 0
+    return out

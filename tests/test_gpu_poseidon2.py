@@ -63,4 +63,4 @@ def test_large_batch_checksum(oracle):
     got = PoseidonChipset(32).hash(x)
     sel = np.arange(0, n, 4099)
     assert np.array_equal(got[sel], oracle.poseidon2_hash(32, x[sel]))
-    assert len(np.unique(got[:, 0])) > n - 16
+    assert len(np.unique(got.view([('', got.dtype)] * 8))) == n      # digests of distinct preimages are distinct

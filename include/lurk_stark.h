@@ -93,6 +93,43 @@ int lsk_mem_trace(lsk_ctx* ctx, const lsk_record* r, uint32_t mem_idx, uint32_t*
 int lsk_bytes_trace(lsk_ctx* ctx, const lsk_record* r, uint32_t shard, uint32_t* out_row_major /* 65536 x 13 */);
 int lsk_bytes_preprocessed(lsk_ctx* ctx, uint32_t* out_row_major /* 65536 x 6 */);
 
+/* ---- A7-A12: the STARK machine -------------------------------------------------------------------
+ * lsk_machine_new = new_machine (src/core/stark_machine.rs:20-30) + machine.setup (repl.rs:175-176):
+ * `blob` is the captured chip vector ('MACH' image, lurk_b200/air.py::serialize_machine; format in
+ * csrc/machine.h), i.e. what sphinx's Chip::new collects by running Air::eval symbolically
+ * (src/lair/lair_chip.rs:196-231).  Commits the byte table's preprocessed trace.  The machine
+ * borrows `ctx` and `prog`. */
+int lsk_machine_new(lsk_ctx* ctx, const lsk_program* prog, uint32_t entry_func, const uint32_t* blob, size_t n,
+                    uint32_t num_queries, uint32_t pow_bits, lsk_machine** out);
+void lsk_machine_free(lsk_machine* m);
+int lsk_machine_prep_commit(const lsk_machine* m, uint32_t out8[8]);
+/* machine.prove::<LocalProver<_,_>>(&pk, shard, &mut challenger, opts): src/core/cli/repl.rs:194-196,
+ * benches/fib.rs:154-158, tests/fib.rs:90-94.  `rec` is a HOST record; it is uploaded, sharded by
+ * `shard_size` rows (Shard::shard, src/lair/execute.rs:186-216) and proved; `*words` receives a
+ * malloc'd proof (canonical u32 words, layout in DESIGN.md), free with lsk_proof_free. */
+int lsk_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard_size, uint32_t** words, size_t* len);
+void lsk_proof_free(uint32_t* words);
+/* host<->device bytes moved by the last lsk_prove / lsk_shard_* sequence */
+size_t lsk_machine_last_h2d_bytes(const lsk_machine* m);
+size_t lsk_machine_last_d2h_bytes(const lsk_machine* m);
+/* Two-phase form for shard-per-GPU proving (one process per GPU): every rank commits its shards,
+ * the 8-word roots are all-gathered by the caller, then each rank proves its shards against the
+ * transcript that has observed all roots.  Concatenating {0x4c505246, nshards, shard proofs in
+ * order} gives exactly lsk_prove's output. */
+int lsk_shard_commit(lsk_machine* m, const lsk_record* rec, uint32_t shard, uint32_t shard_size, uint32_t root_out[8]);
+int lsk_shard_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard, const uint32_t* all_roots, uint32_t nshards,
+                    uint32_t** words, size_t* len);
+void lsk_release_record(lsk_machine* m);   /* drops the device copy of the record + uncommitted shards */
+
+/* ---- stage-level entry points (parity tests and roofline measurement) ---------------------------------
+ * Third-party p3 pieces behind machine.prove: Radix2DitParallel::coset_lde_batch + bit_reverse_rows
+ * and FieldMerkleTreeMmcs::commit.  `rows` is h x w row-major canonical over in_shift*H_h (natural
+ * rows), shift_kind 0: in_shift = 1, 1: in_shift = g, 2: in_shift = g*w_2h; `out` is 2h x w
+ * row-major canonical over g*H_2h, rows bit-reversed. */
+int lsk_coset_lde(lsk_ctx* ctx, const uint32_t* rows, size_t h, size_t w, int shift_kind, uint32_t* out);
+int lsk_merkle_root(lsk_ctx* ctx, const uint32_t* const* mats, const size_t* hs, const size_t* ws, size_t nmats,
+                    uint32_t out8[8]);
+
 #ifdef __cplusplus
 }
 #endif

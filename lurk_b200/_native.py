@@ -46,7 +46,8 @@ def lib():
         L.lsk_last_error.restype = ctypes.c_char_p
         L.lsk_ctx_stream.restype = ctypes.c_void_p
         for f in ("lsk_record_num_queries", "lsk_record_num_mem", "lsk_record_public_values",
-                  "lsk_func_trace_height", "lsk_mem_trace_height", "lsk_record_device_bytes"):
+                  "lsk_func_trace_height", "lsk_mem_trace_height", "lsk_record_device_bytes",
+                  "lsk_machine_last_h2d_bytes", "lsk_machine_last_d2h_bytes"):
             getattr(L, f).restype = ctypes.c_size_t
         L.lsk_record_num_shards.restype = ctypes.c_uint32
         _lib = L

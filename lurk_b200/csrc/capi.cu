@@ -3,6 +3,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "ntt.cuh"
 #include "trace.cuh"
 
 namespace lsk {
@@ -55,6 +56,7 @@ void lsk_ctx_destroy(lsk_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  ntt_ctx_destroy(ctx);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -18,6 +18,7 @@ struct lsk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
+  void* ntt_tables = nullptr;   // lsk::NttTables (ntt.cu): twiddle / coset-scale tables, built lazily per size
 };
 
 namespace lsk {

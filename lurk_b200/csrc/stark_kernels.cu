@@ -1,0 +1,449 @@
+// Device stages of the shard prover (see stark_kernels.cuh for the reference map).
+//
+// Roofline notes: the LogUp trace, quotient, opening and FRI-reduce kernels stream
+// column-major LDE cells once with fully coalesced row-parallel access (thread = row, so a warp
+// reads 128 contiguous bytes of each column) and are HBM-bound; the per-row scalar work (one
+// extension-field inversion, a few dozen modmuls) rides under the loads.
+#include <algorithm>
+#include <vector>
+
+#include "poseidon2.cuh"
+#include "stark_kernels.cuh"
+
+namespace lsk {
+
+// ---- shared device helpers ---------------------------------------------------------------------------
+struct Cells {  // local-row view of a chip's main + preprocessed matrices
+  const uint32_t* main; size_t mstride;
+  const uint32_t* prep; size_t pstride;
+  size_t r;
+  LSK_D uint32_t get(uint32_t is_prep, uint32_t col) const {
+    return is_prep ? prep[(size_t)col * pstride + r] : main[(size_t)col * mstride + r];
+  }
+};
+LSK_D uint32_t eval_affine(const uint32_t* __restrict__& s, const Cells& c) {
+  uint32_t n = s[0], acc = s[1];
+  s += 2;
+  for (uint32_t i = 0; i < n; i++, s += 3) acc = fadd(acc, fmul(c.get(s[0], s[1]), s[2]));
+  return acc;
+}
+// one interaction: rlc = alpha + kind + sum_v beta^(v+1) value_v ; m = +-multiplicity
+LSK_D void eval_interaction(const uint32_t* __restrict__& s, const Cells& c, const Ext& alpha,
+                            const Ext* __restrict__ beta_pows, Ext& rlc, uint32_t& m) {
+  uint32_t kind = s[0], sign = s[1], nv = s[2];
+  s += 3;
+  m = eval_affine(s, c);
+  if (sign) m = fneg(m);
+  rlc = eadd_base(alpha, kind);
+  for (uint32_t v = 0; v < nv; v++) {
+    uint32_t val = eval_affine(s, c);
+    rlc = eadd(rlc, emul_base(beta_pows[v], val));
+  }
+}
+LSK_D Ext load_ext_cols(const uint32_t* __restrict__ m, size_t stride, uint32_t first_col, size_t r) {
+  Ext e;
+#pragma unroll
+  for (int k = 0; k < 4; k++) e.c[k] = m[(size_t)(first_col + k) * stride + r];
+  return e;
+}
+
+// ---- LogUp permutation trace --------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) perm_rows_kernel(const uint32_t* __restrict__ inter, uint32_t nint,
+                                                         const uint32_t* __restrict__ main, size_t mstride,
+                                                         const uint32_t* __restrict__ prep, size_t pstride, unsigned logn,
+                                                         Ext alpha, const Ext* __restrict__ beta_pows,
+                                                         uint32_t* __restrict__ perm, size_t perm_stride,
+                                                         Ext* __restrict__ rowsum_nat) {
+  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >> logn) return;
+  Cells cells{main, mstride, prep, pstride, r};
+  const uint32_t* s = inter;
+  Ext rowsum = ext_zero();
+  for (uint32_t b = 0; 2 * b < nint; b++) {
+    Ext r0, v;
+    uint32_t m0;
+    eval_interaction(s, cells, alpha, beta_pows, r0, m0);
+    if (2 * b + 1 < nint) {
+      Ext r1;
+      uint32_t m1;
+      eval_interaction(s, cells, alpha, beta_pows, r1, m1);
+      Ext num = eadd(emul_base(r1, m0), emul_base(r0, m1));
+      v = (m0 | m1) ? emul(num, einv(emul(r0, r1))) : ext_zero();
+    } else {
+      v = m0 ? emul_base(einv(r0), m0) : ext_zero();
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) perm[(size_t)(4 * b + k) * perm_stride + r] = v.c[k];
+    rowsum = eadd(rowsum, v);
+  }
+  rowsum_nat[bitrev32((uint32_t)r, logn)] = rowsum;
+}
+
+// inclusive scan of extension elements, 1024 per block
+__global__ void __launch_bounds__(256) scan_block_kernel(Ext* __restrict__ data, size_t n, Ext* __restrict__ block_sums) {
+  __shared__ Ext warp_tot[8];
+  size_t base = (size_t)blockIdx.x * 1024 + threadIdx.x * 4;
+  Ext v[4];
+#pragma unroll
+  for (int k = 0; k < 4; k++) v[k] = base + k < n ? data[base + k] : ext_zero();
+#pragma unroll
+  for (int k = 1; k < 4; k++) v[k] = eadd(v[k], v[k - 1]);
+  Ext inc = v[3];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    Ext t;
+#pragma unroll
+    for (int k = 0; k < 4; k++) t.c[k] = __shfl_up_sync(0xffffffffu, inc.c[k], d);
+    if (lane >= d) inc = eadd(inc, t);
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  Ext off = esub(inc, v[3]);  // exclusive within the warp
+  for (unsigned w = 0; w < warp; w++) off = eadd(off, warp_tot[w]);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    if (base + k < n) data[base + k] = eadd(v[k], off);
+  if (threadIdx.x == 255 && block_sums) block_sums[blockIdx.x] = eadd(v[3], off);
+}
+__global__ void scan_add_kernel(Ext* __restrict__ data, size_t n, const Ext* __restrict__ block_sums) {
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x + 1024;  // block 0 needs no offset
+  if (i < n) data[i] = eadd(data[i], block_sums[i / 1024 - 1]);
+}
+static void scan_ext_dev(lsk_ctx* ctx, Ext* data, size_t n) {
+  size_t nb = (n + 1023) / 1024;
+  if (nb <= 1) {
+    scan_block_kernel<<<1, 256, 0, ctx->stream>>>(data, n, nullptr);
+    return;
+  }
+  DevBuf<Ext> sums(ctx, nb);
+  scan_block_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(data, n, sums.p);
+  scan_ext_dev(ctx, sums.p, nb);
+  scan_add_kernel<<<div_up(n - 1024, 256), 256, 0, ctx->stream>>>(data, n, sums.p);
+}
+__global__ void phi_scatter_kernel(const Ext* __restrict__ phi_nat, unsigned logn, uint32_t* __restrict__ perm,
+                                   size_t perm_stride, uint32_t first_col, Ext* __restrict__ cum_sum) {
+  size_t k = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (k >> logn) return;
+  Ext v = phi_nat[k];
+  size_t r = bitrev32((uint32_t)k, logn);
+#pragma unroll
+  for (int e = 0; e < 4; e++) perm[(size_t)(first_col + e) * perm_stride + r] = v.c[e];
+  if (k + 1 == ((size_t)1 << logn)) *cum_sum = v;
+}
+
+void perm_trace_dev(lsk_ctx* ctx, const ChipDev& chip, const uint32_t* main, size_t mstride, const uint32_t* prep,
+                    size_t pstride, unsigned logn, Ext chal_alpha, const Ext* beta_pows_dev, uint32_t* perm_out,
+                    size_t perm_stride, Ext* scratch, Ext* cum_sum_out) {
+  size_t n = (size_t)1 << logn;
+  perm_rows_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(chip.inter.p, chip.nint, main, mstride, prep, pstride, logn,
+                                                            chal_alpha, beta_pows_dev, perm_out, perm_stride, scratch);
+  scan_ext_dev(ctx, scratch, n);
+  phi_scatter_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(scratch, logn, perm_out, perm_stride, 4 * (chip.pw - 1),
+                                                              cum_sum_out);
+  LSK_CUDA(cudaGetLastError());
+}
+
+// ---- quotient -----------------------------------------------------------------------------------------
+struct QuotientConsts {
+  uint32_t g, w2n, wn_inv, zh[2], inv_zh[2];
+};
+template <int MAXREGS>
+__global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientConsts qc,
+                                                        const uint4* __restrict__ code, uint32_t ninstr,
+                                                        const uint32_t* __restrict__ consts,
+                                                        const uint32_t* __restrict__ inter, uint32_t nint, uint32_t pw) {
+  const unsigned l2 = a.logn + 1;
+  const size_t n2 = (size_t)1 << l2;
+  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= n2) return;
+  uint32_t i = bitrev32((uint32_t)r, l2);
+  size_t rn = bitrev32((uint32_t)((i + 2) & (n2 - 1)), l2);
+  uint32_t x = fmul(qc.g, fpow(qc.w2n, i));
+  uint32_t zh = qc.zh[i & 1];
+  uint32_t xm1 = fsub(x, R1), xml = fsub(x, qc.wn_inv);
+  uint32_t inv = finv(fmul(xm1, xml));
+  uint32_t sel[3] = {fmul(zh, fmul(inv, xml)), fmul(zh, fmul(inv, xm1)), xml};  // is_first, is_last, is_transition
+  uint32_t regs[MAXREGS];
+  regs[0] = 0;
+  auto operand = [&](uint32_t w) -> uint32_t {
+    uint32_t idx = w & 0x0fffffffu;
+    switch (w >> 28) {
+      case 0: return regs[idx];
+      case 1: return consts[idx];
+      case 2: return a.main[(size_t)idx * a.mstride + r];
+      case 3: return a.main[(size_t)idx * a.mstride + rn];
+      case 4: return a.prep[(size_t)idx * a.pstride + r];
+      case 5: return a.prep[(size_t)idx * a.pstride + rn];
+      case 6: return a.pv[idx];
+      default: return sel[idx];
+    }
+  };
+  Ext acc = ext_zero();
+  uint32_t ci = 0;
+  for (uint32_t pc = 0; pc < ninstr; pc++) {
+    uint4 ins = __ldg(code + pc);
+    switch (ins.x) {
+      case 1: regs[ins.y] = fadd(operand(ins.z), operand(ins.w)); break;
+      case 2: regs[ins.y] = fsub(operand(ins.z), operand(ins.w)); break;
+      case 3: regs[ins.y] = fmul(operand(ins.z), operand(ins.w)); break;
+      case 4: regs[ins.y] = fneg(operand(ins.z)); break;
+      default: acc = eadd(acc, emul_base(a.apow[a.n_total - 1 - (ci++)], operand(ins.z))); break;
+    }
+  }
+  // LogUp constraints (sphinx eval_permutation_constraints)
+  Cells cells{a.main, a.mstride, a.prep, a.pstride, r};
+  const uint32_t* s = inter;
+  Ext sum_local = ext_zero(), sum_next = ext_zero();
+  for (uint32_t b = 0; 2 * b < nint; b++) {
+    Ext r0, lhs, rhs;
+    uint32_t m0;
+    eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r0, m0);
+    Ext pl = load_ext_cols(a.perm, a.permstride, 4 * b, r);
+    if (2 * b + 1 < nint) {
+      Ext r1;
+      uint32_t m1;
+      eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r1, m1);
+      lhs = emul(emul(pl, r0), r1);
+      rhs = eadd(emul_base(r1, m0), emul_base(r0, m1));
+    } else {
+      lhs = emul(pl, r0);
+      rhs = ext_from_base(m0);
+    }
+    acc = eadd(acc, emul(a.apow[a.n_total - 1 - (ci++)], esub(lhs, rhs)));
+    sum_local = eadd(sum_local, pl);
+    sum_next = eadd(sum_next, load_ext_cols(a.perm, a.permstride, 4 * b, rn));
+  }
+  Ext phi_local = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), r);
+  Ext phi_next = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), rn);
+  acc = eadd(acc, emul(a.apow[a.n_total - 1 - (ci++)], emul_base(esub(esub(phi_next, phi_local), sum_next), sel[2])));
+  acc = eadd(acc, emul(a.apow[a.n_total - 1 - (ci++)], emul_base(esub(phi_local, sum_local), sel[0])));
+  acc = eadd(acc, emul(a.apow[a.n_total - 1 - (ci++)], emul_base(esub(phi_local, *a.cum_sum), sel[1])));
+  Ext q = emul_base(acc, qc.inv_zh[i & 1]);
+#pragma unroll
+  for (int k = 0; k < 4; k++) a.out[(size_t)k * a.ostride + r] = q.c[k];
+}
+
+void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a) {
+  QuotientConsts qc;
+  qc.g = to_mont(GEN);
+  qc.w2n = two_adic_generator(a.logn + 1);
+  qc.wn_inv = finv(two_adic_generator(a.logn));
+  uint32_t gn = fpow(qc.g, (uint64_t)1 << a.logn);
+  qc.zh[0] = fsub(gn, R1);
+  qc.zh[1] = fsub(fneg(gn), R1);
+  qc.inv_zh[0] = finv(qc.zh[0]);
+  qc.inv_zh[1] = finv(qc.zh[1]);
+  size_t n2 = (size_t)2 << a.logn;
+  unsigned grid = div_up(n2, 256);
+  const uint4* code = reinterpret_cast<const uint4*>(chip.code.p);
+#define QK(R)                                                                                                    \
+  quotient_kernel<R><<<grid, 256, 0, ctx->stream>>>(a, qc, code, chip.ninstr, chip.consts.p, chip.inter.p, chip.nint, \
+                                                    chip.pw)
+  if (chip.n_regs <= 8) QK(8);
+  else if (chip.n_regs <= 32) QK(32);
+  else if (chip.n_regs <= 128) QK(128);
+  else if (chip.n_regs <= 1024) QK(1024);
+  else fail(LSK_ERR_ARG, "constraint program needs %u registers (> 1024)", chip.n_regs);
+#undef QK
+  LSK_CUDA(cudaGetLastError());
+}
+
+// ---- openings -------------------------------------------------------------------------------------------
+__global__ void bary_weights_kernel(unsigned logn, uint32_t g, uint32_t wn, Ext z, Ext scale, Ext* __restrict__ wts) {
+  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >> logn) return;
+  uint32_t x = fmul(g, fpow(wn, bitrev32((uint32_t)r, logn)));
+  Ext d = einv(esub_base(z, x));   // z - x
+  wts[r] = emul(emul_base(d, x), scale);
+}
+void bary_weights_dev(lsk_ctx* ctx, unsigned logn, Ext z, Ext* wts) {
+  size_t n = (size_t)1 << logn;
+  uint32_t g = to_mont(GEN);
+  uint32_t gn = fpow(g, n);
+  // scale = (z^n - g^n) / (g^n * n)
+  Ext zn = epow(z, n);
+  Ext scale = emul_base(esub_base(zn, gn), finv(fmul(gn, to_mont((uint32_t)n))));
+  bary_weights_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(logn, g, two_adic_generator(logn), z, scale, wts);
+  LSK_CUDA(cudaGetLastError());
+}
+
+constexpr int OPEN_COLS = 8;
+__global__ void __launch_bounds__(256) open_partial_kernel(const uint32_t* __restrict__ m, size_t stride, uint32_t w,
+                                                            size_t n, const Ext* __restrict__ wts0,
+                                                            const Ext* __restrict__ wts1, Ext* __restrict__ partial,
+                                                            uint32_t nchunks) {
+  __shared__ uint32_t red[8][OPEN_COLS * 8];
+  const uint32_t c0 = blockIdx.y * OPEN_COLS;
+  const size_t row0 = (size_t)blockIdx.x * OPEN_ROWS;
+  Ext acc[OPEN_COLS][2];
+#pragma unroll
+  for (int c = 0; c < OPEN_COLS; c++) acc[c][0] = acc[c][1] = ext_zero();
+  for (unsigned k = 0; k < OPEN_ROWS / 256; k++) {
+    size_t r = row0 + k * 256 + threadIdx.x;
+    if (r >= n) break;
+    Ext w0 = wts0[r], w1 = wts1[r];
+#pragma unroll
+    for (int c = 0; c < OPEN_COLS; c++) {
+      if (c0 + c < w) {
+        uint32_t v = m[(size_t)(c0 + c) * stride + r];
+        acc[c][0] = eadd(acc[c][0], emul_base(w0, v));
+        acc[c][1] = eadd(acc[c][1], emul_base(w1, v));
+      }
+    }
+  }
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < OPEN_COLS; c++)
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        uint32_t v = acc[c][p].c[e];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
+        if (lane == 0) red[warp][(c * 2 + p) * 4 + e] = v;
+      }
+  __syncthreads();
+  if (threadIdx.x < OPEN_COLS * 8) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) v = fadd(v, red[wv][threadIdx.x]);
+    uint32_t cp = threadIdx.x / 4, e = threadIdx.x % 4;  // cp = c * 2 + p
+    uint32_t c = c0 + cp / 2;
+    if (c < w) partial[((size_t)(c * 2 + (cp & 1)) * nchunks + blockIdx.x)].c[e] = v;
+  }
+}
+__global__ void __launch_bounds__(128) open_reduce_kernel(const Ext* __restrict__ partial, uint32_t nchunks,
+                                                           Ext* __restrict__ out) {
+  __shared__ Ext red[4];
+  const Ext* p = partial + (size_t)blockIdx.x * nchunks;
+  Ext acc = ext_zero();
+  for (uint32_t k = threadIdx.x; k < nchunks; k += 128) acc = eadd(acc, p[k]);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    uint32_t v = acc.c[e];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
+    acc.c[e] = v;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) out[blockIdx.x] = eadd(eadd(red[0], red[1]), eadd(red[2], red[3]));
+}
+void open_columns_dev(lsk_ctx* ctx, const uint32_t* m, size_t stride, uint32_t w, unsigned logn, const Ext* wts0,
+                      const Ext* wts1, Ext* partial, Ext* out) {
+  if (!w) return;
+  size_t n = (size_t)1 << logn;
+  uint32_t nchunks = div_up(n, OPEN_ROWS);
+  open_partial_kernel<<<dim3(nchunks, div_up(w, OPEN_COLS)), 256, 0, ctx->stream>>>(m, stride, w, n, wts0, wts1, partial,
+                                                                                    nchunks);
+  open_reduce_kernel<<<w * 2, 128, 0, ctx->stream>>>(partial, nchunks, out);
+  LSK_CUDA(cudaGetLastError());
+}
+
+// ---- FRI: reduced openings, fold, grind --------------------------------------------------------------------
+__global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* __restrict__ mats, uint32_t nmats,
+                                                               unsigned lh, uint32_t g, uint32_t w, Ext z0, Ext z1,
+                                                               const Ext* __restrict__ apow, Ext* __restrict__ ro) {
+  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >> lh) return;
+  uint32_t x = fmul(g, fpow(w, bitrev32((uint32_t)r, lh)));
+  Ext acc0 = ext_zero(), acc1 = ext_zero();
+  bool any1 = false;
+  for (uint32_t mi = 0; mi < nmats; mi++) {
+    const ReduceMat& m = mats[mi];
+    Ext s = ext_zero();
+    const uint32_t* p = m.p + r;
+    for (uint32_t c = 0; c < m.w; c++) s = eadd(s, emul_base(apow[c], p[(size_t)c * m.stride]));
+    acc0 = eadd(acc0, emul(m.off[0], esub(m.y[0], s)));
+    if (m.npoints > 1) {
+      acc1 = eadd(acc1, emul(m.off[1], esub(m.y[1], s)));
+      any1 = true;
+    }
+  }
+  Ext out = emul(acc0, einv(esub_base(z0, x)));
+  if (any1) out = eadd(out, emul(acc1, einv(esub_base(z1, x))));
+  ro[r] = out;
+}
+void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats, unsigned lh, Ext zeta,
+                         const Ext* alpha_pows_dev, Ext* ro) {
+  size_t n = (size_t)1 << lh;
+  Ext z1 = emul_base(zeta, two_adic_generator(lh - 1));
+  reduce_openings_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
+                                                                  two_adic_generator(lh), zeta, z1, alpha_pows_dev, ro);
+  LSK_CUDA(cudaGetLastError());
+}
+
+__global__ void __launch_bounds__(256) fri_fold_kernel(const Ext* __restrict__ cur, unsigned logh, uint32_t ginv,
+                                                        uint32_t one_half, Ext half_beta, const Ext* __restrict__ add,
+                                                        Ext* __restrict__ out) {
+  size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >> logh) return;
+  Ext a = cur[2 * i], b = cur[2 * i + 1];
+  Ext t = emul_base(half_beta, fpow(ginv, bitrev32((uint32_t)i, logh)));
+  // (1/2 + t) a + (1/2 - t) b = (a + b)/2 + t (a - b)
+  Ext v = eadd(emul_base(eadd(a, b), one_half), emul(t, esub(a, b)));
+  if (add) v = eadd(v, add[i]);
+  out[i] = v;
+}
+void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, Ext beta, const Ext* add, Ext* out) {
+  size_t half = (size_t)1 << logh;
+  uint32_t one_half = finv(to_mont(2));
+  fri_fold_kernel<<<div_up(half, 256), 256, 0, ctx->stream>>>(cur, logh, finv(two_adic_generator(logh + 1)), one_half,
+                                                              emul_base(beta, one_half), add, out);
+  LSK_CUDA(cudaGetLastError());
+}
+
+struct GrindState {
+  uint32_t s[16];  // Montgomery, pending inputs already written; slot `pos` takes the witness
+  uint32_t pos, mask;
+};
+__global__ void __launch_bounds__(128) grind_kernel(GrindState gs, uint32_t base, uint32_t* __restrict__ best) {
+  uint32_t w = base + blockIdx.x * 128 + threadIdx.x;
+  if (w >= P) return;
+  uint32_t s[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) s[i] = gs.s[i];
+  uint32_t wm = to_mont(w);
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    if ((uint32_t)i == gs.pos) s[i] = wm;
+  p2_permute<16>(s);
+  if ((from_mont(s[7]) & gs.mask) == 0) atomicMin(best, w);
+}
+uint32_t grind_dev(lsk_ctx* ctx, const uint32_t state[16], const uint32_t* pending, unsigned n_pending, unsigned bits) {
+  if (n_pending >= 8 || bits > 30) fail(LSK_ERR_ARG, "bad grind arguments");
+  GrindState gs;
+  for (int i = 0; i < 16; i++) gs.s[i] = to_mont(state[i]);
+  for (unsigned i = 0; i < n_pending; i++) gs.s[i] = to_mont(pending[i]);
+  gs.pos = n_pending;
+  gs.mask = (1u << bits) - 1;
+  DevBuf<uint32_t> best(ctx, 1);
+  const uint32_t batch = 1u << 20;
+  for (uint64_t base = 0; base < P; base += batch) {
+    uint32_t h = 0xffffffffu;
+    best.upload(&h, 1);
+    grind_kernel<<<batch / 128, 128, 0, ctx->stream>>>(gs, (uint32_t)base, best.p);
+    LSK_CUDA(cudaGetLastError());
+    best.download(&h, 1);
+    LSK_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h != 0xffffffffu) return h;
+  }
+  fail(LSK_ERR_EXEC, "proof-of-work grinding found no witness");
+}
+
+// ---- query gathers -------------------------------------------------------------------------------------------
+__global__ void gather_kernel(const GatherJob* __restrict__ jobs, uint32_t* __restrict__ out) {
+  const GatherJob j = jobs[blockIdx.x];
+  for (uint32_t k = threadIdx.x; k < j.count; k += 32) out[j.dst + k] = from_mont(j.p[j.first + (size_t)k * j.stride]);
+}
+void gather_dev(lsk_ctx* ctx, const GatherJob* jobs_dev, uint32_t njobs, uint32_t* out) {
+  if (!njobs) return;
+  gather_kernel<<<njobs, 32, 0, ctx->stream>>>(jobs_dev, out);
+  LSK_CUDA(cudaGetLastError());
+}
+
+void init_stark_kernels() { LSK_CUDA(p2_upload_constants()); }
+
+}  // namespace lsk

@@ -1,0 +1,80 @@
+// Device stages of the shard prover other than LDE and Merkle: LogUp permutation trace (A8),
+// quotient evaluation (A6 + A10), openings (A11), FRI reduce / fold / grind / query gathers (A12).
+// Everything here replaces third-party sphinx-core / p3-fri code reached from `machine.prove`
+// (src/core/cli/repl.rs:196, benches/fib.rs:158); the oracle restates it in oracle/stark_prove.h.
+// All matrices are column-major, Montgomery form, rows in bit-reversed order.
+#pragma once
+#include "device.cuh"
+#include "field.cuh"
+
+namespace lsk {
+
+struct ChipDev {  // a chip's compiled AIR, device resident (built once per machine)
+  DevBuf<uint32_t> code;    // constraint program, 4 words per instruction
+  DevBuf<uint32_t> consts;  // Montgomery
+  DevBuf<uint32_t> inter;   // interaction stream: {kind_mont sign nvalues affine(mult) affine(value)*}*, sends first
+  uint32_t ninstr = 0, nint = 0, n_regs = 0, width = 0, prep_width = 0, pw = 0, n_constraints = 0;
+};
+
+void init_stark_kernels();
+
+// ---- LogUp -----------------------------------------------------------------------------------------
+// main/prep: N rows (natural domain H_N, bit-reversed order).  perm_out: 4*pw columns of N rows.
+// cum_sum_out: one Ext (device).  scratch: N Ext.
+void perm_trace_dev(lsk_ctx* ctx, const ChipDev& chip, const uint32_t* main, size_t mstride, const uint32_t* prep,
+                    size_t pstride, unsigned logn, Ext chal_alpha, const Ext* beta_pows_dev, uint32_t* perm_out,
+                    size_t perm_stride, Ext* scratch, Ext* cum_sum_out);
+
+// ---- quotient --------------------------------------------------------------------------------------
+struct QuotientArgs {
+  const uint32_t* main; size_t mstride;   // LDEs, 2N rows
+  const uint32_t* prep; size_t pstride;
+  const uint32_t* perm; size_t permstride;
+  const uint32_t* pv;       // public values, Montgomery, device
+  const Ext* apow;          // apow[k] = alpha^k; constraint i (AIR first, then LogUp) is weighted alpha^(n_total-1-i)
+  uint32_t n_total;
+  const Ext* beta_pows;     // beta^(v+1)
+  const Ext* cum_sum;
+  Ext chal_alpha;
+  unsigned logn;
+  uint32_t* out; size_t ostride;  // 4 columns of 2N rows
+};
+void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a);
+
+// ---- openings --------------------------------------------------------------------------------------
+// wts[r] = barycentric weight of row r (< N) of the coset g*H_N (bit-reversed) for the point z
+void bary_weights_dev(lsk_ctx* ctx, unsigned logn, Ext z, Ext* wts);
+// out[c * 2 + p] = sum_r wts_p[r] * m[c][r] for c < w, p < 2 (wts1 may alias wts0 when only one
+// point is needed).  partial: scratch of w * 2 * ceil(N / OPEN_ROWS) Ext.
+constexpr unsigned OPEN_ROWS = 2048;
+void open_columns_dev(lsk_ctx* ctx, const uint32_t* m, size_t stride, uint32_t w, unsigned logn, const Ext* wts0,
+                      const Ext* wts1, Ext* partial, Ext* out);
+
+// ---- FRI ---------------------------------------------------------------------------------------------
+struct ReduceMat {  // one opened matrix of LDE height 2^lh
+  const uint32_t* p;
+  uint64_t stride;
+  uint32_t w, npoints;
+  Ext y[2];    // sum_c alpha^c * opened_value_p[c]
+  Ext off[2];  // alpha offset of (matrix, point)
+};
+// ro[r] = sum over mats, points of off * (y - sum_c alpha^c m[r][c]) / (z_p - x_r), x_r = g * w_{2^lh}^bitrev(r),
+// z_0 = zeta, z_1 = zeta * w_{2^(lh-1)}
+void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats, unsigned lh, Ext zeta,
+                         const Ext* alpha_pows_dev, Ext* ro);
+// out[i] = (1/2 + t) cur[2i] + (1/2 - t) cur[2i+1] (+ add[i]),  t = beta / (2 * w_{2^(logh+1)}^bitrev(i))
+void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, Ext beta, const Ext* add, Ext* out);
+// smallest witness w such that the duplex challenger, after observing w, samples `bits` zero bits.
+// state: 16 canonical words; pending: the challenger's input buffer (n_pending < 8 canonical words)
+uint32_t grind_dev(lsk_ctx* ctx, const uint32_t state[16], const uint32_t* pending, unsigned n_pending, unsigned bits);
+
+// ---- query gathers -----------------------------------------------------------------------------------
+struct GatherJob {  // copies `count` canonical words to out[dst ..]
+  const uint32_t* p;
+  uint64_t stride;  // words between consecutive items (matrix: column stride; digests / ext: 1)
+  uint64_t first;   // word offset of the first item
+  uint32_t count, dst;
+};
+void gather_dev(lsk_ctx* ctx, const GatherJob* jobs_dev, uint32_t njobs, uint32_t* out);
+
+}  // namespace lsk

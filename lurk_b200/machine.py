@@ -1,0 +1,172 @@
+"""Host-side mirror of the reference's STARK machine interface for the proving hot path.
+
+  new_machine(toplevel)                    src/core/stark_machine.rs:20-30
+  machine.setup(&LairMachineProgram)       src/core/cli/repl.rs:175-176, benches/fib.rs:142
+  machine.prove::<LocalProver>(&pk, shard, &mut challenger, opts)
+                                           src/core/cli/repl.rs:194-196, benches/fib.rs:154-158,
+                                           src/lair/lair_chip.rs:258-275, tests/fib.rs:90-94
+  MachineProof / ShardProof                src/core/cli/proofs.rs:5-10,61-76
+
+Same names and argument meaning; the prover behind `prove` is liblurkstark (CUDA, no CPU
+fallback).  A proof is the canonical-u32 word image documented in DESIGN.md.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from . import _native as N
+from .air import ChipDesc, build_chip_vector, serialize_machine
+from .execute import DEFAULT_SHARD_SIZE, Shard, ShardingConfig, program_of
+from .lair import DEPTH_W, Func, FuncChip, Toplevel
+
+PROOF_MAGIC = 0x4C505246
+
+
+@dataclass
+class SphinxCoreOpts:
+    """FRI parameters the reference takes from SphinxCoreOpts::default() / the FRI_QUERIES env."""
+    num_queries: int = 100
+    proof_of_work_bits: int = 16
+
+    @classmethod
+    def default(cls) -> "SphinxCoreOpts":
+        return cls()
+
+
+@dataclass
+class MachineProof:
+    """MachineProof<BabyBearPoseidon2> as a flat word image: MAGIC, nshards, ShardProof*."""
+    words: np.ndarray
+
+    def num_shards(self) -> int:
+        return int(self.words[1])
+
+    def to_bytes(self) -> bytes:
+        return self.words.astype("<u4").tobytes()
+
+
+@dataclass
+class ProvingKey:
+    commit: np.ndarray     # preprocessed commitment (byte table)
+
+
+@dataclass
+class VerifyingKey:
+    commit: np.ndarray
+    pc_start: int = 0      # LairMachineProgram::pc_start, src/lair/lair_chip.rs:71-77
+
+
+class LairMachineProgram:
+    pass
+
+
+class StarkMachine:
+    """sphinx_core::stark::StarkMachine<BabyBearPoseidon2, LairChip> for one Toplevel + entry func."""
+
+    def __init__(self, chips: List[ChipDesc], num_pv: int, toplevel: Toplevel, entry: Func,
+                 ctx: Optional[N.Context] = None, opts: Optional[SphinxCoreOpts] = None):
+        self._chips = chips
+        self.num_pv = num_pv
+        self.toplevel = toplevel
+        self.entry = entry
+        self.ctx = ctx or N.default_context()
+        self.opts = opts or SphinxCoreOpts.default()
+        self.program = program_of(toplevel)
+        self.blob = serialize_machine(chips, num_pv)
+        self.h = ctypes.c_void_p()
+        N.check(N.lib().lsk_machine_new(self.ctx.h, self.program.h, entry.index, N.vp(self.blob),
+                                        ctypes.c_size_t(len(self.blob)), self.opts.num_queries,
+                                        self.opts.proof_of_work_bits, ctypes.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                N.lib().lsk_machine_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def chips(self) -> List[ChipDesc]:
+        return self._chips
+
+    def setup(self, program: Optional[LairMachineProgram] = None):
+        c = np.zeros(8, dtype=np.uint32)
+        N.check(N.lib().lsk_machine_prep_commit(self.h, N.vp(c)))
+        return ProvingKey(c), VerifyingKey(c.copy())
+
+    # -- whole proof on this GPU ---------------------------------------------------------------
+    def prove(self, pk: ProvingKey, shard: Shard, challenger=None, opts=None) -> MachineProof:
+        """`shard` is Shard::new(&record): the whole record; it is cut into shards of
+        shard.shard_config.max_shard_size rows (reference default 2^22, env SHARD_SIZE)."""
+        out = ctypes.POINTER(ctypes.c_uint32)()
+        n = ctypes.c_size_t()
+        N.check(N.lib().lsk_prove(self.h, shard.queries.h, shard.shard_config.max_shard_size, ctypes.byref(out),
+                                  ctypes.byref(n)))
+        words = np.ctypeslib.as_array(out, shape=(n.value,)).copy()
+        N.lib().lsk_proof_free(out)
+        return MachineProof(words)
+
+    def last_transfer_bytes(self):
+        return N.lib().lsk_machine_last_h2d_bytes(self.h), N.lib().lsk_machine_last_d2h_bytes(self.h)
+
+    # -- shard-per-GPU form (one process per GPU; see parallel.py) ---------------------------------
+    def commit_shard(self, shard: Shard) -> np.ndarray:
+        root = np.zeros(8, dtype=np.uint32)
+        N.check(N.lib().lsk_shard_commit(self.h, shard.queries.h, shard.index, shard.shard_config.max_shard_size,
+                                         N.vp(root)))
+        return root
+
+    def prove_shard(self, shard: Shard, all_roots: np.ndarray) -> np.ndarray:
+        roots = N.u32(all_roots).reshape(-1, 8)
+        out = ctypes.POINTER(ctypes.c_uint32)()
+        n = ctypes.c_size_t()
+        N.check(N.lib().lsk_shard_prove(self.h, shard.queries.h, shard.index, N.vp(roots), len(roots),
+                                        ctypes.byref(out), ctypes.byref(n)))
+        words = np.ctypeslib.as_array(out, shape=(n.value,)).copy()
+        N.lib().lsk_proof_free(out)
+        return words
+
+    def release_record(self):
+        N.lib().lsk_release_record(self.h)
+
+
+def new_machine(toplevel: Toplevel, entry: Optional[str] = None, ctx: Optional[N.Context] = None,
+                opts: Optional[SphinxCoreOpts] = None) -> StarkMachine:
+    """new_machine (src/core/stark_machine.rs:20-30): chip vector of `entry` (reference: lurk_main;
+    here any func of the toplevel, e.g. "fib" of demo_toplevel as in src/lair/lair_chip.rs:246-276)."""
+    if entry is None:
+        entry = "lurk_main"
+    chip = FuncChip.from_name(entry, toplevel)
+    f = chip.func
+    num_pv = f.input_size + f.output_size + (DEPTH_W if f.partial else 0)
+    return StarkMachine(build_chip_vector(chip), num_pv, toplevel, f, ctx, opts)
+
+
+def assemble_proof(shard_words: List[np.ndarray]) -> MachineProof:
+    head = np.asarray([PROOF_MAGIC, len(shard_words)], dtype=np.uint32)
+    return MachineProof(np.concatenate([head] + [N.u32(w) for w in shard_words]))
+
+
+def smoke_prove():
+    """One small prove on cuda:0 checked bit-for-bit against the CPU oracle (used by smoke())."""
+    from oracle import pyoracle
+    from .execute import QueryRecord, execute_by_name
+    from .lair import demo_toplevel
+    top = demo_toplevel()
+    opts = SphinxCoreOpts(num_queries=8, proof_of_work_bits=8)
+    m = new_machine(top, "fib", opts=opts)
+    pk, _ = m.setup()
+    q = QueryRecord.new(top)
+    execute_by_name(top, "fib", [300], q)
+    proof = m.prove(pk, Shard.new(q))
+    ot = pyoracle.OracleToplevel(top.serialize())
+    om = pyoracle.OracleMachine(ot, m.entry.index, m.blob, opts.num_queries, opts.proof_of_work_bits)
+    rec = pyoracle.OracleRecord(ot)
+    rec.execute(m.entry.index, [300], 1)
+    want = om.prove(rec)
+    assert np.array_equal(proof.words, want), "GPU proof != oracle proof"
+    assert om.verify(proof.words), om.last_error

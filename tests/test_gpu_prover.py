@@ -1,0 +1,159 @@
+"""GPU parity for the prover stages and for whole proofs: every test calls the CUDA library through
+its C ABI and compares, bit for bit, with the CPU oracle (oracle/stark.h, oracle/stark_prove.h).
+The oracle's verifier must also accept every GPU proof and reject a tampered one."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import goldens
+from lurk_b200 import _native as N
+from lurk_b200.execute import QueryRecord, Shard, ShardingConfig, execute_by_name
+from lurk_b200.lair import demo_toplevel
+from lurk_b200.machine import SphinxCoreOpts, assemble_proof, new_machine
+
+pytestmark = pytest.mark.gpu
+P = 2013265921
+
+
+def two_adic_generator(bits):
+    return pow(0x1A427A41, 1 << (27 - bits), P)
+
+
+def gpu_coset_lde(rows, kind):
+    rows = N.u32(rows)
+    h, w = rows.shape
+    out = np.zeros((2 * h, w), dtype=np.uint32)
+    N.check(N.lib().lsk_coset_lde(N.default_context().h, N.vp(rows), ctypes.c_size_t(h), ctypes.c_size_t(w), kind,
+                                  N.vp(out)))
+    return out
+
+
+def gpu_merkle_root(mats):
+    ms = [N.u32(m) for m in mats]
+    n = len(ms)
+    ptrs = (ctypes.c_void_p * n)(*[m.ctypes.data for m in ms])
+    hs = (ctypes.c_size_t * n)(*[m.shape[0] for m in ms])
+    ws = (ctypes.c_size_t * n)(*[m.shape[1] for m in ms])
+    out = np.zeros(8, dtype=np.uint32)
+    N.check(N.lib().lsk_merkle_root(N.default_context().h, ptrs, hs, ws, ctypes.c_size_t(n), N.vp(out)))
+    return out
+
+
+@pytest.mark.parametrize("logh,w", [(0, 3), (1, 1), (2, 6), (5, 18), (10, 7), (12, 5), (13, 3), (14, 18), (17, 4),
+                                    (21, 2)])
+def test_coset_lde_matches_oracle(oracle, logh, w):
+    rng = np.random.default_rng(logh * 100 + w)
+    rows = rng.integers(0, P, size=(1 << logh, w), dtype=np.uint32)
+    assert np.array_equal(gpu_coset_lde(rows, 0), oracle.coset_lde(rows, 1))
+
+
+@pytest.mark.parametrize("logh", [0, 3, 12, 14])
+def test_quotient_chunk_lde_matches_oracle(oracle, logh):
+    rng = np.random.default_rng(7 + logh)
+    rows = rng.integers(0, P, size=(1 << logh, 4), dtype=np.uint32)
+    assert np.array_equal(gpu_coset_lde(rows, 1), oracle.coset_lde(rows, 31))
+    shift = 31 * two_adic_generator(logh + 1) % P
+    assert np.array_equal(gpu_coset_lde(rows, 2), oracle.coset_lde(rows, shift))
+
+
+def test_lde_is_linear_and_extends_constants():
+    # size-independent properties at a size the oracle is too slow for
+    rng = np.random.default_rng(1)
+    h, w = 1 << 20, 3
+    a = rng.integers(0, P, size=(h, w), dtype=np.uint32)
+    b = rng.integers(0, P, size=(h, w), dtype=np.uint32)
+    s = ((a.astype(np.uint64) + b) % P).astype(np.uint32)
+    la, lb, ls = gpu_coset_lde(a, 0), gpu_coset_lde(b, 0), gpu_coset_lde(s, 0)
+    assert np.array_equal(((la.astype(np.uint64) + lb) % P).astype(np.uint32), ls)
+    c = np.full((h, 1), 12345, dtype=np.uint32)
+    assert (gpu_coset_lde(c, 0) == 12345).all()
+
+
+@pytest.mark.parametrize("shapes", [
+    [(1, 3)], [(2, 8)], [(8, 5), (8, 9)], [(64, 18), (8, 3), (64, 2), (1, 7)], [(4096, 16), (2048, 1), (2, 40)],
+    [(1 << 15, 8), (1 << 15, 13), (1 << 11, 655), (4, 6)],
+])
+def test_merkle_root_matches_oracle(oracle, shapes):
+    rng = np.random.default_rng(len(shapes))
+    mats = [rng.integers(0, P, size=s, dtype=np.uint32) for s in shapes]
+    assert np.array_equal(gpu_merkle_root(mats), oracle.merkle_root(mats))
+
+
+def _prove_both(oracle, top, entry, arg_list, shard_size=1 << 22, nq=6, pow_bits=6):
+    opts = SphinxCoreOpts(num_queries=nq, proof_of_work_bits=pow_bits)
+    m = new_machine(top, entry, opts=opts)
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    ot = oracle.OracleToplevel(top.serialize())
+    om = oracle.OracleMachine(ot, m.entry.index, m.blob, nq, pow_bits)
+    rec = oracle.OracleRecord(ot)
+    for args in arg_list:
+        execute_by_name(top, entry, args, q)
+        rec.execute(m.entry.index, list(args), m.entry.output_size)
+    assert np.array_equal(pk.commit, om.prep_commit())
+    proof = m.prove(pk, Shard(q, 0, ShardingConfig(shard_size)))
+    want = om.prove(rec, shard_size)
+    return m, om, q, proof, want
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 100, 5000])
+def test_fib_proof_is_bit_exact(oracle, n):
+    # src/lair/lair_chip.rs:246-276 / benches/fib.rs shape on the demo toplevel's fib
+    m, om, q, proof, want = _prove_both(oracle, demo_toplevel(), "fib", [[n]])
+    assert len(proof.words) == len(want)
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+    bad = proof.words.copy()
+    bad[40] = (int(bad[40]) + 1) % P
+    assert not om.verify(bad)
+
+
+def test_factorial_proof_default_parameters(oracle):
+    # lair_chip.rs:246-276 (factorial), sphinx default FRI parameters: 100 queries, 16 PoW bits
+    m, om, q, proof, want = _prove_both(oracle, demo_toplevel(), "factorial", [[5]], nq=100, pow_bits=16)
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+
+
+@pytest.mark.parametrize("tname,fname,args", [
+    ("range", "range_test", [100, 12, 64]),     # byte lookups -> non-trivial Bytes chip
+    ("memory", "test", []),                      # store / load -> Mem chips
+    ("match_many", "match_many", [1, 0]),
+    ("assert", "assert", [2, 4, 6, 8]),
+    ("not_eq", "eq", [4, 2]),
+])
+def test_reference_test_programs_prove_bit_exact(oracle, tname, fname, args):
+    top = goldens.toplevel_for(tname)
+    m, om, q, proof, want = _prove_both(oracle, top, fname, [args])
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+
+
+def test_multi_shard_proof_is_bit_exact(oracle):
+    # the reference tests sharding with tiny shard sizes (src/air/debug.rs:119-158); ragged last shard
+    top = goldens.toplevel_for("ackermann")
+    m, om, q, proof, want = _prove_both(oracle, top, "ackermann", [[2, 30]], shard_size=64)
+    assert proof.num_shards() == 3
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+    # two-phase (shard-per-GPU) API gives the same bytes
+    shards = Shard(q, 0, ShardingConfig(64)).shard(ShardingConfig(64))
+    roots = np.stack([m.commit_shard(s) for s in shards])
+    parts = [m.prove_shard(s, roots) for s in shards]
+    m.release_record()
+    assert np.array_equal(assemble_proof(parts).words, want)
+
+
+def test_large_fib_proof_verifies(oracle):
+    # 2^16 rows: too slow to re-prove on the CPU inside the test budget -> acceptance by the oracle verifier
+    top = demo_toplevel()
+    opts = SphinxCoreOpts(num_queries=20, proof_of_work_bits=12)
+    m = new_machine(top, "fib", opts=opts)
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    execute_by_name(top, "fib", [(1 << 16) - 1], q)
+    proof = m.prove(pk, Shard.new(q))
+    ot = oracle.OracleToplevel(top.serialize())
+    om = oracle.OracleMachine(ot, m.entry.index, m.blob, 20, 12)
+    assert om.verify(proof.words), om.last_error

@@ -54,8 +54,8 @@ def test_sharded_traces_match_oracle(oracle):
     # reference tests multi-shard with tiny shard sizes (src/air/debug.rs:119-158); ragged last shard
     top = goldens.toplevel_for("ackermann")
     q = QueryRecord.new(top)
-    execute_by_name(top, "ackermann", [2, 7], q)
-    rec = _oracle_rec(oracle, top, "ackermann", [2, 7])
+    execute_by_name(top, "ackermann", [2, 30], q)
+    rec = _oracle_rec(oracle, top, "ackermann", [2, 30])
     cfg = ShardingConfig(64)
     shards = Shard.new(q).shard(cfg)
     assert len(shards) == rec.num_shards(64) and len(shards) > 2

@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- Lurk-fib prove throughput (trace rows / s) on B200, next to the CPU prover.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--log-rows L] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): Lair `fib` of the reference's demo toplevel
+(src/lair/mod.rs:65-83) with n = G * 2^L - 1, i.e. exactly 2^L trace rows per shard and one shard
+per GPU (weak scaling); 12 chips (Entrypoint, 4 funcs of which fib is non-empty, 6 memory tables,
+byte table); sphinx default FRI parameters (100 queries, 16 proof-of-work bits).  A step is one
+complete prove of the record: trace generation, 3 commitments, quotient, openings, FRI, queries.
+
+  value  rows/s with the flattened record already resident in HBM (lsk_shard_commit + lsk_shard_prove)
+  e2e    rows/s through lsk_prove with the record in HOST memory (upload + proof download inside)
+  roofline      the kernel family with the largest share of the step, from CUDA events recorded by
+                the library around every launch during the timed steps
+  cpu_baseline  the CPU oracle prover (restated reference; the Rust reference cannot be built
+                offline) on this box's host cores
+
+`--impl reference` times that CPU prover alone (rank 0 only under torchrun).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "lurk_fib_prove_trace_rows_per_sec"
+UNIT = "rows/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def workload_name(log_rows, world):
+    return (f"Lair fib(n={world}*2^{log_rows}-1) of demo_toplevel: 2^{log_rows} trace rows x 18 cols per shard, "
+            f"{world} shard(s), 12 chips, FRI 100 queries / 16 PoW bits")
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU prover (oracle) -- cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+class CpuProver:
+    def __init__(self):
+        from oracle import pyoracle
+        from lurk_b200.air import build_chip_vector, serialize_machine
+        from lurk_b200.lair import FuncChip, demo_toplevel
+        pyoracle.build()
+        self.o = pyoracle
+        top = demo_toplevel()
+        fc = FuncChip.from_name("fib", top)
+        self.func = fc.func.index
+        blob = serialize_machine(build_chip_vector(fc), 2)
+        self.ot = pyoracle.OracleToplevel(top.serialize())
+        self.m = pyoracle.OracleMachine(self.ot, self.func, blob, 100, 16)
+        self.cores = os.cpu_count() or 1
+
+    def record(self, log_rows):
+        rec = self.o.OracleRecord(self.ot)
+        rec.execute(self.func, [(1 << log_rows) - 1], 1)
+        return rec
+
+    def time_prove(self, rec, log_rows):
+        t = time.perf_counter()
+        self.m.prove(rec, 1 << log_rows)
+        return time.perf_counter() - t
+
+
+def cpu_baseline(log_rows, budget_s=25.0):
+    """Oracle prover on a bounded sample: the largest 2^l <= 2^log_rows rows whose prove fits the budget."""
+    cp = CpuProver()
+    t14 = cp.time_prove(cp.record(14), 14)
+    t16 = cp.time_prove(cp.record(16), 16)
+    per_row = max((t16 - t14) / (3 << 14), 1e-7)
+    fixed = max(t14 - per_row * (1 << 14), 0.0)
+    l = 16
+    while l < log_rows and fixed + per_row * (1 << (l + 1)) <= budget_s:
+        l += 1
+    t = cp.time_prove(cp.record(l), l) if l > 16 else t16
+    return {"value": (1 << l) / t, "unit": UNIT, "cores": cp.cores, "kind": "port",
+            "sample": f"oracle CPU prover (C++, std::thread x{cp.cores}), one prove of fib at 2^{l} rows, {t:.2f} s"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = args.gpus
+    cp = CpuProver()
+    steps, warmup = args.steps, args.warmup
+    t14 = cp.time_prove(cp.record(14), 14)
+    t16 = cp.time_prove(cp.record(16), 16)
+    per_row = max((t16 - t14) / (3 << 14), 1e-7)
+    fixed = max(t14 - per_row * (1 << 14), 0.0)
+    budget = 150.0 / max(1, steps + warmup)
+    l = 14
+    while l < args.log_rows and fixed + per_row * (1 << (l + 1)) <= budget:
+        l += 1
+    rec = cp.record(l)
+    for _ in range(warmup):
+        cp.time_prove(rec, l)
+    times = [cp.time_prove(rec, l) for _ in range(steps)]
+    total = sum(times)
+    value = steps * (1 << l) / total
+    sample = f"oracle CPU prover (C++, std::thread x{cp.cores}), each step one prove of fib at 2^{l} rows"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload_name(args.log_rows, world), "log_rows": args.log_rows,
+                   "sample_log_rows": l},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cp.cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "restated CPU baseline (oracle port), not the Rust reference binary: cargo and the un-vendored "
+                "sphinx/Plonky3 git dependencies are unavailable offline (SURVEY.md F1/F3)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from lurk_b200 import _native as N
+    from lurk_b200.execute import QueryRecord, Shard, ShardingConfig, execute_by_name
+    from lurk_b200.lair import demo_toplevel
+    from lurk_b200.machine import assemble_proof, new_machine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: liblurkstark has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    ctx = N.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+
+    L = args.log_rows
+    top = demo_toplevel()
+    m = new_machine(top, "fib", ctx=ctx)
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    t0 = time.perf_counter()
+    out = execute_by_name(top, "fib", [world * (1 << L) - 1], q)
+    t_exec = time.perf_counter() - t0
+    cfg = ShardingConfig(1 << L)
+    shards = Shard(q, 0, cfg).shard(cfg)
+    assert len(shards) == world, (len(shards), world)
+    mine = shards[rank]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_roots(root):
+        if world == 1:
+            return root.reshape(1, 8)
+        t = torch.from_numpy(root.astype(np.int64)).to(dev)
+        outs = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(outs, t)
+        return torch.stack(outs).cpu().numpy().astype(np.uint32)
+
+    def step_resident():
+        root = m.commit_shard(mine)
+        return m.prove_shard(mine, gather_roots(root))
+
+    def step_e2e():
+        if world == 1:
+            return m.prove(pk, mine).words
+        m.release_record()             # force the host -> device upload of the record
+        part = step_resident()
+        # the proof of the job is the concatenation of the shard proofs: collect them on rank 0
+        n = torch.tensor([len(part)], device=dev)
+        sizes = [torch.empty_like(n) for _ in range(world)]
+        dist.all_gather(sizes, n)
+        mx = int(max(int(s) for s in sizes))
+        buf = torch.zeros(mx, dtype=torch.int64, device=dev)
+        buf[:len(part)] = torch.from_numpy(part.astype(np.int64)).to(dev)
+        outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
+        dist.gather(buf, outs, dst=0)
+        if rank == 0:
+            return assemble_proof([o[:int(s)].cpu().numpy().astype(np.uint32) for o, s in zip(outs, sizes)]).words
+        return part
+
+    def timed(step, steps, profile):
+        total_ms = 0.0
+        launches = 0
+        prof_acc = {}
+        for _ in range(steps):
+            flush.fill_(1)             # evict L2 between iterations (256 MiB write, outside the timed pair)
+            barrier()
+            if profile:
+                ctx.profile_enable(True)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step()
+            b.record(stream)
+            barrier()
+            ms = torch.tensor([a.elapsed_time(b)], device=dev)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            total_ms += float(ms)
+            if profile:
+                for k, v in ctx.profile_read().items():
+                    acc = prof_acc.setdefault(k, {"ms": 0.0, "bytes": 0.0, "launches": 0})
+                    for f in acc:
+                        acc[f] += v[f]
+                ctx.profile_enable(False)
+        return total_ms, prof_acc
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    proof = step_e2e()
+    barrier()
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    res_ms, prof = timed(step_resident, args.steps, True)
+    e2e_ms, _ = timed(step_e2e, args.steps, False)
+    clk = clocks.stop()
+    h2d, d2h = m.last_transfer_bytes()
+
+    rows = world * (1 << L)
+    value = rows * args.steps / (res_ms / 1e3)
+    e2e_value = rows * args.steps / (e2e_ms / 1e3)
+
+    if rank == 0:
+        peak, peak_kind = measured_peaks()
+        kernels = {}
+        top_k, top_ms = None, -1.0
+        for k, v in prof.items():
+            gbs = v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else 0.0
+            kernels[k] = {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] // args.steps,
+                          "algorithmic_GBps": gbs}
+            if v["ms"] > top_ms:
+                top_k, top_ms = k, v["ms"]
+        tv = prof[top_k]
+        achieved = tv["bytes"] / (tv["ms"] * 1e6)
+        gpu_ms = sum(v["ms"] for v in prof.values())
+        roofline = {"kernel": top_k, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                    "bytes_per_launch": tv["bytes"] / max(1, tv["launches"]),
+                    "ms_per_launch": tv["ms"] / max(1, tv["launches"]),
+                    "share_of_step_gpu_time": tv["ms"] / gpu_ms if gpu_ms else None}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": res_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": {"workload": workload_name(L, world), "log_rows": L, "shards": world,
+                       "rows_per_step": rows, "l2": "flushed between timed steps (256 MiB write)",
+                       "executor_s": round(t_exec, 3), "fib_mod_p": int(out[0]), "proof_words": int(len(proof))},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(sum(v["launches"] for v in prof.values())),
+            "clocks": clk,
+            "roofline": roofline,
+            "kernels": kernels,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(L)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--log-rows", type=int, default=20, help="log2 trace rows per shard (= per GPU)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

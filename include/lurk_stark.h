@@ -43,6 +43,15 @@ void lsk_ctx_destroy(lsk_ctx* ctx);
 void* lsk_ctx_stream(lsk_ctx* ctx);
 int lsk_ctx_sync(lsk_ctx* ctx);
 
+/* Per-kernel accounting (new; the reference has no profiler).  Launch and
+ * algorithmic-byte counters are always on; lsk_profile_enable(ctx, 1) additionally brackets every
+ * kernel family with CUDA events on the context's stream.  lsk_profile_enable resets the counters;
+ * lsk_profile_read synchronises, fills up to `cap` entries per array (index = tag, name from
+ * lsk_profile_tag_name) and returns the number of tags. */
+int lsk_profile_enable(lsk_ctx* ctx, int on);
+int lsk_profile_read(lsk_ctx* ctx, double* ms, double* bytes, uint64_t* launches, int cap);
+const char* lsk_profile_tag_name(int tag);
+
 /* ---- A1: Poseidon2 hashing of content-addressed data ------------------------------------------
  * replaces PoseidonChipset::hash / execute_simple, src/core/poseidon.rs:29-39,61-63 as called from
  * ZStore::hash3/4/5, src/core/zstore.rs:305-333.  width in {24, 32, 40} (also 16: the commitment

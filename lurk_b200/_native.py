@@ -50,6 +50,7 @@ def lib():
                   "lsk_machine_last_h2d_bytes", "lsk_machine_last_d2h_bytes"):
             getattr(L, f).restype = ctypes.c_size_t
         L.lsk_record_num_shards.restype = ctypes.c_uint32
+        L.lsk_profile_tag_name.restype = ctypes.c_char_p
         _lib = L
     return _lib
 
@@ -92,6 +93,22 @@ class Context:
 
     def sync(self):
         check(lib().lsk_ctx_sync(self.h))
+
+    def profile_enable(self, on: bool = True):
+        """Reset the per-kernel counters; with on=True also time every kernel family with CUDA events."""
+        check(lib().lsk_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self) -> dict:
+        """{kernel family: {"ms", "bytes" (algorithmic), "launches"}} since the last profile_enable."""
+        cap = 64
+        ms = (ctypes.c_double * cap)()
+        by = (ctypes.c_double * cap)()
+        ln = (ctypes.c_uint64 * cap)()
+        n = lib().lsk_profile_read(self.h, ms, by, ln, cap)
+        if n < 0:
+            check(n)
+        return {lib().lsk_profile_tag_name(i).decode(): {"ms": ms[i], "bytes": by[i], "launches": int(ln[i])}
+                for i in range(n) if ln[i]}
 
 
 _default_ctx = None

@@ -57,6 +57,8 @@ void lsk_ctx_destroy(lsk_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   ntt_ctx_destroy(ctx);
+  for (auto& r : ctx->prof.recs) cudaEventDestroy(r.a), cudaEventDestroy(r.b);
+  for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -68,6 +70,40 @@ int lsk_ctx_sync(lsk_ctx* ctx) {
   return LSK_OK;
   LSK_API_END
 }
+
+int lsk_profile_enable(lsk_ctx* ctx, int on) {
+  LSK_API_BEGIN
+  if (!ctx) fail(LSK_ERR_ARG, "null ctx");
+  LSK_CUDA(cudaStreamSynchronize(ctx->stream));
+  Profiler& p = ctx->prof;
+  for (auto& r : p.recs) p.pool.push_back(r.a), p.pool.push_back(r.b);
+  p.recs.clear();
+  for (int i = 0; i < PT_COUNT; i++) p.launches[i] = 0, p.bytes[i] = 0, p.ms[i] = 0;
+  p.timing = on != 0;
+  return LSK_OK;
+  LSK_API_END
+}
+int lsk_profile_read(lsk_ctx* ctx, double* ms, double* bytes, uint64_t* launches, int cap) {
+  LSK_API_BEGIN
+  if (!ctx) fail(LSK_ERR_ARG, "null ctx");
+  LSK_CUDA(cudaStreamSynchronize(ctx->stream));
+  Profiler& p = ctx->prof;
+  for (auto& r : p.recs) {
+    float t = 0;
+    LSK_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    p.ms[r.tag] += t;
+    p.pool.push_back(r.a), p.pool.push_back(r.b);
+  }
+  p.recs.clear();
+  for (int i = 0; i < PT_COUNT && i < cap; i++) {
+    if (ms) ms[i] = p.ms[i];
+    if (bytes) bytes[i] = p.bytes[i];
+    if (launches) launches[i] = p.launches[i];
+  }
+  return PT_COUNT;
+  LSK_API_END
+}
+const char* lsk_profile_tag_name(int tag) { return tag >= 0 && tag < PT_COUNT ? PROF_NAMES[tag] : ""; }
 
 static void check_width(int width, bool allow16) {
   if (!(width == 24 || width == 32 || width == 40 || (allow16 && width == 16)))

@@ -14,12 +14,74 @@
     if (_e != cudaSuccess) lsk::fail(LSK_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
   } while (0)
 
+#include <vector>
+
+namespace lsk {
+// Per-kernel accounting: every launcher opens a ProfScope naming the kernel family, the number of
+// kernels it launches and the ALGORITHMIC bytes they move (each array read / written once).  The
+// launch counters are always on; CUDA-event timing (on the context's stream) only when enabled
+// through lsk_profile_enable, which is how bench.py measures per-kernel achieved bandwidth live.
+enum ProfTag : int {
+  PT_TRACE = 0, PT_LDE_SMALL, PT_LDE_K1, PT_LDE_K2, PT_LDE_K3, PT_MERKLE_LEAF, PT_MERKLE_LAYER, PT_MERKLE_TOP,
+  PT_FRI_LEAF, PT_PERM_ROWS, PT_SCAN, PT_QUOTIENT, PT_BARY, PT_OPEN, PT_REDUCE_OPEN, PT_FRI_FOLD, PT_GRIND,
+  PT_GATHER, PT_POSEIDON2, PT_LAYOUT, PT_COUNT
+};
+static const char* const PROF_NAMES[PT_COUNT] = {
+    "trace_gen", "lde_small", "lde_k1", "lde_k2", "lde_k3", "merkle_leaf", "merkle_layer", "merkle_top", "fri_leaf",
+    "perm_rows", "scan", "quotient", "bary_weights", "open", "reduce_openings", "fri_fold", "grind", "gather",
+    "poseidon2", "layout"};
+struct Profiler {
+  bool timing = false;
+  struct Rec { int tag; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  unsigned long long launches[PT_COUNT] = {};
+  double bytes[PT_COUNT] = {};
+  double ms[PT_COUNT] = {};
+  cudaEvent_t get() {
+    if (!pool.empty()) {
+      cudaEvent_t e = pool.back();
+      pool.pop_back();
+      return e;
+    }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+  }
+};
+}  // namespace lsk
+
 struct lsk_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   void* ntt_tables = nullptr;   // lsk::NttTables (ntt.cu): twiddle / coset-scale tables, built lazily per size
+  lsk::Profiler prof;
 };
+
+namespace lsk {
+struct ProfScope {
+  lsk_ctx* ctx;
+  int tag;
+  cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(lsk_ctx* c, int t, unsigned nlaunch, double algorithmic_bytes) : ctx(c), tag(t) {
+    Profiler& p = ctx->prof;
+    p.launches[t] += nlaunch;
+    p.bytes[t] += algorithmic_bytes;
+    if (p.timing) {
+      a = p.get();
+      b = p.get();
+      cudaEventRecord(a, ctx->stream);
+    }
+  }
+  ~ProfScope() {
+    if (a) {
+      cudaEventRecord(b, ctx->stream);
+      ctx->prof.recs.push_back({tag, a, b});
+    }
+  }
+};
+}  // namespace lsk
 
 namespace lsk {
 

@@ -120,6 +120,7 @@ static void build_upper(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std
   unsigned l = 1;
   for (; l <= tree.log_max && tree.log_max - l > TOP_LOG; l++) {
     size_t n = (size_t)1 << (tree.log_max - l);
+    ProfScope ps(ctx, PT_MERKLE_LAYER, 1, (double)n * (96.0 + 4.0 * groups[l].second));
     merkle_layer_kernel<<<div_up(n, MK_BLOCK), MK_BLOCK, 0, st>>>(
         tree.nodes.p + tree.layer_off[l - 1] * 8, tree.nodes.p + tree.layer_off[l] * 8, n,
         tree.colptrs.p + groups[l].first, groups[l].second);
@@ -135,6 +136,7 @@ static void build_upper(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std
     }
     unsigned threads = 1u << (tree.log_max - l);
     threads = std::max(32u, threads);
+    ProfScope ps(ctx, PT_MERKLE_TOP, 1, 96.0 * 2 * threads);
     merkle_top_kernel<<<1, threads, 0, st>>>(tree.nodes.p, tl, tree.colptrs.p);
   }
   LSK_CUDA(cudaGetLastError());
@@ -162,8 +164,11 @@ void merkle_commit_dev(lsk_ctx* ctx, const std::vector<MatRef>& mats, MerkleTree
   tree.colptrs.upload(ptrs.data(), ptrs.size());
   layout_layers(ctx, tree);
   size_t rows = (size_t)1 << tree.log_max;
-  merkle_leaf_kernel<<<div_up(rows, MK_BLOCK), MK_BLOCK, 0, ctx->stream>>>(tree.colptrs.p + groups[0].first,
-                                                                          groups[0].second, rows, tree.nodes.p);
+  {
+    ProfScope ps(ctx, PT_MERKLE_LEAF, 1, (double)rows * (4.0 * groups[0].second + 32.0));
+    merkle_leaf_kernel<<<div_up(rows, MK_BLOCK), MK_BLOCK, 0, ctx->stream>>>(tree.colptrs.p + groups[0].first,
+                                                                            groups[0].second, rows, tree.nodes.p);
+  }
   LSK_CUDA(cudaGetLastError());
   build_upper(ctx, tree, groups);
 }
@@ -177,7 +182,10 @@ void merkle_commit_fri_layer_dev(lsk_ctx* ctx, const uint32_t* vals, unsigned lo
   tree.colptrs.upload(&none, 1);
   layout_layers(ctx, tree);
   size_t rows = (size_t)1 << log_rows;
-  merkle_fri_leaf_kernel<<<div_up(rows, MK_BLOCK), MK_BLOCK, 0, ctx->stream>>>(vals, rows, tree.nodes.p);
+  {
+    ProfScope ps(ctx, PT_FRI_LEAF, 1, 64.0 * rows);
+    merkle_fri_leaf_kernel<<<div_up(rows, MK_BLOCK), MK_BLOCK, 0, ctx->stream>>>(vals, rows, tree.nodes.p);
+  }
   LSK_CUDA(cudaGetLastError());
   std::vector<std::pair<uint32_t, uint32_t>> groups(log_rows + 1, {0u, 0u});
   build_upper(ctx, tree, groups);

@@ -270,6 +270,7 @@ void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, 
   if (logn <= LOG_BLOCK) {
     unsigned n = 1u << logn;
     unsigned threads = n / 2 < 32 ? 32 : (n / 2 > 1024 ? 1024 : n / 2);
+    ProfScope ps(ctx, PT_LDE_SMALL, 1, 12.0 * n * ncols);
     lde_small_kernel<<<ncols, threads, 2 * n * sizeof(uint32_t), st>>>(in, in_stride, out, out_stride, logn,
                                                                       t->tw_fwd.p, t->tw_inv.p, sc->a.p);
     LSK_CUDA(cudaGetLastError());
@@ -279,7 +280,11 @@ void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, 
   unsigned tt = logn - LOG_BLOCK;
   unsigned blocks = 1u << tt;
   if (ncols > 65535) fail(LSK_ERR_ARG, "too many columns");
-  lde_k1_kernel<<<dim3(blocks, ncols), 1024, 0, st>>>(in, in_stride, out, out_stride, t->tw_inv.p);
+  const double cells = (double)((size_t)1 << logn) * ncols;
+  {
+    ProfScope ps(ctx, PT_LDE_K1, 1, 8.0 * cells);
+    lde_k1_kernel<<<dim3(blocks, ncols), 1024, 0, st>>>(in, in_stride, out, out_stride, t->tw_inv.p);
+  }
   // tile = max(4096, 2^t * 16) elements, except 2^t * 8 for t >= 11
   unsigned log_tile = tt <= 8 ? 12 : (tt <= 10 ? tt + 4 : tt + 3);
   unsigned c = log_tile - tt;
@@ -288,15 +293,21 @@ void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, 
 #define K2(EPT)                                                                                                   \
   lde_k2_kernel<EPT><<<grid, 1024, smem, st>>>(out, out_stride, logn, c, t->tw_fwd.p, t->tw_inv.p, bg->lo_f.p,   \
                                                bg->hi_f.p, bg->lo_i.p, bg->hi_i.p, sc->a.p, sc->b.p)
-  switch (log_tile) {
-    case 12: K2(4); break;
-    case 13: K2(8); break;
-    case 14: K2(16); break;
-    case 15: K2(32); break;
-    default: fail(LSK_ERR_ARG, "bad LDE tile");
+  {
+    ProfScope ps(ctx, PT_LDE_K2, 1, 12.0 * cells);
+    switch (log_tile) {
+      case 12: K2(4); break;
+      case 13: K2(8); break;
+      case 14: K2(16); break;
+      case 15: K2(32); break;
+      default: fail(LSK_ERR_ARG, "bad LDE tile");
+    }
   }
 #undef K2
-  lde_k3_kernel<<<dim3(2 * blocks, ncols), 1024, 0, st>>>(out, out_stride, t->tw_fwd.p);
+  {
+    ProfScope ps(ctx, PT_LDE_K3, 1, 16.0 * cells);
+    lde_k3_kernel<<<dim3(2 * blocks, ncols), 1024, 0, st>>>(out, out_stride, t->tw_fwd.p);
+  }
   LSK_CUDA(cudaGetLastError());
 }
 

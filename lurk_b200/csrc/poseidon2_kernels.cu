@@ -70,6 +70,7 @@ template <int MODE>
 static void launch_rows(lsk_ctx* ctx, int width, const uint32_t* in_dev, size_t n, uint32_t* out_dev) {
   if (!n) return;
   unsigned grid = div_up(n, P2_BLOCK);
+  ProfScope ps(ctx, PT_POSEIDON2, 1, 4.0 * n * (width + (MODE == 0 ? 8 : width)));
   switch (width) {
     case 16: poseidon2_rows_kernel<16, MODE><<<grid, P2_BLOCK, 0, ctx->stream>>>(in_dev, n, out_dev); break;
     case 24: poseidon2_rows_kernel<24, MODE><<<grid, P2_BLOCK, 0, ctx->stream>>>(in_dev, n, out_dev); break;
@@ -97,6 +98,7 @@ int poseidon2_witness_cols(int width) {
 void poseidon2_witness_dev(lsk_ctx* ctx, int width, const uint32_t* in_dev, size_t n, uint32_t* out_dev) {
   if (!n) return;
   unsigned grid = div_up(n, P2_BLOCK);
+  ProfScope ps(ctx, PT_POSEIDON2, 1, 4.0 * n * (width + poseidon2_witness_cols(width)));
   switch (width) {
     case 24: poseidon2_witness_kernel<24><<<grid, P2_BLOCK, 0, ctx->stream>>>(in_dev, n, out_dev); break;
     case 32: poseidon2_witness_kernel<32><<<grid, P2_BLOCK, 0, ctx->stream>>>(in_dev, n, out_dev); break;

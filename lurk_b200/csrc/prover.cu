@@ -439,7 +439,9 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     ro[lh].alloc(ctx, (size_t)1 << lh);
     ro_desc[lh].alloc(ctx, by_height[lh].size());
     ro_desc[lh].upload(by_height[lh].data(), by_height[lh].size());
-    reduce_openings_dev(ctx, ro_desc[lh].p, (uint32_t)by_height[lh].size(), lh, zeta, d_fri.p, ro[lh].p);
+    double bytes = 16.0 * (double)((size_t)1 << lh);
+    for (auto& rmat : by_height[lh]) bytes += 4.0 * rmat.w * (double)((size_t)1 << lh);
+    reduce_openings_dev(ctx, ro_desc[lh].p, (uint32_t)by_height[lh].size(), lh, zeta, d_fri.p, ro[lh].p, bytes);
   }
 
   // ---- FRI commit phase
@@ -662,6 +664,7 @@ void lsk_release_record(lsk_machine* m) {
   m->pending.clear();
   m->drec.reset();
   m->drec_for = nullptr;
+  m->last_h2d = m->last_d2h = 0;
 }
 
 int lsk_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard_size, uint32_t** words, size_t* len) {

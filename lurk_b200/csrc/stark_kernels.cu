@@ -113,12 +113,17 @@ __global__ void scan_add_kernel(Ext* __restrict__ data, size_t n, const Ext* __r
 static void scan_ext_dev(lsk_ctx* ctx, Ext* data, size_t n) {
   size_t nb = (n + 1023) / 1024;
   if (nb <= 1) {
+    ProfScope ps(ctx, PT_SCAN, 1, 32.0 * n);
     scan_block_kernel<<<1, 256, 0, ctx->stream>>>(data, n, nullptr);
     return;
   }
   DevBuf<Ext> sums(ctx, nb);
-  scan_block_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(data, n, sums.p);
+  {
+    ProfScope ps(ctx, PT_SCAN, 1, 32.0 * n);
+    scan_block_kernel<<<(unsigned)nb, 256, 0, ctx->stream>>>(data, n, sums.p);
+  }
   scan_ext_dev(ctx, sums.p, nb);
+  ProfScope ps(ctx, PT_SCAN, 1, 32.0 * n);
   scan_add_kernel<<<div_up(n - 1024, 256), 256, 0, ctx->stream>>>(data, n, sums.p);
 }
 __global__ void phi_scatter_kernel(const Ext* __restrict__ phi_nat, unsigned logn, uint32_t* __restrict__ perm,
@@ -136,9 +141,14 @@ void perm_trace_dev(lsk_ctx* ctx, const ChipDev& chip, const uint32_t* main, siz
                     size_t pstride, unsigned logn, Ext chal_alpha, const Ext* beta_pows_dev, uint32_t* perm_out,
                     size_t perm_stride, Ext* scratch, Ext* cum_sum_out) {
   size_t n = (size_t)1 << logn;
-  perm_rows_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(chip.inter.p, chip.nint, main, mstride, prep, pstride, logn,
-                                                            chal_alpha, beta_pows_dev, perm_out, perm_stride, scratch);
+  {
+    ProfScope ps(ctx, PT_PERM_ROWS, 1, (double)n * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw));
+    perm_rows_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(chip.inter.p, chip.nint, main, mstride, prep, pstride,
+                                                              logn, chal_alpha, beta_pows_dev, perm_out, perm_stride,
+                                                              scratch);
+  }
   scan_ext_dev(ctx, scratch, n);
+  ProfScope ps(ctx, PT_SCAN, 1, 32.0 * n);
   phi_scatter_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(scratch, logn, perm_out, perm_stride, 4 * (chip.pw - 1),
                                                               cum_sum_out);
   LSK_CUDA(cudaGetLastError());
@@ -237,6 +247,7 @@ void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a) {
   size_t n2 = (size_t)2 << a.logn;
   unsigned grid = div_up(n2, 256);
   const uint4* code = reinterpret_cast<const uint4*>(chip.code.p);
+  ProfScope ps(ctx, PT_QUOTIENT, 1, (double)n2 * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw + 16.0));
 #define QK(R)                                                                                                    \
   quotient_kernel<R><<<grid, 256, 0, ctx->stream>>>(a, qc, code, chip.ninstr, chip.consts.p, chip.inter.p, chip.nint, \
                                                     chip.pw)
@@ -264,6 +275,7 @@ void bary_weights_dev(lsk_ctx* ctx, unsigned logn, Ext z, Ext* wts) {
   // scale = (z^n - g^n) / (g^n * n)
   Ext zn = epow(z, n);
   Ext scale = emul_base(esub_base(zn, gn), finv(fmul(gn, to_mont((uint32_t)n))));
+  ProfScope ps(ctx, PT_BARY, 1, 16.0 * n);
   bary_weights_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(logn, g, two_adic_generator(logn), z, scale, wts);
   LSK_CUDA(cudaGetLastError());
 }
@@ -336,6 +348,7 @@ void open_columns_dev(lsk_ctx* ctx, const uint32_t* m, size_t stride, uint32_t w
   if (!w) return;
   size_t n = (size_t)1 << logn;
   uint32_t nchunks = div_up(n, OPEN_ROWS);
+  ProfScope ps(ctx, PT_OPEN, 2, (double)n * (4.0 * w + 32.0));
   open_partial_kernel<<<dim3(nchunks, div_up(w, OPEN_COLS)), 256, 0, ctx->stream>>>(m, stride, w, n, wts0, wts1, partial,
                                                                                     nchunks);
   open_reduce_kernel<<<w * 2, 128, 0, ctx->stream>>>(partial, nchunks, out);
@@ -367,8 +380,9 @@ __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* _
   ro[r] = out;
 }
 void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats, unsigned lh, Ext zeta,
-                         const Ext* alpha_pows_dev, Ext* ro) {
+                         const Ext* alpha_pows_dev, Ext* ro, double algorithmic_bytes) {
   size_t n = (size_t)1 << lh;
+  ProfScope ps(ctx, PT_REDUCE_OPEN, 1, algorithmic_bytes);
   Ext z1 = emul_base(zeta, two_adic_generator(lh - 1));
   reduce_openings_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
                                                                   two_adic_generator(lh), zeta, z1, alpha_pows_dev, ro);
@@ -390,6 +404,7 @@ __global__ void __launch_bounds__(256) fri_fold_kernel(const Ext* __restrict__ c
 void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, Ext beta, const Ext* add, Ext* out) {
   size_t half = (size_t)1 << logh;
   uint32_t one_half = finv(to_mont(2));
+  ProfScope ps(ctx, PT_FRI_FOLD, 1, (double)half * (48.0 + (add ? 16.0 : 0.0)));
   fri_fold_kernel<<<div_up(half, 256), 256, 0, ctx->stream>>>(cur, logh, finv(two_adic_generator(logh + 1)), one_half,
                                                               emul_base(beta, one_half), add, out);
   LSK_CUDA(cudaGetLastError());
@@ -424,6 +439,7 @@ uint32_t grind_dev(lsk_ctx* ctx, const uint32_t state[16], const uint32_t* pendi
   for (uint64_t base = 0; base < P; base += batch) {
     uint32_t h = 0xffffffffu;
     best.upload(&h, 1);
+    ProfScope ps(ctx, PT_GRIND, 1, 0.0);
     grind_kernel<<<batch / 128, 128, 0, ctx->stream>>>(gs, (uint32_t)base, best.p);
     LSK_CUDA(cudaGetLastError());
     best.download(&h, 1);
@@ -440,6 +456,7 @@ __global__ void gather_kernel(const GatherJob* __restrict__ jobs, uint32_t* __re
 }
 void gather_dev(lsk_ctx* ctx, const GatherJob* jobs_dev, uint32_t njobs, uint32_t* out) {
   if (!njobs) return;
+  ProfScope ps(ctx, PT_GATHER, 1, 0.0);
   gather_kernel<<<njobs, 32, 0, ctx->stream>>>(jobs_dev, out);
   LSK_CUDA(cudaGetLastError());
 }

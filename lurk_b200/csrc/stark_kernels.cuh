@@ -61,7 +61,7 @@ struct ReduceMat {  // one opened matrix of LDE height 2^lh
 // ro[r] = sum over mats, points of off * (y - sum_c alpha^c m[r][c]) / (z_p - x_r), x_r = g * w_{2^lh}^bitrev(r),
 // z_0 = zeta, z_1 = zeta * w_{2^(lh-1)}
 void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats, unsigned lh, Ext zeta,
-                         const Ext* alpha_pows_dev, Ext* ro);
+                         const Ext* alpha_pows_dev, Ext* ro, double algorithmic_bytes);
 // out[i] = (1/2 + t) cur[2i] + (1/2 - t) cur[2i+1] (+ add[i]),  t = beta / (2 * w_{2^(logh+1)}^bitrev(i))
 void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, Ext beta, const Ext* add, Ext* out);
 // smallest witness w such that the duplex challenger, after observing w, samples `bits` zero bits.

@@ -335,6 +335,7 @@ void func_trace_dev(lsk_ctx* ctx, const lsk_program& prog, const DeviceRecord& d
   const uint32_t* chips = w + 3;
   uint32_t body = prog.body(func);
   bool col = layout == TraceLayout::ColMajorBitrevMont;
+  ProfScope ps(ctx, PT_TRACE, 1, 4.0 * height * width + 4.0 * real_rows * (hdr.in + hdr.out + 6));
 #define LAUNCH(CAP)                                                                                                  \
   do {                                                                                                               \
     if (col)                                                                                                         \
@@ -360,6 +361,7 @@ void mem_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, uint32_t mem_idx, uin
   LSK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)height * (4 + mt.len) * 4, ctx->stream));
   if (!mt.rows) return;
   uint32_t log_h = log2_exact(height);
+  ProfScope ps(ctx, PT_TRACE, 1, 8.0 * mt.rows * (4 + mt.len));
   if (layout == TraceLayout::ColMajorBitrevMont)
     mem_trace_kernel<true><<<div_up(mt.rows, 128), 128, 0, ctx->stream>>>(mt, height, log_h, d_out);
   else
@@ -370,6 +372,7 @@ void mem_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, uint32_t mem_idx, uin
 void bytes_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, bool real, TraceLayout layout, uint32_t* d_out) {
   LSK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)65536 * 13 * 4, ctx->stream));
   if (!real || !drec.bytes.p) return;
+  ProfScope ps(ctx, PT_TRACE, 1, 65536.0 * 25 * 4);
   if (layout == TraceLayout::ColMajorBitrevMont)
     bytes_trace_kernel<true><<<65536 / 256, 256, 0, ctx->stream>>>(drec.bytes.p, d_out);
   else
@@ -378,6 +381,7 @@ void bytes_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, bool real, TraceLay
 }
 
 void bytes_preprocessed_dev(lsk_ctx* ctx, TraceLayout layout, uint32_t* d_out) {
+  ProfScope ps(ctx, PT_TRACE, 1, 65536.0 * 6 * 4);
   if (layout == TraceLayout::ColMajorBitrevMont)
     bytes_prep_kernel<true><<<65536 / 256, 256, 0, ctx->stream>>>(d_out);
   else

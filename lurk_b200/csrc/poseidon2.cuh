@@ -23,7 +23,8 @@ template <> struct P2Rounds<40> { static constexpr int RP = 38; };
 
 template <int T>
 struct P2Const {
-  uint32_t diag[T];
+  uint32_t diag[T];        // plain residues: the internal layer multiplies by them Shoup-style
+  uint32_t diag_shoup[T];
   uint32_t full_rc[8 * T];
   uint32_t part_rc[P2Rounds<T>::RP];
 };
@@ -78,45 +79,38 @@ LSK_D void p2_external_linear(uint32_t (&s)[T]) {
   for (int i = 0; i < T; i++) s[i] = fadd(s[i], sums[i & 3]);
 }
 
+// One copy of each round body (external rounds 0-3, the partial rounds, external rounds 4-7 run
+// through the same code): ~17 KB of SASS per instantiation, so a kernel with a single call site
+// stays inside the 32 KB instruction cache level even when its warps are in different phases.
 template <int T, class Wit>
 LSK_D void p2_permute(uint32_t (&s)[T], Wit& wit) {
   const P2Const<T>& c = p2c<T>();
   constexpr int RP = P2Rounds<T>::RP;
   p2_external_linear<T>(s);
 #pragma unroll 1
-  for (int r = 0; r < 4; r++) {
-#pragma unroll
-    for (int i = 0; i < T; i++) {
-      wit.ext_state(r, i, s[i]);
-      uint32_t x = fadd(s[i], c.full_rc[r * T + i]);
-      uint32_t x3 = fmul(fsqr(x), x);
-      wit.ext_sbox(r, i, x3);
-      s[i] = fmul(x, fsqr(x3));
-    }
-    p2_external_linear<T>(s);
-  }
+  for (int r = 0; r < 8; r++) {
+    if (r == 4) {
 #pragma unroll 1
-  for (int r = 0; r < RP; r++) {
-    if (r == 0) {
+      for (int q = 0; q < RP; q++) {
+        if (q == 0) {
 #pragma unroll
-      for (int i = 0; i < T; i++) wit.int_init(i, s[i]);
-    } else {
-      wit.int_state0(r - 1, s[0]);
+          for (int i = 0; i < T; i++) wit.int_init(i, s[i]);
+        } else {
+          wit.int_state0(q - 1, s[0]);
+        }
+        uint32_t x = fadd(s[0], c.part_rc[q]);
+        uint32_t x3 = fmul(fsqr(x), x);
+        wit.int_sbox(q, x3);
+        s[0] = fmul(x, fsqr(x3));
+        // sum of the state: each term < P, T <= 40 terms < 2^37 -> one 64-bit accumulate + reduce
+        uint64_t acc = 0;
+#pragma unroll
+        for (int i = 0; i < T; i += 2) acc += (uint32_t)(s[i] + s[i + 1]);  // each term < 2^32
+        uint32_t sum = reduce_small64(acc);
+#pragma unroll
+        for (int i = 0; i < T; i++) s[i] = fadd(fmul_shoup(s[i], c.diag[i], c.diag_shoup[i]), sum);
+      }
     }
-    uint32_t x = fadd(s[0], c.part_rc[r]);
-    uint32_t x3 = fmul(fsqr(x), x);
-    wit.int_sbox(r, x3);
-    s[0] = fmul(x, fsqr(x3));
-    // sum of the state: each term < P, T <= 40 terms < 2^37 -> one 64-bit accumulate + reduce
-    uint64_t acc = 0;
-#pragma unroll
-    for (int i = 0; i < T; i += 2) acc += (uint32_t)(s[i] + s[i + 1]);  // each term < 2^32
-    uint32_t sum = reduce_small64(acc);
-#pragma unroll
-    for (int i = 0; i < T; i++) s[i] = fadd(fmul(s[i], c.diag[i]), sum);
-  }
-#pragma unroll 1
-  for (int r = 4; r < 8; r++) {
 #pragma unroll
     for (int i = 0; i < T; i++) {
       wit.ext_state(r, i, s[i]);
@@ -147,7 +141,7 @@ LSK_D void p2_compress(const uint32_t (&l)[8], const uint32_t (&r)[8], uint32_t 
 
 template <int T>
 static inline void p2_fill_const(P2Const<T>& h, const uint32_t* diag, const uint32_t* full, const uint32_t* part) {
-  for (int i = 0; i < T; i++) h.diag[i] = to_mont(diag[i]);
+  for (int i = 0; i < T; i++) h.diag[i] = diag[i] % P, h.diag_shoup[i] = shoup_precompute(diag[i] % P);
   for (int i = 0; i < 8 * T; i++) h.full_rc[i] = to_mont(full[i]);
   for (int i = 0; i < P2Rounds<T>::RP; i++) h.part_rc[i] = to_mont(part[i]);
 }

@@ -12,6 +12,8 @@
 // transcript (challenger.h) runs on the host; everything that touches a trace cell runs on the
 // device and nothing but commitments, opened values and query answers is copied back.
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -27,6 +29,21 @@ namespace lsk {
 
 constexpr uint32_t PROOF_MAGIC = 0x4c505246u;  // 'LPRF'
 constexpr unsigned LOG_BLOWUP = 1;
+
+// LSK_PHASES=1: host wall-clock per prover phase on stderr (synchronises at phase boundaries)
+struct PhaseTimer {
+  lsk_ctx* ctx;
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  explicit PhaseTimer(lsk_ctx* c) : ctx(c), on(std::getenv("LSK_PHASES") != nullptr) { t0 = std::chrono::steady_clock::now(); }
+  void mark(const char* name) {
+    if (!on) return;
+    cudaStreamSynchronize(ctx->stream);
+    auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[lsk phase] %-18s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 struct ShardState {  // phase-1 result of one shard, kept until its proof is written
   uint32_t shard = 0;
@@ -168,7 +185,9 @@ static DeviceRecord& device_record(lsk_machine& m, const lsk_record& rec) {
 
 static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record& rec, uint32_t shard, uint32_t ss) {
   lsk_ctx* ctx = m.ctx;
+  PhaseTimer pt(ctx);
   DeviceRecord& drec = device_record(m, rec);
+  pt.mark("record upload");
   if (rec.public_values.size() != m.num_pv) fail(LSK_ERR_ARG, "record has %zu public values, machine expects %u",
                                                  rec.public_values.size(), m.num_pv);
   struct Item { uint32_t chip; unsigned logn; };
@@ -224,8 +243,10 @@ static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record
     sd->main_lde.push_back(std::move(lde));
   }
   if (refs.empty()) fail(LSK_ERR_ARG, "shard %u has no chips", shard);
+  pt.mark("trace + main LDE");
   merkle_commit_dev(ctx, refs, sd->main_tree);
   merkle_root_host(ctx, sd->main_tree, sd->main_root);
+  pt.mark("main commit");
   return sd;
 }
 
@@ -253,6 +274,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   lsk_ctx* ctx = m.ctx;
   cudaStream_t st = ctx->stream;
   const size_t nchips = sd.chip_ids.size();
+  PhaseTimer pt(ctx);
   Ext chal_alpha = ch.sample_ext(), chal_beta = ch.sample_ext();
 
   size_t max_vals = 1, max_total = 1, max_w = 8, max_n = 1;
@@ -291,12 +313,14 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     refs.push_back(MatRef{perm_lde[i].p, 2 * n, sd.logn[i] + 1, pcols});
     sd.main[i].release();  // the natural-domain trace is not needed past this point
   }
+  pt.mark("perm trace + LDE");
   MerkleTreeDev perm_tree;
   merkle_commit_dev(ctx, refs, perm_tree);
   uint32_t perm_root[8];
   merkle_root_host(ctx, perm_tree, perm_root);
   for (int k = 0; k < 8; k++) ch.observe(to_mont(perm_root[k]));
   Ext alpha = ch.sample_ext();
+  pt.mark("perm commit");
 
   // ---- quotient, LDE of the two chunks, commit
   upload_pows(alpha, max_total, true, h_alpha, d_alpha);
@@ -335,12 +359,14 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       }
     }
   }
+  pt.mark("quotient + LDE");
   MerkleTreeDev quot_tree;
   merkle_commit_dev(ctx, refs, quot_tree);
   uint32_t quot_root[8];
   merkle_root_host(ctx, quot_tree, quot_root);
   for (int k = 0; k < 8; k++) ch.observe(to_mont(quot_root[k]));
   Ext zeta = ch.sample_ext();
+  pt.mark("quotient commit");
 
   // ---- openings at zeta and zeta * w_N
   // layout of `opened` per chip: prep | main | perm | quot0 | quot1, each as [col][point]
@@ -382,6 +408,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   cums.download(h_cums.data(), nchips);
   LSK_CUDA(cudaStreamSynchronize(st));
   m.last_d2h += (nopen + nchips) * sizeof(Ext);
+  pt.mark("openings");
 
   // rounds in the order the PCS sees them: preprocessed, main, permutation, quotient
   struct RoundMat { const uint32_t* p; size_t stride; unsigned lh; uint32_t w, npoints; size_t open_off; };
@@ -444,6 +471,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     reduce_openings_dev(ctx, ro_desc[lh].p, (uint32_t)by_height[lh].size(), lh, zeta, d_fri.p, ro[lh].p, bytes);
   }
 
+  pt.mark("reduce openings");
   // ---- FRI commit phase
   const unsigned nlayers = log_max - LOG_BLOWUP;
   std::vector<DevBuf<Ext>> fri_vals(nlayers + 1);
@@ -465,6 +493,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   if (!ext_eq(fin[0], fin[1])) fail(LSK_ERR_EXEC, "FRI final polynomial is not constant (prover bug)");
   Ext final_poly = fin[0];
   ch.observe(final_poly);
+  pt.mark("FRI commit phase");
   // proof of work: smallest witness, found on the device
   uint32_t pow_witness;
   {
@@ -475,6 +504,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     if (!ch.check_witness(m.pow_bits, to_mont(pow_witness))) fail(LSK_ERR_EXEC, "device grinding returned a bad witness");
   }
 
+  pt.mark("grind");
   // ---- query phase: build the gather script
   ProofScript ps;
   ps.lit(m.num_queries);
@@ -513,6 +543,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     m.last_d2h += (size_t)ps.total * 4;
   }
 
+  pt.mark("queries");
   // ---- serialise (word-for-word the oracle's / verifier's layout, canonical values)
   W.push_back(sd.shard);
   for (int k = 0; k < 8; k++) W.push_back(sd.main_root[k]);
@@ -553,6 +584,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       cur += it.count;
     }
   }
+  pt.mark("serialise");
 }
 
 static Challenger initial_challenger(const lsk_machine& m) {

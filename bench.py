@@ -226,17 +226,12 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def gather_roots(root):
-        if world == 1:
-            return root.reshape(1, 8)
-        t = torch.from_numpy(root.astype(np.int64)).to(dev)
-        outs = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(outs, t)
-        return torch.stack(outs).cpu().numpy().astype(np.uint32)
+    from lurk_b200.parallel import all_gather_roots, gather_shard_proofs
 
     def step_resident():
         root = m.commit_shard(mine)
-        return m.prove_shard(mine, gather_roots(root))
+        roots = all_gather_roots({rank: root}, world) if world > 1 else root.reshape(1, 8)
+        return m.prove_shard(mine, roots)
 
     def step_e2e():
         if world == 1:
@@ -244,17 +239,8 @@ def run_ours(args):
         m.release_record()             # force the host -> device upload of the record
         part = step_resident()
         # the proof of the job is the concatenation of the shard proofs: collect them on rank 0
-        n = torch.tensor([len(part)], device=dev)
-        sizes = [torch.empty_like(n) for _ in range(world)]
-        dist.all_gather(sizes, n)
-        mx = int(max(int(s) for s in sizes))
-        buf = torch.zeros(mx, dtype=torch.int64, device=dev)
-        buf[:len(part)] = torch.from_numpy(part.astype(np.int64)).to(dev)
-        outs = [torch.empty_like(buf) for _ in range(world)] if rank == 0 else None
-        dist.gather(buf, outs, dst=0)
-        if rank == 0:
-            return assemble_proof([o[:int(s)].cpu().numpy().astype(np.uint32) for o, s in zip(outs, sizes)]).words
-        return part
+        parts = gather_shard_proofs({rank: part}, world, 0)
+        return assemble_proof(parts).words if rank == 0 else part
 
     def timed(step, steps, profile):
         total_ms = 0.0

@@ -1,0 +1,83 @@
+"""The N>1 host logic (shard ownership, root all-gather, proof gather + assembly) on CPU with the
+gloo backend, world_size 2 and 3, driven by a stand-in machine (the real prover needs a GPU; the
+GPU test test_multi_shard_proof_is_bit_exact checks the same two-phase API against lsk_prove)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from lurk_b200.machine import PROOF_MAGIC
+from lurk_b200.parallel import prove_distributed, shards_of_rank
+
+
+class FakeShard:
+    def __init__(self, index):
+        self.index = index
+
+
+class FakeMachine:
+    """commit: root = f(shard); prove: words depend on the shard and on ALL roots (like the transcript)."""
+
+    def commit_shard(self, shard):
+        return (np.arange(8, dtype=np.uint32) * 7 + shard.index * 1000 + 1).astype(np.uint32)
+
+    def prove_shard(self, shard, roots):
+        assert roots.shape[1] == 8
+        n = 5 + 3 * shard.index          # ragged lengths
+        mix = int(roots.astype(np.uint64).sum() % 2013265921)
+        return (np.arange(n, dtype=np.uint64) * 31 + shard.index + mix).astype(np.uint32)
+
+
+def expected(num_shards):
+    m = FakeMachine()
+    shards = [FakeShard(i) for i in range(num_shards)]
+    roots = np.stack([m.commit_shard(s) for s in shards])
+    parts = [m.prove_shard(s, roots) for s in shards]
+    return np.concatenate([np.asarray([PROOF_MAGIC, num_shards], dtype=np.uint32)] + parts)
+
+
+def _worker(rank, world, port, num_shards, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        proof = prove_distributed(FakeMachine(), [FakeShard(i) for i in range(num_shards)])
+        if rank == 0:
+            q.put(proof.words)
+        else:
+            assert proof is None
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world,num_shards", [(2, 2), (2, 5), (3, 4), (2, 1)])
+def test_prove_distributed_matches_sequential(world, num_shards):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, num_shards, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    words = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(words, expected(num_shards))
+
+
+def test_shard_ownership_is_a_partition():
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 4, 9):
+            owned = sorted(s for r in range(world) for s in shards_of_rank(n, r, world))
+            assert owned == list(range(n))

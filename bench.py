@@ -215,6 +215,7 @@ def run_ours(args):
     t0 = time.perf_counter()
     out = execute_by_name(top, "fib", [world * (1 << L) - 1], q)
     t_exec = time.perf_counter() - t0
+    q.pin()                            # the record is the step's input: keep it in pinned host memory
     cfg = ShardingConfig(1 << L)
     shards = Shard(q, 0, cfg).shard(cfg)
     assert len(shards) == world, (len(shards), world)

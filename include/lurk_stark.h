@@ -86,6 +86,10 @@ size_t lsk_record_num_queries(const lsk_record* r, uint32_t func);
 size_t lsk_record_num_mem(const lsk_record* r, uint32_t mem_idx);
 size_t lsk_record_public_values(const lsk_record* r, uint32_t* out, size_t cap);
 uint32_t lsk_record_num_shards(const lsk_record* r, uint32_t shard_size);  /* Shard::shard, execute.rs:186-216 */
+/* Page-lock the record's tables in place (cudaHostRegister) so that lsk_prove's upload runs at PCIe
+ * speed; idempotent; undone by lsk_record_unpin, lsk_execute (the tables grow) and lsk_record_free. */
+int lsk_record_pin(lsk_record* r);
+void lsk_record_unpin(lsk_record* r);
 /* bytes a prove call moves host->device for this record (for end-to-end accounting) */
 size_t lsk_record_device_bytes(const lsk_record* r);
 

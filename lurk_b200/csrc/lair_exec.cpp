@@ -389,7 +389,11 @@ int lsk_record_new(const lsk_program* p, lsk_record** out) {
   return LSK_OK;
   LSK_API_END
 }
-void lsk_record_free(lsk_record* r) { delete r; }
+void lsk_record_free(lsk_record* r) {
+  if (!r) return;
+  lsk::record_unpin(r);
+  delete r;
+}
 
 int lsk_execute(const lsk_program* p, lsk_record* r, uint32_t func, const uint32_t* args, size_t nargs, uint32_t* out,
                 size_t nout) {
@@ -397,6 +401,7 @@ int lsk_execute(const lsk_program* p, lsk_record* r, uint32_t func, const uint32
   if (!p || !r || func >= p->nfuncs) fail(LSK_ERR_ARG, "bad argument");
   for (size_t i = 0; i < nargs; i++)
     if (args[i] >= Pq) fail(LSK_ERR_ARG, "argument not canonical");
+  lsk::record_unpin(r);  // the tables are about to grow
   Executor ex(*p, *r);
   std::vector<uint32_t> o;
   ex.run(func, args, (uint32_t)nargs, o);

@@ -614,6 +614,11 @@ __global__ void export_rows_kernel(const uint32_t* __restrict__ cols, size_t h, 
   rows[i] = from_mont(cols[c * h + r]);
 }
 
+void record_unpin(lsk_record* r) {
+  for (void* p : r->pinned) cudaHostUnregister(p);
+  r->pinned.clear();
+}
+
 void init_prover_kernels() {
   init_ntt_kernels();
   init_merkle_kernels();
@@ -697,6 +702,32 @@ void lsk_release_record(lsk_machine* m) {
   m->drec.reset();
   m->drec_for = nullptr;
   m->last_h2d = m->last_d2h = 0;
+}
+
+int lsk_record_pin(lsk_record* r) {
+  LSK_API_BEGIN
+  if (!r) fail(LSK_ERR_ARG, "null record");
+  if (!r->pinned.empty()) return LSK_OK;
+  auto pin = [&](std::vector<uint32_t>& v) {
+    if (v.size() < 16384) return;  // small tables are not worth a registration
+    LSK_CUDA(cudaHostRegister(v.data(), v.size() * 4, cudaHostRegisterDefault));
+    r->pinned.push_back(v.data());
+  };
+  try {
+    for (auto& t : r->funcs) {
+      pin(t.args); pin(t.outs); pin(t.provide); pin(t.req_off); pin(t.reqs); pin(t.hint_off); pin(t.hints);
+    }
+    for (auto& mt : r->mems) { pin(mt.vals); pin(mt.provide); }
+    pin(r->bytes);
+  } catch (...) {
+    record_unpin(r);
+    throw;
+  }
+  return LSK_OK;
+  LSK_API_END
+}
+void lsk_record_unpin(lsk_record* r) {
+  if (r) record_unpin(r);
 }
 
 int lsk_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard_size, uint32_t** words, size_t* len) {

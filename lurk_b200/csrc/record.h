@@ -130,4 +130,8 @@ struct lsk_record {
   std::vector<uint32_t> bytes;   // [65536][6][2] provide records (nonce, count); BytesRecord
   bool bytes_used = false;
   std::vector<uint32_t> public_values;
+  std::vector<void*> pinned;     // host ranges page-locked by lsk_record_pin (released by lsk_record_unpin / free)
 };
+namespace lsk {
+void record_unpin(lsk_record* r);  // prover.cu (needs the CUDA runtime)
+}

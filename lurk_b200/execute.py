@@ -75,6 +75,10 @@ class QueryRecord:
         N.check(N.lib().lsk_inject_inv_queries(self.program.h, self.h, f.index, N.vp(inps), N.vp(outs),
                                                ctypes.c_size_t(len(inps))))
 
+    def pin(self):
+        """Page-lock the record's tables so that prove uploads them at PCIe speed."""
+        N.check(N.lib().lsk_record_pin(self.h))
+
     def device_bytes(self) -> int:
         return N.lib().lsk_record_device_bytes(self.h)
 

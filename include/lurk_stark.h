@@ -64,6 +64,10 @@ int lsk_poseidon2_permute(lsk_ctx* ctx, int width, const uint32_t* in, size_t n,
  * src/poseidon/wide/trace.rs:12-82): out row = digest[8] ++ wide witness; lsk_poseidon2_witness_cols
  * gives the row length (457 / 611 / 763). */
 int lsk_poseidon2_witness_cols(int width);
+/* The permutation's parameters as canonical residues (src/poseidon/constants.rs via config.rs:157-287):
+ * diag[width], full_rc[8][width], part_rc[R_P]; returns R_P (21 / 30 / 38; 13 for width 16).  Host-only;
+ * used by the AIR capture of the hasher chips (Poseidon2Cols::eval, src/poseidon/wide/air.rs:11-124). */
+int lsk_poseidon2_constants(int width, uint32_t* diag, uint32_t* full_rc, uint32_t* part_rc, size_t part_cap);
 int lsk_poseidon2_witness(lsk_ctx* ctx, int width, const uint32_t* in, size_t n, uint32_t* out);
 
 /* ---- A2/A3: program + flattened record ------------------------------------------------------

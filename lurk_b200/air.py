@@ -388,10 +388,87 @@ def _eval_op(b: SymbolicBuilder, op: Op, cols: _Cols, sel: Expr, vmap, top: Topl
             pn, pc, ci = reqs[j]
             b.require([b.const(BYTE_TAG), b.const(1), i1, i2], nonce, pn, pc, ci, sel)
     elif k == "extern_call":
-        raise NotImplementedError("AIR capture of extern chips (Poseidon2 wide air, src/poseidon/wide/air.rs) "
-                                  "is not implemented yet")
+        # Op::ExternCall (src/lair/air.rs:461-482): witness columns first, then the require triples
+        chip = top.chips[a[0]]
+        inp = [vmap[i][0] for i in a[1]]
+        witness = [cols.next_aux() for _ in range(chip.witness_size)]
+        requires = [cols.next_require() for _ in range(chip.require_size)]
+        for o in _eval_chip(b, chip, sel, inp, witness, nonce, requires):
+            vmap.append((o, 1))
     else:
         raise ValueError(k)
+
+
+def _eval_chip(b: SymbolicBuilder, chip, is_real: Expr, inp, witness, nonce, requires) -> List[Expr]:
+    """Chipset::eval dispatch (src/core/chipset.rs:133-171)."""
+    if chip.kind in (1, 2, 3):
+        return eval_poseidon_chipset(b, {1: 24, 2: 32, 3: 40}[chip.kind], is_real, inp, witness)
+    raise NotImplementedError(f"AIR capture of extern chip {chip.name!r} (kind {chip.kind})")
+
+
+def _external_linear(s: List[Expr]) -> List[Expr]:
+    """Poseidon2ExternalMatrixGeneral (third-party p3-poseidon2): M4 = circ(2,3,1,1) on each 4-chunk,
+    then every element gains the sum of its residue class mod 4 (structure: src/poseidon/air.rs:133-138)."""
+    out = []
+    for i in range(0, len(s), 4):
+        x0, x1, x2, x3 = s[i:i + 4]
+        t01, t23 = x0 + x1, x2 + x3
+        t = t01 + t23
+        t1, t3 = t + x1, t + x3
+        out += [t1 + t01, t1 + 2 * x2, t3 + t23, t3 + 2 * x0]
+    sums = [None] * 4
+    for i, x in enumerate(out):
+        sums[i & 3] = x if sums[i & 3] is None else sums[i & 3] + x
+    return [x + sums[i & 3] for i, x in enumerate(out)]
+
+
+def eval_poseidon_chipset(b: SymbolicBuilder, width: int, is_real: Expr, inp, witness) -> List[Expr]:
+    """PoseidonChipset::eval (src/core/poseidon.rs:78-93) + Poseidon2Cols::eval
+    (src/poseidon/wide/air.rs:11-124); witness = output[8] ++ Poseidon2Cols (wide/columns.rs:17-32)."""
+    from .poseidon import constants
+    diag, full_rc, part_rc = constants(width)
+    rp = len(part_rc)
+    output, w = witness[:8], witness[8:]
+    assert len(inp) == width and len(w) == 17 * width + 2 * rp - 1
+    ext_state = [w[r * width:(r + 1) * width] for r in range(8)]
+    ext_sbox = [w[(8 + r) * width:(9 + r) * width] for r in range(8)]
+    o = 16 * width
+    int_init, int_state0, int_sbox = w[o:o + width], w[o + width:o + width + rp - 1], w[o + width + rp - 1:]
+    assert len(int_sbox) == rp
+
+    state = _external_linear([is_real * x for x in inp])
+
+    def external_round(state, r):
+        for i in range(width):
+            b.assert_eq(state[i], ext_state[r][i])
+        state = [ext_state[r][i] + is_real * int(full_rc[r][i]) for i in range(width)]
+        for i in range(width):
+            b.assert_eq(state[i] * state[i] * state[i], ext_sbox[r][i])
+            state[i] = state[i] * (ext_sbox[r][i] * ext_sbox[r][i])
+        return _external_linear(state)
+
+    for r in range(4):
+        state = external_round(state, r)
+    for r in range(rp):
+        if r == 0:
+            for i in range(width):
+                b.assert_eq(state[i], int_init[i])
+            state = list(int_init)
+        else:
+            b.assert_eq(state[0], int_state0[r - 1])
+            state[0] = int_state0[r - 1]
+        x = state[0] + is_real * int(part_rc[r])
+        b.assert_eq(x * x * x, int_sbox[r])
+        state[0] = x * (int_sbox[r] * int_sbox[r])
+        total = state[0]
+        for v in state[1:]:
+            total = total + v
+        state = [v * int(diag[i]) + total for i, v in enumerate(state)]     # config.rs:104-119
+    for r in range(4, 8):
+        state = external_round(state, r)
+    for st, out in zip(state, output):
+        b.assert_eq(st, is_real * out)
+    return list(output)
 
 
 def eval_mem(b: SymbolicBuilder, length: int):

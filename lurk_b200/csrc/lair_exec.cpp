@@ -368,6 +368,24 @@ int lsk_program_load(const uint32_t* words, size_t n, lsk_program** out) {
   LSK_API_END
 }
 void lsk_program_free(lsk_program* p) { delete p; }
+
+int lsk_poseidon2_constants(int width, uint32_t* diag, uint32_t* full_rc, uint32_t* part_rc, size_t part_cap) {
+  LSK_API_BEGIN
+  const uint32_t *d, *f, *pr;
+  int rp;
+  switch (width) {
+    case 16: d = P2_DIAG_16; f = P2_FULL_RC_16; pr = P2_PART_RC_16; rp = P2_RP_16; break;
+    case 24: d = P2_DIAG_24; f = P2_FULL_RC_24; pr = P2_PART_RC_24; rp = P2_RP_24; break;
+    case 32: d = P2_DIAG_32; f = P2_FULL_RC_32; pr = P2_PART_RC_32; rp = P2_RP_32; break;
+    case 40: d = P2_DIAG_40; f = P2_FULL_RC_40; pr = P2_PART_RC_40; rp = P2_RP_40; break;
+    default: fail(LSK_ERR_ARG, "unsupported Poseidon2 width %d", width);
+  }
+  if (diag) std::copy(d, d + width, diag);
+  if (full_rc) std::copy(f, f + 8 * width, full_rc);
+  if (part_rc) std::copy(pr, pr + std::min<size_t>(rp, part_cap), part_rc);
+  return rp;
+  LSK_API_END
+}
 int lsk_program_num_funcs(const lsk_program* p) { return p ? (int)p->nfuncs : LSK_ERR_ARG; }
 int lsk_program_func_width(const lsk_program* p, uint32_t func) {
   return p && func < p->nfuncs ? (int)p->width(func) : LSK_ERR_ARG;

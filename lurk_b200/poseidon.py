@@ -55,6 +55,18 @@ class PoseidonChipset:
                                                ctypes.c_void_p(out_ptr)))
 
 
+def constants(width: int):
+    """(diag[W], full_rc[8][W], part_rc[R_P]) as canonical residues -- PoseidonConfig::{matrix_diag,
+    external_constants, internal_constants}, src/poseidon/config.rs:20-75.  Host-only (no GPU needed)."""
+    diag = np.empty(width, dtype=np.uint32)
+    full = np.empty((8, width), dtype=np.uint32)
+    part = np.empty(64, dtype=np.uint32)
+    rp = N.lib().lsk_poseidon2_constants(int(width), N.vp(diag), N.vp(full), N.vp(part), ctypes.c_size_t(64))
+    if rp < 0:
+        N.check(rp)
+    return diag, full, part[:rp].copy()
+
+
 def hash3(preimages, ctx=None):
     return PoseidonChipset(24, ctx).hash(preimages)
 

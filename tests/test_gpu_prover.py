@@ -130,6 +130,34 @@ def test_reference_test_programs_prove_bit_exact(oracle, tname, fname, args):
     assert om.verify(proof.words), om.last_error
 
 
+@pytest.mark.parametrize("fname,args", [("commit_cons", "kat2"), ("cons_chain", [9]), ("env_chain", [4])])
+def test_hasher_chip_programs_prove_bit_exact(oracle, fname, args):
+    # hash3/hash4/hash5 funcs (widths 493/655/815): Poseidon2 wide witness on the GPU + the captured
+    # Poseidon2Cols::eval constraints (src/poseidon/wide/air.rs:11-124) in the quotient kernel
+    from test_oracle_stark import KAT2, big_uint, kat2_args
+    top = goldens.toplevel_for("hash")
+    a = kat2_args() if args == "kat2" else args
+    m, om, q, proof, want = _prove_both(oracle, top, fname, [a])
+    if args == "kat2":
+        assert big_uint(q.expect_public_values()[-8:]) == KAT2
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+
+
+def test_cons_chain_2pow12_verifies(oracle):
+    # Lurk-shaped load: the 655-wide hash4 chip dominates (2^12 x 655 main trace); acceptance by the verifier
+    top = goldens.toplevel_for("hash")
+    opts = SphinxCoreOpts(num_queries=10, proof_of_work_bits=8)
+    m = new_machine(top, "cons_chain", opts=opts)
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    execute_by_name(top, "cons_chain", [(1 << 12) - 1], q)
+    proof = m.prove(pk, Shard.new(q))
+    ot = oracle.OracleToplevel(top.serialize())
+    om = oracle.OracleMachine(ot, m.entry.index, m.blob, 10, 8)
+    assert om.verify(proof.words), om.last_error
+
+
 def test_multi_shard_proof_is_bit_exact(oracle):
     # the reference tests sharding with tiny shard sizes (src/air/debug.rs:119-158); ragged last shard
     top = goldens.toplevel_for("ackermann")

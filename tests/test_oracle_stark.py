@@ -42,6 +42,51 @@ def test_prove_verify_roundtrip(oracle, tname, fname, args):
     assert not om.verify(proof[:-1])
 
 
+KAT2 = 0x955f855f302a30ed988cc48685c442ebd98c8711e989fc64df8f27f52e1350   # src/core/cli/tests/prove.lurk:12-17
+
+
+def big_uint(limbs):
+    v = 0
+    for x in reversed(limbs):     # little-endian base-p limbs, src/core/big_num.rs:101-108
+        v = v * P + int(x)
+    return v
+
+
+def kat2_args():
+    a = [0] * 8 + [13] + [0] * 7
+    b = [0] * 8 + [17] + [0] * 7
+    return a + b + [0] * 8 + [11] + [0] * 7
+
+
+@pytest.mark.parametrize("fname,args", [("commit_cons", None), ("cons_chain", [5]), ("env_chain", [3])])
+def test_hasher_chips_prove_verify(oracle, fname, args):
+    # Poseidon2Cols::eval (src/poseidon/wide/air.rs:11-124) captured into the constraint program: the proof
+    # only verifies if every wide-witness cell satisfies the hasher AIR
+    top = goldens.toplevel_for("hash")
+    ot, om, f = oracle_machine(oracle, top, fname)
+    rec = oracle.OracleRecord(ot)
+    out = rec.execute(f.index, args if args is not None else kat2_args(), f.output_size)
+    if args is None:
+        assert big_uint(out) == KAT2
+    proof = om.prove(rec)
+    assert om.verify(proof), om.last_error
+    bad = proof.copy()
+    bad[len(bad) // 2] = (int(bad[len(bad) // 2]) + 1) % P
+    assert not om.verify(bad)
+
+
+def test_hasher_air_shape():
+    # 611 hasher constraints + outputs... the chip's constraint count and degree (sphinx: max degree 3)
+    top = goldens.toplevel_for("hash")
+    chips = {c.name: c for c in build_chip_vector(FuncChip.from_name("commit_cons", top))}
+    for name, t, rp in (("Func[hash3]", 24, 21), ("Func[hash4]", 32, 30), ("Func[hash5]", 40, 38)):
+        c = chips[name]
+        # 16t (external state + sbox) + t (internal init) + (rp - 1) + rp + 8 outputs; + nonce, sel-bool, 8 returns
+        assert c.n_constraints == 17 * t + 2 * rp - 1 + 8 + 10
+        assert c.max_degree == 3 and c.log_quotient_degree == 1
+        assert len(c.sends) == 1 and len(c.receives) == 1
+
+
 def test_multi_shard_roundtrip(oracle):
     # sharding tested with tiny shards as in src/air/debug.rs:119-158; cross-shard lookups must cancel
     top = goldens.toplevel_for("ackermann")

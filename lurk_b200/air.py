@@ -27,7 +27,8 @@ from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .lair import (DEPTH_W, MEM_TABLE_SIZES, Block, Ctrl, Func, FuncChip, Op, P, Toplevel)
+from .lair import (DEPTH_LESS_THAN_REQUIRES, DEPTH_LESS_THAN_SIZE, DEPTH_W, MEM_TABLE_SIZES, Block, Ctrl, Func,
+                   FuncChip, Op, P, Toplevel)
 
 CALL_TAG, MEMORY_TAG, BYTE_TAG = 0, 1, 3
 INTERACTION_KIND_MEMORY = 1  # sphinx_core::lookup::InteractionKind::Memory as usize
@@ -254,15 +255,79 @@ def eval_func(b: SymbolicBuilder, f: Func, top: Toplevel):
     b.assert_bool(toplevel_sel)
     last_nonce, last_count = cols.next_aux(), cols.next_aux()
     out = [cols.output(i) for i in range(f.output_size)]
+    depth: List[Expr] = []
     if f.partial:
-        raise NotImplementedError("partial funcs (depth provenance, src/lair/provenance.rs) are not captured yet")
+        # src/lair/air.rs:210-224: the row's depth as DEPTH_W range-checked bytes, part of the provided relation
+        depth = [cols.next_aux() for _ in range(DEPTH_W)]
+        requires = [cols.next_require() for _ in range((DEPTH_W + 1) // 2)]
+        rec = _ByteAirRecord()
+        rec.range_check_u8_iter(depth, toplevel_sel)
+        rec.require_all(b, nonce, requires)
+        out = out + depth
     b.provide([b.const(CALL_TAG), b.const(f.index)] + call_inp + out, last_nonce, last_count, toplevel_sel)
-    _eval_block(b, f.body, cols, toplevel_sel, vmap, top)
+    _eval_block(b, f.body, cols, toplevel_sel, vmap, top, depth)
 
 
-def _eval_block(b, block: Block, cols: _Cols, sel: Expr, vmap, top: Toplevel):
+class _ByteAirRecord:
+    """BytesAirRecordWithContext (src/gadgets/bytes/builder.rs:18-89): byte relations logged while a
+    gadget evaluates, then required in order against the row's require triples."""
+
+    def __init__(self):
+        self.records: List[Tuple[List, Expr]] = []
+
+    def range_check_u8_iter(self, xs, is_real):     # src/gadgets/bytes/mod.rs:127-138
+        xs = list(xs)
+        for i in range(0, len(xs), 2):
+            self.records.append(([1, xs[i], xs[i + 1] if i + 1 < len(xs) else 0], is_real))
+
+    def less_than(self, i1, i2, r, is_real):
+        self.records.append(([3, i1, i2, r], is_real))
+
+    def require_all(self, b: SymbolicBuilder, nonce, requires):
+        assert len(requires) == len(self.records)
+        cv = lambda x: x if isinstance(x, Expr) else b.const(x)
+        for (rel, is_real), (pn, pc, ci) in zip(self.records, requires):
+            b.require([b.const(BYTE_TAG)] + [cv(x) for x in rel], nonce, pn, pc, ci, is_real)
+
+
+def _assert_less_than(b: SymbolicBuilder, wit: List[Expr], lhs: List[Expr], rhs: List[Expr], rec: _ByteAirRecord,
+                      is_real: Expr):
+    """LessThanWitness::assert_less_than (src/gadgets/unsigned/less_than.rs:49-103);
+    wit = is_comp[W] ++ [lhs_comp_limb, rhs_comp_limb]."""
+    w = len(lhs)
+    is_comp, lhs_limb, rhs_limb = wit[:w], wit[w], wit[w + 1]
+    with b.when(is_real):
+        is_equal = b.const(0)
+        for i in range(w):
+            if i > 0:
+                with b.when(is_equal):
+                    b.assert_eq(lhs[i], rhs[i])
+            b.assert_bool(is_comp[i])
+            is_equal = is_equal + is_comp[i]
+        b.assert_one(is_equal)
+        sel_l, sel_r = b.const(0), b.const(0)
+        for i in range(w):
+            sel_l = sel_l + lhs[i] * is_comp[i]
+            sel_r = sel_r + rhs[i] * is_comp[i]
+        b.assert_eq(sel_l, lhs_limb)
+        b.assert_eq(sel_r, rhs_limb)
+    rec.less_than(lhs_limb, rhs_limb, 1, is_real)
+
+
+def _eval_depth(b: SymbolicBuilder, cols: _Cols, depth: List[Expr], sel: Expr, out: List[Expr]):
+    """eval_depth (src/lair/air.rs:105-131): the callee's depth bytes, proven smaller than the row's own."""
+    dep_depth = [cols.next_aux() for _ in range(DEPTH_W)]
+    witness = [cols.next_aux() for _ in range(DEPTH_LESS_THAN_SIZE)]
+    rec = _ByteAirRecord()
+    _assert_less_than(b, witness, dep_depth, depth, rec, sel)
+    requires = [cols.next_require() for _ in range(DEPTH_LESS_THAN_REQUIRES)]
+    rec.require_all(b, cols.nonce(), requires)
+    out.extend(dep_depth)
+
+
+def _eval_block(b, block: Block, cols: _Cols, sel: Expr, vmap, top: Toplevel, depth=()):
     for op in block.ops:
-        _eval_op(b, op, cols, sel, vmap, top)
+        _eval_op(b, op, cols, sel, vmap, top, depth)
     c = block.ctrl
     if c.kind == "return":
         s = cols.sel(c.args[0])
@@ -273,12 +338,12 @@ def _eval_block(b, block: Block, cols: _Cols, sel: Expr, vmap, top: Toplevel):
     blocks = [blk for _, blk in c.args[1]] + ([c.args[2]] if c.args[2] is not None else [])
     n, st = len(vmap), cols.save()
     for blk in blocks:
-        _eval_block(b, blk, cols, _return_sel(blk, cols), vmap, top)
+        _eval_block(b, blk, cols, _return_sel(blk, cols), vmap, top, depth)
         del vmap[n:]
         cols.restore(st)
 
 
-def _eval_op(b: SymbolicBuilder, op: Op, cols: _Cols, sel: Expr, vmap, top: Toplevel):
+def _eval_op(b: SymbolicBuilder, op: Op, cols: _Cols, sel: Expr, vmap, top: Toplevel, depth=()):
     k, a = op.kind, op.args
     nonce = cols.nonce()
     if k == "assert_ne":
@@ -349,7 +414,7 @@ def _eval_op(b: SymbolicBuilder, op: Op, cols: _Cols, sel: Expr, vmap, top: Topl
         inp = [vmap[i][0] for i in a[1]]
         pn, pc, ci = cols.next_require()
         if callee.partial:
-            raise NotImplementedError("partial callee")
+            _eval_depth(b, cols, list(depth), sel, out)
         b.require([b.const(CALL_TAG), b.const(a[0])] + inp + out, nonce, pn, pc, ci, sel)
     elif k == "preimg":
         callee = top.funcs[a[0]]
@@ -361,7 +426,7 @@ def _eval_op(b: SymbolicBuilder, op: Op, cols: _Cols, sel: Expr, vmap, top: Topl
         out = [vmap[o][0] for o in a[1]]
         pn, pc, ci = cols.next_require()
         if callee.partial:
-            raise NotImplementedError("partial callee")
+            _eval_depth(b, cols, list(depth), sel, out)
         b.require([b.const(CALL_TAG), b.const(a[0])] + inp + out, nonce, pn, pc, ci, sel)
     elif k == "store":
         ptr = cols.next_aux()

@@ -76,7 +76,7 @@ static inline int chip_width(uint32_t kind) { return kind == 1 ? 24 : kind == 2 
 
 struct Frame {
   uint32_t func, nonce, pc, ops_left;
-  size_t map_base, req_base, hint_base;
+  size_t map_base, req_base, hint_base, depth_base;
   bool preimg;  // this frame was entered through PreImg: the caller receives the inputs
 };
 
@@ -84,7 +84,7 @@ struct Executor {
   const lsk_program& prog;
   lsk_record& rec;
   const uint32_t* w;
-  std::vector<uint32_t> vals, req_stack, hint_stack;
+  std::vector<uint32_t> vals, req_stack, hint_stack, depth_stack;
   std::vector<Frame> frames;
   Executor(const lsk_program& p, lsk_record& r) : prog(p), rec(r), w(p.words.data()) {}
 
@@ -104,6 +104,10 @@ struct Executor {
     t.provide.push_back(seed_count);
     t.req_off.push_back(0);
     t.hint_off.push_back(0);
+    if (t.partial) {
+      t.depth.push_back(0);
+      t.dreq_off.push_back(0);
+    }
     t.index.insert_new(t.args.data(), t.in, row);
     return row;
   }
@@ -112,7 +116,7 @@ struct Executor {
     f.pc = block + 2;
   }
   void push_frame(uint32_t func, uint32_t nonce, const uint32_t* inp, uint32_t n, bool preimg) {
-    Frame f{func, nonce, 0, 0, vals.size(), req_stack.size(), hint_stack.size(), preimg};
+    Frame f{func, nonce, 0, 0, vals.size(), req_stack.size(), hint_stack.size(), depth_stack.size(), preimg};
     // NB `inp` may point into `vals`; copy before growing
     std::vector<uint32_t> tmp(inp, inp + n);
     vals.insert(vals.end(), tmp.begin(), tmp.end());
@@ -129,6 +133,12 @@ struct Executor {
     vals.insert(vals.end(), tmp.begin(), tmp.end());
     new_lookup(&t.provide[(size_t)row * 2], f.nonce, req_stack);
     hint_stack.push_back(row);
+    if (t.partial && rec.funcs[f.func].partial) depth_stack.push_back(t.depth[row]);  // execute.rs:510-512,751-753
+  }
+  uint32_t* byte_record(uint32_t i1, uint32_t i2, int slot) {  // BytesInputRecord field of ByteInput (i1, i2)
+    if (rec.bytes.empty()) rec.bytes.assign((size_t)65536 * 12, 0);
+    rec.bytes_used = true;
+    return &rec.bytes[(size_t)(i1 | (i2 << 8)) * 12 + 2 * slot];
   }
 
   void run(uint32_t entry, const uint32_t* args, uint32_t nargs, std::vector<uint32_t>& out) {
@@ -149,6 +159,8 @@ struct Executor {
     while (!frames.empty()) step(out);
     rec.public_values.assign(args, args + nargs);
     rec.public_values.insert(rec.public_values.end(), out.begin(), out.end());
+    if (et.partial)  // execute.rs:387-389: the entry's depth as little-endian bytes
+      for (int b = 0; b < 4; b++) rec.public_values.push_back((et.depth[row] >> (8 * b)) & 255u);
   }
 
   void step(std::vector<uint32_t>& final_out) {
@@ -261,13 +273,10 @@ struct Executor {
         } break;
         case OP_RANGE_U8: {
           uint32_t n = op[1];
-          if (rec.bytes.empty()) rec.bytes.assign((size_t)65536 * 12, 0);
-          rec.bytes_used = true;
           for (uint32_t i = 0; i < n; i += 2) {
             uint32_t i1 = m[op[2 + i]], i2 = i + 1 < n ? m[op[3 + i]] : 0;
             if (i1 > 255 || i2 > 255) fail(LSK_ERR_EXEC, "Variable not in u8 range");
-            size_t key = i1 | (i2 << 8);
-            new_lookup(&rec.bytes[key * 12 + 0], f.nonce, req_stack);  // slot 0 = range_u8 pair
+            new_lookup(byte_record(i1, i2, 0), f.nonce, req_stack);  // slot 0 = range_u8 pair
           }
         } break;
         default: fail(LSK_ERR_EXEC, "bad opcode %u", op[0]);
@@ -296,6 +305,21 @@ struct Executor {
                             t.args.begin() + (size_t)(f.nonce + 1) * t.in);
           t.inv_index.insert_new(t.inv_outs.data(), t.out, slot);
         }
+      }
+      if (t.partial) {  // execute.rs:702-711: depth = 1 + max over the partial callees, range check + comparisons
+        uint32_t depth = 0;
+        for (size_t i = f.depth_base; i < depth_stack.size(); i++) depth = std::max(depth, depth_stack[i] + 1);
+        t.dreq_off[f.nonce] = (uint32_t)(t.dreqs.size() / 2);
+        for (int b = 0; b < 4; b += 2)
+          new_lookup(byte_record((depth >> (8 * b)) & 255u, (depth >> (8 * b + 8)) & 255u, 0), f.nonce, t.dreqs);
+        for (size_t i = f.depth_base; i < depth_stack.size(); i++) {
+          uint32_t dep = depth_stack[i];  // dep < depth; most significant differing byte (LessThanWitness::populate)
+          int b = 3;
+          while (((dep >> (8 * b)) & 255u) == ((depth >> (8 * b)) & 255u)) b--;
+          new_lookup(byte_record((dep >> (8 * b)) & 255u, (depth >> (8 * b)) & 255u, 2), f.nonce, t.dreqs);
+        }
+        t.depth[f.nonce] = depth;
+        depth_stack.resize(f.depth_base);
       }
       t.req_off[f.nonce] = (uint32_t)(t.reqs.size() / 2);
       t.reqs.insert(t.reqs.end(), req_stack.begin() + f.req_base, req_stack.end());
@@ -361,7 +385,41 @@ int lsk_program_load(const uint32_t* words, size_t n, lsk_program** out) {
   }
   for (uint32_t f = 0; f < p->nfuncs; f++) {
     if (p->func_offset(f) + FUNC_HEADER_WORDS + 2 > n) { delete p; fail(LSK_ERR_ARG, "bad func offset"); }
-    if (p->header(f).partial) { delete p; fail(LSK_ERR_ARG, "partial funcs (depth provenance) are not supported yet"); }
+  }
+  // a total func may not call a partial one ("assertion failed: ctx.partial", src/lair/execute.rs:1005-1023)
+  for (uint32_t f = 0; f < p->nfuncs; f++) {
+    if (p->header(f).partial) continue;
+    const uint32_t* w = p->words.data();
+    uint32_t body = p->body(f), end = body + w[body];
+    if (end > n) { delete p; fail(LSK_ERR_ARG, "bad block length"); }
+    std::vector<uint32_t> blocks{body};
+    while (!blocks.empty()) {
+      uint32_t b = blocks.back();
+      blocks.pop_back();
+      uint32_t pc = b + 2;
+      for (uint32_t k = 0; k < w[b + 1]; k++) {
+        const uint32_t* op = w + pc;
+        if ((op[0] == OP_CALL || op[0] == OP_PREIMG) && op[1] < p->nfuncs && p->header(op[1]).partial) {
+          delete p;
+          fail(LSK_ERR_ARG, "assertion failed: ctx.partial (func %u is total but calls partial func %u)", f, op[1]);
+        }
+        uint32_t ow = op_words(op);
+        if (!ow) { delete p; fail(LSK_ERR_ARG, "bad opcode in program image"); }
+        pc += ow;
+      }
+      const uint32_t* c = w + pc;
+      if (c[0] == CTRL_CHOOSE || c[0] == CTRL_CHOOSE_MANY) {
+        uint32_t nv = c[1], nb = c[2 + nv], has_d = c[3 + nv];
+        uint32_t q = pc + 4 + nv;
+        for (uint32_t i = 0; i < nb; i++) {
+          uint32_t nk = w[q++];
+          q += c[0] == CTRL_CHOOSE ? nk : nv * nk;
+          blocks.push_back(q);
+          q += w[q];
+        }
+        if (has_d) blocks.push_back(q);
+      }
+    }
   }
   *out = p;
   return LSK_OK;
@@ -401,6 +459,7 @@ int lsk_record_new(const lsk_program* p, lsk_record** out) {
     r->funcs[f].in = h.in;
     r->funcs[f].out = h.out;
     r->funcs[f].invertible = h.invertible != 0;
+    r->funcs[f].partial = h.partial != 0;
   }
   for (int i = 0; i < NUM_MEM_TABLES; i++) r->mems[i].len = (uint32_t)mem_table_len(i);
   *out = r;
@@ -479,7 +538,7 @@ size_t lsk_record_device_bytes(const lsk_record* r) {
   size_t b = 0;
   for (auto& t : r->funcs)
     b += 4 * (t.args.size() + t.outs.size() + t.provide.size() + t.req_off.size() + t.reqs.size() + t.hint_off.size() +
-              t.hints.size());
+              t.hints.size() + t.depth.size() + t.dreq_off.size() + t.dreqs.size());
   for (auto& m : r->mems) b += 4 * (m.vals.size() + m.provide.size());
   b += 4 * r->bytes.size();
   return b;

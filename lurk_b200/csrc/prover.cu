@@ -715,7 +715,7 @@ int lsk_record_pin(lsk_record* r) {
   };
   try {
     for (auto& t : r->funcs) {
-      pin(t.args); pin(t.outs); pin(t.provide); pin(t.req_off); pin(t.reqs); pin(t.hint_off); pin(t.hints);
+      pin(t.args); pin(t.outs); pin(t.provide); pin(t.req_off); pin(t.reqs); pin(t.hint_off); pin(t.hints); pin(t.depth); pin(t.dreq_off); pin(t.dreqs);
     }
     for (auto& mt : r->mems) { pin(mt.vals); pin(mt.provide); }
     pin(r->bytes);

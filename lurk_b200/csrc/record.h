@@ -91,6 +91,11 @@ struct FuncTable {
   std::vector<uint32_t> reqs;      // pairs (prev_nonce, prev_count) in op order
   std::vector<uint32_t> hint_off;  // [n]
   std::vector<uint32_t> hints;     // callee / memory row per Call, PreImg, Store in op order
+  // partial funcs only (depth provenance, src/lair/provenance.rs; QueryResult::{depth, depth_requires}):
+  bool partial = false;
+  std::vector<uint32_t> depth;     // [n]
+  std::vector<uint32_t> dreq_off;  // [n] index (in pairs) of the row's first depth require
+  std::vector<uint32_t> dreqs;     // pairs: 2 range checks of the depth bytes, then one less-than per partial callee
   HashIndex index;                 // args -> row
   // inverse queries (PreImg): out -> inp, both produced at Return and injected from outside
   std::vector<uint32_t> inv_outs, inv_inps;

@@ -11,6 +11,7 @@ namespace lsk {
 
 struct DevFuncTable {
   const uint32_t *args, *outs, *provide, *req_off, *reqs, *hint_off, *hints;
+  const uint32_t *depth, *dreq_off, *dreqs;   // partial funcs only (else null)
   uint32_t in, out, rows;
 };
 struct DevMemTable {

@@ -75,12 +75,35 @@ __device__ void populate_row(const uint32_t* __restrict__ w, uint32_t body, Func
   st(aux++, to_mont(self.provide[(size_t)q * 2 + 1]));
   const uint32_t* reqs = self.reqs + (size_t)self.req_off[q] * 2;
   const uint32_t* hints = self.hints + self.hint_off[q];
-  auto push_require = [&]() {  // Record::into_require, src/air/builder.rs:159-168
-    uint32_t pn = reqs[0], pc = reqs[1];
-    reqs += 2;
+  auto push_record = [&](const uint32_t*& r) {  // Record::into_require, src/air/builder.rs:159-168
+    uint32_t pn = r[0], pc = r[1];
+    r += 2;
     st(aux++, to_mont(pn));
     st(aux++, to_mont(pc));
     st(aux++, finv(to_mont(pc + 1)));
+  };
+  auto push_require = [&]() { push_record(reqs); };
+  // depth provenance (src/lair/trace.rs:110-121,235-254): the row's own depth as 4 range-checked bytes ...
+  const uint32_t* dreqs = nullptr;
+  uint32_t depth = 0;
+  if (hdr.partial) {
+    dreqs = self.dreqs + (size_t)self.dreq_off[q] * 2;
+    depth = self.depth[q];
+    for (int b = 0; b < 4; b++) st(aux++, to_mont((depth >> (8 * b)) & 255u));
+    push_record(dreqs);
+    push_record(dreqs);
+  }
+  // ... and, per partial callee, its depth bytes, the LessThanWitness (is_comp[4], lhs limb, rhs limb:
+  // src/gadgets/unsigned/less_than.rs:12-41) proving dep < depth, and the byte lookup's require
+  auto push_depth = [&](uint32_t dep) {
+    for (int b = 0; b < 4; b++) st(aux++, to_mont((dep >> (8 * b)) & 255u));
+    int cb = 3;
+    while (cb > 0 && ((dep >> (8 * cb)) & 255u) == ((depth >> (8 * cb)) & 255u)) cb--;
+    st(aux + cb, R1);
+    st(aux + 4, to_mont((dep >> (8 * cb)) & 255u));
+    st(aux + 5, to_mont((depth >> (8 * cb)) & 255u));
+    aux += 6;
+    push_record(dreqs);
   };
   uint32_t pc = body;
   for (;;) {
@@ -143,6 +166,7 @@ __device__ void populate_row(const uint32_t* __restrict__ w, uint32_t body, Func
             st(aux++, v);
           }
           push_require();
+          if (op[4 + op[2]]) push_depth(callee.depth[row]);
         } break;
         case OP_PREIMG: {
           const DevFuncTable& callee = funcs[op[1]];
@@ -153,6 +177,7 @@ __device__ void populate_row(const uint32_t* __restrict__ w, uint32_t body, Func
             st(aux++, v);
           }
           push_require();
+          if (op[4 + op[2]]) push_depth(callee.depth[row]);
         } break;
         case OP_STORE: {
           uint32_t row = *hints++;
@@ -298,6 +323,7 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
     DevFuncTable d{};
     d.args = up(t.args); d.outs = up(t.outs); d.provide = up(t.provide);
     d.req_off = up(t.req_off); d.reqs = up(t.reqs); d.hint_off = up(t.hint_off); d.hints = up(t.hints);
+    d.depth = up(t.depth); d.dreq_off = up(t.dreq_off); d.dreqs = up(t.dreqs);
     d.in = t.in; d.out = t.out; d.rows = (uint32_t)t.rows();
     h_funcs.push_back(d);
   }

@@ -168,6 +168,7 @@ class _Linker:
         self.link: Dict[str, List[int]] = {}
         self.info = info
         self.chips = chips
+        self.partial = False
         self.uniq = 0
 
     def new(self, v: VarRef) -> List[int]:
@@ -236,7 +237,9 @@ def _compile_block(stmts: List[St], pre_ops: List[St], ctx: _Linker) -> Block:
             ops.append(Op("contains", (list(ctx.get(a[0])), ctx.get(a[1])[0])))
         elif k in ("call", "preimg"):
             outs, name, inps = a
-            idx, in_sz, out_sz, _ = ctx.info[name]
+            idx, in_sz, out_sz, callee_partial = ctx.info[name]
+            if callee_partial:   # src/lair/toplevel.rs:640-641
+                assert ctx.partial, "assertion failed: ctx.partial"
             flat = [j for v in inps for j in ctx.get(v)]
             want_in, want_out = (in_sz, out_sz) if k == "call" else (out_sz, in_sz)
             assert len(flat) == want_in, f"Input mismatch on {k} {name}"
@@ -380,6 +383,7 @@ class Toplevel:
         self.funcs: List[Func] = []
         for i, fe in enumerate(funcs_e):
             ctx = _Linker(info, chip_map)
+            ctx.partial = fe.partial
             for v in fe.input_params:
                 ctx.new(v)
             body = _compile_block(fe.body, [], ctx)

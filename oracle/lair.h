@@ -10,7 +10,8 @@
 //   Entrypoint trace   src/lair/lair_chip.rs:112-118
 //   sharding           src/lair/execute.rs:106-111,186-216
 // Pinned by the reference's golden matrices (tests/test_oracle_lair.py cites each one).
-// Not restated (documented gaps): partial funcs / depth provenance (src/lair/provenance.rs).
+//   depth provenance   src/lair/provenance.rs, src/lair/execute.rs:510-512,702-711,751-753,
+//                      src/lair/trace.rs:110-121,235-254, src/gadgets/unsigned/less_than.rs:19-41
 #pragma once
 #include <map>
 #include <memory>
@@ -153,7 +154,6 @@ static inline Toplevel* parse_toplevel(const uint32_t* w, size_t n) {
     f.input_size = w[q++]; f.output_size = w[q++]; f.partial = w[q++]; f.invertible = w[q++];
     f.aux = w[q++]; f.sel = w[q++]; f.max_map = w[q++];
     parse_block(w, q, f.body);
-    if (f.partial) throw std::runtime_error("partial funcs are not restated in the oracle yet");
   }
   return t;
 }
@@ -173,6 +173,8 @@ struct QueryResult {  // src/lair/execute.rs:26-33
   std::vector<Fp> output;
   Record provide;
   std::vector<Record> requires_;
+  uint32_t depth = 0;
+  std::vector<Record> depth_requires;
 };
 struct VecHash {
   size_t operator()(const std::vector<uint32_t>& v) const {
@@ -232,6 +234,8 @@ struct CallerState {
   uint32_t func_index, nonce;
   std::vector<Fp> map;
   std::vector<Record> requires_;
+  bool partial;
+  std::vector<uint32_t> depths;
 };
 
 static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const std::vector<Fp>& args, QueryRecord& q) {
@@ -243,6 +247,8 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
   uint32_t nonce = q.func_queries[func_index].insert(args, first);
   std::vector<Fp> map = args;
   std::vector<Record> requires_;
+  bool partial = top.funcs[entry].partial;
+  std::vector<uint32_t> depths;
   std::vector<ExecEntry> stack;
   std::vector<CallerState> callers;
   auto push_block = [&](const Block& b) {
@@ -251,11 +257,13 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
   };
   auto enter = [&](bool preimg, uint32_t callee, std::vector<Fp> inp) {
     uint32_t callee_nonce = q.func_queries[callee].insert(inp, QueryResult());
-    callers.push_back({preimg, func_index, nonce, std::move(map), std::move(requires_)});
+    callers.push_back({preimg, func_index, nonce, std::move(map), std::move(requires_), partial, std::move(depths)});
     map = std::move(inp);
     requires_.clear();
+    depths.clear();
     func_index = callee;
     nonce = callee_nonce;
+    partial = top.funcs[callee].partial;
     push_block(top.funcs[callee].body);
   };
   push_block(top.funcs[entry].body);
@@ -288,6 +296,7 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
             if (!r.has_output) throw std::runtime_error("Loop detected");
             map.insert(map.end(), r.output.begin(), r.output.end());
             requires_.push_back(r.provide.new_lookup(nonce));
+            if (partial && top.funcs[op.a].partial) depths.push_back(r.depth);
           } else {
             enter(false, op.a, std::move(inp));
           }
@@ -304,6 +313,7 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
             if (!r.has_output) throw std::runtime_error("Loop detected");
             map.insert(map.end(), inp.begin(), inp.end());
             requires_.push_back(r.provide.new_lookup(nonce));
+            if (partial && top.funcs[op.a].partial) depths.push_back(r.depth);
           } else {
             enter(true, op.a, std::move(inp));
           }
@@ -364,19 +374,41 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
         if (r.has_output) throw std::runtime_error("output already set");
         std::vector<Fp> inp = qm.keys[nonce];
         if (top.funcs[func_index].invertible) q.inv_func_queries[func_index][QueryMap::raw(out)] = inp;
+        if (partial) {  // execute.rs:702-711
+          uint32_t depth = 0;
+          for (uint32_t d : depths) depth = std::max(depth, d + 1);
+          auto byte_of = [](uint32_t x, int i) { return (x >> (8 * i)) & 255u; };
+          for (int i = 0; i < 4; i += 2)  // range_check_u8_iter(depth.to_le_bytes()), bytes/mod.rs:97-103
+            r.depth_requires.push_back(
+                q.bytes[(uint16_t)(byte_of(depth, i) | (byte_of(depth, i + 1) << 8))].rec[0].new_lookup(nonce));
+          for (uint32_t dep : depths) {  // LessThanWitness::populate, less_than.rs:19-41
+            if (!(dep < depth)) throw std::runtime_error("depth comparison failed");
+            for (int i = 3; i >= 0; i--)
+              if (byte_of(dep, i) != byte_of(depth, i)) {
+                r.depth_requires.push_back(
+                    q.bytes[(uint16_t)(byte_of(dep, i) | (byte_of(depth, i) << 8))].rec[2].new_lookup(nonce));
+                break;
+              }
+          }
+          r.depth = depth;
+        }
         r.has_output = true;
         r.output = out;
         r.requires_ = std::move(requires_);
         if (!callers.empty()) {
+          bool callee_partial = partial;
           CallerState cs = std::move(callers.back());
           callers.pop_back();
           func_index = cs.func_index;
           nonce = cs.nonce;
           map = std::move(cs.map);
           requires_ = std::move(cs.requires_);
+          partial = cs.partial;
+          depths = std::move(cs.depths);
           const auto& ext = cs.preimg ? inp : out;
           map.insert(map.end(), ext.begin(), ext.end());
           requires_.push_back(r.provide.new_lookup(nonce));
+          if (partial && callee_partial) depths.push_back(r.depth);
         } else {
           if (!stack.empty()) throw std::runtime_error("stack not empty at exit");
           map = out;
@@ -405,6 +437,11 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
   // Toplevel::execute, execute.rs:376-392
   q.public_values = args;
   q.public_values.insert(q.public_values.end(), map.begin(), map.end());
+  if (top.funcs[entry].partial) {
+    uint32_t depth = 0;
+    for (uint32_t d : depths) depth = std::max(depth, d + 1);
+    for (int i = 0; i < 4; i++) q.public_values.push_back(Fp::from_u32((depth >> (8 * i)) & 255u));
+  }
   return map;
 }
 
@@ -431,13 +468,38 @@ struct RowCtx {
   size_t aux_at, width;
   const std::vector<Record>* requires_;
   size_t req_at = 0;
+  const std::vector<Record>* depth_requires = nullptr;
+  size_t dreq_at = 0;
+  uint32_t depth = 0;
   void push_aux(Fp f) { row[aux_at++] = f; }
-  void push_require() {  // Record::into_require, builder.rs:159-168
-    if (req_at >= requires_->size()) throw std::runtime_error("Not enough require hints");
-    Record r = (*requires_)[req_at++];
+  void push_record(Record r) {  // Record::into_require, builder.rs:159-168
     push_aux(Fp::from_u32(r.nonce));
     push_aux(Fp::from_u32(r.count));
     push_aux(fp_inv(Fp::from_u32(r.count) + Fp::one()));
+  }
+  void push_require() {
+    if (req_at >= requires_->size()) throw std::runtime_error("Not enough require hints");
+    push_record((*requires_)[req_at++]);
+  }
+  void push_depth_require() {
+    if (!depth_requires || dreq_at >= depth_requires->size()) throw std::runtime_error("Not enough require hints");
+    push_record((*depth_requires)[dreq_at++]);
+  }
+  void push_depth(uint32_t dep) {  // trace.rs:235-254
+    for (int i = 0; i < 4; i++) push_aux(Fp::from_u32((dep >> (8 * i)) & 255u));
+    Fp wit[6] = {Fp::zero(), Fp::zero(), Fp::zero(), Fp::zero(), Fp::zero(), Fp::zero()};
+    if (!(dep < depth)) throw std::runtime_error("depth comparison failed");
+    for (int i = 3; i >= 0; i--) {
+      uint32_t l = (dep >> (8 * i)) & 255u, r = (depth >> (8 * i)) & 255u;
+      if (l != r) {
+        wit[i] = Fp::one();
+        wit[4] = Fp::from_u32(l);
+        wit[5] = Fp::from_u32(r);
+        break;
+      }
+    }
+    for (Fp x : wit) push_aux(x);
+    push_depth_require();
   }
 };
 
@@ -494,6 +556,7 @@ static inline void populate_block(const Toplevel& top, const QueryRecord& q, con
         if (qi < 0) throw std::runtime_error("Cannot find query result");
         for (Fp o : q.func_queries[op.a].vals[qi].output) { map.push_back(o); cx.push_aux(o); }
         cx.push_require();
+        if (top.funcs[op.a].partial) cx.push_depth(q.func_queries[op.a].vals[qi].depth);
       } break;
       case OP_PREIMG: {
         std::vector<Fp> out;
@@ -502,6 +565,11 @@ static inline void populate_block(const Toplevel& top, const QueryRecord& q, con
         if (it == q.inv_func_queries[op.a].end()) throw std::runtime_error("Cannot find preimage");
         for (Fp i : it->second) { map.push_back(i); cx.push_aux(i); }
         cx.push_require();
+        if (top.funcs[op.a].partial) {
+          long qi = q.func_queries[op.a].find(it->second);
+          if (qi < 0) throw std::runtime_error("Cannot find query result");
+          cx.push_depth(q.func_queries[op.a].vals[qi].depth);
+        }
       } break;
       case OP_STORE: {
         std::vector<Fp> vals;
@@ -539,6 +607,7 @@ static inline void populate_block(const Toplevel& top, const QueryRecord& q, con
   const CtrlNode& c = b.ctrl;
   if (c.kind == CTRL_RETURN) {
     if (cx.req_at != cx.requires_->size()) throw std::runtime_error("unused require hints");
+    if (cx.depth_requires && cx.dreq_at != cx.depth_requires->size()) throw std::runtime_error("unused depth require hints");
     cx.row[cx.width - f.sel + c.ident] = Fp::one();
     return;
   }
@@ -579,6 +648,13 @@ static inline std::vector<Fp> func_trace(const Toplevel& top, const QueryRecord&
       RowCtx cx{row, (size_t)1 + f.input_size + f.output_size, width, &res.requires_};
       cx.push_aux(Fp::from_u32(res.provide.nonce));
       cx.push_aux(Fp::from_u32(res.provide.count));
+      if (f.partial) {  // trace.rs:110-121
+        cx.depth_requires = &res.depth_requires;
+        cx.depth = res.depth;
+        for (int b = 0; b < 4; b++) cx.push_aux(Fp::from_u32((res.depth >> (8 * b)) & 255u));
+        cx.push_depth_require();
+        cx.push_depth_require();
+      }
       std::vector<Fp> map(args);
       populate_block(top, q, f, f.body, map, cx);
     } catch (std::exception& e) {

@@ -167,3 +167,33 @@ def hash_toplevel():
         ret("d"),
     ])
     return Toplevel([commit_cons, cons_chain, env_chain, h3, h4, h5], chips)
+
+
+def partial_toplevel():
+    """Partial funcs (depth provenance, src/lair/provenance.rs; `partial fn` in src/lair/macros.rs:14-47):
+    every row carries its call depth as 4 range-checked bytes, every call to a partial func proves
+    callee depth < own depth with a LessThanWitness (src/gadgets/unsigned/less_than.rs).
+      pfib(n)      partial fib: depth(n) = n - 1, so n > 257 exercises multi-byte depth comparisons
+      pdouble(x)   invertible partial;  phalf(y) = preimg pdouble(y)
+      pmain(n, x)  calls all of them (a total helper `twice` in between is allowed: partial -> total)"""
+    from lurk_b200.lair import preimg
+    pfib = func("pfib", ["n"], 1, [
+        const("one", 1),
+        match("n", [((0, 1), [ret("one")])]),
+        sub("n1", "n", "one"),
+        call(["a"], "pfib", ["n1"]),
+        sub("n2", "n1", "one"),
+        call(["b"], "pfib", ["n2"]),
+        add("r", "a", "b"),
+        ret("r"),
+    ], partial=True)
+    twice = func("twice", ["x"], 1, [add("y", "x", "x"), ret("y")])
+    pdouble = func("pdouble", ["x"], 1, [call(["y"], "twice", ["x"]), ret("y")], invertible=True, partial=True)
+    phalf = func("phalf", ["y"], 1, [preimg(["x"], "pdouble", ["y"]), ret("x")], partial=True)
+    pmain = func("pmain", ["n", "x"], 2, [
+        call(["f"], "pfib", ["n"]),
+        call(["d"], "pdouble", ["x"]),
+        call(["h"], "phalf", ["d"]),
+        ret("f", "h"),
+    ], partial=True)
+    return Toplevel.new_pure([pmain, pfib, twice, pdouble, phalf])

@@ -144,6 +144,15 @@ def test_hasher_chip_programs_prove_bit_exact(oracle, fname, args):
     assert om.verify(proof.words), om.last_error
 
 
+@pytest.mark.parametrize("fname,args,ss", [("pfib", [12], 1 << 22), ("pmain", [300, 21], 1 << 22), ("pmain", [700, 5], 256)])
+def test_partial_func_programs_prove_bit_exact(oracle, fname, args, ss):
+    # depth provenance on the GPU: depth bytes + LessThanWitness in the trace kernel, byte less-than lookups
+    top = goldens.toplevel_for("partial")
+    m, om, q, proof, want = _prove_both(oracle, top, fname, [args], shard_size=ss)
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+
+
 def test_cons_chain_2pow12_verifies(oracle):
     # Lurk-shaped load: the 655-wide hash4 chip dominates (2^12 x 655 main trace); acceptance by the verifier
     top = goldens.toplevel_for("hash")

@@ -93,3 +93,16 @@ def test_hash_chip_trace_matches_oracle(oracle):
         b = rec.execute(0, pre, 8)
         assert np.array_equal(a, b)
     assert np.array_equal(chip.generate_trace(Shard.new(q)), rec.func_trace(0))
+
+
+def test_partial_func_traces_match_oracle(oracle):
+    # src/lair/trace.rs:110-121,235-254: depth bytes, require triples of the range checks, per-call
+    # callee depth + LessThanWitness + byte-lookup require; Bytes chip gains less-than records
+    top = goldens.toplevel_for("partial")
+    q = QueryRecord.new(top)
+    execute_by_name(top, "pmain", [600, 9], q)
+    rec = _oracle_rec(oracle, top, "pmain", [600, 9])
+    for name in ("pmain", "pfib", "twice", "pdouble", "phalf"):
+        chip = FuncChip.from_name(name, top)
+        assert np.array_equal(chip.generate_trace(Shard.new(q)), rec.func_trace(chip.func.index)), name
+    assert np.array_equal(BytesChip().generate_trace(Shard.new(q)), rec.bytes_trace(0))

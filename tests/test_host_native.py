@@ -55,6 +55,33 @@ def test_executor_matches_oracle(oracle, case):
     assert q.num_queries(f.index) <= golden.shape[0]
 
 
+def test_partial_funcs_depth_provenance(oracle):
+    # src/lair/execute.rs:387-389,510-512,702-711: depth = 1 + max over partial callees, public values
+    # gain the depth's 4 little-endian bytes; the native executor and the oracle agree
+    top = goldens.toplevel_for("partial")
+    f = top.func_by_name("pmain")
+    q = QueryRecord.new(top)
+    got = execute_by_name(top, "pmain", [300, 21], q)
+    ot = oracle.OracleToplevel(top.serialize())
+    orec = oracle.OracleRecord(ot)
+    want = orec.execute(f.index, [300, 21], 2)
+    assert np.array_equal(got, want) and int(got[1]) == 21
+    pv = q.expect_public_values()
+    assert np.array_equal(pv, orec.public_values())
+    assert list(pv[-4:]) == [300 & 255, 300 >> 8, 0, 0]       # pfib(300) has depth 299
+    for fi in range(top.num_funcs()):
+        assert q.num_queries(fi) == orec.num_queries(fi)
+
+
+def test_total_func_may_not_call_partial():
+    # src/lair/execute.rs:1005-1023 (nonpartial_calls_partial: "assertion failed: ctx.partial")
+    from lurk_b200.lair import Toplevel, call, func, ret
+    foo = func("foo", ["a"], 1, [ret("a")], partial=True)
+    bar = func("bar", ["a"], 1, [call(["b"], "foo", ["a"]), ret("b")])
+    with pytest.raises(AssertionError, match="ctx.partial"):
+        Toplevel.new_pure([foo, bar])
+
+
 def test_executor_fib_100000():
     # src/lair/execute.rs:826-834
     top = demo_toplevel()

@@ -87,6 +87,22 @@ def test_hasher_air_shape():
         assert len(c.sends) == 1 and len(c.receives) == 1
 
 
+@pytest.mark.parametrize("fname,args", [("pfib", [12]), ("pmain", [300, 21])])
+def test_partial_funcs_prove_verify(oracle, fname, args):
+    # depth provenance: eval_depth + LessThanWitness::assert_less_than + byte less-than lookups
+    # (src/lair/air.rs:105-131,210-224, src/gadgets/unsigned/less_than.rs:49-103); pmain's depth 300 needs
+    # a second byte, so the comparison limb moves
+    top = goldens.toplevel_for("partial")
+    ot, om, f = oracle_machine(oracle, top, fname)
+    rec = oracle.OracleRecord(ot)
+    rec.execute(f.index, args, f.output_size)
+    proof = om.prove(rec)
+    assert om.verify(proof), om.last_error
+    bad = proof.copy()
+    bad[len(bad) // 2] = (int(bad[len(bad) // 2]) + 1) % P
+    assert not om.verify(bad)
+
+
 def test_multi_shard_roundtrip(oracle):
     # sharding tested with tiny shards as in src/air/debug.rs:119-158; cross-shard lookups must cancel
     top = goldens.toplevel_for("ackermann")

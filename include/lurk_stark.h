@@ -32,6 +32,7 @@ typedef struct lsk_ctx lsk_ctx;
 typedef struct lsk_program lsk_program;   /* a loaded Toplevel (src/lair/toplevel.rs:25-56) */
 typedef struct lsk_record lsk_record;     /* a flattened QueryRecord (src/lair/execute.rs:67-75) */
 typedef struct lsk_machine lsk_machine;   /* StarkMachine + pk/vk (src/core/stark_machine.rs:20-30) */
+typedef struct lsk_vk lsk_vk;             /* verifying key + chip vector: all `machine.verify` needs */
 
 const char* lsk_last_error(void);
 int lsk_version(void);
@@ -126,6 +127,16 @@ int lsk_machine_prep_commit(const lsk_machine* m, uint32_t out8[8]);
  * malloc'd proof (canonical u32 words, layout in DESIGN.md), free with lsk_proof_free. */
 int lsk_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard_size, uint32_t** words, size_t* len);
 void lsk_proof_free(uint32_t* words);
+/* machine.verify(&vk, &proof, &mut challenger): src/core/cli/repl.rs:186,198, src/core/cli/meta.rs:928-932,
+ * src/lair/lair_chip.rs:273-275, tests/fib.rs:96.  Host code (the reference verifies on the CPU too);
+ * LSK_OK = accepted, LSK_ERR_VERIFY = rejected with the reason in lsk_last_error().  lsk_vk_* is the
+ * same verifier without a machine / device: `blob` as for lsk_machine_new, `prep_commit` from
+ * lsk_machine_prep_commit (canonical), has_prep = whether any chip has a preprocessed trace. */
+int lsk_verify(const lsk_machine* m, const uint32_t* words, size_t len);
+int lsk_vk_new(const uint32_t* blob, size_t n, const uint32_t prep_commit[8], int has_prep, uint32_t num_queries,
+               uint32_t pow_bits, lsk_vk** out);
+void lsk_vk_free(lsk_vk* vk);
+int lsk_vk_verify(const lsk_vk* vk, const uint32_t* words, size_t len);
 /* host<->device bytes moved by the last lsk_prove / lsk_shard_* sequence */
 size_t lsk_machine_last_h2d_bytes(const lsk_machine* m);
 size_t lsk_machine_last_d2h_bytes(const lsk_machine* m);

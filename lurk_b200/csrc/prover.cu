@@ -24,6 +24,7 @@
 #include "ntt.cuh"
 #include "stark_kernels.cuh"
 #include "trace.cuh"
+#include "verify.h"
 
 namespace lsk {
 
@@ -660,6 +661,21 @@ int lsk_machine_prep_commit(const lsk_machine* m, uint32_t out8[8]) {
   LSK_API_BEGIN
   if (!m || !out8) fail(LSK_ERR_ARG, "null argument");
   memcpy(out8, m->prep_commit, 32);
+  return LSK_OK;
+  LSK_API_END
+}
+
+int lsk_verify(const lsk_machine* m, const uint32_t* words, size_t len) {
+  LSK_API_BEGIN
+  if (!m || !words) fail(LSK_ERR_ARG, "null argument");
+  VerifyingKey vk;
+  vk.chips = m->chips;
+  vk.num_pv = m->num_pv;
+  for (int k = 0; k < 8; k++) vk.prep_commit[k] = to_mont(m->prep_commit[k]);
+  vk.has_prep = m->prep_chip >= 0;
+  vk.num_queries = m->num_queries;
+  vk.pow_bits = m->pow_bits;
+  verify_proof(vk, words, len);
   return LSK_OK;
   LSK_API_END
 }

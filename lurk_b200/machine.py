@@ -60,6 +60,45 @@ class VerifyingKey:
     pc_start: int = 0      # LairMachineProgram::pc_start, src/lair/lair_chip.rs:71-77
 
 
+class VerificationError(Exception):
+    """machine.verify(...) returned Err: the reason is the message."""
+
+
+class Verifier:
+    """`machine.verify` without a machine or a GPU (the reference verifies on the CPU): the chip vector
+    of `entry`, the preprocessed commitment from `setup`, and the FRI parameters.  Host code in
+    liblurkstark (csrc/verify.cu); never touches a device."""
+
+    def __init__(self, toplevel: Toplevel, entry: str, vk: VerifyingKey, opts: Optional[SphinxCoreOpts] = None,
+                 blob: Optional[np.ndarray] = None):
+        opts = opts or SphinxCoreOpts.default()
+        if blob is None:
+            chip = FuncChip.from_name(entry, toplevel)
+            f = chip.func
+            num_pv = f.input_size + f.output_size + (DEPTH_W if f.partial else 0)
+            blob = serialize_machine(build_chip_vector(chip), num_pv)
+        self.blob = N.u32(blob)
+        self.h = ctypes.c_void_p()
+        commit = N.u32(vk.commit)
+        N.check(N.lib().lsk_vk_new(N.vp(self.blob), ctypes.c_size_t(len(self.blob)), N.vp(commit), 1,
+                                   opts.num_queries, opts.proof_of_work_bits, ctypes.byref(self.h)))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                N.lib().lsk_vk_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def verify(self, proof) -> None:
+        words = N.u32(proof.words if isinstance(proof, MachineProof) else proof)
+        rc = N.lib().lsk_vk_verify(self.h, N.vp(words), ctypes.c_size_t(len(words)))
+        if rc == -4:
+            raise VerificationError(N.lib().lsk_last_error().decode())
+        N.check(rc)
+
+
 class LairMachineProgram:
     pass
 
@@ -109,6 +148,17 @@ class StarkMachine:
         words = np.ctypeslib.as_array(out, shape=(n.value,)).copy()
         N.lib().lsk_proof_free(out)
         return MachineProof(words)
+
+    def verify(self, vk: VerifyingKey, proof: MachineProof, challenger=None) -> None:
+        """machine.verify(&vk, &proof, &mut challenger) (src/core/cli/repl.rs:186,198): raises
+        VerificationError when the proof is rejected."""
+        if not np.array_equal(N.u32(vk.commit), self.setup()[1].commit):
+            raise VerificationError("verifying key does not belong to this machine")
+        words = N.u32(proof.words if isinstance(proof, MachineProof) else proof)
+        rc = N.lib().lsk_verify(self.h, N.vp(words), ctypes.c_size_t(len(words)))
+        if rc == -4:
+            raise VerificationError(N.lib().lsk_last_error().decode())
+        N.check(rc)
 
     def last_transfer_bytes(self):
         return N.lib().lsk_machine_last_h2d_bytes(self.h), N.lib().lsk_machine_last_d2h_bytes(self.h)

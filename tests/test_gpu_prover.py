@@ -165,6 +165,7 @@ def test_cons_chain_2pow12_verifies(oracle):
     ot = oracle.OracleToplevel(top.serialize())
     om = oracle.OracleMachine(ot, m.entry.index, m.blob, 10, 8)
     assert om.verify(proof.words), om.last_error
+    m.verify(vk, proof)
 
 
 def test_multi_shard_proof_is_bit_exact(oracle):
@@ -194,3 +195,10 @@ def test_large_fib_proof_verifies(oracle):
     ot = oracle.OracleToplevel(top.serialize())
     om = oracle.OracleMachine(ot, m.entry.index, m.blob, 20, 12)
     assert om.verify(proof.words), om.last_error
+    # machine.verify (the product's own host verifier, csrc/verify.cu) agrees, also on a tampered proof
+    from lurk_b200.machine import VerificationError
+    m.verify(vk, proof)
+    bad = proof.words.copy()
+    bad[len(bad) // 2] = (int(bad[len(bad) // 2]) + 1) % P
+    with pytest.raises(VerificationError):
+        m.verify(vk, bad)

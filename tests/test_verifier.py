@@ -1,0 +1,72 @@
+"""The product verifier (lurk_b200/csrc/verify.cu behind lsk_vk_verify / lsk_verify; machine.verify,
+src/core/cli/repl.rs:186,198) against proofs of the CPU oracle prover: it is independent code (the
+oracle's own verifier lives in oracle/stark_prove.h), needs no GPU, must accept every honest proof and
+reject every tampered one, for every kind of chip the machine has."""
+import numpy as np
+import pytest
+
+import goldens
+from lurk_b200.machine import SphinxCoreOpts, VerificationError, Verifier, VerifyingKey
+from test_oracle_stark import kat2_args, oracle_machine
+
+P = 2013265921
+OPTS = SphinxCoreOpts(num_queries=6, proof_of_work_bits=6)
+
+
+def _proof(oracle, tname, fname, args, shard_size=None):
+    top = goldens.toplevel_for(tname)
+    ot, om, f = oracle_machine(oracle, top, fname)
+    rec = oracle.OracleRecord(ot)
+    rec.execute(f.index, args, f.output_size)
+    proof = om.prove(rec, shard_size) if shard_size else om.prove(rec)
+    v = Verifier(top, fname, VerifyingKey(om.prep_commit()), OPTS)
+    return om, v, proof
+
+
+@pytest.mark.parametrize("tname,fname,args,ss", [
+    ("demo", "fib", [100], None),
+    ("demo", "factorial", [5], None),
+    ("range", "range_test", [100, 12, 64], None),
+    ("memory", "test", [], None),
+    ("match_many", "match_many", [1, 0], None),
+    ("ackermann", "ackermann", [2, 30], 64),        # 3 shards
+    ("hash", "commit_cons", kat2_args(), None),     # hasher chips
+    ("partial", "pmain", [300, 21], None),          # depth provenance
+])
+def test_verifier_accepts_honest_and_rejects_tampered(oracle, tname, fname, args, ss):
+    om, v, proof = _proof(oracle, tname, fname, args, ss)
+    v.verify(proof)
+    rng = np.random.default_rng(len(proof))
+    positions = [2, 12, 30, len(proof) // 3, len(proof) // 2, len(proof) - 5] + list(rng.integers(2, len(proof), 12))
+    for pos in positions:
+        bad = proof.copy()
+        bad[pos] = (int(bad[pos]) + 1) % P
+        with pytest.raises(VerificationError):
+            v.verify(bad)
+        assert not om.verify(bad)       # the two verifiers agree
+    with pytest.raises(VerificationError):
+        v.verify(proof[:-1])
+    with pytest.raises(VerificationError):
+        v.verify(np.concatenate([proof, [0]]).astype(np.uint32))
+
+
+def test_verifier_rejects_wrong_key_and_wrong_parameters(oracle):
+    om, v, proof = _proof(oracle, "demo", "fib", [20])
+    top = goldens.toplevel_for("demo")
+    bad_commit = om.prep_commit().copy()
+    bad_commit[0] ^= 1
+    with pytest.raises(VerificationError):
+        Verifier(top, "fib", VerifyingKey(bad_commit), OPTS).verify(proof)
+    with pytest.raises(VerificationError):
+        Verifier(top, "fib", VerifyingKey(om.prep_commit()), SphinxCoreOpts(7, 6)).verify(proof)
+    with pytest.raises(VerificationError):      # another entry point: different Entrypoint chip
+        Verifier(top, "factorial", VerifyingKey(om.prep_commit()), OPTS).verify(proof)
+
+
+def test_verifier_rejects_swapped_shards(oracle):
+    om, v, proof = _proof(oracle, "ackermann", "ackermann", [2, 30], 64)
+    assert int(proof[1]) == 3
+    fewer = proof.copy()
+    fewer[1] = 2
+    with pytest.raises(VerificationError):
+        v.verify(fewer)

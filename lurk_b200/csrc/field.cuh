@@ -45,9 +45,12 @@ LSK_HD uint32_t mont_reduce(uint64_t x) {
 #endif
 }
 // Integer multiplies issue on the half-rate "fmaheavy" pipe only (measured on B200: IMAD.lo 64,
-// IMAD.HI 32, IMAD.WIDE ~26 lanes/clk/SM), so a Montgomery product costs ~11 pipe cycles per warp
-// and that pipe, not HBM, bounds every hashing kernel; corrections use the min() forms so they stay
-// 1-2 instructions on the full-rate ALU pipe.
+// IMAD.HI 32, IMAD.WIDE ~26 lanes/clk/SM), so a Montgomery product costs ~11 pipe cycles per warp;
+// corrections use the min() forms (one fused VIADDMNMX).  Additions are not free either: ptxas emits
+// about half of the plain adds as IMAD.IADD on that same pipe and the rest on the ALU pipe, and
+// forcing all of them onto the ALU pipe (three-input IADD3 with an opaque zero) made the hashing
+// kernels 3 % SLOWER on B200 -- the ALU pipe is then the bound.  The two integer pipes together,
+// ~19 k pipe-cycles per width-16 permutation per warp, are the roofline of every hashing kernel.
 LSK_HD uint32_t fmul(uint32_t a, uint32_t b) { return mont_reduce((uint64_t)a * b); }
 LSK_HD uint32_t fadd(uint32_t a, uint32_t b) {
   uint32_t s = a + b;

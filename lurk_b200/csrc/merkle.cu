@@ -7,6 +7,7 @@
 // integer pipes (one width-16 permutation ~ 750 modmuls per 32 B absorbed), not by HBM.
 #include <algorithm>
 
+#include "fri.cuh"
 #include "merkle.cuh"
 #include "poseidon2.cuh"
 
@@ -61,6 +62,98 @@ LSK_D void merkle_digest(const uint32_t* const* __restrict__ cols, uint32_t ncol
   }
 }
 
+// ---- 16 lanes per permutation ------------------------------------------------------------------------
+// A permutation computed by one thread takes ~10 us end to end (measured: every extra level of a
+// single-CTA tree tail costs that much), so the last levels of every tree -- too few nodes to fill
+// the machine -- are latency-bound.  There a half-warp shares one permutation, one state word per
+// lane: an S-box round is 4 dependent products instead of 64 interleaved ones, the external layer
+// is 5 shuffles (circ(2,3,1,1) inside each 4-lane group, then the column sums over the 4 groups),
+// and in the partial rounds every lane recomputes the S-box of word 0 (no broadcast) while the sum
+// of the other 15 words is carried incrementally (rest' = sum_i d_i s_i + 15 * sum), its butterfly
+// running under the next round's S-box chain.  ~5x lower latency for ~1.4x the multiplies.
+static __device__ uint32_t g_coop16[10 * 16];  // [r][lane]: full-round constants r = 0..7, diag (plain), diag (Shoup)
+struct Coop16 {
+  uint32_t rc[8], d, dsh;
+};
+LSK_D Coop16 coop16_load(unsigned lane) {
+  Coop16 k;
+#pragma unroll
+  for (int r = 0; r < 8; r++) k.rc[r] = g_coop16[r * 16 + (lane & 15)];
+  k.d = g_coop16[8 * 16 + (lane & 15)];
+  k.dsh = g_coop16[9 * 16 + (lane & 15)];
+  return k;
+}
+LSK_D uint32_t coop16_sum(uint32_t v) {  // sum over the 16 lanes of this half-warp, in every lane
+#pragma unroll
+  for (int d = 1; d < 16; d <<= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
+  return v;
+}
+LSK_D uint32_t coop16_linear(uint32_t x, unsigned lane) {
+  uint32_t t = fadd(x, __shfl_xor_sync(0xffffffffu, x, 1));
+  t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 2));
+  uint32_t nxt = __shfl_sync(0xffffffffu, x, (lane & ~3u) | ((lane + 1) & 3u));
+  uint32_t y = fadd(fadd(t, x), fdbl(nxt));  // row j of circ(2,3,1,1): sum + x_j + 2 x_{j+1}
+  uint32_t c = fadd(y, __shfl_xor_sync(0xffffffffu, y, 4));
+  c = fadd(c, __shfl_xor_sync(0xffffffffu, c, 8));
+  return fadd(y, c);
+}
+LSK_D uint32_t sbox7(uint32_t x) {
+  uint32_t x3 = fmul(fsqr(x), x);
+  return fmul(x, fsqr(x3));
+}
+LSK_D uint32_t coop16_permute(uint32_t s, const Coop16& k, unsigned lane) {
+  const P2Const<16>& c = p2c<16>();
+  const bool first = (lane & 15) == 0;
+  s = coop16_linear(s, lane);
+#pragma unroll
+  for (int r = 0; r < 4; r++) s = coop16_linear(sbox7(fadd(s, k.rc[r])), lane);
+  uint32_t s0 = __shfl_sync(0xffffffffu, s, lane & 16u);
+  uint32_t rest = coop16_sum(first ? 0u : s);
+#pragma unroll 1
+  for (int q = 0; q < P2Rounds<16>::RP; q++) {
+    uint32_t m = first ? 0u : fmul_shoup(s, k.d, k.dsh);
+    uint32_t dsum = coop16_sum(m);
+    uint32_t s0n = sbox7(fadd(s0, c.part_rc[q]));
+    uint32_t sum = fadd(s0n, rest);
+    s0 = fadd(fmul_shoup(s0n, c.diag[0], c.diag_shoup[0]), sum);
+    s = first ? s0 : fadd(m, sum);
+    uint32_t s2 = fdbl(sum), s4 = fdbl(s2), s8 = fdbl(s4);
+    rest = fadd(dsum, fsub(fdbl(s8), sum));
+  }
+#pragma unroll
+  for (int r = 4; r < 8; r++) s = coop16_linear(sbox7(fadd(s, k.rc[r])), lane);
+  return s;
+}
+// merkle_digest with the state spread over a half-warp: the lane's state word after the last
+// permutation (lanes 0..7 of the half hold the digest).  All 32 lanes of the warp must call it with
+// the same ncols / packed / children-ness.
+LSK_D uint32_t merkle_digest_coop(const uint32_t* const* __restrict__ cols, uint32_t ncols, size_t r,
+                                  const uint32_t* __restrict__ packed_row, const uint32_t* __restrict__ children,
+                                  const Coop16& k, unsigned lane) {
+  const unsigned g = lane & 15;
+  const uint32_t nabs = packed_row ? 1u : (ncols + 7) / 8;
+  const uint32_t total = nabs + (children ? (nabs ? 2u : 1u) : 0u);
+  uint32_t s = 0, rd = 0;
+#pragma unroll 1
+  for (uint32_t step = 0; step < total; step++) {
+    if (step < nabs) {
+      if (packed_row) {
+        if (g < 8) s = packed_row[g];
+      } else if (g < 8 && step * 8 + g < ncols) {
+        s = cols[step * 8 + g][r];
+      }
+    } else if (step == nabs) {
+      rd = s;
+      s = children[g];
+    } else {
+      uint32_t t = __shfl_sync(0xffffffffu, rd, (lane & 16u) | (g & 7u));
+      if (g >= 8) s = t;
+    }
+    s = coop16_permute(s, k, lane);
+  }
+  return s;
+}
+
 // One launch builds up to ST_LEVELS + 1 layers: a CTA takes 2 * ST_THREADS consecutive nodes of
 // layer l0 (in the leaf modes it first hashes them from the matrices) and reduces them to one node
 // of layer l0 + ST_LEVELS; intermediate digests go straight to their layers in global memory (they
@@ -68,6 +161,7 @@ LSK_D void merkle_digest(const uint32_t* const* __restrict__ cols, uint32_t ncol
 // commitment is 3 launches instead of 22, and the sequential tail of a tree costs one launch.
 constexpr int ST_THREADS = 256;
 constexpr unsigned ST_LEVELS = 9;  // log2(2 * ST_THREADS)
+constexpr uint32_t COOP_MAX = 64;  // levels of a CTA with at most this many nodes use 16 lanes per permutation
 struct SubtreeArgs {
   uint32_t* nodes;
   const uint32_t* const* cols;
@@ -76,25 +170,102 @@ struct SubtreeArgs {
   uint32_t off[ST_LEVELS + 1];           // digest offsets of layers l0 .. l0 + levels
   uint32_t inj_first[ST_LEVELS + 1];     // column-list range of the height group of layer l0 + k
   uint32_t inj_ncols[ST_LEVELS + 1];     // (k = 0: the leaf group in LEAF mode)
+  FriChallenge fc;                       // set on the launch that produces a FRI layer's root
 };
 enum { ST_NODES = 0, ST_LEAVES = 1, ST_FRI_LEAVES = 2 };
+
+// levels first_k .. levels of the subtree whose 2^log_in inputs start at node in0 of the input layer
+template <int MODE>
+LSK_D void subtree_build(uint32_t* __restrict__ nodes, const uint32_t* const* __restrict__ cols,
+                         const uint32_t* __restrict__ fri_vals, uint32_t levels, uint32_t log_in,
+                         const uint32_t* __restrict__ off, const uint32_t* __restrict__ inj_first,
+                         const uint32_t* __restrict__ inj_ncols, size_t in0, const Coop16& ck) {
+  const uint32_t nin = 1u << log_in;
+  const unsigned lane = threadIdx.x & 31;
+#pragma unroll 1
+  for (uint32_t k = (MODE == ST_NODES ? 1u : 0u); k <= levels; k++) {
+    const uint32_t cnt = nin >> k;
+    uint32_t* layer = nodes + (size_t)off[k] * 8;
+    const uint32_t* prev = k ? nodes + (size_t)off[k - 1] * 8 : nullptr;
+    const bool packed = MODE == ST_FRI_LEAVES && k == 0;
+    const uint32_t ncols = packed || !inj_ncols ? 0u : inj_ncols[k];
+    const uint32_t* const* gcols = inj_first ? cols + inj_first[k] : cols;
+    if (cnt <= COOP_MAX) {
+      // whole warps loop together (the permutation shuffles): slots past cnt recompute the last node
+#pragma unroll 1
+      for (uint32_t t0 = (threadIdx.x >> 5) * 2; t0 < cnt; t0 += ST_THREADS / 16) {
+        const uint32_t t = t0 + (lane >> 4);
+        const size_t i = (in0 >> k) + (t < cnt ? t : cnt - 1);
+        uint32_t s = merkle_digest_coop(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr,
+                                        k ? prev + 16 * i : nullptr, ck, lane);
+        if (t < cnt && (lane & 15) < 8) layer[i * 8 + (lane & 15)] = s;
+      }
+    } else {
+#pragma unroll 1
+      for (uint32_t t = threadIdx.x; t < cnt; t += ST_THREADS) {
+        const size_t i = (in0 >> k) + t;
+        uint32_t st[16];
+        merkle_digest(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr, k ? prev + 16 * i : nullptr, st);
+        store_digest(layer + i * 8, st);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// The FRI commit phase's transcript step, on the device (one warp): observe the layer's root, sample
+// the folding challenge.  DuplexChallenger<.., 16, 8> with an empty input buffer (it always is here:
+// the previous operation was a sample): state[0..8) = root, permute, beta = the last four of the
+// first eight output words, popped from the back (challenger.h::sample_ext).
+LSK_D void fri_challenge(const FriChallenge& fc, const uint32_t* __restrict__ root, const Coop16& ck) {
+  const unsigned lane = threadIdx.x & 31, g = lane & 15;
+  uint32_t s = g < 8 ? root[g] : fc.chal[g];
+  s = coop16_permute(s, ck, lane);
+  if (lane < 16) {
+    fc.chal[g] = s;
+    if (g >= 4 && g < 8) fc.beta_out->c[7 - g] = s;
+    if (g < 8) fc.root_out[g] = root[g];
+  }
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(ST_THREADS) merkle_subtree_kernel(SubtreeArgs a) {
-  const size_t in0 = (size_t)blockIdx.x << a.log_in;
-  const uint32_t nin = 1u << a.log_in;
+  const Coop16 ck = coop16_load(threadIdx.x & 31);
+  subtree_build<MODE>(a.nodes, a.cols, a.fri_vals, a.levels, a.log_in, a.off, a.inj_first, a.inj_ncols,
+                      (size_t)blockIdx.x << a.log_in, ck);
+  if (a.fc.chal && blockIdx.x == 0 && threadIdx.x < 32) fri_challenge(a.fc, a.nodes + (size_t)a.off[a.levels] * 8, ck);
+}
+
+// The small end of the FRI commit phase in ONE launch of one CTA: for every remaining layer, hash
+// the leaves (row i = values 2i, 2i+1), build the tree, run the transcript step, fold into the next
+// layer's vector.  Replaces ~2 launches + a device->host round trip per layer.
+struct FriTailArgs {
+  uint32_t nlayers, first_lfh;            // layers of 2^first_lfh, 2^(first_lfh-1), ..., 2 rows
+  Ext* vals[FRI_TAIL_LOG + 2];            // vals[j]: input of layer j; vals[nlayers]: the final 2 values
+  uint32_t* nodes[FRI_TAIL_LOG + 1];
+  const Ext* add[FRI_TAIL_LOG + 1];       // reduced openings joining the folded vector of layer j (or null)
+  uint32_t ginv[FRI_TAIL_LOG + 1];        // 1 / w_{2^(lfh+1)}
+  uint32_t one_half;
+  FriChallenge fc;                        // beta_out / root_out: slot of the first tail layer
+};
+__global__ void __launch_bounds__(ST_THREADS) fri_tail_kernel(FriTailArgs a) {
+  const Coop16 ck = coop16_load(threadIdx.x & 31);
+  __shared__ uint32_t off[ST_LEVELS + 1];
 #pragma unroll 1
-  for (uint32_t k = (MODE == ST_NODES ? 1u : 0u); k <= a.levels; k++) {
-    const uint32_t cnt = nin >> k;
-    uint32_t* layer = a.nodes + (size_t)a.off[k] * 8;
-    const uint32_t* prev = k ? a.nodes + (size_t)a.off[k - 1] * 8 : nullptr;
-    const bool packed = MODE == ST_FRI_LEAVES && k == 0;
-#pragma unroll 1
-    for (uint32_t t = threadIdx.x; t < cnt; t += ST_THREADS) {
-      const size_t i = (in0 >> k) + t;
-      uint32_t st[16];
-      merkle_digest(a.cols + a.inj_first[k], packed ? 0u : a.inj_ncols[k], i, packed ? a.fri_vals + i * 8 : nullptr,
-                    k ? prev + 16 * i : nullptr, st);
-      store_digest(layer + i * 8, st);
+  for (uint32_t j = 0; j < a.nlayers; j++) {
+    const uint32_t lfh = a.first_lfh - j;
+    if (threadIdx.x <= lfh) off[threadIdx.x] = (2u << lfh) - (2u << (lfh - threadIdx.x));
+    __syncthreads();
+    subtree_build<ST_FRI_LEAVES>(a.nodes[j], nullptr, (const uint32_t*)a.vals[j], lfh, lfh, off, nullptr, nullptr, 0, ck);
+    FriChallenge fc{a.fc.chal, a.fc.beta_out + j, a.fc.root_out + 8 * j};
+    if (threadIdx.x < 32) fri_challenge(fc, a.nodes[j] + (size_t)off[lfh] * 8, ck);
+    __syncthreads();
+    const Ext beta = *fc.beta_out;
+    const Ext half_beta = emul_base(beta, a.one_half);
+    for (uint32_t i = threadIdx.x; i < (1u << lfh); i += ST_THREADS) {
+      Ext v = fri_fold_pair(a.vals[j][2 * i], a.vals[j][2 * i + 1], half_beta, a.one_half, a.ginv[j], i, lfh);
+      if (a.add[j]) v = eadd(v, a.add[j][i]);
+      a.vals[j + 1][i] = v;
     }
     __syncthreads();
   }
@@ -116,7 +287,16 @@ __global__ void __launch_bounds__(MK_BLOCK) merkle_flat_kernel(const uint32_t* c
   store_digest(out + i * 8, st);
 }
 
-void init_merkle_kernels() { LSK_CUDA(p2_upload_constants()); }
+void init_merkle_kernels() {
+  LSK_CUDA(p2_upload_constants());
+  uint32_t h[10 * 16];
+  for (int i = 0; i < 16; i++) {
+    for (int r = 0; r < 8; r++) h[r * 16 + i] = to_mont(P2_FULL_RC_16[r * 16 + i]);
+    h[8 * 16 + i] = P2_DIAG_16[i] % P;
+    h[9 * 16 + i] = shoup_precompute(P2_DIAG_16[i] % P);
+  }
+  LSK_CUDA(cudaMemcpyToSymbol(g_coop16, h, sizeof h));
+}
 
 static void layout_layers(lsk_ctx* ctx, MerkleTreeDev& tree) {
   tree.layer_off.resize(tree.log_max + 1);
@@ -131,7 +311,7 @@ static void layout_layers(lsk_ctx* ctx, MerkleTreeDev& tree) {
 
 // groups: per layer l (0..log_max) the column-list range injected there (layer 0 = leaves)
 static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std::pair<uint32_t, uint32_t>>& groups,
-                       int leaf_mode, const uint32_t* fri_vals) {
+                       int leaf_mode, const uint32_t* fri_vals, FriChallenge fc = {}) {
   cudaStream_t st = ctx->stream;
   unsigned l0 = 0;
   bool first = true;
@@ -180,6 +360,7 @@ static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std:
     }
     unsigned grid = 1u << (log_nodes - log_in);
     int mode = first ? leaf_mode : ST_NODES;
+    if (l0 + a.levels == tree.log_max) a.fc = fc;  // this launch produces the root
     ProfScope ps(ctx, PT_MERKLE_TOP, 1, bytes);
     if (mode == ST_LEAVES) merkle_subtree_kernel<ST_LEAVES><<<grid, ST_THREADS, 0, st>>>(a);
     else if (mode == ST_FRI_LEAVES) merkle_subtree_kernel<ST_FRI_LEAVES><<<grid, ST_THREADS, 0, st>>>(a);
@@ -215,7 +396,8 @@ void merkle_commit_dev(lsk_ctx* ctx, const std::vector<MatRef>& mats, MerkleTree
   build_tree(ctx, tree, groups, ST_LEAVES, nullptr);
 }
 
-void merkle_commit_fri_layer_dev(lsk_ctx* ctx, const uint32_t* vals, unsigned log_rows, MerkleTreeDev& tree) {
+void merkle_commit_fri_layer_dev(lsk_ctx* ctx, const uint32_t* vals, unsigned log_rows, MerkleTreeDev& tree,
+                                 FriChallenge fc) {
   tree.mats.clear();
   tree.mats.push_back(MatRef{vals, 0, log_rows, 8});
   tree.log_max = log_rows;
@@ -224,7 +406,36 @@ void merkle_commit_fri_layer_dev(lsk_ctx* ctx, const uint32_t* vals, unsigned lo
   tree.colptrs.upload(&none, 1);
   layout_layers(ctx, tree);
   std::vector<std::pair<uint32_t, uint32_t>> groups(log_rows + 1, {0u, 0u});
-  build_tree(ctx, tree, groups, ST_FRI_LEAVES, vals);
+  build_tree(ctx, tree, groups, ST_FRI_LEAVES, vals, fc);
+}
+
+void fri_commit_tail_dev(lsk_ctx* ctx, unsigned first_lfh, Ext* const* vals, MerkleTreeDev* trees, const Ext* const* add,
+                         FriChallenge fc) {
+  if (first_lfh < 1 || first_lfh > FRI_TAIL_LOG) fail(LSK_ERR_ARG, "bad FRI tail height");
+  FriTailArgs a{};
+  a.nlayers = first_lfh;
+  a.first_lfh = first_lfh;
+  a.one_half = finv(to_mont(2));
+  a.fc = fc;
+  double bytes = 0;
+  for (unsigned j = 0; j < first_lfh; j++) {
+    unsigned lfh = first_lfh - j;
+    MerkleTreeDev& t = trees[j];
+    t.mats.clear();
+    t.mats.push_back(MatRef{(const uint32_t*)vals[j], 0, lfh, 8});
+    t.log_max = lfh;
+    t.colptrs.release();
+    layout_layers(ctx, t);
+    a.vals[j] = vals[j];
+    a.nodes[j] = t.nodes.p;
+    a.add[j] = add[j];
+    a.ginv[j] = finv(two_adic_generator(lfh + 1));
+    bytes += (double)((size_t)1 << lfh) * (32.0 + 32.0 + 64.0);
+  }
+  a.vals[first_lfh] = vals[first_lfh];
+  ProfScope ps(ctx, PT_MERKLE_TOP, 1, bytes);
+  fri_tail_kernel<<<1, ST_THREADS, 0, ctx->stream>>>(a);
+  LSK_CUDA(cudaGetLastError());
 }
 
 void merkle_root_host(lsk_ctx* ctx, const MerkleTreeDev& tree, uint32_t out8[8]) {

@@ -473,24 +473,48 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   }
 
   pt.mark("reduce openings");
-  // ---- FRI commit phase
+  // ---- FRI commit phase: the transcript step (observe root, sample beta) runs on the device, so the
+  // layers are queued back to back; the host reads all roots once at the end and replays them
   const unsigned nlayers = log_max - LOG_BLOWUP;
   std::vector<DevBuf<Ext>> fri_vals(nlayers + 1);
   std::vector<MerkleTreeDev> fri_trees(nlayers);
   std::vector<std::array<uint32_t, 8>> fri_roots(nlayers);
   fri_vals[0] = std::move(ro[log_max]);
+  if (!ch.in.empty()) fail(LSK_ERR_EXEC, "transcript input buffer not empty before the FRI commit phase");
+  DevBuf<uint32_t> d_chal(ctx, 16), d_roots(ctx, 8 * (size_t)nlayers);
+  DevBuf<Ext> d_betas(ctx, nlayers);
+  d_chal.upload(ch.state, 16);
   for (unsigned li = 0; li < nlayers; li++) {
     unsigned lfh = log_max - 1 - li;  // log height of the folded vector = rows of this layer's matrix
-    merkle_commit_fri_layer_dev(ctx, (const uint32_t*)fri_vals[li].p, lfh, fri_trees[li]);
-    merkle_root_host(ctx, fri_trees[li], fri_roots[li].data());
-    for (int k = 0; k < 8; k++) ch.observe(to_mont(fri_roots[li][k]));
-    Ext beta = ch.sample_ext();
+    FriChallenge fc{d_chal.p, d_betas.p + li, d_roots.p + 8 * (size_t)li};
+    if (lfh <= FRI_TAIL_LOG) {  // the remaining layers in one launch
+      std::vector<Ext*> vals;
+      std::vector<const Ext*> add;
+      for (unsigned j = 0; j <= lfh; j++) {
+        if (j) fri_vals[li + j].alloc(ctx, (size_t)2 << (lfh - j));
+        vals.push_back(fri_vals[li + j].p);
+        if (j < lfh) add.push_back(ro[lfh - j].p);
+      }
+      fri_commit_tail_dev(ctx, lfh, vals.data(), &fri_trees[li], add.data(), fc);
+      break;
+    }
+    merkle_commit_fri_layer_dev(ctx, (const uint32_t*)fri_vals[li].p, lfh, fri_trees[li], fc);
     fri_vals[li + 1].alloc(ctx, (size_t)1 << lfh);
-    fri_fold_dev(ctx, fri_vals[li].p, lfh, beta, ro[lfh].p, fri_vals[li + 1].p);
+    fri_fold_dev(ctx, fri_vals[li].p, lfh, d_betas.p + li, ro[lfh].p, fri_vals[li + 1].p);
   }
   Ext fin[2];
+  std::vector<uint32_t> h_roots(8 * (size_t)nlayers);
   fri_vals[nlayers].download(fin, 2);
+  d_roots.download(h_roots.data(), h_roots.size());
   LSK_CUDA(cudaStreamSynchronize(st));
+  for (unsigned li = 0; li < nlayers; li++) {
+    for (int k = 0; k < 8; k++) {
+      ch.observe(h_roots[8 * li + k]);
+      fri_roots[li][k] = from_mont(h_roots[8 * li + k]);
+    }
+    ch.sample_ext();  // the beta the device already used
+  }
+  m.last_d2h += h_roots.size() * 4 + sizeof fin;
   if (!ext_eq(fin[0], fin[1])) fail(LSK_ERR_EXEC, "FRI final polynomial is not constant (prover bug)");
   Ext final_poly = fin[0];
   ch.observe(final_poly);

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <vector>
 
+#include "fri.cuh"
 #include "poseidon2.cuh"
 #include "stark_kernels.cuh"
 
@@ -390,23 +391,21 @@ void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats
 }
 
 __global__ void __launch_bounds__(256) fri_fold_kernel(const Ext* __restrict__ cur, unsigned logh, uint32_t ginv,
-                                                        uint32_t one_half, Ext half_beta, const Ext* __restrict__ add,
-                                                        Ext* __restrict__ out) {
+                                                        uint32_t one_half, const Ext* __restrict__ beta,
+                                                        const Ext* __restrict__ add, Ext* __restrict__ out) {
   size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >> logh) return;
-  Ext a = cur[2 * i], b = cur[2 * i + 1];
-  Ext t = emul_base(half_beta, fpow(ginv, bitrev32((uint32_t)i, logh)));
-  // (1/2 + t) a + (1/2 - t) b = (a + b)/2 + t (a - b)
-  Ext v = eadd(emul_base(eadd(a, b), one_half), emul(t, esub(a, b)));
+  Ext half_beta = emul_base(*beta, one_half);
+  Ext v = fri_fold_pair(cur[2 * i], cur[2 * i + 1], half_beta, one_half, ginv, (uint32_t)i, logh);
   if (add) v = eadd(v, add[i]);
   out[i] = v;
 }
-void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, Ext beta, const Ext* add, Ext* out) {
+void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, const Ext* beta_dev, const Ext* add, Ext* out) {
   size_t half = (size_t)1 << logh;
   uint32_t one_half = finv(to_mont(2));
   ProfScope ps(ctx, PT_FRI_FOLD, 1, (double)half * (48.0 + (add ? 16.0 : 0.0)));
   fri_fold_kernel<<<div_up(half, 256), 256, 0, ctx->stream>>>(cur, logh, finv(two_adic_generator(logh + 1)), one_half,
-                                                              emul_base(beta, one_half), add, out);
+                                                              beta_dev, add, out);
   LSK_CUDA(cudaGetLastError());
 }
 
@@ -435,8 +434,9 @@ uint32_t grind_dev(lsk_ctx* ctx, const uint32_t state[16], const uint32_t* pendi
   gs.pos = n_pending;
   gs.mask = (1u << bits) - 1;
   DevBuf<uint32_t> best(ctx, 1);
-  const uint32_t batch = 1u << 20;
-  for (uint64_t base = 0; base < P; base += batch) {
+  // the expected smallest witness is ~2^bits: start with a batch of that order, then widen
+  uint32_t batch = std::max(1u << 14, std::min(1u << 20, 4u << bits));
+  for (uint64_t base = 0; base < P; base += batch, batch = std::min(1u << 22, batch * 4)) {
     uint32_t h = 0xffffffffu;
     best.upload(&h, 1);
     ProfScope ps(ctx, PT_GRIND, 1, 0.0);

@@ -63,7 +63,8 @@ struct ReduceMat {  // one opened matrix of LDE height 2^lh
 void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats, unsigned lh, Ext zeta,
                          const Ext* alpha_pows_dev, Ext* ro, double algorithmic_bytes);
 // out[i] = (1/2 + t) cur[2i] + (1/2 - t) cur[2i+1] (+ add[i]),  t = beta / (2 * w_{2^(logh+1)}^bitrev(i))
-void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, Ext beta, const Ext* add, Ext* out);
+// beta is read from device memory (written by the device-side transcript step, merkle.cuh::FriChallenge)
+void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, const Ext* beta_dev, const Ext* add, Ext* out);
 // smallest witness w such that the duplex challenger, after observing w, samples `bits` zero bits.
 // state: 16 canonical words; pending: the challenger's input buffer (n_pending < 8 canonical words)
 uint32_t grind_dev(lsk_ctx* ctx, const uint32_t state[16], const uint32_t* pending, unsigned n_pending, unsigned bits);

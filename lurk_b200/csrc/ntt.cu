@@ -6,14 +6,17 @@
 // permutation pass.  For N <= 2^12 one CTA does the whole column in shared memory.  Larger N is
 // split Bailey-style at bit 12, N = 2^12 * 2^t:
 //   K1  DIT stages 1..12 on contiguous 4096-blocks                      (4R + 4W bytes / element)
-//   K2  per group of C consecutive low indices: inter-pass twiddle, DIT over the 2^t blocks ->
-//       coefficients (kept in registers), then for both cosets: scale, DIF over the blocks,
+//   K2  per group of 2^c consecutive low indices: inter-pass twiddle, DIT over the 2^t blocks ->
+//       coefficients (shared memory), then for both cosets: scale, DIF over the blocks,
 //       inter-pass twiddle, store                                        (4R + 8W)
 //   K3  DIF stages 12..1 on contiguous 4096-blocks of both cosets        (8R + 8W)
 // i.e. 36 B of HBM traffic per input element against the 12 B algorithmic minimum (4 read, 8
-// written), and ~3*logn/2 modmuls per element: at B200's ~5 instructions per HBM byte the
-// butterflies, not HBM, bound this stage.  Small stage twiddles w_{2^s}^k are read from a 16 KB
-// level-packed table (L1-resident); they do not depend on N.
+// written).  Butterflies run radix-16 in REGISTERS: a thread owns the 16 elements that differ in four
+// index bits, does four stages without touching memory, and the 4096-element tile is re-dealt
+// through (padded) shared memory between such passes -- 3 passes and 2 barriers for 12 stages
+// instead of 12 shared-memory round trips.  Twiddles are (w, floor(w 2^32 / p)) pairs so every
+// twiddle product is a Shoup multiplication (3 multiply-pipe instructions on constants instead of
+// the 3 + 2 of a Montgomery product); the level-packed table w_{2^s}^k is 32 KB and L1-resident.
 #include <map>
 #include <memory>
 #include <vector>
@@ -27,29 +30,34 @@ constexpr unsigned LOG_BLOCK = 12;
 constexpr unsigned BLOCK_ELEMS = 1u << LOG_BLOCK;
 
 // level-packed twiddles: tw[2^(s-1) + k] = w_{2^s}^(+-k), k < 2^(s-1), s = 1..12  (index 0 unused)
+// every table entry is a Shoup pair {c, floor(c * 2^32 / p)} of a plain residue c
 struct NttTables {
-  DevBuf<uint32_t> tw_fwd, tw_inv;
+  DevBuf<uint2> tw_fwd, tw_inv;
   struct Big {  // per logn > 12
-    DevBuf<uint32_t> lo_f, hi_f, lo_i, hi_i;  // W_N^(+-x), x < 4096; W_N^(+-4096 y), y < N / 4096
+    DevBuf<uint2> lo_f, hi_f, lo_i, hi_i;  // W_N^(+-x), x < 4096; W_N^(+-4096 y), y < N / 4096
   };
   struct Scale {  // per (logn, kind): a[j][lo] = s_j^lo / N (lo < min(N, 4096)); b[j][k2] = s_j^(4096 k2)
-    DevBuf<uint32_t> a, b;
+    DevBuf<uint2> a, b;
   };
   std::map<unsigned, std::unique_ptr<Big>> big;
   std::map<std::pair<unsigned, int>, std::unique_ptr<Scale>> scale;
 };
 
-static std::vector<uint32_t> powers(uint32_t base, size_t n, uint32_t first = R1) {
-  std::vector<uint32_t> v(n);
+static std::vector<uint2> powers(uint32_t base, size_t n, uint32_t first = R1) {  // Montgomery in, Shoup pairs out
+  std::vector<uint2> v(n);
   uint32_t p = first;
-  for (size_t i = 0; i < n; i++) v[i] = p, p = fmul(p, base);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t c = from_mont(p);
+    v[i] = make_uint2(c, shoup_precompute(c));
+    p = fmul(p, base);
+  }
   return v;
 }
 
 static NttTables* tables(lsk_ctx* ctx) {
   if (!ctx->ntt_tables) {
     auto* t = new NttTables;
-    std::vector<uint32_t> f(BLOCK_ELEMS, 0), inv(BLOCK_ELEMS, 0);
+    std::vector<uint2> f(BLOCK_ELEMS, make_uint2(0, 0)), inv(BLOCK_ELEMS, make_uint2(0, 0));
     for (unsigned s = 1; s <= LOG_BLOCK; s++) {
       uint32_t w = two_adic_generator(s), wi = finv(w);
       auto pf = powers(w, (size_t)1 << (s - 1)), pi = powers(wi, (size_t)1 << (s - 1));
@@ -99,7 +107,7 @@ static NttTables::Scale* scale_tables(lsk_ctx* ctx, unsigned logn, LdeShift kind
   uint32_t ninv = finv(to_mont((uint32_t)1 << logn));
   size_t na = (size_t)1 << (logn < LOG_BLOCK ? logn : LOG_BLOCK);
   size_t nb = logn > LOG_BLOCK ? (size_t)1 << (logn - LOG_BLOCK) : 1;
-  std::vector<uint32_t> a, b;
+  std::vector<uint2> a, b;
   for (int j = 0; j < 2; j++) {
     auto pa = powers(s[j], na, ninv);
     auto pb = powers(fpow(s[j], BLOCK_ELEMS), nb);
@@ -112,48 +120,75 @@ static NttTables::Scale* scale_tables(lsk_ctx* ctx, unsigned logn, LdeShift kind
   return (t->scale[key] = std::move(sc)).get();
 }
 
-// ---- shared-memory butterfly stages ---------------------------------------------------------------
-// The tile holds 2^t "rows" of 2^c consecutive elements (element (q, j) at s[(q << c) | j]); the
-// transform runs over q.  c = 0 is a plain contiguous transform.
-LSK_D void dit_stages(uint32_t* s, unsigned t, unsigned c, const uint32_t* __restrict__ tw) {
-  const unsigned half_tile = 1u << (t + c - 1);
+// ---- radix-2^R butterflies in registers ----------------------------------------------------------------
+// x[jj] is the element whose index is (high << (s0 + R)) | (jj << s0) | low; stages s0+1 .. s0+R of a
+// transform only pair elements inside such a group.  tw: level-packed table, w_{2^s}^(+-k) at 2^(s-1) + k.
+LSK_D uint32_t shoup(uint32_t a, uint2 c) { return fmul_shoup(a, c.x, c.y); }
+template <int R>
+LSK_D void dit_local(uint32_t (&x)[1 << R], unsigned s0, unsigned low, const uint2* __restrict__ tw) {
+#pragma unroll
+  for (int u = 1; u <= R; u++) {
+    const unsigned h = 1u << (u - 1), H = 1u << (s0 + u - 1);
+#pragma unroll
+    for (unsigned b = 0; b < (1u << (R - 1)); b++) {
+      const unsigned kl = b & (h - 1);
+      const unsigned j0 = ((b >> (u - 1)) << u) | kl, j1 = j0 + h;
+      uint32_t v = shoup(x[j1], __ldg(tw + H + low + (kl << s0)));
+      uint32_t a = x[j0];
+      x[j0] = fadd(a, v);
+      x[j1] = fsub(a, v);
+    }
+  }
+}
+template <int R>
+LSK_D void dif_local(uint32_t (&x)[1 << R], unsigned s0, unsigned low, const uint2* __restrict__ tw) {
+#pragma unroll
+  for (int u = R; u >= 1; u--) {
+    const unsigned h = 1u << (u - 1), H = 1u << (s0 + u - 1);
+#pragma unroll
+    for (unsigned b = 0; b < (1u << (R - 1)); b++) {
+      const unsigned kl = b & (h - 1);
+      const unsigned j0 = ((b >> (u - 1)) << u) | kl, j1 = j0 + h;
+      uint32_t a = x[j0], c = x[j1];
+      x[j0] = fadd(a, c);
+      x[j1] = shoup(fsub(a, c), __ldg(tw + H + low + (kl << s0)));
+    }
+  }
+}
+
+// ---- N <= 4096: whole column in one CTA (small chips; launch-latency bound) -----------------------------
+LSK_D void dit_stages(uint32_t* s, unsigned t, const uint2* __restrict__ tw) {
+  const unsigned half_tile = 1u << (t - 1);
   for (unsigned st = 1; st <= t; st++) {
     const unsigned h = 1u << (st - 1);
-    for (unsigned b = threadIdx.x; b < half_tile; b += blockDim.x) {
-      unsigned j = b & ((1u << c) - 1), p = b >> c;
+    for (unsigned p = threadIdx.x; p < half_tile; p += blockDim.x) {
       unsigned k = p & (h - 1);
-      unsigned q0 = ((p >> (st - 1)) << st) | k;
-      unsigned i0 = (q0 << c) | j, i1 = i0 + (h << c);
-      uint32_t u = s[i0], v = fmul(s[i1], __ldg(tw + h + k));
+      unsigned i0 = ((p >> (st - 1)) << st) | k, i1 = i0 + h;
+      uint32_t u = s[i0], v = shoup(s[i1], __ldg(tw + h + k));
       s[i0] = fadd(u, v);
       s[i1] = fsub(u, v);
     }
     __syncthreads();
   }
 }
-LSK_D void dif_stages(uint32_t* s, unsigned t, unsigned c, const uint32_t* __restrict__ tw) {
-  const unsigned half_tile = 1u << (t + c - 1);
+LSK_D void dif_stages(uint32_t* s, unsigned t, const uint2* __restrict__ tw) {
+  const unsigned half_tile = 1u << (t - 1);
   for (unsigned st = t; st >= 1; st--) {
     const unsigned h = 1u << (st - 1);
-    for (unsigned b = threadIdx.x; b < half_tile; b += blockDim.x) {
-      unsigned j = b & ((1u << c) - 1), p = b >> c;
+    for (unsigned p = threadIdx.x; p < half_tile; p += blockDim.x) {
       unsigned k = p & (h - 1);
-      unsigned q0 = ((p >> (st - 1)) << st) | k;
-      unsigned i0 = (q0 << c) | j, i1 = i0 + (h << c);
+      unsigned i0 = ((p >> (st - 1)) << st) | k, i1 = i0 + h;
       uint32_t u = s[i0], v = s[i1];
       s[i0] = fadd(u, v);
-      s[i1] = fmul(fsub(u, v), __ldg(tw + h + k));
+      s[i1] = shoup(fsub(u, v), __ldg(tw + h + k));
     }
     __syncthreads();
   }
 }
-
-// ---- N <= 4096: whole column in one CTA -------------------------------------------------------------
 __global__ void __launch_bounds__(1024) lde_small_kernel(const uint32_t* __restrict__ in, size_t in_stride,
                                                           uint32_t* __restrict__ out, size_t out_stride, unsigned logn,
-                                                          const uint32_t* __restrict__ tw_fwd,
-                                                          const uint32_t* __restrict__ tw_inv,
-                                                          const uint32_t* __restrict__ scale_a) {
+                                                          const uint2* __restrict__ tw_fwd, const uint2* __restrict__ tw_inv,
+                                                          const uint2* __restrict__ scale_a) {
   extern __shared__ uint32_t smem[];
   const unsigned n = 1u << logn;
   uint32_t* coef = smem;
@@ -162,102 +197,182 @@ __global__ void __launch_bounds__(1024) lde_small_kernel(const uint32_t* __restr
   uint32_t* dst = out + (size_t)blockIdx.x * out_stride;
   for (unsigned i = threadIdx.x; i < n; i += blockDim.x) coef[i] = src[i];
   __syncthreads();
-  if (logn) dit_stages(coef, logn, 0, tw_inv);
+  if (logn) dit_stages(coef, logn, tw_inv);
   for (int j = 0; j < 2; j++) {
-    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) work[i] = fmul(coef[i], __ldg(scale_a + j * n + i));
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) work[i] = shoup(coef[i], __ldg(scale_a + j * n + i));
     __syncthreads();
-    if (logn) dif_stages(work, logn, 0, tw_fwd);
+    if (logn) dif_stages(work, logn, tw_fwd);
     for (unsigned i = threadIdx.x; i < n; i += blockDim.x) dst[(size_t)j * n + i] = work[i];
     __syncthreads();
   }
 }
 
 // ---- N > 4096 ---------------------------------------------------------------------------------------
+// 4096-element tile, 256 threads x 16 registers.  Shared-memory index of element i is i + (i >> 4) (one
+// pad word per 16) so that both "16 consecutive per thread" and "stride 16 / 256 per thread" are
+// conflict-free.
+constexpr int K13_THREADS = 256;
+constexpr unsigned K13_SMEM = BLOCK_ELEMS + BLOCK_ELEMS / 16;
+LSK_D unsigned pad16(unsigned i) { return i + (i >> 4); }
+
 // K1: DIT stages 1..12 on each contiguous 4096-block; in (N per column) -> out rows [0, N)
-__global__ void __launch_bounds__(1024) lde_k1_kernel(const uint32_t* __restrict__ in, size_t in_stride,
-                                                       uint32_t* __restrict__ out, size_t out_stride,
-                                                       const uint32_t* __restrict__ tw_inv) {
-  __shared__ uint32_t s[BLOCK_ELEMS];
+__global__ void __launch_bounds__(K13_THREADS) lde_k1_kernel(const uint32_t* __restrict__ in, size_t in_stride,
+                                                              uint32_t* __restrict__ out, size_t out_stride,
+                                                              const uint2* __restrict__ tw_inv) {
+  __shared__ uint32_t s[K13_SMEM];
   const uint32_t* src = in + (size_t)blockIdx.y * in_stride + (size_t)blockIdx.x * BLOCK_ELEMS;
   uint32_t* dst = out + (size_t)blockIdx.y * out_stride + (size_t)blockIdx.x * BLOCK_ELEMS;
-  for (unsigned i = threadIdx.x; i < BLOCK_ELEMS / 4; i += blockDim.x)
-    reinterpret_cast<uint4*>(s)[i] = reinterpret_cast<const uint4*>(src)[i];
-  __syncthreads();
-  dit_stages(s, LOG_BLOCK, 0, tw_inv);
-  for (unsigned i = threadIdx.x; i < BLOCK_ELEMS / 4; i += blockDim.x)
-    reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(s)[i];
-}
-
-// K2: the middle pass.  EPT elements per thread; tile = EPT * 1024 = 2^t blocks x 2^c low indices.
-template <int EPT>
-__global__ void __launch_bounds__(1024) lde_k2_kernel(uint32_t* __restrict__ out, size_t out_stride, unsigned logn,
-                                                       unsigned c, const uint32_t* __restrict__ tw_fwd,
-                                                       const uint32_t* __restrict__ tw_inv,
-                                                       const uint32_t* __restrict__ lo_f, const uint32_t* __restrict__ hi_f,
-                                                       const uint32_t* __restrict__ lo_i, const uint32_t* __restrict__ hi_i,
-                                                       const uint32_t* __restrict__ scale_a,
-                                                       const uint32_t* __restrict__ scale_b) {
-  extern __shared__ uint32_t smem[];
-  const unsigned t = logn - LOG_BLOCK;
-  const unsigned cmask = (1u << c) - 1;
-  const unsigned lo_base = blockIdx.x << c;
-  const size_t n = (size_t)1 << logn;
-  uint32_t* col = out + (size_t)blockIdx.y * out_stride;
-  uint32_t keep[EPT];
-  // load + inverse inter-pass twiddle W_N^(-bitrev_t(q) * lo)
+  const unsigned t = threadIdx.x, hi = t >> 4, lo = t & 15;
+  uint32_t x[16];
 #pragma unroll
-  for (int r = 0; r < EPT; r++) {
-    unsigned e = threadIdx.x + r * 1024;
-    unsigned q = e >> c, lo = lo_base + (e & cmask);
-    unsigned ex = bitrev32(q, t) * lo;
-    uint32_t w = fmul(__ldg(lo_i + (ex & (BLOCK_ELEMS - 1))), __ldg(hi_i + (ex >> LOG_BLOCK)));
-    smem[e] = fmul(col[((size_t)q << LOG_BLOCK) | lo], w);
+  for (int k = 0; k < 4; k++) {  // elements 16 t .. 16 t + 15: index bits 0-3 in registers
+    uint4 v = reinterpret_cast<const uint4*>(src)[t * 4 + k];
+    x[4 * k] = v.x; x[4 * k + 1] = v.y; x[4 * k + 2] = v.z; x[4 * k + 3] = v.w;
   }
+  dit_local<4>(x, 0, 0, tw_inv);
+#pragma unroll
+  for (int j = 0; j < 16; j++) s[pad16(t * 16 + j)] = x[j];
   __syncthreads();
-  dit_stages(smem, t, c, tw_inv);
 #pragma unroll
-  for (int r = 0; r < EPT; r++) keep[r] = smem[threadIdx.x + r * 1024];
-  for (int j = 0; j < 2; j++) {
-    const uint32_t* sa = scale_a + j * BLOCK_ELEMS;
-    const uint32_t* sb = scale_b + ((size_t)j << t);
-    __syncthreads();
+  for (int j = 0; j < 16; j++) x[j] = s[pad16(hi * 256 + j * 16 + lo)];  // bits 4-7 in registers
+  dit_local<4>(x, 4, lo, tw_inv);
 #pragma unroll
-    for (int r = 0; r < EPT; r++) {
-      unsigned e = threadIdx.x + r * 1024;
-      unsigned q = e >> c, lo = lo_base + (e & cmask);
-      smem[e] = fmul(keep[r], fmul(__ldg(sa + lo), __ldg(sb + q)));
-    }
-    __syncthreads();
-    dif_stages(smem, t, c, tw_fwd);
+  for (int j = 0; j < 16; j++) s[pad16(hi * 256 + j * 16 + lo)] = x[j];
+  __syncthreads();
 #pragma unroll
-    for (int r = 0; r < EPT; r++) {
-      unsigned e = threadIdx.x + r * 1024;
-      unsigned q = e >> c, lo = lo_base + (e & cmask);
-      unsigned ex = bitrev32(q, t) * lo;
-      uint32_t w = fmul(__ldg(lo_f + (ex & (BLOCK_ELEMS - 1))), __ldg(hi_f + (ex >> LOG_BLOCK)));
-      col[(size_t)j * n + (((size_t)q << LOG_BLOCK) | lo)] = fmul(smem[e], w);
-    }
-  }
+  for (int j = 0; j < 16; j++) x[j] = s[pad16(j * 256 + t)];             // bits 8-11 in registers
+  dit_local<4>(x, 8, t, tw_inv);
+#pragma unroll
+  for (int j = 0; j < 16; j++) dst[j * 256 + t] = x[j];
 }
 
 // K3: DIF stages 12..1 in place on each contiguous 4096-block of the 2N outputs
-__global__ void __launch_bounds__(1024) lde_k3_kernel(uint32_t* __restrict__ out, size_t out_stride,
-                                                       const uint32_t* __restrict__ tw_fwd) {
-  __shared__ uint32_t s[BLOCK_ELEMS];
+__global__ void __launch_bounds__(K13_THREADS) lde_k3_kernel(uint32_t* __restrict__ out, size_t out_stride,
+                                                              const uint2* __restrict__ tw_fwd) {
+  __shared__ uint32_t s[K13_SMEM];
   uint32_t* p = out + (size_t)blockIdx.y * out_stride + (size_t)blockIdx.x * BLOCK_ELEMS;
-  for (unsigned i = threadIdx.x; i < BLOCK_ELEMS / 4; i += blockDim.x)
-    reinterpret_cast<uint4*>(s)[i] = reinterpret_cast<const uint4*>(p)[i];
+  const unsigned t = threadIdx.x, hi = t >> 4, lo = t & 15;
+  uint32_t x[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) x[j] = p[j * 256 + t];
+  dif_local<4>(x, 8, t, tw_fwd);
+#pragma unroll
+  for (int j = 0; j < 16; j++) s[pad16(j * 256 + t)] = x[j];
   __syncthreads();
-  dif_stages(s, LOG_BLOCK, 0, tw_fwd);
-  for (unsigned i = threadIdx.x; i < BLOCK_ELEMS / 4; i += blockDim.x)
-    reinterpret_cast<uint4*>(p)[i] = reinterpret_cast<const uint4*>(s)[i];
+#pragma unroll
+  for (int j = 0; j < 16; j++) x[j] = s[pad16(hi * 256 + j * 16 + lo)];
+  dif_local<4>(x, 4, lo, tw_fwd);
+#pragma unroll
+  for (int j = 0; j < 16; j++) s[pad16(hi * 256 + j * 16 + lo)] = x[j];
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; j++) x[j] = s[pad16(t * 16 + j)];
+  dif_local<4>(x, 0, 0, tw_fwd);
+#pragma unroll
+  for (int k = 0; k < 4; k++)
+    reinterpret_cast<uint4*>(p)[t * 4 + k] = make_uint4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+}
+
+// K2: the middle pass over a tile of 2^t blocks (q) x 2^c consecutive low indices (lo), element (q, lo)
+// at shared index (q << c) | lo.  The size-2^t transforms over q run as ceil(t/4) register passes of
+// 2^r (r <= 4) elements each; the first DIT pass reads global memory (applying the inverse inter-pass
+// twiddle W_N^(-bitrev_t(q) * lo)), the last DIF pass of each coset writes it (forward twiddle).
+struct K2Args {
+  uint32_t* out;
+  size_t out_stride;
+  unsigned logn, c;
+  const uint2 *tw_fwd, *tw_inv, *lo_f, *hi_f, *lo_i, *hi_i, *scale_a, *scale_b;
+};
+enum { K2_GLOBAL = 0, K2_COEF = 1, K2_WORK = 2 };
+template <int R, bool DIF>
+LSK_D void k2_pass(const K2Args& a, uint32_t* __restrict__ col, uint32_t* __restrict__ coef, uint32_t* __restrict__ work,
+                   unsigned t, unsigned s0, int src, int dst, int coset) {
+  const unsigned c = a.c, cmask = (1u << c) - 1, lo_base = blockIdx.x << c;
+  const unsigned nitems = 1u << (t - R + c);
+  const size_t n = (size_t)1 << a.logn;
+  for (unsigned it = threadIdx.x; it < nitems; it += blockDim.x) {
+    const unsigned lo = it & cmask, rest = it >> c;
+    const unsigned ql = rest & ((1u << s0) - 1), qh = rest >> s0;
+    const unsigned qbase = (qh << (s0 + R)) | ql, glo = lo_base + lo;
+    uint32_t x[1 << R];
+    if (src == K2_GLOBAL) {
+#pragma unroll
+      for (int jj = 0; jj < (1 << R); jj++) {
+        const unsigned q = qbase | (jj << s0);
+        const unsigned ex = bitrev32(q, t) * glo;
+        uint32_t v = col[((size_t)q << LOG_BLOCK) | glo];
+        x[jj] = shoup(shoup(v, __ldg(a.lo_i + (ex & (BLOCK_ELEMS - 1)))), __ldg(a.hi_i + (ex >> LOG_BLOCK)));
+      }
+    } else if (src == K2_COEF && DIF) {  // first DIF pass of a coset: coefficient m = q * 4096 + lo times s_j^m / N
+      const uint2 sa = __ldg(a.scale_a + coset * BLOCK_ELEMS + glo);
+#pragma unroll
+      for (int jj = 0; jj < (1 << R); jj++) {
+        const unsigned q = qbase | (jj << s0);
+        x[jj] = shoup(shoup(coef[(q << c) | lo], sa), __ldg(a.scale_b + ((size_t)coset << t) + q));
+      }
+    } else {
+      const uint32_t* sp = src == K2_COEF ? coef : work;
+#pragma unroll
+      for (int jj = 0; jj < (1 << R); jj++) x[jj] = sp[((qbase | (jj << s0)) << c) | lo];
+    }
+    if (DIF) dif_local<R>(x, s0, ql, a.tw_fwd);
+    else dit_local<R>(x, s0, ql, a.tw_inv);
+    if (dst == K2_GLOBAL) {
+#pragma unroll
+      for (int jj = 0; jj < (1 << R); jj++) {
+        const unsigned q = qbase | (jj << s0);
+        const unsigned ex = bitrev32(q, t) * glo;
+        uint32_t v = shoup(shoup(x[jj], __ldg(a.lo_f + (ex & (BLOCK_ELEMS - 1)))), __ldg(a.hi_f + (ex >> LOG_BLOCK)));
+        col[(size_t)coset * n + (((size_t)q << LOG_BLOCK) | glo)] = v;
+      }
+    } else {
+      uint32_t* dp = dst == K2_COEF ? coef : work;
+#pragma unroll
+      for (int jj = 0; jj < (1 << R); jj++) dp[((qbase | (jj << s0)) << c) | lo] = x[jj];
+    }
+  }
+}
+template <bool DIF>
+LSK_D void k2_pass_r(unsigned r, const K2Args& a, uint32_t* col, uint32_t* coef, uint32_t* work, unsigned t, unsigned s0,
+                     int src, int dst, int coset) {
+  switch (r) {
+    case 1: k2_pass<1, DIF>(a, col, coef, work, t, s0, src, dst, coset); break;
+    case 2: k2_pass<2, DIF>(a, col, coef, work, t, s0, src, dst, coset); break;
+    case 3: k2_pass<3, DIF>(a, col, coef, work, t, s0, src, dst, coset); break;
+    default: k2_pass<4, DIF>(a, col, coef, work, t, s0, src, dst, coset); break;
+  }
+}
+template <int NT>
+__global__ void __launch_bounds__(NT, 768 / NT > 0 ? 768 / NT : 1) lde_k2_kernel(K2Args a) {
+  extern __shared__ uint32_t smem[];
+  const unsigned t = a.logn - LOG_BLOCK;
+  uint32_t* coef = smem;
+  uint32_t* work = smem + ((size_t)1 << (t + a.c));
+  uint32_t* col = a.out + (size_t)blockIdx.y * a.out_stride;
+  // pass plan: ceil(t / 4) passes, sizes as even as possible (t = 10 -> 4, 3, 3)
+  const unsigned np = (t + 3) / 4, base = t / np, rem = t % np;
+  unsigned s0 = 0;
+  for (unsigned p = 0; p < np; p++) {  // DIT: stages 1 .. t
+    const unsigned r = base + (p < rem ? 1u : 0u);
+    k2_pass_r<false>(r, a, col, coef, work, t, s0, p == 0 ? K2_GLOBAL : K2_COEF, K2_COEF, 0);
+    s0 += r;
+    __syncthreads();
+  }
+  for (int coset = 0; coset < 2; coset++) {  // DIF: stages t .. 1
+    unsigned top = t;
+    for (unsigned p = np; p-- > 0;) {
+      const unsigned r = base + (p < rem ? 1u : 0u);
+      top -= r;
+      k2_pass_r<true>(r, a, col, coef, work, t, top, p == np - 1 ? K2_COEF : K2_WORK, p == 0 ? K2_GLOBAL : K2_WORK, coset);
+      __syncthreads();
+    }
+  }
 }
 
 void init_ntt_kernels() {
-  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 1024 * 4));
-  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 1024 * 4));
-  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 1024 * 4));
-  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 * 1024 * 4));
+  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
+  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
+  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
 }
 
 void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, size_t out_stride, unsigned logn,
@@ -283,30 +398,25 @@ void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, 
   const double cells = (double)((size_t)1 << logn) * ncols;
   {
     ProfScope ps(ctx, PT_LDE_K1, 1, 8.0 * cells);
-    lde_k1_kernel<<<dim3(blocks, ncols), 1024, 0, st>>>(in, in_stride, out, out_stride, t->tw_inv.p);
+    lde_k1_kernel<<<dim3(blocks, ncols), K13_THREADS, 0, st>>>(in, in_stride, out, out_stride, t->tw_inv.p);
   }
-  // tile = max(4096, 2^t * 16) elements, except 2^t * 8 for t >= 11
-  unsigned log_tile = tt <= 8 ? 12 : (tt <= 10 ? tt + 4 : tt + 3);
+  // tile = 2^t blocks x 2^c low indices = 2^12 .. 2^14 elements (c = 4 up to t = 10, then 3, 2), two
+  // copies in shared memory (coefficients + work), 16 elements per thread
+  unsigned log_tile = tt <= 8 ? 12 : (tt <= 10 ? tt + 4 : 14);
   unsigned c = log_tile - tt;
   dim3 grid(BLOCK_ELEMS >> c, ncols);
-  size_t smem = ((size_t)1 << log_tile) * sizeof(uint32_t);
-#define K2(EPT)                                                                                                   \
-  lde_k2_kernel<EPT><<<grid, 1024, smem, st>>>(out, out_stride, logn, c, t->tw_fwd.p, t->tw_inv.p, bg->lo_f.p,   \
-                                               bg->hi_f.p, bg->lo_i.p, bg->hi_i.p, sc->a.p, sc->b.p)
+  size_t smem = 2 * ((size_t)1 << log_tile) * sizeof(uint32_t);
   {
     ProfScope ps(ctx, PT_LDE_K2, 1, 12.0 * cells);
-    switch (log_tile) {
-      case 12: K2(4); break;
-      case 13: K2(8); break;
-      case 14: K2(16); break;
-      case 15: K2(32); break;
-      default: fail(LSK_ERR_ARG, "bad LDE tile");
-    }
+    K2Args a{out, out_stride, logn, c, t->tw_fwd.p, t->tw_inv.p, bg->lo_f.p, bg->hi_f.p, bg->lo_i.p, bg->hi_i.p,
+             sc->a.p, sc->b.p};
+    if (log_tile == 12) lde_k2_kernel<256><<<grid, 256, smem, st>>>(a);
+    else if (log_tile == 13) lde_k2_kernel<512><<<grid, 512, smem, st>>>(a);
+    else lde_k2_kernel<1024><<<grid, 1024, smem, st>>>(a);
   }
-#undef K2
   {
     ProfScope ps(ctx, PT_LDE_K3, 1, 16.0 * cells);
-    lde_k3_kernel<<<dim3(2 * blocks, ncols), 1024, 0, st>>>(out, out_stride, t->tw_fwd.p);
+    lde_k3_kernel<<<dim3(2 * blocks, ncols), K13_THREADS, 0, st>>>(out, out_stride, t->tw_fwd.p);
   }
   LSK_CUDA(cudaGetLastError());
 }

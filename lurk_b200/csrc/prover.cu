@@ -251,21 +251,6 @@ static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record
   return sd;
 }
 
-// ---- proof script: literals interleaved with words gathered from the device ------------------------------
-struct ProofScript {
-  struct Item { uint32_t literal; uint32_t count; };  // count == 0: literal, else `count` gathered words
-  std::vector<Item> items;
-  std::vector<GatherJob> jobs;
-  uint32_t total = 0;
-  void lit(uint32_t v) { items.push_back({v, 0}); }
-  void data(const uint32_t* p, uint64_t first, uint64_t stride, uint32_t count) {
-    if (!count) return;
-    jobs.push_back(GatherJob{p, stride, first, count, total});
-    items.push_back({0, count});
-    total += count;
-  }
-};
-
 static void push_ext(std::vector<uint32_t>& w, const Ext& e) {
   for (int k = 0; k < 4; k++) w.push_back(from_mont(e.c[k]));
 }
@@ -530,42 +515,49 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   }
 
   pt.mark("grind");
-  // ---- query phase: build the gather script
-  ProofScript ps;
-  ps.lit(m.num_queries);
-  for (unsigned qi = 0; qi < m.num_queries; qi++) {
-    size_t index = ch.sample_bits(log_max);
-    ps.lit((uint32_t)rounds.size());
-    for (auto& rd : rounds) {
-      const MerkleTreeDev& t = *rd.tree;
-      size_t idx = index >> (log_max - t.log_max);
-      ps.lit((uint32_t)rd.mats.size());
-      for (auto& mt : rd.mats) {
-        size_t r = idx >> (t.log_max - mt.lh);
-        ps.lit(mt.w);
-        ps.data(mt.p, r, mt.stride, mt.w);
-      }
-      ps.lit(t.log_max);
-      for (unsigned l = 0; l < t.log_max; l++) ps.data(t.layer(l), ((idx >> l) ^ 1) * 8, 1, 8);
+  // ---- query phase: one query template, instantiated on the device for every sampled index
+  std::vector<QuerySeg> segs;
+  uint32_t wpq = 0;  // words per query
+  auto lit = [&](uint32_t v) {
+    segs.push_back(QuerySeg{nullptr, 0, 1, wpq, 0, 0, 0, v});
+    wpq += 1;
+  };
+  auto data = [&](const uint32_t* p, uint64_t stride, uint32_t count, uint32_t shift, uint32_t xor1, uint32_t mul) {
+    if (!count) return;
+    segs.push_back(QuerySeg{p, stride, count, wpq, shift, xor1, mul, 0});
+    wpq += count;
+  };
+  lit((uint32_t)rounds.size());
+  for (auto& rd : rounds) {
+    const MerkleTreeDev& t = *rd.tree;
+    const uint32_t tshift = log_max - t.log_max;  // idx = index >> tshift
+    lit((uint32_t)rd.mats.size());
+    for (auto& mt : rd.mats) {
+      lit(mt.w);
+      data(mt.p, mt.stride, mt.w, log_max - mt.lh, 0, 1);  // row r = index >> (log_max - lh), one word per column
     }
-    ps.lit(nlayers);
-    for (unsigned li = 0; li < nlayers; li++) {
-      size_t idx = index >> li, pair = idx >> 1;
-      const MerkleTreeDev& t = fri_trees[li];
-      ps.data((const uint32_t*)fri_vals[li].p, (idx ^ 1) * 4, 1, 4);
-      ps.lit(t.log_max);
-      for (unsigned l = 0; l < t.log_max; l++) ps.data(t.layer(l), ((pair >> l) ^ 1) * 8, 1, 8);
-    }
+    lit(t.log_max);
+    for (unsigned l = 0; l < t.log_max; l++) data(t.layer(l), 1, 8, tshift + l, 1, 8);  // sibling digest of layer l
   }
-  std::vector<uint32_t> gathered(ps.total);
-  if (ps.total) {
-    DevBuf<GatherJob> d_jobs(ctx, ps.jobs.size());
-    DevBuf<uint32_t> d_out(ctx, ps.total);
-    d_jobs.upload(ps.jobs.data(), ps.jobs.size());
-    gather_dev(ctx, d_jobs.p, (uint32_t)ps.jobs.size(), d_out.p);
-    d_out.download(gathered.data(), ps.total);
+  lit(nlayers);
+  for (unsigned li = 0; li < nlayers; li++) {
+    const MerkleTreeDev& t = fri_trees[li];
+    data((const uint32_t*)fri_vals[li].p, 1, 4, li, 1, 4);  // the other element of the pair
+    lit(t.log_max);
+    for (unsigned l = 0; l < t.log_max; l++) data(t.layer(l), 1, 8, li + 1 + l, 1, 8);
+  }
+  std::vector<uint32_t> indices(m.num_queries);
+  for (auto& ix : indices) ix = ch.sample_bits(log_max);
+  std::vector<uint32_t> gathered((size_t)m.num_queries * wpq);
+  {
+    DevBuf<QuerySeg> d_segs(ctx, segs.size());
+    DevBuf<uint32_t> d_idx(ctx, indices.size()), d_out(ctx, gathered.size());
+    d_segs.upload(segs.data(), segs.size());
+    d_idx.upload(indices.data(), indices.size());
+    query_assemble_dev(ctx, d_segs.p, (uint32_t)segs.size(), d_idx.p, m.num_queries, wpq, d_out.p);
+    d_out.download(gathered.data(), gathered.size());
     LSK_CUDA(cudaStreamSynchronize(st));
-    m.last_d2h += (size_t)ps.total * 4;
+    m.last_d2h += gathered.size() * 4;
   }
 
   pt.mark("queries");
@@ -600,15 +592,8 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     for (int k = 0; k < 8; k++) W.push_back(r[k]);
   push_ext(W, final_poly);
   W.push_back(pow_witness);
-  size_t cur = 0;
-  for (auto& it : ps.items) {
-    if (!it.count) {
-      W.push_back(it.literal);
-    } else {
-      W.insert(W.end(), gathered.begin() + cur, gathered.begin() + cur + it.count);
-      cur += it.count;
-    }
-  }
+  W.push_back(m.num_queries);
+  W.insert(W.end(), gathered.begin(), gathered.end());
   pt.mark("serialise");
 }
 

@@ -461,6 +461,30 @@ void gather_dev(lsk_ctx* ctx, const GatherJob* jobs_dev, uint32_t njobs, uint32_
   LSK_CUDA(cudaGetLastError());
 }
 
+__global__ void __launch_bounds__(256) query_assemble_kernel(const QuerySeg* __restrict__ segs, uint32_t nsegs,
+                                                              const uint32_t* __restrict__ indices, uint32_t wpq,
+                                                              uint32_t* __restrict__ out) {
+  const uint32_t index = indices[blockIdx.x];
+  uint32_t* o = out + (size_t)blockIdx.x * wpq;
+  const unsigned lane = threadIdx.x & 31;
+  for (uint32_t s = threadIdx.x >> 5; s < nsegs; s += 8) {  // one warp per segment
+    const QuerySeg g = segs[s];
+    if (!g.p) {
+      for (uint32_t k = lane; k < g.count; k += 32) o[g.dst + k] = g.lit;
+    } else {
+      const size_t first = (size_t)((index >> g.shift) ^ g.xor1) * g.mul;
+      for (uint32_t k = lane; k < g.count; k += 32) o[g.dst + k] = from_mont(g.p[first + (size_t)k * g.stride]);
+    }
+  }
+}
+void query_assemble_dev(lsk_ctx* ctx, const QuerySeg* segs_dev, uint32_t nsegs, const uint32_t* indices_dev,
+                        uint32_t nqueries, uint32_t words_per_query, uint32_t* out) {
+  if (!nqueries || !nsegs) return;
+  ProfScope ps(ctx, PT_GATHER, 1, 4.0 * nqueries * words_per_query);
+  query_assemble_kernel<<<nqueries, 256, 0, ctx->stream>>>(segs_dev, nsegs, indices_dev, words_per_query, out);
+  LSK_CUDA(cudaGetLastError());
+}
+
 void init_stark_kernels() { LSK_CUDA(p2_upload_constants()); }
 
 }  // namespace lsk

@@ -78,4 +78,18 @@ struct GatherJob {  // copies `count` canonical words to out[dst ..]
 };
 void gather_dev(lsk_ctx* ctx, const GatherJob* jobs_dev, uint32_t njobs, uint32_t* out);
 
+// Query phase: every FRI query has the same shape, so the host describes ONE query as a list of
+// segments and the device instantiates it for each sampled index, writing the proof words of all
+// queries (literals included) in their final order.  A segment is `count` words at dst:
+//   p == nullptr : the literal `lit`;
+//   else         : from_mont(p[first + k * stride]), first = (((index >> shift) ^ xor1) * mul).
+struct QuerySeg {
+  const uint32_t* p;
+  uint64_t stride;
+  uint32_t count, dst, shift, xor1, mul, lit;
+};
+// out: nqueries x words_per_query
+void query_assemble_dev(lsk_ctx* ctx, const QuerySeg* segs_dev, uint32_t nsegs, const uint32_t* indices_dev,
+                        uint32_t nqueries, uint32_t words_per_query, uint32_t* out);
+
 }  // namespace lsk

@@ -62,68 +62,6 @@ LSK_D void merkle_digest(const uint32_t* const* __restrict__ cols, uint32_t ncol
   }
 }
 
-// ---- 16 lanes per permutation ------------------------------------------------------------------------
-// A permutation computed by one thread takes ~10 us end to end (measured: every extra level of a
-// single-CTA tree tail costs that much), so the last levels of every tree -- too few nodes to fill
-// the machine -- are latency-bound.  There a half-warp shares one permutation, one state word per
-// lane: an S-box round is 4 dependent products instead of 64 interleaved ones, the external layer
-// is 5 shuffles (circ(2,3,1,1) inside each 4-lane group, then the column sums over the 4 groups),
-// and in the partial rounds every lane recomputes the S-box of word 0 (no broadcast) while the sum
-// of the other 15 words is carried incrementally (rest' = sum_i d_i s_i + 15 * sum), its butterfly
-// running under the next round's S-box chain.  ~5x lower latency for ~1.4x the multiplies.
-static __device__ uint32_t g_coop16[10 * 16];  // [r][lane]: full-round constants r = 0..7, diag (plain), diag (Shoup)
-struct Coop16 {
-  uint32_t rc[8], d, dsh;
-};
-LSK_D Coop16 coop16_load(unsigned lane) {
-  Coop16 k;
-#pragma unroll
-  for (int r = 0; r < 8; r++) k.rc[r] = g_coop16[r * 16 + (lane & 15)];
-  k.d = g_coop16[8 * 16 + (lane & 15)];
-  k.dsh = g_coop16[9 * 16 + (lane & 15)];
-  return k;
-}
-LSK_D uint32_t coop16_sum(uint32_t v) {  // sum over the 16 lanes of this half-warp, in every lane
-#pragma unroll
-  for (int d = 1; d < 16; d <<= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
-  return v;
-}
-LSK_D uint32_t coop16_linear(uint32_t x, unsigned lane) {
-  uint32_t t = fadd(x, __shfl_xor_sync(0xffffffffu, x, 1));
-  t = fadd(t, __shfl_xor_sync(0xffffffffu, t, 2));
-  uint32_t nxt = __shfl_sync(0xffffffffu, x, (lane & ~3u) | ((lane + 1) & 3u));
-  uint32_t y = fadd(fadd(t, x), fdbl(nxt));  // row j of circ(2,3,1,1): sum + x_j + 2 x_{j+1}
-  uint32_t c = fadd(y, __shfl_xor_sync(0xffffffffu, y, 4));
-  c = fadd(c, __shfl_xor_sync(0xffffffffu, c, 8));
-  return fadd(y, c);
-}
-LSK_D uint32_t sbox7(uint32_t x) {
-  uint32_t x3 = fmul(fsqr(x), x);
-  return fmul(x, fsqr(x3));
-}
-LSK_D uint32_t coop16_permute(uint32_t s, const Coop16& k, unsigned lane) {
-  const P2Const<16>& c = p2c<16>();
-  const bool first = (lane & 15) == 0;
-  s = coop16_linear(s, lane);
-#pragma unroll
-  for (int r = 0; r < 4; r++) s = coop16_linear(sbox7(fadd(s, k.rc[r])), lane);
-  uint32_t s0 = __shfl_sync(0xffffffffu, s, lane & 16u);
-  uint32_t rest = coop16_sum(first ? 0u : s);
-#pragma unroll 1
-  for (int q = 0; q < P2Rounds<16>::RP; q++) {
-    uint32_t m = first ? 0u : fmul_shoup(s, k.d, k.dsh);
-    uint32_t dsum = coop16_sum(m);
-    uint32_t s0n = sbox7(fadd(s0, c.part_rc[q]));
-    uint32_t sum = fadd(s0n, rest);
-    s0 = fadd(fmul_shoup(s0n, c.diag[0], c.diag_shoup[0]), sum);
-    s = first ? s0 : fadd(m, sum);
-    uint32_t s2 = fdbl(sum), s4 = fdbl(s2), s8 = fdbl(s4);
-    rest = fadd(dsum, fsub(fdbl(s8), sum));
-  }
-#pragma unroll
-  for (int r = 4; r < 8; r++) s = coop16_linear(sbox7(fadd(s, k.rc[r])), lane);
-  return s;
-}
 // merkle_digest with the state spread over a half-warp: the lane's state word after the last
 // permutation (lanes 0..7 of the half hold the digest).  All 32 lanes of the warp must call it with
 // the same ncols / packed / children-ness.
@@ -159,9 +97,8 @@ LSK_D uint32_t merkle_digest_coop(const uint32_t* const* __restrict__ cols, uint
 // of layer l0 + ST_LEVELS; intermediate digests go straight to their layers in global memory (they
 // are needed for the query openings) and are re-read by the same CTA through L1/L2.  A 2^21-leaf
 // commitment is 3 launches instead of 22, and the sequential tail of a tree costs one launch.
-constexpr int ST_THREADS = 256;
-constexpr unsigned ST_LEVELS = 9;  // log2(2 * ST_THREADS)
-constexpr uint32_t COOP_MAX = 64;  // levels of a CTA with at most this many nodes use 16 lanes per permutation
+constexpr int ST_THREADS = 512;
+constexpr unsigned ST_LEVELS = 9;  // a CTA reduces 2^ST_LEVELS inputs to one node
 struct SubtreeArgs {
   uint32_t* nodes;
   const uint32_t* const* cols;
@@ -174,39 +111,53 @@ struct SubtreeArgs {
 };
 enum { ST_NODES = 0, ST_LEAVES = 1, ST_FRI_LEAVES = 2 };
 
-// levels first_k .. levels of the subtree whose 2^log_in inputs start at node in0 of the input layer
+// Levels (MODE == ST_NODES ? 1 : 0) .. levels of the subtree whose 2^log_in inputs start at node in0 of
+// the input layer.  Measured on B200 (tools/perm_latency.cu): one thread computes a permutation in
+// 18.7 k cycles, a half-warp in 5.2 k -- but at ~11x the instructions, so on the single SM a CTA owns
+// the 16-lane form only wins while a level has <= COOP_MAX nodes; wider levels use one thread per
+// node.  A level's digests go to the tree and, through shared memory (`sdig`, 2 x 512 digests), to
+// the next level.
+constexpr uint32_t COOP_MAX = 64;
 template <int MODE>
 LSK_D void subtree_build(uint32_t* __restrict__ nodes, const uint32_t* const* __restrict__ cols,
                          const uint32_t* __restrict__ fri_vals, uint32_t levels, uint32_t log_in,
                          const uint32_t* __restrict__ off, const uint32_t* __restrict__ inj_first,
-                         const uint32_t* __restrict__ inj_ncols, size_t in0, const Coop16& ck) {
+                         const uint32_t* __restrict__ inj_ncols, size_t in0, const Coop16& ck, uint32_t* sdig) {
   const uint32_t nin = 1u << log_in;
   const unsigned lane = threadIdx.x & 31;
+  const uint32_t k0 = MODE == ST_NODES ? 1u : 0u;
 #pragma unroll 1
-  for (uint32_t k = (MODE == ST_NODES ? 1u : 0u); k <= levels; k++) {
+  for (uint32_t k = k0; k <= levels; k++) {
     const uint32_t cnt = nin >> k;
     uint32_t* layer = nodes + (size_t)off[k] * 8;
     const uint32_t* prev = k ? nodes + (size_t)off[k - 1] * 8 : nullptr;
     const bool packed = MODE == ST_FRI_LEAVES && k == 0;
     const uint32_t ncols = packed || !inj_ncols ? 0u : inj_ncols[k];
     const uint32_t* const* gcols = inj_first ? cols + inj_first[k] : cols;
+    uint32_t* scur = sdig + (k & 1) * (512 * 8);
+    const uint32_t* sprev = sdig + ((k - 1) & 1) * (512 * 8);
     if (cnt <= COOP_MAX) {
       // whole warps loop together (the permutation shuffles): slots past cnt recompute the last node
 #pragma unroll 1
       for (uint32_t t0 = (threadIdx.x >> 5) * 2; t0 < cnt; t0 += ST_THREADS / 16) {
-        const uint32_t t = t0 + (lane >> 4);
-        const size_t i = (in0 >> k) + (t < cnt ? t : cnt - 1);
-        uint32_t s = merkle_digest_coop(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr,
-                                        k ? prev + 16 * i : nullptr, ck, lane);
-        if (t < cnt && (lane & 15) < 8) layer[i * 8 + (lane & 15)] = s;
+        const uint32_t t = t0 + (lane >> 4), tc = t < cnt ? t : cnt - 1;
+        const size_t i = (in0 >> k) + tc;
+        const uint32_t* children = !k ? nullptr : (k > k0 ? sprev + 16 * tc : prev + 16 * i);
+        uint32_t s = merkle_digest_coop(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr, children, ck, lane);
+        if (t < cnt && (lane & 15) < 8) {
+          layer[i * 8 + (lane & 15)] = s;
+          scur[t * 8 + (lane & 15)] = s;
+        }
       }
     } else {
 #pragma unroll 1
       for (uint32_t t = threadIdx.x; t < cnt; t += ST_THREADS) {
         const size_t i = (in0 >> k) + t;
+        const uint32_t* children = !k ? nullptr : (k > k0 ? sprev + 16 * t : prev + 16 * i);
         uint32_t st[16];
-        merkle_digest(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr, k ? prev + 16 * i : nullptr, st);
+        merkle_digest(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr, children, st);
         store_digest(layer + i * 8, st);
+        store_digest(scur + t * 8, st);
       }
     }
     __syncthreads();
@@ -231,8 +182,9 @@ LSK_D void fri_challenge(const FriChallenge& fc, const uint32_t* __restrict__ ro
 template <int MODE>
 __global__ void __launch_bounds__(ST_THREADS) merkle_subtree_kernel(SubtreeArgs a) {
   const Coop16 ck = coop16_load(threadIdx.x & 31);
+  __shared__ __align__(16) uint32_t sdig[2 * 512 * 8];
   subtree_build<MODE>(a.nodes, a.cols, a.fri_vals, a.levels, a.log_in, a.off, a.inj_first, a.inj_ncols,
-                      (size_t)blockIdx.x << a.log_in, ck);
+                      (size_t)blockIdx.x << a.log_in, ck, sdig);
   if (a.fc.chal && blockIdx.x == 0 && threadIdx.x < 32) fri_challenge(a.fc, a.nodes + (size_t)a.off[a.levels] * 8, ck);
 }
 
@@ -251,12 +203,14 @@ struct FriTailArgs {
 __global__ void __launch_bounds__(ST_THREADS) fri_tail_kernel(FriTailArgs a) {
   const Coop16 ck = coop16_load(threadIdx.x & 31);
   __shared__ uint32_t off[ST_LEVELS + 1];
+  __shared__ __align__(16) uint32_t sdig[2 * 512 * 8];
 #pragma unroll 1
   for (uint32_t j = 0; j < a.nlayers; j++) {
     const uint32_t lfh = a.first_lfh - j;
     if (threadIdx.x <= lfh) off[threadIdx.x] = (2u << lfh) - (2u << (lfh - threadIdx.x));
     __syncthreads();
-    subtree_build<ST_FRI_LEAVES>(a.nodes[j], nullptr, (const uint32_t*)a.vals[j], lfh, lfh, off, nullptr, nullptr, 0, ck);
+    subtree_build<ST_FRI_LEAVES>(a.nodes[j], nullptr, (const uint32_t*)a.vals[j], lfh, lfh, off, nullptr, nullptr, 0, ck,
+                                 sdig);
     FriChallenge fc{a.fc.chal, a.fc.beta_out + j, a.fc.root_out + 8 * j};
     if (threadIdx.x < 32) fri_challenge(fc, a.nodes[j] + (size_t)off[lfh] * 8, ck);
     __syncthreads();
@@ -289,13 +243,7 @@ __global__ void __launch_bounds__(MK_BLOCK) merkle_flat_kernel(const uint32_t* c
 
 void init_merkle_kernels() {
   LSK_CUDA(p2_upload_constants());
-  uint32_t h[10 * 16];
-  for (int i = 0; i < 16; i++) {
-    for (int r = 0; r < 8; r++) h[r * 16 + i] = to_mont(P2_FULL_RC_16[r * 16 + i]);
-    h[8 * 16 + i] = P2_DIAG_16[i] % P;
-    h[9 * 16 + i] = shoup_precompute(P2_DIAG_16[i] % P);
-  }
-  LSK_CUDA(cudaMemcpyToSymbol(g_coop16, h, sizeof h));
+  LSK_CUDA(coop16_upload_constants());
 }
 
 static void layout_layers(lsk_ctx* ctx, MerkleTreeDev& tree) {

@@ -42,32 +42,55 @@ def measured_peaks():
         return 6650.0, "fallback"
 
 
-def workload_name(log_rows, world):
+def ncu_summary():
+    """Per-kernel figures read off the committed `ncu --set full` capture (profiles/ncu_summary.json):
+    DRAM bytes per launch of the dominant kernel and the utilisation of the pipe that bounds it."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_summary.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def workload_name(log_rows, world, workload="fib"):
+    if workload == "cons":
+        return (f"Lurk-shaped cons_chain(n={world}*2^{log_rows}-1): per shard 2^{log_rows} rows of the 655-wide hash4 chip "
+                f"(Poseidon2 wide witness) + 2^{log_rows} x 37 caller rows, {world} shard(s), FRI 100 queries / 16 PoW bits")
     return (f"Lair fib(n={world}*2^{log_rows}-1) of demo_toplevel: 2^{log_rows} trace rows x 18 cols per shard, "
             f"{world} shard(s), 12 chips, FRI 100 queries / 16 PoW bits")
+
+
+def workload_program(workload):
+    """(toplevel, entry func name) -- fib: src/lair/mod.rs:65-83 (benches/fib.rs shape); cons: lurk_b200/programs.py"""
+    if workload == "cons":
+        from lurk_b200.programs import hash_toplevel
+        return hash_toplevel(), "cons_chain"
+    from lurk_b200.lair import demo_toplevel
+    return demo_toplevel(), "fib"
 
 
 # ------------------------------------------------------------------------------------------------
 # CPU prover (oracle) -- cpu_baseline leg and --impl reference
 # ------------------------------------------------------------------------------------------------
 class CpuProver:
-    def __init__(self):
+    def __init__(self, workload="fib"):
         from oracle import pyoracle
         from lurk_b200.air import build_chip_vector, serialize_machine
-        from lurk_b200.lair import FuncChip, demo_toplevel
+        from lurk_b200.lair import FuncChip
         pyoracle.build()
         self.o = pyoracle
-        top = demo_toplevel()
-        fc = FuncChip.from_name("fib", top)
+        top, entry = workload_program(workload)
+        fc = FuncChip.from_name(entry, top)
         self.func = fc.func.index
-        blob = serialize_machine(build_chip_vector(fc), 2)
+        self.nout = fc.func.output_size
+        blob = serialize_machine(build_chip_vector(fc), fc.func.input_size + fc.func.output_size)
         self.ot = pyoracle.OracleToplevel(top.serialize())
         self.m = pyoracle.OracleMachine(self.ot, self.func, blob, 100, 16)
         self.cores = os.cpu_count() or 1
 
     def record(self, log_rows):
         rec = self.o.OracleRecord(self.ot)
-        rec.execute(self.func, [(1 << log_rows) - 1], 1)
+        rec.execute(self.func, [(1 << log_rows) - 1], self.nout)
         return rec
 
     def time_prove(self, rec, log_rows):
@@ -76,19 +99,20 @@ class CpuProver:
         return time.perf_counter() - t
 
 
-def cpu_baseline(log_rows, budget_s=25.0):
+def cpu_baseline(log_rows, budget_s=25.0, workload="fib"):
     """Oracle prover on a bounded sample: the largest 2^l <= 2^log_rows rows whose prove fits the budget."""
-    cp = CpuProver()
-    t14 = cp.time_prove(cp.record(14), 14)
-    t16 = cp.time_prove(cp.record(16), 16)
-    per_row = max((t16 - t14) / (3 << 14), 1e-7)
-    fixed = max(t14 - per_row * (1 << 14), 0.0)
-    l = 16
+    cp = CpuProver(workload)
+    la, lb = (14, 16) if workload == "fib" else (8, 10)
+    ta = cp.time_prove(cp.record(la), la)
+    tb = cp.time_prove(cp.record(lb), lb)
+    per_row = max((tb - ta) / ((1 << lb) - (1 << la)), 1e-7)
+    fixed = max(ta - per_row * (1 << la), 0.0)
+    l = lb
     while l < log_rows and fixed + per_row * (1 << (l + 1)) <= budget_s:
         l += 1
-    t = cp.time_prove(cp.record(l), l) if l > 16 else t16
+    t = cp.time_prove(cp.record(l), l) if l > lb else tb
     return {"value": (1 << l) / t, "unit": UNIT, "cores": cp.cores, "kind": "port",
-            "sample": f"oracle CPU prover (C++, std::thread x{cp.cores}), one prove of fib at 2^{l} rows, {t:.2f} s"}
+            "sample": f"oracle CPU prover (C++, std::thread x{cp.cores}), one prove of {workload} at 2^{l} rows, {t:.2f} s"}
 
 
 def run_reference(args):
@@ -96,14 +120,15 @@ def run_reference(args):
     if rank != 0:
         return
     world = args.gpus
-    cp = CpuProver()
+    cp = CpuProver(args.workload)
     steps, warmup = args.steps, args.warmup
-    t14 = cp.time_prove(cp.record(14), 14)
-    t16 = cp.time_prove(cp.record(16), 16)
-    per_row = max((t16 - t14) / (3 << 14), 1e-7)
-    fixed = max(t14 - per_row * (1 << 14), 0.0)
+    la, lb = (14, 16) if args.workload == "fib" else (8, 10)
+    ta = cp.time_prove(cp.record(la), la)
+    tb = cp.time_prove(cp.record(lb), lb)
+    per_row = max((tb - ta) / ((1 << lb) - (1 << la)), 1e-7)
+    fixed = max(ta - per_row * (1 << la), 0.0)
     budget = 150.0 / max(1, steps + warmup)
-    l = 14
+    l = la
     while l < args.log_rows and fixed + per_row * (1 << (l + 1)) <= budget:
         l += 1
     rec = cp.record(l)
@@ -112,12 +137,12 @@ def run_reference(args):
     times = [cp.time_prove(rec, l) for _ in range(steps)]
     total = sum(times)
     value = steps * (1 << l) / total
-    sample = f"oracle CPU prover (C++, std::thread x{cp.cores}), each step one prove of fib at 2^{l} rows"
+    sample = f"oracle CPU prover (C++, std::thread x{cp.cores}), each step one prove of {args.workload} at 2^{l} rows"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * total / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": workload_name(args.log_rows, world), "log_rows": args.log_rows,
+        "config": {"workload": workload_name(args.log_rows, world, args.workload), "log_rows": args.log_rows,
                    "sample_log_rows": l},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cp.cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -190,7 +215,6 @@ def run_ours(args):
 
     from lurk_b200 import _native as N
     from lurk_b200.execute import QueryRecord, Shard, ShardingConfig, execute_by_name
-    from lurk_b200.lair import demo_toplevel
     from lurk_b200.machine import assemble_proof, new_machine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -208,12 +232,12 @@ def run_ours(args):
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     L = args.log_rows
-    top = demo_toplevel()
-    m = new_machine(top, "fib", ctx=ctx)
+    top, entry = workload_program(args.workload)
+    m = new_machine(top, entry, ctx=ctx)
     pk, vk = m.setup()
     q = QueryRecord.new(top)
     t0 = time.perf_counter()
-    out = execute_by_name(top, "fib", [world * (1 << L) - 1], q)
+    out = execute_by_name(top, entry, [world * (1 << L) - 1], q)
     t_exec = time.perf_counter() - t0
     q.pin()                            # the record is the step's input: keep it in pinned host memory
     cfg = ShardingConfig(1 << L)
@@ -272,6 +296,11 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         step_resident()
     proof = step_e2e()
+    verify_ms = None
+    if rank == 0:                      # machine.verify (host C++ verifier of the library) accepts the job's proof
+        t0 = time.perf_counter()
+        m.verify(vk, proof)
+        verify_ms = 1e3 * (time.perf_counter() - t0)
     step_resident()                    # re-upload the record so that it is resident for the timed steps
     barrier()
 
@@ -303,8 +332,11 @@ def run_ours(args):
         tv = prof[top_k]
         achieved = tv["bytes"] / (tv["ms"] * 1e6)
         gpu_ms = sum(v["ms"] for v in prof.values())
+        ncu = ncu_summary().get(top_k, {})
         roofline = {"kernel": top_k, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                    "frac": achieved / peak, "traffic": ncu.get("dram_bytes_per_launch"),
+                    "traffic_source": ncu.get("source"), "pipe": ncu.get("pipe"),
+                    "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                     "bytes_per_launch": tv["bytes"] / max(1, tv["launches"]),
                     "ms_per_launch": tv["ms"] / max(1, tv["launches"]),
                     "share_of_step_gpu_time": tv["ms"] / gpu_ms if gpu_ms else None,
@@ -313,9 +345,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": res_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(L, world), "log_rows": L, "shards": world,
+            "config": {"workload": workload_name(L, world, args.workload), "log_rows": L, "shards": world,
                        "rows_per_step": rows, "l2": "flushed between timed steps (256 MiB write)",
-                       "executor_s": round(t_exec, 3), "fib_mod_p": int(out[0]), "proof_words": int(len(proof))},
+                       "executor_s": round(t_exec, 3), "output_word0": int(out[0]), "proof_words": int(len(proof)),
+                       "proof_verified_ms": verify_ms},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(sum(v["launches"] for v in prof.values())),
@@ -324,7 +357,7 @@ def run_ours(args):
             "kernels": kernels,
         }
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(L)
+            line["cpu_baseline"] = cpu_baseline(L, workload=args.workload)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
@@ -337,6 +370,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-rows", type=int, default=20, help="log2 trace rows per shard (= per GPU)")
+    ap.add_argument("--workload", default="fib", choices=["fib", "cons"],
+                    help="fib: BASELINE configs[1] (default); cons: Lurk-shaped hash-chip load (configs[2] substitute)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -251,6 +251,15 @@ __global__ void __launch_bounds__(128) func_trace_kernel(const uint32_t* __restr
                                                           uint32_t* __restrict__ out) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= height) return;
+  if (COLMAJOR && log_h >= 5) {
+    // Row i is stored at position bitrev(i) of every column.  With thread = row, a warp's store to one
+    // column would hit 32 different sectors (4 useful bytes each; beyond L2 capacity that is a DRAM
+    // read-modify-write per cell).  Instead a warp takes the 32 rows whose top three and bottom two index
+    // bits vary: the 8 rows sharing the bottom bits land on 8 consecutive positions -- one full 32 B
+    // sector per store -- while the record tables are still read in runs of 4 consecutive rows.
+    const uint32_t lane = i & 31, m = i >> 5;
+    i = ((lane & 7u) << (log_h - 3)) | (m << 2) | (lane >> 3);
+  }
   uint32_t width = 1 + hdr.in + hdr.out + hdr.aux + hdr.sel;
   const DevFuncTable self = funcs[func];
   if (COLMAJOR) {

@@ -1,0 +1,52 @@
+"""Lair programs shipped with the package (workloads of bench.py and the smoke test).
+
+`hash_toplevel` wires the Poseidon2 hasher chips the way the Lurk toplevel does (`hash3`/`hash4`/`hash5`
+funcs around `extern_call`s, src/core/misc.rs:5-128 and src/core/chipset.rs:20-63); `cons_chain(n)` is
+the Lurk-shaped load of bench.py --workload cons: one 655-wide hash4 row per list element, so the hash
+chip dominates the trace exactly as it does when Lurk ingresses data."""
+from .lair import (ChipInfo, Toplevel, array, call, const, extern_call, func, match, ret, sub)
+
+
+def hash_toplevel():
+    """Content-addressed hashing through the hasher chips, the way the Lurk toplevel wires them:
+    `hash3`/`hash4`/`hash5` funcs wrapping `extern_call`s (src/core/misc.rs:5-128 hash funcs,
+    chips src/core/chipset.rs:20-63; widths 493/655/815 pinned at src/core/eval_direct.rs:2053-2055).
+      commit_cons(a, b, secret, tag) = hash3(secret ++ tag ++ hash4(a ++ b))   -- KAT-2's shape
+                                                     (src/core/cli/tests/prove.lurk:12-17)
+      cons_chain(n) = digest of the list (n n-1 ... 1): one hash4 row per element
+      env_chain(n)  = the same through hash5 (fun/env shape: 16 + 16 + 8 words, zstore.rs:195-204)"""
+    chips = [ChipInfo("hasher3", 24, 8, 457, 0, kind=1), ChipInfo("hasher4", 32, 8, 611, 0, kind=2),
+             ChipInfo("hasher5", 40, 8, 763, 0, kind=3)]
+    h3 = func("hash3", [("preimg", 24)], 8, [extern_call([("img", 8)], "hasher3", ["preimg"]), ret("img")])
+    h4 = func("hash4", [("preimg", 32)], 8, [extern_call([("img", 8)], "hasher4", ["preimg"]), ret("img")])
+    h5 = func("hash5", [("preimg", 40)], 8, [extern_call([("img", 8)], "hasher5", ["preimg"]), ret("img")])
+    commit_cons = func("commit_cons", [("a", 16), ("b", 16), ("secret", 8), ("tag", 8)], 8, [
+        call([("d", 8)], "hash4", ["a", "b"]),
+        call([("c", 8)], "hash3", ["secret", "tag", "d"]),
+        ret("c"),
+    ])
+    cons_chain = func("cons_chain", ["n"], 8, [
+        array("nil", [0] * 8),
+        match("n", [(0, [ret("nil")])]),
+        const("one", 1),
+        sub("pred", "n", "one"),
+        call([("tail", 8)], "cons_chain", ["pred"]),
+        array("num_tag", [1, 0, 0, 0, 0, 0, 0, 0]),       # Tag::Num, src/core/tag.rs:23-39
+        array("cons_tag", [11, 0, 0, 0, 0, 0, 0, 0]),     # Tag::Cons
+        array("pad7", [0] * 7),
+        call([("d", 8)], "hash4", ["num_tag", "n", "pad7", "cons_tag", "tail"]),
+        ret("d"),
+    ])
+    env_chain = func("env_chain", ["n"], 8, [
+        array("nil", [0] * 8),
+        match("n", [(0, [ret("nil")])]),
+        const("one", 1),
+        sub("pred", "n", "one"),
+        call([("tail", 8)], "env_chain", ["pred"]),
+        array("sym_tag", [6, 0, 0, 0, 0, 0, 0, 0]),
+        array("num_tag", [1, 0, 0, 0, 0, 0, 0, 0]),
+        array("pad7", [0] * 7),
+        call([("d", 8)], "hash5", ["sym_tag", "n", "pad7", "num_tag", "pred", "pad7", "tail"]),
+        ret("d"),
+    ])
+    return Toplevel([commit_cons, cons_chain, env_chain, h3, h4, h5], chips)

@@ -238,6 +238,7 @@ def run_ours(args):
     q = QueryRecord.new(top)
     t0 = time.perf_counter()
     out = execute_by_name(top, entry, [world * (1 << L) - 1], q)
+    q.finalize()                       # row-ordered tables: each rank uploads only its shard's slice
     t_exec = time.perf_counter() - t0
     q.pin()                            # the record is the step's input: keep it in pinned host memory
     cfg = ShardingConfig(1 << L)

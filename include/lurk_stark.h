@@ -91,6 +91,10 @@ size_t lsk_record_num_queries(const lsk_record* r, uint32_t func);
 size_t lsk_record_num_mem(const lsk_record* r, uint32_t mem_idx);
 size_t lsk_record_public_values(const lsk_record* r, uint32_t* out, size_t cap);
 uint32_t lsk_record_num_shards(const lsk_record* r, uint32_t shard_size);  /* Shard::shard, execute.rs:186-216 */
+/* Re-pack the per-row require / hint arrays in row order (the executor appends them in completion order).
+ * Optional: afterwards a shard's rows own one contiguous range of every table, and lsk_shard_commit uploads
+ * only that range instead of the whole record (what each of N GPUs would otherwise copy N times). */
+int lsk_record_finalize(lsk_record* r);
 /* Page-lock the record's tables in place (cudaHostRegister) so that lsk_prove's upload runs at PCIe
  * speed; idempotent; undone by lsk_record_unpin, lsk_execute (the tables grow) and lsk_record_free. */
 int lsk_record_pin(lsk_record* r);

@@ -104,9 +104,12 @@ struct Executor {
     t.provide.push_back(seed_count);
     t.req_off.push_back(0);
     t.hint_off.push_back(0);
+    t.req_len.push_back(0);
+    t.hint_len.push_back(0);
     if (t.partial) {
       t.depth.push_back(0);
       t.dreq_off.push_back(0);
+      t.dreq_len.push_back(0);
     }
     t.index.insert_new(t.args.data(), t.in, row);
     return row;
@@ -319,12 +322,17 @@ struct Executor {
           new_lookup(byte_record((dep >> (8 * b)) & 255u, (depth >> (8 * b)) & 255u, 2), f.nonce, t.dreqs);
         }
         t.depth[f.nonce] = depth;
+        t.dreq_len[f.nonce] = (uint32_t)(t.dreqs.size() / 2) - t.dreq_off[f.nonce];
         depth_stack.resize(f.depth_base);
       }
+      // segments are appended in completion order; a row finishing after a higher-numbered one breaks row order
+      if (f.nonce != t.completed++) t.row_ordered = false;
       t.req_off[f.nonce] = (uint32_t)(t.reqs.size() / 2);
       t.reqs.insert(t.reqs.end(), req_stack.begin() + f.req_base, req_stack.end());
+      t.req_len[f.nonce] = (uint32_t)(req_stack.size() - f.req_base) / 2;
       t.hint_off[f.nonce] = (uint32_t)t.hints.size();
       t.hints.insert(t.hints.end(), hint_stack.begin() + f.hint_base, hint_stack.end());
+      t.hint_len[f.nonce] = (uint32_t)(hint_stack.size() - f.hint_base);
       req_stack.resize(f.req_base);
       hint_stack.resize(f.hint_base);
       vals.resize(f.map_base);
@@ -366,11 +374,45 @@ struct Executor {
   }
 };
 
+// Re-pack the CSR arrays of every func table in row order (see FuncTable::row_ordered).
+static void repack(std::vector<uint32_t>& off, const std::vector<uint32_t>& len, std::vector<uint32_t>& data, uint32_t unit) {
+  std::vector<uint32_t> out;
+  out.reserve(data.size());
+  for (size_t i = 0; i < off.size(); i++) {
+    uint32_t start = (uint32_t)(out.size() / unit);
+    out.insert(out.end(), data.begin() + (size_t)off[i] * unit, data.begin() + ((size_t)off[i] + len[i]) * unit);
+    off[i] = start;
+  }
+  data.swap(out);
+}
+bool record_row_ordered(const lsk_record& r) {
+  for (auto& t : r.funcs)
+    if (!t.row_ordered) return false;
+  return true;
+}
+
 }  // namespace lsk
 
 using namespace lsk;
 
 extern "C" {
+
+int lsk_record_finalize(lsk_record* r) {
+  LSK_API_BEGIN
+  if (!r) fail(LSK_ERR_ARG, "null record");
+  lsk::record_unpin(r);
+  for (auto& t : r->funcs) {
+    if (t.row_ordered) continue;
+    for (size_t i = 0; i < t.rows(); i++)
+      if (!t.done[i]) fail(LSK_ERR_ARG, "record has an unfinished query");
+    repack(t.req_off, t.req_len, t.reqs, 2);
+    repack(t.hint_off, t.hint_len, t.hints, 1);
+    if (t.partial) repack(t.dreq_off, t.dreq_len, t.dreqs, 2);
+    t.row_ordered = true;
+  }
+  return LSK_OK;
+  LSK_API_END
+}
 
 int lsk_program_load(const uint32_t* words, size_t n, lsk_program** out) {
   LSK_API_BEGIN

@@ -76,6 +76,7 @@ struct lsk_machine {
   std::map<uint32_t, std::unique_ptr<ShardState>> pending;
   std::unique_ptr<DeviceRecord> drec;
   const lsk_record* drec_for = nullptr;
+  uint32_t drec_shard = 0, drec_ss = 0;   // slice the device copy holds (drec_ss == 0: the whole record)
   size_t last_h2d = 0, last_d2h = 0;
 };
 
@@ -174,20 +175,26 @@ static bool chip_included(const lsk_machine& m, const ChipH& c, const lsk_record
   }
 }
 
-static DeviceRecord& device_record(lsk_machine& m, const lsk_record& rec) {
-  if (!m.drec || m.drec_for != &rec) {
+// whole = false: the caller proves one shard of a sharded record (lsk_shard_commit): upload its slice only
+static DeviceRecord& device_record(lsk_machine& m, const lsk_record& rec, uint32_t shard, uint32_t ss, bool whole) {
+  const bool slice = !whole && record_row_ordered(rec) && lsk_record_num_shards(&rec, ss) > 1;
+  const uint32_t want_ss = slice ? ss : 0, want_shard = slice ? shard : 0;
+  if (!m.drec || m.drec_for != &rec || m.drec_ss != want_ss || m.drec_shard != want_shard) {
     m.drec = std::make_unique<DeviceRecord>();
-    m.drec->upload(m.ctx, *m.prog, rec);
+    m.drec->upload(m.ctx, *m.prog, rec, want_shard, want_ss);
     m.drec_for = &rec;
+    m.drec_ss = want_ss;
+    m.drec_shard = want_shard;
     m.last_h2d += m.drec->h2d_bytes;
   }
   return *m.drec;
 }
 
-static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record& rec, uint32_t shard, uint32_t ss) {
+static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record& rec, uint32_t shard, uint32_t ss,
+                                                bool whole_record) {
   lsk_ctx* ctx = m.ctx;
   PhaseTimer pt(ctx);
-  DeviceRecord& drec = device_record(m, rec);
+  DeviceRecord& drec = device_record(m, rec, shard, ss, whole_record);
   pt.mark("record upload");
   if (rec.public_values.size() != m.num_pv) fail(LSK_ERR_ARG, "record has %zu public values, machine expects %u",
                                                  rec.public_values.size(), m.num_pv);
@@ -694,7 +701,7 @@ int lsk_shard_commit(lsk_machine* m, const lsk_record* rec, uint32_t shard, uint
   if (!m || !rec || !root_out || !shard_size) fail(LSK_ERR_ARG, "bad argument");
   LSK_CUDA(cudaSetDevice(m->ctx->device));
   if (shard >= lsk_record_num_shards(rec, shard_size)) fail(LSK_ERR_ARG, "shard %u out of range", shard);
-  auto sd = commit_shard(*m, *rec, shard, shard_size);
+  auto sd = commit_shard(*m, *rec, shard, shard_size, false);
   memcpy(root_out, sd->main_root, 32);
   m->pending[shard] = std::move(sd);
   return LSK_OK;
@@ -771,7 +778,7 @@ int lsk_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard_size, uint32
   std::vector<std::unique_ptr<ShardState>> shards;
   Challenger ch = initial_challenger(*m);
   for (uint32_t s = 0; s < ns; s++) {
-    shards.push_back(commit_shard(*m, *rec, s, shard_size));
+    shards.push_back(commit_shard(*m, *rec, s, shard_size, true));
     observe_shard(*m, ch, shards.back()->main_root, rec->public_values.data());
   }
   std::vector<uint32_t> W;

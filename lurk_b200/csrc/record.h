@@ -96,6 +96,13 @@ struct FuncTable {
   std::vector<uint32_t> depth;     // [n]
   std::vector<uint32_t> dreq_off;  // [n] index (in pairs) of the row's first depth require
   std::vector<uint32_t> dreqs;     // pairs: 2 range checks of the depth bytes, then one less-than per partial callee
+  // The executor appends a row's require / hint / depth-require segments when the row RETURNS, i.e. in
+  // completion order; *_len keeps each row's segment length so that lsk_record_finalize can re-pack the
+  // three CSR arrays in row order (host-only bookkeeping, never uploaded).  row_ordered: offsets are
+  // monotone in the row index, so a shard's rows own one contiguous range of each array.
+  std::vector<uint32_t> req_len, hint_len, dreq_len;
+  bool row_ordered = true;
+  size_t completed = 0;            // rows that have returned so far
   HashIndex index;                 // args -> row
   // inverse queries (PreImg): out -> inp, both produced at Return and injected from outside
   std::vector<uint32_t> inv_outs, inv_inps;
@@ -139,4 +146,5 @@ struct lsk_record {
 };
 namespace lsk {
 void record_unpin(lsk_record* r);  // prover.cu (needs the CUDA runtime)
+bool record_row_ordered(const lsk_record& r);
 }

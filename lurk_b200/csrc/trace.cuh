@@ -30,7 +30,11 @@ struct DeviceRecord {
   std::vector<DevFuncTable> h_funcs;
   std::vector<DevMemTable> h_mems;
   size_t h2d_bytes = 0;
-  void upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_record& rec);
+  // shard_size == 0: the whole record.  Otherwise, if the record is row-ordered (lsk_record_finalize), only
+  // what proving `shard` touches: the per-row tables of its row range (device pointers are biased so that
+  // kernels keep indexing by absolute row) plus the tables other rows gather from (outputs, depths,
+  // arguments of invertible funcs, memory values).
+  void upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_record& rec, uint32_t shard = 0, uint32_t shard_size = 0);
 };
 
 // Output layouts

@@ -317,29 +317,55 @@ __global__ void bytes_prep_kernel(uint32_t* __restrict__ out) {
 
 void init_trace_kernels() { LSK_CUDA(p2_upload_constants()); }
 
-void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_record& rec) {
+void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_record& rec, uint32_t shard,
+                          uint32_t shard_size) {
   bufs.clear();
   h2d_bytes = 0;
-  auto up = [&](const std::vector<uint32_t>& v) -> const uint32_t* {
-    if (v.empty()) return nullptr;
-    bufs.emplace_back(ctx, v.size());
-    bufs.back().upload(v.data(), v.size());
-    h2d_bytes += v.size() * 4;
-    return bufs.back().p;
+  const bool sliced = shard_size != 0 && record_row_ordered(rec);
+  // words [first, first + count) of v; the returned pointer is biased by -first so that v's own indices work
+  auto up_range = [&](const std::vector<uint32_t>& v, size_t first, size_t count) -> const uint32_t* {
+    if (!count) return nullptr;
+    bufs.emplace_back(ctx, count);
+    LSK_CUDA(cudaMemcpyAsync(bufs.back().p, v.data() + first, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    h2d_bytes += count * 4;
+    return bufs.back().p - first;
   };
+  auto up = [&](const std::vector<uint32_t>& v) { return up_range(v, 0, v.size()); };
   h_funcs.clear();
   for (const FuncTable& t : rec.funcs) {
     DevFuncTable d{};
-    d.args = up(t.args); d.outs = up(t.outs); d.provide = up(t.provide);
-    d.req_off = up(t.req_off); d.reqs = up(t.reqs); d.hint_off = up(t.hint_off); d.hints = up(t.hints);
-    d.depth = up(t.depth); d.dreq_off = up(t.dreq_off); d.dreqs = up(t.dreqs);
-    d.in = t.in; d.out = t.out; d.rows = (uint32_t)t.rows();
+    const size_t n = t.rows();
+    size_t s = 0, e = n;
+    if (sliced) s = std::min(n, (size_t)shard * shard_size), e = std::min(n, (size_t)(shard + 1) * shard_size);
+    const size_t cnt = e - s;
+    d.outs = up(t.outs);
+    d.depth = up(t.depth);
+    d.args = t.invertible || !sliced ? up(t.args) : up_range(t.args, s * t.in, cnt * t.in);
+    d.provide = up_range(t.provide, 2 * s, 2 * cnt);
+    d.req_off = up_range(t.req_off, s, cnt);
+    d.hint_off = up_range(t.hint_off, s, cnt);
+    d.dreq_off = t.partial ? up_range(t.dreq_off, s, cnt) : nullptr;
+    if (cnt) {
+      // row-ordered CSR: the rows [s, e) own [off[s], off[e]) of each array
+      size_t r0 = t.req_off[s], r1 = e < n ? t.req_off[e] : t.reqs.size() / 2;
+      size_t h0 = t.hint_off[s], h1 = e < n ? t.hint_off[e] : t.hints.size();
+      if (!sliced) r0 = 0, r1 = t.reqs.size() / 2, h0 = 0, h1 = t.hints.size();
+      d.reqs = up_range(t.reqs, 2 * r0, 2 * (r1 - r0));
+      d.hints = up_range(t.hints, h0, h1 - h0);
+      if (t.partial) {
+        size_t q0 = t.dreq_off[s], q1 = e < n ? t.dreq_off[e] : t.dreqs.size() / 2;
+        if (!sliced) q0 = 0, q1 = t.dreqs.size() / 2;
+        d.dreqs = up_range(t.dreqs, 2 * q0, 2 * (q1 - q0));
+      }
+    }
+    d.in = t.in; d.out = t.out; d.rows = (uint32_t)n;
     h_funcs.push_back(d);
   }
   h_mems.clear();
   for (const MemTable& m : rec.mems) {
     DevMemTable d{};
-    d.vals = up(m.vals); d.provide = up(m.provide);
+    d.vals = up(m.vals);
+    d.provide = !sliced || shard == 0 ? up(m.provide) : nullptr;  // the Mem chips live in shard 0
     d.len = m.len; d.rows = (uint32_t)m.rows();
     h_mems.push_back(d);
   }
@@ -349,7 +375,7 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
   mems.upload(h_mems.data(), h_mems.size());
   program.alloc(ctx, prog.words.size());
   program.upload(prog.words.data(), prog.words.size());
-  if (rec.bytes_used) {
+  if (rec.bytes_used && (!sliced || shard == 0)) {  // the byte table's main trace is non-empty in shard 0 only
     bytes.alloc(ctx, rec.bytes.size());
     bytes.upload(rec.bytes.data(), rec.bytes.size());
     h2d_bytes += rec.bytes.size() * 4;

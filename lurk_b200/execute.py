@@ -75,6 +75,11 @@ class QueryRecord:
         N.check(N.lib().lsk_inject_inv_queries(self.program.h, self.h, f.index, N.vp(inps), N.vp(outs),
                                                ctypes.c_size_t(len(inps))))
 
+    def finalize(self):
+        """Re-pack the per-row require / hint arrays in row order so that shard-per-GPU proving uploads only
+        each shard's slice of the record (lsk_record_finalize); call once after the last execute."""
+        N.check(N.lib().lsk_record_finalize(self.h))
+
     def pin(self):
         """Page-lock the record's tables so that prove uploads them at PCIe speed."""
         N.check(N.lib().lsk_record_pin(self.h))

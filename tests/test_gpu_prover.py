@@ -80,6 +80,10 @@ def test_merkle_root_matches_oracle(oracle, shapes):
     assert np.array_equal(gpu_merkle_root(mats), oracle.merkle_root(mats))
 
 
+def pk_of(m):
+    return m.setup()[0]
+
+
 def _prove_both(oracle, top, entry, arg_list, shard_size=1 << 22, nq=6, pow_bits=6):
     opts = SphinxCoreOpts(num_queries=nq, proof_of_work_bits=pow_bits)
     m = new_machine(top, entry, opts=opts)
@@ -151,6 +155,14 @@ def test_partial_func_programs_prove_bit_exact(oracle, fname, args, ss):
     m, om, q, proof, want = _prove_both(oracle, top, fname, [args], shard_size=ss)
     assert np.array_equal(proof.words, want)
     assert om.verify(proof.words), om.last_error
+    if ss < 1 << 22:   # sharded: the sliced two-phase path (preimg / depth gathers cross shard boundaries)
+        q.finalize()
+        cfg = ShardingConfig(ss)
+        shards = Shard(q, 0, cfg).shard(cfg)
+        roots = np.stack([m.commit_shard(s) for s in shards])
+        parts = [m.prove_shard(s, roots) for s in shards]
+        m.release_record()
+        assert np.array_equal(assemble_proof(parts).words, want)
 
 
 def test_cons_chain_2pow12_verifies(oracle):
@@ -175,12 +187,18 @@ def test_multi_shard_proof_is_bit_exact(oracle):
     assert proof.num_shards() == 3
     assert np.array_equal(proof.words, want)
     assert om.verify(proof.words), om.last_error
-    # two-phase (shard-per-GPU) API gives the same bytes
+    # two-phase (shard-per-GPU) API gives the same bytes: whole-record uploads first, then (finalized record)
+    # per-shard slices of the record tables
     shards = Shard(q, 0, ShardingConfig(64)).shard(ShardingConfig(64))
-    roots = np.stack([m.commit_shard(s) for s in shards])
-    parts = [m.prove_shard(s, roots) for s in shards]
-    m.release_record()
-    assert np.array_equal(assemble_proof(parts).words, want)
+    for finalize in (False, True):
+        if finalize:
+            q.finalize()
+        roots = np.stack([m.commit_shard(s) for s in shards])
+        parts = [m.prove_shard(s, roots) for s in shards]
+        h2d = m.last_transfer_bytes()[0]
+        m.release_record()
+        assert np.array_equal(assemble_proof(parts).words, want)
+    assert np.array_equal(m.prove(pk_of(m), Shard(q, 0, ShardingConfig(64))).words, want)   # finalized + whole upload
 
 
 def test_large_fib_proof_verifies(oracle):

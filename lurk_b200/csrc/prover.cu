@@ -374,27 +374,28 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     oo[i].quot[0] = nopen; nopen += 8;
     oo[i].quot[1] = nopen; nopen += 8;
   }
-  DevBuf<Ext> opened(ctx, nopen), partial(ctx, 2 * max_w * div_up(max_n, OPEN_ROWS));
+  DevBuf<Ext> opened(ctx, nopen);
   {
-    std::map<unsigned, std::pair<DevBuf<Ext>, DevBuf<Ext>>> wcache;
+    // one batch (two launches) per distinct height: all matrices of the chips of that height
+    std::map<unsigned, std::vector<OpenMat>> by_logn;
     for (size_t i = 0; i < nchips; i++) {
       const ChipH& c = m.chips[sd.chip_ids[i]];
-      unsigned logn = sd.logn[i];
-      size_t n = (size_t)1 << logn;
-      auto it = wcache.find(logn);
-      if (it == wcache.end()) {
-        it = wcache.emplace(logn, std::make_pair(DevBuf<Ext>(ctx, n), DevBuf<Ext>(ctx, n))).first;
-        bary_weights_dev(ctx, logn, zeta, it->second.first.p);
-        bary_weights_dev(ctx, logn, emul_base(zeta, two_adic_generator(logn)), it->second.second.p);
-      }
-      const Ext *w0 = it->second.first.p, *w1 = it->second.second.p;
-      if (c.prep_width) open_columns_dev(ctx, m.prep_lde.p, 2 * n, c.prep_width, logn, w0, w1, partial.p, opened.p + oo[i].prep);
-      open_columns_dev(ctx, sd.main_lde[i].p, 2 * n, c.width, logn, w0, w1, partial.p, opened.p + oo[i].main);
-      open_columns_dev(ctx, perm_lde[i].p, 2 * n, 4 * (uint32_t)c.perm_width(), logn, w0, w1, partial.p, opened.p + oo[i].perm);
-      for (int j = 0; j < 2; j++)
-        open_columns_dev(ctx, quot_lde[2 * i + j].p, 2 * n, 4, logn, w0, w0, partial.p, opened.p + oo[i].quot[j]);
+      const size_t n2 = (size_t)2 << sd.logn[i];
+      auto& v = by_logn[sd.logn[i]];
+      if (c.prep_width) v.push_back(OpenMat{m.prep_lde.p, n2, c.prep_width, (uint32_t)oo[i].prep, 0});
+      v.push_back(OpenMat{sd.main_lde[i].p, n2, c.width, (uint32_t)oo[i].main, 0});
+      v.push_back(OpenMat{perm_lde[i].p, n2, 4 * (uint32_t)c.perm_width(), (uint32_t)oo[i].perm, 0});
+      for (int j = 0; j < 2; j++) v.push_back(OpenMat{quot_lde[2 * i + j].p, n2, 4, (uint32_t)oo[i].quot[j], 1});
     }
-    // wcache buffers are freed stream-ordered after the kernels that read them
+    for (auto& kv : by_logn) {
+      const unsigned logn = kv.first;
+      const size_t n = (size_t)1 << logn;
+      DevBuf<Ext> w0(ctx, n), w1(ctx, n);
+      bary_weights_dev(ctx, logn, zeta, w0.p);
+      bary_weights_dev(ctx, logn, emul_base(zeta, two_adic_generator(logn)), w1.p);
+      open_batch_dev(ctx, kv.second, logn, w0.p, w1.p, opened.p);
+      // the weight buffers are freed stream-ordered after the kernels that read them
+    }
   }
   std::vector<Ext> h_open(nopen), h_cums(nchips);
   opened.download(h_open.data(), nopen);

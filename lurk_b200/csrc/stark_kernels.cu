@@ -356,6 +356,105 @@ void open_columns_dev(lsk_ctx* ctx, const uint32_t* m, size_t stride, uint32_t w
   LSK_CUDA(cudaGetLastError());
 }
 
+struct OpenGroup { uint32_t mat, c0; };
+__global__ void __launch_bounds__(256) open_partial_batch_kernel(const OpenMat* __restrict__ mats,
+                                                                  const OpenGroup* __restrict__ groups, size_t n,
+                                                                  const Ext* __restrict__ wts0, const Ext* __restrict__ wts1,
+                                                                  Ext* __restrict__ partial, uint32_t nchunks) {
+  __shared__ uint32_t red[8][OPEN_COLS * 8];
+  const OpenGroup g = groups[blockIdx.y];
+  const OpenMat mt = mats[g.mat];
+  const uint32_t c0 = g.c0, w = mt.w;
+  const uint32_t* __restrict__ m = mt.p;
+  const size_t stride = mt.stride;
+  const size_t row0 = (size_t)blockIdx.x * OPEN_ROWS;
+  Ext acc[OPEN_COLS][2];
+#pragma unroll
+  for (int c = 0; c < OPEN_COLS; c++) acc[c][0] = acc[c][1] = ext_zero();
+  for (unsigned k = 0; k < OPEN_ROWS / 256; k++) {
+    size_t r = row0 + k * 256 + threadIdx.x;
+    if (r >= n) break;
+    Ext w0 = wts0[r], w1 = mt.one_point ? w0 : wts1[r];
+#pragma unroll
+    for (int c = 0; c < OPEN_COLS; c++) {
+      if (c0 + c < w) {
+        uint32_t v = m[(size_t)(c0 + c) * stride + r];
+        acc[c][0] = eadd(acc[c][0], emul_base(w0, v));
+        if (!mt.one_point) acc[c][1] = eadd(acc[c][1], emul_base(w1, v));
+      }
+    }
+  }
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < OPEN_COLS; c++)
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        uint32_t v = acc[c][p].c[e];
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
+        if (lane == 0) red[warp][(c * 2 + p) * 4 + e] = v;
+      }
+  __syncthreads();
+  if (threadIdx.x < OPEN_COLS * 8) {
+    uint32_t cp = threadIdx.x / 4, e = threadIdx.x % 4;  // cp = c * 2 + p
+    if (mt.one_point && (cp & 1)) cp ^= 1;               // the second output repeats the first
+    uint32_t v = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; wv++) v = fadd(v, red[wv][cp * 4 + e]);
+    uint32_t c = c0 + (threadIdx.x / 4) / 2;
+    if (c < w) partial[(size_t)(mt.out_off + c * 2 + ((threadIdx.x / 4) & 1)) * nchunks + blockIdx.x].c[e] = v;
+  }
+}
+__global__ void __launch_bounds__(128) open_reduce_batch_kernel(const Ext* __restrict__ partial, uint32_t nchunks,
+                                                                 const uint32_t* __restrict__ outs, Ext* __restrict__ out) {
+  __shared__ Ext red[4];
+  const uint32_t o = outs[blockIdx.x];
+  const Ext* p = partial + (size_t)o * nchunks;
+  Ext acc = ext_zero();
+  for (uint32_t k = threadIdx.x; k < nchunks; k += 128) acc = eadd(acc, p[k]);
+#pragma unroll
+  for (int e = 0; e < 4; e++) {
+    uint32_t v = acc.c[e];
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
+    acc.c[e] = v;
+  }
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) out[o] = eadd(eadd(red[0], red[1]), eadd(red[2], red[3]));
+}
+void open_batch_dev(lsk_ctx* ctx, const std::vector<OpenMat>& mats, unsigned logn, const Ext* wts0, const Ext* wts1,
+                    Ext* out) {
+  if (mats.empty()) return;
+  const size_t n = (size_t)1 << logn;
+  const uint32_t nchunks = div_up(n, OPEN_ROWS);
+  std::vector<OpenGroup> groups;
+  std::vector<uint32_t> outs;
+  uint32_t max_out = 0;
+  double bytes = 0;
+  for (uint32_t i = 0; i < mats.size(); i++) {
+    for (uint32_t c0 = 0; c0 < mats[i].w; c0 += OPEN_COLS) groups.push_back({i, c0});
+    for (uint32_t k = 0; k < 2 * mats[i].w; k++) outs.push_back(mats[i].out_off + k);
+    max_out = std::max(max_out, mats[i].out_off + 2 * mats[i].w);
+    bytes += (double)n * 4.0 * mats[i].w;
+  }
+  if (groups.empty()) return;
+  DevBuf<OpenMat> d_mats(ctx, mats.size());
+  DevBuf<OpenGroup> d_groups(ctx, groups.size());
+  DevBuf<uint32_t> d_outs(ctx, outs.size());
+  DevBuf<Ext> partial(ctx, (size_t)max_out * nchunks);
+  d_mats.upload(mats.data(), mats.size());
+  d_groups.upload(groups.data(), groups.size());
+  d_outs.upload(outs.data(), outs.size());
+  ProfScope ps(ctx, PT_OPEN, 2, bytes + 32.0 * n);
+  open_partial_batch_kernel<<<dim3(nchunks, (unsigned)groups.size()), 256, 0, ctx->stream>>>(d_mats.p, d_groups.p, n, wts0,
+                                                                                            wts1, partial.p, nchunks);
+  open_reduce_batch_kernel<<<(unsigned)outs.size(), 128, 0, ctx->stream>>>(partial.p, nchunks, d_outs.p, out);
+  LSK_CUDA(cudaGetLastError());
+}
+
 // ---- FRI: reduced openings, fold, grind --------------------------------------------------------------------
 __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* __restrict__ mats, uint32_t nmats,
                                                                unsigned lh, uint32_t g, uint32_t w, Ext z0, Ext z1,

@@ -4,6 +4,8 @@
 // (src/core/cli/repl.rs:196, benches/fib.rs:158); the oracle restates it in oracle/stark_prove.h.
 // All matrices are column-major, Montgomery form, rows in bit-reversed order.
 #pragma once
+#include <vector>
+
 #include "device.cuh"
 #include "field.cuh"
 
@@ -49,6 +51,15 @@ void bary_weights_dev(lsk_ctx* ctx, unsigned logn, Ext z, Ext* wts);
 constexpr unsigned OPEN_ROWS = 2048;
 void open_columns_dev(lsk_ctx* ctx, const uint32_t* m, size_t stride, uint32_t w, unsigned logn, const Ext* wts0,
                       const Ext* wts1, Ext* partial, Ext* out);
+// All matrices of one height in two launches (a shard has ~5 matrices per chip and most chips are small):
+// out[mat.out_off + c * 2 + p] as above; one_point: both outputs use wts0 (quotient chunks).
+struct OpenMat {
+  const uint32_t* p;
+  uint64_t stride;
+  uint32_t w, out_off, one_point;
+};
+void open_batch_dev(lsk_ctx* ctx, const std::vector<OpenMat>& mats, unsigned logn, const Ext* wts0, const Ext* wts1,
+                    Ext* out);
 
 // ---- FRI ---------------------------------------------------------------------------------------------
 struct ReduceMat {  // one opened matrix of LDE height 2^lh

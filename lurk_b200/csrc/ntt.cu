@@ -207,6 +207,26 @@ __global__ void __launch_bounds__(1024) lde_small_kernel(const uint32_t* __restr
   }
 }
 
+__global__ void __launch_bounds__(1024) lde_small_batch_kernel(const LdeSmallJob* __restrict__ jobs,
+                                                                const uint2* __restrict__ tw_fwd,
+                                                                const uint2* __restrict__ tw_inv) {
+  extern __shared__ uint32_t smem[];
+  const LdeSmallJob job = jobs[blockIdx.x];
+  const unsigned logn = job.logn, n = 1u << logn;
+  uint32_t* coef = smem;
+  uint32_t* work = smem + n;
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) coef[i] = job.in[i];
+  __syncthreads();
+  if (logn) dit_stages(coef, logn, tw_inv);
+  for (int j = 0; j < 2; j++) {
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) work[i] = shoup(coef[i], __ldg(job.scale + j * n + i));
+    __syncthreads();
+    if (logn) dif_stages(work, logn, tw_fwd);
+    for (unsigned i = threadIdx.x; i < n; i += blockDim.x) job.out[(size_t)j * n + i] = work[i];
+    __syncthreads();
+  }
+}
+
 // ---- N > 4096 ---------------------------------------------------------------------------------------
 // 4096-element tile, 256 threads x 16 registers.  Shared-memory index of element i is i + (i >> 4) (one
 // pad word per 16) so that both "16 consecutive per thread" and "stride 16 / 256 per thread" are
@@ -375,13 +395,36 @@ void init_ntt_kernels() {
   LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
 }
 
+void lde_flush(lsk_ctx* ctx, LdeBatch& batch) {
+  if (batch.jobs.empty()) return;
+  NttTables* t = tables(ctx);
+  DevBuf<LdeSmallJob> d_jobs(ctx, batch.jobs.size());
+  d_jobs.upload(batch.jobs.data(), batch.jobs.size());
+  unsigned n = 1u << batch.max_logn;
+  unsigned threads = n / 2 < 32 ? 32 : (n / 2 > 1024 ? 1024 : n / 2);
+  double bytes = 0;
+  for (auto& j : batch.jobs) bytes += 12.0 * (double)(1u << j.logn);
+  ProfScope ps(ctx, PT_LDE_SMALL, 1, bytes);
+  lde_small_batch_kernel<<<(unsigned)batch.jobs.size(), threads, 2 * n * sizeof(uint32_t), ctx->stream>>>(
+      d_jobs.p, t->tw_fwd.p, t->tw_inv.p);
+  LSK_CUDA(cudaGetLastError());
+  batch.jobs.clear();
+  batch.max_logn = 0;
+}
+
 void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, size_t out_stride, unsigned logn,
-             uint32_t ncols, LdeShift kind) {
+             uint32_t ncols, LdeShift kind, LdeBatch* batch) {
   if (!ncols) return;
   if (logn > 24) fail(LSK_ERR_ARG, "trace height 2^%u exceeds the supported 2^24", logn);
   NttTables* t = tables(ctx);
   NttTables::Scale* sc = scale_tables(ctx, logn, kind);
   cudaStream_t st = ctx->stream;
+  if (logn <= LOG_BLOCK && batch) {
+    for (uint32_t c = 0; c < ncols; c++)
+      batch->jobs.push_back(LdeSmallJob{in + (size_t)c * in_stride, out + (size_t)c * out_stride, sc->a.p, logn});
+    batch->max_logn = std::max(batch->max_logn, logn);
+    return;
+  }
   if (logn <= LOG_BLOCK) {
     unsigned n = 1u << logn;
     unsigned threads = n / 2 < 32 ? 32 : (n / 2 > 1024 ? 1024 : n / 2);

@@ -10,6 +10,8 @@
 // bit-reversed order (the commitment layout: leaf r of the Merkle tree is row r), so that rows
 // [0, N) are the coset g*H_N and rows [N, 2N) the coset g*w_2N*H_N.
 #pragma once
+#include <vector>
+
 #include "device.cuh"
 
 namespace lsk {
@@ -20,10 +22,25 @@ enum class LdeShift : int {
   QuotChunk1 = 2,  // in_shift = g * w_2N        (quotient chunk 1 lives on g * w_2N * H_N)
 };
 
+// Columns of small matrices (N <= 2^12: one CTA each) collected over a prover phase and extended by ONE
+// launch at flush time: a shard has many small chips and their launches are pure latency.
+struct LdeSmallJob {
+  const uint32_t* in;
+  uint32_t* out;
+  const uint2* scale;   // the (logn, kind) coset-scale table
+  uint32_t logn;
+};
+struct LdeBatch {
+  std::vector<LdeSmallJob> jobs;
+  unsigned max_logn = 0;
+};
+void lde_flush(lsk_ctx* ctx, LdeBatch& batch);
+
 void init_ntt_kernels();
 void ntt_ctx_destroy(lsk_ctx* ctx);
 // in_stride / out_stride: distance in words between consecutive columns.
+// With `batch`, matrices of N <= 2^12 are only queued (lde_flush extends them); larger ones launch at once.
 void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, size_t out_stride, unsigned logn,
-             uint32_t ncols, LdeShift kind);
+             uint32_t ncols, LdeShift kind, LdeBatch* batch = nullptr);
 
 }  // namespace lsk

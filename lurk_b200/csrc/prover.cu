@@ -216,6 +216,7 @@ static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record
   auto sd = std::make_unique<ShardState>();
   sd->shard = shard;
   std::vector<MatRef> refs;
+  LdeBatch small_ldes;
   for (auto& it : items) {
     const ChipH& c = m.chips[it.chip];
     size_t n = (size_t)1 << it.logn;
@@ -243,7 +244,7 @@ static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record
         tr.upload(pv.data(), pv.size());
       }
     }
-    lde_dev(ctx, tr.p, n, lde.p, 2 * n, it.logn, c.width, LdeShift::Trace);
+    lde_dev(ctx, tr.p, n, lde.p, 2 * n, it.logn, c.width, LdeShift::Trace, &small_ldes);
     refs.push_back(MatRef{lde.p, 2 * n, it.logn + 1, c.width});
     sd->chip_ids.push_back(it.chip);
     sd->logn.push_back(it.logn);
@@ -251,6 +252,7 @@ static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record
     sd->main_lde.push_back(std::move(lde));
   }
   if (refs.empty()) fail(LSK_ERR_ARG, "shard %u has no chips", shard);
+  lde_flush(ctx, small_ldes);
   pt.mark("trace + main LDE");
   merkle_commit_dev(ctx, refs, sd->main_tree);
   merkle_root_host(ctx, sd->main_tree, sd->main_root);
@@ -293,6 +295,8 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   std::vector<DevBuf<uint32_t>> perm_lde(nchips);
   DevBuf<Ext> cums(ctx, nchips), scratch(ctx, max_n);
   std::vector<MatRef> refs;
+  LdeBatch small_ldes;
+  std::vector<DevBuf<uint32_t>> small_perms;  // natural-domain traces of queued small LDEs, alive until the flush
   for (size_t i = 0; i < nchips; i++) {
     const ChipH& c = m.chips[sd.chip_ids[i]];
     const ChipDev& d = m.dchips[sd.chip_ids[i]];
@@ -302,10 +306,13 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     perm_lde[i].alloc(ctx, 2 * n * pcols);
     perm_trace_dev(ctx, d, sd.main[i].p, n, c.prep_width ? m.prep_trace.p : nullptr, n, sd.logn[i], chal_alpha, d_beta.p,
                    perm.p, n, scratch.p, cums.p + i);
-    lde_dev(ctx, perm.p, n, perm_lde[i].p, 2 * n, sd.logn[i], pcols, LdeShift::Trace);
+    lde_dev(ctx, perm.p, n, perm_lde[i].p, 2 * n, sd.logn[i], pcols, LdeShift::Trace, &small_ldes);
     refs.push_back(MatRef{perm_lde[i].p, 2 * n, sd.logn[i] + 1, pcols});
+    if (sd.logn[i] <= 12) small_perms.push_back(std::move(perm));
     sd.main[i].release();  // the natural-domain trace is not needed past this point
   }
+  lde_flush(ctx, small_ldes);
+  small_perms.clear();
   pt.mark("perm trace + LDE");
   MerkleTreeDev perm_tree;
   merkle_commit_dev(ctx, refs, perm_tree);
@@ -327,10 +334,17 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   refs.clear();
   {
     DevBuf<uint32_t> qv(ctx, 2 * max_n * 4);
+    LdeBatch small_ldes;
+    std::vector<DevBuf<uint32_t>> small_qv;  // quotient values of the queued small LDEs
     for (size_t i = 0; i < nchips; i++) {
       const ChipH& c = m.chips[sd.chip_ids[i]];
       const ChipDev& d = m.dchips[sd.chip_ids[i]];
       size_t n = (size_t)1 << sd.logn[i];
+      uint32_t* qvp = qv.p;
+      if (sd.logn[i] <= 12) {
+        small_qv.emplace_back(ctx, 2 * n * 4);
+        qvp = small_qv.back().p;
+      }
       QuotientArgs a{};
       a.main = sd.main_lde[i].p; a.mstride = 2 * n;
       a.prep = c.prep_width ? m.prep_lde.p : nullptr; a.pstride = 2 * n;
@@ -342,15 +356,16 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       a.cum_sum = cums.p + i;
       a.chal_alpha = chal_alpha;
       a.logn = sd.logn[i];
-      a.out = qv.p; a.ostride = 2 * n;
+      a.out = qvp; a.ostride = 2 * n;
       quotient_dev(ctx, d, a);
       for (int j = 0; j < 2; j++) {
         quot_lde[2 * i + j].alloc(ctx, 2 * n * 4);
-        lde_dev(ctx, qv.p + (size_t)j * n, 2 * n, quot_lde[2 * i + j].p, 2 * n, sd.logn[i], 4,
-                j ? LdeShift::QuotChunk1 : LdeShift::QuotChunk0);
+        lde_dev(ctx, qvp + (size_t)j * n, 2 * n, quot_lde[2 * i + j].p, 2 * n, sd.logn[i], 4,
+                j ? LdeShift::QuotChunk1 : LdeShift::QuotChunk0, &small_ldes);
         refs.push_back(MatRef{quot_lde[2 * i + j].p, 2 * n, sd.logn[i] + 1, 4});
       }
     }
+    lde_flush(ctx, small_ldes);
   }
   pt.mark("quotient + LDE");
   MerkleTreeDev quot_tree;

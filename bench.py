@@ -237,14 +237,16 @@ def run_ours(args):
     pk, vk = m.setup()
     q = QueryRecord.new(top)
     t0 = time.perf_counter()
-    out = execute_by_name(top, entry, [world * (1 << L) - 1], q)
+    K = args.shards_per_gpu
+    out = execute_by_name(top, entry, [world * K * (1 << L) - 1], q)
     q.finalize()                       # row-ordered tables: each rank uploads only its shard's slice
     t_exec = time.perf_counter() - t0
     q.pin()                            # the record is the step's input: keep it in pinned host memory
     cfg = ShardingConfig(1 << L)
     shards = Shard(q, 0, cfg).shard(cfg)
-    assert len(shards) == world, (len(shards), world)
-    mine = shards[rank]
+    assert len(shards) == world * K, (len(shards), world, K)
+    mine_all = [shards[rank + j * world] for j in range(K)]   # rank r proves shards r, r + G, ...
+    mine = mine_all[0]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -255,18 +257,21 @@ def run_ours(args):
     from lurk_b200.parallel import all_gather_roots, gather_shard_proofs
 
     def step_resident():
-        root = m.commit_shard(mine)
-        roots = all_gather_roots({rank: root}, world) if world > 1 else root.reshape(1, 8)
-        return m.prove_shard(mine, roots)
+        mine_roots = {s.index: m.commit_shard(s) for s in mine_all}
+        if world > 1:
+            roots = all_gather_roots(mine_roots, world * K)
+        else:
+            roots = np.stack([mine_roots[i] for i in range(K)])
+        return {s.index: m.prove_shard(s, roots) for s in mine_all}
 
     def step_e2e():
         if world == 1:
-            return m.prove(pk, mine).words
+            return m.prove(pk, mine).words      # lsk_prove: upload, all K shards, one proof
         m.release_record()             # force the host -> device upload of the record
-        part = step_resident()
+        parts = step_resident()
         # the proof of the job is the concatenation of the shard proofs: collect them on rank 0
-        parts = gather_shard_proofs({rank: part}, world, 0)
-        return assemble_proof(parts).words if rank == 0 else part
+        parts = gather_shard_proofs(parts, world * K, 0)
+        return assemble_proof(parts).words if rank == 0 else None
 
     def timed(step, steps, profile):
         total_ms = 0.0
@@ -316,7 +321,7 @@ def run_ours(args):
     prof_ms, prof = timed(step_resident, args.steps, True)
     clk = clocks.stop()
 
-    rows = world * (1 << L)
+    rows = world * K * (1 << L)
     value = rows * args.steps / (res_ms / 1e3)
     e2e_value = rows * args.steps / (e2e_ms / 1e3)
 
@@ -346,7 +351,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": res_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-            "config": {"workload": workload_name(L, world, args.workload), "log_rows": L, "shards": world,
+            "config": {"workload": workload_name(L, world * K, args.workload), "log_rows": L, "shards": world * K,
                        "rows_per_step": rows, "l2": "flushed between timed steps (256 MiB write)",
                        "executor_s": round(t_exec, 3), "output_word0": int(out[0]), "proof_words": int(len(proof)),
                        "proof_verified_ms": verify_ms},
@@ -371,6 +376,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--log-rows", type=int, default=20, help="log2 trace rows per shard (= per GPU)")
+    ap.add_argument("--shards-per-gpu", type=int, default=1,
+                    help="shards each GPU proves per step (configs[3]: --log-rows 22 --shards-per-gpu 4 = 2^24 rows)")
     ap.add_argument("--workload", default="fib", choices=["fib", "cons"],
                     help="fib: BASELINE configs[1] (default); cons: Lurk-shaped hash-chip load (configs[2] substitute)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -74,9 +74,10 @@ struct lsk_machine {
   uint32_t prep_commit[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // two-phase API state
   std::map<uint32_t, std::unique_ptr<ShardState>> pending;
-  std::unique_ptr<DeviceRecord> drec;
+  // device copies of the record: key 0xffffffff = the whole record, else the slice of that shard
+  std::map<uint32_t, std::unique_ptr<DeviceRecord>> drecs;
   const lsk_record* drec_for = nullptr;
-  uint32_t drec_shard = 0, drec_ss = 0;   // slice the device copy holds (drec_ss == 0: the whole record)
+  uint32_t drec_ss = 0;
   size_t last_h2d = 0, last_d2h = 0;
 };
 
@@ -178,16 +179,19 @@ static bool chip_included(const lsk_machine& m, const ChipH& c, const lsk_record
 // whole = false: the caller proves one shard of a sharded record (lsk_shard_commit): upload its slice only
 static DeviceRecord& device_record(lsk_machine& m, const lsk_record& rec, uint32_t shard, uint32_t ss, bool whole) {
   const bool slice = !whole && record_row_ordered(rec) && lsk_record_num_shards(&rec, ss) > 1;
-  const uint32_t want_ss = slice ? ss : 0, want_shard = slice ? shard : 0;
-  if (!m.drec || m.drec_for != &rec || m.drec_ss != want_ss || m.drec_shard != want_shard) {
-    m.drec = std::make_unique<DeviceRecord>();
-    m.drec->upload(m.ctx, *m.prog, rec, want_shard, want_ss);
+  const uint32_t key = slice ? shard : 0xffffffffu;
+  if (m.drec_for != &rec || m.drec_ss != ss) {
+    m.drecs.clear();
     m.drec_for = &rec;
-    m.drec_ss = want_ss;
-    m.drec_shard = want_shard;
-    m.last_h2d += m.drec->h2d_bytes;
+    m.drec_ss = ss;
   }
-  return *m.drec;
+  auto& slot = m.drecs[key];
+  if (!slot) {
+    slot = std::make_unique<DeviceRecord>();
+    slot->upload(m.ctx, *m.prog, rec, slice ? shard : 0, slice ? ss : 0);
+    m.last_h2d += slot->h2d_bytes;
+  }
+  return *slot;
 }
 
 static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record& rec, uint32_t shard, uint32_t ss,
@@ -747,7 +751,7 @@ void lsk_release_record(lsk_machine* m) {
   if (!m) return;
   cudaSetDevice(m->ctx->device);
   m->pending.clear();
-  m->drec.reset();
+  m->drecs.clear();
   m->drec_for = nullptr;
   m->last_h2d = m->last_d2h = 0;
 }
@@ -785,11 +789,11 @@ int lsk_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard_size, uint32
   uint32_t ns = lsk_record_num_shards(rec, shard_size);
   if (!ns) fail(LSK_ERR_ARG, "empty record");
   m->last_h2d = m->last_d2h = 0;
-  m->drec.reset();  // always re-upload: the record is a host buffer owned by the caller
+  m->drecs.clear();  // always re-upload: the record is a host buffer owned by the caller
   m->drec_for = nullptr;
   struct Cleanup {
     lsk_machine* m;
-    ~Cleanup() { m->pending.clear(); m->drec.reset(); m->drec_for = nullptr; }
+    ~Cleanup() { m->pending.clear(); m->drecs.clear(); m->drec_for = nullptr; }
   } cleanup{m};
   std::vector<std::unique_ptr<ShardState>> shards;
   Challenger ch = initial_challenger(*m);

@@ -220,3 +220,72 @@ def test_large_fib_proof_verifies(oracle):
     bad[len(bad) // 2] = (int(bad[len(bad) // 2]) + 1) % P
     with pytest.raises(VerificationError):
         m.verify(vk, bad)
+
+
+def test_full_size_fib_2pow20_default_parameters_verifies():
+    # BASELINE configs[1] at full size with sphinx's default FRI parameters (100 queries, 16 PoW bits): too big
+    # for the CPU prover inside a test, so acceptance is by the product verifier (independent host code), which
+    # must also reject a flipped word anywhere in the 1.1 MB proof
+    from lurk_b200.machine import VerificationError, Verifier
+    top = demo_toplevel()
+    m = new_machine(top, "fib")
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    out = execute_by_name(top, "fib", [(1 << 20) - 1], q)
+    proof = m.prove(pk, Shard.new(q))
+    assert list(q.expect_public_values()) == [(1 << 20) - 1, int(out[0])]
+    m.verify(vk, proof)
+    Verifier(top, "fib", vk).verify(proof)          # the device-free form agrees
+    rng = np.random.default_rng(5)
+    for pos in rng.integers(2, len(proof.words), 6):
+        bad = proof.words.copy()
+        bad[pos] = (int(bad[pos]) + 1) % P
+        with pytest.raises(VerificationError):
+            m.verify(vk, bad)
+    # proving is deterministic (smallest PoW witness): a second prove gives the same bytes
+    assert np.array_equal(m.prove(pk, Shard.new(q)).words, proof.words)
+
+
+def test_default_shard_size_sharding_2pow22():
+    # ShardingConfig::default() = 2^22 rows (src/lair/execute.rs:226-241): 2^22 + 5 rows -> 2 shards, ragged tail;
+    # exercises the 3-pass (4,3,3) middle LDE kernel at t = 10 and the sliced record upload
+    top = demo_toplevel()
+    opts = SphinxCoreOpts(num_queries=12, proof_of_work_bits=10)
+    m = new_machine(top, "fib", opts=opts)
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    execute_by_name(top, "fib", [(1 << 22) + 4], q)
+    q.finalize()
+    shards = Shard.new(q).shard(ShardingConfig.default())
+    assert len(shards) == 2
+    whole = m.prove(pk, Shard.new(q))
+    assert whole.num_shards() == 2
+    m.verify(vk, whole)
+    roots = np.stack([m.commit_shard(s) for s in shards])
+    parts = [m.prove_shard(s, roots) for s in shards]
+    m.release_record()
+    assert np.array_equal(assemble_proof(parts).words, whole.words)
+
+
+def test_lde_2pow22_is_linear_and_extends_constants():
+    rng = np.random.default_rng(22)
+    h = 1 << 22
+    a = rng.integers(0, P, size=(h, 1), dtype=np.uint32)
+    b = rng.integers(0, P, size=(h, 1), dtype=np.uint32)
+    s = ((a.astype(np.uint64) + b) % P).astype(np.uint32)
+    la, lb, ls = gpu_coset_lde(a, 0), gpu_coset_lde(b, 0), gpu_coset_lde(s, 0)
+    assert np.array_equal(((la.astype(np.uint64) + lb) % P).astype(np.uint32), ls)
+    assert (gpu_coset_lde(np.full((h, 1), 7, dtype=np.uint32), 0) == 7).all()
+    # the LDE restricted to the original domain's coset is NOT the input, but extending x -> x (degree 1) must give
+    # the coset points themselves: row r of the output is g * w_{2N}^bitrev(r)
+    w = pow(0x1A427A41, 1 << (27 - 22), P)
+    xs = np.empty(h, dtype=np.uint64)
+    acc = 1
+    for i in range(h):      # natural-order domain H_N
+        xs[i] = acc
+        acc = acc * w % P
+    lx = gpu_coset_lde(xs.astype(np.uint32).reshape(h, 1), 0)[:, 0]
+    w2 = pow(0x1A427A41, 1 << (27 - 23), P)
+    for r in (0, 1, 2, 12345, 2 * h - 1):
+        br = int(format(r, "023b")[::-1], 2)
+        assert int(lx[r]) == 31 * pow(w2, br, P) % P

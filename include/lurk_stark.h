@@ -162,6 +162,23 @@ int lsk_coset_lde(lsk_ctx* ctx, const uint32_t* rows, size_t h, size_t w, int sh
 int lsk_merkle_root(lsk_ctx* ctx, const uint32_t* const* mats, const size_t* hs, const size_t* ws, size_t nmats,
                     uint32_t out8[8]);
 
+/* ---- column-sharded commit of ONE matrix over G GPUs (BASELINE north star) ---------------
+ * The per-GPU pieces; lurk_b200/parallel.py::column_sharded_commit strings them together with NCCL
+ * (one all-to-all turning the column partition into a row partition, one all-gather of G digests).
+ * `_dev` pointers are DEVICE pointers in the library's internal layout: column-major, rows in bit-reversed
+ * order, Montgomery form (what lsk_import_columns_dev produces from a canonical row-major host matrix).
+ *   1. every rank extends its w/G columns:            lsk_lde_columns_dev      (N -> 2N rows)
+ *   2. all-to-all: rank d receives rows [d 2N/G, (d+1) 2N/G) of every column
+ *   3. every rank hashes its rows and builds its subtree: lsk_merkle_subtree_root_dev
+ *   4. all-gather of the G subtree roots; top log2 G levels: lsk_merkle_join_roots (host)
+ * The result equals lsk_merkle_root of the whole LDE. */
+int lsk_import_columns_dev(lsk_ctx* ctx, const uint32_t* rows, size_t h, size_t w, uint32_t* cols_dev);
+int lsk_lde_columns_dev(lsk_ctx* ctx, const uint32_t* in_dev, size_t in_stride, uint32_t* out_dev, size_t out_stride,
+                        uint32_t logn, uint32_t ncols, int shift_kind);
+int lsk_merkle_subtree_root_dev(lsk_ctx* ctx, const uint32_t* cols_dev, size_t stride, uint32_t log_rows, uint32_t w,
+                                uint32_t root_out8[8]);
+int lsk_merkle_join_roots(const uint32_t* roots, uint32_t count, uint32_t out8[8]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -860,4 +860,59 @@ int lsk_merkle_root(lsk_ctx* ctx, const uint32_t* const* mats, const size_t* hs,
   LSK_API_END
 }
 
+// ---- column-sharded commit: device-pointer pieces strung together by the host layer ----------
+int lsk_import_columns_dev(lsk_ctx* ctx, const uint32_t* rows, size_t h, size_t w, uint32_t* cols_dev) {
+  LSK_API_BEGIN
+  if (!ctx || !rows || !cols_dev || !h || !w || (h & (h - 1))) fail(LSK_ERR_ARG, "bad argument");
+  LSK_CUDA(cudaSetDevice(ctx->device));
+  DevBuf<uint32_t> d_rows(ctx, h * w);
+  d_rows.upload(rows, h * w);
+  import_rows_kernel<<<div_up(h * w, 256), 256, 0, ctx->stream>>>(d_rows.p, h, (uint32_t)w, log2_exact(h), true, cols_dev);
+  LSK_CUDA(cudaGetLastError());
+  LSK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LSK_OK;
+  LSK_API_END
+}
+int lsk_lde_columns_dev(lsk_ctx* ctx, const uint32_t* in_dev, size_t in_stride, uint32_t* out_dev, size_t out_stride,
+                        uint32_t logn, uint32_t ncols, int shift_kind) {
+  LSK_API_BEGIN
+  if (!ctx || !in_dev || !out_dev || shift_kind < 0 || shift_kind > 2) fail(LSK_ERR_ARG, "bad argument");
+  LSK_CUDA(cudaSetDevice(ctx->device));
+  lde_dev(ctx, in_dev, in_stride, out_dev, out_stride, logn, ncols, (LdeShift)shift_kind);
+  return LSK_OK;
+  LSK_API_END
+}
+int lsk_merkle_subtree_root_dev(lsk_ctx* ctx, const uint32_t* cols_dev, size_t stride, uint32_t log_rows, uint32_t w,
+                                uint32_t root_out8[8]) {
+  LSK_API_BEGIN
+  if (!ctx || !cols_dev || !w || !root_out8) fail(LSK_ERR_ARG, "bad argument");
+  LSK_CUDA(cudaSetDevice(ctx->device));
+  MerkleTreeDev tree;
+  merkle_commit_dev(ctx, {MatRef{cols_dev, stride, log_rows, w}}, tree);
+  merkle_root_host(ctx, tree, root_out8);
+  return LSK_OK;
+  LSK_API_END
+}
+int lsk_merkle_join_roots(const uint32_t* roots, uint32_t count, uint32_t out8[8]) {
+  LSK_API_BEGIN
+  if (!roots || !out8 || !count || (count & (count - 1))) fail(LSK_ERR_ARG, "the number of subtree roots must be a power of two");
+  static const HostPerm16 perm;
+  std::vector<uint32_t> cur(roots, roots + 8 * (size_t)count);
+  for (auto& x : cur) {
+    if (x >= P) fail(LSK_ERR_ARG, "non-canonical digest");
+    x = to_mont(x);
+  }
+  for (uint32_t n = count; n > 1; n >>= 1) {
+    for (uint32_t i = 0; i < n / 2; i++) {
+      uint32_t st[16];
+      memcpy(st, &cur[16 * i], 64);
+      perm.permute(st);
+      memcpy(&cur[8 * i], st, 32);
+    }
+  }
+  for (int k = 0; k < 8; k++) out8[k] = from_mont(cur[k]);
+  return LSK_OK;
+  LSK_API_END
+}
+
 }  // extern "C"

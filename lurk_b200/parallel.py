@@ -86,3 +86,77 @@ def prove_distributed(machine, shards: Sequence, dst: int = 0) -> Optional[Machi
     roots = all_gather_roots({s: machine.commit_shard(shards[s]) for s in mine}, n)
     parts = gather_shard_proofs({s: machine.prove_shard(shards[s], roots) for s in mine}, n, dst)
     return assemble_proof(parts) if parts is not None else None
+
+
+# ------------------------------------------------------------------------------------------------
+# Column-sharded commit of one matrix (the second multi-GPU mode of the north star)
+# ------------------------------------------------------------------------------------------------
+def column_partition(width: int, world: int, rank: int) -> range:
+    """Columns of rank `rank`: equal slices (the all-to-all below needs them equal; pad the matrix with
+    zero columns on the caller's side if world does not divide width -- zero columns change the root)."""
+    assert width % world == 0, "column_sharded_commit needs world | width"
+    per = width // world
+    return range(rank * per, (rank + 1) * per)
+
+
+def column_sharded_commit(ctx, cols_dev: "torch.Tensor", log_n: int, shift_kind: int = 0, timers: Optional[dict] = None):
+    """Commit the coset LDE of an (N x w) matrix whose COLUMNS are spread over the ranks.
+
+    cols_dev: this rank's (w / G, N) int32 CUDA tensor in the library's internal layout (column-major, rows
+    bit-reversed, Montgomery form; `import_columns`).  NTT/LDE is column-local; Merkle leaves need whole rows,
+    so one all-to-all turns the column partition into a row partition (each rank keeps rows
+    [d * 2N/G, (d+1) * 2N/G) of ALL columns), each rank hashes its rows and builds its subtree, the G subtree
+    roots are all-gathered and the top log2(G) levels are joined on every rank.  Returns the root (8
+    canonical words), identical on every rank and identical to the single-GPU commitment.
+    """
+    import ctypes
+    from . import _native as N
+    world, rank = dist.get_world_size(), dist.get_rank()
+    assert world & (world - 1) == 0, "the number of GPUs must be a power of two"
+    wl, n = cols_dev.shape
+    assert n == 1 << log_n and cols_dev.dtype == torch.int32 and cols_dev.is_contiguous()
+    dev = cols_dev.device
+    stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    with torch.cuda.stream(stream):
+        ev[0].record(stream)
+        lde = torch.empty((wl, 2 * n), dtype=torch.int32, device=dev)
+        N.check(N.lib().lsk_lde_columns_dev(ctx.h, ctypes.c_void_p(cols_dev.data_ptr()), ctypes.c_size_t(n),
+                                            ctypes.c_void_p(lde.data_ptr()), ctypes.c_size_t(2 * n), log_n, wl,
+                                            shift_kind))
+        ev[1].record(stream)
+        rows = 2 * n // world
+        # [wl][G][rows] -> [G][wl][rows]: block d goes to rank d; received blocks are ordered by source rank,
+        # i.e. by global column index, so the result is the column-major (w x rows) slab of this rank's rows
+        send = lde.view(wl, world, rows).permute(1, 0, 2).contiguous()
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send)
+        ev[2].record(stream)
+        root = np.zeros(8, dtype=np.uint32)
+        N.check(N.lib().lsk_merkle_subtree_root_dev(ctx.h, ctypes.c_void_p(recv.data_ptr()), ctypes.c_size_t(rows),
+                                                    (rows - 1).bit_length(), wl * world, N.vp(root)))
+        ev[3].record(stream)
+        mine = torch.from_numpy(root.astype(np.int64)).to(dev)
+        outs = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(outs, mine)
+        roots = np.stack([o.cpu().numpy().astype(np.uint32) for o in outs])
+        ev[4].record(stream)
+    out = np.zeros(8, dtype=np.uint32)
+    N.check(N.lib().lsk_merkle_join_roots(N.vp(N.u32(roots)), world, N.vp(out)))
+    if timers is not None:
+        torch.cuda.synchronize()
+        for name, a, b in (("lde", 0, 1), ("all_to_all", 1, 2), ("leaves+subtree", 2, 3), ("all_gather_roots", 3, 4)):
+            timers[name] = timers.get(name, 0.0) + ev[a].elapsed_time(ev[b])
+    return out
+
+
+def import_columns(ctx, rows_host: np.ndarray, device) -> "torch.Tensor":
+    """Canonical row-major (N x w) host matrix -> (w, N) int32 CUDA tensor in the internal layout."""
+    import ctypes
+    from . import _native as N
+    rows_host = N.u32(rows_host)
+    h, w = rows_host.shape
+    out = torch.empty((w, h), dtype=torch.int32, device=device)
+    N.check(N.lib().lsk_import_columns_dev(ctx.h, N.vp(rows_host), ctypes.c_size_t(h), ctypes.c_size_t(w),
+                                           ctypes.c_void_p(out.data_ptr())))
+    return out

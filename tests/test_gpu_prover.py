@@ -289,3 +289,20 @@ def test_lde_2pow22_is_linear_and_extends_constants():
     for r in (0, 1, 2, 12345, 2 * h - 1):
         br = int(format(r, "023b")[::-1], 2)
         assert int(lx[r]) == 31 * pow(w2, br, P) % P
+
+
+def test_column_sharded_commit_tool_single_rank():
+    # SURVEY 8e.2 pieces (lsk_lde_columns_dev, all-to-all, lsk_merkle_subtree_root_dev, lsk_merkle_join_roots)
+    # through the real NCCL code path with a one-rank group; the tool asserts root == lsk_merkle_root.
+    # (G = 2, 4, 8 are run with `gpurun --gpus G` and recorded in profiles/r01_column_sharded_commit.jsonl.)
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29577", RANK="0", LOCAL_RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "column_sharded_commit.py"), "--log-rows", "13",
+                          "--width", "24", "--steps", "1"], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == 1 and line["value"] > 0

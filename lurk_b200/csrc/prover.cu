@@ -137,7 +137,30 @@ static void compile_chip(lsk_ctx* ctx, const ChipH& c, uint32_t num_pv, ChipDev&
       push_affine(inter, it.mult, c.width, c.prep_width);
       for (auto& v : it.values) push_affine(inter, v, c.width, c.prep_width);
     }
+  // device form: fold the operand kinds of add / sub / mul into the opcode where both operands are a
+  // register, a main-trace cell of the row or a constant (stark_kernels.cuh)
   std::vector<uint32_t> code = c.code;
+  auto kind_of = [](uint32_t w) -> int {  // tag 0 reg, 1 const, 2 main local
+    switch (w >> 28) { case 0: return 0; case 2: return 1; case 1: return 2; default: return -1; }
+  };
+  for (size_t i = 0; i < code.size(); i += 4) {
+    uint32_t op = code[i], a = code[i + 2], b = code[i + 3];
+    if (op >= COP_ADD && op <= COP_MUL) {
+      int ka = kind_of(a), kb = kind_of(b);
+      if (ka >= 0 && kb >= 0) {
+        code[i] = 9 * (op - COP_ADD) + 3 * (uint32_t)ka + (uint32_t)kb;
+        code[i + 2] = a & 0x0fffffffu;
+        code[i + 3] = b & 0x0fffffffu;
+      } else {
+        code[i] = op == COP_ADD ? QOP_ADD : op == COP_SUB ? QOP_SUB : QOP_MUL;
+      }
+    } else if (op == COP_NEG) {
+      code[i] = QOP_NEG;
+    } else {  // COP_ASSERT
+      if ((a >> 28) == 0) code[i] = QOP_ASSERT_REG, code[i + 2] = a & 0x0fffffffu;
+      else code[i] = QOP_ASSERT;
+    }
+  }
   if (code.empty()) code.assign(4, 0), d.ninstr = 0;
   if (consts.empty()) consts.push_back(0);
   if (inter.empty()) inter.push_back(0);

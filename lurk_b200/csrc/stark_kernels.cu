@@ -192,16 +192,34 @@ __global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientC
   };
   Ext acc = ext_zero();
   uint32_t ci = 0;
+  // Device form of the constraint program (prover.cu::compile_chip): the operand kinds of the common
+  // instructions are folded into the opcode -- op = 9 * {add, sub, mul} + 3 * kind(a) + kind(b) with kind
+  // 0 register, 1 main-trace cell of this row, 2 constant -- so that one indexed branch replaces the
+  // opcode switch plus two operand-tag switches; everything else takes the generic tagged path.
+  auto R = [&](uint32_t i) { return regs[i]; };
+  auto M = [&](uint32_t i) { return a.main[(size_t)i * a.mstride + r]; };
+  auto C = [&](uint32_t i) { return __ldg(consts + i); };
+#define LSK_Q3(BASE, FN, KA, LA)                                                  \
+  case BASE + 3 * KA + 0: regs[ins.y] = FN(LA(ins.z), R(ins.w)); break;           \
+  case BASE + 3 * KA + 1: regs[ins.y] = FN(LA(ins.z), M(ins.w)); break;           \
+  case BASE + 3 * KA + 2: regs[ins.y] = FN(LA(ins.z), C(ins.w)); break;
+#define LSK_Q9(BASE, FN) LSK_Q3(BASE, FN, 0, R) LSK_Q3(BASE, FN, 1, M) LSK_Q3(BASE, FN, 2, C)
   for (uint32_t pc = 0; pc < ninstr; pc++) {
-    uint4 ins = __ldg(code + pc);
+    const uint4 ins = __ldg(code + pc);
     switch (ins.x) {
-      case 1: regs[ins.y] = fadd(operand(ins.z), operand(ins.w)); break;
-      case 2: regs[ins.y] = fsub(operand(ins.z), operand(ins.w)); break;
-      case 3: regs[ins.y] = fmul(operand(ins.z), operand(ins.w)); break;
-      case 4: regs[ins.y] = fneg(operand(ins.z)); break;
-      default: acc = eadd(acc, emul_base(a.apow[a.n_total - 1 - (ci++)], operand(ins.z))); break;
+      LSK_Q9(0, fadd)
+      LSK_Q9(9, fsub)
+      LSK_Q9(18, fmul)
+      case QOP_NEG: regs[ins.y] = fneg(operand(ins.z)); break;
+      case QOP_ASSERT_REG: acc = eadd(acc, emul_base(a.apow[a.n_total - 1 - (ci++)], regs[ins.z])); break;
+      case QOP_ASSERT: acc = eadd(acc, emul_base(a.apow[a.n_total - 1 - (ci++)], operand(ins.z))); break;
+      case QOP_ADD: regs[ins.y] = fadd(operand(ins.z), operand(ins.w)); break;
+      case QOP_SUB: regs[ins.y] = fsub(operand(ins.z), operand(ins.w)); break;
+      default: regs[ins.y] = fmul(operand(ins.z), operand(ins.w)); break;
     }
   }
+#undef LSK_Q9
+#undef LSK_Q3
   // LogUp constraints (sphinx eval_permutation_constraints)
   Cells cells{a.main, a.mstride, a.prep, a.pstride, r};
   const uint32_t* s = inter;

@@ -11,8 +11,11 @@
 
 namespace lsk {
 
+// device opcodes of the constraint program: 0..26 = 9 * {add, sub, mul} + 3 * kind(a) + kind(b) with raw
+// indices (kind 0 register, 1 main-trace cell of the row, 2 constant); the rest keep tagged operands
+enum : uint32_t { QOP_NEG = 27, QOP_ASSERT_REG = 28, QOP_ASSERT = 29, QOP_ADD = 30, QOP_SUB = 31, QOP_MUL = 32 };
 struct ChipDev {  // a chip's compiled AIR, device resident (built once per machine)
-  DevBuf<uint32_t> code;    // constraint program, 4 words per instruction
+  DevBuf<uint32_t> code;    // constraint program, 4 words per instruction (device opcodes, see above)
   DevBuf<uint32_t> consts;  // Montgomery
   DevBuf<uint32_t> inter;   // interaction stream: {kind_mont sign nvalues affine(mult) affine(value)*}*, sends first
   uint32_t ninstr = 0, nint = 0, n_regs = 0, width = 0, prep_width = 0, pw = 0, n_constraints = 0;

@@ -162,6 +162,17 @@ int lsk_coset_lde(lsk_ctx* ctx, const uint32_t* rows, size_t h, size_t w, int sh
 int lsk_merkle_root(lsk_ctx* ctx, const uint32_t* const* mats, const size_t* hs, const size_t* ws, size_t nmats,
                     uint32_t out8[8]);
 
+/* ---- C++ host layer (csrc/host_lair.h, host_air.cpp): what the reference does in Rust before it can call the
+ * prover -- Toplevel::new (expand + compile the `func!` definitions, src/lair/toplevel.rs), FuncChip layout
+ * (src/lair/func_chip.rs:90-277) and Chip::new's symbolic run of every Air::eval (src/lair/lair_chip.rs:
+ * 196-231).  `surface` is the FuncE list as words (format in host_lair.cpp); results are malloc'd word images
+ * (free with lsk_words_free): the program image for lsk_program_load and the 'MACH' blob for lsk_machine_new /
+ * lsk_vk_new.  C++ callers use the builder API of host_lair.h directly. */
+int lsk_host_compile_toplevel(const uint32_t* surface, size_t n, uint32_t** words, size_t* len);
+int lsk_host_chip_vector(const uint32_t* surface, size_t n, uint32_t entry_func, uint32_t** words, size_t* len);
+int lsk_host_demo_toplevel(uint32_t** words, size_t* len);   /* demo_toplevel, src/lair/mod.rs:53-112 */
+void lsk_words_free(uint32_t* words);
+
 /* ---- column-sharded commit of ONE matrix over G GPUs (BASELINE north star) ---------------
  * The per-GPU pieces; lurk_b200/parallel.py::column_sharded_commit strings them together with NCCL
  * (one all-to-all turning the column partition into a row partition, one all-gather of G digests).

@@ -29,6 +29,21 @@ def build(jobs: int = 8):
     subprocess.check_call(["make", "-s", f"-j{jobs}", "-C", os.path.join(_PKG, "csrc")])
 
 
+def build_cpp_tests():
+    """Compile the C++ programs under tests/cpp against the in-tree library (host builder API + C ABI)."""
+    root = os.path.dirname(_PKG)
+    outs = []
+    for name in ("host_layout_test", "fib_prove"):
+        src = os.path.join(root, "tests", "cpp", name + ".cpp")
+        out = os.path.join(root, "tests", "cpp", name)
+        if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(src), os.path.getmtime(LIB_PATH)):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", os.path.join(_PKG, "csrc"), "-I",
+                                   os.path.join(root, "include"), src, "-o", out, "-L", _PKG, "-llurkstark",
+                                   "-Wl,-rpath," + _PKG])
+        outs.append(out)
+    return outs
+
+
 def declared_symbols():
     """Every `lsk_*` function declared in include/lurk_stark.h."""
     src = open(HEADER).read()

@@ -390,6 +390,7 @@ class Toplevel:
             self.funcs.append(Func(fe.name, fe.invertible, fe.partial, i, fe.input_size, fe.output_size, body))
         self._by_name = {f.name: f for f in self.funcs}
         self._serial: Optional[np.ndarray] = None
+        self.funcs_e: List[FuncE] = list(funcs_e)
 
     @classmethod
     def new_pure(cls, funcs_e: Sequence[FuncE]) -> "Toplevel":
@@ -479,11 +480,90 @@ class Toplevel:
             op_aux = 3 * ((len(a[0]) + 1) // 2)
         st.aux += op_aux
 
+    # ---- surface image: the FuncE list as words, for the C++ host layer (csrc/host_lair.cpp) -----------
+    def surface_image(self) -> np.ndarray:
+        strs: Dict[str, int] = {}
+
+        def sid(name: str) -> int:
+            if name not in strs:
+                strs[name] = len(strs)
+            return strs[name]
+
+        KIND = {"const": 0, "array": 1, "add": 2, "sub": 3, "mul": 4, "div": 5, "inv": 6, "not": 7, "eq": 8,
+                "assert_eq": 9, "assert_ne": 10, "contains": 11, "call": 12, "preimg": 13, "store": 14, "load": 15,
+                "extern_call": 16, "range_u8": 17, "return": 18, "if": 19, "match": 20, "match_many": 21}
+
+        def vars_(vs) -> List[int]:
+            out = [len(vs)]
+            for v in vs:
+                out += [sid(_vname(v)), _vsize(v)]
+            return out
+
+        def names(ns) -> List[int]:
+            return [len(ns)] + [sid(n) for n in ns]
+
+        def block(stmts) -> List[int]:
+            out = [len(stmts)]
+            for st in stmts:
+                out += stmt(st)
+            return out
+
+        def stmt(st: St) -> List[int]:
+            k, a = st.kind, st.args
+            out = [KIND[k]]
+            if k == "const":
+                out += [sid(a[0]), a[1]]
+            elif k == "array":
+                out += [sid(a[0]), len(a[1])] + list(a[1])
+            elif k in ("add", "sub", "mul", "div", "eq"):
+                out += [sid(_vname(a[0])), sid(a[1]), sid(a[2])]
+            elif k in ("inv", "not"):
+                out += [sid(_vname(a[0])), sid(a[1])]
+            elif k in ("assert_eq", "assert_ne", "contains"):
+                out += [sid(a[0]), sid(a[1])]
+            elif k in ("call", "preimg", "extern_call"):
+                out += vars_(a[0]) + [sid(a[1])] + names(a[2])
+            elif k == "store":
+                out += [sid(a[0])] + names(a[1])
+            elif k == "load":
+                out += vars_(a[0]) + [sid(a[1])]
+            elif k in ("range_u8", "return"):
+                out += names(a[0])
+            elif k == "if":
+                out += [sid(a[0])] + block(a[1]) + ([1] + block(a[2]) if a[2] is not None else [0])
+            elif k in ("match", "match_many"):
+                out += [sid(a[0]), len(a[1])]
+                for keys, blk in a[1]:
+                    out += [len(keys)] + list(keys) + block(blk)
+                out += ([1] + block(a[2]) if a[2] is not None else [0]) + [int(a[3])]
+            else:
+                raise ValueError(k)
+            return out
+
+        body: List[int] = [len(self.chips)]
+        for c in self.chips:
+            body += [sid(c.name), c.kind, c.input_size, c.output_size, c.witness_size, c.require_size]
+        body.append(len(self.funcs_e))
+        for fe in self.funcs_e:
+            body += [sid(fe.name)] + vars_(fe.input_params) + [fe.output_size, int(fe.invertible), int(fe.partial)]
+            body += block(fe.body)
+        head = [0x4C535246, len(strs)]
+        for name in strs:                    # insertion order = index order
+            raw = name.encode()
+            head.append(len(raw))
+            head += list(np.frombuffer(raw + b"\0" * (-len(raw) % 4), dtype=np.uint32)) if raw else []
+        return np.asarray(head + body, dtype=np.uint32)
+
     # ---- flat serialisation ---------------------------------------------------------------------
     def serialize(self) -> np.ndarray:
-        """Flat u32 program image consumed by the native library (layout in include/lurk_stark.h)."""
-        if self._serial is not None:
-            return self._serial
+        """Flat u32 program image consumed by the native library (layout in csrc/program.h), compiled by the
+        C++ host layer (csrc/host_lair.cpp); `serialize_py` is the same pass in Python."""
+        if self._serial is None:
+            from . import host
+            self._serial = host.compile_toplevel(self.surface_image())
+        return self._serial
+
+    def serialize_py(self) -> np.ndarray:
         out: List[int] = [0x4c414952, len(self.funcs), len(self.chips)]  # 'LAIR'
         for c in self.chips:
             out += [c.kind, c.input_size, c.output_size, c.witness_size, c.require_size]
@@ -494,8 +574,7 @@ class Toplevel:
             ls = self.compute_layout_sizes(f)
             out += [f.input_size, f.output_size, int(f.partial), int(f.invertible), ls.aux, ls.sel, ls.max_map]
             self._ser_block(f.body, [1] * f.input_size, out)
-        self._serial = np.asarray(out, dtype=np.uint32)
-        return self._serial
+        return np.asarray(out, dtype=np.uint32)
 
     def _ser_block(self, b: Block, degrees: List[int], out: List[int]):
         start = len(out)

@@ -73,10 +73,8 @@ class Verifier:
                  blob: Optional[np.ndarray] = None):
         opts = opts or SphinxCoreOpts.default()
         if blob is None:
-            chip = FuncChip.from_name(entry, toplevel)
-            f = chip.func
-            num_pv = f.input_size + f.output_size + (DEPTH_W if f.partial else 0)
-            blob = serialize_machine(build_chip_vector(chip), num_pv)
+            from . import host
+            blob = host.chip_vector_blob(toplevel.surface_image(), toplevel.func_by_name(entry).index)
         self.blob = N.u32(blob)
         self.h = ctypes.c_void_p()
         commit = N.u32(vk.commit)
@@ -106,8 +104,9 @@ class LairMachineProgram:
 class StarkMachine:
     """sphinx_core::stark::StarkMachine<BabyBearPoseidon2, LairChip> for one Toplevel + entry func."""
 
-    def __init__(self, chips: List[ChipDesc], num_pv: int, toplevel: Toplevel, entry: Func,
-                 ctx: Optional[N.Context] = None, opts: Optional[SphinxCoreOpts] = None):
+    def __init__(self, chips: Optional[List[ChipDesc]], num_pv: int, toplevel: Toplevel, entry: Func,
+                 ctx: Optional[N.Context] = None, opts: Optional[SphinxCoreOpts] = None,
+                 blob: Optional[np.ndarray] = None):
         self._chips = chips
         self.num_pv = num_pv
         self.toplevel = toplevel
@@ -115,7 +114,7 @@ class StarkMachine:
         self.ctx = ctx or N.default_context()
         self.opts = opts or SphinxCoreOpts.default()
         self.program = program_of(toplevel)
-        self.blob = serialize_machine(chips, num_pv)
+        self.blob = blob if blob is not None else serialize_machine(chips, num_pv)
         self.h = ctypes.c_void_p()
         N.check(N.lib().lsk_machine_new(self.ctx.h, self.program.h, entry.index, N.vp(self.blob),
                                         ctypes.c_size_t(len(self.blob)), self.opts.num_queries,
@@ -130,6 +129,8 @@ class StarkMachine:
             pass
 
     def chips(self) -> List[ChipDesc]:
+        if self._chips is None:     # introspection only: the Python restatement of the capture
+            self._chips = build_chip_vector(FuncChip(self.entry, self.toplevel))
         return self._chips
 
     def setup(self, program: Optional[LairMachineProgram] = None):
@@ -190,10 +191,12 @@ def new_machine(toplevel: Toplevel, entry: Optional[str] = None, ctx: Optional[N
     here any func of the toplevel, e.g. "fib" of demo_toplevel as in src/lair/lair_chip.rs:246-276)."""
     if entry is None:
         entry = "lurk_main"
-    chip = FuncChip.from_name(entry, toplevel)
-    f = chip.func
+    from . import host
+    f = toplevel.func_by_name(entry)
     num_pv = f.input_size + f.output_size + (DEPTH_W if f.partial else 0)
-    return StarkMachine(build_chip_vector(chip), num_pv, toplevel, f, ctx, opts)
+    # Chip::new for the whole chip vector, in the C++ host layer (csrc/host_air.cpp)
+    blob = host.chip_vector_blob(toplevel.surface_image(), f.index)
+    return StarkMachine(None, num_pv, toplevel, f, ctx, opts, blob=blob)
 
 
 def assemble_proof(shard_words: List[np.ndarray]) -> MachineProof:

@@ -306,3 +306,12 @@ def test_column_sharded_commit_tool_single_rank():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["n_gpus"] == 1 and line["value"] > 0
+
+
+def test_cpp_end_to_end():
+    # tests/cpp/fib_prove.cpp: demo_toplevel built with the C++ builder, executed, proved on the GPU and verified
+    # through the C ABI only -- the shape of src/lair/lair_chip.rs:246-276 with no Python in the loop
+    import subprocess
+    exe = N.build_cpp_tests()[1]
+    out = subprocess.run([exe, "5000"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "verified" in out.stdout, out.stderr + out.stdout

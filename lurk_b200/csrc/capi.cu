@@ -40,11 +40,6 @@ int lsk_ctx_create(int device, lsk_ctx** out) {
   cudaDeviceProp prop;
   LSK_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
-  // keep freed blocks in the stream-ordered pool: steady-state proving never calls the driver allocator
-  cudaMemPool_t pool;
-  LSK_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-  uint64_t threshold = UINT64_MAX;
-  LSK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
   init_poseidon2_kernels();
   init_trace_kernels();
   init_prover_kernels();
@@ -59,8 +54,12 @@ void lsk_ctx_destroy(lsk_ctx* ctx) {
   ntt_ctx_destroy(ctx);
   for (auto& r : ctx->prof.recs) cudaEventDestroy(r.a), cudaEventDestroy(r.b);
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
+  ctx->pool.trim();
   cudaStreamDestroy(ctx->stream);
-  delete ctx;
+  ctx->stream = nullptr;
+  // objects that still own device buffers (a machine freed after its context) release into this pool later:
+  // keep the (small) context object alive for them rather than leave them a dangling pointer
+  if (ctx->pool.live_bytes == 0) delete ctx;
 }
 void* lsk_ctx_stream(lsk_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 int lsk_ctx_sync(lsk_ctx* ctx) {

@@ -315,3 +315,20 @@ def test_cpp_end_to_end():
     exe = N.build_cpp_tests()[1]
     out = subprocess.run([exe, "5000"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "verified" in out.stdout, out.stderr + out.stdout
+
+
+def test_lair_shard_test_ackermann_3_18():
+    # the reference's heaviest prover test, `lair_shard_test` (src/lair/trace.rs:654-727, #[ignore]d there):
+    # ackermann(3, 18) has 5 242 889 queries -> two shards at the default 2^22 shard size; prove, verify
+    top = goldens.toplevel_for("ackermann")
+    m = new_machine(top, "ackermann")          # sphinx default FRI parameters
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    out = execute_by_name(top, "ackermann", [3, 18], q)
+    assert int(out[0]) == 2097149                 # 2^(18+3) - 3
+    assert q.num_queries(0) == 5242889            # trace.rs:685-687
+    shard = Shard.new(q)
+    assert len(shard.shard(ShardingConfig.default())) == 2
+    proof = m.prove(pk, shard)
+    assert proof.num_shards() == 2
+    m.verify(vk, proof)

@@ -468,7 +468,58 @@ def _eval_chip(b: SymbolicBuilder, chip, is_real: Expr, inp, witness, nonce, req
     """Chipset::eval dispatch (src/core/chipset.rs:133-171)."""
     if chip.kind in (1, 2, 3):
         return eval_poseidon_chipset(b, {1: 24, 2: 32, 3: 40}[chip.kind], is_real, inp, witness)
+    if chip.kind in (4, 5, 6):
+        return eval_u64_chipset(b, chip.kind, is_real, inp, witness, nonce, requires)
     raise NotImplementedError(f"AIR capture of extern chip {chip.name!r} (kind {chip.kind})")
+
+
+def _assert_add(b: SymbolicBuilder, lhs, rhs, out, is_real: Expr):
+    """AddWitness::assert_add (src/gadgets/unsigned/add.rs:19-60): byte-wise lhs + rhs = out with boolean carries"""
+    base_inv = pow(256, P - 2, P)
+    with b.when(is_real):
+        carry = b.const(0)
+        for o, x, y in zip(out, lhs, rhs):
+            total = x + y + carry
+            carry = (total - o) * base_inv
+            b.assert_bool(carry)
+    return carry
+
+
+def eval_u64_chipset(b: SymbolicBuilder, kind: int, is_real: Expr, inp, witness, nonce, requires) -> List[Expr]:
+    """U64::{Add, Sub, LessThan}::eval (src/core/u64.rs:170-222): Sum64 / Diff64 (src/gadgets/unsigned/add.rs:
+    63-175) and Compare64 (src/gadgets/unsigned/cmp.rs:49-128); kinds 4 / 5 / 6."""
+    in1, in2 = list(inp[:8]), list(inp[8:16])
+    rec = _ByteAirRecord()
+    if kind in (4, 5):
+        result = list(witness[:8])
+        rec.range_check_u8_iter(result, is_real)            # UncheckedWord::into_checked
+        if kind == 4:
+            _assert_add(b, in1, in2, result, is_real)
+        else:                                               # result + rhs = lhs
+            _assert_add(b, result, in2, in1, is_real)
+        out = result
+    else:
+        is_comp, lhs_limb, rhs_limb, diff_inv, is_lt = witness[:8], witness[8], witness[9], witness[10], witness[11]
+        with b.when(is_real):
+            is_equal = b.const(1)
+            for i in reversed(range(8)):
+                b.assert_bool(is_comp[i])
+                is_equal = is_equal - is_comp[i]
+                with b.when(is_equal):
+                    b.assert_eq(in1[i], in2[i])
+            b.assert_bool(is_equal)
+            sel_l, sel_r = b.const(0), b.const(0)
+            for i in range(8):
+                sel_l = sel_l + in1[i] * is_comp[i]
+                sel_r = sel_r + in2[i] * is_comp[i]
+            b.assert_eq(sel_l, lhs_limb)
+            b.assert_eq(sel_r, rhs_limb)
+            is_different = 1 - is_equal
+            b.assert_eq((lhs_limb - rhs_limb) * diff_inv, is_different)
+        rec.less_than(lhs_limb, rhs_limb, is_lt, is_real)
+        out = [is_lt]
+    rec.require_all(b, nonce, requires)
+    return out
 
 
 def _external_linear(s: List[Expr]) -> List[Expr]:

@@ -330,8 +330,71 @@ std::vector<E> eval_poseidon_chipset(Builder& b, int width, E is_real, const std
   return output;
 }
 
-std::vector<E> eval_chip(Builder& b, const ChipInfo& chip, E is_real, const std::vector<E>& inp, const std::vector<E>& witness) {
+// AddWitness::assert_add (src/gadgets/unsigned/add.rs:19-60): byte-wise lhs + rhs = out with boolean carries
+void assert_add(Builder& b, const std::vector<E>& lhs, const std::vector<E>& rhs, const std::vector<E>& out, E is_real) {
+  Graph& g = b.g;
+  uint64_t base = 256, r = 1, e = Pm - 2;
+  while (e) {
+    if (e & 1) r = r * base % Pm;
+    base = base * base % Pm;
+    e >>= 1;
+  }
+  const uint32_t base_inv = (uint32_t)r;
+  Builder::When w(b, is_real);
+  E carry = b.k(0);
+  for (size_t i = 0; i < out.size(); i++) {
+    E total = g.add(g.add(lhs[i], rhs[i]), carry);
+    carry = g.mul(g.sub(total, out[i]), b.k(base_inv));
+    b.assert_bool(carry);
+  }
+}
+
+// U64::{Add, Sub, LessThan}::eval (src/core/u64.rs:170-222): Sum64 / Diff64 (src/gadgets/unsigned/add.rs:63-175)
+// and Compare64 (src/gadgets/unsigned/cmp.rs:49-128); chip kinds 4 / 5 / 6
+std::vector<E> eval_u64_chipset(Builder& b, uint32_t kind, E is_real, const std::vector<E>& inp, const std::vector<E>& witness,
+                                E nonce, const std::vector<Cols::Req>& requires_) {
+  Graph& g = b.g;
+  std::vector<E> in1(inp.begin(), inp.begin() + 8), in2(inp.begin() + 8, inp.begin() + 16), out;
+  ByteAirRecord rec;
+  if (kind == 4 || kind == 5) {
+    std::vector<E> result(witness.begin(), witness.begin() + 8);
+    rec.range_check_u8_iter(b, result, is_real);  // UncheckedWord::into_checked
+    if (kind == 4) assert_add(b, in1, in2, result, is_real);
+    else assert_add(b, result, in2, in1, is_real);  // result + rhs = lhs
+    out = result;
+  } else {
+    E lhs_limb = witness[8], rhs_limb = witness[9], diff_inv = witness[10], is_lt = witness[11];
+    {
+      Builder::When w(b, is_real);
+      E is_equal = b.k(1);
+      for (int i = 7; i >= 0; i--) {
+        b.assert_bool(witness[i]);
+        is_equal = g.sub(is_equal, witness[i]);
+        Builder::When we(b, is_equal);
+        b.assert_eq(in1[i], in2[i]);
+      }
+      b.assert_bool(is_equal);
+      E sel_l = b.k(0), sel_r = b.k(0);
+      for (int i = 0; i < 8; i++) {
+        sel_l = g.add(sel_l, g.mul(in1[i], witness[i]));
+        sel_r = g.add(sel_r, g.mul(in2[i], witness[i]));
+      }
+      b.assert_eq(sel_l, lhs_limb);
+      b.assert_eq(sel_r, rhs_limb);
+      E is_different = g.sub(b.k(1), is_equal);
+      b.assert_eq(g.mul(g.sub(lhs_limb, rhs_limb), diff_inv), is_different);
+    }
+    rec.less_than(b, lhs_limb, rhs_limb, is_lt, is_real);
+    out = {is_lt};
+  }
+  rec.require_all(b, nonce, requires_);
+  return out;
+}
+
+std::vector<E> eval_chip(Builder& b, const ChipInfo& chip, E is_real, const std::vector<E>& inp, const std::vector<E>& witness,
+                         E nonce, const std::vector<Cols::Req>& requires_) {
   if (chip.kind >= 1 && chip.kind <= 3) return eval_poseidon_chipset(b, chip.kind == 1 ? 24 : chip.kind == 2 ? 32 : 40, is_real, inp, witness);
+  if (chip.kind >= 4 && chip.kind <= 6) return eval_u64_chipset(b, chip.kind, is_real, inp, witness, nonce, requires_);
   throw std::runtime_error("AIR capture of extern chip " + chip.name + " is not implemented");
 }
 
@@ -492,8 +555,9 @@ void eval_op(Builder& b, const Op& op, Cols& cols, E sel, VMap& vmap, const Topl
       std::vector<E> inp, witness;
       for (uint32_t i : op.xs) inp.push_back(vmap[i].first);
       for (uint32_t i = 0; i < chip.witness_size; i++) witness.push_back(cols.next_aux());
-      for (uint32_t i = 0; i < chip.require_size; i++) cols.next_require();
-      for (E o : eval_chip(b, chip, sel, inp, witness)) vmap.push_back({o, 1});
+      std::vector<Cols::Req> reqs;
+      for (uint32_t i = 0; i < chip.require_size; i++) reqs.push_back(cols.next_require());
+      for (E o : eval_chip(b, chip, sel, inp, witness, nonce, reqs)) vmap.push_back({o, 1});
     } break;
   }
 }

@@ -267,6 +267,31 @@ struct Executor {
         } break;
         case OP_EXTERN: {
           const uint32_t* chip = prog.chip(op[1]);
+          if (chip[0] >= 4 && chip[0] <= 6) {  // U64::{Add, Sub, LessThan}::execute, src/core/u64.rs:76-128
+            if (op[2] != 16) fail(LSK_ERR_EXEC, "bad extern chip call");
+            uint8_t a[8], b[8];
+            for (int i = 0; i < 16; i++) {
+              uint32_t v = m[op[3 + i]];
+              if (v > 255) fail(LSK_ERR_EXEC, "u64 chip input is not a byte");  // into_u64: try_into().unwrap()
+              (i < 8 ? a[i] : b[i - 8]) = (uint8_t)v;
+            }
+            if (chip[0] == 6) {  // CompareWitness::populate, src/gadgets/unsigned/cmp.rs:23-46
+              int i = 7;
+              while (i >= 0 && a[i] == b[i]) i--;
+              uint32_t l = i >= 0 ? a[i] : 0, r = i >= 0 ? b[i] : 0;
+              new_lookup(byte_record(l, r, 2), f.nonce, req_stack);
+              vals.push_back(l < r ? 1u : 0u);
+            } else {             // Sum / Diff::populate: wrapping result, range-checked in byte pairs
+              uint64_t x = 0, y = 0;
+              for (int i = 7; i >= 0; i--) x = x << 8 | a[i], y = y << 8 | b[i];
+              uint64_t z = chip[0] == 4 ? x + y : x - y;
+              uint32_t out[8];
+              for (int i = 0; i < 8; i++) out[i] = (uint32_t)(z >> (8 * i)) & 255u;
+              for (int i = 0; i < 8; i += 2) new_lookup(byte_record(out[i], out[i + 1], 0), f.nonce, req_stack);
+              vals.insert(vals.end(), out, out + 8);
+            }
+            break;
+          }
           int t = chip_width(chip[0]);
           if (!t || op[2] != (uint32_t)t) fail(LSK_ERR_EXEC, "bad extern chip call");
           uint32_t st[40];

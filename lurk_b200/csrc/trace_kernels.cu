@@ -198,10 +198,44 @@ __device__ void populate_row(const uint32_t* __restrict__ w, uint32_t body, Func
           push_require();
         } break;
         case OP_EXTERN: {
-          uint32_t kind = chips[op[1] * CHIP_WORDS];
+          const uint32_t* chip = chips + op[1] * CHIP_WORDS;
+          const uint32_t kind = chip[0];
           if (kind == 1) extern_poseidon<24, Store>(op, map, map_len, aux, st);
           else if (kind == 2) extern_poseidon<32, Store>(op, map, map_len, aux, st);
           else if (kind == 3) extern_poseidon<40, Store>(op, map, map_len, aux, st);
+          else if (kind >= 4 && kind <= 6) {  // U64::populate_witness, src/core/u64.rs:130-168
+            uint32_t a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = from_mont(map[op[3 + i]]), b[i] = from_mont(map[op[11 + i]]);
+            if (kind == 6) {  // CompareWitness (cmp.rs:12-46): is_comp[8], lhs limb, rhs limb, 1/(lhs - rhs), is_less_than
+              int i = 7;
+              while (i >= 0 && a[i] == b[i]) i--;
+              uint32_t lt = 0;
+              if (i >= 0) {
+                uint32_t l = to_mont(a[i]), r = to_mont(b[i]);
+                st(aux + i, R1);
+                st(aux + 8, l);
+                st(aux + 9, r);
+                st(aux + 10, finv(fsub(l, r)));
+                lt = a[i] < b[i] ? R1 : 0u;
+                st(aux + 11, lt);
+              }
+              map[map_len++] = lt;
+              aux += 12;
+            } else {          // Sum / Diff (add.rs:63-175): the wrapping result's bytes
+              uint64_t x = 0, y = 0;
+#pragma unroll
+              for (int i = 7; i >= 0; i--) x = x << 8 | a[i], y = y << 8 | b[i];
+              const uint64_t z = kind == 4 ? x + y : x - y;
+#pragma unroll
+              for (int i = 0; i < 8; i++) {
+                uint32_t v = to_mont((uint32_t)(z >> (8 * i)) & 255u);
+                map[map_len++] = v;
+                st(aux++, v);
+              }
+            }
+          }
+          for (uint32_t i = 0; i < chip[4]; i++) push_require();  // order: witness, requires (trace.rs:398-406)
         } break;
         case OP_RANGE_U8: {
           uint32_t n = (op[1] + 1) / 2;

@@ -50,3 +50,36 @@ def hash_toplevel():
         ret("d"),
     ])
     return Toplevel([commit_cons, cons_chain, env_chain, h3, h4, h5], chips)
+
+
+U64_CHIPS = [ChipInfo("u64_add", 16, 8, 8, 4, kind=4), ChipInfo("u64_sub", 16, 8, 8, 4, kind=5),
+             ChipInfo("u64_lessthan", 16, 1, 12, 1, kind=6)]
+
+
+def u64_toplevel():
+    """The u64 chipsets Lurk's evaluator uses for fib / lcs / sum (src/core/chipset.rs:34-52, src/core/u64.rs):
+    `add`, `sub`, `less_than` are the funcs of the reference's own u64_add_test / u64_sub_test /
+    u64_lessthan tests (src/core/u64.rs:237-420); `fibu(n)` = the n-th Fibonacci number as a wrapping u64 (8
+    little-endian bytes, one u64_add row per step) and `maxu(a, b)` exercise them inside ordinary funcs."""
+    from .lair import add as add_, match as match_
+    add = func("add", [("a", 8), ("b", 8)], 8, [extern_call([("c", 8)], "u64_add", ["a", "b"]), ret("c")])
+    sub_f = func("sub", [("a", 8), ("b", 8)], 8, [extern_call([("c", 8)], "u64_sub", ["a", "b"]), ret("c")])
+    less_than = func("less_than", [("a", 8), ("b", 8)], 1, [extern_call(["c"], "u64_lessthan", ["a", "b"]), ret("c")])
+    fibu = func("fibu", ["n"], 8, [
+        array("zero", [0] * 8),
+        array("one", [1] + [0] * 7),
+        match_("n", [(0, [ret("zero")]), (1, [ret("one")])]),
+        const("c1", 1),
+        sub("n1", "n", "c1"),
+        call([("a", 8)], "fibu", ["n1"]),
+        sub("n2", "n1", "c1"),
+        call([("b", 8)], "fibu", ["n2"]),
+        extern_call([("r", 8)], "u64_add", ["a", "b"]),
+        ret("r"),
+    ])
+    maxu = func("maxu", [("a", 8), ("b", 8)], 8, [
+        extern_call(["lt"], "u64_lessthan", ["a", "b"]),
+        match_("lt", [(1, [ret("b")])]),
+        ret("a"),
+    ])
+    return Toplevel([add, sub_f, less_than, fibu, maxu], U64_CHIPS)

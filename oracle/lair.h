@@ -346,6 +346,31 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
         } break;
         case OP_EXTERN: {
           const ChipDef& c = top.chips[op.a];
+          if (c.kind >= 4 && c.kind <= 6) {  // U64::{Add, Sub, LessThan}::execute, src/core/u64.rs:76-128
+            uint8_t a[8], b[8];
+            for (int i = 0; i < 16; i++) {
+              uint32_t v = map[op.xs[i]].to_u32();
+              if (v > 255) throw std::runtime_error("u64 chip input is not a byte");
+              (i < 8 ? a[i] : b[i - 8]) = (uint8_t)v;
+            }
+            if (c.kind == 6) {  // cmp.rs:23-46: most significant differing byte pair, (0, 0) when equal
+              int i = 7;
+              while (i >= 0 && a[i] == b[i]) i--;
+              uint32_t l = i >= 0 ? a[i] : 0, r = i >= 0 ? b[i] : 0;
+              requires_.push_back(q.bytes[(uint16_t)(l | (r << 8))].rec[2].new_lookup(nonce));
+              map.push_back(Fp::from_u32(l < r));
+            } else {            // add.rs:71-80,122-131 + UncheckedWord::assign_bytes (unsigned/mod.rs:114-120)
+              uint64_t x = 0, y = 0;
+              for (int i = 7; i >= 0; i--) x = x << 8 | a[i], y = y << 8 | b[i];
+              uint64_t z = c.kind == 4 ? x + y : x - y;
+              for (int i = 0; i < 8; i += 2) {
+                uint32_t b0 = (z >> (8 * i)) & 255u, b1 = (z >> (8 * i + 8)) & 255u;
+                requires_.push_back(q.bytes[(uint16_t)(b0 | (b1 << 8))].rec[0].new_lookup(nonce));
+              }
+              for (int i = 0; i < 8; i++) map.push_back(Fp::from_u32((uint32_t)(z >> (8 * i)) & 255u));
+            }
+            break;
+          }
           int w = chip_width(c.kind);
           if (!w) throw std::runtime_error("unknown extern chip kind");
           Fp st[40];
@@ -587,8 +612,38 @@ static inline void populate_block(const Toplevel& top, const QueryRecord& q, con
         for (Fp v : mm.keys[ptr - 1]) { map.push_back(v); cx.push_aux(v); }
         cx.push_require();
       } break;
-      case OP_EXTERN: {  // trace.rs:388-407 + core/poseidon.rs:65-72
+      case OP_EXTERN: {  // trace.rs:388-407 + core/poseidon.rs:65-72 / core/u64.rs:130-168
         const ChipDef& c = top.chips[op.a];
+        if (c.kind >= 4 && c.kind <= 6) {
+          uint32_t a[8], b[8];
+          for (int i = 0; i < 8; i++) a[i] = map[op.xs[i]].to_u32(), b[i] = map[op.xs[8 + i]].to_u32();
+          if (c.kind == 6) {  // CompareWitness: is_comp[8], lhs_comp_limb, rhs_comp_limb, comp_diff_inv, is_less_than
+            Fp wit[12];
+            for (auto& x : wit) x = Fp::zero();
+            int i = 7;
+            while (i >= 0 && a[i] == b[i]) i--;
+            if (i >= 0) {
+              wit[i] = Fp::one();
+              wit[8] = Fp::from_u32(a[i]);
+              wit[9] = Fp::from_u32(b[i]);
+              wit[10] = fp_inv(wit[8] - wit[9]);
+              wit[11] = Fp::from_u32(a[i] < b[i]);
+            }
+            map.push_back(wit[11]);
+            for (Fp x : wit) cx.push_aux(x);
+          } else {
+            uint64_t x = 0, y = 0;
+            for (int i = 7; i >= 0; i--) x = x << 8 | a[i], y = y << 8 | b[i];
+            uint64_t z = c.kind == 4 ? x + y : x - y;
+            for (int i = 0; i < 8; i++) {
+              Fp v = Fp::from_u32((uint32_t)(z >> (8 * i)) & 255u);
+              map.push_back(v);
+              cx.push_aux(v);
+            }
+          }
+          for (uint32_t i = 0; i < c.require_size; i++) cx.push_require();
+          break;
+        }
         int w = chip_width(c.kind);
         Fp st[40];
         for (int i = 0; i < w; i++) st[i] = map[op.xs[i]];

@@ -157,3 +157,8 @@ def partial_toplevel():
         ret("f", "h"),
     ], partial=True)
     return Toplevel.new_pure([pmain, pfib, twice, pdouble, phalf])
+
+
+def u64_toplevel():
+    from lurk_b200.programs import u64_toplevel as u
+    return u()

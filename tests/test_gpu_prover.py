@@ -165,6 +165,20 @@ def test_partial_func_programs_prove_bit_exact(oracle, fname, args, ss):
         assert np.array_equal(assemble_proof(parts).words, want)
 
 
+@pytest.mark.parametrize("fname,args", [("add", "add"), ("sub", "sub"), ("less_than", "lt"), ("fibu", [200]), ("maxu", "max")])
+def test_u64_chipset_programs_prove_bit_exact(oracle, fname, args):
+    # U64::{Add, Sub, LessThan} witnesses on the GPU + their AIR in the quotient kernel + byte lookups
+    from test_oracle_stark import u64_bytes
+    a = {"add": u64_bytes(2**64 - 1) + u64_bytes(2), "sub": u64_bytes(0) + u64_bytes(1),
+         "lt": u64_bytes(0x0102030405060708) + u64_bytes(0x0102030505060708),
+         "max": u64_bytes(9) + u64_bytes(10**15)}.get(args, args) if isinstance(args, str) else args
+    top = goldens.toplevel_for("u64")
+    m, om, q, proof, want = _prove_both(oracle, top, fname, [a])
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+    m.verify(m.setup()[1], proof)
+
+
 def test_cons_chain_2pow12_verifies(oracle):
     # Lurk-shaped load: the 655-wide hash4 chip dominates (2^12 x 655 main trace); acceptance by the verifier
     top = goldens.toplevel_for("hash")

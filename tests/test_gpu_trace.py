@@ -106,3 +106,16 @@ def test_partial_func_traces_match_oracle(oracle):
         chip = FuncChip.from_name(name, top)
         assert np.array_equal(chip.generate_trace(Shard.new(q)), rec.func_trace(chip.func.index)), name
     assert np.array_equal(BytesChip().generate_trace(Shard.new(q)), rec.bytes_trace(0))
+
+
+def test_u64_chip_traces_match_oracle(oracle):
+    # src/core/u64.rs:130-168 (populate_witness of Sum64 / Diff64 / Compare64) inside func rows
+    top = goldens.toplevel_for("u64")
+    for fname, args in [("fibu", [300]), ("maxu", [9, 0, 0, 0, 0, 0, 0, 1] + [9, 0, 0, 0, 0, 0, 1, 0]),
+                        ("sub", [0] * 8 + [1] + [0] * 7), ("less_than", [5] * 8 + [5] * 8)]:
+        q = QueryRecord.new(top)
+        execute_by_name(top, fname, args, q)
+        rec = _oracle_rec(oracle, top, fname, args)
+        chip = FuncChip.from_name(fname, top)
+        assert np.array_equal(chip.generate_trace(Shard.new(q)), rec.func_trace(chip.func.index)), fname
+        assert np.array_equal(BytesChip().generate_trace(Shard.new(q)), rec.bytes_trace(0)), fname

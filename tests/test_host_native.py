@@ -73,6 +73,28 @@ def test_partial_funcs_depth_provenance(oracle):
         assert q.num_queries(fi) == orec.num_queries(fi)
 
 
+def test_u64_chipsets_executor_matches_oracle(oracle):
+    # src/core/u64.rs:76-128: native executor == oracle, incl. the byte-lookup bookkeeping (public values, counts)
+    from test_oracle_stark import u64_bytes
+    top = goldens.toplevel_for("u64")
+    ot = oracle.OracleToplevel(top.serialize())
+    for fname, args in [("add", u64_bytes(2**64 - 3) + u64_bytes(77)), ("sub", u64_bytes(5) + u64_bytes(2**40)),
+                        ("less_than", u64_bytes(2**56) + u64_bytes(2**56 + 1)), ("fibu", [120]),
+                        ("maxu", u64_bytes(3) + u64_bytes(3))]:
+        f = top.func_by_name(fname)
+        q = QueryRecord.new(top)
+        got = execute_by_name(top, fname, args, q)
+        orec = oracle.OracleRecord(ot)
+        want = orec.execute(f.index, args, f.output_size)
+        assert np.array_equal(got, want), fname
+        assert np.array_equal(q.expect_public_values(), orec.public_values())
+        for fi in range(top.num_funcs()):
+            assert q.num_queries(fi) == orec.num_queries(fi)
+    q = QueryRecord.new(top)
+    with pytest.raises(N.LurkStarkError, match="byte"):
+        execute_by_name(top, "add", [256] + [0] * 15, q)       # into_u64 panics on a non-byte limb
+
+
 def test_total_func_may_not_call_partial():
     # src/lair/execute.rs:1005-1023 (nonpartial_calls_partial: "assertion failed: ctx.partial")
     from lurk_b200.lair import Toplevel, call, func, ret

@@ -103,6 +103,34 @@ def test_partial_funcs_prove_verify(oracle, fname, args):
     assert not om.verify(bad)
 
 
+def u64_bytes(x):
+    return [(x >> (8 * i)) & 255 for i in range(8)]
+
+
+@pytest.mark.parametrize("fname,args,want", [
+    ("add", u64_bytes(200) + u64_bytes(56), u64_bytes(256)),                      # u64_add_test, src/core/u64.rs:237-290
+    ("add", u64_bytes(2**64 - 1) + u64_bytes(2), u64_bytes(1)),                   # wraps
+    ("sub", u64_bytes(256) + u64_bytes(1), u64_bytes(255)),                       # u64_sub_test
+    ("sub", u64_bytes(0) + u64_bytes(1), u64_bytes(2**64 - 1)),
+    ("less_than", u64_bytes(0x0102030405060708) + u64_bytes(0x0102030505060708), [1]),
+    ("less_than", u64_bytes(77) + u64_bytes(77), [0]),                            # equal: the (0, 0) byte lookup
+    ("less_than", u64_bytes(2**63) + u64_bytes(5), [0]),
+    ("fibu", [90], u64_bytes(2880067194370816120)),
+    ("fibu", [100], u64_bytes(354224848179261915075 % 2**64)),                    # wrapping u64 arithmetic
+    ("maxu", u64_bytes(9) + u64_bytes(10**15), u64_bytes(10**15)),
+])
+def test_u64_chipsets_prove_verify(oracle, fname, args, want):
+    # U64::{Add, Sub, LessThan} (src/core/u64.rs): execute, witness, AIR (assert_add carries, CompareWitness) and
+    # their byte lookups; the proof only verifies if all of them are consistent
+    top = goldens.toplevel_for("u64")
+    ot, om, f = oracle_machine(oracle, top, fname)
+    rec = oracle.OracleRecord(ot)
+    out = rec.execute(f.index, args, f.output_size)
+    assert list(out) == want
+    proof = om.prove(rec)
+    assert om.verify(proof), om.last_error
+
+
 def test_multi_shard_roundtrip(oracle):
     # sharding tested with tiny shards as in src/air/debug.rs:119-158; cross-shard lookups must cancel
     top = goldens.toplevel_for("ackermann")

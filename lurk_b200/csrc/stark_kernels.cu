@@ -159,50 +159,69 @@ void perm_trace_dev(lsk_ctx* ctx, const ChipDev& chip, const uint32_t* main, siz
 struct QuotientConsts {
   uint32_t g, w2n, wn_inv, zh[2], inv_zh[2];
 };
-template <int MAXREGS>
+// ROWS rows per thread (rows t, t + 256, ... of the CTA's slab, so every access stays coalesced): the long
+// constraint programs of the hasher chips are bound by instruction fetch / decode and by the latency of the
+// register file in local memory, both of which a second independent row amortises.
+template <int MAXREGS, int ROWS>
 __global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientConsts qc,
                                                         const uint4* __restrict__ code, uint32_t ninstr,
                                                         const uint32_t* __restrict__ consts,
                                                         const uint32_t* __restrict__ inter, uint32_t nint, uint32_t pw) {
   const unsigned l2 = a.logn + 1;
   const size_t n2 = (size_t)1 << l2;
-  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (r >= n2) return;
-  uint32_t i = bitrev32((uint32_t)r, l2);
-  size_t rn = bitrev32((uint32_t)((i + 2) & (n2 - 1)), l2);
-  uint32_t x = fmul(qc.g, fpow(qc.w2n, i));
-  uint32_t zh = qc.zh[i & 1];
-  uint32_t xm1 = fsub(x, R1), xml = fsub(x, qc.wn_inv);
-  uint32_t inv = finv(fmul(xm1, xml));
-  uint32_t sel[3] = {fmul(zh, fmul(inv, xml)), fmul(zh, fmul(inv, xm1)), xml};  // is_first, is_last, is_transition
-  uint32_t regs[MAXREGS];
-  regs[0] = 0;
-  auto operand = [&](uint32_t w) -> uint32_t {
+  const size_t base = (size_t)blockIdx.x * (256 * ROWS) + threadIdx.x;
+  if (base >= n2) return;
+  size_t r[ROWS], rn[ROWS];
+  uint32_t ii[ROWS], sel[ROWS][3];
+  bool live[ROWS];
+  uint32_t regs[ROWS][MAXREGS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    r[k] = base + (size_t)k * 256;
+    live[k] = r[k] < n2;
+    if (!live[k]) r[k] = base;  // recompute a valid row, never stored
+    ii[k] = bitrev32((uint32_t)r[k], l2);
+    rn[k] = bitrev32((uint32_t)((ii[k] + 2) & (n2 - 1)), l2);
+    uint32_t x = fmul(qc.g, fpow(qc.w2n, ii[k]));
+    uint32_t zh = qc.zh[ii[k] & 1];
+    uint32_t xm1 = fsub(x, R1), xml = fsub(x, qc.wn_inv);
+    uint32_t inv = finv(fmul(xm1, xml));
+    sel[k][0] = fmul(zh, fmul(inv, xml));  // is_first
+    sel[k][1] = fmul(zh, fmul(inv, xm1));  // is_last
+    sel[k][2] = xml;                       // is_transition
+    regs[k][0] = 0;
+  }
+  auto operand = [&](int k, uint32_t w) -> uint32_t {
     uint32_t idx = w & 0x0fffffffu;
     switch (w >> 28) {
-      case 0: return regs[idx];
+      case 0: return regs[k][idx];
       case 1: return consts[idx];
-      case 2: return a.main[(size_t)idx * a.mstride + r];
-      case 3: return a.main[(size_t)idx * a.mstride + rn];
-      case 4: return a.prep[(size_t)idx * a.pstride + r];
-      case 5: return a.prep[(size_t)idx * a.pstride + rn];
+      case 2: return a.main[(size_t)idx * a.mstride + r[k]];
+      case 3: return a.main[(size_t)idx * a.mstride + rn[k]];
+      case 4: return a.prep[(size_t)idx * a.pstride + r[k]];
+      case 5: return a.prep[(size_t)idx * a.pstride + rn[k]];
       case 6: return a.pv[idx];
-      default: return sel[idx];
+      default: return sel[k][idx];
     }
   };
-  Ext acc = ext_zero();
+  Ext acc[ROWS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) acc[k] = ext_zero();
   uint32_t ci = 0;
   // Device form of the constraint program (prover.cu::compile_chip): the operand kinds of the common
   // instructions are folded into the opcode -- op = 9 * {add, sub, mul} + 3 * kind(a) + kind(b) with kind
   // 0 register, 1 main-trace cell of this row, 2 constant -- so that one indexed branch replaces the
   // opcode switch plus two operand-tag switches; everything else takes the generic tagged path.
-  auto R = [&](uint32_t i) { return regs[i]; };
-  auto M = [&](uint32_t i) { return a.main[(size_t)i * a.mstride + r]; };
-  auto C = [&](uint32_t i) { return __ldg(consts + i); };
-#define LSK_Q3(BASE, FN, KA, LA)                                                  \
-  case BASE + 3 * KA + 0: regs[ins.y] = FN(LA(ins.z), R(ins.w)); break;           \
-  case BASE + 3 * KA + 1: regs[ins.y] = FN(LA(ins.z), M(ins.w)); break;           \
-  case BASE + 3 * KA + 2: regs[ins.y] = FN(LA(ins.z), C(ins.w)); break;
+  auto R = [&](int k, uint32_t i) { return regs[k][i]; };
+  auto M = [&](int k, uint32_t i) { return a.main[(size_t)i * a.mstride + r[k]]; };
+  auto C = [&](int, uint32_t i) { return __ldg(consts + i); };
+#define LSK_QROWS(EXPR)              \
+  _Pragma("unroll") for (int k = 0; k < ROWS; k++) { EXPR; } \
+  break;
+#define LSK_Q3(BASE, FN, KA, LA)                                                              \
+  case BASE + 3 * KA + 0: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), R(k, ins.w)))           \
+  case BASE + 3 * KA + 1: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), M(k, ins.w)))           \
+  case BASE + 3 * KA + 2: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), C(k, ins.w)))
 #define LSK_Q9(BASE, FN) LSK_Q3(BASE, FN, 0, R) LSK_Q3(BASE, FN, 1, M) LSK_Q3(BASE, FN, 2, C)
   for (uint32_t pc = 0; pc < ninstr; pc++) {
     const uint4 ins = __ldg(code + pc);
@@ -210,47 +229,61 @@ __global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientC
       LSK_Q9(0, fadd)
       LSK_Q9(9, fsub)
       LSK_Q9(18, fmul)
-      case QOP_NEG: regs[ins.y] = fneg(operand(ins.z)); break;
-      case QOP_ASSERT_REG: acc = eadd(acc, emul_base(a.apow[a.n_total - 1 - (ci++)], regs[ins.z])); break;
-      case QOP_ASSERT: acc = eadd(acc, emul_base(a.apow[a.n_total - 1 - (ci++)], operand(ins.z))); break;
-      case QOP_ADD: regs[ins.y] = fadd(operand(ins.z), operand(ins.w)); break;
-      case QOP_SUB: regs[ins.y] = fsub(operand(ins.z), operand(ins.w)); break;
-      default: regs[ins.y] = fmul(operand(ins.z), operand(ins.w)); break;
+      case QOP_NEG: LSK_QROWS(regs[k][ins.y] = fneg(operand(k, ins.z)))
+      case QOP_ASSERT_REG: {
+        const Ext ap = a.apow[a.n_total - 1 - (ci++)];
+        LSK_QROWS(acc[k] = eadd(acc[k], emul_base(ap, regs[k][ins.z])))
+      }
+      case QOP_ASSERT: {
+        const Ext ap = a.apow[a.n_total - 1 - (ci++)];
+        LSK_QROWS(acc[k] = eadd(acc[k], emul_base(ap, operand(k, ins.z))))
+      }
+      case QOP_ADD: LSK_QROWS(regs[k][ins.y] = fadd(operand(k, ins.z), operand(k, ins.w)))
+      case QOP_SUB: LSK_QROWS(regs[k][ins.y] = fsub(operand(k, ins.z), operand(k, ins.w)))
+      default: LSK_QROWS(regs[k][ins.y] = fmul(operand(k, ins.z), operand(k, ins.w)))
     }
   }
 #undef LSK_Q9
 #undef LSK_Q3
-  // LogUp constraints (sphinx eval_permutation_constraints)
-  Cells cells{a.main, a.mstride, a.prep, a.pstride, r};
-  const uint32_t* s = inter;
-  Ext sum_local = ext_zero(), sum_next = ext_zero();
-  for (uint32_t b = 0; 2 * b < nint; b++) {
-    Ext r0, lhs, rhs;
-    uint32_t m0;
-    eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r0, m0);
-    Ext pl = load_ext_cols(a.perm, a.permstride, 4 * b, r);
-    if (2 * b + 1 < nint) {
-      Ext r1;
-      uint32_t m1;
-      eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r1, m1);
-      lhs = emul(emul(pl, r0), r1);
-      rhs = eadd(emul_base(r1, m0), emul_base(r0, m1));
-    } else {
-      lhs = emul(pl, r0);
-      rhs = ext_from_base(m0);
+#undef LSK_QROWS
+  // LogUp constraints (sphinx eval_permutation_constraints), row by row
+#pragma unroll 1
+  for (int k = 0; k < ROWS; k++) {
+    Cells cells{a.main, a.mstride, a.prep, a.pstride, r[k]};
+    const uint32_t* s = inter;
+    uint32_t cj = ci;
+    Ext ac = acc[k];
+    Ext sum_local = ext_zero(), sum_next = ext_zero();
+    for (uint32_t b = 0; 2 * b < nint; b++) {
+      Ext r0, lhs, rhs;
+      uint32_t m0;
+      eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r0, m0);
+      Ext pl = load_ext_cols(a.perm, a.permstride, 4 * b, r[k]);
+      if (2 * b + 1 < nint) {
+        Ext r1;
+        uint32_t m1;
+        eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r1, m1);
+        lhs = emul(emul(pl, r0), r1);
+        rhs = eadd(emul_base(r1, m0), emul_base(r0, m1));
+      } else {
+        lhs = emul(pl, r0);
+        rhs = ext_from_base(m0);
+      }
+      ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], esub(lhs, rhs)));
+      sum_local = eadd(sum_local, pl);
+      sum_next = eadd(sum_next, load_ext_cols(a.perm, a.permstride, 4 * b, rn[k]));
     }
-    acc = eadd(acc, emul(a.apow[a.n_total - 1 - (ci++)], esub(lhs, rhs)));
-    sum_local = eadd(sum_local, pl);
-    sum_next = eadd(sum_next, load_ext_cols(a.perm, a.permstride, 4 * b, rn));
-  }
-  Ext phi_local = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), r);
-  Ext phi_next = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), rn);
-  acc = eadd(acc, emul(a.apow[a.n_total - 1 - (ci++)], emul_base(esub(esub(phi_next, phi_local), sum_next), sel[2])));
-  acc = eadd(acc, emul(a.apow[a.n_total - 1 - (ci++)], emul_base(esub(phi_local, sum_local), sel[0])));
-  acc = eadd(acc, emul(a.apow[a.n_total - 1 - (ci++)], emul_base(esub(phi_local, *a.cum_sum), sel[1])));
-  Ext q = emul_base(acc, qc.inv_zh[i & 1]);
+    Ext phi_local = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), r[k]);
+    Ext phi_next = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), rn[k]);
+    ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(esub(phi_next, phi_local), sum_next), sel[k][2])));
+    ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(phi_local, sum_local), sel[k][0])));
+    ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(phi_local, *a.cum_sum), sel[k][1])));
+    Ext q = emul_base(ac, qc.inv_zh[ii[k] & 1]);
+    if (live[k]) {
 #pragma unroll
-  for (int k = 0; k < 4; k++) a.out[(size_t)k * a.ostride + r] = q.c[k];
+      for (int e = 0; e < 4; e++) a.out[(size_t)e * a.ostride + r[k]] = q.c[e];
+    }
+  }
 }
 
 void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a) {
@@ -264,16 +297,18 @@ void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a) {
   qc.inv_zh[0] = finv(qc.zh[0]);
   qc.inv_zh[1] = finv(qc.zh[1]);
   size_t n2 = (size_t)2 << a.logn;
-  unsigned grid = div_up(n2, 256);
   const uint4* code = reinterpret_cast<const uint4*>(chip.code.p);
   ProfScope ps(ctx, PT_QUOTIENT, 1, (double)n2 * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw + 16.0));
-#define QK(R)                                                                                                    \
-  quotient_kernel<R><<<grid, 256, 0, ctx->stream>>>(a, qc, code, chip.ninstr, chip.consts.p, chip.inter.p, chip.nint, \
-                                                    chip.pw)
-  if (chip.n_regs <= 8) QK(8);
-  else if (chip.n_regs <= 32) QK(32);
-  else if (chip.n_regs <= 128) QK(128);
-  else if (chip.n_regs <= 1024) QK(1024);
+#define QK(R, ROWS)                                                                                              \
+  quotient_kernel<R, ROWS><<<div_up(n2, 256 * ROWS), 256, 0, ctx->stream>>>(a, qc, code, chip.ninstr, chip.consts.p, \
+                                                                            chip.inter.p, chip.nint, chip.pw)
+  // two rows per thread for the long programs (hasher chips) once there are enough rows to fill the machine
+  // (measured on the 655-wide hash4 chip, 2^21 LDE rows: 35.8 ms with one row per thread, 24.1 with two, 29.2 with four)
+  const bool two = chip.ninstr >= 1024 && n2 >= ((size_t)1 << 19);
+  if (chip.n_regs <= 8) QK(8, 1);
+  else if (chip.n_regs <= 32) QK(32, 1);
+  else if (chip.n_regs <= 128) { if (two) QK(128, 2); else QK(128, 1); }
+  else if (chip.n_regs <= 1024) QK(1024, 1);
   else fail(LSK_ERR_ARG, "constraint program needs %u registers (> 1024)", chip.n_regs);
 #undef QK
   LSK_CUDA(cudaGetLastError());
@@ -300,80 +335,6 @@ void bary_weights_dev(lsk_ctx* ctx, unsigned logn, Ext z, Ext* wts) {
 }
 
 constexpr int OPEN_COLS = 8;
-__global__ void __launch_bounds__(256) open_partial_kernel(const uint32_t* __restrict__ m, size_t stride, uint32_t w,
-                                                            size_t n, const Ext* __restrict__ wts0,
-                                                            const Ext* __restrict__ wts1, Ext* __restrict__ partial,
-                                                            uint32_t nchunks) {
-  __shared__ uint32_t red[8][OPEN_COLS * 8];
-  const uint32_t c0 = blockIdx.y * OPEN_COLS;
-  const size_t row0 = (size_t)blockIdx.x * OPEN_ROWS;
-  Ext acc[OPEN_COLS][2];
-#pragma unroll
-  for (int c = 0; c < OPEN_COLS; c++) acc[c][0] = acc[c][1] = ext_zero();
-  for (unsigned k = 0; k < OPEN_ROWS / 256; k++) {
-    size_t r = row0 + k * 256 + threadIdx.x;
-    if (r >= n) break;
-    Ext w0 = wts0[r], w1 = wts1[r];
-#pragma unroll
-    for (int c = 0; c < OPEN_COLS; c++) {
-      if (c0 + c < w) {
-        uint32_t v = m[(size_t)(c0 + c) * stride + r];
-        acc[c][0] = eadd(acc[c][0], emul_base(w0, v));
-        acc[c][1] = eadd(acc[c][1], emul_base(w1, v));
-      }
-    }
-  }
-  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int c = 0; c < OPEN_COLS; c++)
-#pragma unroll
-    for (int p = 0; p < 2; p++)
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        uint32_t v = acc[c][p].c[e];
-#pragma unroll
-        for (int d = 16; d >= 1; d >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
-        if (lane == 0) red[warp][(c * 2 + p) * 4 + e] = v;
-      }
-  __syncthreads();
-  if (threadIdx.x < OPEN_COLS * 8) {
-    uint32_t v = 0;
-#pragma unroll
-    for (int wv = 0; wv < 8; wv++) v = fadd(v, red[wv][threadIdx.x]);
-    uint32_t cp = threadIdx.x / 4, e = threadIdx.x % 4;  // cp = c * 2 + p
-    uint32_t c = c0 + cp / 2;
-    if (c < w) partial[((size_t)(c * 2 + (cp & 1)) * nchunks + blockIdx.x)].c[e] = v;
-  }
-}
-__global__ void __launch_bounds__(128) open_reduce_kernel(const Ext* __restrict__ partial, uint32_t nchunks,
-                                                           Ext* __restrict__ out) {
-  __shared__ Ext red[4];
-  const Ext* p = partial + (size_t)blockIdx.x * nchunks;
-  Ext acc = ext_zero();
-  for (uint32_t k = threadIdx.x; k < nchunks; k += 128) acc = eadd(acc, p[k]);
-#pragma unroll
-  for (int e = 0; e < 4; e++) {
-    uint32_t v = acc.c[e];
-#pragma unroll
-    for (int d = 16; d >= 1; d >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
-    acc.c[e] = v;
-  }
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) out[blockIdx.x] = eadd(eadd(red[0], red[1]), eadd(red[2], red[3]));
-}
-void open_columns_dev(lsk_ctx* ctx, const uint32_t* m, size_t stride, uint32_t w, unsigned logn, const Ext* wts0,
-                      const Ext* wts1, Ext* partial, Ext* out) {
-  if (!w) return;
-  size_t n = (size_t)1 << logn;
-  uint32_t nchunks = div_up(n, OPEN_ROWS);
-  ProfScope ps(ctx, PT_OPEN, 2, (double)n * (4.0 * w + 32.0));
-  open_partial_kernel<<<dim3(nchunks, div_up(w, OPEN_COLS)), 256, 0, ctx->stream>>>(m, stride, w, n, wts0, wts1, partial,
-                                                                                    nchunks);
-  open_reduce_kernel<<<w * 2, 128, 0, ctx->stream>>>(partial, nchunks, out);
-  LSK_CUDA(cudaGetLastError());
-}
-
 struct OpenGroup { uint32_t mat, c0; };
 __global__ void __launch_bounds__(256) open_partial_batch_kernel(const OpenMat* __restrict__ mats,
                                                                   const OpenGroup* __restrict__ groups, size_t n,
@@ -567,17 +528,6 @@ uint32_t grind_dev(lsk_ctx* ctx, const uint32_t state[16], const uint32_t* pendi
 }
 
 // ---- query gathers -------------------------------------------------------------------------------------------
-__global__ void gather_kernel(const GatherJob* __restrict__ jobs, uint32_t* __restrict__ out) {
-  const GatherJob j = jobs[blockIdx.x];
-  for (uint32_t k = threadIdx.x; k < j.count; k += 32) out[j.dst + k] = from_mont(j.p[j.first + (size_t)k * j.stride]);
-}
-void gather_dev(lsk_ctx* ctx, const GatherJob* jobs_dev, uint32_t njobs, uint32_t* out) {
-  if (!njobs) return;
-  ProfScope ps(ctx, PT_GATHER, 1, 0.0);
-  gather_kernel<<<njobs, 32, 0, ctx->stream>>>(jobs_dev, out);
-  LSK_CUDA(cudaGetLastError());
-}
-
 __global__ void __launch_bounds__(256) query_assemble_kernel(const QuerySeg* __restrict__ segs, uint32_t nsegs,
                                                               const uint32_t* __restrict__ indices, uint32_t wpq,
                                                               uint32_t* __restrict__ out) {

@@ -49,13 +49,10 @@ void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a);
 // ---- openings --------------------------------------------------------------------------------------
 // wts[r] = barycentric weight of row r (< N) of the coset g*H_N (bit-reversed) for the point z
 void bary_weights_dev(lsk_ctx* ctx, unsigned logn, Ext z, Ext* wts);
-// out[c * 2 + p] = sum_r wts_p[r] * m[c][r] for c < w, p < 2 (wts1 may alias wts0 when only one
-// point is needed).  partial: scratch of w * 2 * ceil(N / OPEN_ROWS) Ext.
+// out[mat.out_off + c * 2 + p] = sum_r wts_p[r] * m[c][r] for c < w, p < 2, for ALL matrices of one height in
+// two launches (a shard has ~5 matrices per chip and most chips are small); one_point: both outputs use
+// wts0 (quotient chunks).
 constexpr unsigned OPEN_ROWS = 2048;
-void open_columns_dev(lsk_ctx* ctx, const uint32_t* m, size_t stride, uint32_t w, unsigned logn, const Ext* wts0,
-                      const Ext* wts1, Ext* partial, Ext* out);
-// All matrices of one height in two launches (a shard has ~5 matrices per chip and most chips are small):
-// out[mat.out_off + c * 2 + p] as above; one_point: both outputs use wts0 (quotient chunks).
 struct OpenMat {
   const uint32_t* p;
   uint64_t stride;
@@ -83,15 +80,7 @@ void fri_fold_dev(lsk_ctx* ctx, const Ext* cur, unsigned logh, const Ext* beta_d
 // state: 16 canonical words; pending: the challenger's input buffer (n_pending < 8 canonical words)
 uint32_t grind_dev(lsk_ctx* ctx, const uint32_t state[16], const uint32_t* pending, unsigned n_pending, unsigned bits);
 
-// ---- query gathers -----------------------------------------------------------------------------------
-struct GatherJob {  // copies `count` canonical words to out[dst ..]
-  const uint32_t* p;
-  uint64_t stride;  // words between consecutive items (matrix: column stride; digests / ext: 1)
-  uint64_t first;   // word offset of the first item
-  uint32_t count, dst;
-};
-void gather_dev(lsk_ctx* ctx, const GatherJob* jobs_dev, uint32_t njobs, uint32_t* out);
-
+// ---- query phase ---------------------------------------------------------------------------------------
 // Query phase: every FRI query has the same shape, so the host describes ONE query as a list of
 // segments and the device instantiates it for each sampled index, writing the proof words of all
 // queries (literals included) in their final order.  A segment is `count` words at dst:

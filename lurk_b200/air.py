@@ -283,6 +283,9 @@ class _ByteAirRecord:
     def less_than(self, i1, i2, r, is_real):
         self.records.append(([3, i1, i2, r], is_real))
 
+    def range_check_u16(self, i, is_real):
+        self.records.append(([2, i], is_real))
+
     def require_all(self, b: SymbolicBuilder, nonce, requires):
         assert len(requires) == len(self.records)
         cv = lambda x: x if isinstance(x, Expr) else b.const(x)
@@ -468,7 +471,7 @@ def _eval_chip(b: SymbolicBuilder, chip, is_real: Expr, inp, witness, nonce, req
     """Chipset::eval dispatch (src/core/chipset.rs:133-171)."""
     if chip.kind in (1, 2, 3):
         return eval_poseidon_chipset(b, {1: 24, 2: 32, 3: 40}[chip.kind], is_real, inp, witness)
-    if chip.kind in (4, 5, 6):
+    if chip.kind in (4, 5, 6, 7, 8, 9):
         return eval_u64_chipset(b, chip.kind, is_real, inp, witness, nonce, requires)
     raise NotImplementedError(f"AIR capture of extern chip {chip.name!r} (kind {chip.kind})")
 
@@ -485,9 +488,56 @@ def _assert_add(b: SymbolicBuilder, lhs, rhs, out, is_real: Expr):
     return carry
 
 
+def _eval_compare(b: SymbolicBuilder, wit, lhs, rhs, rec: "_ByteAirRecord", is_real: Expr):
+    """CompareWitness::eval (src/gadgets/unsigned/cmp.rs:49-128) -> (is_less_than, is_equal);
+    wit = is_comp[W] ++ [lhs_comp_limb, rhs_comp_limb, comp_diff_inv, is_less_than]"""
+    w = len(lhs)
+    is_comp, lhs_limb, rhs_limb, diff_inv, is_lt = wit[:w], wit[w], wit[w + 1], wit[w + 2], wit[w + 3]
+    with b.when(is_real):
+        is_equal = b.const(1)
+        for i in reversed(range(w)):
+            b.assert_bool(is_comp[i])
+            is_equal = is_equal - is_comp[i]
+            with b.when(is_equal):
+                b.assert_eq(lhs[i], rhs[i])
+        b.assert_bool(is_equal)
+        sel_l, sel_r = b.const(0), b.const(0)
+        for i in range(w):
+            sel_l = sel_l + lhs[i] * is_comp[i]
+            sel_r = sel_r + rhs[i] * is_comp[i]
+        b.assert_eq(sel_l, lhs_limb)
+        b.assert_eq(sel_r, rhs_limb)
+        is_different = 1 - is_equal
+        b.assert_eq((lhs_limb - rhs_limb) * diff_inv, is_different)
+    rec.less_than(lhs_limb, rhs_limb, is_lt, is_real)
+    return is_lt, is_equal
+
+
+def _eval_product(b: SymbolicBuilder, wit, lhs, rhs, rec: "_ByteAirRecord", is_real: Expr):
+    """Product::eval = MulWitness::assert_mul + range-checked result (src/gadgets/unsigned/mul.rs:68-164);
+    wit = carry[W] ++ result[W]"""
+    w = len(lhs)
+    carry, result = wit[:w], list(wit[w:2 * w])
+    products = [b.const(0) for _ in range(w)]
+    for i in range(w):
+        for j in range(w):
+            if i + j < w:
+                products[i + j] = products[i + j] + lhs[i] * rhs[j]
+    carry_prev = b.const(0)
+    for k in range(w):
+        rec.range_check_u16(carry[k], is_real)
+        out = result[k] + carry[k] * 256
+        with b.when(is_real):
+            b.assert_eq(products[k] + carry_prev, out)
+        carry_prev = carry[k]
+    rec.range_check_u8_iter(result, is_real)
+    return result
+
+
 def eval_u64_chipset(b: SymbolicBuilder, kind: int, is_real: Expr, inp, witness, nonce, requires) -> List[Expr]:
-    """U64::{Add, Sub, LessThan}::eval (src/core/u64.rs:170-222): Sum64 / Diff64 (src/gadgets/unsigned/add.rs:
-    63-175) and Compare64 (src/gadgets/unsigned/cmp.rs:49-128); kinds 4 / 5 / 6."""
+    """U64::eval (src/core/u64.rs:170-222), kinds 4..9 = Add, Sub, LessThan, IsZero, Mul, DivRem: Sum64 / Diff64
+    (src/gadgets/unsigned/add.rs:63-175), Compare64 (cmp.rs:49-128), IsZero64 (is_zero.rs:46-156), Product64
+    (mul.rs:68-164), DivRem64 (div_rem.rs:62-103)."""
     in1, in2 = list(inp[:8]), list(inp[8:16])
     rec = _ByteAirRecord()
     if kind in (4, 5):
@@ -498,26 +548,39 @@ def eval_u64_chipset(b: SymbolicBuilder, kind: int, is_real: Expr, inp, witness,
         else:                                               # result + rhs = lhs
             _assert_add(b, result, in2, in1, is_real)
         out = result
-    else:
-        is_comp, lhs_limb, rhs_limb, diff_inv, is_lt = witness[:8], witness[8], witness[9], witness[10], witness[11]
+    elif kind == 6:
+        out = [_eval_compare(b, witness[:12], in1, in2, rec, is_real)[0]]
+    elif kind == 7:                                         # IsZeroOrEqual::eval_is_zero
+        inverses, is_zero = witness[:8], witness[8]
         with b.when(is_real):
-            is_equal = b.const(1)
-            for i in reversed(range(8)):
-                b.assert_bool(is_comp[i])
-                is_equal = is_equal - is_comp[i]
-                with b.when(is_equal):
-                    b.assert_eq(in1[i], in2[i])
-            b.assert_bool(is_equal)
-            sel_l, sel_r = b.const(0), b.const(0)
-            for i in range(8):
-                sel_l = sel_l + in1[i] * is_comp[i]
-                sel_r = sel_r + in2[i] * is_comp[i]
-            b.assert_eq(sel_l, lhs_limb)
-            b.assert_eq(sel_r, rhs_limb)
-            is_different = 1 - is_equal
-            b.assert_eq((lhs_limb - rhs_limb) * diff_inv, is_different)
-        rec.less_than(lhs_limb, rhs_limb, is_lt, is_real)
-        out = [is_lt]
+            b.assert_bool(is_zero)
+        with b.when(is_real):
+            lc = b.const(0)
+            for x, inv in zip(in1, inverses):
+                with b.when(is_zero):
+                    b.assert_zero(x)
+                lc = lc + x * inv
+            b.assert_eq(lc, 1 - is_zero)
+        out = [is_zero]
+    elif kind == 8:
+        out = _eval_product(b, witness[:16], in1, in2, rec, is_real)
+    else:                                                   # DivRem::eval, (a, b) = (in1, in2)
+        b_inv, q = witness[:8], list(witness[8:16])
+        w_qb, w_r, w_lt, w_cmp = witness[16:32], list(witness[32:40]), witness[40:50], witness[50:62]
+        with b.when(is_real):                               # IsZeroWitness::assert_non_zero(b)
+            lc = b.const(0)
+            for x, inv in zip(in2, b_inv):
+                lc = lc + x * inv
+            b.assert_one(lc)
+        rec.range_check_u8_iter(q, is_real)
+        qb = _eval_product(b, w_qb, q, in2, rec, is_real)
+        rec.range_check_u8_iter(w_r, is_real)               # Diff::eval: r + qb = a
+        _assert_add(b, w_r, qb, in1, is_real)
+        _assert_less_than(b, w_lt, w_r, in2, rec, is_real)
+        lt, eq_ = _eval_compare(b, w_cmp, qb, in1, rec, is_real)
+        with b.when(is_real):
+            b.assert_one(lt + eq_)
+        out = q + w_r
     rec.require_all(b, nonce, requires)
     return out
 

@@ -195,6 +195,7 @@ struct ByteAirRecord {
       records.push_back({{b.k(1), xs[i], i + 1 < xs.size() ? xs[i + 1] : b.k(0)}, is_real});
   }
   void less_than(Builder& b, E i1, E i2, E r, E is_real) { records.push_back({{b.k(3), i1, i2, r}, is_real}); }
+  void range_check_u16(Builder& b, E i, E is_real) { records.push_back({{b.k(2), i}, is_real}); }
   void require_all(Builder& b, E nonce, const std::vector<Cols::Req>& requires_) {
     if (requires_.size() != records.size()) throw std::runtime_error("byte record / require count mismatch");
     for (size_t i = 0; i < records.size(); i++) {
@@ -349,43 +350,121 @@ void assert_add(Builder& b, const std::vector<E>& lhs, const std::vector<E>& rhs
   }
 }
 
-// U64::{Add, Sub, LessThan}::eval (src/core/u64.rs:170-222): Sum64 / Diff64 (src/gadgets/unsigned/add.rs:63-175)
-// and Compare64 (src/gadgets/unsigned/cmp.rs:49-128); chip kinds 4 / 5 / 6
+// CompareWitness::eval (src/gadgets/unsigned/cmp.rs:49-128) -> (is_less_than, is_equal);
+// wit = is_comp[W] ++ [lhs_comp_limb, rhs_comp_limb, comp_diff_inv, is_less_than]
+std::pair<E, E> eval_compare(Builder& b, const std::vector<E>& wit, const std::vector<E>& lhs, const std::vector<E>& rhs,
+                             ByteAirRecord& rec, E is_real) {
+  Graph& g = b.g;
+  const int w = (int)lhs.size();
+  E lhs_limb = wit[w], rhs_limb = wit[w + 1], diff_inv = wit[w + 2], is_lt = wit[w + 3], is_equal;
+  {
+    Builder::When wr(b, is_real);
+    is_equal = b.k(1);
+    for (int i = w - 1; i >= 0; i--) {
+      b.assert_bool(wit[i]);
+      is_equal = g.sub(is_equal, wit[i]);
+      Builder::When we(b, is_equal);
+      b.assert_eq(lhs[i], rhs[i]);
+    }
+    b.assert_bool(is_equal);
+    E sel_l = b.k(0), sel_r = b.k(0);
+    for (int i = 0; i < w; i++) {
+      sel_l = g.add(sel_l, g.mul(lhs[i], wit[i]));
+      sel_r = g.add(sel_r, g.mul(rhs[i], wit[i]));
+    }
+    b.assert_eq(sel_l, lhs_limb);
+    b.assert_eq(sel_r, rhs_limb);
+    E is_different = g.sub(b.k(1), is_equal);
+    b.assert_eq(g.mul(g.sub(lhs_limb, rhs_limb), diff_inv), is_different);
+  }
+  rec.less_than(b, lhs_limb, rhs_limb, is_lt, is_real);
+  return {is_lt, is_equal};
+}
+
+// Product::eval = MulWitness::assert_mul + range-checked result (src/gadgets/unsigned/mul.rs:68-164);
+// wit = carry[W] ++ result[W]
+std::vector<E> eval_product(Builder& b, const std::vector<E>& wit, const std::vector<E>& lhs, const std::vector<E>& rhs,
+                            ByteAirRecord& rec, E is_real) {
+  Graph& g = b.g;
+  const size_t w = lhs.size();
+  std::vector<E> result(wit.begin() + w, wit.begin() + 2 * w), products;
+  for (size_t k = 0; k < w; k++) products.push_back(b.k(0));
+  for (size_t i = 0; i < w; i++)
+    for (size_t j = 0; j < w; j++)
+      if (i + j < w) products[i + j] = g.add(products[i + j], g.mul(lhs[i], rhs[j]));
+  E carry_prev = b.k(0);
+  for (size_t k = 0; k < w; k++) {
+    rec.range_check_u16(b, wit[k], is_real);
+    E out = g.add(result[k], g.mul(wit[k], b.k(256)));
+    {
+      Builder::When wr(b, is_real);
+      b.assert_eq(g.add(products[k], carry_prev), out);
+    }
+    carry_prev = wit[k];
+  }
+  rec.range_check_u8_iter(b, result, is_real);
+  return result;
+}
+
+// U64::eval (src/core/u64.rs:170-222), chip kinds 4..9 = Add, Sub, LessThan, IsZero, Mul, DivRem: Sum64 / Diff64
+// (src/gadgets/unsigned/add.rs:63-175), Compare64 (cmp.rs:49-128), IsZero64 (is_zero.rs:46-156), Product64
+// (mul.rs:68-164), DivRem64 (div_rem.rs:62-103)
 std::vector<E> eval_u64_chipset(Builder& b, uint32_t kind, E is_real, const std::vector<E>& inp, const std::vector<E>& witness,
                                 E nonce, const std::vector<Cols::Req>& requires_) {
   Graph& g = b.g;
-  std::vector<E> in1(inp.begin(), inp.begin() + 8), in2(inp.begin() + 8, inp.begin() + 16), out;
+  std::vector<E> in1(inp.begin(), inp.begin() + 8), in2, out;
+  if (inp.size() >= 16) in2.assign(inp.begin() + 8, inp.begin() + 16);
   ByteAirRecord rec;
+  auto slice = [&](size_t from, size_t to) { return std::vector<E>(witness.begin() + from, witness.begin() + to); };
   if (kind == 4 || kind == 5) {
-    std::vector<E> result(witness.begin(), witness.begin() + 8);
+    std::vector<E> result = slice(0, 8);
     rec.range_check_u8_iter(b, result, is_real);  // UncheckedWord::into_checked
     if (kind == 4) assert_add(b, in1, in2, result, is_real);
     else assert_add(b, result, in2, in1, is_real);  // result + rhs = lhs
     out = result;
-  } else {
-    E lhs_limb = witness[8], rhs_limb = witness[9], diff_inv = witness[10], is_lt = witness[11];
+  } else if (kind == 6) {
+    out = {eval_compare(b, slice(0, 12), in1, in2, rec, is_real).first};
+  } else if (kind == 7) {  // IsZeroOrEqual::eval_is_zero
+    E is_zero = witness[8];
     {
-      Builder::When w(b, is_real);
-      E is_equal = b.k(1);
-      for (int i = 7; i >= 0; i--) {
-        b.assert_bool(witness[i]);
-        is_equal = g.sub(is_equal, witness[i]);
-        Builder::When we(b, is_equal);
-        b.assert_eq(in1[i], in2[i]);
-      }
-      b.assert_bool(is_equal);
-      E sel_l = b.k(0), sel_r = b.k(0);
-      for (int i = 0; i < 8; i++) {
-        sel_l = g.add(sel_l, g.mul(in1[i], witness[i]));
-        sel_r = g.add(sel_r, g.mul(in2[i], witness[i]));
-      }
-      b.assert_eq(sel_l, lhs_limb);
-      b.assert_eq(sel_r, rhs_limb);
-      E is_different = g.sub(b.k(1), is_equal);
-      b.assert_eq(g.mul(g.sub(lhs_limb, rhs_limb), diff_inv), is_different);
+      Builder::When wr(b, is_real);
+      b.assert_bool(is_zero);
     }
-    rec.less_than(b, lhs_limb, rhs_limb, is_lt, is_real);
-    out = {is_lt};
+    {
+      Builder::When wr(b, is_real);
+      E lc = b.k(0);
+      for (int i = 0; i < 8; i++) {
+        {
+          Builder::When wz(b, is_zero);
+          b.assert_zero(in1[i]);
+        }
+        lc = g.add(lc, g.mul(in1[i], witness[i]));
+      }
+      b.assert_eq(lc, g.sub(b.k(1), is_zero));
+    }
+    out = {is_zero};
+  } else if (kind == 8) {
+    out = eval_product(b, slice(0, 16), in1, in2, rec, is_real);
+  } else {  // DivRem::eval, (a, b) = (in1, in2)
+    std::vector<E> q = slice(8, 16), w_r = slice(32, 40);
+    {
+      Builder::When wr(b, is_real);  // IsZeroWitness::assert_non_zero(b)
+      E lc = b.k(0);
+      for (int i = 0; i < 8; i++) lc = g.add(lc, g.mul(in2[i], witness[i]));
+      b.assert_one(lc);
+    }
+    rec.range_check_u8_iter(b, q, is_real);
+    std::vector<E> qb = eval_product(b, slice(16, 32), q, in2, rec, is_real);
+    rec.range_check_u8_iter(b, w_r, is_real);  // Diff::eval: r + qb = a
+    assert_add(b, w_r, qb, in1, is_real);
+    assert_less_than(b, slice(40, 50), w_r, in2, rec, is_real);
+    auto cmp = eval_compare(b, slice(50, 62), qb, in1, rec, is_real);
+    {
+      Builder::When wr(b, is_real);
+      b.assert_one(g.add(cmp.first, cmp.second));
+    }
+    out = q;
+    out.insert(out.end(), w_r.begin(), w_r.end());
   }
   rec.require_all(b, nonce, requires_);
   return out;
@@ -394,7 +473,7 @@ std::vector<E> eval_u64_chipset(Builder& b, uint32_t kind, E is_real, const std:
 std::vector<E> eval_chip(Builder& b, const ChipInfo& chip, E is_real, const std::vector<E>& inp, const std::vector<E>& witness,
                          E nonce, const std::vector<Cols::Req>& requires_) {
   if (chip.kind >= 1 && chip.kind <= 3) return eval_poseidon_chipset(b, chip.kind == 1 ? 24 : chip.kind == 2 ? 32 : 40, is_real, inp, witness);
-  if (chip.kind >= 4 && chip.kind <= 6) return eval_u64_chipset(b, chip.kind, is_real, inp, witness, nonce, requires_);
+  if (chip.kind >= 4 && chip.kind <= 9) return eval_u64_chipset(b, chip.kind, is_real, inp, witness, nonce, requires_);
   throw std::runtime_error("AIR capture of extern chip " + chip.name + " is not implemented");
 }
 

@@ -267,28 +267,69 @@ struct Executor {
         } break;
         case OP_EXTERN: {
           const uint32_t* chip = prog.chip(op[1]);
-          if (chip[0] >= 4 && chip[0] <= 6) {  // U64::{Add, Sub, LessThan}::execute, src/core/u64.rs:76-128
-            if (op[2] != 16) fail(LSK_ERR_EXEC, "bad extern chip call");
-            uint8_t a[8], b[8];
-            for (int i = 0; i < 16; i++) {
-              uint32_t v = m[op[3 + i]];
+          if (chip[0] >= 4 && chip[0] <= 9) {  // U64::execute, src/core/u64.rs:76-128
+            const uint32_t nin = chip[0] == 7 ? 8u : 16u;
+            if (op[2] != nin) fail(LSK_ERR_EXEC, "bad extern chip call");
+            uint64_t x = 0, y = 0;
+            for (uint32_t i = 0; i < nin; i++) {
+              uint64_t v = m[op[3 + i]];
               if (v > 255) fail(LSK_ERR_EXEC, "u64 chip input is not a byte");  // into_u64: try_into().unwrap()
-              (i < 8 ? a[i] : b[i - 8]) = (uint8_t)v;
+              if (i < 8) x |= v << (8 * i);
+              else y |= v << (8 * (i - 8));
             }
-            if (chip[0] == 6) {  // CompareWitness::populate, src/gadgets/unsigned/cmp.rs:23-46
+            auto byte = [](uint64_t v, int i) { return (uint32_t)(v >> (8 * i)) & 255u; };
+            auto range_pairs = [&](uint64_t v) {  // UncheckedWord::assign_bytes -> range_check_u8_iter
+              for (int i = 0; i < 8; i += 2) new_lookup(byte_record(byte(v, i), byte(v, i + 1), 0), f.nonce, req_stack);
+            };
+            auto push_word = [&](uint64_t v) {
+              for (int i = 0; i < 8; i++) vals.push_back(byte(v, i));
+            };
+            auto compare = [&](uint64_t l, uint64_t r) {  // CompareWitness::populate, cmp.rs:23-46
               int i = 7;
-              while (i >= 0 && a[i] == b[i]) i--;
-              uint32_t l = i >= 0 ? a[i] : 0, r = i >= 0 ? b[i] : 0;
-              new_lookup(byte_record(l, r, 2), f.nonce, req_stack);
-              vals.push_back(l < r ? 1u : 0u);
-            } else {             // Sum / Diff::populate: wrapping result, range-checked in byte pairs
-              uint64_t x = 0, y = 0;
-              for (int i = 7; i >= 0; i--) x = x << 8 | a[i], y = y << 8 | b[i];
-              uint64_t z = chip[0] == 4 ? x + y : x - y;
-              uint32_t out[8];
-              for (int i = 0; i < 8; i++) out[i] = (uint32_t)(z >> (8 * i)) & 255u;
-              for (int i = 0; i < 8; i += 2) new_lookup(byte_record(out[i], out[i + 1], 0), f.nonce, req_stack);
-              vals.insert(vals.end(), out, out + 8);
+              while (i >= 0 && byte(l, i) == byte(r, i)) i--;
+              uint32_t a = i >= 0 ? byte(l, i) : 0, b = i >= 0 ? byte(r, i) : 0;
+              new_lookup(byte_record(a, b, 2), f.nonce, req_stack);
+            };
+            auto product = [&](uint64_t l, uint64_t r) {  // MulWitness::populate + result range checks, mul.rs:27-63,148-155
+              uint32_t prod[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              for (int i = 0; i < 8; i++)
+                for (int j = 0; i + j < 8; j++) prod[i + j] += byte(l, i) * byte(r, j);
+              uint32_t carry = 0;
+              for (int k = 0; k < 8; k++) {
+                carry = (prod[k] + carry) >> 8;
+                new_lookup(byte_record(carry & 255u, carry >> 8, 1), f.nonce, req_stack);  // range_check_u16(carry)
+              }
+              range_pairs(l * r);
+              return l * r;
+            };
+            switch (chip[0]) {
+              case 4: case 5: {  // Sum / Diff::populate: wrapping result
+                uint64_t z = chip[0] == 4 ? x + y : x - y;
+                range_pairs(z);
+                push_word(z);
+              } break;
+              case 6:
+                compare(x, y);
+                vals.push_back(x < y ? 1u : 0u);
+                break;
+              case 7: vals.push_back(x == 0 ? 1u : 0u); break;  // IsZero: no lookups
+              case 8: push_word(product(x, y)); break;
+              default: {  // DivRem::populate, div_rem.rs:35-59
+                if (y == 0) fail(LSK_ERR_EXEC, "expected input to be non-zero");
+                uint64_t q = x / y;
+                range_pairs(q);
+                uint64_t qb = product(q, y);
+                uint64_t r = x - qb;
+                range_pairs(r);
+                {  // LessThanWitness::populate(r, b)
+                  int i = 7;
+                  while (byte(r, i) == byte(y, i)) i--;
+                  new_lookup(byte_record(byte(r, i), byte(y, i), 2), f.nonce, req_stack);
+                }
+                compare(qb, x);
+                push_word(q);
+                push_word(r);
+              }
             }
             break;
           }

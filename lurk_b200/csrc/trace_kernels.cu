@@ -203,35 +203,89 @@ __device__ void populate_row(const uint32_t* __restrict__ w, uint32_t body, Func
           if (kind == 1) extern_poseidon<24, Store>(op, map, map_len, aux, st);
           else if (kind == 2) extern_poseidon<32, Store>(op, map, map_len, aux, st);
           else if (kind == 3) extern_poseidon<40, Store>(op, map, map_len, aux, st);
-          else if (kind >= 4 && kind <= 6) {  // U64::populate_witness, src/core/u64.rs:130-168
-            uint32_t a[8], b[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) a[i] = from_mont(map[op[3 + i]]), b[i] = from_mont(map[op[11 + i]]);
-            if (kind == 6) {  // CompareWitness (cmp.rs:12-46): is_comp[8], lhs limb, rhs limb, 1/(lhs - rhs), is_less_than
+          else if (kind >= 4 && kind <= 9) {  // U64::populate_witness, src/core/u64.rs:130-168
+            const uint32_t nin = kind == 7 ? 8u : 16u;
+            uint64_t x = 0, y = 0;
+            for (uint32_t i = 0; i < nin; i++) {
+              uint64_t v = from_mont(map[op[3 + i]]);
+              if (i < 8) x |= v << (8 * i);
+              else y |= v << (8 * (i - 8));
+            }
+            auto byte = [](uint64_t v, int i) { return (uint32_t)(v >> (8 * i)) & 255u; };
+            auto aux_word = [&](uint64_t v) {
+              for (int i = 0; i < 8; i++) st(aux++, to_mont(byte(v, i)));
+            };
+            auto map_word = [&](uint64_t v) {
+              for (int i = 0; i < 8; i++) map[map_len++] = to_mont(byte(v, i));
+            };
+            auto non_zero_witness = [&](uint64_t v) {  // IsZeroWitness::populate_non_zero (is_zero.rs:17-28); zeros if v == 0
+              bool found = false;
+              for (int i = 0; i < 8; i++) {
+                uint32_t limb = byte(v, i);
+                if (!found && limb) {
+                  st(aux + i, finv(to_mont(limb)));
+                  found = true;
+                }
+              }
+              aux += 8;
+            };
+            // CompareWitness (cmp.rs:12-46): is_comp[8], lhs limb, rhs limb, 1/(lhs - rhs), is_less_than;
+            // LessThanWitness (less_than.rs:12-41) is its first 10 columns
+            auto compare_witness = [&](uint64_t l, uint64_t r, bool full) -> uint32_t {
               int i = 7;
-              while (i >= 0 && a[i] == b[i]) i--;
+              while (i >= 0 && byte(l, i) == byte(r, i)) i--;
               uint32_t lt = 0;
               if (i >= 0) {
-                uint32_t l = to_mont(a[i]), r = to_mont(b[i]);
+                uint32_t lm = to_mont(byte(l, i)), rm = to_mont(byte(r, i));
                 st(aux + i, R1);
-                st(aux + 8, l);
-                st(aux + 9, r);
-                st(aux + 10, finv(fsub(l, r)));
-                lt = a[i] < b[i] ? R1 : 0u;
-                st(aux + 11, lt);
+                st(aux + 8, lm);
+                st(aux + 9, rm);
+                lt = byte(l, i) < byte(r, i) ? R1 : 0u;
+                if (full) {
+                  st(aux + 10, finv(fsub(lm, rm)));
+                  st(aux + 11, lt);
+                }
               }
-              map[map_len++] = lt;
-              aux += 12;
-            } else {          // Sum / Diff (add.rs:63-175): the wrapping result's bytes
-              uint64_t x = 0, y = 0;
-#pragma unroll
-              for (int i = 7; i >= 0; i--) x = x << 8 | a[i], y = y << 8 | b[i];
-              const uint64_t z = kind == 4 ? x + y : x - y;
-#pragma unroll
-              for (int i = 0; i < 8; i++) {
-                uint32_t v = to_mont((uint32_t)(z >> (8 * i)) & 255u);
-                map[map_len++] = v;
-                st(aux++, v);
+              aux += full ? 12 : 10;
+              return lt;
+            };
+            auto product_witness = [&](uint64_t l, uint64_t r) -> uint64_t {  // MulWitness carries (mul.rs:27-63), then the result
+              uint32_t prod[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              for (int i = 0; i < 8; i++)
+                for (int j = 0; i + j < 8; j++) prod[i + j] += byte(l, i) * byte(r, j);
+              uint32_t carry = 0;
+              for (int k = 0; k < 8; k++) {
+                carry = (prod[k] + carry) >> 8;
+                st(aux++, to_mont(carry));
+              }
+              aux_word(l * r);
+              return l * r;
+            };
+            switch (kind) {
+              case 4: case 5: {  // Sum / Diff (add.rs:63-175): the wrapping result's bytes
+                const uint64_t z = kind == 4 ? x + y : x - y;
+                map_word(z);
+                aux_word(z);
+              } break;
+              case 6: map[map_len++] = compare_witness(x, y, true); break;
+              case 7: {  // IsZeroOrEqual::populate_is_zero (is_zero.rs:113-125): inverses[8], result
+                non_zero_witness(x);
+                const uint32_t z = x == 0 ? R1 : 0u;
+                st(aux++, z);
+                map[map_len++] = z;
+              } break;
+              case 8: map_word(product_witness(x, y)); break;
+              default: {  // DivRem (div_rem.rs:17-59): b_non_zero, q, qb, r, r_lt_b, qb_cmp_a
+                const uint64_t q = y ? x / y : 0;
+                non_zero_witness(y);
+                aux_word(q);
+                const uint64_t qb = product_witness(q, y);
+                const uint64_t r = x - qb;
+                aux_word(r);
+                compare_witness(r, y, false);
+                compare_witness(qb, x, true);
+                map_word(q);
+                map_word(r);
               }
             }
           }

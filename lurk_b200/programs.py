@@ -53,7 +53,8 @@ def hash_toplevel():
 
 
 U64_CHIPS = [ChipInfo("u64_add", 16, 8, 8, 4, kind=4), ChipInfo("u64_sub", 16, 8, 8, 4, kind=5),
-             ChipInfo("u64_lessthan", 16, 1, 12, 1, kind=6)]
+             ChipInfo("u64_lessthan", 16, 1, 12, 1, kind=6), ChipInfo("u64_iszero", 8, 1, 9, 0, kind=7),
+             ChipInfo("u64_mul", 16, 8, 16, 12, kind=8), ChipInfo("u64_divrem", 16, 16, 62, 22, kind=9)]
 
 
 def u64_toplevel():
@@ -82,4 +83,25 @@ def u64_toplevel():
         match_("lt", [(1, [ret("b")])]),
         ret("a"),
     ])
-    return Toplevel([add, sub_f, less_than, fibu, maxu], U64_CHIPS)
+    is_zero = func("is_zero", [("a", 8)], 1, [extern_call(["c"], "u64_iszero", ["a"]), ret("c")])
+    mul_f = func("mul", [("a", 8), ("b", 8)], 8, [extern_call([("c", 8)], "u64_mul", ["a", "b"]), ret("c")])
+    divrem = func("divrem", [("a", 8), ("b", 8)], 16, [extern_call([("qr", 16)], "u64_divrem", ["a", "b"]), ret("qr")])
+    # factu(n) = n! as a wrapping u64: the counter itself is a u64 (decremented with u64_sub, tested with u64_iszero)
+    factu = func("factu", [("n", 8)], 8, [
+        array("one", [1] + [0] * 7),
+        extern_call(["z"], "u64_iszero", ["n"]),
+        match_("z", [(1, [ret("one")])]),
+        extern_call([("pred", 8)], "u64_sub", ["n", "one"]),
+        call([("m", 8)], "factu", ["pred"]),
+        extern_call([("r", 8)], "u64_mul", ["n", "m"]),
+        ret("r"),
+    ])
+    # gcdu(a, b) by Euclid with u64_divrem
+    gcdu = func("gcdu", [("a", 8), ("b", 8)], 8, [
+        extern_call(["z"], "u64_iszero", ["b"]),
+        match_("z", [(1, [ret("a")])]),
+        extern_call([("q", 8), ("r", 8)], "u64_divrem", ["a", "b"]),
+        call([("g", 8)], "gcdu", ["b", "r"]),
+        ret("g"),
+    ])
+    return Toplevel([add, sub_f, less_than, fibu, maxu, is_zero, mul_f, divrem, factu, gcdu], U64_CHIPS)

@@ -346,28 +346,65 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
         } break;
         case OP_EXTERN: {
           const ChipDef& c = top.chips[op.a];
-          if (c.kind >= 4 && c.kind <= 6) {  // U64::{Add, Sub, LessThan}::execute, src/core/u64.rs:76-128
-            uint8_t a[8], b[8];
-            for (int i = 0; i < 16; i++) {
-              uint32_t v = map[op.xs[i]].to_u32();
+          if (c.kind >= 4 && c.kind <= 9) {  // U64::execute, src/core/u64.rs:76-128
+            const size_t nin = c.kind == 7 ? 8 : 16;
+            uint64_t x = 0, y = 0;
+            for (size_t i = 0; i < nin; i++) {
+              uint64_t v = map[op.xs[i]].to_u32();
               if (v > 255) throw std::runtime_error("u64 chip input is not a byte");
-              (i < 8 ? a[i] : b[i - 8]) = (uint8_t)v;
+              if (i < 8) x |= v << (8 * i);
+              else y |= v << (8 * (i - 8));
             }
-            if (c.kind == 6) {  // cmp.rs:23-46: most significant differing byte pair, (0, 0) when equal
+            auto byte = [](uint64_t v, int i) { return (uint32_t)(v >> (8 * i)) & 255u; };
+            auto lookup = [&](uint32_t i1, uint32_t i2, int slot) {
+              requires_.push_back(q.bytes[(uint16_t)(i1 | (i2 << 8))].rec[slot].new_lookup(nonce));
+            };
+            auto range_pairs = [&](uint64_t v) {  // UncheckedWord::assign_bytes, unsigned/mod.rs:114-120
+              for (int i = 0; i < 8; i += 2) lookup(byte(v, i), byte(v, i + 1), 0);
+            };
+            auto push_word = [&](uint64_t v) {
+              for (int i = 0; i < 8; i++) map.push_back(Fp::from_u32(byte(v, i)));
+            };
+            auto compare = [&](uint64_t l, uint64_t r) {  // cmp.rs:23-46
               int i = 7;
-              while (i >= 0 && a[i] == b[i]) i--;
-              uint32_t l = i >= 0 ? a[i] : 0, r = i >= 0 ? b[i] : 0;
-              requires_.push_back(q.bytes[(uint16_t)(l | (r << 8))].rec[2].new_lookup(nonce));
-              map.push_back(Fp::from_u32(l < r));
-            } else {            // add.rs:71-80,122-131 + UncheckedWord::assign_bytes (unsigned/mod.rs:114-120)
-              uint64_t x = 0, y = 0;
-              for (int i = 7; i >= 0; i--) x = x << 8 | a[i], y = y << 8 | b[i];
-              uint64_t z = c.kind == 4 ? x + y : x - y;
-              for (int i = 0; i < 8; i += 2) {
-                uint32_t b0 = (z >> (8 * i)) & 255u, b1 = (z >> (8 * i + 8)) & 255u;
-                requires_.push_back(q.bytes[(uint16_t)(b0 | (b1 << 8))].rec[0].new_lookup(nonce));
+              while (i >= 0 && byte(l, i) == byte(r, i)) i--;
+              lookup(i >= 0 ? byte(l, i) : 0, i >= 0 ? byte(r, i) : 0, 2);
+            };
+            auto product = [&](uint64_t l, uint64_t r) {  // mul.rs:27-63,148-155
+              uint32_t prod[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+              for (int i = 0; i < 8; i++)
+                for (int j = 0; i + j < 8; j++) prod[i + j] += byte(l, i) * byte(r, j);
+              uint32_t carry = 0;
+              for (int k = 0; k < 8; k++) {
+                carry = (prod[k] + carry) >> 8;
+                lookup(carry & 255u, carry >> 8, 1);  // range_check_u16
               }
-              for (int i = 0; i < 8; i++) map.push_back(Fp::from_u32((uint32_t)(z >> (8 * i)) & 255u));
+              range_pairs(l * r);
+              return l * r;
+            };
+            switch (c.kind) {
+              case 4: case 5: {
+                uint64_t z = c.kind == 4 ? x + y : x - y;
+                range_pairs(z);
+                push_word(z);
+              } break;
+              case 6: compare(x, y); map.push_back(Fp::from_u32(x < y)); break;
+              case 7: map.push_back(Fp::from_u32(x == 0)); break;
+              case 8: push_word(product(x, y)); break;
+              default: {  // div_rem.rs:35-59
+                if (y == 0) throw std::runtime_error("expected input to be non-zero");
+                uint64_t qq = x / y;
+                range_pairs(qq);
+                uint64_t qb = product(qq, y);
+                uint64_t r = x - qb;
+                range_pairs(r);
+                int i = 7;
+                while (byte(r, i) == byte(y, i)) i--;
+                lookup(byte(r, i), byte(y, i), 2);
+                compare(qb, x);
+                push_word(qq);
+                push_word(r);
+              }
             }
             break;
           }
@@ -614,31 +651,87 @@ static inline void populate_block(const Toplevel& top, const QueryRecord& q, con
       } break;
       case OP_EXTERN: {  // trace.rs:388-407 + core/poseidon.rs:65-72 / core/u64.rs:130-168
         const ChipDef& c = top.chips[op.a];
-        if (c.kind >= 4 && c.kind <= 6) {
-          uint32_t a[8], b[8];
-          for (int i = 0; i < 8; i++) a[i] = map[op.xs[i]].to_u32(), b[i] = map[op.xs[8 + i]].to_u32();
-          if (c.kind == 6) {  // CompareWitness: is_comp[8], lhs_comp_limb, rhs_comp_limb, comp_diff_inv, is_less_than
+        if (c.kind >= 4 && c.kind <= 9) {  // U64::populate_witness, src/core/u64.rs:130-168
+          const size_t nin = c.kind == 7 ? 8 : 16;
+          uint64_t x = 0, y = 0;
+          for (size_t i = 0; i < nin; i++) {
+            uint64_t v = map[op.xs[i]].to_u32();
+            if (i < 8) x |= v << (8 * i);
+            else y |= v << (8 * (i - 8));
+          }
+          auto byte = [](uint64_t v, int i) { return (uint32_t)(v >> (8 * i)) & 255u; };
+          auto aux_word = [&](uint64_t v) {
+            for (int i = 0; i < 8; i++) cx.push_aux(Fp::from_u32(byte(v, i)));
+          };
+          auto map_word = [&](uint64_t v) {
+            for (int i = 0; i < 8; i++) map.push_back(Fp::from_u32(byte(v, i)));
+          };
+          auto non_zero_witness = [&](uint64_t v) {  // IsZeroWitness::populate_non_zero, is_zero.rs:17-28
+            bool found = false;
+            for (int i = 0; i < 8; i++) {
+              if (!found && byte(v, i)) {
+                cx.push_aux(fp_inv(Fp::from_u32(byte(v, i))));
+                found = true;
+              } else {
+                cx.push_aux(Fp::zero());
+              }
+            }
+          };
+          auto compare_witness = [&](uint64_t l, uint64_t r, bool full) {  // CompareWitness / LessThanWitness
             Fp wit[12];
-            for (auto& x : wit) x = Fp::zero();
+            for (auto& t : wit) t = Fp::zero();
             int i = 7;
-            while (i >= 0 && a[i] == b[i]) i--;
+            while (i >= 0 && byte(l, i) == byte(r, i)) i--;
             if (i >= 0) {
               wit[i] = Fp::one();
-              wit[8] = Fp::from_u32(a[i]);
-              wit[9] = Fp::from_u32(b[i]);
+              wit[8] = Fp::from_u32(byte(l, i));
+              wit[9] = Fp::from_u32(byte(r, i));
               wit[10] = fp_inv(wit[8] - wit[9]);
-              wit[11] = Fp::from_u32(a[i] < b[i]);
+              wit[11] = Fp::from_u32(byte(l, i) < byte(r, i));
             }
-            map.push_back(wit[11]);
-            for (Fp x : wit) cx.push_aux(x);
-          } else {
-            uint64_t x = 0, y = 0;
-            for (int i = 7; i >= 0; i--) x = x << 8 | a[i], y = y << 8 | b[i];
-            uint64_t z = c.kind == 4 ? x + y : x - y;
-            for (int i = 0; i < 8; i++) {
-              Fp v = Fp::from_u32((uint32_t)(z >> (8 * i)) & 255u);
-              map.push_back(v);
-              cx.push_aux(v);
+            for (int k = 0; k < (full ? 12 : 10); k++) cx.push_aux(wit[k]);
+          };
+          auto product_witness = [&](uint64_t l, uint64_t r) {  // MulWitness carries, then the result
+            uint32_t prod[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int i = 0; i < 8; i++)
+              for (int j = 0; i + j < 8; j++) prod[i + j] += byte(l, i) * byte(r, j);
+            uint32_t carry = 0;
+            for (int k = 0; k < 8; k++) {
+              carry = (prod[k] + carry) >> 8;
+              cx.push_aux(Fp::from_u32(carry));
+            }
+            aux_word(l * r);
+            return l * r;
+          };
+          switch (c.kind) {
+            case 4: case 5: {
+              uint64_t z = c.kind == 4 ? x + y : x - y;
+              map_word(z);
+              aux_word(z);
+            } break;
+            case 6:
+              map.push_back(Fp::from_u32(x < y));
+              compare_witness(x, y, true);
+              break;
+            case 7:
+              map.push_back(Fp::from_u32(x == 0));
+              if (x) non_zero_witness(x);
+              else
+                for (int i = 0; i < 8; i++) cx.push_aux(Fp::zero());
+              cx.push_aux(Fp::from_u32(x == 0));
+              break;
+            case 8: map_word(product_witness(x, y)); break;
+            default: {  // DivRem: b_non_zero, q, qb (Product), r (Diff), r_lt_b (LessThanWitness), qb_cmp_a (CompareWitness)
+              uint64_t qq = x / y;
+              non_zero_witness(y);
+              aux_word(qq);
+              uint64_t qb = product_witness(qq, y);
+              uint64_t r = x - qb;
+              aux_word(r);
+              compare_witness(r, y, false);
+              compare_witness(qb, x, true);
+              map_word(qq);
+              map_word(r);
             }
           }
           for (uint32_t i = 0; i < c.require_size; i++) cx.push_require();

@@ -165,13 +165,16 @@ def test_partial_func_programs_prove_bit_exact(oracle, fname, args, ss):
         assert np.array_equal(assemble_proof(parts).words, want)
 
 
-@pytest.mark.parametrize("fname,args", [("add", "add"), ("sub", "sub"), ("less_than", "lt"), ("fibu", [200]), ("maxu", "max")])
+@pytest.mark.parametrize("fname,args", [("add", "add"), ("sub", "sub"), ("less_than", "lt"), ("fibu", [200]), ("maxu", "max"),
+                                        ("is_zero", "z"), ("mul", "mul"), ("divrem", "div"), ("factu", "fact"), ("gcdu", "gcd")])
 def test_u64_chipset_programs_prove_bit_exact(oracle, fname, args):
     # U64::{Add, Sub, LessThan} witnesses on the GPU + their AIR in the quotient kernel + byte lookups
     from test_oracle_stark import u64_bytes
     a = {"add": u64_bytes(2**64 - 1) + u64_bytes(2), "sub": u64_bytes(0) + u64_bytes(1),
          "lt": u64_bytes(0x0102030405060708) + u64_bytes(0x0102030505060708),
-         "max": u64_bytes(9) + u64_bytes(10**15)}.get(args, args) if isinstance(args, str) else args
+         "max": u64_bytes(9) + u64_bytes(10**15), "z": u64_bytes(0), "mul": u64_bytes(2**64 - 1) + u64_bytes(2**64 - 1),
+         "div": u64_bytes(10**18 + 7) + u64_bytes(12345), "fact": u64_bytes(25),
+         "gcd": u64_bytes(2**40 * 3**5 * 7) + u64_bytes(2**20 * 3**9 * 11)}.get(args, args) if isinstance(args, str) else args
     top = goldens.toplevel_for("u64")
     m, om, q, proof, want = _prove_both(oracle, top, fname, [a])
     assert np.array_equal(proof.words, want)

@@ -112,7 +112,9 @@ def test_u64_chip_traces_match_oracle(oracle):
     # src/core/u64.rs:130-168 (populate_witness of Sum64 / Diff64 / Compare64) inside func rows
     top = goldens.toplevel_for("u64")
     for fname, args in [("fibu", [300]), ("maxu", [9, 0, 0, 0, 0, 0, 0, 1] + [9, 0, 0, 0, 0, 0, 1, 0]),
-                        ("sub", [0] * 8 + [1] + [0] * 7), ("less_than", [5] * 8 + [5] * 8)]:
+                        ("sub", [0] * 8 + [1] + [0] * 7), ("less_than", [5] * 8 + [5] * 8),
+                        ("factu", [40] + [0] * 7), ("gcdu", [0, 0, 0, 1, 2, 3, 4, 5] + [0, 7, 0, 0, 9, 0, 0, 0]),
+                        ("divrem", [255] * 8 + [1, 1] + [0] * 6), ("is_zero", [0] * 8), ("mul", [255] * 16)]:
         q = QueryRecord.new(top)
         execute_by_name(top, fname, args, q)
         rec = _oracle_rec(oracle, top, fname, args)

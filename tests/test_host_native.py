@@ -80,7 +80,9 @@ def test_u64_chipsets_executor_matches_oracle(oracle):
     ot = oracle.OracleToplevel(top.serialize())
     for fname, args in [("add", u64_bytes(2**64 - 3) + u64_bytes(77)), ("sub", u64_bytes(5) + u64_bytes(2**40)),
                         ("less_than", u64_bytes(2**56) + u64_bytes(2**56 + 1)), ("fibu", [120]),
-                        ("maxu", u64_bytes(3) + u64_bytes(3))]:
+                        ("maxu", u64_bytes(3) + u64_bytes(3)), ("factu", u64_bytes(30)),
+                        ("gcdu", u64_bytes(10**18) + u64_bytes(6**20)), ("divrem", u64_bytes(2**64 - 1) + u64_bytes(2**32 + 1)),
+                        ("mul", u64_bytes(2**63 + 12345) + u64_bytes(2**33 + 99)), ("is_zero", u64_bytes(256))]:
         f = top.func_by_name(fname)
         q = QueryRecord.new(top)
         got = execute_by_name(top, fname, args, q)
@@ -93,6 +95,8 @@ def test_u64_chipsets_executor_matches_oracle(oracle):
     q = QueryRecord.new(top)
     with pytest.raises(N.LurkStarkError, match="byte"):
         execute_by_name(top, "add", [256] + [0] * 15, q)       # into_u64 panics on a non-byte limb
+    with pytest.raises(N.LurkStarkError, match="non-zero"):
+        execute_by_name(top, "divrem", u64_bytes(7) + u64_bytes(0), QueryRecord.new(top))   # division by zero
 
 
 def test_total_func_may_not_call_partial():

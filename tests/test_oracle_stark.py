@@ -118,6 +118,15 @@ def u64_bytes(x):
     ("fibu", [90], u64_bytes(2880067194370816120)),
     ("fibu", [100], u64_bytes(354224848179261915075 % 2**64)),                    # wrapping u64 arithmetic
     ("maxu", u64_bytes(9) + u64_bytes(10**15), u64_bytes(10**15)),
+    ("is_zero", u64_bytes(0), [1]),
+    ("is_zero", u64_bytes(2**40), [0]),
+    ("mul", u64_bytes(0xFFFFFFFFFFFFFFFF) + u64_bytes(0xFFFFFFFFFFFFFFFF), u64_bytes(1)),      # wraps
+    ("mul", u64_bytes(123456789) + u64_bytes(987654321), u64_bytes(123456789 * 987654321)),
+    ("divrem", u64_bytes(10**18 + 7) + u64_bytes(12345), u64_bytes((10**18 + 7) // 12345) + u64_bytes((10**18 + 7) % 12345)),
+    ("divrem", u64_bytes(5) + u64_bytes(2**63), u64_bytes(0) + u64_bytes(5)),
+    ("divrem", u64_bytes(2**64 - 1) + u64_bytes(1), u64_bytes(2**64 - 1) + u64_bytes(0)),
+    ("factu", u64_bytes(25), u64_bytes(15511210043330985984000000 % 2**64)),
+    ("gcdu", u64_bytes(2**40 * 3**5 * 7) + u64_bytes(2**20 * 3**9 * 11), u64_bytes(2**20 * 3**5)),
 ])
 def test_u64_chipsets_prove_verify(oracle, fname, args, want):
     # U64::{Add, Sub, LessThan} (src/core/u64.rs): execute, witness, AIR (assert_add carries, CompareWitness) and

@@ -473,6 +473,8 @@ def _eval_chip(b: SymbolicBuilder, chip, is_real: Expr, inp, witness, nonce, req
         return eval_poseidon_chipset(b, {1: 24, 2: 32, 3: 40}[chip.kind], is_real, inp, witness)
     if chip.kind in (4, 5, 6, 7, 8, 9):
         return eval_u64_chipset(b, chip.kind, is_real, inp, witness, nonce, requires)
+    if chip.kind == 10:
+        return eval_big_num_less_than(b, is_real, inp, witness, nonce, requires)
     raise NotImplementedError(f"AIR capture of extern chip {chip.name!r} (kind {chip.kind})")
 
 
@@ -532,6 +534,55 @@ def _eval_product(b: SymbolicBuilder, wit, lhs, rhs, rec: "_ByteAirRecord", is_r
         carry_prev = carry[k]
     rec.range_check_u8_iter(result, is_real)
     return result
+
+
+def _eval_field_to_word32(b: SymbolicBuilder, wit, field: Expr, rec: "_ByteAirRecord", is_real: Expr):
+    """FieldToWord32::eval (src/gadgets/unsigned/field.rs:36-140): wit = [is_msb_less_than] ++ result[4]; the
+    bytes recompose to the field element and are its canonical (< p = 0x78000001) representation"""
+    is_lt, word = wit[0], list(wit[1:5])
+    with b.when(is_real):
+        b.assert_bool(is_lt)
+    recomposed = b.const(0)
+    for i in reversed(range(4)):
+        recomposed = recomposed * 256 + word[i]
+    with b.when(is_real):
+        b.assert_eq(field, recomposed)
+    rec.less_than(word[3], 0x78, is_lt, is_real)
+    with b.when(is_real * (1 - is_lt)):
+        b.assert_eq(word[3], b.const(0x78))
+        for i in range(3):
+            b.assert_eq(word[i], b.const(0))
+    rec.range_check_u8_iter(word, is_real)
+    return word
+
+
+def eval_big_num_less_than(b: SymbolicBuilder, is_real: Expr, inp, witness, nonce, requires) -> List[Expr]:
+    """BigNum::LessThan (src/core/big_num.rs:75-97) = BigNumCompareWitness::eval (src/gadgets/big_num/cmp.rs:48-124):
+    witness = is_comp[8], lhs_comp_limb, rhs_comp_limb, lhs_comp_word (5), rhs_comp_word (5), CompareWitness<4> (8)"""
+    lhs, rhs = list(inp[:8]), list(inp[8:16])
+    is_comp, lhs_limb, rhs_limb = witness[:8], witness[8], witness[9]
+    rec = _ByteAirRecord()
+    with b.when(is_real):
+        is_equal = b.const(1)
+        for i in reversed(range(8)):
+            b.assert_bool(is_comp[i])
+            is_equal = is_equal - is_comp[i]
+            with b.when(is_equal):
+                b.assert_eq(lhs[i], rhs[i])
+        b.assert_bool(is_equal)
+        sel_l, sel_r = b.const(0), b.const(0)
+        for i in range(8):
+            sel_l = sel_l + lhs[i] * is_comp[i]
+            sel_r = sel_r + rhs[i] * is_comp[i]
+        b.assert_eq(sel_l, lhs_limb)
+        b.assert_eq(sel_r, rhs_limb)
+    lhs_word = _eval_field_to_word32(b, witness[10:15], lhs_limb, rec, is_real)
+    rhs_word = _eval_field_to_word32(b, witness[15:20], rhs_limb, rec, is_real)
+    lt, word_equal = _eval_compare(b, witness[20:28], lhs_word, rhs_word, rec, is_real)
+    with b.when(is_real):
+        b.assert_eq(is_equal, word_equal)
+    rec.require_all(b, nonce, requires)
+    return [lt]
 
 
 def eval_u64_chipset(b: SymbolicBuilder, kind: int, is_real: Expr, inp, witness, nonce, requires) -> List[Expr]:

@@ -470,10 +470,73 @@ std::vector<E> eval_u64_chipset(Builder& b, uint32_t kind, E is_real, const std:
   return out;
 }
 
+// FieldToWord32::eval (src/gadgets/unsigned/field.rs:36-140): wit = [is_msb_less_than] ++ result[4]
+std::vector<E> eval_field_to_word32(Builder& b, const std::vector<E>& wit, E field, ByteAirRecord& rec, E is_real) {
+  Graph& g = b.g;
+  E is_lt = wit[0];
+  std::vector<E> word(wit.begin() + 1, wit.begin() + 5);
+  {
+    Builder::When w(b, is_real);
+    b.assert_bool(is_lt);
+  }
+  E recomposed = b.k(0);
+  for (int i = 3; i >= 0; i--) recomposed = g.add(g.mul(recomposed, b.k(256)), word[i]);
+  {
+    Builder::When w(b, is_real);
+    b.assert_eq(field, recomposed);
+  }
+  rec.less_than(b, word[3], b.k(0x78), is_lt, is_real);
+  {
+    Builder::When w(b, g.mul(is_real, g.sub(b.k(1), is_lt)));
+    b.assert_eq(word[3], b.k(0x78));
+    for (int i = 0; i < 3; i++) b.assert_eq(word[i], b.k(0));
+  }
+  rec.range_check_u8_iter(b, word, is_real);
+  return word;
+}
+
+// BigNum::LessThan (src/core/big_num.rs:75-97) = BigNumCompareWitness::eval (src/gadgets/big_num/cmp.rs:48-124)
+std::vector<E> eval_big_num_less_than(Builder& b, E is_real, const std::vector<E>& inp, const std::vector<E>& witness, E nonce,
+                                      const std::vector<Cols::Req>& requires_) {
+  Graph& g = b.g;
+  std::vector<E> lhs(inp.begin(), inp.begin() + 8), rhs(inp.begin() + 8, inp.begin() + 16);
+  E lhs_limb = witness[8], rhs_limb = witness[9], is_equal;
+  ByteAirRecord rec;
+  auto slice = [&](size_t from, size_t to) { return std::vector<E>(witness.begin() + from, witness.begin() + to); };
+  {
+    Builder::When wr(b, is_real);
+    is_equal = b.k(1);
+    for (int i = 7; i >= 0; i--) {
+      b.assert_bool(witness[i]);
+      is_equal = g.sub(is_equal, witness[i]);
+      Builder::When we(b, is_equal);
+      b.assert_eq(lhs[i], rhs[i]);
+    }
+    b.assert_bool(is_equal);
+    E sel_l = b.k(0), sel_r = b.k(0);
+    for (int i = 0; i < 8; i++) {
+      sel_l = g.add(sel_l, g.mul(lhs[i], witness[i]));
+      sel_r = g.add(sel_r, g.mul(rhs[i], witness[i]));
+    }
+    b.assert_eq(sel_l, lhs_limb);
+    b.assert_eq(sel_r, rhs_limb);
+  }
+  std::vector<E> lhs_word = eval_field_to_word32(b, slice(10, 15), lhs_limb, rec, is_real);
+  std::vector<E> rhs_word = eval_field_to_word32(b, slice(15, 20), rhs_limb, rec, is_real);
+  auto cmp = eval_compare(b, slice(20, 28), lhs_word, rhs_word, rec, is_real);
+  {
+    Builder::When wr(b, is_real);
+    b.assert_eq(is_equal, cmp.second);
+  }
+  rec.require_all(b, nonce, requires_);
+  return {cmp.first};
+}
+
 std::vector<E> eval_chip(Builder& b, const ChipInfo& chip, E is_real, const std::vector<E>& inp, const std::vector<E>& witness,
                          E nonce, const std::vector<Cols::Req>& requires_) {
   if (chip.kind >= 1 && chip.kind <= 3) return eval_poseidon_chipset(b, chip.kind == 1 ? 24 : chip.kind == 2 ? 32 : 40, is_real, inp, witness);
   if (chip.kind >= 4 && chip.kind <= 9) return eval_u64_chipset(b, chip.kind, is_real, inp, witness, nonce, requires_);
+  if (chip.kind == 10) return eval_big_num_less_than(b, is_real, inp, witness, nonce, requires_);
   throw std::runtime_error("AIR capture of extern chip " + chip.name + " is not implemented");
 }
 

@@ -267,6 +267,26 @@ struct Executor {
         } break;
         case OP_EXTERN: {
           const uint32_t* chip = prog.chip(op[1]);
+          if (chip[0] == 10) {  // BigNum::LessThan::execute (src/core/big_num.rs:42-60) = BigNumCompareWitness::populate
+            if (op[2] != 16) fail(LSK_ERR_EXEC, "bad extern chip call");
+            uint32_t l = 0, r = 0;  // most significant differing field limbs (big_num/cmp.rs:31-45); (0, 0) when equal
+            for (int i = 7; i >= 0; i--)
+              if (m[op[3 + i]] != m[op[11 + i]]) {
+                l = m[op[3 + i]];
+                r = m[op[11 + i]];
+                break;
+              }
+            for (uint32_t v : {l, r}) {  // FieldToWord32::populate: msb < 0x78 lookup, then the 4 bytes in pairs
+              new_lookup(byte_record(v >> 24, 0x78, 2), f.nonce, req_stack);
+              new_lookup(byte_record(v & 255u, (v >> 8) & 255u, 0), f.nonce, req_stack);
+              new_lookup(byte_record((v >> 16) & 255u, v >> 24, 0), f.nonce, req_stack);
+            }
+            int i = 3;  // CompareWitness<4>::populate on the two words
+            while (i >= 0 && ((l >> (8 * i)) & 255u) == ((r >> (8 * i)) & 255u)) i--;
+            new_lookup(byte_record(i >= 0 ? (l >> (8 * i)) & 255u : 0, i >= 0 ? (r >> (8 * i)) & 255u : 0, 2), f.nonce, req_stack);
+            vals.push_back(l < r ? 1u : 0u);
+            break;
+          }
           if (chip[0] >= 4 && chip[0] <= 9) {  // U64::execute, src/core/u64.rs:76-128
             const uint32_t nin = chip[0] == 7 ? 8u : 16u;
             if (op[2] != nin) fail(LSK_ERR_EXEC, "bad extern chip call");

@@ -203,6 +203,40 @@ __device__ void populate_row(const uint32_t* __restrict__ w, uint32_t body, Func
           if (kind == 1) extern_poseidon<24, Store>(op, map, map_len, aux, st);
           else if (kind == 2) extern_poseidon<32, Store>(op, map, map_len, aux, st);
           else if (kind == 3) extern_poseidon<40, Store>(op, map, map_len, aux, st);
+          else if (kind == 10) {  // BigNumCompareWitness (src/gadgets/big_num/cmp.rs:12-45), 28 columns
+            uint32_t l = 0, r = 0;
+            for (int i = 7; i >= 0; i--) {
+              uint32_t a = map[op[3 + i]], b = map[op[11 + i]];
+              if (a != b) {
+                st(aux + i, R1);      // is_comp
+                st(aux + 8, a);       // lhs_comp_limb
+                st(aux + 9, b);       // rhs_comp_limb
+                l = from_mont(a);
+                r = from_mont(b);
+                break;
+              }
+            }
+            const uint32_t vv[2] = {l, r};
+            for (int k = 0; k < 2; k++) {  // FieldToWord32: is_msb_less_than, the 4 bytes
+              st(aux + 10 + 5 * k, (vv[k] >> 24) < 0x78 ? R1 : 0u);
+              for (int j = 0; j < 4; j++) st(aux + 11 + 5 * k + j, to_mont((vv[k] >> (8 * j)) & 255u));
+            }
+            int i = 3;  // CompareWitness<4> on the two words
+            while (i >= 0 && ((l >> (8 * i)) & 255u) == ((r >> (8 * i)) & 255u)) i--;
+            uint32_t lt = 0;
+            if (i >= 0) {
+              uint32_t a = (l >> (8 * i)) & 255u, b = (r >> (8 * i)) & 255u;
+              uint32_t am = to_mont(a), bm = to_mont(b);
+              st(aux + 20 + i, R1);
+              st(aux + 24, am);
+              st(aux + 25, bm);
+              st(aux + 26, finv(fsub(am, bm)));
+              lt = a < b ? R1 : 0u;
+              st(aux + 27, lt);
+            }
+            map[map_len++] = lt;
+            aux += 28;
+          }
           else if (kind >= 4 && kind <= 9) {  // U64::populate_witness, src/core/u64.rs:130-168
             const uint32_t nin = kind == 7 ? 8u : 16u;
             uint64_t x = 0, y = 0;

@@ -54,7 +54,8 @@ def hash_toplevel():
 
 U64_CHIPS = [ChipInfo("u64_add", 16, 8, 8, 4, kind=4), ChipInfo("u64_sub", 16, 8, 8, 4, kind=5),
              ChipInfo("u64_lessthan", 16, 1, 12, 1, kind=6), ChipInfo("u64_iszero", 8, 1, 9, 0, kind=7),
-             ChipInfo("u64_mul", 16, 8, 16, 12, kind=8), ChipInfo("u64_divrem", 16, 16, 62, 22, kind=9)]
+             ChipInfo("u64_mul", 16, 8, 16, 12, kind=8), ChipInfo("u64_divrem", 16, 16, 62, 22, kind=9),
+             ChipInfo("big_num_lessthan", 16, 1, 28, 7, kind=10)]
 
 
 def u64_toplevel():
@@ -104,4 +105,8 @@ def u64_toplevel():
         call([("g", 8)], "gcdu", ["b", "r"]),
         ret("g"),
     ])
-    return Toplevel([add, sub_f, less_than, fibu, maxu, is_zero, mul_f, divrem, factu, gcdu], U64_CHIPS)
+    # BigNum::LessThan on two 8-limb digests read as base-p integers (src/core/big_num.rs; Lurk compares
+    # commitments / big nums this way)
+    big_lt = func("big_num_less_than", [("a", 8), ("b", 8)], 1,
+                  [extern_call(["c"], "big_num_lessthan", ["a", "b"]), ret("c")])
+    return Toplevel([add, sub_f, less_than, fibu, maxu, is_zero, mul_f, divrem, factu, gcdu, big_lt], U64_CHIPS)

@@ -346,6 +346,28 @@ static inline std::vector<Fp> execute(const Toplevel& top, uint32_t entry, const
         } break;
         case OP_EXTERN: {
           const ChipDef& c = top.chips[op.a];
+          if (c.kind == 10) {  // BigNum::LessThan::execute, src/core/big_num.rs:42-60 + big_num/cmp.rs:25-45
+            uint32_t l = 0, r = 0;
+            for (int i = 7; i >= 0; i--)
+              if (map[op.xs[i]] != map[op.xs[8 + i]]) {
+                l = map[op.xs[i]].to_u32();
+                r = map[op.xs[8 + i]].to_u32();
+                break;
+              }
+            auto lookup = [&](uint32_t i1, uint32_t i2, int slot) {
+              requires_.push_back(q.bytes[(uint16_t)(i1 | (i2 << 8))].rec[slot].new_lookup(nonce));
+            };
+            for (uint32_t v : {l, r}) {  // FieldToWord32::populate, unsigned/field.rs:20-34,113-118
+              lookup(v >> 24, 0x78, 2);
+              lookup(v & 255u, (v >> 8) & 255u, 0);
+              lookup((v >> 16) & 255u, v >> 24, 0);
+            }
+            int i = 3;
+            while (i >= 0 && ((l >> (8 * i)) & 255u) == ((r >> (8 * i)) & 255u)) i--;
+            lookup(i >= 0 ? (l >> (8 * i)) & 255u : 0, i >= 0 ? (r >> (8 * i)) & 255u : 0, 2);
+            map.push_back(Fp::from_u32(l < r));
+            break;
+          }
           if (c.kind >= 4 && c.kind <= 9) {  // U64::execute, src/core/u64.rs:76-128
             const size_t nin = c.kind == 7 ? 8 : 16;
             uint64_t x = 0, y = 0;
@@ -651,6 +673,39 @@ static inline void populate_block(const Toplevel& top, const QueryRecord& q, con
       } break;
       case OP_EXTERN: {  // trace.rs:388-407 + core/poseidon.rs:65-72 / core/u64.rs:130-168
         const ChipDef& c = top.chips[op.a];
+        if (c.kind == 10) {  // BigNumCompareWitness (big_num/cmp.rs:12-45): is_comp[8], limbs, 2 x FieldToWord32, CompareWitness<4>
+          Fp wit[28];
+          for (auto& t : wit) t = Fp::zero();
+          uint32_t l = 0, r = 0;
+          for (int i = 7; i >= 0; i--)
+            if (map[op.xs[i]] != map[op.xs[8 + i]]) {
+              wit[i] = Fp::one();
+              wit[8] = map[op.xs[i]];
+              wit[9] = map[op.xs[8 + i]];
+              l = wit[8].to_u32();
+              r = wit[9].to_u32();
+              break;
+            }
+          uint32_t vv[2] = {l, r};
+          for (int k = 0; k < 2; k++) {
+            wit[10 + 5 * k] = Fp::from_u32((vv[k] >> 24) < 0x78);
+            for (int j = 0; j < 4; j++) wit[11 + 5 * k + j] = Fp::from_u32((vv[k] >> (8 * j)) & 255u);
+          }
+          int i = 3;
+          while (i >= 0 && ((l >> (8 * i)) & 255u) == ((r >> (8 * i)) & 255u)) i--;
+          if (i >= 0) {
+            uint32_t a = (l >> (8 * i)) & 255u, b = (r >> (8 * i)) & 255u;
+            wit[20 + i] = Fp::one();
+            wit[24] = Fp::from_u32(a);
+            wit[25] = Fp::from_u32(b);
+            wit[26] = fp_inv(wit[24] - wit[25]);
+            wit[27] = Fp::from_u32(a < b);
+          }
+          map.push_back(wit[27]);
+          for (Fp t : wit) cx.push_aux(t);
+          for (uint32_t k = 0; k < c.require_size; k++) cx.push_require();
+          break;
+        }
         if (c.kind >= 4 && c.kind <= 9) {  // U64::populate_witness, src/core/u64.rs:130-168
           const size_t nin = c.kind == 7 ? 8 : 16;
           uint64_t x = 0, y = 0;

@@ -166,7 +166,9 @@ def test_partial_func_programs_prove_bit_exact(oracle, fname, args, ss):
 
 
 @pytest.mark.parametrize("fname,args", [("add", "add"), ("sub", "sub"), ("less_than", "lt"), ("fibu", [200]), ("maxu", "max"),
-                                        ("is_zero", "z"), ("mul", "mul"), ("divrem", "div"), ("factu", "fact"), ("gcdu", "gcd")])
+                                        ("is_zero", "z"), ("mul", "mul"), ("divrem", "div"), ("factu", "fact"), ("gcdu", "gcd"),
+                                        ("big_num_less_than", [5, 7, 0, 0, 0, 0, 0, 2013265920] + [6, 7, 0, 0, 0, 0, 0, 2013265920]),
+                                        ("big_num_less_than", [4] * 16)])
 def test_u64_chipset_programs_prove_bit_exact(oracle, fname, args):
     # U64::{Add, Sub, LessThan} witnesses on the GPU + their AIR in the quotient kernel + byte lookups
     from test_oracle_stark import u64_bytes

@@ -114,7 +114,9 @@ def test_u64_chip_traces_match_oracle(oracle):
     for fname, args in [("fibu", [300]), ("maxu", [9, 0, 0, 0, 0, 0, 0, 1] + [9, 0, 0, 0, 0, 0, 1, 0]),
                         ("sub", [0] * 8 + [1] + [0] * 7), ("less_than", [5] * 8 + [5] * 8),
                         ("factu", [40] + [0] * 7), ("gcdu", [0, 0, 0, 1, 2, 3, 4, 5] + [0, 7, 0, 0, 9, 0, 0, 0]),
-                        ("divrem", [255] * 8 + [1, 1] + [0] * 6), ("is_zero", [0] * 8), ("mul", [255] * 16)]:
+                        ("divrem", [255] * 8 + [1, 1] + [0] * 6), ("is_zero", [0] * 8), ("mul", [255] * 16),
+                        ("big_num_less_than", [1, 2, 3, 2013265920, 5, 6, 7, 8] + [1, 2, 3, 0x77FFFFFF, 5, 6, 7, 8]),
+                        ("big_num_less_than", [7] * 16)]:
         q = QueryRecord.new(top)
         execute_by_name(top, fname, args, q)
         rec = _oracle_rec(oracle, top, fname, args)

@@ -82,7 +82,8 @@ def test_u64_chipsets_executor_matches_oracle(oracle):
                         ("less_than", u64_bytes(2**56) + u64_bytes(2**56 + 1)), ("fibu", [120]),
                         ("maxu", u64_bytes(3) + u64_bytes(3)), ("factu", u64_bytes(30)),
                         ("gcdu", u64_bytes(10**18) + u64_bytes(6**20)), ("divrem", u64_bytes(2**64 - 1) + u64_bytes(2**32 + 1)),
-                        ("mul", u64_bytes(2**63 + 12345) + u64_bytes(2**33 + 99)), ("is_zero", u64_bytes(256))]:
+                        ("mul", u64_bytes(2**63 + 12345) + u64_bytes(2**33 + 99)), ("is_zero", u64_bytes(256)),
+                        ("big_num_less_than", [9, 8, 7, 6, 5, 4, 3, 2013265920] + [9, 8, 7, 6, 5, 4, 3, 77])]:
         f = top.func_by_name(fname)
         q = QueryRecord.new(top)
         got = execute_by_name(top, fname, args, q)

@@ -126,6 +126,10 @@ def u64_bytes(x):
     ("divrem", u64_bytes(5) + u64_bytes(2**63), u64_bytes(0) + u64_bytes(5)),
     ("divrem", u64_bytes(2**64 - 1) + u64_bytes(1), u64_bytes(2**64 - 1) + u64_bytes(0)),
     ("factu", u64_bytes(25), u64_bytes(15511210043330985984000000 % 2**64)),
+    ("big_num_less_than", [5, 7, 0, 0, 0, 0, 0, 9] + [6, 7, 0, 0, 0, 0, 0, 9], [1]),          # differ in the lowest limb
+    ("big_num_less_than", [1, 2, 3, 4, 5, 6, 7, 2013265920] + [1, 2, 3, 4, 5, 6, 7, 2013265919], [0]),   # p - 1 vs p - 2: msb = 0x78 path
+    ("big_num_less_than", [3] * 8 + [3] * 8, [0]),                                             # equal
+    ("big_num_less_than", [0, 0, 0, 0x01000000, 9, 9, 9, 0] + [0, 0, 0, 0x00FFFFFF, 9, 9, 9, 0], [0]),   # byte 3 decides
     ("gcdu", u64_bytes(2**40 * 3**5 * 7) + u64_bytes(2**20 * 3**9 * 11), u64_bytes(2**20 * 3**5)),
 ])
 def test_u64_chipsets_prove_verify(oracle, fname, args, want):

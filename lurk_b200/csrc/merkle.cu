@@ -92,11 +92,11 @@ LSK_D uint32_t merkle_digest_coop(const uint32_t* const* __restrict__ cols, uint
   return s;
 }
 
-// One launch builds up to ST_LEVELS + 1 layers: a CTA takes 2 * ST_THREADS consecutive nodes of
-// layer l0 (in the leaf modes it first hashes them from the matrices) and reduces them to one node
-// of layer l0 + ST_LEVELS; intermediate digests go straight to their layers in global memory (they
-// are needed for the query openings) and are re-read by the same CTA through L1/L2.  A 2^21-leaf
-// commitment is 3 launches instead of 22, and the sequential tail of a tree costs one launch.
+// One launch builds up to ST_LEVELS + 1 layers: a CTA takes 2^ST_LEVELS consecutive nodes of layer l0 (in
+// the leaf modes it first hashes them from the matrices) and reduces them to one node of layer
+// l0 + ST_LEVELS; every level's digests go to the tree in global memory (the query openings need them)
+// and to the next level through shared memory.  A 2^21-leaf commitment is 7 flat launches + 2 of
+// these, and the sequential tail of a tree costs one launch.
 constexpr int ST_THREADS = 512;
 constexpr unsigned ST_LEVELS = 9;  // a CTA reduces 2^ST_LEVELS inputs to one node
 struct SubtreeArgs {

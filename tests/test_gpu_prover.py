@@ -351,3 +351,31 @@ def test_lair_shard_test_ackermann_3_18():
     proof = m.prove(pk, shard)
     assert proof.num_shards() == 2
     m.verify(vk, proof)
+
+
+def _powers(w, n):
+    """w^0 .. w^(n-1) mod P, vectorised by doubling"""
+    out = np.ones(n, dtype=np.uint64)
+    k, wk = 1, w % P
+    while k < n:
+        m = min(k, n - k)
+        out[k:k + m] = out[:m] * np.uint64(wk) % np.uint64(P)
+        wk = wk * wk % P
+        k *= 2
+    return out
+
+
+@pytest.mark.parametrize("logh", [13, 21, 23, 24])
+def test_lde_of_identity_polynomial_at_every_tile_shape(logh):
+    # the trace x -> x on H_N extends to the coset points themselves: output row r = g * w_{2N}^bitrev(r).  Checks
+    # every row, at the sizes that select each middle-pass tile shape of the LDE (t = 1, 9, 11, 12: c = 4, 4, 3, 2)
+    # up to the largest supported height 2^24.
+    h = 1 << logh
+    xs = _powers(pow(0x1A427A41, 1 << (27 - logh), P), h).astype(np.uint32).reshape(h, 1)
+    got = gpu_coset_lde(xs, 0)[:, 0]
+    nat = _powers(pow(0x1A427A41, 1 << (27 - logh - 1), P), 2 * h) * np.uint64(31) % np.uint64(P)   # g * w_2N^i
+    r = np.arange(2 * h, dtype=np.uint64)
+    br = np.zeros(2 * h, dtype=np.uint64)
+    for b in range(logh + 1):
+        br |= ((r >> np.uint64(b)) & np.uint64(1)) << np.uint64(logh - b)
+    assert np.array_equal(got, nat[br].astype(np.uint32))

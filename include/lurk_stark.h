@@ -190,6 +190,28 @@ int lsk_merkle_subtree_root_dev(lsk_ctx* ctx, const uint32_t* cols_dev, size_t s
                                 uint32_t root_out8[8]);
 int lsk_merkle_join_roots(const uint32_t* roots, uint32_t count, uint32_t out8[8]);
 
+/* ---- column-sharded PROVE of one shard over G GPUs (BASELINE configs[3]) ---------------------
+ * G processes, one GPU and one lsk_ctx each, join a device group; afterwards lsk_prove / lsk_shard_commit /
+ * lsk_shard_prove on those contexts, called by every rank with the SAME record and arguments, prove each shard
+ * together: the throughput-bound stages (LDE by column block; Merkle leaves and layers, quotient and reduced
+ * openings by row range; openings by column block) are split over the group and re-assembled with NCCL
+ * all-gathers over NVLink, the transcript is replayed identically by every rank, and every rank returns the
+ * same proof -- word for word the proof one GPU produces.  The reference has no such path (its prover is one
+ * process, sphinx `LocalProver`, src/core/cli/repl.rs:196); this is the north star's multi-GPU partition.
+ * NCCL is loaded at run time (libnccl.so.2).  G must be a power of two.
+ *   rank 0: lsk_comm_unique_id(id); the host distributes the 128 bytes (any transport);
+ *   every rank: lsk_ctx_comm_init(ctx, rank, G, id)  (collective), ... proves ..., lsk_ctx_comm_destroy(ctx). */
+#define LSK_COMM_ID_BYTES 128
+int lsk_comm_unique_id(uint8_t out[LSK_COMM_ID_BYTES]);
+int lsk_ctx_comm_init(lsk_ctx* ctx, int rank, int size, const uint8_t id[LSK_COMM_ID_BYTES]);
+int lsk_ctx_comm_destroy(lsk_ctx* ctx);
+/* rank / size of the context's group (0 / 1 without one) and the bytes its collectives delivered to this rank
+ * since the last lsk_profile_enable */
+int lsk_ctx_comm_info(const lsk_ctx* ctx, int* rank, int* size, double* bytes_received);
+/* the contiguous share [begin, end) of n items (columns, rows, Merkle nodes) that `rank` of `size` computes;
+ * host only, no GPU needed */
+int lsk_comm_partition(uint64_t n, int rank, int size, uint64_t* begin, uint64_t* end);
+
 #ifdef __cplusplus
 }
 #endif

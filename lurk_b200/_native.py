@@ -109,6 +109,20 @@ class Context:
     def sync(self):
         check(lib().lsk_ctx_sync(self.h))
 
+    # ---- device group of a column-sharded prove (include/lurk_stark.h, lsk_ctx_comm_*) ----
+    def comm_init(self, rank: int, size: int, unique_id: bytes):
+        """Collective: join a group of `size` contexts (one per GPU / process) that prove each shard together."""
+        buf = (ctypes.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        check(lib().lsk_ctx_comm_init(self.h, int(rank), int(size), buf))
+
+    def comm_destroy(self):
+        check(lib().lsk_ctx_comm_destroy(self.h))
+
+    def comm_info(self) -> dict:
+        r, s, b = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+        check(lib().lsk_ctx_comm_info(self.h, ctypes.byref(r), ctypes.byref(s), ctypes.byref(b)))
+        return {"rank": r.value, "size": s.value, "bytes_received": b.value}
+
     def profile_enable(self, on: bool = True):
         """Reset the per-kernel counters; with on=True also time every kernel family with CUDA events."""
         check(lib().lsk_profile_enable(self.h, 1 if on else 0))
@@ -124,6 +138,20 @@ class Context:
             check(n)
         return {lib().lsk_profile_tag_name(i).decode(): {"ms": ms[i], "bytes": by[i], "launches": int(ln[i])}
                 for i in range(n) if ln[i]}
+
+
+def comm_unique_id() -> bytes:
+    """The 128-byte id rank 0 creates and hands to every member of a device group (any transport)."""
+    buf = (ctypes.c_uint8 * 128)()
+    check(lib().lsk_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_partition(n: int, rank: int, size: int) -> range:
+    """The share of n columns / rows / Merkle nodes that `rank` of `size` computes (host only)."""
+    b, e = ctypes.c_uint64(), ctypes.c_uint64()
+    check(lib().lsk_comm_partition(ctypes.c_uint64(n), int(rank), int(size), ctypes.byref(b), ctypes.byref(e)))
+    return range(b.value, e.value)
 
 
 _default_ctx = None

@@ -3,6 +3,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "comm.cuh"
 #include "ntt.cuh"
 #include "trace.cuh"
 
@@ -51,6 +52,7 @@ void lsk_ctx_destroy(lsk_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  comm_destroy(ctx);
   ntt_ctx_destroy(ctx);
   for (auto& r : ctx->prof.recs) cudaEventDestroy(r.a), cudaEventDestroy(r.b);
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
@@ -78,6 +80,7 @@ int lsk_profile_enable(lsk_ctx* ctx, int on) {
   for (auto& r : p.recs) p.pool.push_back(r.a), p.pool.push_back(r.b);
   p.recs.clear();
   for (int i = 0; i < PT_COUNT; i++) p.launches[i] = 0, p.bytes[i] = 0, p.ms[i] = 0;
+  if (ctx->comm) ctx->comm->bytes_received = 0;
   p.timing = on != 0;
   return LSK_OK;
   LSK_API_END

@@ -1,6 +1,5 @@
-// CUDA plumbing shared by the kernels' host wrappers: error checks, the context, stream-ordered
-// device buffers (cudaMallocAsync on the context's stream; the pool keeps freed blocks so steady-
-// state proving does no driver allocation).
+// CUDA plumbing shared by the kernels' host wrappers: error checks, the context, the per-kernel
+// profiler and the context-owned caching allocator behind DevBuf.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -25,12 +24,12 @@ namespace lsk {
 enum ProfTag : int {
   PT_TRACE = 0, PT_LDE_SMALL, PT_LDE_K1, PT_LDE_K2, PT_LDE_K3, PT_MERKLE_LEAF, PT_MERKLE_LAYER, PT_MERKLE_TOP,
   PT_FRI_LEAF, PT_PERM_ROWS, PT_SCAN, PT_QUOTIENT, PT_BARY, PT_OPEN, PT_REDUCE_OPEN, PT_FRI_FOLD, PT_GRIND,
-  PT_GATHER, PT_POSEIDON2, PT_LAYOUT, PT_COUNT
+  PT_GATHER, PT_POSEIDON2, PT_LAYOUT, PT_COMM, PT_COUNT
 };
 static const char* const PROF_NAMES[PT_COUNT] = {
     "trace_gen", "lde_small", "lde_k1", "lde_k2", "lde_k3", "merkle_leaf", "merkle_layer", "merkle_top", "fri_leaf",
     "perm_rows", "scan", "quotient", "bary_weights", "open", "reduce_openings", "fri_fold", "grind", "gather",
-    "poseidon2", "layout"};
+    "poseidon2", "layout", "nccl"};
 struct Profiler {
   bool timing = false;
   struct Rec { int tag; cudaEvent_t a, b; };
@@ -105,8 +104,10 @@ struct MemPool {
 };
 }  // namespace lsk
 
+namespace lsk { struct Comm; }
 struct lsk_ctx {
   int device = 0;
+  lsk::Comm* comm = nullptr;    // device group of a column-sharded prove (comm.cuh); null: this GPU works alone
   cudaStream_t stream = nullptr;
   int sm_count = 148;
   lsk::MemPool pool;

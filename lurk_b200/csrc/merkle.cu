@@ -9,6 +9,8 @@
 
 #include "fri.cuh"
 #include "merkle.cuh"
+
+#include "comm.cuh"
 #include "poseidon2.cuh"
 
 namespace lsk {
@@ -231,9 +233,10 @@ constexpr unsigned TAIL_LOG = 14;  // layers with <= 2^TAIL_LOG nodes are latenc
 template <int MODE>
 __global__ void __launch_bounds__(MK_BLOCK) merkle_flat_kernel(const uint32_t* const* __restrict__ cols, uint32_t ncols,
                                                                 const uint32_t* __restrict__ fri_vals,
-                                                                const uint32_t* __restrict__ prev, size_t n,
-                                                                uint32_t* __restrict__ out) {
-  size_t i = (size_t)blockIdx.x * MK_BLOCK + threadIdx.x;
+                                                                const uint32_t* __restrict__ prev, size_t node0,
+                                                                size_t n, uint32_t* __restrict__ out) {
+  // nodes [node0, n) of the layer (node0 != 0: this rank's range of a tree built by a device group)
+  size_t i = node0 + (size_t)blockIdx.x * MK_BLOCK + threadIdx.x;
   if (i >= n) return;
   uint32_t st[16];
   merkle_digest(cols, MODE == ST_FRI_LEAVES ? 0u : ncols, i, MODE == ST_FRI_LEAVES ? fri_vals + i * 8 : nullptr,
@@ -267,27 +270,40 @@ static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std:
     return (double)((size_t)1 << (tree.log_max - l)) * (32.0 + 4.0 * groups[l].second + (l ? 64.0 : 0.0) +
                                                         (l == 0 && leaf_mode == ST_FRI_LEAVES ? 32.0 : 0.0));
   };
-  // big layers: one thread per digest, one launch per layer
+  // big layers: one thread per digest, one launch per layer.  In a device group every rank builds the layers
+  // over its own range of nodes (the children of a range are the same range one layer down, so nothing is
+  // exchanged on the way up); the last of these layers is all-gathered for the tail, the ones below stay
+  // distributed (tree.dist_layers) and are read through their owner when queries are answered.
+  const bool split = comm_splits(ctx, tree.log_max);
   while (tree.log_max - l0 > TAIL_LOG || (first && tree.log_max > ST_LEVELS)) {
-    size_t n = (size_t)1 << (tree.log_max - l0);
+    size_t n = (size_t)1 << (tree.log_max - l0), b = 0, e = n;
+    if (split) comm_range(ctx, n, &b, &e);
     uint32_t* out = tree.nodes.p + tree.layer_off[l0] * 8;
     const uint32_t* const* cols = tree.colptrs.p + groups[l0].first;
-    unsigned grid = div_up(n, MK_BLOCK);
+    unsigned grid = div_up(e - b, MK_BLOCK);
+    const double share = (double)(e - b) / (double)n;
     if (first) {
-      ProfScope ps(ctx, leaf_mode == ST_LEAVES ? PT_MERKLE_LEAF : PT_FRI_LEAF, 1, layer_bytes(0));
+      ProfScope ps(ctx, leaf_mode == ST_LEAVES ? PT_MERKLE_LEAF : PT_FRI_LEAF, 1, layer_bytes(0) * share);
       if (leaf_mode == ST_LEAVES)
-        merkle_flat_kernel<ST_LEAVES><<<grid, MK_BLOCK, 0, st>>>(cols, groups[0].second, nullptr, nullptr, n, out);
+        merkle_flat_kernel<ST_LEAVES><<<grid, MK_BLOCK, 0, st>>>(cols, groups[0].second, nullptr, nullptr, b, e, out);
       else
-        merkle_flat_kernel<ST_FRI_LEAVES><<<grid, MK_BLOCK, 0, st>>>(cols, 0, fri_vals, nullptr, n, out);
+        merkle_flat_kernel<ST_FRI_LEAVES><<<grid, MK_BLOCK, 0, st>>>(cols, 0, fri_vals, nullptr, b, e, out);
       first = false;
     } else {
-      ProfScope ps(ctx, PT_MERKLE_LAYER, 1, layer_bytes(l0));
+      ProfScope ps(ctx, PT_MERKLE_LAYER, 1, layer_bytes(l0) * share);
       merkle_flat_kernel<ST_NODES><<<grid, MK_BLOCK, 0, st>>>(cols, groups[l0].second, nullptr,
-                                                             tree.nodes.p + tree.layer_off[l0 - 1] * 8, n, out);
+                                                             tree.nodes.p + tree.layer_off[l0 - 1] * 8, b, e, out);
     }
     l0++;
   }
   if (!first) l0--;  // l0 = last layer already built
+  tree.dist_layers = 0;
+  if (split && !first) {
+    LSK_CUDA(cudaGetLastError());
+    size_t n = (size_t)1 << (tree.log_max - l0);
+    comm_allgather(ctx, tree.nodes.p + tree.layer_off[l0] * 8, n / ctx->comm->size * 32);
+    tree.dist_layers = l0;
+  }
   // latency-bound tail (or a whole small tree): subtree launches
   while (first || l0 < tree.log_max) {
     unsigned log_nodes = tree.log_max - l0;  // log2(nodes of layer l0)

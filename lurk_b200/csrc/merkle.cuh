@@ -24,6 +24,8 @@ struct MerkleTreeDev {
   DevBuf<uint32_t> nodes;              // all layers, 8 Montgomery words per digest; layer i at layer_off[i]
   std::vector<size_t> layer_off;       // in digests; layer 0 = leaves, layer log_max = root
   DevBuf<const uint32_t*> colptrs;     // per-column base pointers, grouped by height (tallest first)
+  unsigned dist_layers = 0;            // built by a device group (comm.cuh): layers [0, dist_layers) hold only this
+                                       // rank's range of nodes, the layers above are complete on every rank
   const uint32_t* layer(unsigned i) const { return nodes.p + layer_off[i] * 8; }
   const uint32_t* root_dev() const { return layer(log_max); }
 };

@@ -19,6 +19,7 @@
 #include <memory>
 
 #include "challenger.h"
+#include "comm.cuh"
 #include "machine.h"
 #include "merkle.cuh"
 #include "ntt.cuh"
@@ -217,6 +218,17 @@ static DeviceRecord& device_record(lsk_machine& m, const lsk_record& rec, uint32
   return *slot;
 }
 
+// lde_dev of a whole matrix; in a device group (comm.cuh) each rank extends a block of the columns of a tall
+// matrix and the blocks are all-gathered (columns are contiguous in the column-major LDE buffer)
+static void lde_matrix(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, size_t out_stride, unsigned logn,
+                       uint32_t w, LdeShift kind, LdeBatch* batch) {
+  if (!comm_splits(ctx, logn + 1)) return lde_dev(ctx, in, in_stride, out, out_stride, logn, w, kind, batch);
+  size_t c0, c1;
+  comm_range(ctx, w, &c0, &c1);
+  lde_dev(ctx, in + c0 * in_stride, in_stride, out + c0 * out_stride, out_stride, logn, (uint32_t)(c1 - c0), kind, nullptr);
+  comm_allgather_columns(ctx, out, out_stride, w);
+}
+
 static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record& rec, uint32_t shard, uint32_t ss,
                                                 bool whole_record) {
   lsk_ctx* ctx = m.ctx;
@@ -271,7 +283,7 @@ static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record
         tr.upload(pv.data(), pv.size());
       }
     }
-    lde_dev(ctx, tr.p, n, lde.p, 2 * n, it.logn, c.width, LdeShift::Trace, &small_ldes);
+    lde_matrix(ctx, tr.p, n, lde.p, 2 * n, it.logn, c.width, LdeShift::Trace, &small_ldes);
     refs.push_back(MatRef{lde.p, 2 * n, it.logn + 1, c.width});
     sd->chip_ids.push_back(it.chip);
     sd->logn.push_back(it.logn);
@@ -333,7 +345,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     perm_lde[i].alloc(ctx, 2 * n * pcols);
     perm_trace_dev(ctx, d, sd.main[i].p, n, c.prep_width ? m.prep_trace.p : nullptr, n, sd.logn[i], chal_alpha, d_beta.p,
                    perm.p, n, scratch.p, cums.p + i);
-    lde_dev(ctx, perm.p, n, perm_lde[i].p, 2 * n, sd.logn[i], pcols, LdeShift::Trace, &small_ldes);
+    lde_matrix(ctx, perm.p, n, perm_lde[i].p, 2 * n, sd.logn[i], pcols, LdeShift::Trace, &small_ldes);
     refs.push_back(MatRef{perm_lde[i].p, 2 * n, sd.logn[i] + 1, pcols});
     if (sd.logn[i] <= 12) small_perms.push_back(std::move(perm));
     sd.main[i].release();  // the natural-domain trace is not needed past this point
@@ -387,8 +399,8 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       quotient_dev(ctx, d, a);
       for (int j = 0; j < 2; j++) {
         quot_lde[2 * i + j].alloc(ctx, 2 * n * 4);
-        lde_dev(ctx, qvp + (size_t)j * n, 2 * n, quot_lde[2 * i + j].p, 2 * n, sd.logn[i], 4,
-                j ? LdeShift::QuotChunk1 : LdeShift::QuotChunk0, &small_ldes);
+        lde_matrix(ctx, qvp + (size_t)j * n, 2 * n, quot_lde[2 * i + j].p, 2 * n, sd.logn[i], 4,
+                   j ? LdeShift::QuotChunk1 : LdeShift::QuotChunk0, &small_ldes);
         refs.push_back(MatRef{quot_lde[2 * i + j].p, 2 * n, sd.logn[i] + 1, 4});
       }
     }
@@ -417,6 +429,8 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     oo[i].quot[1] = nopen; nopen += 8;
   }
   DevBuf<Ext> opened(ctx, nopen);
+  const bool grouped = comm_active(ctx);
+  if (grouped) opened.zero();   // every value is computed by exactly one rank and summed over the group
   {
     // one batch (two launches) per distinct height: all matrices of the chips of that height
     std::map<unsigned, std::vector<OpenMat>> by_logn;
@@ -432,6 +446,30 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     for (auto& kv : by_logn) {
       const unsigned logn = kv.first;
       const size_t n = (size_t)1 << logn;
+      if (grouped) {
+        // tall matrices: this rank's block of the concatenated column list; the rest: rank 0 alone
+        std::vector<OpenMat> mine;
+        if (comm_splits(ctx, logn + 1)) {
+          size_t total = 0, b, e, at = 0;
+          for (auto& om : kv.second) total += om.w;
+          comm_range(ctx, total, &b, &e);
+          for (auto& om : kv.second) {
+            const size_t lo = std::max(b, at), hi = std::min(e, at + om.w);
+            if (lo < hi) {
+              OpenMat part = om;
+              part.p += (lo - at) * om.stride;
+              part.w = (uint32_t)(hi - lo);
+              part.out_off += 2 * (uint32_t)(lo - at);
+              mine.push_back(part);
+            }
+            at += om.w;
+          }
+        } else if (ctx->comm->rank == 0) {
+          mine = kv.second;
+        }
+        kv.second.swap(mine);
+        if (kv.second.empty()) continue;
+      }
       DevBuf<Ext> w0(ctx, n), w1(ctx, n);
       bary_weights_dev(ctx, logn, zeta, w0.p);
       bary_weights_dev(ctx, logn, emul_base(zeta, two_adic_generator(logn)), w1.p);
@@ -439,6 +477,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       // the weight buffers are freed stream-ordered after the kernels that read them
     }
   }
+  if (grouped) comm_allreduce_u32(ctx, (uint32_t*)opened.p, 4 * nopen);
   std::vector<Ext> h_open(nopen), h_cums(nchips);
   opened.download(h_open.data(), nopen);
   cums.download(h_cums.data(), nchips);
@@ -568,14 +607,24 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   // ---- query phase: one query template, instantiated on the device for every sampled index
   std::vector<QuerySeg> segs;
   uint32_t wpq = 0;  // words per query
+  // in a device group rank 0 supplies the literals and everything read from replicated buffers; the
+  // distributed bottom layers of a tree are supplied by the rank that owns the node (comm.cuh)
+  const int32_t common = !grouped ? QSEG_ALL : (ctx->comm->rank == 0 ? QSEG_ALL : QSEG_NONE);
   auto lit = [&](uint32_t v) {
-    segs.push_back(QuerySeg{nullptr, 0, 1, wpq, 0, 0, 0, v});
+    segs.push_back(QuerySeg{nullptr, 0, 1, wpq, 0, 0, 0, v, 0, common});
     wpq += 1;
   };
   auto data = [&](const uint32_t* p, uint64_t stride, uint32_t count, uint32_t shift, uint32_t xor1, uint32_t mul) {
     if (!count) return;
-    segs.push_back(QuerySeg{p, stride, count, wpq, shift, xor1, mul, 0});
+    segs.push_back(QuerySeg{p, stride, count, wpq, shift, xor1, mul, 0, 0, common});
     wpq += count;
+  };
+  auto digest = [&](const MerkleTreeDev& t, unsigned l, uint32_t shift) {   // sibling digest of layer l
+    data(t.layer(l), 1, 8, shift, 1, 8);
+    if (l < t.dist_layers) {
+      segs.back().own_shift = t.log_max - l - ctx->comm->log_size;
+      segs.back().own_rank = ctx->comm->rank;
+    }
   };
   lit((uint32_t)rounds.size());
   for (auto& rd : rounds) {
@@ -587,14 +636,14 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       data(mt.p, mt.stride, mt.w, log_max - mt.lh, 0, 1);  // row r = index >> (log_max - lh), one word per column
     }
     lit(t.log_max);
-    for (unsigned l = 0; l < t.log_max; l++) data(t.layer(l), 1, 8, tshift + l, 1, 8);  // sibling digest of layer l
+    for (unsigned l = 0; l < t.log_max; l++) digest(t, l, tshift + l);
   }
   lit(nlayers);
   for (unsigned li = 0; li < nlayers; li++) {
     const MerkleTreeDev& t = fri_trees[li];
     data((const uint32_t*)fri_vals[li].p, 1, 4, li, 1, 4);  // the other element of the pair
     lit(t.log_max);
-    for (unsigned l = 0; l < t.log_max; l++) data(t.layer(l), 1, 8, li + 1 + l, 1, 8);
+    for (unsigned l = 0; l < t.log_max; l++) digest(t, l, li + 1 + l);
   }
   std::vector<uint32_t> indices(m.num_queries);
   for (auto& ix : indices) ix = ch.sample_bits(log_max);
@@ -605,6 +654,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     d_segs.upload(segs.data(), segs.size());
     d_idx.upload(indices.data(), indices.size());
     query_assemble_dev(ctx, d_segs.p, (uint32_t)segs.size(), d_idx.p, m.num_queries, wpq, d_out.p);
+    if (grouped) comm_allreduce_u32(ctx, d_out.p, gathered.size());
     d_out.download(gathered.data(), gathered.size());
     LSK_CUDA(cudaStreamSynchronize(st));
     m.last_d2h += gathered.size() * 4;

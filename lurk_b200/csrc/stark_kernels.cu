@@ -11,6 +11,8 @@
 #include "poseidon2.cuh"
 #include "stark_kernels.cuh"
 
+#include "comm.cuh"
+
 namespace lsk {
 
 // ---- shared device helpers ---------------------------------------------------------------------------
@@ -169,8 +171,8 @@ __global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientC
                                                         const uint32_t* __restrict__ inter, uint32_t nint, uint32_t pw) {
   const unsigned l2 = a.logn + 1;
   const size_t n2 = (size_t)1 << l2;
-  const size_t base = (size_t)blockIdx.x * (256 * ROWS) + threadIdx.x;
-  if (base >= n2) return;
+  const size_t base = a.row_begin + (size_t)blockIdx.x * (256 * ROWS) + threadIdx.x;
+  if (base >= a.row_end) return;
   size_t r[ROWS], rn[ROWS];
   uint32_t ii[ROWS], sel[ROWS][3];
   bool live[ROWS];
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientC
 #pragma unroll
   for (int k = 0; k < ROWS; k++) {
     r[k] = base + (size_t)k * 256;
-    live[k] = r[k] < n2;
+    live[k] = r[k] < a.row_end;
     if (!live[k]) r[k] = base;  // recompute a valid row, never stored
     ii[k] = bitrev32((uint32_t)r[k], l2);
     rn[k] = bitrev32((uint32_t)((ii[k] + 2) & (n2 - 1)), l2);
@@ -286,7 +288,8 @@ __global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientC
   }
 }
 
-void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a) {
+void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& args) {
+  QuotientArgs a = args;
   QuotientConsts qc;
   qc.g = to_mont(GEN);
   qc.w2n = two_adic_generator(a.logn + 1);
@@ -297,11 +300,17 @@ void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a) {
   qc.inv_zh[0] = finv(qc.zh[0]);
   qc.inv_zh[1] = finv(qc.zh[1]);
   size_t n2 = (size_t)2 << a.logn;
+  // in a device group each rank evaluates a contiguous range of LDE rows; the 4 output columns are all-gathered
+  const bool split = comm_splits(ctx, a.logn + 1);
+  a.row_begin = 0, a.row_end = n2;
+  if (split) comm_range(ctx, n2, &a.row_begin, &a.row_end);
+  const size_t nrows = a.row_end - a.row_begin;
   const uint4* code = reinterpret_cast<const uint4*>(chip.code.p);
-  ProfScope ps(ctx, PT_QUOTIENT, 1, (double)n2 * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw + 16.0));
+  {
+  ProfScope ps(ctx, PT_QUOTIENT, 1, (double)nrows * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw + 16.0));
 #define QK(R, ROWS)                                                                                              \
-  quotient_kernel<R, ROWS><<<div_up(n2, 256 * ROWS), 256, 0, ctx->stream>>>(a, qc, code, chip.ninstr, chip.consts.p, \
-                                                                            chip.inter.p, chip.nint, chip.pw)
+  quotient_kernel<R, ROWS><<<div_up(nrows, 256 * ROWS), 256, 0, ctx->stream>>>(a, qc, code, chip.ninstr, chip.consts.p, \
+                                                                               chip.inter.p, chip.nint, chip.pw)
   // two rows per thread for the long programs (hasher chips) once there are enough rows to fill the machine
   // (measured on the 655-wide hash4 chip, 2^21 LDE rows: 35.8 ms with one row per thread, 24.1 with two, 29.2 with four)
   const bool two = chip.ninstr >= 1024 && n2 >= ((size_t)1 << 19);
@@ -312,6 +321,8 @@ void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a) {
   else fail(LSK_ERR_ARG, "constraint program needs %u registers (> 1024)", chip.n_regs);
 #undef QK
   LSK_CUDA(cudaGetLastError());
+  }
+  if (split) comm_allgather_strided(ctx, a.out, a.ostride * 4, 4, nrows * 4);
 }
 
 // ---- openings -------------------------------------------------------------------------------------------
@@ -437,9 +448,10 @@ void open_batch_dev(lsk_ctx* ctx, const std::vector<OpenMat>& mats, unsigned log
 // ---- FRI: reduced openings, fold, grind --------------------------------------------------------------------
 __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* __restrict__ mats, uint32_t nmats,
                                                                unsigned lh, uint32_t g, uint32_t w, Ext z0, Ext z1,
-                                                               const Ext* __restrict__ apow, Ext* __restrict__ ro) {
-  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (r >> lh) return;
+                                                               const Ext* __restrict__ apow, size_t row_begin,
+                                                               size_t row_end, Ext* __restrict__ ro) {
+  size_t r = row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= row_end) return;
   uint32_t x = fmul(g, fpow(w, bitrev32((uint32_t)r, lh)));
   Ext acc0 = ext_zero(), acc1 = ext_zero();
   bool any1 = false;
@@ -460,12 +472,18 @@ __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* _
 }
 void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats, unsigned lh, Ext zeta,
                          const Ext* alpha_pows_dev, Ext* ro, double algorithmic_bytes) {
-  size_t n = (size_t)1 << lh;
-  ProfScope ps(ctx, PT_REDUCE_OPEN, 1, algorithmic_bytes);
-  Ext z1 = emul_base(zeta, two_adic_generator(lh - 1));
-  reduce_openings_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
-                                                                  two_adic_generator(lh), zeta, z1, alpha_pows_dev, ro);
-  LSK_CUDA(cudaGetLastError());
+  size_t n = (size_t)1 << lh, b = 0, e = n;
+  const bool split = comm_splits(ctx, lh);   // each rank reduces a range of rows, the vector is all-gathered
+  if (split) comm_range(ctx, n, &b, &e);
+  {
+    ProfScope ps(ctx, PT_REDUCE_OPEN, 1, algorithmic_bytes * (double)(e - b) / (double)n);
+    Ext z1 = emul_base(zeta, two_adic_generator(lh - 1));
+    reduce_openings_kernel<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
+                                                                        two_adic_generator(lh), zeta, z1, alpha_pows_dev,
+                                                                        b, e, ro);
+    LSK_CUDA(cudaGetLastError());
+  }
+  if (split) comm_allgather(ctx, ro, (e - b) * sizeof(Ext));
 }
 
 __global__ void __launch_bounds__(256) fri_fold_kernel(const Ext* __restrict__ cur, unsigned logh, uint32_t ginv,
@@ -536,10 +554,13 @@ __global__ void __launch_bounds__(256) query_assemble_kernel(const QuerySeg* __r
   const unsigned lane = threadIdx.x & 31;
   for (uint32_t s = threadIdx.x >> 5; s < nsegs; s += 8) {  // one warp per segment
     const QuerySeg g = segs[s];
-    if (!g.p) {
+    const uint32_t node = (index >> g.shift) ^ g.xor1;
+    if (g.own_rank != QSEG_ALL && (g.own_rank == QSEG_NONE || (node >> g.own_shift) != (uint32_t)g.own_rank)) {
+      for (uint32_t k = lane; k < g.count; k += 32) o[g.dst + k] = 0;   // another rank of the group supplies these
+    } else if (!g.p) {
       for (uint32_t k = lane; k < g.count; k += 32) o[g.dst + k] = g.lit;
     } else {
-      const size_t first = (size_t)((index >> g.shift) ^ g.xor1) * g.mul;
+      const size_t first = (size_t)node * g.mul;
       for (uint32_t k = lane; k < g.count; k += 32) o[g.dst + k] = from_mont(g.p[first + (size_t)k * g.stride]);
     }
   }

@@ -43,6 +43,7 @@ struct QuotientArgs {
   Ext chal_alpha;
   unsigned logn;
   uint32_t* out; size_t ostride;  // 4 columns of 2N rows
+  size_t row_begin, row_end;      // set by quotient_dev: the LDE rows this launch evaluates
 };
 void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a);
 
@@ -86,10 +87,17 @@ uint32_t grind_dev(lsk_ctx* ctx, const uint32_t state[16], const uint32_t* pendi
 // queries (literals included) in their final order.  A segment is `count` words at dst:
 //   p == nullptr : the literal `lit`;
 //   else         : from_mont(p[first + k * stride]), first = (((index >> shift) ^ xor1) * mul).
+// In a device group (comm.cuh) every rank instantiates the same template but writes zeros for the words another
+// rank supplies, and the query words are summed over the group: own_rank = QSEG_ALL writes always, QSEG_NONE
+// never, r >= 0 only when the source node ((index >> shift) ^ xor1) >> own_shift equals r (distributed Merkle
+// layers: the owner of a node also owns its sibling).
+constexpr int32_t QSEG_ALL = -1, QSEG_NONE = -2;
 struct QuerySeg {
   const uint32_t* p;
   uint64_t stride;
   uint32_t count, dst, shift, xor1, mul, lit;
+  uint32_t own_shift;
+  int32_t own_rank;
 };
 // out: nqueries x words_per_query
 void query_assemble_dev(lsk_ctx* ctx, const QuerySeg* segs_dev, uint32_t nsegs, const uint32_t* indices_dev,

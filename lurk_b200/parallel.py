@@ -89,6 +89,22 @@ def prove_distributed(machine, shards: Sequence, dst: int = 0) -> Optional[Machi
 
 
 # ------------------------------------------------------------------------------------------------
+# Column-sharded prove: the ranks of the process group prove every shard TOGETHER
+# ------------------------------------------------------------------------------------------------
+def join_device_group(ctx) -> None:
+    """Make the ranks of the torch.distributed process group one device group of the library: afterwards
+    `machine.prove(record)` called by every rank with the same record splits the throughput-bound stages of each
+    shard over the GPUs (LDE by column block, Merkle / quotient / reduced openings by row range) and returns the
+    same proof on every rank -- word for word the single-GPU proof.  torch.distributed only carries the 128-byte
+    NCCL id; the collectives on the data path are issued by the library on its own stream."""
+    from . import _native as N
+    world, rank = dist.get_world_size(), dist.get_rank()
+    box = [N.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    ctx.comm_init(rank, world, box[0])
+
+
+# ------------------------------------------------------------------------------------------------
 # Column-sharded commit of one matrix (SURVEY.md 8e.2; the second multi-GPU mode of the north star)
 # ------------------------------------------------------------------------------------------------
 def column_partition(width: int, world: int, rank: int) -> range:

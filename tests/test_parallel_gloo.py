@@ -81,3 +81,17 @@ def test_shard_ownership_is_a_partition():
         for n in (0, 1, 4, 9):
             owned = sorted(s for r in range(world) for s in shards_of_rank(n, r, world))
             assert owned == list(range(n))
+def test_device_group_partition_is_a_contiguous_cover():
+    # lsk_comm_partition: the share of columns / rows / Merkle nodes each rank of a column-sharded prove computes
+    from lurk_b200 import _native as N
+    for n in (0, 1, 4, 18, 655, 1 << 20, (1 << 22) + 5):
+        for size in (1, 2, 4, 8):
+            parts = [N.comm_partition(n, r, size) for r in range(size)]
+            assert parts[0].start == 0 and parts[-1].stop == n
+            for a, b in zip(parts, parts[1:]):
+                assert a.stop == b.start
+            if n % size == 0:
+                assert len({len(p) for p in parts}) == 1      # equal shares: what the in-place all-gathers need
+            assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    with pytest.raises(N.LurkStarkError):
+        N.comm_partition(8, 2, 2)

@@ -238,8 +238,12 @@ def run_ours(args):
     q = QueryRecord.new(top)
     t0 = time.perf_counter()
     K = args.shards_per_gpu
-    column = args.partition == "column"   # every shard is proved by ALL ranks together (strong scaling)
-    nshards = K if column else world * K
+    column = args.partition == "column"   # every shard is proved by a GROUP of ranks together
+    g = (args.gpus_per_shard or world) if column else 1
+    if world % g:
+        raise SystemExit("--gpus-per-shard must divide --gpus")
+    ngroups = world // g
+    nshards = ngroups * K
     out = execute_by_name(top, entry, [nshards * (1 << L) - 1], q)
     q.finalize()                       # row-ordered tables: each rank uploads only its shard's slice
     t_exec = time.perf_counter() - t0
@@ -247,12 +251,14 @@ def run_ours(args):
     cfg = ShardingConfig(1 << L)
     shards = Shard(q, 0, cfg).shard(cfg)
     assert len(shards) == nshards, (len(shards), world, K)
+    shards_of = None
     if column:
-        mine_all = list(shards)
+        from lurk_b200.parallel import group_shards, join_device_group
+        mine_all = [shards[rank // g + j * ngroups] for j in range(K)]   # group j proves shards j, j + ngroups, ...
         whole = Shard(q, 0, cfg)
+        shards_of = group_shards(nshards, ngroups, g)
         if world > 1:
-            from lurk_b200.parallel import join_device_group
-            join_device_group(ctx)     # the library splits each stage over the group and all-gathers (NCCL, own stream)
+            join_device_group(ctx, g)  # the library splits each stage over the group and all-gathers (NCCL, own stream)
     else:
         mine_all = [shards[rank + j * world] for j in range(K)]   # rank r proves shards r, r + G, ...
     mine = mine_all[0]
@@ -267,21 +273,21 @@ def run_ours(args):
 
     def step_resident():
         mine_roots = {s.index: m.commit_shard(s) for s in mine_all}
-        if world > 1 and not column:
-            roots = all_gather_roots(mine_roots, world * K)
+        if ngroups > 1:
+            roots = all_gather_roots(mine_roots, nshards, shards_of)
         else:
             roots = np.stack([mine_roots[i] for i in range(K)])
         return {s.index: m.prove_shard(s, roots) for s in mine_all}
 
     def step_e2e():
-        if column:
+        if column and ngroups == 1:
             return m.prove(pk, whole).words     # every rank uploads the record and ends with the same proof
         if world == 1:
             return m.prove(pk, mine).words      # lsk_prove: upload, all K shards, one proof
         m.release_record()             # force the host -> device upload of the record
         parts = step_resident()
         # the proof of the job is the concatenation of the shard proofs: collect them on rank 0
-        parts = gather_shard_proofs(parts, world * K, 0)
+        parts = gather_shard_proofs(parts, nshards, 0, shards_of)
         return assemble_proof(parts).words if rank == 0 else None
 
     def timed(step, steps, profile):
@@ -361,10 +367,11 @@ def run_ours(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": res_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if column else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "scaling": "strong" if column and ngroups == 1 else "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": {"workload": workload_name(L, nshards, args.workload), "log_rows": L, "shards": nshards,
-                       "partition": ("column-sharded: every shard proved by all %d GPUs together (LDE by column block, "
-                                     "Merkle / quotient / reduced openings by row range, NCCL all-gathers)" % world)
+                       "partition": ("column-sharded: %d group(s) of %d GPUs, every shard proved by one group together (LDE by "
+                                     "column block, Merkle / quotient / reduced openings by row range, NCCL all-gathers)"
+                                     % (ngroups, g))
                        if column else "one shard per GPU at a time (rank r proves shards r, r+G, ...)",
                        "rows_per_step": rows, "l2": "flushed between timed steps (256 MiB write)",
                        "executor_s": round(t_exec, 3), "output_word0": int(out[0]), "proof_words": int(len(proof)),
@@ -395,6 +402,9 @@ def main():
     ap.add_argument("--partition", default="shard", choices=["shard", "column"],
                     help="multi-GPU mode: shard = one shard per GPU (weak scaling, the default); column = all GPUs prove "
                          "each of --shards-per-gpu shards together (strong scaling; configs[3])")
+    ap.add_argument("--gpus-per-shard", type=int, default=0,
+                    help="with --partition column: GPUs that prove one shard together (default: all of them); "
+                         "--gpus 8 --gpus-per-shard 2 proves 4 shards at a time, two GPUs each")
     ap.add_argument("--workload", default="fib", choices=["fib", "cons"],
                     help="fib: BASELINE configs[1] (default); cons: Lurk-shaped hash-chip load (configs[2] substitute)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

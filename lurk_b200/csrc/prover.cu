@@ -468,7 +468,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
           mine = kv.second;
         }
         kv.second.swap(mine);
-        if (kv.second.empty()) continue;
+        if (kv.second.empty() && !comm_splits(ctx, logn)) continue;   // (split weights are a collective)
       }
       DevBuf<Ext> w0(ctx, n), w1(ctx, n);
       bary_weights_dev(ctx, logn, zeta, w0.p);

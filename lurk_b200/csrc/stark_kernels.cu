@@ -326,9 +326,10 @@ void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& args) {
 }
 
 // ---- openings -------------------------------------------------------------------------------------------
-__global__ void bary_weights_kernel(unsigned logn, uint32_t g, uint32_t wn, Ext z, Ext scale, Ext* __restrict__ wts) {
-  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (r >> logn) return;
+__global__ void bary_weights_kernel(unsigned logn, uint32_t g, uint32_t wn, Ext z, Ext scale, size_t row_begin,
+                                    size_t row_end, Ext* __restrict__ wts) {
+  size_t r = row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= row_end) return;
   uint32_t x = fmul(g, fpow(wn, bitrev32((uint32_t)r, logn)));
   Ext d = einv(esub_base(z, x));   // z - x
   wts[r] = emul(emul_base(d, x), scale);
@@ -340,9 +341,15 @@ void bary_weights_dev(lsk_ctx* ctx, unsigned logn, Ext z, Ext* wts) {
   // scale = (z^n - g^n) / (g^n * n)
   Ext zn = epow(z, n);
   Ext scale = emul_base(esub_base(zn, gn), finv(fmul(gn, to_mont((uint32_t)n))));
-  ProfScope ps(ctx, PT_BARY, 1, 16.0 * n);
-  bary_weights_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(logn, g, two_adic_generator(logn), z, scale, wts);
-  LSK_CUDA(cudaGetLastError());
+  size_t b = 0, e = n;
+  const bool split = comm_splits(ctx, logn);   // one Ext inversion per row: a range of rows per rank, all-gathered
+  if (split) comm_range(ctx, n, &b, &e);
+  {
+    ProfScope ps(ctx, PT_BARY, 1, 16.0 * (e - b));
+    bary_weights_kernel<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(logn, g, two_adic_generator(logn), z, scale, b, e, wts);
+    LSK_CUDA(cudaGetLastError());
+  }
+  if (split) comm_allgather(ctx, wts, (e - b) * sizeof(Ext));
 }
 
 constexpr int OPEN_COLS = 8;

@@ -29,12 +29,16 @@ def shards_of_rank(num_shards: int, rank: int, world: int) -> List[int]:
     return list(range(rank, num_shards, world))
 
 
-def all_gather_roots(local: dict, num_shards: int) -> np.ndarray:
-    """local: {shard index: 8-word root} for this rank's shards -> (num_shards, 8) array on every rank."""
+def all_gather_roots(local: dict, num_shards: int, shards_of=None) -> np.ndarray:
+    """local: {shard index: 8-word root} for this rank's shards -> (num_shards, 8) array on every rank.
+    shards_of(r): the shards rank r contributes (default: r, r + G, ...; device groups: the group leader's)."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    per = (num_shards + world - 1) // world
+    if shards_of is None:
+        def shards_of(r):
+            return shards_of_rank(num_shards, r, world)
+    per = max(1, max(len(shards_of(r)) for r in range(world)))
     buf = torch.zeros((per, 8), dtype=torch.int64)
-    for k, s in enumerate(shards_of_rank(num_shards, rank, world)):
+    for k, s in enumerate(shards_of(rank)):
         buf[k] = torch.from_numpy(np.asarray(local[s], dtype=np.int64))
     buf = buf.to(_device())
     outs = [torch.empty_like(buf) for _ in range(world)]
@@ -42,23 +46,26 @@ def all_gather_roots(local: dict, num_shards: int) -> np.ndarray:
     roots = np.zeros((num_shards, 8), dtype=np.uint32)
     for r, o in enumerate(outs):
         o = o.cpu().numpy()
-        for k, s in enumerate(shards_of_rank(num_shards, r, world)):
+        for k, s in enumerate(shards_of(r)):
             roots[s] = o[k].astype(np.uint32)
     return roots
 
 
-def gather_shard_proofs(local: dict, num_shards: int, dst: int = 0) -> Optional[List[np.ndarray]]:
+def gather_shard_proofs(local: dict, num_shards: int, dst: int = 0, shards_of=None) -> Optional[List[np.ndarray]]:
     """local: {shard index: proof words}; returns the ordered list on rank `dst`, None elsewhere."""
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = _device()
-    mine = shards_of_rank(num_shards, rank, world)
+    if shards_of is None:
+        def shards_of(r):
+            return shards_of_rank(num_shards, r, world)
+    mine = shards_of(rank)
     sizes = torch.zeros(num_shards, dtype=torch.int64)
     for s in mine:
         sizes[s] = len(local[s])
     sizes = sizes.to(dev)
     dist.all_reduce(sizes)                      # every shard is owned by exactly one rank
     sizes = sizes.cpu().numpy()
-    per = (num_shards + world - 1) // world
+    per = max(1, max(len(shards_of(r)) for r in range(world)))
     cap = int(sizes.max()) if num_shards else 0
     buf = torch.zeros((per, cap), dtype=torch.int64)
     for k, s in enumerate(mine):
@@ -71,37 +78,53 @@ def gather_shard_proofs(local: dict, num_shards: int, dst: int = 0) -> Optional[
     parts: List[Optional[np.ndarray]] = [None] * num_shards
     for r, o in enumerate(outs):
         o = o.cpu().numpy()
-        for k, s in enumerate(shards_of_rank(num_shards, r, world)):
+        for k, s in enumerate(shards_of(r)):
             parts[s] = o[k, :int(sizes[s])].astype(np.uint32)
     return parts
 
 
-def prove_distributed(machine, shards: Sequence, dst: int = 0) -> Optional[MachineProof]:
+def prove_distributed(machine, shards: Sequence, dst: int = 0, gpus_per_group: int = 1) -> Optional[MachineProof]:
     """machine.prove for a record cut into `shards` (Shard::shard), spread over the process group.
     `machine` needs commit_shard(shard) -> root and prove_shard(shard, roots) -> words
-    (lurk_b200.machine.StarkMachine).  Returns the MachineProof on rank `dst`."""
+    (lurk_b200.machine.StarkMachine).  Returns the MachineProof on rank `dst`.
+    gpus_per_group > 1: consecutive ranks form device groups (join_device_group) that prove their shards
+    together -- every rank of group j makes the same calls for shards j, j + groups, ..., the leader reports."""
     world, rank = dist.get_world_size(), dist.get_rank()
     n = len(shards)
-    mine = shards_of_rank(n, rank, world)
-    roots = all_gather_roots({s: machine.commit_shard(shards[s]) for s in mine}, n)
-    parts = gather_shard_proofs({s: machine.prove_shard(shards[s], roots) for s in mine}, n, dst)
+    assert world % gpus_per_group == 0
+    shards_of = group_shards(n, world // gpus_per_group, gpus_per_group)
+    mine = list(range(rank // gpus_per_group, n, world // gpus_per_group))
+    roots = all_gather_roots({s: machine.commit_shard(shards[s]) for s in mine}, n, shards_of)
+    parts = gather_shard_proofs({s: machine.prove_shard(shards[s], roots) for s in mine}, n, dst, shards_of)
     return assemble_proof(parts) if parts is not None else None
 
 
 # ------------------------------------------------------------------------------------------------
 # Column-sharded prove: the ranks of the process group prove every shard TOGETHER (SURVEY.md 8e.2)
 # ------------------------------------------------------------------------------------------------
-def join_device_group(ctx) -> None:
-    """Make the ranks of the torch.distributed process group one device group of the library: afterwards
-    `machine.prove(record)` called by every rank with the same record splits the throughput-bound stages of each
-    shard over the GPUs (LDE by column block, Merkle / quotient / reduced openings by row range) and returns the
-    same proof on every rank -- word for word the single-GPU proof.  torch.distributed only carries the 128-byte
-    NCCL id; the collectives on the data path are issued by the library on its own stream."""
+def join_device_group(ctx, gpus_per_group: Optional[int] = None):
+    """Make the ranks of the torch.distributed process group device groups of the library (consecutive ranks,
+    `gpus_per_group` each; default: one group of all ranks): afterwards `machine.prove(record)` /
+    `commit_shard` / `prove_shard` called by every rank of a group with the same arguments splits the
+    throughput-bound stages of each shard over the group's GPUs (LDE by column block, Merkle / quotient / reduced
+    openings by row range) and returns the same proof on every rank of the group -- word for word the single-GPU
+    proof.  torch.distributed only carries the 128-byte NCCL ids; the collectives on the data path are issued by
+    the library on its own stream.  Returns (group index, number of groups, rank within the group)."""
     from . import _native as N
     world, rank = dist.get_world_size(), dist.get_rank()
-    box = [N.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(box, src=0)
-    ctx.comm_init(rank, world, box[0])
+    g = gpus_per_group or world
+    assert world % g == 0 and g & (g - 1) == 0, "group size must be a power of two dividing the number of ranks"
+    ids = [None] * world
+    dist.all_gather_object(ids, N.comm_unique_id() if rank % g == 0 else None)
+    ctx.comm_init(rank % g, g, ids[rank - rank % g])
+    return rank // g, world // g, rank % g
+
+
+def group_shards(num_shards: int, ngroups: int, gpus_per_group: int):
+    """shards_of(rank) for device groups: group j proves shards j, j + ngroups, ...; its leader reports them."""
+    def shards_of(r):
+        return list(range(r // gpus_per_group, num_shards, ngroups)) if r % gpus_per_group == 0 else []
+    return shards_of
 
 
 # ------------------------------------------------------------------------------------------------

@@ -39,12 +39,13 @@ def expected(num_shards):
     return np.concatenate([np.asarray([PROOF_MAGIC, num_shards], dtype=np.uint32)] + parts)
 
 
-def _worker(rank, world, port, num_shards, q):
+def _worker(rank, world, port, num_shards, q, gpus_per_group=1):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        proof = prove_distributed(FakeMachine(), [FakeShard(i) for i in range(num_shards)])
+        proof = prove_distributed(FakeMachine(), [FakeShard(i) for i in range(num_shards)],
+                                  gpus_per_group=gpus_per_group)
         if rank == 0:
             q.put(proof.words)
         else:
@@ -61,12 +62,14 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world,num_shards", [(2, 2), (2, 5), (3, 4), (2, 1)])
-def test_prove_distributed_matches_sequential(world, num_shards):
+# (world, shards, ranks per device group): the last two rows are the column-sharded layouts -- one group of 2
+# proving every shard together, and 2 groups of 2 taking alternate shards (each rank of a group makes the same calls)
+@pytest.mark.parametrize("world,num_shards,group", [(2, 2, 1), (2, 5, 1), (3, 4, 1), (2, 1, 1), (2, 3, 2), (4, 5, 2)])
+def test_prove_distributed_matches_sequential(world, num_shards, group):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, num_shards, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, num_shards, q, group)) for r in range(world)]
     for p in procs:
         p.start()
     words = q.get(timeout=120)
@@ -81,6 +84,8 @@ def test_shard_ownership_is_a_partition():
         for n in (0, 1, 4, 9):
             owned = sorted(s for r in range(world) for s in shards_of_rank(n, r, world))
             assert owned == list(range(n))
+
+
 def test_device_group_partition_is_a_contiguous_cover():
     # lsk_comm_partition: the share of columns / rows / Merkle nodes each rank of a column-sharded prove computes
     from lurk_b200 import _native as N

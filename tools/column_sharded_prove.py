@@ -74,7 +74,8 @@ def main():
         cases += [("fib 2^16 rows, one shard", "fib", (1 << 16) - 1, None),
                   ("fib 2^17+5 rows in shards of 2^16", "fib", (1 << 17) + 4, 1 << 16),
                   ("cons 2^15 rows of the hash4 chip", "cons", (1 << 15) - 1, None)]
-    cases.append(("timed: %s 2^%d rows" % (args.workload, args.log_rows), args.workload, (1 << args.log_rows) - 1, None))
+    cases.append(("timed: %s 2^%d rows, one shard" % (args.workload, args.log_rows), args.workload,
+                  (1 << args.log_rows) - 1, max(1 << 22, 1 << args.log_rows)))
     alone = {}
     built = {}
     for name, wl, n_arg, ss in cases:

@@ -620,7 +620,9 @@ struct Reader {
     std::vector<Var> v;
     for (uint32_t i = 0; i < cnt; i++) {
       std::string name = s();
-      v.emplace_back(name, u());
+      uint32_t size = u();
+      if (size == 0 || size > (1u << 16)) bail("bad variable size in surface image");
+      v.emplace_back(name, size);
     }
     return v;
   }
@@ -678,8 +680,8 @@ std::pair<std::vector<FuncE>, std::vector<ChipInfo>> parse_surface(const uint32_
   if (r.u() != 0x4c535246u) bail("bad surface image magic");
   uint32_t ns = r.u();
   for (uint32_t i = 0; i < ns; i++) {
-    uint32_t nb = r.u(), nw = (nb + 3) / 4;
-    if (r.p + nw > n) bail("surface image truncated");
+    const size_t nb = r.u(), nw = (nb + 3) / 4;
+    if (nw > n - r.p) bail("surface image truncated");
     r.strs.emplace_back((const char*)(w + r.p), nb);
     r.p += nw;
   }

@@ -12,6 +12,7 @@
 // This is the producer of the hot path's input; it is sequential by construction (memo table +
 // nonce order) and stays on the CPU exactly like the reference's.
 #include <cstring>
+#include <memory>
 
 #include "common.h"
 #include "poseidon2_constants.h"
@@ -481,6 +482,168 @@ bool record_row_ordered(const lsk_record& r) {
 
 using namespace lsk;
 
+// The executor and the trace kernel walk the program image without further checks, so lsk_program_load accepts
+// only images every walk of which stays inside the image and inside the per-row value stack: block lengths and
+// nesting, operand indices against the stack height at that point (and the stack against the declared
+// max_map), func / chip / memory-table references and arities, the shape of every control node.  It also keeps
+// the reference's load-time rule that a total func may not call a partial one ("assertion failed: ctx.partial",
+// src/lair/execute.rs:1005-1023).  The column budget (aux, sel) is the compiler's statement and is trusted.
+namespace {
+struct ImageChecker {
+  const lsk_program& p;
+  const uint32_t* w;
+  size_t n;
+  uint32_t func = 0, max_map = 0, out_size = 0;
+  bool total = false;
+  [[noreturn]] void bad(const char* what) const { fail(LSK_ERR_ARG, "bad program image: %s (func %u)", what, func); }
+  uint32_t at(size_t i, size_t end) const {
+    if (i >= end) bad("truncated block");
+    return w[i];
+  }
+  void operands(size_t first, uint32_t count, size_t end, uint32_t height) const {
+    if (count > end || first + count > end) bad("operand list runs past its block");
+    for (uint32_t k = 0; k < count; k++)
+      if (w[first + k] >= height) bad("operand above the value stack");
+  }
+  uint32_t push(uint32_t height, uint32_t count) const {
+    if (count > max_map || height + count > max_map) bad("value stack exceeds max_map");
+    return height + count;
+  }
+  // returns the end of the block starting at `b`; `limit` = end of the enclosing region
+  size_t block(size_t b, size_t limit, uint32_t height, unsigned depth) const {
+    if (depth > 4096) bad("blocks nested too deeply");
+    if (b + 2 > limit) bad("truncated block");
+    const size_t len = w[b];
+    if (len < 2 || len > limit - b) bad("block length");
+    const size_t end = b + len;
+    const uint32_t nops = w[b + 1];
+    size_t pc = b + 2;
+    for (uint32_t k = 0; k < nops; k++) {
+      const uint32_t opc = at(pc, end);
+      switch (opc) {
+        case OP_CONST: at(pc + 1, end); height = push(height, 1); pc += 2; break;
+        case OP_ADD: case OP_SUB: operands(pc + 1, 2, end, height); height = push(height, 1); pc += 3; break;
+        case OP_MUL: operands(pc + 1, 2, end, height); at(pc + 3, end); height = push(height, 1); pc += 4; break;
+        case OP_INV: case OP_NOT: operands(pc + 1, 1, end, height); at(pc + 2, end); height = push(height, 1); pc += 3; break;
+        case OP_ASSERT_EQ: case OP_ASSERT_NE: {
+          const uint32_t cnt = at(pc + 1, end);
+          operands(pc + 2, cnt, end, height);
+          operands(pc + 2 + cnt, cnt, end, height);
+          pc += 2 + 2 * (size_t)cnt;
+        } break;
+        case OP_CONTAINS: {
+          const uint32_t cnt = at(pc + 1, end);
+          operands(pc + 2, cnt, end, height);
+          operands(pc + 2 + cnt, 1, end, height);
+          pc += 3 + (size_t)cnt;
+        } break;
+        case OP_CALL: case OP_PREIMG: {
+          const uint32_t callee = at(pc + 1, end), cnt = at(pc + 2, end);
+          if (callee >= p.nfuncs) bad("call of an unknown func");
+          const FuncHeader h = p.header(callee);
+          if (total && h.partial) fail(LSK_ERR_ARG, "assertion failed: ctx.partial (func %u is total but calls partial func %u)", func, callee);
+          if (cnt > 64 || cnt != (opc == OP_CALL ? h.in : h.out)) bad("call arity");
+          operands(pc + 3, cnt, end, height);
+          const uint32_t produced = at(pc + 3 + cnt, end);
+          at(pc + 4 + cnt, end);
+          if (produced != (opc == OP_CALL ? h.out : h.in)) bad("call result size");
+          if (opc == OP_PREIMG && !h.invertible) bad("preimage of a func that is not invertible");
+          height = push(height, produced);
+          pc += 5 + (size_t)cnt;
+        } break;
+        case OP_STORE: {
+          const uint32_t cnt = at(pc + 1, end);
+          if (mem_index_from_len((int)std::min<uint32_t>(cnt, 1000)) < 0) bad("store of an unsupported length");
+          operands(pc + 2, cnt, end, height);
+          height = push(height, 1);
+          pc += 2 + (size_t)cnt;
+        } break;
+        case OP_LOAD: {
+          const uint32_t len = at(pc + 1, end);
+          if (mem_index_from_len((int)std::min<uint32_t>(len, 1000)) < 0) bad("load of an unsupported length");
+          operands(pc + 2, 1, end, height);
+          height = push(height, len);
+          pc += 3;
+        } break;
+        case OP_EXTERN: {
+          const uint32_t chip = at(pc + 1, end), cnt = at(pc + 2, end);
+          if (chip >= p.nchips) bad("unknown extern chip");
+          const uint32_t* c = p.chip(chip);   // kind in out witness requires
+          if (cnt != c[1]) bad("extern chip arity");
+          operands(pc + 3, cnt, end, height);
+          height = push(height, c[2]);
+          pc += 3 + (size_t)cnt;
+        } break;
+        case OP_RANGE_U8: {
+          const uint32_t cnt = at(pc + 1, end);
+          operands(pc + 2, cnt, end, height);
+          pc += 2 + (size_t)cnt;
+        } break;
+        default: bad("unknown opcode");
+      }
+      if (pc > end) bad("op runs past its block");
+    }
+    const uint32_t ctrl = at(pc, end);
+    if (ctrl == CTRL_RETURN) {
+      at(pc + 1, end);
+      const uint32_t cnt = at(pc + 2, end);
+      if (cnt != out_size) bad("return arity");
+      operands(pc + 3, cnt, end, height);
+      pc += 3 + (size_t)cnt;
+    } else if (ctrl == CTRL_CHOOSE || ctrl == CTRL_CHOOSE_MANY) {
+      const uint32_t nv = at(pc + 1, end);
+      if (nv == 0 || nv > 64 || (ctrl == CTRL_CHOOSE && nv != 1)) bad("choose arity");
+      operands(pc + 2, nv, end, height);
+      const uint32_t nb = at(pc + 2 + nv, end), has_d = at(pc + 3 + nv, end);
+      if (has_d > 1) bad("choose default flag");
+      size_t q = pc + 4 + nv;
+      for (uint32_t i = 0; i < nb; i++) {
+        const uint32_t nk = at(q, end);
+        if (ctrl == CTRL_CHOOSE_MANY && nk != 1) bad("choose-many branch key count");
+        const size_t keys = ctrl == CTRL_CHOOSE ? (size_t)nk : (size_t)nv * nk;
+        if (keys > end - q) bad("branch keys run past their block");
+        q = block(q + 1 + keys, end, height, depth + 1);
+      }
+      if (has_d) q = block(q, end, height, depth + 1);
+      pc = q;
+    } else {
+      bad("unknown control node");
+    }
+    const uint32_t nret = at(pc, end);
+    if (nret > end - pc - 1) bad("return ident list runs past its block");
+    if (pc + 1 + nret != end) bad("block length does not match its contents");
+    return end;
+  }
+};
+
+void validate_program(const lsk_program& p) {
+  const size_t n = p.words.size();
+  const size_t table = 3 + (size_t)p.nchips * CHIP_WORDS;
+  if (p.nchips > n || p.nfuncs > n || table + p.nfuncs > n) fail(LSK_ERR_ARG, "truncated program image");
+  for (uint32_t c = 0; c < p.nchips; c++) {
+    const uint32_t* ch = p.chip(c);
+    if (ch[1] > 64 || ch[2] > 4096 || ch[3] > (1u << 16) || ch[4] > 4096) fail(LSK_ERR_ARG, "bad program image: chip %u sizes", c);
+  }
+  for (uint32_t f = 0; f < p.nfuncs; f++) {
+    const size_t off = p.func_offset(f);
+    if (off < table + p.nfuncs || off + FUNC_HEADER_WORDS + 2 > n) fail(LSK_ERR_ARG, "bad program image: func %u offset", f);
+    const FuncHeader h = p.header(f);
+    if (h.in > 64 || h.out > 4096 || h.partial > 1 || h.invertible > 1 || h.aux > (1u << 20) || h.sel > (1u << 20) ||
+        h.max_map > (1u << 20) || h.in > h.max_map)
+      fail(LSK_ERR_ARG, "bad program image: func %u header", f);
+  }
+  for (uint32_t f = 0; f < p.nfuncs; f++) {
+    const FuncHeader h = p.header(f);
+    ImageChecker ck{p, p.words.data(), n};
+    ck.func = f;
+    ck.max_map = h.max_map;
+    ck.out_size = h.out;
+    ck.total = !h.partial;
+    ck.block(p.body(f), n, h.in, 0);
+  }
+}
+}  // namespace
+
 extern "C" {
 
 int lsk_record_finalize(lsk_record* r) {
@@ -502,54 +665,13 @@ int lsk_record_finalize(lsk_record* r) {
 
 int lsk_program_load(const uint32_t* words, size_t n, lsk_program** out) {
   LSK_API_BEGIN
-  if (!words || n < 3 || words[0] != PROGRAM_MAGIC) fail(LSK_ERR_ARG, "bad program image");
-  auto* p = new lsk_program;
+  if (!words || !out || n < 3 || words[0] != PROGRAM_MAGIC) fail(LSK_ERR_ARG, "bad program image");
+  auto p = std::make_unique<lsk_program>();
   p->words.assign(words, words + n);
   p->nfuncs = words[1];
   p->nchips = words[2];
-  if (3 + (size_t)p->nchips * CHIP_WORDS + p->nfuncs > n) {
-    delete p;
-    fail(LSK_ERR_ARG, "truncated program image");
-  }
-  for (uint32_t f = 0; f < p->nfuncs; f++) {
-    if (p->func_offset(f) + FUNC_HEADER_WORDS + 2 > n) { delete p; fail(LSK_ERR_ARG, "bad func offset"); }
-  }
-  // a total func may not call a partial one ("assertion failed: ctx.partial", src/lair/execute.rs:1005-1023)
-  for (uint32_t f = 0; f < p->nfuncs; f++) {
-    if (p->header(f).partial) continue;
-    const uint32_t* w = p->words.data();
-    uint32_t body = p->body(f), end = body + w[body];
-    if (end > n) { delete p; fail(LSK_ERR_ARG, "bad block length"); }
-    std::vector<uint32_t> blocks{body};
-    while (!blocks.empty()) {
-      uint32_t b = blocks.back();
-      blocks.pop_back();
-      uint32_t pc = b + 2;
-      for (uint32_t k = 0; k < w[b + 1]; k++) {
-        const uint32_t* op = w + pc;
-        if ((op[0] == OP_CALL || op[0] == OP_PREIMG) && op[1] < p->nfuncs && p->header(op[1]).partial) {
-          delete p;
-          fail(LSK_ERR_ARG, "assertion failed: ctx.partial (func %u is total but calls partial func %u)", f, op[1]);
-        }
-        uint32_t ow = op_words(op);
-        if (!ow) { delete p; fail(LSK_ERR_ARG, "bad opcode in program image"); }
-        pc += ow;
-      }
-      const uint32_t* c = w + pc;
-      if (c[0] == CTRL_CHOOSE || c[0] == CTRL_CHOOSE_MANY) {
-        uint32_t nv = c[1], nb = c[2 + nv], has_d = c[3 + nv];
-        uint32_t q = pc + 4 + nv;
-        for (uint32_t i = 0; i < nb; i++) {
-          uint32_t nk = w[q++];
-          q += c[0] == CTRL_CHOOSE ? nk : nv * nk;
-          blocks.push_back(q);
-          q += w[q];
-        }
-        if (has_d) blocks.push_back(q);
-      }
-    }
-  }
-  *out = p;
+  validate_program(*p);
+  *out = p.release();
   return LSK_OK;
   LSK_API_END
 }

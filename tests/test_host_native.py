@@ -135,3 +135,53 @@ def test_sharding_policy():
     assert len(shards) == 3
     assert [len(s.get_func_range(1)) for s in shards] == [4, 4, 2]
     assert len(Shard.new(q).shard(ShardingConfig.default())) == 1
+
+
+def test_loaders_reject_malformed_images_without_crashing():
+    # lsk_host_compile_toplevel (surface image), lsk_program_load (program image: every walk of the executor and of
+    # the trace kernel must stay inside the image and the value stack) and lsk_vk_new ('MACH' blob): truncations,
+    # absurd counts at any position and random words end in an error code or in another well-formed object
+    import ctypes
+    from lurk_b200 import host
+    from lurk_b200.programs import hash_toplevel
+    L = N.lib()
+    rng = np.random.default_rng(3)
+
+    def try_surface(w):
+        out, n = ctypes.POINTER(ctypes.c_uint32)(), ctypes.c_size_t()
+        rc = L.lsk_host_compile_toplevel(N.vp(w), ctypes.c_size_t(len(w)), ctypes.byref(out), ctypes.byref(n))
+        if rc == 0:
+            L.lsk_words_free(out)
+        return rc
+
+    def try_image(w):
+        h = ctypes.c_void_p()
+        rc = L.lsk_program_load(N.vp(w), ctypes.c_size_t(len(w)), ctypes.byref(h))
+        if rc == 0:
+            L.lsk_program_free(h)
+        return rc
+
+    def try_blob(w):
+        h = ctypes.c_void_p()
+        rc = L.lsk_vk_new(N.vp(w), ctypes.c_size_t(len(w)), N.vp(N.u32(np.zeros(8))), 1, 6, 6, ctypes.byref(h))
+        if rc == 0:
+            L.lsk_vk_free(h)
+        return rc
+
+    for top, entry in ((demo_toplevel(), "fib"), (hash_toplevel(), "cons_chain")):
+        surface = N.u32(top.surface_image())
+        image = N.u32(top.serialize())
+        blob = N.u32(host.chip_vector_blob(surface, top.func_by_name(entry).index))
+        for fn, base in ((try_surface, surface), (try_image, image), (try_blob, blob)):
+            assert fn(base) == 0
+            rejected = 0
+            for k in list(range(12)) + list(rng.integers(0, len(base), 40)):
+                rejected += fn(N.u32(base[:k])) != 0
+            assert rejected >= 45                       # a prefix is (almost) never a whole image
+            for pos in list(range(min(len(base), 150))) + list(rng.integers(0, len(base), 150)):
+                for val in (0xffffffff, 1 << 24):
+                    w = base.copy()
+                    w[pos] = val
+                    fn(w)                               # must return, whatever it answers
+            for _ in range(30):
+                assert fn(rng.integers(0, 2 ** 32, size=int(rng.integers(1, 2000)), dtype=np.uint64).astype(np.uint32)) != 0

@@ -70,3 +70,35 @@ def test_verifier_rejects_swapped_shards(oracle):
     fewer[1] = 2
     with pytest.raises(VerificationError):
         v.verify(fewer)
+
+
+def test_verifier_survives_hostile_input(oracle):
+    # the verifier parses untrusted words: truncations, absurd counts / lengths / non-canonical residues at any
+    # position, random garbage and garbage behind a valid prefix must all end in VerificationError (never a crash,
+    # never acceptance); a mutation that leaves the words unchanged is the only thing accepted
+    om, v, proof = _proof(oracle, "demo", "fib", [50])
+    v.verify(proof)
+    n = len(proof)
+    rng = np.random.default_rng(1)
+
+    def rejected(words):
+        words = np.asarray(words, dtype=np.uint32)
+        if len(words) == n and np.array_equal(words, proof):
+            return
+        with pytest.raises(VerificationError):
+            v.verify(words)
+
+    for k in list(range(40)) + list(rng.integers(0, n, 60)):
+        rejected(proof[:k])
+    for pos in list(range(120)) + list(rng.integers(0, n, 150)):
+        for val in (0xffffffff, 1 << 20, 0, P):
+            bad = proof.copy()
+            bad[pos] = val
+            rejected(bad)
+    for _ in range(60):
+        rejected(rng.integers(0, 2 ** 32, size=int(rng.integers(0, 3000)), dtype=np.uint64).astype(np.uint32))
+    for _ in range(60):
+        bad = proof.copy()
+        k = int(rng.integers(2, n))
+        bad[k:] = rng.integers(0, 2 ** 32, size=n - k, dtype=np.uint64).astype(np.uint32)
+        rejected(bad)

@@ -125,6 +125,15 @@ int lsk_machine_new(lsk_ctx* ctx, const lsk_program* prog, uint32_t entry_func, 
                     uint32_t num_queries, uint32_t pow_bits, lsk_machine** out);
 void lsk_machine_free(lsk_machine* m);
 int lsk_machine_prep_commit(const lsk_machine* m, uint32_t out8[8]);
+/* Long constraint programs (>= 1024 instructions per row: the hasher chips behind `Air::eval` of
+ * src/poseidon/wide/air.rs:11-124) can run as machine code: the program is emitted as CUDA source, compiled by NVRTC
+ * for sm_100a (~30 s per chip) and kept in a cubin cache (env LSK_JIT_CACHE, default <library directory>/jit_cache).
+ * Env LSK_JIT: "0" always interpret, "1" compile on a cache miss, unset: use cached cubins only.  The interpreter
+ * and the compiled form produce identical proofs.
+ *   lsk_jit_precompile: fill the cache for every eligible chip of a 'MACH' blob; needs NVRTC, no GPU.
+ *   lsk_machine_jit_chips: how many chips of this machine run compiled programs. */
+int lsk_jit_precompile(const uint32_t* blob, size_t n, uint32_t* compiled, uint32_t* cached);
+int lsk_machine_jit_chips(const lsk_machine* m);
 /* machine.prove::<LocalProver<_,_>>(&pk, shard, &mut challenger, opts): src/core/cli/repl.rs:194-196,
  * benches/fib.rs:154-158, tests/fib.rs:90-94.  `rec` is a HOST record; it is uploaded, sharded by
  * `shard_size` rows (Shard::shard, src/lair/execute.rs:186-216) and proved; `*words` receives a

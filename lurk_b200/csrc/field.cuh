@@ -10,7 +10,13 @@
 // A Montgomery product costs 1 IMAD.WIDE + 1 IMAD (lo) + 1 IMAD.HI + sub/compare/select on the
 // fma/alu pipes; there are no tensor-core shaped operations anywhere on this path.
 #pragma once
+#if defined(__CUDACC_RTC__)   // NVRTC (jit.cu) has no system headers
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+typedef unsigned long size_t;
+#else
 #include <stdint.h>
+#endif
 
 #if defined(__CUDACC__)
 #define LSK_HD __host__ __device__ __forceinline__

@@ -1,0 +1,294 @@
+// Run-time compilation of long constraint programs (quotient_kernel.cuh, LSK_JIT_PROGRAM).
+//
+// The interpreter pays ~24 machine instructions per program instruction (fetch, indexed branch, register file
+// in local memory with computed indices); the hasher chips of a Lurk machine have 5-10 k instructions per row.
+// For such a chip the program is emitted as CUDA source -- one statement per instruction, constants and
+// alpha-power indices as literals, 128-statement __noinline__ chunks so that NVVM never sees one giant basic
+// block (a single 7.5 k-statement block compiles for 5 minutes into 255 registers and runs slower than the
+// chunked form) -- compiled by NVRTC for sm_100a and loaded through the driver API.  NVRTC and libcuda are
+// bound with dlopen: the library links against neither.
+//
+// Compiling one hash chip takes ~30 s, so cubins are kept in a disk cache (LSK_JIT_CACHE, default
+// <directory of liblurkstark.so>/jit_cache) keyed by a hash of the generated source; lsk_jit_precompile fills
+// it without a GPU (the build step does that for the stock hasher programs).  Policy (env LSK_JIT): "0" never
+// use compiled programs; "1" compile on a cache miss; unset: use what the cache holds, interpret the rest.
+// The interpreter stays the reference path: both forms execute the same field operations in the same order,
+// and the GPU tests compare their proofs word for word.
+#include "jit.h"
+
+#include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include "device.cuh"
+#include "field.cuh"
+
+namespace lsk {
+namespace {
+
+#include "build/jit_sources.inc"   // FIELD_CUH_SRC, QUOTIENT_KERNEL_CUH_SRC (Makefile)
+
+// ---- NVRTC / driver API through dlopen ---------------------------------------------------------------------
+struct Nvrtc {
+  int (*CreateProgram)(void**, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+  int (*DestroyProgram)(void**) = nullptr;
+  int (*CompileProgram)(void*, int, const char* const*) = nullptr;
+  int (*GetProgramLogSize)(void*, size_t*) = nullptr;
+  int (*GetProgramLog)(void*, char*) = nullptr;
+  int (*GetCUBINSize)(void*, size_t*) = nullptr;
+  int (*GetCUBIN)(void*, char*) = nullptr;
+  int (*Version)(int*, int*) = nullptr;
+  bool ok = false;
+};
+struct Driver {
+  int (*ModuleLoadData)(void**, const void*) = nullptr;
+  int (*ModuleGetFunction)(void**, void*, const char*) = nullptr;
+  int (*ModuleUnload)(void*) = nullptr;
+  int (*LaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**,
+                      void**) = nullptr;
+  bool ok = false;
+};
+Nvrtc g_rtc;
+Driver g_drv;
+std::once_flag g_rtc_once, g_drv_once;
+
+template <class F>
+bool sym(void* h, F& f, const char* name) {
+  f = reinterpret_cast<F>(dlsym(h, name));
+  return f != nullptr;
+}
+Nvrtc& nvrtc() {
+  std::call_once(g_rtc_once, [] {
+    void* h = nullptr;
+    for (const char* n : {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so"})
+      if ((h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+    if (!h) return;
+    g_rtc.ok = sym(h, g_rtc.CreateProgram, "nvrtcCreateProgram") && sym(h, g_rtc.DestroyProgram, "nvrtcDestroyProgram") &&
+               sym(h, g_rtc.CompileProgram, "nvrtcCompileProgram") && sym(h, g_rtc.GetProgramLogSize, "nvrtcGetProgramLogSize") &&
+               sym(h, g_rtc.GetProgramLog, "nvrtcGetProgramLog") && sym(h, g_rtc.GetCUBINSize, "nvrtcGetCUBINSize") &&
+               sym(h, g_rtc.GetCUBIN, "nvrtcGetCUBIN") && sym(h, g_rtc.Version, "nvrtcVersion");
+  });
+  return g_rtc;
+}
+Driver& driver() {
+  std::call_once(g_drv_once, [] {
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    g_drv.ok = sym(h, g_drv.ModuleLoadData, "cuModuleLoadData") && sym(h, g_drv.ModuleGetFunction, "cuModuleGetFunction") &&
+               sym(h, g_drv.ModuleUnload, "cuModuleUnload") && sym(h, g_drv.LaunchKernel, "cuLaunchKernel");
+  });
+  return g_drv;
+}
+
+// ---- source generation ---------------------------------------------------------------------------------------
+// statements per __noinline__ chunk (LSK_JIT_CHUNK overrides, for tuning; part of the source, hence of the cache key)
+uint32_t chunk_size() {
+  if (const char* e = getenv("LSK_JIT_CHUNK")) {
+    long v = atol(e);
+    if (v >= 8 && v <= 4096) return (uint32_t)v;
+  }
+  return 128;   // measured on the hash4 chip, 2^21 rows: 32 -> 12.9 ms, 64 -> 11.5, 128 -> 10.7, 192 -> 10.9, 256 -> 14.5
+}
+
+void operand(std::string& o, uint32_t w, const ChipH& c) {
+  const uint32_t idx = w & 0x0fffffffu;
+  char buf[48];
+  switch (w >> 28) {
+    case 0: snprintf(buf, sizeof buf, "R[%u]", idx); break;
+    case 1: snprintf(buf, sizeof buf, "%uu", to_mont(c.consts[idx] % P)); break;   // Montgomery literal
+    case 2: snprintf(buf, sizeof buf, "LSK_ML(%u)", idx); break;
+    case 3: snprintf(buf, sizeof buf, "LSK_MN(%u)", idx); break;
+    case 4: snprintf(buf, sizeof buf, "LSK_PL(%u)", idx); break;
+    case 5: snprintf(buf, sizeof buf, "LSK_PN(%u)", idx); break;
+    case 6: snprintf(buf, sizeof buf, "LSK_PV(%u)", idx); break;
+    default: snprintf(buf, sizeof buf, "LSK_SEL(%u)", idx); break;
+  }
+  o += buf;
+}
+
+std::string program_source(const ChipH& c) {
+  const size_t ninstr = c.code.size() / 4;
+  std::string body, calls;
+  body.reserve(ninstr * 48);
+  uint32_t ci = 0;
+  char buf[64];
+  static const char* const SIG =
+      "(uint32_t* __restrict__ R, Ext& acc, const QuotientArgs& a, const QuotientRow& q)";
+  const uint32_t CHUNK = chunk_size();
+  bool asserts_in_chunk = false;
+  // a chunk folds its constraints into four 64-bit sums (kept below P * 2^32, one Montgomery reduction per
+  // coefficient when the chunk ends) instead of an extension-field multiply-add per constraint
+  auto close_chunk = [&] {
+    if (asserts_in_chunk) body += "  LSK_ASSERT_END;\n";
+    body += "}\n";
+    asserts_in_chunk = false;
+  };
+  for (size_t i = 0; i < ninstr; i++) {
+    if (i % CHUNK == 0) {
+      if (i) close_chunk();
+      snprintf(buf, sizeof buf, "__device__ __noinline__ void lsk_chunk_%zu", i / CHUNK);
+      body += buf;
+      body += SIG;
+      body += " {\n";
+      snprintf(buf, sizeof buf, "  lsk_chunk_%zu(R, acc, a, q);\n", i / CHUNK);
+      calls += buf;
+    }
+    const uint32_t op = c.code[4 * i], dst = c.code[4 * i + 1], x = c.code[4 * i + 2], y = c.code[4 * i + 3];
+    body += "  ";
+    if (op == COP_ASSERT) {
+      if (!asserts_in_chunk) body += "LSK_ASSERT_BEGIN;\n  ";
+      asserts_in_chunk = true;
+      snprintf(buf, sizeof buf, "LSK_ASSERT(%u, ", ci++);
+      body += buf;
+      operand(body, x, c);
+      body += ");\n";
+      continue;
+    }
+    snprintf(buf, sizeof buf, "R[%u] = ", dst);
+    body += buf;
+    body += op == COP_ADD ? "fadd(" : op == COP_SUB ? "fsub(" : op == COP_MUL ? "fmul(" : "fneg(";
+    operand(body, x, c);
+    if (op != COP_NEG) {
+      body += ", ";
+      operand(body, y, c);
+    }
+    body += ");\n";
+  }
+  if (ninstr) close_chunk();
+  body += "__device__ __forceinline__ void lsk_program";
+  body += SIG;
+  body += " {\n" + calls + "}\n";
+  return body;
+}
+
+// the translation unit NVRTC compiles: three defines and the kernel header, which includes "lsk_program.cuh"
+std::string main_source(const ChipH& c) {
+  uint32_t asserts = 0;
+  for (size_t i = 0; i < c.code.size(); i += 4) asserts += c.code[i] == COP_ASSERT;
+  char buf[200];
+  snprintf(buf, sizeof buf,
+           "#define LSK_JIT_PROGRAM 1\n#define LSK_JIT_REGS %u\n#define LSK_JIT_ASSERTS %u\n#include \"quotient_kernel.cuh\"\n",
+           c.n_regs ? c.n_regs : 1u, asserts);
+  return buf;
+}
+
+uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
+  for (unsigned char ch : s) h = (h ^ ch) * 1099511628211ull;
+  return h;
+}
+
+std::string cache_dir() {
+  if (const char* e = getenv("LSK_JIT_CACHE")) return e;
+  Dl_info info;
+  if (dladdr((void*)&cache_dir, &info) && info.dli_fname) {
+    std::string p = info.dli_fname;
+    size_t k = p.rfind('/');
+    return (k == std::string::npos ? std::string(".") : p.substr(0, k)) + "/jit_cache";
+  }
+  return "./jit_cache";
+}
+
+bool read_file(const std::string& path, std::vector<char>& out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  out.resize(n > 0 ? (size_t)n : 0);
+  bool ok = n > 0 && fread(out.data(), 1, (size_t)n, f) == (size_t)n;
+  fclose(f);
+  return ok;
+}
+void write_file(const std::string& dir, const std::string& path, const std::vector<char>& data) {
+  mkdir(dir.c_str(), 0755);
+  std::string tmp = path + ".tmp" + std::to_string((long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  bool ok = fwrite(data.data(), 1, data.size(), f) == data.size();
+  fclose(f);
+  if (ok) rename(tmp.c_str(), path.c_str());
+  else remove(tmp.c_str());
+}
+
+}  // namespace
+
+bool jit_eligible(const ChipH& c) { return c.code.size() / 4 >= JIT_MIN_INSTR; }
+
+bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, std::string* how) {
+  const std::string program_hdr = program_source(c), main_src = main_source(c);
+  uint64_t key = fnv1a(program_hdr);
+  key = fnv1a(main_src, key);
+  key = fnv1a(FIELD_CUH_SRC, key);
+  key = fnv1a(QUOTIENT_KERNEL_CUH_SRC, key);
+  char name[64];
+  snprintf(name, sizeof name, "/q_%016llx_sm100a.cubin", (unsigned long long)key);
+  const std::string dir = cache_dir(), path = dir + name;
+  if (read_file(path, cubin)) {
+    if (how) *how = "cache";
+    return true;
+  }
+  if (!compile_on_miss) return false;
+  if (!nvrtc().ok) fail(LSK_ERR_CUDA, "NVRTC (libnvrtc.so.12) could not be loaded");
+  void* prog = nullptr;
+  const char* hdr_src[3] = {FIELD_CUH_SRC, QUOTIENT_KERNEL_CUH_SRC, program_hdr.c_str()};
+  const char* hdr_name[3] = {"field.cuh", "quotient_kernel.cuh", "lsk_program.cuh"};
+  if (nvrtc().CreateProgram(&prog, main_src.c_str(), "lsk_quotient_jit.cu", 3, hdr_src, hdr_name) != 0)
+    fail(LSK_ERR_CUDA, "nvrtcCreateProgram failed");
+  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17"};
+  int rc = nvrtc().CompileProgram(prog, 2, opts);
+  if (rc != 0) {
+    size_t n = 0;
+    nvrtc().GetProgramLogSize(prog, &n);
+    std::string log(n, '\0');
+    if (n) nvrtc().GetProgramLog(prog, &log[0]);
+    nvrtc().DestroyProgram(&prog);
+    fail(LSK_ERR_CUDA, "NVRTC failed on the constraint program of %s: %.400s", c.name.c_str(), log.c_str());
+  }
+  size_t n = 0;
+  nvrtc().GetCUBINSize(prog, &n);
+  cubin.resize(n);
+  nvrtc().GetCUBIN(prog, cubin.data());
+  nvrtc().DestroyProgram(&prog);
+  write_file(dir, path, cubin);
+  if (how) *how = "compiled";
+  return true;
+}
+
+JitKernel* jit_quotient(const ChipH& c) {
+  const char* env = getenv("LSK_JIT");
+  if (env && env[0] == '0') return nullptr;
+  if (!jit_eligible(c)) return nullptr;
+  std::vector<char> cubin;
+  if (!jit_cubin(c, env && env[0] == '1', cubin, nullptr)) return nullptr;
+  if (!driver().ok) fail(LSK_ERR_CUDA, "libcuda.so.1 could not be loaded for a compiled constraint program");
+  auto k = new JitKernel;
+  int rc = driver().ModuleLoadData(&k->module, cubin.data());
+  if (rc == 0) rc = driver().ModuleGetFunction(&k->function, k->module, "lsk_quotient_jit");
+  if (rc != 0) {
+    delete k;
+    fail(LSK_ERR_CUDA, "loading the compiled constraint program of %s failed (CUresult %d)", c.name.c_str(), rc);
+  }
+  return k;
+}
+
+void jit_free(JitKernel* k) {
+  if (!k) return;
+  if (k->module && g_drv.ok) g_drv.ModuleUnload(k->module);
+  delete k;
+}
+
+void jit_launch(lsk_ctx* ctx, const JitKernel* k, const QuotientArgs& a, const QuotientConsts& qc, const uint32_t* inter,
+                uint32_t nint, uint32_t pw) {
+  const size_t nrows = a.row_end - a.row_begin;
+  void* params[] = {(void*)&a, (void*)&qc, (void*)&inter, (void*)&nint, (void*)&pw};
+  int rc = driver().LaunchKernel(k->function, div_up(nrows, 256), 1, 1, 256, 1, 1, 0, ctx->stream, params, nullptr);
+  if (rc != 0) fail(LSK_ERR_CUDA, "cuLaunchKernel of a compiled constraint program failed (CUresult %d)", rc);
+}
+
+}  // namespace lsk

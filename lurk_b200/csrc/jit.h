@@ -1,0 +1,30 @@
+// Run-time compiled constraint programs (jit.cu; kernel in quotient_kernel.cuh).
+#pragma once
+#include <string>
+#include <vector>
+
+#include "machine.h"
+#include "quotient_kernel.cuh"
+
+struct lsk_ctx;
+
+namespace lsk {
+
+constexpr size_t JIT_MIN_INSTR = 1024;   // shorter programs are interpreted (the fixed per-row work dominates them)
+
+struct JitKernel {
+  void* module = nullptr;    // CUmodule
+  void* function = nullptr;  // CUfunction of lsk_quotient_jit
+};
+
+bool jit_eligible(const ChipH& c);
+// cubin of the chip's compiled quotient kernel: from the disk cache, else (compile_on_miss) from NVRTC, which
+// also stores it.  No GPU needed.  false: not cached and not compiled.
+bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, std::string* how);
+// nullptr when the policy (env LSK_JIT, cache contents) says "interpret"
+JitKernel* jit_quotient(const ChipH& c);
+void jit_free(JitKernel* k);
+void jit_launch(lsk_ctx* ctx, const JitKernel* k, const QuotientArgs& a, const QuotientConsts& qc, const uint32_t* inter,
+                uint32_t nint, uint32_t pw);
+
+}  // namespace lsk

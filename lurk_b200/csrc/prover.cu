@@ -17,6 +17,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <thread>
 
 #include "challenger.h"
 #include "comm.cuh"
@@ -168,6 +169,8 @@ static void compile_chip(lsk_ctx* ctx, const ChipH& c, uint32_t num_pv, ChipDev&
   d.code.alloc(ctx, code.size()); d.code.upload(code.data(), code.size());
   d.consts.alloc(ctx, consts.size()); d.consts.upload(consts.data(), consts.size());
   d.inter.alloc(ctx, inter.size()); d.inter.upload(inter.data(), inter.size());
+  // long programs (the hasher chips): machine code from NVRTC when the policy / cubin cache provides it (jit.cu)
+  d.jit.reset(jit_quotient(c), jit_free);
 }
 
 static void machine_setup(lsk_machine& m) {
@@ -770,6 +773,45 @@ int lsk_machine_prep_commit(const lsk_machine* m, uint32_t out8[8]) {
   LSK_API_BEGIN
   if (!m || !out8) fail(LSK_ERR_ARG, "null argument");
   memcpy(out8, m->prep_commit, 32);
+  return LSK_OK;
+  LSK_API_END
+}
+
+int lsk_machine_jit_chips(const lsk_machine* m) {
+  if (!m) return 0;
+  int n = 0;
+  for (auto& d : m->dchips) n += d.jit != nullptr;
+  return n;
+}
+
+int lsk_jit_precompile(const uint32_t* blob, size_t n, uint32_t* compiled, uint32_t* cached) {
+  LSK_API_BEGIN
+  if (!blob) fail(LSK_ERR_ARG, "null blob");
+  uint32_t num_pv = 0;
+  const std::vector<ChipH> chips = parse_machine_blob(blob, n, &num_pv);
+  std::vector<const ChipH*> todo;
+  for (const ChipH& c : chips)
+    if (jit_eligible(c)) todo.push_back(&c);
+  // one NVRTC compilation per chip, side by side (each takes tens of seconds)
+  std::vector<std::string> how(todo.size()), err(todo.size());
+  std::vector<std::thread> workers;
+  for (size_t i = 0; i < todo.size(); i++)
+    workers.emplace_back([&, i] {
+      try {
+        std::vector<char> cubin;
+        jit_cubin(*todo[i], true, cubin, &how[i]);
+      } catch (const std::exception& e) {
+        err[i] = e.what();
+      }
+    });
+  for (auto& w : workers) w.join();
+  uint32_t nc = 0, nh = 0;
+  for (size_t i = 0; i < todo.size(); i++) {
+    if (!err[i].empty()) fail(LSK_ERR_CUDA, "%s", err[i].c_str());
+    (how[i] == "cache" ? nh : nc)++;
+  }
+  if (compiled) *compiled = nc;
+  if (cached) *cached = nh;
   return LSK_OK;
   LSK_API_END
 }

@@ -1,0 +1,251 @@
+// Quotient evaluation (A6 + A10): the kernel that evaluates a chip's constraints on the LDE rows.
+//
+// This header is compiled twice: by nvcc into liblurkstark.so (the INTERPRETER: quotient_kernel<MAXREGS, ROWS>
+// walks the chip's constraint program instruction by instruction) and, at run time, by NVRTC for the chips whose
+// programs are long enough to pay for it (jit.cu: the program is emitted as straight-line CUDA -- 128-statement
+// __noinline__ chunks over a register file in local memory, constants and alpha-power indices as literals -- and
+// included as "lsk_program.cuh"; measured on the 655-wide hash4 chip, 2^21 rows: 24.1 ms interpreted,
+// 10.7 ms compiled).  Row set-up (selectors, vanishing polynomial) and the LogUp constraints + division are
+// shared.  Only "field.cuh" may be included here: NVRTC has no system headers.
+#pragma once
+#include "field.cuh"
+
+namespace lsk {
+
+// device opcodes of the constraint program: 0..26 = 9 * {add, sub, mul} + 3 * kind(a) + kind(b) with raw
+// indices (kind 0 register, 1 main-trace cell of the row, 2 constant); the rest keep tagged operands
+enum : uint32_t { QOP_NEG = 27, QOP_ASSERT_REG = 28, QOP_ASSERT = 29, QOP_ADD = 30, QOP_SUB = 31, QOP_MUL = 32 };
+
+struct QuotientArgs {
+  const uint32_t* main; size_t mstride;   // LDEs, 2N rows
+  const uint32_t* prep; size_t pstride;
+  const uint32_t* perm; size_t permstride;
+  const uint32_t* pv;       // public values, Montgomery, device
+  const Ext* apow;          // apow[k] = alpha^k; constraint i (AIR first, then LogUp) is weighted alpha^(n_total-1-i)
+  uint32_t n_total;
+  const Ext* beta_pows;     // beta^(v+1)
+  const Ext* cum_sum;
+  Ext chal_alpha;
+  unsigned logn;
+  uint32_t* out; size_t ostride;  // 4 columns of 2N rows
+  size_t row_begin, row_end;      // set by quotient_dev: the LDE rows this launch evaluates
+};
+struct QuotientConsts {
+  uint32_t g, w2n, wn_inv, zh[2], inv_zh[2];
+};
+
+// ---- device helpers shared with the LogUp trace kernel ---------------------------------------------------------
+struct Cells {  // local-row view of a chip's main + preprocessed matrices
+  const uint32_t* main; size_t mstride;
+  const uint32_t* prep; size_t pstride;
+  size_t r;
+  LSK_D uint32_t get(uint32_t is_prep, uint32_t col) const {
+    return is_prep ? prep[(size_t)col * pstride + r] : main[(size_t)col * mstride + r];
+  }
+};
+LSK_D uint32_t eval_affine(const uint32_t* __restrict__& s, const Cells& c) {
+  uint32_t n = s[0], acc = s[1];
+  s += 2;
+  for (uint32_t i = 0; i < n; i++, s += 3) acc = fadd(acc, fmul(c.get(s[0], s[1]), s[2]));
+  return acc;
+}
+// one interaction: rlc = alpha + kind + sum_v beta^(v+1) value_v ; m = +-multiplicity
+LSK_D void eval_interaction(const uint32_t* __restrict__& s, const Cells& c, const Ext& alpha,
+                            const Ext* __restrict__ beta_pows, Ext& rlc, uint32_t& m) {
+  uint32_t kind = s[0], sign = s[1], nv = s[2];
+  s += 3;
+  m = eval_affine(s, c);
+  if (sign) m = fneg(m);
+  rlc = eadd_base(alpha, kind);
+  for (uint32_t v = 0; v < nv; v++) {
+    uint32_t val = eval_affine(s, c);
+    rlc = eadd(rlc, emul_base(beta_pows[v], val));
+  }
+}
+LSK_D Ext load_ext_cols(const uint32_t* __restrict__ m, size_t stride, uint32_t first_col, size_t r) {
+  Ext e;
+#pragma unroll
+  for (int k = 0; k < 4; k++) e.c[k] = m[(size_t)(first_col + k) * stride + r];
+  return e;
+}
+
+
+// ---- one LDE row: position, selectors ---------------------------------------------------------------------------
+struct QuotientRow {
+  size_t r, rn;        // storage position (bit-reversed) of the row and of the next row of the trace domain
+  uint32_t ii;         // natural index on the quotient domain
+  uint32_t sel[3];     // is_first, is_last, is_transition
+};
+LSK_D void quotient_row_setup(const QuotientArgs& a, const QuotientConsts& qc, size_t row, QuotientRow& q) {
+  const unsigned l2 = a.logn + 1;
+  const size_t n2 = (size_t)1 << l2;
+  q.r = row;
+  q.ii = bitrev32((uint32_t)row, l2);
+  q.rn = bitrev32((uint32_t)((q.ii + 2) & (n2 - 1)), l2);
+  uint32_t x = fmul(qc.g, fpow(qc.w2n, q.ii));
+  uint32_t zh = qc.zh[q.ii & 1];
+  uint32_t xm1 = fsub(x, R1), xml = fsub(x, qc.wn_inv);
+  uint32_t inv = finv(fmul(xm1, xml));
+  q.sel[0] = fmul(zh, fmul(inv, xml));  // is_first
+  q.sel[1] = fmul(zh, fmul(inv, xm1));  // is_last
+  q.sel[2] = xml;                       // is_transition
+}
+// LogUp constraints (sphinx eval_permutation_constraints) on top of the folded AIR constraints `ac` (the first
+// `ci` alpha powers are spent), division by the vanishing polynomial, store
+LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, const QuotientRow& q, Ext ac, uint32_t ci,
+                               const uint32_t* __restrict__ inter, uint32_t nint, uint32_t pw, bool live) {
+  Cells cells{a.main, a.mstride, a.prep, a.pstride, q.r};
+  const uint32_t* s = inter;
+  uint32_t cj = ci;
+  Ext sum_local = ext_zero(), sum_next = ext_zero();
+  for (uint32_t b = 0; 2 * b < nint; b++) {
+    Ext r0, lhs, rhs;
+    uint32_t m0;
+    eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r0, m0);
+    Ext pl = load_ext_cols(a.perm, a.permstride, 4 * b, q.r);
+    if (2 * b + 1 < nint) {
+      Ext r1;
+      uint32_t m1;
+      eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r1, m1);
+      lhs = emul(emul(pl, r0), r1);
+      rhs = eadd(emul_base(r1, m0), emul_base(r0, m1));
+    } else {
+      lhs = emul(pl, r0);
+      rhs = ext_from_base(m0);
+    }
+    ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], esub(lhs, rhs)));
+    sum_local = eadd(sum_local, pl);
+    sum_next = eadd(sum_next, load_ext_cols(a.perm, a.permstride, 4 * b, q.rn));
+  }
+  Ext phi_local = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), q.r);
+  Ext phi_next = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), q.rn);
+  ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(esub(phi_next, phi_local), sum_next), q.sel[2])));
+  ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(phi_local, sum_local), q.sel[0])));
+  ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(phi_local, *a.cum_sum), q.sel[1])));
+  Ext quot = emul_base(ac, qc.inv_zh[q.ii & 1]);
+  if (live) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) a.out[(size_t)e * a.ostride + q.r] = quot.c[e];
+  }
+}
+
+#if defined(LSK_JIT_PROGRAM)
+// ---- compiled form: jit.cu defines LSK_JIT_REGS and LSK_JIT_ASSERTS and supplies "lsk_program.cuh" with the
+// chunk functions lsk_chunk_<k>(R, acc, a, q) plus lsk_program(R, acc, a, q) that calls them in order
+#define LSK_ML(i) a.main[(size_t)(i) * a.mstride + q.r]
+#define LSK_MN(i) a.main[(size_t)(i) * a.mstride + q.rn]
+#define LSK_PL(i) a.prep[(size_t)(i) * a.pstride + q.r]
+#define LSK_PN(i) a.prep[(size_t)(i) * a.pstride + q.rn]
+#define LSK_PV(i) a.pv[i]
+#define LSK_SEL(i) q.sel[i]
+// constraints of one chunk: sum_i alpha^(n_total-1-ci) * v_i as four 64-bit sums of raw products, each kept below
+// P * 2^32 (what mont_reduce accepts) by one conditional subtraction per term; reduced once when the chunk ends
+#define LSK_ASSERT_BEGIN uint64_t lsk_s0 = 0, lsk_s1 = 0, lsk_s2 = 0, lsk_s3 = 0
+#define LSK_ASSERT(ci, v)                                               \
+  {                                                                     \
+    const Ext lsk_ap = a.apow[a.n_total - 1 - (ci)];                    \
+    const uint32_t lsk_x = (v);                                         \
+    lsk_s0 = acc_reduce64(lsk_s0 + (uint64_t)lsk_ap.c[0] * lsk_x);      \
+    lsk_s1 = acc_reduce64(lsk_s1 + (uint64_t)lsk_ap.c[1] * lsk_x);      \
+    lsk_s2 = acc_reduce64(lsk_s2 + (uint64_t)lsk_ap.c[2] * lsk_x);      \
+    lsk_s3 = acc_reduce64(lsk_s3 + (uint64_t)lsk_ap.c[3] * lsk_x);      \
+  }
+#define LSK_ASSERT_END \
+  acc = eadd(acc, Ext{{mont_reduce(lsk_s0), mont_reduce(lsk_s1), mont_reduce(lsk_s2), mont_reduce(lsk_s3)}})
+#include "lsk_program.cuh"
+extern "C" __global__ void __launch_bounds__(256) lsk_quotient_jit(QuotientArgs a, QuotientConsts qc,
+                                                                   const uint32_t* __restrict__ inter, uint32_t nint,
+                                                                   uint32_t pw) {
+  const size_t row = a.row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (row >= a.row_end) return;
+  QuotientRow q;
+  quotient_row_setup(a, qc, row, q);
+  uint32_t R[LSK_JIT_REGS];
+  R[0] = 0;
+  Ext acc = ext_zero();
+  lsk_program(R, acc, a, q);
+  quotient_row_finish(a, qc, q, acc, LSK_JIT_ASSERTS, inter, nint, pw, true);
+}
+#else
+// ---- interpreted form.  ROWS rows per thread (rows t, t + 256, ... of the CTA's slab, so every access stays
+// coalesced): the long constraint programs of the hasher chips are bound by instruction fetch / decode and by the
+// latency of the register file in local memory, both of which a second independent row amortises.
+template <int MAXREGS, int ROWS>
+__global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientConsts qc,
+                                                        const uint4* __restrict__ code, uint32_t ninstr,
+                                                        const uint32_t* __restrict__ consts,
+                                                        const uint32_t* __restrict__ inter, uint32_t nint, uint32_t pw) {
+  const size_t base = a.row_begin + (size_t)blockIdx.x * (256 * ROWS) + threadIdx.x;
+  if (base >= a.row_end) return;
+  QuotientRow q[ROWS];
+  bool live[ROWS];
+  uint32_t regs[ROWS][MAXREGS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) {
+    size_t row = base + (size_t)k * 256;
+    live[k] = row < a.row_end;
+    if (!live[k]) row = base;  // recompute a valid row, never stored
+    quotient_row_setup(a, qc, row, q[k]);
+    regs[k][0] = 0;
+  }
+  auto operand = [&](int k, uint32_t w) -> uint32_t {
+    uint32_t idx = w & 0x0fffffffu;
+    switch (w >> 28) {
+      case 0: return regs[k][idx];
+      case 1: return consts[idx];
+      case 2: return a.main[(size_t)idx * a.mstride + q[k].r];
+      case 3: return a.main[(size_t)idx * a.mstride + q[k].rn];
+      case 4: return a.prep[(size_t)idx * a.pstride + q[k].r];
+      case 5: return a.prep[(size_t)idx * a.pstride + q[k].rn];
+      case 6: return a.pv[idx];
+      default: return q[k].sel[idx];
+    }
+  };
+  Ext acc[ROWS];
+#pragma unroll
+  for (int k = 0; k < ROWS; k++) acc[k] = ext_zero();
+  uint32_t ci = 0;
+  // Device form of the constraint program (prover.cu::compile_chip): the operand kinds of the common
+  // instructions are folded into the opcode -- op = 9 * {add, sub, mul} + 3 * kind(a) + kind(b) with kind
+  // 0 register, 1 main-trace cell of this row, 2 constant -- so that one indexed branch replaces the
+  // opcode switch plus two operand-tag switches; everything else takes the generic tagged path.
+  auto R = [&](int k, uint32_t i) { return regs[k][i]; };
+  auto M = [&](int k, uint32_t i) { return a.main[(size_t)i * a.mstride + q[k].r]; };
+  auto C = [&](int, uint32_t i) { return __ldg(consts + i); };
+#define LSK_QROWS(EXPR)              \
+  _Pragma("unroll") for (int k = 0; k < ROWS; k++) { EXPR; } \
+  break;
+#define LSK_Q3(BASE, FN, KA, LA)                                                              \
+  case BASE + 3 * KA + 0: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), R(k, ins.w)))           \
+  case BASE + 3 * KA + 1: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), M(k, ins.w)))           \
+  case BASE + 3 * KA + 2: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), C(k, ins.w)))
+#define LSK_Q9(BASE, FN) LSK_Q3(BASE, FN, 0, R) LSK_Q3(BASE, FN, 1, M) LSK_Q3(BASE, FN, 2, C)
+  for (uint32_t pc = 0; pc < ninstr; pc++) {
+    const uint4 ins = __ldg(code + pc);
+    switch (ins.x) {
+      LSK_Q9(0, fadd)
+      LSK_Q9(9, fsub)
+      LSK_Q9(18, fmul)
+      case QOP_NEG: LSK_QROWS(regs[k][ins.y] = fneg(operand(k, ins.z)))
+      case QOP_ASSERT_REG: {
+        const Ext ap = a.apow[a.n_total - 1 - (ci++)];
+        LSK_QROWS(acc[k] = eadd(acc[k], emul_base(ap, regs[k][ins.z])))
+      }
+      case QOP_ASSERT: {
+        const Ext ap = a.apow[a.n_total - 1 - (ci++)];
+        LSK_QROWS(acc[k] = eadd(acc[k], emul_base(ap, operand(k, ins.z))))
+      }
+      case QOP_ADD: LSK_QROWS(regs[k][ins.y] = fadd(operand(k, ins.z), operand(k, ins.w)))
+      case QOP_SUB: LSK_QROWS(regs[k][ins.y] = fsub(operand(k, ins.z), operand(k, ins.w)))
+      default: LSK_QROWS(regs[k][ins.y] = fmul(operand(k, ins.z), operand(k, ins.w)))
+    }
+  }
+#undef LSK_Q9
+#undef LSK_Q3
+#undef LSK_QROWS
+#pragma unroll 1
+  for (int k = 0; k < ROWS; k++) quotient_row_finish(a, qc, q[k], acc[k], ci, inter, nint, pw, live[k]);
+}
+#endif  // LSK_JIT_PROGRAM
+
+}  // namespace lsk

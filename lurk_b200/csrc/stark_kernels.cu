@@ -10,45 +10,11 @@
 #include "fri.cuh"
 #include "poseidon2.cuh"
 #include "stark_kernels.cuh"
+#include "quotient_kernel.cuh"
 
 #include "comm.cuh"
 
 namespace lsk {
-
-// ---- shared device helpers ---------------------------------------------------------------------------
-struct Cells {  // local-row view of a chip's main + preprocessed matrices
-  const uint32_t* main; size_t mstride;
-  const uint32_t* prep; size_t pstride;
-  size_t r;
-  LSK_D uint32_t get(uint32_t is_prep, uint32_t col) const {
-    return is_prep ? prep[(size_t)col * pstride + r] : main[(size_t)col * mstride + r];
-  }
-};
-LSK_D uint32_t eval_affine(const uint32_t* __restrict__& s, const Cells& c) {
-  uint32_t n = s[0], acc = s[1];
-  s += 2;
-  for (uint32_t i = 0; i < n; i++, s += 3) acc = fadd(acc, fmul(c.get(s[0], s[1]), s[2]));
-  return acc;
-}
-// one interaction: rlc = alpha + kind + sum_v beta^(v+1) value_v ; m = +-multiplicity
-LSK_D void eval_interaction(const uint32_t* __restrict__& s, const Cells& c, const Ext& alpha,
-                            const Ext* __restrict__ beta_pows, Ext& rlc, uint32_t& m) {
-  uint32_t kind = s[0], sign = s[1], nv = s[2];
-  s += 3;
-  m = eval_affine(s, c);
-  if (sign) m = fneg(m);
-  rlc = eadd_base(alpha, kind);
-  for (uint32_t v = 0; v < nv; v++) {
-    uint32_t val = eval_affine(s, c);
-    rlc = eadd(rlc, emul_base(beta_pows[v], val));
-  }
-}
-LSK_D Ext load_ext_cols(const uint32_t* __restrict__ m, size_t stride, uint32_t first_col, size_t r) {
-  Ext e;
-#pragma unroll
-  for (int k = 0; k < 4; k++) e.c[k] = m[(size_t)(first_col + k) * stride + r];
-  return e;
-}
 
 // ---- LogUp permutation trace --------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) perm_rows_kernel(const uint32_t* __restrict__ inter, uint32_t nint,
@@ -158,136 +124,6 @@ void perm_trace_dev(lsk_ctx* ctx, const ChipDev& chip, const uint32_t* main, siz
 }
 
 // ---- quotient -----------------------------------------------------------------------------------------
-struct QuotientConsts {
-  uint32_t g, w2n, wn_inv, zh[2], inv_zh[2];
-};
-// ROWS rows per thread (rows t, t + 256, ... of the CTA's slab, so every access stays coalesced): the long
-// constraint programs of the hasher chips are bound by instruction fetch / decode and by the latency of the
-// register file in local memory, both of which a second independent row amortises.
-template <int MAXREGS, int ROWS>
-__global__ void __launch_bounds__(256) quotient_kernel(QuotientArgs a, QuotientConsts qc,
-                                                        const uint4* __restrict__ code, uint32_t ninstr,
-                                                        const uint32_t* __restrict__ consts,
-                                                        const uint32_t* __restrict__ inter, uint32_t nint, uint32_t pw) {
-  const unsigned l2 = a.logn + 1;
-  const size_t n2 = (size_t)1 << l2;
-  const size_t base = a.row_begin + (size_t)blockIdx.x * (256 * ROWS) + threadIdx.x;
-  if (base >= a.row_end) return;
-  size_t r[ROWS], rn[ROWS];
-  uint32_t ii[ROWS], sel[ROWS][3];
-  bool live[ROWS];
-  uint32_t regs[ROWS][MAXREGS];
-#pragma unroll
-  for (int k = 0; k < ROWS; k++) {
-    r[k] = base + (size_t)k * 256;
-    live[k] = r[k] < a.row_end;
-    if (!live[k]) r[k] = base;  // recompute a valid row, never stored
-    ii[k] = bitrev32((uint32_t)r[k], l2);
-    rn[k] = bitrev32((uint32_t)((ii[k] + 2) & (n2 - 1)), l2);
-    uint32_t x = fmul(qc.g, fpow(qc.w2n, ii[k]));
-    uint32_t zh = qc.zh[ii[k] & 1];
-    uint32_t xm1 = fsub(x, R1), xml = fsub(x, qc.wn_inv);
-    uint32_t inv = finv(fmul(xm1, xml));
-    sel[k][0] = fmul(zh, fmul(inv, xml));  // is_first
-    sel[k][1] = fmul(zh, fmul(inv, xm1));  // is_last
-    sel[k][2] = xml;                       // is_transition
-    regs[k][0] = 0;
-  }
-  auto operand = [&](int k, uint32_t w) -> uint32_t {
-    uint32_t idx = w & 0x0fffffffu;
-    switch (w >> 28) {
-      case 0: return regs[k][idx];
-      case 1: return consts[idx];
-      case 2: return a.main[(size_t)idx * a.mstride + r[k]];
-      case 3: return a.main[(size_t)idx * a.mstride + rn[k]];
-      case 4: return a.prep[(size_t)idx * a.pstride + r[k]];
-      case 5: return a.prep[(size_t)idx * a.pstride + rn[k]];
-      case 6: return a.pv[idx];
-      default: return sel[k][idx];
-    }
-  };
-  Ext acc[ROWS];
-#pragma unroll
-  for (int k = 0; k < ROWS; k++) acc[k] = ext_zero();
-  uint32_t ci = 0;
-  // Device form of the constraint program (prover.cu::compile_chip): the operand kinds of the common
-  // instructions are folded into the opcode -- op = 9 * {add, sub, mul} + 3 * kind(a) + kind(b) with kind
-  // 0 register, 1 main-trace cell of this row, 2 constant -- so that one indexed branch replaces the
-  // opcode switch plus two operand-tag switches; everything else takes the generic tagged path.
-  auto R = [&](int k, uint32_t i) { return regs[k][i]; };
-  auto M = [&](int k, uint32_t i) { return a.main[(size_t)i * a.mstride + r[k]]; };
-  auto C = [&](int, uint32_t i) { return __ldg(consts + i); };
-#define LSK_QROWS(EXPR)              \
-  _Pragma("unroll") for (int k = 0; k < ROWS; k++) { EXPR; } \
-  break;
-#define LSK_Q3(BASE, FN, KA, LA)                                                              \
-  case BASE + 3 * KA + 0: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), R(k, ins.w)))           \
-  case BASE + 3 * KA + 1: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), M(k, ins.w)))           \
-  case BASE + 3 * KA + 2: LSK_QROWS(regs[k][ins.y] = FN(LA(k, ins.z), C(k, ins.w)))
-#define LSK_Q9(BASE, FN) LSK_Q3(BASE, FN, 0, R) LSK_Q3(BASE, FN, 1, M) LSK_Q3(BASE, FN, 2, C)
-  for (uint32_t pc = 0; pc < ninstr; pc++) {
-    const uint4 ins = __ldg(code + pc);
-    switch (ins.x) {
-      LSK_Q9(0, fadd)
-      LSK_Q9(9, fsub)
-      LSK_Q9(18, fmul)
-      case QOP_NEG: LSK_QROWS(regs[k][ins.y] = fneg(operand(k, ins.z)))
-      case QOP_ASSERT_REG: {
-        const Ext ap = a.apow[a.n_total - 1 - (ci++)];
-        LSK_QROWS(acc[k] = eadd(acc[k], emul_base(ap, regs[k][ins.z])))
-      }
-      case QOP_ASSERT: {
-        const Ext ap = a.apow[a.n_total - 1 - (ci++)];
-        LSK_QROWS(acc[k] = eadd(acc[k], emul_base(ap, operand(k, ins.z))))
-      }
-      case QOP_ADD: LSK_QROWS(regs[k][ins.y] = fadd(operand(k, ins.z), operand(k, ins.w)))
-      case QOP_SUB: LSK_QROWS(regs[k][ins.y] = fsub(operand(k, ins.z), operand(k, ins.w)))
-      default: LSK_QROWS(regs[k][ins.y] = fmul(operand(k, ins.z), operand(k, ins.w)))
-    }
-  }
-#undef LSK_Q9
-#undef LSK_Q3
-#undef LSK_QROWS
-  // LogUp constraints (sphinx eval_permutation_constraints), row by row
-#pragma unroll 1
-  for (int k = 0; k < ROWS; k++) {
-    Cells cells{a.main, a.mstride, a.prep, a.pstride, r[k]};
-    const uint32_t* s = inter;
-    uint32_t cj = ci;
-    Ext ac = acc[k];
-    Ext sum_local = ext_zero(), sum_next = ext_zero();
-    for (uint32_t b = 0; 2 * b < nint; b++) {
-      Ext r0, lhs, rhs;
-      uint32_t m0;
-      eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r0, m0);
-      Ext pl = load_ext_cols(a.perm, a.permstride, 4 * b, r[k]);
-      if (2 * b + 1 < nint) {
-        Ext r1;
-        uint32_t m1;
-        eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r1, m1);
-        lhs = emul(emul(pl, r0), r1);
-        rhs = eadd(emul_base(r1, m0), emul_base(r0, m1));
-      } else {
-        lhs = emul(pl, r0);
-        rhs = ext_from_base(m0);
-      }
-      ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], esub(lhs, rhs)));
-      sum_local = eadd(sum_local, pl);
-      sum_next = eadd(sum_next, load_ext_cols(a.perm, a.permstride, 4 * b, rn[k]));
-    }
-    Ext phi_local = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), r[k]);
-    Ext phi_next = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), rn[k]);
-    ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(esub(phi_next, phi_local), sum_next), sel[k][2])));
-    ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(phi_local, sum_local), sel[k][0])));
-    ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(phi_local, *a.cum_sum), sel[k][1])));
-    Ext q = emul_base(ac, qc.inv_zh[ii[k] & 1]);
-    if (live[k]) {
-#pragma unroll
-      for (int e = 0; e < 4; e++) a.out[(size_t)e * a.ostride + r[k]] = q.c[e];
-    }
-  }
-}
-
 void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& args) {
   QuotientArgs a = args;
   QuotientConsts qc;
@@ -306,7 +142,10 @@ void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& args) {
   if (split) comm_range(ctx, n2, &a.row_begin, &a.row_end);
   const size_t nrows = a.row_end - a.row_begin;
   const uint4* code = reinterpret_cast<const uint4*>(chip.code.p);
-  {
+  if (chip.jit) {   // the program compiled to machine code (one row per thread)
+    ProfScope ps(ctx, PT_QUOTIENT, 1, (double)nrows * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw + 16.0));
+    jit_launch(ctx, chip.jit.get(), a, qc, chip.inter.p, chip.nint, chip.pw);
+  } else {
   ProfScope ps(ctx, PT_QUOTIENT, 1, (double)nrows * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw + 16.0));
 #define QK(R, ROWS)                                                                                              \
   quotient_kernel<R, ROWS><<<div_up(nrows, 256 * ROWS), 256, 0, ctx->stream>>>(a, qc, code, chip.ninstr, chip.consts.p, \

@@ -4,21 +4,22 @@
 // (src/core/cli/repl.rs:196, benches/fib.rs:158); the oracle restates it in oracle/stark_prove.h.
 // All matrices are column-major, Montgomery form, rows in bit-reversed order.
 #pragma once
+#include <memory>
 #include <vector>
 
 #include "device.cuh"
 #include "field.cuh"
+#include "jit.h"
+#include "quotient_kernel.cuh"
 
 namespace lsk {
 
-// device opcodes of the constraint program: 0..26 = 9 * {add, sub, mul} + 3 * kind(a) + kind(b) with raw
-// indices (kind 0 register, 1 main-trace cell of the row, 2 constant); the rest keep tagged operands
-enum : uint32_t { QOP_NEG = 27, QOP_ASSERT_REG = 28, QOP_ASSERT = 29, QOP_ADD = 30, QOP_SUB = 31, QOP_MUL = 32 };
 struct ChipDev {  // a chip's compiled AIR, device resident (built once per machine)
   DevBuf<uint32_t> code;    // constraint program, 4 words per instruction (device opcodes, see above)
   DevBuf<uint32_t> consts;  // Montgomery
   DevBuf<uint32_t> inter;   // interaction stream: {kind_mont sign nvalues affine(mult) affine(value)*}*, sends first
   uint32_t ninstr = 0, nint = 0, n_regs = 0, width = 0, prep_width = 0, pw = 0, n_constraints = 0;
+  std::shared_ptr<JitKernel> jit;   // the constraint program compiled by NVRTC (jit.cu), or null: interpret `code`
 };
 
 void init_stark_kernels();
@@ -31,20 +32,6 @@ void perm_trace_dev(lsk_ctx* ctx, const ChipDev& chip, const uint32_t* main, siz
                     size_t perm_stride, Ext* scratch, Ext* cum_sum_out);
 
 // ---- quotient --------------------------------------------------------------------------------------
-struct QuotientArgs {
-  const uint32_t* main; size_t mstride;   // LDEs, 2N rows
-  const uint32_t* prep; size_t pstride;
-  const uint32_t* perm; size_t permstride;
-  const uint32_t* pv;       // public values, Montgomery, device
-  const Ext* apow;          // apow[k] = alpha^k; constraint i (AIR first, then LogUp) is weighted alpha^(n_total-1-i)
-  uint32_t n_total;
-  const Ext* beta_pows;     // beta^(v+1)
-  const Ext* cum_sum;
-  Ext chal_alpha;
-  unsigned logn;
-  uint32_t* out; size_t ostride;  // 4 columns of 2N rows
-  size_t row_begin, row_end;      // set by quotient_dev: the LDE rows this launch evaluates
-};
 void quotient_dev(lsk_ctx* ctx, const ChipDev& chip, const QuotientArgs& a);
 
 // ---- openings --------------------------------------------------------------------------------------

@@ -422,3 +422,26 @@ def test_column_sharded_prove_two_gpus():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert all(line["parity_vs_single_gpu_proof"].values())
+
+
+def test_compiled_constraint_programs_match_the_interpreter(monkeypatch):
+    # csrc/jit.cu: the hasher chips' constraint programs compiled by NVRTC (cubins cached in lurk_b200/jit_cache by
+    # `python -m lurk_b200.jit_warm`, part of build()).  The same record proved with the interpreter and with the
+    # compiled programs must give the same words; the verifier accepts them.
+    from lurk_b200.programs import hash_toplevel
+    top = hash_toplevel()
+    q = QueryRecord.new(top)
+    execute_by_name(top, "cons_chain", [3000], q)
+    monkeypatch.setenv("LSK_JIT", "0")
+    m0 = new_machine(top, "cons_chain")
+    assert N.lib().lsk_machine_jit_chips(m0.h) == 0
+    interpreted = m0.prove(m0.setup()[0], Shard.new(q))
+    monkeypatch.delenv("LSK_JIT")
+    m1 = new_machine(top, "cons_chain")
+    if N.lib().lsk_machine_jit_chips(m1.h) == 0:      # cold cache (no build() step ran): compile now
+        monkeypatch.setenv("LSK_JIT", "1")
+        m1 = new_machine(top, "cons_chain")
+    assert N.lib().lsk_machine_jit_chips(m1.h) == 3   # hash3, hash4, hash5
+    compiled = m1.prove(m1.setup()[0], Shard.new(q))
+    assert np.array_equal(interpreted.words, compiled.words)
+    m1.verify(m1.setup()[1], compiled)

@@ -185,3 +185,16 @@ def test_loaders_reject_malformed_images_without_crashing():
                     fn(w)                               # must return, whatever it answers
             for _ in range(30):
                 assert fn(rng.integers(0, 2 ** 32, size=int(rng.integers(1, 2000)), dtype=np.uint64).astype(np.uint32)) != 0
+
+
+def test_jit_precompile_fills_and_reuses_the_cubin_cache(tmp_path, monkeypatch):
+    # csrc/jit.cu: NVRTC needs no GPU.  A small program is below the threshold (nothing to do); the u64 chipset
+    # programs (2 chips above 1024 instructions) compile into an empty cache and are found there the second time.
+    from lurk_b200 import jit_warm
+    from lurk_b200.programs import u64_toplevel
+    monkeypatch.setenv("LSK_JIT_CACHE", str(tmp_path / "cache"))
+    assert jit_warm.precompile(demo_toplevel(), "fib") == {"compiled": 0, "cached": 0}
+    assert jit_warm.precompile(u64_toplevel(), "factu") == {"compiled": 2, "cached": 0}
+    assert jit_warm.precompile(u64_toplevel(), "factu") == {"compiled": 0, "cached": 2}
+    files = sorted(p.name for p in (tmp_path / "cache").iterdir())
+    assert len(files) == 2 and all(f.startswith("q_") and f.endswith("_sm100a.cubin") for f in files)

@@ -375,7 +375,8 @@ def run_ours(args):
                        if column else "one shard per GPU at a time (rank r proves shards r, r+G, ...)",
                        "rows_per_step": rows, "l2": "flushed between timed steps (256 MiB write)",
                        "executor_s": round(t_exec, 3), "output_word0": int(out[0]), "proof_words": int(len(proof)),
-                       "proof_verified_ms": verify_ms},
+                       "proof_verified_ms": verify_ms,
+                       "compiled_constraint_programs": int(N.lib().lsk_machine_jit_chips(m.h))},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(sum(v["launches"] for v in prof.values())),

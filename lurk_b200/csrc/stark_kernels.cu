@@ -303,9 +303,18 @@ __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* _
   bool any1 = false;
   for (uint32_t mi = 0; mi < nmats; mi++) {
     const ReduceMat& m = mats[mi];
-    Ext s = ext_zero();
+    uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;   // raw 64-bit products below P * 2^32, one reduction per matrix
     const uint32_t* p = m.p + r;
-    for (uint32_t c = 0; c < m.w; c++) s = eadd(s, emul_base(apow[c], p[(size_t)c * m.stride]));
+#pragma unroll 4
+    for (uint32_t c = 0; c < m.w; c++) {
+      const Ext ap = apow[c];
+      const uint32_t v = p[(size_t)c * m.stride];
+      s0 = acc_reduce64(s0 + (uint64_t)ap.c[0] * v);
+      s1 = acc_reduce64(s1 + (uint64_t)ap.c[1] * v);
+      s2 = acc_reduce64(s2 + (uint64_t)ap.c[2] * v);
+      s3 = acc_reduce64(s3 + (uint64_t)ap.c[3] * v);
+    }
+    const Ext s{{mont_reduce(s0), mont_reduce(s1), mont_reduce(s2), mont_reduce(s3)}};
     acc0 = eadd(acc0, emul(m.off[0], esub(m.y[0], s)));
     if (m.npoints > 1) {
       acc1 = eadd(acc1, emul(m.off[1], esub(m.y[1], s)));

@@ -125,9 +125,9 @@ int lsk_machine_new(lsk_ctx* ctx, const lsk_program* prog, uint32_t entry_func, 
                     uint32_t num_queries, uint32_t pow_bits, lsk_machine** out);
 void lsk_machine_free(lsk_machine* m);
 int lsk_machine_prep_commit(const lsk_machine* m, uint32_t out8[8]);
-/* Long constraint programs (>= 1024 instructions per row: the hasher chips behind `Air::eval` of
- * src/poseidon/wide/air.rs:11-124) can run as machine code: the program is emitted as CUDA source, compiled by NVRTC
- * for sm_100a (~30 s per chip) and kept in a cubin cache (env LSK_JIT_CACHE, default <library directory>/jit_cache).
+/* Constraint programs of >= 16 instructions per row (above all the hasher chips behind `Air::eval` of
+ * src/poseidon/wide/air.rs:11-124, 5-10 k instructions) can run as machine code: the program is emitted as CUDA source, compiled by NVRTC
+ * for sm_100a (1 s for a small chip, ~20 s for a hasher chip) and kept in a cubin cache (env LSK_JIT_CACHE, default <library directory>/jit_cache).
  * Env LSK_JIT: "0" always interpret, "1" compile on a cache miss, unset: use cached cubins only.  The interpreter
  * and the compiled form produce identical proofs.
  *   lsk_jit_precompile: fill the cache for every eligible chip of a 'MACH' blob; needs NVRTC, no GPU.

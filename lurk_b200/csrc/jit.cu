@@ -22,6 +22,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -218,7 +219,11 @@ void write_file(const std::string& dir, const std::string& path, const std::vect
 
 }  // namespace
 
-bool jit_eligible(const ChipH& c) { return c.code.size() / 4 >= JIT_MIN_INSTR; }
+bool jit_eligible(const ChipH& c) {
+  size_t min_instr = JIT_MIN_INSTR;
+  if (const char* e = getenv("LSK_JIT_MIN_INSTR")) min_instr = (size_t)std::max(1L, atol(e));
+  return c.code.size() / 4 >= min_instr;
+}
 
 bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, std::string* how) {
   const std::string program_hdr = program_source(c), main_src = main_source(c);

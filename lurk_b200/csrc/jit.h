@@ -10,7 +10,7 @@ struct lsk_ctx;
 
 namespace lsk {
 
-constexpr size_t JIT_MIN_INSTR = 1024;   // shorter programs are interpreted (the fixed per-row work dominates them)
+constexpr size_t JIT_MIN_INSTR = 16;   // shorter programs are interpreted (the fixed per-row work dominates them); env LSK_JIT_MIN_INSTR
 
 struct JitKernel {
   void* module = nullptr;    // CUmodule

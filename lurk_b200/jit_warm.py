@@ -24,8 +24,9 @@ def precompile(toplevel, entry: str) -> dict:
 
 
 def stock_programs():
+    from .lair import demo_toplevel
     from .programs import hash_toplevel, u64_toplevel
-    return [(hash_toplevel(), "cons_chain"), (u64_toplevel(), "factu")]
+    return [(hash_toplevel(), "cons_chain"), (u64_toplevel(), "factu"), (demo_toplevel(), "fib")]
 
 
 def main():

@@ -441,7 +441,7 @@ def test_compiled_constraint_programs_match_the_interpreter(monkeypatch):
     if N.lib().lsk_machine_jit_chips(m1.h) == 0:      # cold cache (no build() step ran): compile now
         monkeypatch.setenv("LSK_JIT", "1")
         m1 = new_machine(top, "cons_chain")
-    assert N.lib().lsk_machine_jit_chips(m1.h) == 3   # hash3, hash4, hash5
+    assert N.lib().lsk_machine_jit_chips(m1.h) >= 3   # hash3, hash4, hash5 (+ the short programs above 16 instructions)
     compiled = m1.prove(m1.setup()[0], Shard.new(q))
     assert np.array_equal(interpreted.words, compiled.words)
     m1.verify(m1.setup()[1], compiled)

@@ -188,11 +188,12 @@ def test_loaders_reject_malformed_images_without_crashing():
 
 
 def test_jit_precompile_fills_and_reuses_the_cubin_cache(tmp_path, monkeypatch):
-    # csrc/jit.cu: NVRTC needs no GPU.  A small program is below the threshold (nothing to do); the u64 chipset
-    # programs (2 chips above 1024 instructions) compile into an empty cache and are found there the second time.
+    # csrc/jit.cu: NVRTC needs no GPU.  With the threshold at 1024 instructions a small program has nothing to
+    # compile; the u64 chipset programs (2 chips above it) compile into an empty cache and are found there again.
     from lurk_b200 import jit_warm
     from lurk_b200.programs import u64_toplevel
     monkeypatch.setenv("LSK_JIT_CACHE", str(tmp_path / "cache"))
+    monkeypatch.setenv("LSK_JIT_MIN_INSTR", "1024")
     assert jit_warm.precompile(demo_toplevel(), "fib") == {"compiled": 0, "cached": 0}
     assert jit_warm.precompile(u64_toplevel(), "factu") == {"compiled": 2, "cached": 0}
     assert jit_warm.precompile(u64_toplevel(), "factu") == {"compiled": 0, "cached": 2}

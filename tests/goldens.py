@@ -1,110 +1,35 @@
-"""Golden trace matrices copied as *data* from the reference's own tests (file:line cited)."""
+"""Golden trace matrices restated as *data* from the reference's own tests: tests/golden/lair_traces.json holds the
+matrices with the reference file:line of each; this module loads them and lists the cases."""
+import json
+import os
+
 import numpy as np
 
+_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+with open(os.path.join(_DIR, "lair_traces.json")) as _f:
+    _TRACES = json.load(_f)
+with open(os.path.join(_DIR, "known_answers.json")) as _f:
+    KNOWN_ANSWERS = json.load(_f)
 
-def _m(rows, width):
-    a = np.asarray(rows, dtype=np.uint32)
-    return a.reshape(-1, width)
+
+def _load(name):
+    t = _TRACES[name]
+    return np.asarray(t["rows"], dtype=np.uint32).reshape(-1, t["width"])
 
 
-# src/lair/trace.rs:472-489
-FACTORIAL_5 = _m([
-    0, 5, 120, 0, 1, 1610612737, 24, 0, 0, 1, 120, 0, 1,
-    1, 4, 24, 0, 1, 1509949441, 6, 0, 0, 1, 24, 0, 1,
-    2, 3, 6, 1, 1, 1342177281, 2, 0, 0, 1, 6, 0, 1,
-    3, 2, 2, 2, 1, 1006632961, 1, 0, 0, 1, 2, 0, 1,
-    4, 1, 1, 3, 1, 1, 1, 0, 0, 1, 1, 0, 1,
-    5, 0, 1, 4, 1, 0, 0, 0, 0, 0, 0, 1, 0,
-    6, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-    7, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-], 13)
-
-# src/lair/trace.rs:498-513
-FIB_7 = _m([
-    0, 7, 13, 0, 1, 862828252, 1677721601, 8, 0, 0, 1, 5, 1, 1, 1006632961, 0, 0, 1,
-    1, 6, 8, 0, 1, 1677721601, 1610612737, 5, 0, 0, 1, 3, 2, 1, 1006632961, 0, 0, 1,
-    2, 5, 5, 0, 2, 1610612737, 1509949441, 3, 0, 0, 1, 2, 3, 1, 1006632961, 0, 0, 1,
-    3, 4, 3, 1, 2, 1509949441, 1342177281, 2, 0, 0, 1, 1, 4, 1, 1006632961, 0, 0, 1,
-    4, 3, 2, 2, 2, 1342177281, 1006632961, 1, 0, 0, 1, 1, 5, 1, 1006632961, 0, 0, 1,
-    5, 2, 1, 3, 2, 1006632961, 1, 1, 0, 0, 1, 0, 0, 0, 1, 0, 0, 1,
-    6, 1, 1, 4, 2, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0,
-    7, 0, 0, 5, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0,
-], 18)
-
-# src/lair/trace.rs:560-574
-MATCH_5_2 = _m([
-    0, 5, 2, 16, 0, 1, 1610612737, 1509949441, 1342177281, 1006632961, 16, 0, 0, 1, 0, 0, 0, 0, 1,
-    1, 4, 2, 16, 0, 1, 1509949441, 1342177281, 1006632961, 1, 16, 0, 0, 1, 0, 0, 0, 0, 1,
-    2, 3, 2, 16, 1, 1, 4, 16, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0,
-    3, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-], 19)
-
-# src/lair/trace.rs:640-651
-INNER_MATCH = _m([
-    0, 0, 0, 0, 0, 1, 1, 0, 0, 0,
-    1, 0, 1, 1, 0, 1, 0, 1, 0, 0,
-    2, 1, 0, 2, 0, 1, 0, 0, 1, 0,
-    3, 1, 1, 3, 0, 1, 0, 0, 0, 1,
-], 10)
-
-# src/lair/air.rs:662-674
-NOT = _m([
-    0, 4, 0, 0, 1, 1509949441, 0, 1,
-    1, 8, 0, 0, 1, 1761607681, 0, 1,
-    2, 0, 1, 0, 1, 0, 1, 1,
-    3, 1, 0, 0, 1, 1, 0, 1,
-], 8)
-
-# src/lair/air.rs:697-708
-EQ = _m([
-    0, 4, 2, 0, 0, 1, 1006632961, 0, 1,
-    1, 4, 4, 1, 0, 1, 0, 1, 1,
-    2, 0, 3, 0, 0, 1, 671088640, 0, 1,
-    3, 0, 0, 1, 0, 1, 0, 1, 1,
-], 9)
-
-# src/lair/air.rs:752-763
-IF_MANY = _m([
-    0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0,
-    1, 1, 3, 8, 2, 1, 0, 1, 1, 0, 0, 0, 0, 1,
-    2, 0, 0, 4, 1, 1, 0, 1, 0, 0, 1509949441, 0, 0, 1,
-    3, 0, 0, 0, 9, 1, 0, 1, 0, 0, 0, 447392427, 0, 1,
-], 14)
-
-# src/lair/air.rs:826-842
-MATCH_MANY = _m([
-    0, 0, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0, 0,
-    1, 0, 1, 1, 1, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0,
-    2, 1, 0, 1, 2, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0,
-    3, 1, 1, 1, 3, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0,
-    4, 0, 8, 0, 0, 0, 1, 0, 1761607681, 0, 862828252, 2013265920, 0, 2013265920, 0, 0, 0, 0, 0, 1,
-    5, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-    6, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-    7, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-], 20)
-
-# src/lair/air.rs:875-880
-ASSERT = _m([0, 2, 4, 6, 8, 2, 4, 6, 8, 0, 1, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 1], 22)
-
-# src/lair/air.rs:923-935
-EQUAL_BRANCH = _m([
-    0, 1, 1, 0, 1, 2013265920, 1006632960, 671088640, 0, 1,
-    1, 2, 1, 0, 1, 0, 0, 0, 1, 0,
-    2, 3, 1, 0, 1, 0, 0, 0, 1, 0,
-    3, 4, 1, 0, 1, 2, 0, 0, 1, 0,
-], 10)
-
-# src/lair/air.rs:960-962
-RANGE = _m([0, 100, 12, 64, 0, 1, 0, 0, 1, 0, 0, 1, 1], 13)
-
-# src/lair/memory.rs:150-153 and :163-168
-MEMORY_FUNC = _m([0, 2, 2, 0, 1, 1, 0, 0, 1, 2, 0, 0, 1, 1, 2, 3, 0, 1, 1006632961, 1], 20)
-MEMORY_MEM3 = _m([
-    1, 1, 0, 2, 1, 2, 3,
-    1, 2, 0, 1, 1, 1, 1,
-    0, 0, 0, 0, 0, 0, 0,
-    0, 0, 0, 0, 0, 0, 0,
-], 7)
+ASSERT = _load("ASSERT")   # src/lair/air.rs:875-880
+EQ = _load("EQ")   # src/lair/air.rs:697-708
+EQUAL_BRANCH = _load("EQUAL_BRANCH")   # src/lair/air.rs:923-935
+FACTORIAL_5 = _load("FACTORIAL_5")   # src/lair/trace.rs:472-489
+FIB_7 = _load("FIB_7")   # src/lair/trace.rs:498-513
+IF_MANY = _load("IF_MANY")   # src/lair/air.rs:752-763
+INNER_MATCH = _load("INNER_MATCH")   # src/lair/trace.rs:640-651
+MATCH_5_2 = _load("MATCH_5_2")   # src/lair/trace.rs:560-574
+MATCH_MANY = _load("MATCH_MANY")   # src/lair/air.rs:826-842
+MEMORY_FUNC = _load("MEMORY_FUNC")   # src/lair/memory.rs:150-153
+MEMORY_MEM3 = _load("MEMORY_MEM3")   # src/lair/memory.rs:163-168
+NOT = _load("NOT")   # src/lair/air.rs:662-674
+RANGE = _load("RANGE")   # src/lair/air.rs:960-962
 
 # (toplevel factory name, func name, list of argument tuples executed in order, golden)
 CASES = [

@@ -97,11 +97,15 @@ uint32_t chunk_size() {
   return 128;   // measured on the hash4 chip, 2^21 rows: 32 -> 12.9 ms, 64 -> 11.5, 128 -> 10.7, 192 -> 10.9, 256 -> 14.5
 }
 
-void operand(std::string& o, uint32_t w, const ChipH& c) {
+// `local_def`: for a register operand, the index of the chunk-local temporary that holds its value, or -1
+void operand(std::string& o, uint32_t w, const ChipH& c, long local_def) {
   const uint32_t idx = w & 0x0fffffffu;
   char buf[48];
   switch (w >> 28) {
-    case 0: snprintf(buf, sizeof buf, "R[%u]", idx); break;
+    case 0:
+      if (local_def >= 0) snprintf(buf, sizeof buf, "t%ld", local_def);
+      else snprintf(buf, sizeof buf, "R[%u]", idx);
+      break;
     case 1: snprintf(buf, sizeof buf, "%uu", to_mont(c.consts[idx] % P)); break;   // Montgomery literal
     case 2: snprintf(buf, sizeof buf, "LSK_ML(%u)", idx); break;
     case 3: snprintf(buf, sizeof buf, "LSK_MN(%u)", idx); break;
@@ -122,6 +126,23 @@ std::string program_source(const ChipH& c) {
   static const char* const SIG =
       "(uint32_t* __restrict__ R, Ext& acc, const QuotientArgs& a, const QuotientRow& q)";
   const uint32_t CHUNK = chunk_size();
+  // Liveness: the program is straight-line, so every register read has one reaching definition.  A value whose
+  // last read lies in the chunk that defines it becomes a C++ temporary (a machine register); only values that
+  // cross a chunk boundary go through the register file R[] in local memory.
+  std::vector<long> reach(c.n_regs ? c.n_regs : 1, -1), last_use(ninstr, -1), src_a(ninstr, -1), src_b(ninstr, -1);
+  for (size_t i = 0; i < ninstr; i++) {
+    const uint32_t op = c.code[4 * i], dst = c.code[4 * i + 1], x = c.code[4 * i + 2], y = c.code[4 * i + 3];
+    if ((x >> 28) == 0) {
+      src_a[i] = reach[x & 0x0fffffffu];
+      if (src_a[i] >= 0) last_use[src_a[i]] = (long)i;
+    }
+    if (op >= COP_ADD && op <= COP_MUL && (y >> 28) == 0) {
+      src_b[i] = reach[y & 0x0fffffffu];
+      if (src_b[i] >= 0) last_use[src_b[i]] = (long)i;
+    }
+    if (op != COP_ASSERT) reach[dst] = (long)i;
+  }
+  auto is_local = [&](long def) { return def >= 0 && (last_use[def] < 0 || (size_t)last_use[def] / CHUNK == (size_t)def / CHUNK); };
   bool asserts_in_chunk = false;
   // a chunk folds its constraints into four 64-bit sums (kept below P * 2^32, one Montgomery reduction per
   // coefficient when the chunk ends) instead of an extension-field multiply-add per constraint
@@ -147,17 +168,18 @@ std::string program_source(const ChipH& c) {
       asserts_in_chunk = true;
       snprintf(buf, sizeof buf, "LSK_ASSERT(%u, ", ci++);
       body += buf;
-      operand(body, x, c);
+      operand(body, x, c, is_local(src_a[i]) ? src_a[i] : -1);
       body += ");\n";
       continue;
     }
-    snprintf(buf, sizeof buf, "R[%u] = ", dst);
+    if (is_local((long)i)) snprintf(buf, sizeof buf, "const uint32_t t%zu = ", i);
+    else snprintf(buf, sizeof buf, "R[%u] = ", dst);
     body += buf;
     body += op == COP_ADD ? "fadd(" : op == COP_SUB ? "fsub(" : op == COP_MUL ? "fmul(" : "fneg(";
-    operand(body, x, c);
+    operand(body, x, c, is_local(src_a[i]) ? src_a[i] : -1);
     if (op != COP_NEG) {
       body += ", ";
-      operand(body, y, c);
+      operand(body, y, c, is_local(src_b[i]) ? src_b[i] : -1);
     }
     body += ");\n";
   }

@@ -191,8 +191,12 @@ void bary_weights_dev(lsk_ctx* ctx, unsigned logn, Ext z, Ext* wts) {
   if (split) comm_allgather(ctx, wts, (e - b) * sizeof(Ext));
 }
 
-constexpr int OPEN_COLS = 8;
+constexpr int OPEN_COLS = 4;
 struct OpenGroup { uint32_t mat, c0; };
+// One CTA: OPEN_ROWS rows x OPEN_COLS columns of one matrix.  The dot products are accumulated as raw 64-bit
+// products kept below P * 2^32 (one conditional subtraction per term, one Montgomery reduction at the end: a third
+// of the multiply-pipe work of a Montgomery product per term); rows are predicated, not broken out of, so the
+// loop unrolls and the loads of two rows are in flight together.
 __global__ void __launch_bounds__(256) open_partial_batch_kernel(const OpenMat* __restrict__ mats,
                                                                   const OpenGroup* __restrict__ groups, size_t n,
                                                                   const Ext* __restrict__ wts0, const Ext* __restrict__ wts1,
@@ -204,21 +208,31 @@ __global__ void __launch_bounds__(256) open_partial_batch_kernel(const OpenMat* 
   const uint32_t* __restrict__ m = mt.p;
   const size_t stride = mt.stride;
   const size_t row0 = (size_t)blockIdx.x * OPEN_ROWS;
-  Ext acc[OPEN_COLS][2];
+  const bool two = !mt.one_point;
+  uint64_t acc[OPEN_COLS][2][4];
 #pragma unroll
-  for (int c = 0; c < OPEN_COLS; c++) acc[c][0] = acc[c][1] = ext_zero();
+  for (int c = 0; c < OPEN_COLS; c++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) acc[c][0][e] = acc[c][1][e] = 0;
+#pragma unroll 2
   for (unsigned k = 0; k < OPEN_ROWS / 256; k++) {
-    size_t r = row0 + k * 256 + threadIdx.x;
-    if (r >= n) break;
-    Ext w0 = wts0[r], w1 = mt.one_point ? w0 : wts1[r];
-#pragma unroll
-    for (int c = 0; c < OPEN_COLS; c++) {
-      if (c0 + c < w) {
-        uint32_t v = m[(size_t)(c0 + c) * stride + r];
-        acc[c][0] = eadd(acc[c][0], emul_base(w0, v));
-        if (!mt.one_point) acc[c][1] = eadd(acc[c][1], emul_base(w1, v));
-      }
+    const size_t r = row0 + k * 256 + threadIdx.x;
+    const bool ok = r < n;
+    Ext w0 = ext_zero(), w1 = ext_zero();
+    if (ok) {
+      w0 = wts0[r];
+      if (two) w1 = wts1[r];
     }
+    uint32_t v[OPEN_COLS];
+#pragma unroll
+    for (int c = 0; c < OPEN_COLS; c++) v[c] = (ok && c0 + c < w) ? m[(size_t)(c0 + c) * stride + r] : 0u;
+#pragma unroll
+    for (int c = 0; c < OPEN_COLS; c++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        acc[c][0][e] = acc_reduce64(acc[c][0][e] + (uint64_t)w0.c[e] * v[c]);
+        if (two) acc[c][1][e] = acc_reduce64(acc[c][1][e] + (uint64_t)w1.c[e] * v[c]);
+      }
   }
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -227,7 +241,7 @@ __global__ void __launch_bounds__(256) open_partial_batch_kernel(const OpenMat* 
     for (int p = 0; p < 2; p++)
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        uint32_t v = acc[c][p].c[e];
+        uint32_t v = mont_reduce(acc[c][p][e]);
 #pragma unroll
         for (int d = 16; d >= 1; d >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
         if (lane == 0) red[warp][(c * 2 + p) * 4 + e] = v;

@@ -143,13 +143,13 @@ std::string program_source(const ChipH& c) {
     if (op != COP_ASSERT) reach[dst] = (long)i;
   }
   auto is_local = [&](long def) { return def >= 0 && (last_use[def] < 0 || (size_t)last_use[def] / CHUNK == (size_t)def / CHUNK); };
-  bool asserts_in_chunk = false;
+  bool asserts_in_chunk = false, pending = false;   // pending: an LSK_ASSERT_A term awaits its reducing partner
   // a chunk folds its constraints into four 64-bit sums (kept below P * 2^32, one Montgomery reduction per
   // coefficient when the chunk ends) instead of an extension-field multiply-add per constraint
   auto close_chunk = [&] {
     if (asserts_in_chunk) body += "  LSK_ASSERT_END;\n";
     body += "}\n";
-    asserts_in_chunk = false;
+    asserts_in_chunk = pending = false;
   };
   for (size_t i = 0; i < ninstr; i++) {
     if (i % CHUNK == 0) {
@@ -166,7 +166,8 @@ std::string program_source(const ChipH& c) {
     if (op == COP_ASSERT) {
       if (!asserts_in_chunk) body += "LSK_ASSERT_BEGIN;\n  ";
       asserts_in_chunk = true;
-      snprintf(buf, sizeof buf, "LSK_ASSERT(%u, ", ci++);
+      snprintf(buf, sizeof buf, pending ? "LSK_ASSERT_B(%u, " : "LSK_ASSERT_A(%u, ", ci++);
+      pending = !pending;
       body += buf;
       operand(body, x, c, is_local(src_a[i]) ? src_a[i] : -1);
       body += ");\n";

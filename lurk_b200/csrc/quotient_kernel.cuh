@@ -141,7 +141,18 @@ LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, 
 // constraints of one chunk: sum_i alpha^(n_total-1-ci) * v_i as four 64-bit sums of raw products, each kept below
 // P * 2^32 (what mont_reduce accepts) by one conditional subtraction per term; reduced once when the chunk ends
 #define LSK_ASSERT_BEGIN uint64_t lsk_s0 = 0, lsk_s1 = 0, lsk_s2 = 0, lsk_s3 = 0
-#define LSK_ASSERT(ci, v)                                               \
+// LSK_ASSERT_A adds a term without reducing (sum < P * 2^32 + P^2), LSK_ASSERT_B adds the next one and reduces
+// (P * 2^32 + 2 P^2 < 2^64): jit.cu alternates them; LSK_ASSERT_END reduces whatever is pending
+#define LSK_ASSERT_A(ci, v)                                \
+  {                                                        \
+    const Ext lsk_ap = a.apow[a.n_total - 1 - (ci)];       \
+    const uint32_t lsk_x = (v);                            \
+    lsk_s0 += (uint64_t)lsk_ap.c[0] * lsk_x;               \
+    lsk_s1 += (uint64_t)lsk_ap.c[1] * lsk_x;               \
+    lsk_s2 += (uint64_t)lsk_ap.c[2] * lsk_x;               \
+    lsk_s3 += (uint64_t)lsk_ap.c[3] * lsk_x;               \
+  }
+#define LSK_ASSERT_B(ci, v)                                             \
   {                                                                     \
     const Ext lsk_ap = a.apow[a.n_total - 1 - (ci)];                    \
     const uint32_t lsk_x = (v);                                         \
@@ -150,8 +161,9 @@ LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, 
     lsk_s2 = acc_reduce64(lsk_s2 + (uint64_t)lsk_ap.c[2] * lsk_x);      \
     lsk_s3 = acc_reduce64(lsk_s3 + (uint64_t)lsk_ap.c[3] * lsk_x);      \
   }
-#define LSK_ASSERT_END \
-  acc = eadd(acc, Ext{{mont_reduce(lsk_s0), mont_reduce(lsk_s1), mont_reduce(lsk_s2), mont_reduce(lsk_s3)}})
+#define LSK_ASSERT_END                                                                                     \
+  acc = eadd(acc, Ext{{mont_reduce(acc_reduce64(lsk_s0)), mont_reduce(acc_reduce64(lsk_s1)),               \
+                       mont_reduce(acc_reduce64(lsk_s2)), mont_reduce(acc_reduce64(lsk_s3))}})
 #include "lsk_program.cuh"
 extern "C" __global__ void __launch_bounds__(256) lsk_quotient_jit(QuotientArgs a, QuotientConsts qc,
                                                                    const uint32_t* __restrict__ inter, uint32_t nint,

@@ -214,24 +214,33 @@ __global__ void __launch_bounds__(256) open_partial_batch_kernel(const OpenMat* 
   for (int c = 0; c < OPEN_COLS; c++)
 #pragma unroll
     for (int e = 0; e < 4; e++) acc[c][0][e] = acc[c][1][e] = 0;
-#pragma unroll 2
-  for (unsigned k = 0; k < OPEN_ROWS / 256; k++) {
-    const size_t r = row0 + k * 256 + threadIdx.x;
-    const bool ok = r < n;
-    Ext w0 = ext_zero(), w1 = ext_zero();
-    if (ok) {
-      w0 = wts0[r];
-      if (two) w1 = wts1[r];
+  // two rows per step: acc < P * 2^32 plus two products < P^2 stays below 2^64, so ONE conditional subtraction
+  // serves two terms
+#pragma unroll 1
+  for (unsigned k = 0; k < OPEN_ROWS / 256; k += 2) {
+    const size_t ra = row0 + k * 256 + threadIdx.x, rb = ra + 256;
+    const bool oka = ra < n, okb = rb < n;
+    Ext w0a = ext_zero(), w1a = ext_zero(), w0b = ext_zero(), w1b = ext_zero();
+    if (oka) {
+      w0a = wts0[ra];
+      if (two) w1a = wts1[ra];
     }
-    uint32_t v[OPEN_COLS];
+    if (okb) {
+      w0b = wts0[rb];
+      if (two) w1b = wts1[rb];
+    }
+    uint32_t va[OPEN_COLS], vb[OPEN_COLS];
 #pragma unroll
-    for (int c = 0; c < OPEN_COLS; c++) v[c] = (ok && c0 + c < w) ? m[(size_t)(c0 + c) * stride + r] : 0u;
+    for (int c = 0; c < OPEN_COLS; c++) {
+      va[c] = (oka && c0 + c < w) ? m[(size_t)(c0 + c) * stride + ra] : 0u;
+      vb[c] = (okb && c0 + c < w) ? m[(size_t)(c0 + c) * stride + rb] : 0u;
+    }
 #pragma unroll
     for (int c = 0; c < OPEN_COLS; c++)
 #pragma unroll
       for (int e = 0; e < 4; e++) {
-        acc[c][0][e] = acc_reduce64(acc[c][0][e] + (uint64_t)w0.c[e] * v[c]);
-        if (two) acc[c][1][e] = acc_reduce64(acc[c][1][e] + (uint64_t)w1.c[e] * v[c]);
+        acc[c][0][e] = acc_reduce64(acc[c][0][e] + (uint64_t)w0a.c[e] * va[c] + (uint64_t)w0b.c[e] * vb[c]);
+        if (two) acc[c][1][e] = acc_reduce64(acc[c][1][e] + (uint64_t)w1a.c[e] * va[c] + (uint64_t)w1b.c[e] * vb[c]);
       }
   }
   const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -319,8 +328,17 @@ __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* _
     const ReduceMat& m = mats[mi];
     uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;   // raw 64-bit products below P * 2^32, one reduction per matrix
     const uint32_t* p = m.p + r;
-#pragma unroll 4
-    for (uint32_t c = 0; c < m.w; c++) {
+    uint32_t c = 0;
+#pragma unroll 2
+    for (; c + 2 <= m.w; c += 2) {   // two terms per conditional subtraction (acc + 2 products < 2^64)
+      const Ext ap = apow[c], aq = apow[c + 1];
+      const uint32_t v = p[(size_t)c * m.stride], u = p[(size_t)(c + 1) * m.stride];
+      s0 = acc_reduce64(s0 + (uint64_t)ap.c[0] * v + (uint64_t)aq.c[0] * u);
+      s1 = acc_reduce64(s1 + (uint64_t)ap.c[1] * v + (uint64_t)aq.c[1] * u);
+      s2 = acc_reduce64(s2 + (uint64_t)ap.c[2] * v + (uint64_t)aq.c[2] * u);
+      s3 = acc_reduce64(s3 + (uint64_t)ap.c[3] * v + (uint64_t)aq.c[3] * u);
+    }
+    if (c < m.w) {
       const Ext ap = apow[c];
       const uint32_t v = p[(size_t)c * m.stride];
       s0 = acc_reduce64(s0 + (uint64_t)ap.c[0] * v);

@@ -122,7 +122,7 @@ std::string program_source(const ChipH& c) {
   std::string body, calls;
   body.reserve(ninstr * 48);
   uint32_t ci = 0;
-  char buf[64];
+  char buf[96];
   static const char* const SIG =
       "(uint32_t* __restrict__ R, Ext& acc, const QuotientArgs& a, const QuotientRow& q)";
   const uint32_t CHUNK = chunk_size();
@@ -158,7 +158,7 @@ std::string program_source(const ChipH& c) {
       body += buf;
       body += SIG;
       body += " {\n";
-      snprintf(buf, sizeof buf, "  lsk_chunk_%zu(R, acc, a, q);\n", i / CHUNK);
+      snprintf(buf, sizeof buf, "  lsk_chunk_%zu(R, acc, a, q);\n  __syncthreads();\n", i / CHUNK);
       calls += buf;
     }
     const uint32_t op = c.code[4 * i], dst = c.code[4 * i + 1], x = c.code[4 * i + 2], y = c.code[4 * i + 3];

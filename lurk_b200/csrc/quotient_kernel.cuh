@@ -168,15 +168,19 @@ LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, 
 extern "C" __global__ void __launch_bounds__(256) lsk_quotient_jit(QuotientArgs a, QuotientConsts qc,
                                                                    const uint32_t* __restrict__ inter, uint32_t nint,
                                                                    uint32_t pw) {
-  const size_t row = a.row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (row >= a.row_end) return;
+  // no early exit: the chunks are separated by __syncthreads() so that the warps of a CTA walk the (megabyte-sized,
+  // straight-line) program together and share what the instruction cache fetched -- ncu showed "no instruction"
+  // as the second stall reason without it.  Threads past the end recompute a valid row and do not store.
+  size_t row = a.row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
+  const bool live = row < a.row_end;
+  if (!live) row = a.row_begin;
   QuotientRow q;
   quotient_row_setup(a, qc, row, q);
   uint32_t R[LSK_JIT_REGS];
   R[0] = 0;
   Ext acc = ext_zero();
   lsk_program(R, acc, a, q);
-  quotient_row_finish(a, qc, q, acc, LSK_JIT_ASSERTS, inter, nint, pw, true);
+  quotient_row_finish(a, qc, q, acc, LSK_JIT_ASSERTS, inter, nint, pw, live);
 }
 #else
 // ---- interpreted form.  ROWS rows per thread (rows t, t + 256, ... of the CTA's slab, so every access stays

@@ -106,6 +106,19 @@ void comm_allgather_columns(lsk_ctx* ctx, uint32_t* cols, size_t stride_words, u
   LSK_NCCL(n.GroupEnd());
 }
 
+void comm_broadcast_many(lsk_ctx* ctx, const std::vector<std::pair<void*, size_t>>& bufs, int root) {
+  Comm& c = group(ctx);
+  if (bufs.empty()) return;
+  double bytes = 0;
+  for (auto& b : bufs) bytes += (double)b.second;
+  ProfScope ps(ctx, PT_COMM, 1, bytes);
+  if (c.rank != root) c.bytes_received += bytes;
+  NcclApi& n = nccl();
+  LSK_NCCL(n.GroupStart());
+  for (auto& b : bufs) LSK_NCCL(n.Broadcast(b.first, b.first, b.second, NCCL_UINT8, root, (NcclComm)c.nccl, ctx->stream));
+  LSK_NCCL(n.GroupEnd());
+}
+
 void comm_allreduce_u32(lsk_ctx* ctx, uint32_t* buf, size_t count) {
   Comm& c = group(ctx);
   if (!count) return;

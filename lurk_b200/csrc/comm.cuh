@@ -11,6 +11,8 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <utility>
+#include <vector>
 
 #include "device.cuh"
 
@@ -46,6 +48,8 @@ void comm_allgather(lsk_ctx* ctx, void* buf, size_t bytes_per_rank);
 void comm_allgather_strided(lsk_ctx* ctx, void* base, size_t stride_bytes, unsigned nseg, size_t bytes_per_rank);
 // a column-major matrix whose columns were computed in blocks: rank r owns columns comm_range_of(r, size, w)
 void comm_allgather_columns(lsk_ctx* ctx, uint32_t* cols, size_t stride_words, uint32_t w);
+// every buffer of the list: rank `root`'s contents to all ranks (one NCCL group)
+void comm_broadcast_many(lsk_ctx* ctx, const std::vector<std::pair<void*, size_t>>& bufs, int root);
 // element-wise sum of 32-bit words over the group (used where exactly one rank holds a non-zero value)
 void comm_allreduce_u32(lsk_ctx* ctx, uint32_t* buf, size_t count);
 void comm_destroy(lsk_ctx* ctx);

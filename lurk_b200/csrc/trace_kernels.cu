@@ -13,6 +13,7 @@
 // thread i writes row brev(i) of every column, the inverse NTT then needs no reordering pass).
 // HBM-bound by design: 4*N*w bytes written + the record tables read once.
 #include "poseidon2.cuh"
+#include "comm.cuh"
 #include "trace.cuh"
 
 namespace lsk {
@@ -445,11 +446,19 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
   h2d_bytes = 0;
   const bool sliced = shard_size != 0 && record_row_ordered(rec);
   // words [first, first + count) of v; the returned pointer is biased by -first so that v's own indices work
+  // In a device group (comm.cuh) every rank holds the same host record, but only rank 0 of the group sends the
+  // large tables over PCIe; the others receive them over NVLink (one NCCL group of broadcasts at the end).
+  const bool grouped = comm_active(ctx);
+  std::vector<std::pair<void*, size_t>> from_leader;
   auto up_range = [&](const std::vector<uint32_t>& v, size_t first, size_t count) -> const uint32_t* {
     if (!count) return nullptr;
     bufs.emplace_back(ctx, count);
-    LSK_CUDA(cudaMemcpyAsync(bufs.back().p, v.data() + first, count * 4, cudaMemcpyHostToDevice, ctx->stream));
-    h2d_bytes += count * 4;
+    const bool shared = grouped && count * 4 >= (64u << 10);
+    if (!shared || ctx->comm->rank == 0) {
+      LSK_CUDA(cudaMemcpyAsync(bufs.back().p, v.data() + first, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+      h2d_bytes += count * 4;
+    }
+    if (shared) from_leader.emplace_back(bufs.back().p, count * 4);
     return bufs.back().p - first;
   };
   auto up = [&](const std::vector<uint32_t>& v) { return up_range(v, 0, v.size()); };
@@ -491,6 +500,7 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
     d.len = m.len; d.rows = (uint32_t)m.rows();
     h_mems.push_back(d);
   }
+  if (grouped) comm_broadcast_many(ctx, from_leader, 0);
   funcs.alloc(ctx, h_funcs.size());
   if (!h_funcs.empty()) funcs.upload(h_funcs.data(), h_funcs.size());
   mems.alloc(ctx, h_mems.size());

@@ -51,6 +51,7 @@ struct Driver {
   int (*ModuleLoadData)(void**, const void*) = nullptr;
   int (*ModuleGetFunction)(void**, void*, const char*) = nullptr;
   int (*ModuleUnload)(void*) = nullptr;
+  int (*FuncSetAttribute)(void*, int, int) = nullptr;
   int (*LaunchKernel)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**,
                       void**) = nullptr;
   bool ok = false;
@@ -82,12 +83,22 @@ Driver& driver() {
     void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
     if (!h) return;
     g_drv.ok = sym(h, g_drv.ModuleLoadData, "cuModuleLoadData") && sym(h, g_drv.ModuleGetFunction, "cuModuleGetFunction") &&
-               sym(h, g_drv.ModuleUnload, "cuModuleUnload") && sym(h, g_drv.LaunchKernel, "cuLaunchKernel");
+               sym(h, g_drv.ModuleUnload, "cuModuleUnload") && sym(h, g_drv.LaunchKernel, "cuLaunchKernel") &&
+               sym(h, g_drv.FuncSetAttribute, "cuFuncSetAttribute");
   });
   return g_drv;
 }
 
 // ---- source generation ---------------------------------------------------------------------------------------
+// Register file of the compiled program in shared memory ([register][thread], conflict-free) instead of local
+// memory, when it fits (LSK_JIT_SMEM=0 keeps it in local memory).
+constexpr uint32_t JIT_THREADS = 256;
+uint32_t smem_bytes_for(const ChipH& c) {
+  const char* e = getenv("LSK_JIT_SMEM");
+  if (e && e[0] == '0') return 0;
+  const size_t bytes = (size_t)(c.n_regs ? c.n_regs : 1u) * JIT_THREADS * 4;
+  return bytes <= (96u << 10) ? (uint32_t)bytes : 0u;   // at least two CTAs per SM
+}
 // statements per __noinline__ chunk (LSK_JIT_CHUNK overrides, for tuning; part of the source, hence of the cache key)
 uint32_t chunk_size() {
   if (const char* e = getenv("LSK_JIT_CHUNK")) {
@@ -104,7 +115,7 @@ void operand(std::string& o, uint32_t w, const ChipH& c, long local_def) {
   switch (w >> 28) {
     case 0:
       if (local_def >= 0) snprintf(buf, sizeof buf, "t%ld", local_def);
-      else snprintf(buf, sizeof buf, "R[%u]", idx);
+      else snprintf(buf, sizeof buf, "LSK_R(%u)", idx);
       break;
     case 1: snprintf(buf, sizeof buf, "%uu", to_mont(c.consts[idx] % P)); break;   // Montgomery literal
     case 2: snprintf(buf, sizeof buf, "LSK_ML(%u)", idx); break;
@@ -174,7 +185,7 @@ std::string program_source(const ChipH& c) {
       continue;
     }
     if (is_local((long)i)) snprintf(buf, sizeof buf, "const uint32_t t%zu = ", i);
-    else snprintf(buf, sizeof buf, "R[%u] = ", dst);
+    else snprintf(buf, sizeof buf, "LSK_R(%u) = ", dst);
     body += buf;
     body += op == COP_ADD ? "fadd(" : op == COP_SUB ? "fsub(" : op == COP_MUL ? "fmul(" : "fneg(";
     operand(body, x, c, is_local(src_a[i]) ? src_a[i] : -1);
@@ -197,8 +208,9 @@ std::string main_source(const ChipH& c) {
   for (size_t i = 0; i < c.code.size(); i += 4) asserts += c.code[i] == COP_ASSERT;
   char buf[200];
   snprintf(buf, sizeof buf,
-           "#define LSK_JIT_PROGRAM 1\n#define LSK_JIT_REGS %u\n#define LSK_JIT_ASSERTS %u\n#include \"quotient_kernel.cuh\"\n",
-           c.n_regs ? c.n_regs : 1u, asserts);
+           "#define LSK_JIT_PROGRAM 1\n#define LSK_JIT_REGS %u\n#define LSK_JIT_ASSERTS %u\n#define LSK_JIT_SMEM %u\n"
+           "#include \"quotient_kernel.cuh\"\n",
+           c.n_regs ? c.n_regs : 1u, asserts, smem_bytes_for(c) ? 1u : 0u);
   return buf;
 }
 
@@ -296,8 +308,11 @@ JitKernel* jit_quotient(const ChipH& c) {
   if (!jit_cubin(c, env && env[0] == '1', cubin, nullptr)) return nullptr;
   if (!driver().ok) fail(LSK_ERR_CUDA, "libcuda.so.1 could not be loaded for a compiled constraint program");
   auto k = new JitKernel;
+  k->smem_bytes = smem_bytes_for(c);
   int rc = driver().ModuleLoadData(&k->module, cubin.data());
   if (rc == 0) rc = driver().ModuleGetFunction(&k->function, k->module, "lsk_quotient_jit");
+  if (rc == 0 && k->smem_bytes > (48u << 10))
+    rc = driver().FuncSetAttribute(k->function, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)k->smem_bytes);
   if (rc != 0) {
     delete k;
     fail(LSK_ERR_CUDA, "loading the compiled constraint program of %s failed (CUresult %d)", c.name.c_str(), rc);
@@ -315,7 +330,8 @@ void jit_launch(lsk_ctx* ctx, const JitKernel* k, const QuotientArgs& a, const Q
                 uint32_t nint, uint32_t pw) {
   const size_t nrows = a.row_end - a.row_begin;
   void* params[] = {(void*)&a, (void*)&qc, (void*)&inter, (void*)&nint, (void*)&pw};
-  int rc = driver().LaunchKernel(k->function, div_up(nrows, 256), 1, 1, 256, 1, 1, 0, ctx->stream, params, nullptr);
+  int rc = driver().LaunchKernel(k->function, div_up(nrows, JIT_THREADS), 1, 1, JIT_THREADS, 1, 1, k->smem_bytes, ctx->stream,
+                                 params, nullptr);
   if (rc != 0) fail(LSK_ERR_CUDA, "cuLaunchKernel of a compiled constraint program failed (CUresult %d)", rc);
 }
 

@@ -15,6 +15,7 @@ constexpr size_t JIT_MIN_INSTR = 16;   // shorter programs are interpreted (the 
 struct JitKernel {
   void* module = nullptr;    // CUmodule
   void* function = nullptr;  // CUfunction of lsk_quotient_jit
+  uint32_t smem_bytes = 0;   // dynamic shared memory of a launch: the program's register file, or 0 (local memory)
 };
 
 bool jit_eligible(const ChipH& c);

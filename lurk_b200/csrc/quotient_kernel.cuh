@@ -132,6 +132,11 @@ LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, 
 #if defined(LSK_JIT_PROGRAM)
 // ---- compiled form: jit.cu defines LSK_JIT_REGS and LSK_JIT_ASSERTS and supplies "lsk_program.cuh" with the
 // chunk functions lsk_chunk_<k>(R, acc, a, q) plus lsk_program(R, acc, a, q) that calls them in order
+#if LSK_JIT_SMEM   // register file in shared memory, [register][thread]: R points at this thread's column
+#define LSK_R(i) R[(i) * 256]
+#else
+#define LSK_R(i) R[i]
+#endif
 #define LSK_ML(i) a.main[(size_t)(i) * a.mstride + q.r]
 #define LSK_MN(i) a.main[(size_t)(i) * a.mstride + q.rn]
 #define LSK_PL(i) a.prep[(size_t)(i) * a.pstride + q.r]
@@ -176,8 +181,13 @@ extern "C" __global__ void __launch_bounds__(256) lsk_quotient_jit(QuotientArgs 
   if (!live) row = a.row_begin;
   QuotientRow q;
   quotient_row_setup(a, qc, row, q);
+#if LSK_JIT_SMEM
+  extern __shared__ uint32_t lsk_regs[];
+  uint32_t* R = lsk_regs + threadIdx.x;
+#else
   uint32_t R[LSK_JIT_REGS];
-  R[0] = 0;
+#endif
+  LSK_R(0) = 0;
   Ext acc = ext_zero();
   lsk_program(R, acc, a, q);
   quotient_row_finish(a, qc, q, acc, LSK_JIT_ASSERTS, inter, nint, pw, live);

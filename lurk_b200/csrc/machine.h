@@ -66,34 +66,39 @@ inline AffineH parse_affine(const uint32_t* w, size_t n, size_t& p) {
 
 inline std::vector<ChipH> parse_machine_blob(const uint32_t* w, size_t n, uint32_t* num_pv) {
   if (n < 3 || w[0] != MACHINE_MAGIC) fail(LSK_ERR_ARG, "bad machine blob magic");
+  if (w[1] > n) fail(LSK_ERR_ARG, "machine blob truncated");
   std::vector<ChipH> chips(w[1]);
   *num_pv = w[2];
   size_t p = 3;
   for (auto& c : chips) {
     if (p + 10 > n) fail(LSK_ERR_ARG, "machine blob truncated");
     size_t len = w[p++], end = p + len;
-    if (end > n) fail(LSK_ERR_ARG, "machine blob truncated");
-    c.kind = w[p++]; c.index = w[p++]; c.width = w[p++]; c.prep_width = w[p++];
-    c.n_constraints = w[p++]; c.lqd = w[p++]; c.n_regs = w[p++];
-    uint32_t name_len = w[p++], name_words = w[p++];
-    if (p + name_words > end || name_len > 4 * name_words) fail(LSK_ERR_ARG, "bad chip name");
+    if (len > n || end > n) fail(LSK_ERR_ARG, "machine blob truncated");
+    auto rd = [&]() -> uint32_t {   // every read of this chip's descriptor stays inside it
+      if (p >= end) fail(LSK_ERR_ARG, "machine blob truncated");
+      return w[p++];
+    };
+    c.kind = rd(); c.index = rd(); c.width = rd(); c.prep_width = rd();
+    c.n_constraints = rd(); c.lqd = rd(); c.n_regs = rd();
+    uint32_t name_len = rd(), name_words = rd();
+    if (name_words > end - p || name_len > 4ull * name_words) fail(LSK_ERR_ARG, "bad chip name");
     c.name.assign((const char*)(w + p), name_len);
     p += name_words;
-    uint32_t nc = w[p++];
-    if (p + nc + 1 > end) fail(LSK_ERR_ARG, "machine blob truncated");
+    uint32_t nc = rd();
+    if (nc > end - p) fail(LSK_ERR_ARG, "machine blob truncated");
     c.consts.assign(w + p, w + p + nc);
     p += nc;
-    uint32_t ni = w[p++];
-    if (p + 4ull * ni > end) fail(LSK_ERR_ARG, "machine blob truncated");
+    uint32_t ni = rd();
+    if (4ull * ni > end - p) fail(LSK_ERR_ARG, "machine blob truncated");
     c.code.assign(w + p, w + p + 4ull * ni);
     p += 4ull * ni;
     for (int s = 0; s < 2; s++) {
-      uint32_t cnt = w[p++];
+      uint32_t cnt = rd();
       auto& lst = s == 0 ? c.sends : c.receives;
       for (uint32_t i = 0; i < cnt; i++) {
         InteractionH it;
-        it.kind = w[p++];
-        uint32_t nv = w[p++];
+        it.kind = rd();
+        uint32_t nv = rd();
         for (uint32_t k = 0; k < nv; k++) it.values.push_back(parse_affine(w, end, p));
         it.mult = parse_affine(w, end, p);
         lst.push_back(std::move(it));
@@ -101,6 +106,8 @@ inline std::vector<ChipH> parse_machine_blob(const uint32_t* w, size_t n, uint32
     }
     if (p != end) fail(LSK_ERR_ARG, "chip descriptor length mismatch");
     if (c.lqd != 1) fail(LSK_ERR_ARG, "only log_quotient_degree = 1 is supported (chip %s)", c.name.c_str());
+    if (c.width > (1u << 20) || c.prep_width > (1u << 20) || c.n_regs > (1u << 20))
+      fail(LSK_ERR_ARG, "implausible sizes in the descriptor of chip %s", c.name.c_str());
   }
   return chips;
 }

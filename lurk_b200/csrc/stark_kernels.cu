@@ -22,9 +22,12 @@ __global__ void __launch_bounds__(256) perm_rows_kernel(const uint32_t* __restri
                                                          const uint32_t* __restrict__ prep, size_t pstride, unsigned logn,
                                                          Ext alpha, const Ext* __restrict__ beta_pows,
                                                          uint32_t* __restrict__ perm, size_t perm_stride,
-                                                         Ext* __restrict__ rowsum_nat) {
-  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
-  if (r >> logn) return;
+                                                         size_t row_begin, size_t row_end, bool scatter,
+                                                         Ext* __restrict__ rowsum_out) {
+  // rows [row_begin, row_end) in storage (bit-reversed) order; the row sums go to natural order for the scan
+  // (scatter) or, when a device group splits the rows, stay in storage order until they have been all-gathered
+  size_t r = row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= row_end) return;
   Cells cells{main, mstride, prep, pstride, r};
   const uint32_t* s = inter;
   Ext rowsum = ext_zero();
@@ -45,7 +48,12 @@ __global__ void __launch_bounds__(256) perm_rows_kernel(const uint32_t* __restri
     for (int k = 0; k < 4; k++) perm[(size_t)(4 * b + k) * perm_stride + r] = v.c[k];
     rowsum = eadd(rowsum, v);
   }
-  rowsum_nat[bitrev32((uint32_t)r, logn)] = rowsum;
+  rowsum_out[scatter ? bitrev32((uint32_t)r, logn) : r] = rowsum;
+}
+__global__ void bitrev_permute_ext_kernel(const Ext* __restrict__ in, unsigned logn, Ext* __restrict__ out) {
+  size_t r = (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >> logn) return;
+  out[bitrev32((uint32_t)r, logn)] = in[r];
 }
 
 // inclusive scan of extension elements, 1024 per block
@@ -109,12 +117,25 @@ __global__ void phi_scatter_kernel(const Ext* __restrict__ phi_nat, unsigned log
 void perm_trace_dev(lsk_ctx* ctx, const ChipDev& chip, const uint32_t* main, size_t mstride, const uint32_t* prep,
                     size_t pstride, unsigned logn, Ext chal_alpha, const Ext* beta_pows_dev, uint32_t* perm_out,
                     size_t perm_stride, Ext* scratch, Ext* cum_sum_out) {
-  size_t n = (size_t)1 << logn;
+  size_t n = (size_t)1 << logn, b = 0, e = n;
+  // in a device group each rank computes the batch columns and row sums of a range of rows (one extension-field
+  // inversion per batch and row); columns and sums are all-gathered, the scan below runs on every rank
+  const bool split = comm_splits(ctx, logn);
+  if (split) comm_range(ctx, n, &b, &e);
+  DevBuf<Ext> sums_pos;
+  if (split) sums_pos.alloc(ctx, n);
   {
-    ProfScope ps(ctx, PT_PERM_ROWS, 1, (double)n * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw));
-    perm_rows_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(chip.inter.p, chip.nint, main, mstride, prep, pstride,
-                                                              logn, chal_alpha, beta_pows_dev, perm_out, perm_stride,
-                                                              scratch);
+    ProfScope ps(ctx, PT_PERM_ROWS, 1, (double)(e - b) * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw));
+    perm_rows_kernel<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(chip.inter.p, chip.nint, main, mstride, prep, pstride,
+                                                                  logn, chal_alpha, beta_pows_dev, perm_out, perm_stride,
+                                                                  b, e, !split, split ? sums_pos.p : scratch);
+    LSK_CUDA(cudaGetLastError());
+  }
+  if (split) {
+    if (chip.pw > 1) comm_allgather_strided(ctx, perm_out, perm_stride * 4, 4 * (chip.pw - 1), (e - b) * 4);
+    comm_allgather(ctx, sums_pos.p, (e - b) * sizeof(Ext));
+    ProfScope ps(ctx, PT_SCAN, 1, 32.0 * n);
+    bitrev_permute_ext_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(sums_pos.p, logn, scratch);
   }
   scan_ext_dev(ctx, scratch, n);
   ProfScope ps(ctx, PT_SCAN, 1, 32.0 * n);

@@ -34,6 +34,10 @@ METRIC = "lurk_fib_prove_trace_rows_per_sec"
 UNIT = "rows/s"
 
 
+MODMUL_PER_PERM16 = 8 * 16 * 4 + 13 * (4 + 16)      # x^7 = 4 products; 8 full rounds, 13 partial rounds (s-box + diagonal)
+MODMUL_PEAK = 11.97 * 148 * 1.965e9                 # measured Montgomery products/s (profiles/r01_fp64_probe.jsonl)
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -310,7 +314,7 @@ def run_ours(args):
             total_ms += float(ms)
             if profile:
                 for k, v in ctx.profile_read().items():
-                    acc = prof_acc.setdefault(k, {"ms": 0.0, "bytes": 0.0, "launches": 0})
+                    acc = prof_acc.setdefault(k, {"ms": 0.0, "bytes": 0.0, "launches": 0, "work": 0.0})
                     for f in acc:
                         acc[f] += v[f]
                 ctx.profile_enable(False)
@@ -350,6 +354,8 @@ def run_ours(args):
             gbs = v["bytes"] / (v["ms"] * 1e6) if v["ms"] > 0 else 0.0
             kernels[k] = {"ms_per_step": v["ms"] / args.steps, "launches_per_step": v["launches"] // args.steps,
                           "algorithmic_GBps": gbs}
+            if v.get("work"):      # hash kernels: width-16 Poseidon2 permutations, 772 modular products each
+                kernels[k]["poseidon2_perm_per_s"] = v["work"] / (v["ms"] * 1e-3)
             if v["ms"] > top_ms:
                 top_k, top_ms = k, v["ms"]
         tv = prof[top_k]
@@ -364,6 +370,14 @@ def run_ours(args):
                     "ms_per_launch": tv["ms"] / max(1, tv["launches"]),
                     "share_of_step_gpu_time": tv["ms"] / gpu_ms if gpu_ms else None,
                     "profiled_ms_per_step": prof_ms / args.steps, "kernel_ms_per_step": gpu_ms / args.steps}
+        if tv.get("work"):
+            # the bound that actually applies (Poseidon2 is integer-pipe bound): modular products per
+            # second, live, against the measured peak of a dependent-free Montgomery product stream on this chip
+            # (tools/fp64_probe.cu "mont_int": 11.97 products/clk/SM x 148 SMs x 1.965 GHz, profiles/r01_fp64_probe.jsonl)
+            mm = tv["work"] * MODMUL_PER_PERM16 / (tv["ms"] * 1e-3)
+            roofline["compute"] = {"bound": "integer multiply pipe", "achieved": mm / 1e12, "peak": MODMUL_PEAK / 1e12,
+                                   "unit": "T modmul/s", "frac": mm / MODMUL_PEAK,
+                                   "perm_per_s": tv["work"] / (tv["ms"] * 1e-3)}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": res_ms / args.steps, "higher_is_better": True,

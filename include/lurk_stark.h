@@ -51,6 +51,9 @@ int lsk_ctx_sync(lsk_ctx* ctx);
  * lsk_profile_tag_name) and returns the number of tags. */
 int lsk_profile_enable(lsk_ctx* ctx, int on);
 int lsk_profile_read(lsk_ctx* ctx, double* ms, double* bytes, uint64_t* launches, int cap);
+/* arithmetic work per tag since lsk_profile_enable, where the launcher states it: for the hash kernels
+ * (merkle_leaf, merkle_layer, fri_leaf) the number of width-16 Poseidon2 permutations (772 modular products each) */
+int lsk_profile_read_work(lsk_ctx* ctx, double* work, int cap);
 const char* lsk_profile_tag_name(int tag);
 
 /* ---- A1: Poseidon2 hashing of content-addressed data ------------------------------------------

@@ -136,7 +136,9 @@ class Context:
         n = lib().lsk_profile_read(self.h, ms, by, ln, cap)
         if n < 0:
             check(n)
-        return {lib().lsk_profile_tag_name(i).decode(): {"ms": ms[i], "bytes": by[i], "launches": int(ln[i])}
+        wk = (ctypes.c_double * cap)()
+        lib().lsk_profile_read_work(self.h, wk, cap)
+        return {lib().lsk_profile_tag_name(i).decode(): {"ms": ms[i], "bytes": by[i], "launches": int(ln[i]), "work": wk[i]}
                 for i in range(n) if ln[i]}
 
 

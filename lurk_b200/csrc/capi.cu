@@ -79,7 +79,7 @@ int lsk_profile_enable(lsk_ctx* ctx, int on) {
   Profiler& p = ctx->prof;
   for (auto& r : p.recs) p.pool.push_back(r.a), p.pool.push_back(r.b);
   p.recs.clear();
-  for (int i = 0; i < PT_COUNT; i++) p.launches[i] = 0, p.bytes[i] = 0, p.ms[i] = 0;
+  for (int i = 0; i < PT_COUNT; i++) p.launches[i] = 0, p.bytes[i] = 0, p.ms[i] = 0, p.work[i] = 0;
   if (ctx->comm) ctx->comm->bytes_received = 0;
   p.timing = on != 0;
   return LSK_OK;
@@ -102,6 +102,13 @@ int lsk_profile_read(lsk_ctx* ctx, double* ms, double* bytes, uint64_t* launches
     if (bytes) bytes[i] = p.bytes[i];
     if (launches) launches[i] = p.launches[i];
   }
+  return PT_COUNT;
+  LSK_API_END
+}
+int lsk_profile_read_work(lsk_ctx* ctx, double* work, int cap) {
+  LSK_API_BEGIN
+  if (!ctx || !work) fail(LSK_ERR_ARG, "null argument");
+  for (int i = 0; i < PT_COUNT && i < cap; i++) work[i] = ctx->prof.work[i];
   return PT_COUNT;
   LSK_API_END
 }

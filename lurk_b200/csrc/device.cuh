@@ -37,6 +37,7 @@ struct Profiler {
   std::vector<cudaEvent_t> pool;
   unsigned long long launches[PT_COUNT] = {};
   double bytes[PT_COUNT] = {};
+  double work[PT_COUNT] = {};   // arithmetic work where a launcher states it: width-16 Poseidon2 permutations (hash kernels)
   double ms[PT_COUNT] = {};
   cudaEvent_t get() {
     if (!pool.empty()) {
@@ -120,10 +121,11 @@ struct ProfScope {
   lsk_ctx* ctx;
   int tag;
   cudaEvent_t a = nullptr, b = nullptr;
-  ProfScope(lsk_ctx* c, int t, unsigned nlaunch, double algorithmic_bytes) : ctx(c), tag(t) {
+  ProfScope(lsk_ctx* c, int t, unsigned nlaunch, double algorithmic_bytes, double work = 0.0) : ctx(c), tag(t) {
     Profiler& p = ctx->prof;
     p.launches[t] += nlaunch;
     p.bytes[t] += algorithmic_bytes;
+    p.work[t] += work;
     if (p.timing) {
       a = p.get();
       b = p.get();

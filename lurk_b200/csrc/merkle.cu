@@ -266,6 +266,14 @@ static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std:
   cudaStream_t st = ctx->stream;
   unsigned l0 = 0;
   bool first = true;
+  // width-16 permutations of a layer: leaves absorb 8 words per permutation, a node compresses once and absorbs
+  // (+ compresses) what is injected at its layer
+  auto layer_perms = [&](unsigned l) {
+    const double n = (double)((size_t)1 << (tree.log_max - l));
+    const double inj = groups[l].second ? (double)((groups[l].second + 7) / 8) + (l ? 1.0 : 0.0) : 0.0;
+    if (l == 0) return n * (leaf_mode == ST_FRI_LEAVES ? 1.0 : inj);
+    return n * (1.0 + inj);
+  };
   auto layer_bytes = [&](unsigned l) {
     return (double)((size_t)1 << (tree.log_max - l)) * (32.0 + 4.0 * groups[l].second + (l ? 64.0 : 0.0) +
                                                         (l == 0 && leaf_mode == ST_FRI_LEAVES ? 32.0 : 0.0));
@@ -283,14 +291,15 @@ static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std:
     unsigned grid = div_up(e - b, MK_BLOCK);
     const double share = (double)(e - b) / (double)n;
     if (first) {
-      ProfScope ps(ctx, leaf_mode == ST_LEAVES ? PT_MERKLE_LEAF : PT_FRI_LEAF, 1, layer_bytes(0) * share);
+      ProfScope ps(ctx, leaf_mode == ST_LEAVES ? PT_MERKLE_LEAF : PT_FRI_LEAF, 1, layer_bytes(0) * share,
+                   layer_perms(0) * share);
       if (leaf_mode == ST_LEAVES)
         merkle_flat_kernel<ST_LEAVES><<<grid, MK_BLOCK, 0, st>>>(cols, groups[0].second, nullptr, nullptr, b, e, out);
       else
         merkle_flat_kernel<ST_FRI_LEAVES><<<grid, MK_BLOCK, 0, st>>>(cols, 0, fri_vals, nullptr, b, e, out);
       first = false;
     } else {
-      ProfScope ps(ctx, PT_MERKLE_LAYER, 1, layer_bytes(l0) * share);
+      ProfScope ps(ctx, PT_MERKLE_LAYER, 1, layer_bytes(l0) * share, layer_perms(l0) * share);
       merkle_flat_kernel<ST_NODES><<<grid, MK_BLOCK, 0, st>>>(cols, groups[l0].second, nullptr,
                                                              tree.nodes.p + tree.layer_off[l0 - 1] * 8, b, e, out);
     }

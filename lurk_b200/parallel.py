@@ -59,27 +59,30 @@ def gather_shard_proofs(local: dict, num_shards: int, dst: int = 0, shards_of=No
         def shards_of(r):
             return shards_of_rank(num_shards, r, world)
     mine = shards_of(rank)
-    sizes = torch.zeros(num_shards, dtype=torch.int64)
-    for s in mine:
-        sizes[s] = len(local[s])
-    sizes = sizes.to(dev)
-    dist.all_reduce(sizes)                      # every shard is owned by exactly one rank
-    sizes = sizes.cpu().numpy()
+    # one exchange: every rank sends `per` slots of [length, words...] (32-bit patterns; gloo has no uint32, so the
+    # words travel as int32), padded to the longest proof -- the lengths ride in the same message
     per = max(1, max(len(shards_of(r)) for r in range(world)))
-    cap = int(sizes.max()) if num_shards else 0
-    buf = torch.zeros((per, cap), dtype=torch.int64)
+    mylen = torch.tensor([max([len(local[s]) for s in mine], default=0)], dtype=torch.int64, device=dev)
+    dist.all_reduce(mylen, op=dist.ReduceOp.MAX)
+    cap = int(mylen.item())
+    host = np.zeros((per, cap + 1), dtype=np.int32)
     for k, s in enumerate(mine):
-        buf[k, :len(local[s])] = torch.from_numpy(np.asarray(local[s], dtype=np.int64))
-    buf = buf.to(dev)
-    outs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, outs, dst=dst)
-    if rank != dst:
+        w = np.ascontiguousarray(local[s], dtype=np.uint32)
+        host[k, 0] = len(w)
+        host[k, 1:1 + len(w)] = w.view(np.int32)
+    buf = torch.from_numpy(host).to(dev)
+    if rank == dst:
+        out = torch.empty((world, per, cap + 1), dtype=torch.int32, device=dev)
+        dist.gather(buf, list(out.unbind(0)), dst=dst)
+    else:
+        dist.gather(buf, None, dst=dst)
         return None
+    got = out.cpu().numpy()
     parts: List[Optional[np.ndarray]] = [None] * num_shards
-    for r, o in enumerate(outs):
-        o = o.cpu().numpy()
+    for r in range(world):
         for k, s in enumerate(shards_of(r)):
-            parts[s] = o[k, :int(sizes[s])].astype(np.uint32)
+            n = int(got[r, k, 0])
+            parts[s] = got[r, k, 1:1 + n].view(np.uint32).copy()
     return parts
 
 

@@ -1,3 +1,5 @@
+"""Times a standalone cubin of the hash4 constraint program on random data (the experiment behind csrc/jit.cu:
+monolithic vs chunked code generation; cubins from gen_chunked.py).  usage: run_cubin.py a.cubin [b.cubin ...]"""
 import sys, ctypes, numpy as np, torch
 from cuda.bindings import driver as cu
 P = 2013265921

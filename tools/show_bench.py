@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Pretty-print the last JSON line of a bench.py output file."""
-import json, sys
+import json, signal, sys
+signal.signal(signal.SIGPIPE, signal.SIG_DFL)   # `| head` must not raise
 d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
 print("value %.4g rows/s  ms/step %.2f | e2e %.4g rows/s (%.2f ms) | launches %d | clocks %s" % (
     d['value'], d['ms_per_step'], d['e2e']['value'], d['e2e']['ms_per_step'], d['gpu_launches'], d.get('clocks')))

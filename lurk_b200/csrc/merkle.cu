@@ -6,6 +6,7 @@
 // (8*N*w bytes for a blow-up-2 commit) and writes 32 B per row.  The stage is bound by the
 // integer pipes (one width-16 permutation ~ 750 modmuls per 32 B absorbed), not by HBM.
 #include <algorithm>
+#include <cstdlib>
 
 #include "fri.cuh"
 #include "merkle.cuh"
@@ -260,6 +261,18 @@ static void layout_layers(lsk_ctx* ctx, MerkleTreeDev& tree) {
   tree.nodes.alloc(ctx, off * 8);
 }
 
+// inputs per CTA of a tail launch (log2).  ST_LEVELS = 9 (512 nodes per CTA) puts the 256- and 128-node levels of every
+// subtree on ONE SM in thread mode (9.5 us each); a smaller split spreads those levels over more SMs and keeps every
+// level cooperative.  LSK_TAIL_SPLIT overrides (tuning).
+static unsigned tail_split() {
+  static const unsigned v = [] {
+    const char* e = getenv("LSK_TAIL_SPLIT");
+    long x = e ? atol(e) : 8;   // measured (fib 2^20, all tails of one prove): 9 -> 1.885 ms, 8 -> 1.810, 7 -> 1.920, 6 -> 1.973, 5 -> 2.234
+    return (unsigned)std::min<long>(std::max<long>(x, 3), ST_LEVELS);
+  }();
+  return v;
+}
+
 // groups: per layer l (0..log_max) the column-list range injected there (layer 0 = leaves)
 static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std::pair<uint32_t, uint32_t>>& groups,
                        int leaf_mode, const uint32_t* fri_vals, FriChallenge fc = {}) {
@@ -316,7 +329,7 @@ static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std:
   // latency-bound tail (or a whole small tree): subtree launches
   while (first || l0 < tree.log_max) {
     unsigned log_nodes = tree.log_max - l0;  // log2(nodes of layer l0)
-    unsigned log_in = std::min(log_nodes, ST_LEVELS);
+    unsigned log_in = std::min(log_nodes, tail_split());
     SubtreeArgs a{};
     a.nodes = tree.nodes.p;
     a.cols = tree.colptrs.p;

@@ -264,6 +264,14 @@ static void layout_layers(lsk_ctx* ctx, MerkleTreeDev& tree) {
 // inputs per CTA of a tail launch (log2).  ST_LEVELS = 9 (512 nodes per CTA) puts the 256- and 128-node levels of every
 // subtree on ONE SM in thread mode (9.5 us each); a smaller split spreads those levels over more SMs and keeps every
 // level cooperative.  LSK_TAIL_SPLIT overrides (tuning).
+static unsigned tail_log() {   // layers with <= 2^tail_log nodes are finished by subtree launches (LSK_TAIL_LOG: tuning)
+  static const unsigned v = [] {
+    const char* e = getenv("LSK_TAIL_LOG");
+    long x = e ? atol(e) : (long)TAIL_LOG;
+    return (unsigned)std::min<long>(std::max<long>(x, 10), 18);
+  }();
+  return v;
+}
 static unsigned tail_split() {
   static const unsigned v = [] {
     const char* e = getenv("LSK_TAIL_SPLIT");
@@ -296,7 +304,7 @@ static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std:
   // exchanged on the way up); the last of these layers is all-gathered for the tail, the ones below stay
   // distributed (tree.dist_layers) and are read through their owner when queries are answered.
   const bool split = comm_splits(ctx, tree.log_max);
-  while (tree.log_max - l0 > TAIL_LOG || (first && tree.log_max > ST_LEVELS)) {
+  while (tree.log_max - l0 > tail_log() || (first && tree.log_max > ST_LEVELS)) {
     size_t n = (size_t)1 << (tree.log_max - l0), b = 0, e = n;
     if (split) comm_range(ctx, n, &b, &e);
     uint32_t* out = tree.nodes.p + tree.layer_off[l0] * 8;

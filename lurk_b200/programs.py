@@ -4,7 +4,7 @@
 funcs around `extern_call`s, src/core/misc.rs:5-128 and src/core/chipset.rs:20-63); `cons_chain(n)` is
 the Lurk-shaped load of bench.py --workload cons: one 655-wide hash4 row per list element, so the hash
 chip dominates the trace exactly as it does when Lurk ingresses data."""
-from .lair import (ChipInfo, Toplevel, array, call, const, extern_call, func, match, ret, sub)
+from .lair import (ChipInfo, Toplevel, array, call, const, extern_call, func, load, match, ret, store, sub)
 
 
 def hash_toplevel():
@@ -110,3 +110,61 @@ def u64_toplevel():
     big_lt = func("big_num_less_than", [("a", 8), ("b", 8)], 1,
                   [extern_call(["c"], "big_num_lessthan", ["a", "b"]), ret("c")])
     return Toplevel([add, sub_f, less_than, fibu, maxu, is_zero, mul_f, divrem, factu, gcdu, big_lt], U64_CHIPS)
+
+
+def lurk_misc_toplevel():
+    """The eleven helper funcs of the Lurk toplevel that wrap the extern chips, restated from src/core/misc.rs:5-128
+    (hash3 / hash4 / hash5 are `invertible`; the u64 and big-num funcs take and return POINTERS to 8-word values:
+    load, extern_call, store), plus `u64_demo`, a driver that stores two u64 values, runs every u64 func on the
+    pointers and loads the results back (the reference reaches these funcs from eval_binop_num,
+    src/core/eval_direct.rs:1205-1340).  Their trace widths are pinned by the reference's own test
+    (eval_direct.rs:2053-2063): 493, 655, 815, 53, 53, 85, 166, 44, 26, 38, 78."""
+    from .lair import if_
+    chips = [ChipInfo("hasher3", 24, 8, 457, 0, kind=1), ChipInfo("hasher4", 32, 8, 611, 0, kind=2),
+             ChipInfo("hasher5", 40, 8, 763, 0, kind=3)] + U64_CHIPS
+    h3 = func("hash3", [("preimg", 24)], 8, [extern_call([("img", 8)], "hasher3", ["preimg"]), ret("img")], invertible=True)
+    h4 = func("hash4", [("preimg", 32)], 8, [extern_call([("img", 8)], "hasher4", ["preimg"]), ret("img")], invertible=True)
+    h5 = func("hash5", [("preimg", 40)], 8, [extern_call([("img", 8)], "hasher5", ["preimg"]), ret("img")], invertible=True)
+
+    def ptr_binop(name, chip):   # fn name(a, b): [1] { a = load(a); b = load(b); c = extern_call(chip, a, b); store(c) }
+        return func(name, ["a", "b"], 1, [
+            load([("av", 8)], "a"), load([("bv", 8)], "b"),
+            extern_call([("cv", 8)], chip, ["av", "bv"]),
+            store("c", ["cv"]), ret("c")])
+    u64_add, u64_sub, u64_mul = ptr_binop("u64_add", "u64_add"), ptr_binop("u64_sub", "u64_sub"), ptr_binop("u64_mul", "u64_mul")
+    u64_divrem = func("u64_divrem", ["a", "b"], 2, [
+        load([("av", 8)], "a"), load([("bv", 8)], "b"),
+        extern_call([("qv", 8), ("rv", 8)], "u64_divrem", ["av", "bv"]),
+        store("q", ["qv"]), store("r", ["rv"]), ret("q", "r")])
+    u64_lessthan = func("u64_lessthan", ["a", "b"], 1, [
+        load([("av", 8)], "a"), load([("bv", 8)], "b"),
+        extern_call(["c"], "u64_lessthan", ["av", "bv"]), ret("c")])
+    u64_iszero = func("u64_iszero", ["a"], 1, [load([("av", 8)], "a"), extern_call(["b"], "u64_iszero", ["av"]), ret("b")])
+    digest_equal = func("digest_equal", ["a", "b"], 1, [
+        load([("av", 8)], "a"), load([("bv", 8)], "b"),
+        sub(("diff", 8), "av", "bv"),
+        if_("diff", [const("zero", 0), ret("zero")]),
+        const("one", 1), ret("one")])
+    big_num_lessthan = func("big_num_lessthan", ["a", "b"], 1, [
+        load([("av", 8)], "a"), load([("bv", 8)], "b"),
+        extern_call(["c"], "big_num_lessthan", ["av", "bv"]), ret("c")])
+    # driver: (a, b) as 8 little-endian bytes each -> a+b, a-b, a*b, a/b, a%b (8 words each), a<b, b==0, a==b, a <_bignum b
+    u64_demo = func("u64_demo", [("a", 8), ("b", 8)], 44, [
+        store("pa", ["a"]), store("pb", ["b"]),
+        call(["ps"], "u64_add", ["pa", "pb"]), load([("s", 8)], "ps"),
+        call(["pd"], "u64_sub", ["pa", "pb"]), load([("d", 8)], "pd"),
+        call(["pm"], "u64_mul", ["pa", "pb"]), load([("m", 8)], "pm"),
+        call(["z"], "u64_iszero", ["pb"]),
+        call(["lt"], "u64_lessthan", ["pa", "pb"]),
+        call(["e"], "digest_equal", ["pa", "pb"]),
+        call(["blt"], "big_num_lessthan", ["pa", "pb"]),
+        if_("z", [array("zeros", [0] * 16), ret("s", "d", "m", "zeros", "lt", "z", "e", "blt")]),
+        call(["pq", "pr"], "u64_divrem", ["pa", "pb"]), load([("q", 8)], "pq"), load([("r", 8)], "pr"),
+        ret("s", "d", "m", "q", "r", "lt", "z", "e", "blt")])
+    return Toplevel([h3, h4, h5, u64_add, u64_sub, u64_mul, u64_divrem, u64_lessthan, u64_iszero, digest_equal,
+                     big_num_lessthan, u64_demo], chips)
+
+
+LURK_MISC_WIDTHS = {"hash3": 493, "hash4": 655, "hash5": 815, "u64_add": 53, "u64_sub": 53, "u64_mul": 85,
+                    "u64_divrem": 166, "u64_lessthan": 44, "u64_iszero": 26, "digest_equal": 38,
+                    "big_num_lessthan": 78}     # src/core/eval_direct.rs:2053-2063

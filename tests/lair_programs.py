@@ -162,3 +162,8 @@ def partial_toplevel():
 def u64_toplevel():
     from lurk_b200.programs import u64_toplevel as u
     return u()
+
+
+def lurk_misc_toplevel():
+    from lurk_b200.programs import lurk_misc_toplevel as u
+    return u()

@@ -445,3 +445,17 @@ def test_compiled_constraint_programs_match_the_interpreter(monkeypatch):
     compiled = m1.prove(m1.setup()[0], Shard.new(q))
     assert np.array_equal(interpreted.words, compiled.words)
     m1.verify(m1.setup()[1], compiled)
+
+
+@pytest.mark.parametrize("a,b", [(10**18 + 7, 12345), (123456789, 0)])
+def test_lurk_misc_u64_funcs_prove_bit_exact(oracle, a, b):
+    # src/core/misc.rs:32-128 (pointer-taking u64 / big-num / digest_equal funcs; widths pinned by the reference,
+    # tests/golden/known_answers.json) driven by u64_demo: executor, GPU witness (memory chips, byte lookups,
+    # extern chips), AIR, whole proof equal to the oracle's
+    from test_oracle_stark import _u64_demo_expected, u64_bytes
+    top = goldens.toplevel_for("lurk_misc")
+    m, om, q, proof, want = _prove_both(oracle, top, "u64_demo", [u64_bytes(a) + u64_bytes(b)])
+    assert list(q.expect_public_values())[16:] == _u64_demo_expected(a, b)
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+    m.verify(m.setup()[1], proof)

@@ -199,3 +199,13 @@ def test_jit_precompile_fills_and_reuses_the_cubin_cache(tmp_path, monkeypatch):
     assert jit_warm.precompile(u64_toplevel(), "factu") == {"compiled": 0, "cached": 2}
     files = sorted(p.name for p in (tmp_path / "cache").iterdir())
     assert len(files) == 2 and all(f.startswith("q_") and f.endswith("_sm100a.cubin") for f in files)
+
+
+def test_lurk_misc_u64_funcs_native_executor(oracle):
+    # src/core/misc.rs funcs through the native executor: same outputs as the oracle and as Python integers
+    from test_oracle_stark import _u64_demo_expected, u64_bytes
+    top = goldens.toplevel_for("lurk_misc")
+    for a, b in [(10**18 + 7, 12345), (5, 2**64 - 1), (77, 77), (123456789, 0)]:
+        q = QueryRecord.new(top)
+        out = execute_by_name(top, "u64_demo", u64_bytes(a) + u64_bytes(b), q)
+        assert [int(x) for x in out] == _u64_demo_expected(a, b)

@@ -89,3 +89,19 @@ def test_bytes_traces(oracle):
     prep = oracle.bytes_preprocessed()
     i = 0x3c | (0xa5 << 8)
     assert list(prep[i]) == [0x3c, 0xa5, 1, 0x3c & 0xa5, 0x3c ^ 0xa5, 0x3c | 0xa5]
+
+
+def test_lurk_misc_funcs_have_the_reference_widths():
+    # src/core/misc.rs:5-128 restated (lurk_b200/programs.py::lurk_misc_toplevel): the widths the reference's own
+    # test pins for these eleven funcs (eval_direct.rs:2053-2063) -- load / store / extern_call / `if` on an array /
+    # invertible funcs through compute_layout_sizes, in the Python specification and in the C++ host layer
+    import goldens
+    from lurk_b200 import host
+    from lurk_b200.lair import FuncChip
+    top = goldens.toplevel_for("lurk_misc")
+    want = goldens.KNOWN_ANSWERS["lurk_misc_widths"]["value"]
+    assert len(want) == 11
+    for name, width in want.items():
+        assert FuncChip.from_name(name, top).width() == width, name
+    # the C++ layer compiles the same surface to the same image (header words aux / sel give the same widths)
+    assert np.array_equal(host.compile_toplevel(top.surface_image()), top.serialize_py())

@@ -180,3 +180,25 @@ def test_stage_helpers(oracle):
     lb2 = lb.copy()
     lb2[31, 2] ^= 1
     assert not np.array_equal(r0, oracle.merkle_root([la, lb2[:32]]))
+
+
+def _u64_demo_expected(a, b):
+    M = 1 << 64
+    q, r = (a // b, a % b) if b else (0, 0)
+    pa = sum(x * P ** i for i, x in enumerate(u64_bytes(a)))     # the same 8 limbs read as a base-p integer
+    pb = sum(x * P ** i for i, x in enumerate(u64_bytes(b)))
+    return (u64_bytes((a + b) % M) + u64_bytes((a - b) % M) + u64_bytes(a * b % M) + u64_bytes(q) + u64_bytes(r)
+            + [int(a < b), int(b == 0), int(a == b), int(pa < pb)])
+
+
+@pytest.mark.parametrize("a,b", [(10**18 + 7, 12345), (5, 2**64 - 1), (77, 77), (123456789, 0)])
+def test_lurk_misc_u64_funcs_execute_prove_verify(oracle, a, b):
+    # the pointer-taking u64 / big-num / digest_equal funcs of the Lurk toplevel (src/core/misc.rs:32-128) driven the
+    # way eval_binop_num drives them (eval_direct.rs:1205-1340): store the operands, call, load the results
+    top = goldens.toplevel_for("lurk_misc")
+    ot, om, f = oracle_machine(oracle, top, "u64_demo")
+    rec = oracle.OracleRecord(ot)
+    out = rec.execute(f.index, u64_bytes(a) + u64_bytes(b), f.output_size)
+    assert list(out) == _u64_demo_expected(a, b)
+    proof = om.prove(rec)
+    assert om.verify(proof), om.last_error

@@ -167,3 +167,98 @@ def u64_toplevel():
 def lurk_misc_toplevel():
     from lurk_b200.programs import lurk_misc_toplevel as u
     return u()
+
+
+# ---- a slice of the Lurk evaluator, restated from src/core/eval_direct.rs for its pinned widths ------------------------
+# Tag / InternalTag / EvalErr values: src/core/tag.rs:23-39, src/core/ingress.rs:88-98, src/core/error.rs:7-30
+TAG = dict(U64=0, Num=1, BigNum=2, Comm=3, Char=4, Str=5, Key=6, Fun=7, Builtin=8, Coroutine=9, Sym=10, Cons=11, Env=12,
+           Fix=13, Err=14, Nil=15, T=16)
+ERR = dict(UnboundVar=0, InvalidForm=1, NotCons=12)
+
+
+def lurk_eval_subset_toplevel():
+    """coerce_if_sym (eval_direct.rs:903-915), open_comm (:917-930), car_cdr (:932-977) and equal_inner (:1032-1115),
+    statement for statement; `eval` and `ingress` are STUBS with the reference's signatures (partial fn eval(expr_tag,
+    expr, env): [2], fn ingress(tag_full: [8], digest: [8]): [2]) -- a func's layout depends on its own body and on
+    its callees' signatures only.  The reference pins the widths 9, 50, 61, 58 (eval_direct.rs:2044-2048)."""
+    from lurk_b200.lair import (ChipInfo, Toplevel, call, const, func, if_, load, match, mul, preimg, ret, sub)
+    from lurk_b200.programs import U64_CHIPS
+    chips = [ChipInfo("hasher3", 24, 8, 457, 0, kind=1), ChipInfo("hasher4", 32, 8, 611, 0, kind=2),
+             ChipInfo("hasher5", 40, 8, 763, 0, kind=3)] + U64_CHIPS
+    from lurk_b200.lair import extern_call
+    hash3 = func("hash3", [("preimg", 24)], 8, [extern_call([("img", 8)], "hasher3", ["preimg"]), ret("img")], invertible=True)
+    eval_stub = func("eval", ["expr_tag", "expr", "env"], 2, [ret("expr_tag", "expr")], partial=True)
+    ingress_stub = func("ingress", [("tag_full", 8), ("digest", 8)], 2, [const("z", 0), ret("z", "z")])
+
+    coerce_if_sym = func("coerce_if_sym", ["tag"], 1, [
+        match("tag", [((TAG["Nil"], TAG["T"]), [const("sym_tag", TAG["Sym"]), ret("sym_tag")])]),
+        ret("tag")])
+
+    open_comm = func("open_comm", ["hash_ptr"], 2, [
+        load([("comm_hash", 8)], "hash_ptr"),
+        preimg([("_secret", 8), "payload_tag", ("padding", 7), ("val_digest", 8)], "hash3", ["comm_hash"]),
+        call(["payload_tag2", "payload_ptr"], "ingress", ["payload_tag", "padding", "val_digest"]),
+        ret("payload_tag2", "payload_ptr")])
+
+    invalid = [ret("err_tag", "invalid_form", "err_tag", "invalid_form")]
+    car_cdr = func("car_cdr", ["rest_tag", "rest", "env"], 4, [
+        const("nil", 4242),                       # digests.lurk_symbol_ptr("nil"): a ZStore pointer, any constant here
+        const("nil_tag", TAG["Nil"]), const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]),
+        const("invalid_form", ERR["InvalidForm"]),
+        sub("rest_not_cons", "rest_tag", "cons_tag"),
+        if_("rest_not_cons", invalid),
+        load(["expr_tag", "expr", "rest_tag2", "_rest"], "rest"),
+        sub("rest_not_nil", "rest_tag2", "nil_tag"),
+        if_("rest_not_nil", invalid),
+        call(["val_tag", "val"], "eval", ["expr_tag", "expr", "env"]),
+        match("val_tag", [
+            (TAG["Err"], [ret("val_tag", "val", "val_tag", "val")]),
+            (TAG["Cons"], [load(["car_tag", "car", "cdr_tag", "cdr"], "val"), ret("car_tag", "car", "cdr_tag", "cdr")]),
+            (TAG["Nil"], [ret("nil_tag", "nil", "nil_tag", "nil")]),
+            (TAG["Str"], [
+                const("empty", 0),
+                sub("not_empty", "val", "empty"),
+                if_("not_empty", [load(["car_tag", "car", "cdr_tag", "cdr"], "val"), ret("car_tag", "car", "cdr_tag", "cdr")]),
+                const("str_tag", TAG["Str"]),
+                ret("nil_tag", "nil", "str_tag", "empty")]),
+        ]),
+        const("not_cons", ERR["NotCons"]),
+        ret("err_tag", "not_cons", "err_tag", "not_cons")], partial=True)
+
+    def pair_eq(third=None):   # the Str / Cons / Fun / Env arms: load both, compare component-wise, multiply
+        n3 = ["a_trd"] if third else []
+        m3 = ["b_trd"] if third else []
+        body = [load([("a_fst", 2), ("a_snd", 2)] + n3, "a"), load([("b_fst", 2), ("b_snd", 2)] + m3, "b"),
+                call(["fst_eq"], "equal_inner", ["a_fst", "b_fst"]),
+                call(["snd_eq"], "equal_inner", ["a_snd", "b_snd"])]
+        if third:
+            body += [call(["trd_eq"], "equal_inner", [third, "a_trd", third, "b_trd"]),
+                     mul("eq", "fst_eq", "snd_eq"), mul("eq2", "eq", "trd_eq"), ret("eq2")]
+        else:
+            body += [mul("eq", "fst_eq", "snd_eq"), ret("eq")]
+        return body
+
+    def digest_eq(n):
+        return [load([("a_d", n)], "a"), load([("b_d", n)], "b"), sub(("diff", n), "a_d", "b_d"),
+                if_("diff", [ret("zero")]), ret("one")]
+
+    def non_null(body):        # let a_and_b = mul(a, b); if !a_and_b { return zero } body
+        return [mul("a_and_b", "a", "b"), if_("a_and_b", body, [ret("zero")])]
+
+    equal_inner = func("equal_inner", ["a_tag", "a", "b_tag", "b"], 1, [
+        sub("not_eq_tag", "a_tag", "b_tag"),
+        const("zero", 0), const("one", 1),
+        if_("not_eq_tag", [ret("zero")]),
+        sub("not_eq", "a", "b"),
+        if_("not_eq", [                       # `if !not_eq { return one } match ...`  ==  If(not_eq, match..., return one)
+            match("a_tag", [
+                (TAG["Num"], [ret("zero")]),
+                (TAG["Char"], digest_eq(4)),
+                ((TAG["Key"], TAG["Sym"], TAG["Builtin"], TAG["Coroutine"], TAG["U64"], TAG["BigNum"], TAG["Comm"]), digest_eq(8)),
+                (TAG["Str"], non_null(pair_eq())),
+                (TAG["Cons"], pair_eq()),
+                ((TAG["Fun"], TAG["Fix"]), [const("trd_tag", TAG["Env"])] + pair_eq("trd_tag")),
+                (TAG["Env"], non_null(pair_eq("a_tag"))),
+            ], exhaustive=True)],
+            [ret("one")])])
+    return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner], chips)

@@ -105,3 +105,16 @@ def test_lurk_misc_funcs_have_the_reference_widths():
         assert FuncChip.from_name(name, top).width() == width, name
     # the C++ layer compiles the same surface to the same image (header words aux / sel give the same widths)
     assert np.array_equal(host.compile_toplevel(top.surface_image()), top.serialize_py())
+
+
+def test_lurk_evaluator_funcs_have_the_reference_widths():
+    # four funcs of the Lurk evaluator restated statement for statement (tests/lair_programs.py): a partial func with
+    # depth columns (car_cdr), a preimage of an invertible func (open_comm), multi-key and exhaustive matches, negated
+    # ifs, loads into several variables -- the widths the reference's own test pins (eval_direct.rs:2044-2048)
+    import goldens
+    from lurk_b200 import host
+    from lurk_b200.lair import FuncChip
+    top = goldens.toplevel_for("lurk_eval_subset")
+    for name, width in goldens.KNOWN_ANSWERS["lurk_eval_subset_widths"]["value"].items():
+        assert FuncChip.from_name(name, top).width() == width, name
+    assert np.array_equal(host.compile_toplevel(top.surface_image()), top.serialize_py())

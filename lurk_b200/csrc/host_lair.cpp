@@ -68,6 +68,12 @@ St range_u8(const std::vector<std::string>& xs) {
   s.names = xs;
   return s;
 }
+St slice(const std::vector<Var>& outs, const std::vector<std::string>& inps) {
+  St s = mk(SK::Slice);
+  s.outs = outs;
+  s.names = inps;
+  return s;
+}
 St ret(const std::vector<std::string>& vs) {
   St s = mk(SK::Return);
   s.names = vs;
@@ -337,6 +343,15 @@ std::unique_ptr<Block> compile_block(const Stmts& body, const Stmts& pre, Linker
         Op op{OK::RangeU8};
         op.xs = flat(s.names);
         ops.push_back(op);
+      } break;
+      case SK::Slice: {   // pure re-linking (toplevel.rs OpE::Slice)
+        const std::vector<uint32_t> vals = flat(s.names);
+        if (out_size(s.outs) != vals.size()) bail("Var mismatch on slice");
+        size_t pos = 0;
+        for (auto& o : s.outs) {
+          ctx.link[o.name] = std::vector<uint32_t>(vals.begin() + pos, vals.begin() + pos + o.size);
+          pos += o.size;
+        }
       } break;
       default: last = true;
     }
@@ -635,7 +650,7 @@ struct Reader {
   St stmt() {
     St st;
     uint32_t k = u();
-    if (k > (uint32_t)SK::MatchMany) bail("bad statement kind in surface image");
+    if (k > (uint32_t)SK::Slice) bail("bad statement kind in surface image");
     st.kind = (SK)k;
     switch (st.kind) {
       case SK::Const: st.tgt = s(); st.value = u(); break;
@@ -651,6 +666,7 @@ struct Reader {
       case SK::Store: st.tgt = s(); st.names = names(); break;
       case SK::Load: st.outs = vars(); st.a = s(); break;
       case SK::RangeU8: case SK::Return: st.names = names(); break;
+      case SK::Slice: st.outs = vars(); st.names = names(); break;
       case SK::If: {
         st.a = s();
         st.arms.push_back(Arm{{}, block()});

@@ -40,7 +40,7 @@ struct St;
 using Stmts = std::vector<St>;
 enum class SK : uint32_t {
   Const, Array, Add, Sub, Mul, Div, Inv, Not, Eq, AssertEq, AssertNe, Contains, Call, PreImg, Store, Load,
-  ExternCall, RangeU8, Return, If, Match, MatchMany
+  ExternCall, RangeU8, Return, If, Match, MatchMany, Slice
 };
 struct Arm {
   std::vector<uint32_t> keys;  // Match: alternative scalar keys; MatchMany: one key tuple
@@ -78,6 +78,8 @@ St store(const std::string& ptr, const std::vector<std::string>& vals);
 St load(const std::vector<Var>& vals, const std::string& ptr);
 St extern_call(const std::vector<Var>& outs, const std::string& chip, const std::vector<std::string>& inps);
 St range_u8(const std::vector<std::string>& xs);
+// `let (x, y: [7]) = (a, b);` -- OpE::Slice (src/lair/expr.rs:141-143): rebinds the concatenated values, no bytecode
+St slice(const std::vector<Var>& outs, const std::vector<std::string>& inps);
 St ret(const std::vector<std::string>& vs);
 St if_(const std::string& x, Stmts then);                 // the statements that follow form the else block
 St if_else(const std::string& x, Stmts then, Stmts else_);

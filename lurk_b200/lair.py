@@ -68,6 +68,10 @@ def store(ptr: str, vals: Sequence[str]) -> St: return St("store", (ptr, list(va
 def load(vals: Sequence[VarRef], ptr: str) -> St: return St("load", (list(vals), ptr))
 def extern_call(outs: Sequence[VarRef], name: str, inps: Sequence[str]) -> St: return St("extern_call", (list(outs), name, list(inps)))
 def range_u8(xs: Sequence[str]) -> St: return St("range_u8", (list(xs),))
+def slice_(outs: Sequence[VarRef], inps: Sequence[str]) -> St:
+    """`let (x, y: [7]) = (a, b);` -- OpE::Slice (src/lair/expr.rs:141-143, macros.rs:247-268): rebinds the values of
+    `inps`, concatenated, to the names `outs`; emits no bytecode."""
+    return St("slice", (list(outs), list(inps)))
 def ret(*vs: str) -> St: return St("return", (list(vs),))
 
 
@@ -263,6 +267,13 @@ def _compile_block(stmts: List[St], pre_ops: List[St], ctx: _Linker) -> Block:
                 ctx.new(o)
         elif k == "range_u8":
             ops.append(Op("range_u8", ([j for v in a[0] for j in ctx.get(v)],)))
+        elif k == "slice":   # toplevel.rs OpE::Slice: pure re-linking
+            flat = [j for v in a[1] for j in ctx.get(v)]
+            assert sum(_vsize(o) for o in a[0]) == len(flat), "Var mismatch on slice"
+            pos = 0
+            for o in a[0]:
+                ctx.link[_vname(o)] = flat[pos:pos + _vsize(o)]
+                pos += _vsize(o)
         elif k in ("return", "if", "match", "match_many"):
             last = True
         else:
@@ -491,7 +502,7 @@ class Toplevel:
 
         KIND = {"const": 0, "array": 1, "add": 2, "sub": 3, "mul": 4, "div": 5, "inv": 6, "not": 7, "eq": 8,
                 "assert_eq": 9, "assert_ne": 10, "contains": 11, "call": 12, "preimg": 13, "store": 14, "load": 15,
-                "extern_call": 16, "range_u8": 17, "return": 18, "if": 19, "match": 20, "match_many": 21}
+                "extern_call": 16, "range_u8": 17, "return": 18, "if": 19, "match": 20, "match_many": 21, "slice": 22}
 
         def vars_(vs) -> List[int]:
             out = [len(vs)]
@@ -529,6 +540,8 @@ class Toplevel:
                 out += vars_(a[0]) + [sid(a[1])]
             elif k in ("range_u8", "return"):
                 out += names(a[0])
+            elif k == "slice":
+                out += vars_(a[0]) + names(a[1])
             elif k == "if":
                 out += [sid(a[0])] + block(a[1]) + ([1] + block(a[2]) if a[2] is not None else [0])
             elif k in ("match", "match_many"):

@@ -180,7 +180,8 @@ def lurk_eval_subset_toplevel():
     """coerce_if_sym (eval_direct.rs:903-915), open_comm (:917-930), car_cdr (:932-977) and equal_inner (:1032-1115),
     statement for statement; `eval` and `ingress` are STUBS with the reference's signatures (partial fn eval(expr_tag,
     expr, env): [2], fn ingress(tag_full: [8], digest: [8]): [2]) -- a func's layout depends on its own body and on
-    its callees' signatures only.  The reference pins the widths 9, 50, 61, 58 (eval_direct.rs:2044-2048)."""
+    its callees' signatures only.  The reference pins the widths 9, 50, 61, 58 and, for env_lookup (:1937-1956), 52
+    (eval_direct.rs:2044-2050)."""
     from lurk_b200.lair import (ChipInfo, Toplevel, call, const, func, if_, load, match, mul, preimg, ret, sub)
     from lurk_b200.programs import U64_CHIPS
     chips = [ChipInfo("hasher3", 24, 8, 457, 0, kind=1), ChipInfo("hasher4", 32, 8, 611, 0, kind=2),
@@ -261,4 +262,30 @@ def lurk_eval_subset_toplevel():
                 (TAG["Env"], non_null(pair_eq("a_tag"))),
             ], exhaustive=True)],
             [ret("one")])])
-    return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner], chips)
+    # eval_direct.rs:1937-1956: `if !env {..}`, a 5-word load, `let y_tag_digest: [9] = (y_tag, y_digest)` (OpE::Slice)
+    from lurk_b200.lair import slice_
+    env_lookup = func("env_lookup", [("x_tag_digest", 9), "env"], 2, [
+        if_("env", [
+            load(["y_tag", "y", "val_tag", "val", "tail_env"], "env"),
+            load([("y_digest", 8)], "y"),
+            slice_([("y_tag_digest", 9)], ["y_tag", "y_digest"]),
+            sub(("not_eq", 9), "x_tag_digest", "y_tag_digest"),
+            if_("not_eq", [
+                call(["res_tag", "res"], "env_lookup", ["x_tag_digest", "tail_env"]),
+                ret("res_tag", "res")],
+                [ret("val_tag", "val")])],
+            [const("err_tag", TAG["Err"]), const("err", ERR["UnboundVar"]), ret("err_tag", "err")])])
+    # driver: an environment ((a . 7) (b . 9)) built in memory the way the evaluator lays it out -- entries
+    # (sym_tag, sym_ptr, val_tag, val, tail_env), symbols as pointers to 8-word digests -- then env_lookup
+    from lurk_b200.lair import array, store
+    env_demo = func("env_demo", ["x_tag", ("x_digest", 8)], 2, [
+        array("da", list(range(1, 9))), store("pa", ["da"]),
+        array("db", list(range(9, 17))), store("pb", ["db"]),
+        const("sym", TAG["Sym"]), const("num", TAG["Num"]), const("nil_env", 0), const("v7", 7), const("v9", 9),
+        store("env1", ["sym", "pa", "num", "v7", "nil_env"]),
+        store("env2", ["sym", "pb", "num", "v9", "env1"]),
+        slice_([("x_tag_digest", 9)], ["x_tag", "x_digest"]),
+        call(["res_tag", "res"], "env_lookup", ["x_tag_digest", "env2"]),
+        ret("res_tag", "res")])
+    return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
+                     env_demo], chips)

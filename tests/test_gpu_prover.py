@@ -459,3 +459,13 @@ def test_lurk_misc_u64_funcs_prove_bit_exact(oracle, a, b):
     assert np.array_equal(proof.words, want)
     assert om.verify(proof.words), om.last_error
     m.verify(m.setup()[1], proof)
+
+
+@pytest.mark.parametrize("x_digest", [list(range(1, 9)), [5] * 8])
+def test_lurk_env_lookup_proves_bit_exact(oracle, x_digest):
+    # env_lookup of the Lurk evaluator (eval_direct.rs:1937-1956) through the whole GPU path, proof equal to the oracle's
+    top = goldens.toplevel_for("lurk_eval_subset")
+    m, om, q, proof, want = _prove_both(oracle, top, "env_demo", [[10] + x_digest])
+    assert np.array_equal(proof.words, want)
+    assert om.verify(proof.words), om.last_error
+    m.verify(m.setup()[1], proof)

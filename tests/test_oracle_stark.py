@@ -202,3 +202,21 @@ def test_lurk_misc_u64_funcs_execute_prove_verify(oracle, a, b):
     assert list(out) == _u64_demo_expected(a, b)
     proof = om.prove(rec)
     assert om.verify(proof), om.last_error
+
+
+@pytest.mark.parametrize("x_tag,x_digest,want", [
+    (10, list(range(9, 17)), [1, 9]),          # b: the head entry
+    (10, list(range(1, 9)), [1, 7]),           # a: one recursion
+    (10, [5] * 8, [14, 0]),                    # unbound: (Tag::Err, EvalErr::UnboundVar)
+    (6, list(range(1, 9)), [14, 0]),           # same digest under another tag (Key) is a different variable
+])
+def test_lurk_env_lookup_executes_proves_verifies(oracle, x_tag, x_digest, want):
+    # env_lookup (src/core/eval_direct.rs:1937-1956, width pinned at 52) on an environment laid out in memory the way
+    # the evaluator does it: execution result, then a whole proof (memory chips of lengths 5 and 8, recursion)
+    top = goldens.toplevel_for("lurk_eval_subset")
+    ot, om, f = oracle_machine(oracle, top, "env_demo")
+    rec = oracle.OracleRecord(ot)
+    out = rec.execute(f.index, [x_tag] + x_digest, f.output_size)
+    assert list(out) == want
+    proof = om.prove(rec)
+    assert om.verify(proof), om.last_error

@@ -61,6 +61,9 @@ const char* lsk_profile_tag_name(int tag);
  * ZStore::hash3/4/5, src/core/zstore.rs:305-333.  width in {24, 32, 40} (also 16: the commitment
  * permutation); `in` is n rows of `width` words, `out8` n rows of 8 words. */
 int lsk_poseidon2_hash(lsk_ctx* ctx, int width, const uint32_t* in, size_t n, uint32_t* out8);
+/* the same hash on the host, one preimage after another: what ZStore does while it interns data
+ * (`Hasher::hash` -> `PoseidonChipset::execute_simple`, src/core/zstore.rs:228-240,305-333); no GPU involved */
+int lsk_poseidon2_hash_host(int width, const uint32_t* in, size_t n, uint32_t* out8);
 int lsk_poseidon2_hash_dev(lsk_ctx* ctx, int width, const uint32_t* in_dev, size_t n, uint32_t* out8_dev);
 /* full permutation (p3 Poseidon2::permute, hasher() in src/poseidon/config.rs:77-95) */
 int lsk_poseidon2_permute(lsk_ctx* ctx, int width, const uint32_t* in, size_t n, uint32_t* out);

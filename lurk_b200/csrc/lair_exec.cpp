@@ -677,6 +677,23 @@ int lsk_program_load(const uint32_t* words, size_t n, lsk_program** out) {
 }
 void lsk_program_free(lsk_program* p) { delete p; }
 
+int lsk_poseidon2_hash_host(int width, const uint32_t* in, size_t n, uint32_t* out8) {
+  LSK_API_BEGIN
+  if ((!in || !out8) && n) fail(LSK_ERR_ARG, "null argument");
+  if (width != 24 && width != 32 && width != 40) fail(LSK_ERR_ARG, "unsupported Poseidon2 width %d", width);
+  for (size_t i = 0; i < n; i++) {
+    uint32_t st[40];
+    for (int k = 0; k < width; k++) {
+      st[k] = in[i * width + k];
+      if (st[k] >= Pq) fail(LSK_ERR_ARG, "non-canonical field element in a hash preimage");
+    }
+    host_poseidon2(st, width);
+    for (int k = 0; k < 8; k++) out8[i * 8 + k] = st[k];
+  }
+  return LSK_OK;
+  LSK_API_END
+}
+
 int lsk_poseidon2_constants(int width, uint32_t* diag, uint32_t* full_rc, uint32_t* part_rc, size_t part_cap) {
   LSK_API_BEGIN
   const uint32_t *d, *f, *pr;

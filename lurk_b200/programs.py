@@ -4,7 +4,7 @@
 funcs around `extern_call`s, src/core/misc.rs:5-128 and src/core/chipset.rs:20-63); `cons_chain(n)` is
 the Lurk-shaped load of bench.py --workload cons: one 655-wide hash4 row per list element, so the hash
 chip dominates the trace exactly as it does when Lurk ingresses data."""
-from .lair import (ChipInfo, Toplevel, array, call, const, extern_call, func, load, match, ret, store, sub)
+from .lair import (ChipInfo, Toplevel, array, call, const, extern_call, func, load, match, ret, store, sub)  # noqa: E501
 
 
 def hash_toplevel():
@@ -168,3 +168,111 @@ def lurk_misc_toplevel():
 LURK_MISC_WIDTHS = {"hash3": 493, "hash4": 655, "hash5": 815, "u64_add": 53, "u64_sub": 53, "u64_mul": 85,
                     "u64_divrem": 166, "u64_lessthan": 44, "u64_iszero": 26, "digest_equal": 38,
                     "big_num_lessthan": 78}     # src/core/eval_direct.rs:2053-2063
+
+
+def lurk_data_toplevel():
+    """Data in and out of the Lair memory, restated from src/core/ingress.rs:142-329: `ingress(tag_full, digest)`
+    turns a content-addressed ZPtr into (tag, pointer) by walking the hash preimages (`preimg(hash4 / hash5, ..)`,
+    fed by ZStore.inject) and storing the parts; `egress(tag, ptr)` hashes it back.  nil and t become the
+    InternalTags 15 / 16 with the pointers of their preallocated digests (the reference's `preallocate_symbols`
+    stores every built-in symbol first; here `preallocate` stores nil and t, pointers 1 and 2).
+    `data_roundtrip` = preallocate, ingress, egress.  Widths pinned by the reference (eval_direct.rs:2051-2052):
+    ingress 104, egress 81."""
+    from .lair import assert_eq, if_, preimg, range_u8, slice_
+    from .zstore import TAG, ZStore
+    T = dict(TAG, Nil=15, T=16)
+    z = ZStore()
+    nil_digest, t_digest = list(z.nil().digest), list(z.t().digest)
+    NIL_PTR, T_PTR = 1, 2
+    chips = [ChipInfo("hasher3", 24, 8, 457, 0, kind=1), ChipInfo("hasher4", 32, 8, 611, 0, kind=2),
+             ChipInfo("hasher5", 40, 8, 763, 0, kind=3)]
+    h3 = func("hash3", [("preimg", 24)], 8, [extern_call([("img", 8)], "hasher3", ["preimg"]), ret("img")], invertible=True)
+    h4 = func("hash4", [("preimg", 32)], 8, [extern_call([("img", 8)], "hasher4", ["preimg"]), ret("img")], invertible=True)
+    h5 = func("hash5", [("preimg", 40)], 8, [extern_call([("img", 8)], "hasher5", ["preimg"]), ret("img")], invertible=True)
+
+    def pair_in():      # Str (non-empty) and Cons: two children behind hash4
+        return [preimg([("fst_tag_full", 8), ("fst_digest", 8), ("snd_tag_full", 8), ("snd_digest", 8)], "hash4", ["digest"]),
+                call(["fst_tag", "fst_ptr"], "ingress", ["fst_tag_full", "fst_digest"]),
+                call(["snd_tag", "snd_ptr"], "ingress", ["snd_tag_full", "snd_digest"]),
+                store("ptr", ["fst_tag", "fst_ptr", "snd_tag", "snd_ptr"]), ret("tag", "ptr")]
+
+    def triple_in(env_tag_var, mk_env_tag):   # Fun / Fix and Env: two children + an environment behind hash5
+        return ([preimg([("a_tag_full", 8), ("a_digest", 8), ("b_tag_full", 8), ("b_digest", 8), ("env_digest", 8)],
+                        "hash5", ["digest"])] + mk_env_tag +
+                [call(["a_tag", "a_ptr"], "ingress", ["a_tag_full", "a_digest"]),
+                 call(["b_tag", "b_ptr"], "ingress", ["b_tag_full", "b_digest"]),
+                 call(["_env_tag", "env_ptr"], "ingress", [env_tag_var, "zeros", "env_digest"]),
+                 store("ptr", ["a_tag", "a_ptr", "b_tag", "b_ptr", "env_ptr"]), ret("tag", "ptr")])
+
+    ingress = func("ingress", [("tag_full", 8), ("digest", 8)], 2, [
+        array("zeros", [0] * 7),
+        slice_(["tag", ("rest", 7)], ["tag_full"]),
+        assert_eq("rest", "zeros"),
+        match("tag", [
+            (T["Num"], [slice_(["x", ("rest2", 7)], ["digest"]), assert_eq("rest2", "zeros"), ret("tag", "x")]),
+            (T["Char"], [slice_([("bytes", 4), ("rest4", 4)], ["digest"]), range_u8(["bytes"]), array("zeros4", [0] * 4),
+                         assert_eq("rest4", "zeros4"), store("ptr", ["bytes"]), ret("tag", "ptr")]),
+            (T["U64"], [range_u8(["digest"]), store("ptr", ["digest"]), ret("tag", "ptr")]),
+            (T["Sym"], [
+                array("nil_digest", nil_digest),
+                sub(("not_nil", 8), "digest", "nil_digest"),
+                if_("not_nil", [
+                    array("t_digest", t_digest),
+                    sub(("not_t", 8), "digest", "t_digest"),
+                    if_("not_t", [store("ptr", ["digest"]), ret("tag", "ptr")],
+                        [const("t_tag", T["T"]), const("ptr", T_PTR), ret("t_tag", "ptr")])],
+                    [const("nil_tag", T["Nil"]), const("ptr", NIL_PTR), ret("nil_tag", "ptr")])]),
+            ((T["Builtin"], T["Coroutine"], T["Key"], T["BigNum"], T["Comm"]), [store("ptr", ["digest"]), ret("tag", "ptr")]),
+            (T["Str"], [if_("digest", pair_in(), [const("zero", 0), ret("tag", "zero")])]),
+            (T["Cons"], pair_in()),
+            ((T["Fun"], T["Fix"]), triple_in("env_tag", [const("env_tag", T["Env"])])),
+            (T["Env"], [if_("digest", triple_in("tag", []), [const("zero", 0), ret("tag", "zero")])]),
+        ], exhaustive=True)])
+
+    def pair_out():
+        return [load(["fst_tag", "fst_ptr", "snd_tag", "snd_ptr"], "val"),
+                call(["fst_tag2", ("fst_digest", 8)], "egress", ["fst_tag", "fst_ptr"]),
+                call(["snd_tag2", ("snd_digest", 8)], "egress", ["snd_tag", "snd_ptr"]),
+                array("padding", [0] * 7),
+                slice_([("fst_tag_full", 8)], ["fst_tag2", "padding"]),
+                slice_([("snd_tag_full", 8)], ["snd_tag2", "padding"]),
+                call([("digest", 8)], "hash4", ["fst_tag_full", "fst_digest", "snd_tag_full", "snd_digest"]),
+                ret("tag", "digest")]
+
+    def triple_out(env_tag_var, mk_env_tag):
+        return ([load(["a_tag", "a_ptr", "b_tag", "b_ptr", "env_ptr"], "val"),
+                 call(["a_tag2", ("a_digest", 8)], "egress", ["a_tag", "a_ptr"]),
+                 call(["b_tag2", ("b_digest", 8)], "egress", ["b_tag", "b_ptr"])] + mk_env_tag +
+                [call(["_env_tag", ("env_digest", 8)], "egress", [env_tag_var, "env_ptr"]),
+                 array("padding", [0] * 7),
+                 slice_([("a_tag_full", 8)], ["a_tag2", "padding"]),
+                 slice_([("b_tag_full", 8)], ["b_tag2", "padding"]),
+                 call([("digest", 8)], "hash5", ["a_tag_full", "a_digest", "b_tag_full", "b_digest", "env_digest"]),
+                 ret("tag", "digest")])
+
+    egress = func("egress", ["tag", "val"], 9, [
+        match("tag", [
+            ((T["Num"], T["Err"]), [array("padding", [0] * 7), slice_([("digest", 8)], ["val", "padding"]), ret("tag", "digest")]),
+            (T["Char"], [array("padding", [0] * 4), load([("bytes", 4)], "val"), ret("tag", "bytes", "padding")]),
+            (T["Nil"], [const("sym_tag", T["Sym"]), array("digest", nil_digest), ret("sym_tag", "digest")]),
+            (T["T"], [const("sym_tag", T["Sym"]), array("digest", t_digest), ret("sym_tag", "digest")]),
+            ((T["Sym"], T["Builtin"], T["Coroutine"], T["Key"], T["U64"], T["BigNum"], T["Comm"]),
+             [load([("digest", 8)], "val"), ret("tag", "digest")]),
+            (T["Str"], [if_("val", pair_out(), [array("digest", [0] * 8), ret("tag", "digest")])]),
+            (T["Cons"], pair_out()),
+            ((T["Fun"], T["Fix"]), triple_out("env_tag", [const("env_tag", T["Env"])])),
+            (T["Env"], [if_("val", triple_out("tag", []), [array("digest", [0] * 8), ret("tag", "digest")])]),
+        ], exhaustive=True)])
+
+    preallocate = func("preallocate", [], 2, [
+        array("nil_digest", nil_digest), store("nil_ptr", ["nil_digest"]),
+        array("t_digest", t_digest), store("t_ptr", ["t_digest"]),
+        ret("nil_ptr", "t_ptr")])
+    data_roundtrip = func("data_roundtrip", [("tag_full", 8), ("digest", 8)], 9, [
+        call(["nil_ptr", "t_ptr"], "preallocate", []),
+        const("one", NIL_PTR), const("two", T_PTR),
+        assert_eq("nil_ptr", "one"), assert_eq("t_ptr", "two"),
+        call(["tag", "ptr"], "ingress", ["tag_full", "digest"]),
+        call(["out_tag", ("out_digest", 8)], "egress", ["tag", "ptr"]),
+        ret("out_tag", "out_digest")])
+    return Toplevel([data_roundtrip, preallocate, ingress, egress, h3, h4, h5], chips)

@@ -289,3 +289,8 @@ def lurk_eval_subset_toplevel():
         ret("res_tag", "res")])
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
                      env_demo], chips)
+
+
+def lurk_data_toplevel():
+    from lurk_b200.programs import lurk_data_toplevel as u
+    return u()

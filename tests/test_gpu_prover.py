@@ -469,3 +469,34 @@ def test_lurk_env_lookup_proves_bit_exact(oracle, x_digest):
     assert np.array_equal(proof.words, want)
     assert om.verify(proof.words), om.last_error
     m.verify(m.setup()[1], proof)
+
+
+@pytest.mark.parametrize("which", ["list", "fun"])
+def test_lurk_ingress_egress_proves_bit_exact(oracle, which):
+    # src/core/ingress.rs restated (widths pinned: 104 / 81): content-addressed data interned by the ZStore, its
+    # preimages injected (inject_inv_queries), ingress + egress executed, the whole thing proved on the GPU -- hash4 /
+    # hash5 chips with preimage lookups, memory chips of four lengths, byte range checks -- equal to the oracle's proof
+    from lurk_b200.zstore import ZStore
+    from test_zstore import _samples
+    top = goldens.toplevel_for("lurk_data")
+    z = ZStore()
+    x = _samples(z)[which]
+    args = [x.tag] + [0] * 7 + list(x.digest)
+    opts = SphinxCoreOpts(num_queries=6, proof_of_work_bits=6)
+    m = new_machine(top, "data_roundtrip", opts=opts)
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    z.inject(q, top)
+    out = execute_by_name(top, "data_roundtrip", args, q)
+    assert [int(v) for v in out] == [x.tag] + list(x.digest)
+    ot = oracle.OracleToplevel(top.serialize())
+    om = oracle.OracleMachine(ot, m.entry.index, m.blob, 6, 6)
+    rec = oracle.OracleRecord(ot)
+    for name, width in (("hash3", 24), ("hash4", 32), ("hash5", 40)):
+        if z.hashes[width]:
+            rec.inject_inv_queries(top.func_by_name(name).index, [list(k) for k in z.hashes[width]],
+                                   [list(v) for v in z.hashes[width].values()])
+    rec.execute(m.entry.index, args, m.entry.output_size)
+    proof = m.prove(pk, Shard.new(q))
+    assert np.array_equal(proof.words, om.prove(rec))
+    m.verify(vk, proof)

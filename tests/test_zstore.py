@@ -1,0 +1,76 @@
+"""ZStore (lurk_b200/zstore.py, host hashing through lsk_poseidon2_hash_host) against the reference's known answers, and
+data going into and out of the Lair memory through `ingress` / `egress` restated from src/core/ingress.rs."""
+import numpy as np
+import pytest
+
+import goldens
+from lurk_b200.execute import QueryRecord, execute_by_name
+from lurk_b200.lair import FuncChip
+from lurk_b200.zstore import TAG, ZStore
+
+
+def test_zstore_known_answers():
+    z = ZStore()
+    # zstore.rs:1008-1019 and cli/tests/prove.lurk:12-17 / meta.rs:1040
+    assert z.hide([0] * 8, z.num(123)).to_biguint() == int(goldens.KNOWN_ANSWERS["KAT-1"]["digest"], 16)
+    assert z.commit(z.cons(z.u64(13), z.u64(17))).to_biguint() == int(goldens.KNOWN_ANSWERS["KAT-2"]["digest"], 16)
+    # interning is content addressing: equal data, equal pointers; the hash caches remember every preimage
+    assert z.string("abc") == z.string("abc") and z.string("abc") != z.string("abd")
+    assert z.lurk_sym("nil") != z.lurk_sym("t") and z.builtin("cons").tag == TAG["Builtin"]
+    assert len(z.hashes[24]) == 2 and len(z.hashes[32]) > 10
+
+
+def test_ingress_egress_have_the_reference_widths():
+    top = goldens.toplevel_for("lurk_data")
+    for name, width in goldens.KNOWN_ANSWERS["lurk_data_widths"]["value"].items():
+        assert FuncChip.from_name(name, top).width() == width, name
+
+
+def _samples(z):
+    return {
+        "num": z.num(123),
+        "u64": z.u64(2 ** 63 + 5),
+        "char": z.char("é"),
+        "nil": z.nil(),
+        "t": z.t(),
+        "symbol": z.lurk_sym("foo"),
+        "builtin": z.builtin("cons"),
+        "empty string": z.string(""),
+        "string": z.string("hi"),
+        "cons": z.cons(z.u64(13), z.u64(17)),
+        "list": z.list([z.num(1), z.string("ab"), z.t(), z.list([z.u64(7), z.char("x")])]),
+        "comm": z.commit(z.num(5)),
+        "fun": z.tuple110(TAG["Fun"], z.list([z.lurk_sym("x")]), z.lurk_sym("x"),
+                          z.tuple110(TAG["Env"], z.lurk_sym("y"), z.num(3), z.null(TAG["Env"]))),
+    }
+
+
+@pytest.mark.parametrize("which", ["num", "u64", "char", "nil", "t", "symbol", "builtin", "empty string", "string", "cons",
+                                   "list", "comm", "fun"])
+def test_data_round_trips_through_the_lair_memory(oracle, which):
+    # the reference's test_ingress_egress (eval_direct.rs:2067-2120) in spirit: intern, inject the preimages, ingress,
+    # egress, and the same ZPtr comes back -- through the native executor AND the oracle's
+    top = goldens.toplevel_for("lurk_data")
+    z = ZStore()
+    x = _samples(z)[which]
+    args = [x.tag] + [0] * 7 + list(x.digest)
+    q = QueryRecord.new(top)
+    z.inject(q, top)
+    out = [int(v) for v in execute_by_name(top, "data_roundtrip", args, q)]
+    assert out == [x.tag] + list(x.digest)
+    ot = oracle.OracleToplevel(top.serialize())
+    rec = oracle.OracleRecord(ot)
+    for name, width in (("hash3", 24), ("hash4", 32), ("hash5", 40)):
+        if z.hashes[width]:
+            rec.inject_inv_queries(top.func_by_name(name).index, [list(k) for k in z.hashes[width]],
+                                   [list(v) for v in z.hashes[width].values()])
+    f = top.func_by_name("data_roundtrip")
+    assert [int(v) for v in rec.execute(f.index, args, f.output_size)] == out
+
+
+def test_ingress_rejects_a_digest_without_preimage():
+    from lurk_b200._native import LurkStarkError
+    top = goldens.toplevel_for("lurk_data")
+    q = QueryRecord.new(top)
+    with pytest.raises(LurkStarkError, match="Preimg not found"):
+        execute_by_name(top, "data_roundtrip", [TAG["Cons"]] + [0] * 7 + [1, 2, 3, 4, 5, 6, 7, 8], q)

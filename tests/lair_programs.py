@@ -287,8 +287,55 @@ def lurk_eval_subset_toplevel():
         slice_([("x_tag_digest", 9)], ["x_tag", "x_digest"]),
         call(["res_tag", "res"], "env_lookup", ["x_tag_digest", "env2"]),
         ret("res_tag", "res")])
+    # eval_direct.rs:979-1030, 1118-1182: three partial funcs around `eval` (names are re-bound the way the reference's
+    # `let (head_tag, head) = call(eval, head_tag, head, env)` shadows them)
+    err_if = lambda tag, val: match(tag, [(TAG["Err"], [ret(tag, val)])])      # `match x_tag { Tag::Err => return } ;`
+    t_or_nil = [if_("is_equal_inner", [const("t_tag", TAG["T"]), const("t", 4343), ret("t_tag", "t")]),
+                ret("nil_tag", "is_equal_inner")]
+    equal = func("equal", ["rest_tag", "rest", "env", "eval_first"], 2, [
+        const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]), const("nil_tag", TAG["Nil"]),
+        const("invalid_form", ERR["InvalidForm"]),
+        sub("rest_not_cons", "rest_tag", "cons_tag"),
+        if_("rest_not_cons", [ret("err_tag", "invalid_form")]),
+        load(["exp1_tag", "exp1", "rest_tag", "rest"], "rest"),
+        sub("rest_not_cons", "rest_tag", "cons_tag"),
+        if_("rest_not_cons", [ret("err_tag", "invalid_form")]),
+        load(["exp2_tag", "exp2", "rest_tag", "_rest"], "rest"),
+        sub("rest_not_nil", "rest_tag", "nil_tag"),
+        if_("rest_not_nil", [ret("err_tag", "invalid_form")]),
+        call(["val2_tag", "val2"], "eval", ["exp2_tag", "exp2", "env"]),
+        err_if("val2_tag", "val2"),
+        if_("eval_first", [
+            call(["val1_tag", "val1"], "eval", ["exp1_tag", "exp1", "env"]),
+            err_if("val1_tag", "val1"),
+            call(["is_equal_inner"], "equal_inner", ["val1_tag", "val1", "val2_tag", "val2"])] + t_or_nil),
+        call(["is_equal_inner"], "equal_inner", ["exp1_tag", "exp1", "val2_tag", "val2"])] + t_or_nil, partial=True)
+    invalid_tail = [const("err_tag", TAG["Err"]), const("err", ERR["InvalidForm"]), ret("err_tag", "err")]
+    eval_list = func("eval_list", ["rest_tag", "rest", "env"], 2, [
+        match("rest_tag", [
+            (TAG["Nil"], [ret("rest_tag", "rest")]),
+            (TAG["Cons"], [
+                load(["head_tag", "head", "rest_tag", "rest"], "rest"),
+                call(["head_tag", "head"], "eval", ["head_tag", "head", "env"]),
+                err_if("head_tag", "head"),
+                call(["rest_tag", "rest"], "eval_list", ["rest_tag", "rest", "env"]),
+                err_if("rest_tag", "rest"),
+                const("cons_tag", TAG["Cons"]),
+                store("cons", ["head_tag", "head", "rest_tag", "rest"]),
+                ret("cons_tag", "cons")])])] + invalid_tail, partial=True)
+    eval_begin = func("eval_begin", ["rest_tag", "rest", "env"], 2, [
+        match("rest_tag", [
+            (TAG["Nil"], [ret("rest_tag", "rest")]),
+            (TAG["Cons"], [
+                load(["head_tag", "head", "rest_tag", "rest"], "rest"),
+                call(["head_tag", "head"], "eval", ["head_tag", "head", "env"]),
+                err_if("head_tag", "head"),
+                const("nil_tag", TAG["Nil"]),
+                sub("rest_not_nil", "nil_tag", "rest_tag"),
+                if_("rest_not_nil", [call(["res_tag", "res"], "eval_begin", ["rest_tag", "rest", "env"]), ret("res_tag", "res")]),
+                ret("head_tag", "head")])])] + invalid_tail, partial=True)
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
-                     env_demo], chips)
+                     env_demo, equal, eval_list, eval_begin], chips)
 
 
 def lurk_data_toplevel():

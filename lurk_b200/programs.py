@@ -275,4 +275,45 @@ def lurk_data_toplevel():
         call(["tag", "ptr"], "ingress", ["tag_full", "digest"]),
         call(["out_tag", ("out_digest", 8)], "egress", ["tag", "ptr"]),
         ret("out_tag", "out_digest")])
-    return Toplevel([data_roundtrip, preallocate, ingress, egress, h3, h4, h5], chips)
+    # extend_env_with_mutuals (src/core/eval_direct.rs:1674-1725, width pinned at 54): the environment a `letrec`
+    # evaluates its body in -- every binding (var expr) becomes var -> Fix(expr, all bindings, env).  Total and
+    # self-contained, so it runs for real: `mutuals_demo` ingresses a binding list, extends the empty environment
+    # and egresses the result, whose digest the ZStore can predict.
+    inv = [ret("err_tag", "invalid_form_err")]
+    extend_env_with_mutuals = func("extend_env_with_mutuals", ["binds_tag", "binds", "mutual_binds", "mutual_env"], 2, [
+        const("err_tag", T["Err"]), const("env_tag", T["Env"]), const("invalid_form_err", 1),   # EvalErr::InvalidForm
+        match("binds_tag", [
+            (T["Nil"], [ret("env_tag", "mutual_env")]),
+            (T["Cons"], [
+                const("cons_tag", T["Cons"]),
+                load(["binding_tag", "binding", "binds_tag", "binds"], "binds"),
+                sub("binding_not_cons", "binding_tag", "cons_tag"),
+                if_("binding_not_cons", inv),
+                load(["var_tag", "var", "rest_tag", "rest"], "binding"),
+                sub("rest_tag_not_cons", "rest_tag", "cons_tag"),
+                if_("rest_tag_not_cons", inv),
+                load(["expr_tag", "expr", "rest_tag", "_rest"], "rest"),
+                const("nil_tag", T["Nil"]),
+                sub("rest_tag_not_nil", "rest_tag", "nil_tag"),
+                if_("rest_tag_not_nil", inv),
+                match("var_tag", [
+                    ((T["Sym"], T["Builtin"], T["Coroutine"]), [
+                        call(["ext_env_tag", "ext_env"], "extend_env_with_mutuals",
+                             ["binds_tag", "binds", "mutual_binds", "mutual_env"]),
+                        match("ext_env_tag", [(T["Err"], [ret("ext_env_tag", "ext_env")])]),
+                        const("fix_tag", T["Fix"]),
+                        store("fix", ["expr_tag", "expr", "cons_tag", "mutual_binds", "mutual_env"]),
+                        store("res_env", ["var_tag", "var", "fix_tag", "fix", "ext_env"]),
+                        ret("env_tag", "res_env")])]),
+                const("illegal_binding_var_err", 2),                                            # EvalErr::IllegalBindingVar
+                ret("err_tag", "illegal_binding_var_err")])]),
+        ret("err_tag", "invalid_form_err")])
+    mutuals_demo = func("mutuals_demo", [("tag_full", 8), ("digest", 8)], 9, [
+        call(["nil_ptr", "t_ptr"], "preallocate", []),
+        call(["binds_tag", "binds"], "ingress", ["tag_full", "digest"]),
+        const("empty_env", 0),
+        call(["env_tag", "env"], "extend_env_with_mutuals", ["binds_tag", "binds", "binds", "empty_env"]),
+        call(["out_tag", ("out_digest", 8)], "egress", ["env_tag", "env"]),
+        ret("out_tag", "out_digest")])
+    return Toplevel([data_roundtrip, preallocate, ingress, egress, h3, h4, h5, extend_env_with_mutuals, mutuals_demo],
+                    chips)

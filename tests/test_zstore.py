@@ -74,3 +74,29 @@ def test_ingress_rejects_a_digest_without_preimage():
     q = QueryRecord.new(top)
     with pytest.raises(LurkStarkError, match="Preimg not found"):
         execute_by_name(top, "data_roundtrip", [TAG["Cons"]] + [0] * 7 + [1, 2, 3, 4, 5, 6, 7, 8], q)
+
+
+def test_extend_env_with_mutuals_builds_the_letrec_environment(oracle):
+    # src/core/eval_direct.rs:1674-1725 restated (width pinned at 54, eval_direct.rs:2041): for bindings
+    # ((f e1) (g e2)) the result is Env(f, Fix(e1, binds, env0), Env(g, Fix(e2, binds, env0), env0)) -- the ZStore
+    # predicts its digest; the func runs on data ingressed from content-addressed form
+    top = goldens.toplevel_for("lurk_data")
+    assert FuncChip.from_name("extend_env_with_mutuals", top).width() == 54
+    z = ZStore()
+    f, g = z.lurk_sym("f"), z.lurk_sym("g")
+    e1, e2 = z.list([z.builtin("cons"), z.num(1), g]), z.num(42)
+    binds = z.list([z.list([f, e1]), z.list([g, e2])])
+    env0 = z.null(TAG["Env"])
+    fix = lambda e: z.tuple110(TAG["Fix"], e, binds, env0)
+    want = z.tuple110(TAG["Env"], f, fix(e1), z.tuple110(TAG["Env"], g, fix(e2), env0))
+    args = [binds.tag] + [0] * 7 + list(binds.digest)
+    q = QueryRecord.new(top)
+    z.inject(q, top)
+    out = [int(v) for v in execute_by_name(top, "mutuals_demo", args, q)]
+    assert out == [TAG["Env"]] + list(want.digest)
+    # malformed bindings: (f) has no expression -> (Err, InvalidForm); a number as variable -> (Err, IllegalBindingVar)
+    for bad, err in ((z.list([z.list([f])]), 1), (z.list([z.list([z.num(3), e2])]), 2)):
+        q = QueryRecord.new(top)
+        z.inject(q, top)
+        out = [int(v) for v in execute_by_name(top, "mutuals_demo", [bad.tag] + [0] * 7 + list(bad.digest), q)]
+        assert out == [TAG["Err"], err] + [0] * 7

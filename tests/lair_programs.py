@@ -334,8 +334,63 @@ def lurk_eval_subset_toplevel():
                 sub("rest_not_nil", "nil_tag", "rest_tag"),
                 if_("rest_not_nil", [call(["res_tag", "res"], "eval_begin", ["rest_tag", "rest", "env"]), ret("res_tag", "res")]),
                 ret("head_tag", "head")])])] + invalid_tail, partial=True)
+    # eval_direct.rs:1614-1672 (eval_let), 1727-1751 (eval_letrec_bindings), 1753-1775 (eval_letrec); the callee
+    # extend_env_with_mutuals is a stub here (the real one lives in lurk_b200/programs.py::lurk_data_toplevel)
+    from lurk_b200.lair import assert_eq
+    mutuals_stub = func("extend_env_with_mutuals", ["binds_tag", "binds", "mutual_binds", "mutual_env"], 2,
+                        [ret("binds_tag", "mutual_env")])
+    inv2 = [ret("err_tag", "invalid_form")]
+    eval_let = func("eval_let", ["binds_tag", "binds", "body_tag", "body", "env"], 2, [
+        const("err_tag", TAG["Err"]), const("invalid_form", ERR["InvalidForm"]),
+        match("binds_tag", [
+            (TAG["Nil"], [call(["res_tag", "res"], "eval_begin", ["body_tag", "body", "env"]), ret("res_tag", "res")]),
+            (TAG["Cons"], [
+                const("cons_tag", TAG["Cons"]), const("nil_tag", TAG["Nil"]),
+                load(["bind_tag", "bind", "rest_binds_tag", "rest_binds"], "binds"),
+                sub("bind_not_cons", "bind_tag", "cons_tag"),
+                if_("bind_not_cons", inv2),
+                load(["param_tag", "param", "rest_tag", "rest"], "bind"),
+                sub("rest_not_cons", "rest_tag", "cons_tag"),
+                if_("rest_not_cons", inv2),
+                match("param_tag", [
+                    ((TAG["Sym"], TAG["Builtin"], TAG["Coroutine"]), [
+                        load(["expr_tag", "expr", "rest_tag", "_rest"], "rest"),
+                        sub("rest_not_nil", "rest_tag", "nil_tag"),
+                        if_("rest_not_nil", inv2),
+                        call(["val_tag", "val"], "eval", ["expr_tag", "expr", "env"]),
+                        err_if("val_tag", "val"),
+                        store("ext_env", ["param_tag", "param", "val_tag", "val", "env"]),
+                        sub("rest_binds_not_nil", "nil_tag", "rest_binds_tag"),
+                        if_("rest_binds_not_nil", [
+                            call(["res_tag", "res"], "eval_let", ["rest_binds_tag", "rest_binds", "body_tag", "body", "ext_env"]),
+                            ret("res_tag", "res")]),
+                        call(["res_tag", "res"], "eval_begin", ["body_tag", "body", "ext_env"]),
+                        ret("res_tag", "res")])]),
+                const("err", 2),                                   # EvalErr::IllegalBindingVar
+                ret("err_tag", "err")])]),
+        ret("err_tag", "invalid_form")], partial=True)
+    eval_letrec_bindings = func("eval_letrec_bindings", ["init_env", "ext_env"], 2, [
+        sub("not_eq", "ext_env", "init_env"),
+        if_("not_eq", [
+            load(["_var_tag", "_var", "val_tag", "val", "ext_env"], "ext_env"),
+            const("fix_tag", TAG["Fix"]),
+            assert_eq("fix_tag", "val_tag"),
+            const("nil_env", 0),
+            call(["res_tag", "res"], "eval", ["val_tag", "val", "nil_env"]),
+            err_if("res_tag", "res"),
+            call(["res_tag", "res"], "eval_letrec_bindings", ["init_env", "ext_env"]),
+            ret("res_tag", "res")],
+            [const("env_tag", TAG["Env"]), ret("env_tag", "init_env")])], partial=True)
+    eval_letrec = func("eval_letrec", ["binds_tag", "binds", "body_tag", "body", "env"], 2, [
+        call(["ext_env_tag", "ext_env"], "extend_env_with_mutuals", ["binds_tag", "binds", "binds", "env"]),
+        err_if("ext_env_tag", "ext_env"),
+        call(["res_tag", "res"], "eval_letrec_bindings", ["env", "ext_env"]),
+        err_if("res_tag", "res"),
+        call(["res_tag", "res"], "eval_begin", ["body_tag", "body", "ext_env"]),
+        ret("res_tag", "res")], partial=True)
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
-                     env_demo, equal, eval_list, eval_begin], chips)
+                     env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec],
+                    chips)
 
 
 def lurk_data_toplevel():

@@ -178,8 +178,8 @@ ERR = dict(UnboundVar=0, InvalidForm=1, NotCons=12)
 
 def lurk_eval_subset_toplevel():
     """coerce_if_sym (eval_direct.rs:903-915), open_comm (:917-930), car_cdr (:932-977) and equal_inner (:1032-1115),
-    statement for statement; `eval` and `ingress` are STUBS with the reference's signatures (partial fn eval(expr_tag,
-    expr, env): [2], fn ingress(tag_full: [8], digest: [8]): [2]) -- a func's layout depends on its own body and on
+    statement for statement; `ingress`, `eval_builtin_expr`, `eval_coroutine_expr` and `apply` are STUBS with the
+    reference's signatures (e.g. fn ingress(tag_full: [8], digest: [8]): [2]) -- a func's layout depends on its own body and on
     its callees' signatures only.  The reference pins the widths 9, 50, 61, 58 and, for env_lookup (:1937-1956), 52
     (eval_direct.rs:2044-2050)."""
     from lurk_b200.lair import (ChipInfo, Toplevel, call, const, func, if_, load, match, mul, preimg, ret, sub)
@@ -188,7 +188,44 @@ def lurk_eval_subset_toplevel():
              ChipInfo("hasher5", 40, 8, 763, 0, kind=3)] + U64_CHIPS
     from lurk_b200.lair import extern_call
     hash3 = func("hash3", [("preimg", 24)], 8, [extern_call([("img", 8)], "hasher3", ["preimg"]), ret("img")], invertible=True)
-    eval_stub = func("eval", ["expr_tag", "expr", "env"], 2, [ret("expr_tag", "expr")], partial=True)
+    # eval itself (eval_direct.rs:386-441), statement for statement; its three big callees are stubs with the
+    # reference's signatures
+    def stub(name, params):
+        return func(name, params, 2, [ret(params[0], params[1])], partial=True)
+    builtin_stub = stub("eval_builtin_expr", ["head", "rest_tag", "rest", "env"])
+    coroutine_stub = stub("eval_coroutine_expr", ["head", "args_tag", "args", "env"])
+    apply_stub = stub("apply", ["head_tag", "head", "args_tag", "args", "env"])
+    eval_stub = func("eval", ["expr_tag", "expr", "env"], 2, [
+        match("expr_tag", [
+            ((TAG["Builtin"], TAG["Sym"], TAG["Coroutine"]), [
+                load([("expr_digest", 8)], "expr"),
+                call(["res_tag", "res"], "env_lookup", ["expr_tag", "expr_digest", "env"]),
+                match("res_tag", [(TAG["Fix"], [const("nil_env", 0),
+                                                call(["res_tag", "res"], "eval", ["res_tag", "res", "nil_env"]),
+                                                ret("res_tag", "res")])]),
+                ret("res_tag", "res")]),
+            (TAG["Cons"], [
+                load(["head_tag", "head", "rest_tag", "rest"], "expr"),
+                match("head_tag", [
+                    (TAG["Builtin"], [call(["res_tag", "res"], "eval_builtin_expr", ["head", "rest_tag", "rest", "env"]),
+                                      ret("res_tag", "res")]),
+                    (TAG["Coroutine"], [call(["res_tag", "res"], "eval_coroutine_expr", ["head", "rest_tag", "rest", "env"]),
+                                        ret("res_tag", "res")])]),
+                call(["head_tag", "head"], "eval", ["head_tag", "head", "env"]),
+                match("head_tag", [
+                    ((TAG["BigNum"], TAG["Comm"]), [
+                        call(["head_tag", "head"], "open_comm", ["head"]),
+                        call(["res_tag", "res"], "apply", ["head_tag", "head", "rest_tag", "rest", "env"]),
+                        ret("res_tag", "res")]),
+                    (TAG["Err"], [ret("head_tag", "head")])]),
+                call(["res_tag", "res"], "apply", ["head_tag", "head", "rest_tag", "rest", "env"]),
+                ret("res_tag", "res")]),
+            (TAG["Fix"], [
+                load(["body_tag", "body", "binds_tag", "binds", "mutual_env"], "expr"),
+                call(["_tag", "ext_env"], "extend_env_with_mutuals", ["binds_tag", "binds", "binds", "mutual_env"]),
+                call(["res_tag", "res"], "eval", ["body_tag", "body", "ext_env"]),
+                ret("res_tag", "res")])]),
+        ret("expr_tag", "expr")], partial=True)
     ingress_stub = func("ingress", [("tag_full", 8), ("digest", 8)], 2, [const("z", 0), ret("z", "z")])
 
     coerce_if_sym = func("coerce_if_sym", ["tag"], 1, [
@@ -389,8 +426,8 @@ def lurk_eval_subset_toplevel():
         call(["res_tag", "res"], "eval_begin", ["body_tag", "body", "ext_env"]),
         ret("res_tag", "res")], partial=True)
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
-                     env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec],
-                    chips)
+                     env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
+                     builtin_stub, coroutine_stub, apply_stub], chips)
 
 
 def lurk_data_toplevel():

@@ -178,11 +178,12 @@ ERR = dict(UnboundVar=0, InvalidForm=1, NotCons=12)
 
 def lurk_eval_subset_toplevel():
     """coerce_if_sym (eval_direct.rs:903-915), open_comm (:917-930), car_cdr (:932-977) and equal_inner (:1032-1115),
-    statement for statement; `ingress`, `eval_builtin_expr`, `eval_coroutine_expr` and `apply` are STUBS with the
+    statement for statement; `ingress`, `eval_builtin_expr` and `eval_coroutine_expr` are STUBS with the
     reference's signatures (e.g. fn ingress(tag_full: [8], digest: [8]): [2]) -- a func's layout depends on its own body and on
     its callees' signatures only.  The reference pins the widths 9, 50, 61, 58 and, for env_lookup (:1937-1956), 52
     (eval_direct.rs:2044-2050)."""
-    from lurk_b200.lair import (ChipInfo, Toplevel, call, const, func, if_, load, match, mul, preimg, ret, sub)
+    from lurk_b200.lair import (ChipInfo, Toplevel, array, assert_eq, call, const, func, if_, load, match, mul, preimg, ret,
+                                slice_, store, sub)
     from lurk_b200.programs import U64_CHIPS
     chips = [ChipInfo("hasher3", 24, 8, 457, 0, kind=1), ChipInfo("hasher4", 32, 8, 611, 0, kind=2),
              ChipInfo("hasher5", 40, 8, 763, 0, kind=3)] + U64_CHIPS
@@ -194,7 +195,57 @@ def lurk_eval_subset_toplevel():
         return func(name, params, 2, [ret(params[0], params[1])], partial=True)
     builtin_stub = stub("eval_builtin_expr", ["head", "rest_tag", "rest", "env"])
     coroutine_stub = stub("eval_coroutine_expr", ["head", "args_tag", "args", "env"])
-    apply_stub = stub("apply", ["head_tag", "head", "args_tag", "args", "env"])
+    # apply (eval_direct.rs:1777-1935), statement for statement ("&rest" and nil pointers: any constants here)
+    E = dict(ApplyNonFunc=3, ParamsNotList=4, ParamInvalidRest=6, ArgsNotList=7, IllegalBindingVar=2)
+    SYMS = (TAG["Sym"], TAG["Builtin"], TAG["Coroutine"])
+    err = lambda name: [const("err", E[name]), ret("err_tag", "err")]
+    err_if_ = lambda tag, val: match(tag, [(TAG["Err"], [ret(tag, val)])])
+
+    def apply_block():      # the "DUPLICATED APPLY BLOCK"
+        return [match("args_tag", [
+            (TAG["Nil"], [ret("head_tag", "head")]),
+            (TAG["Cons"], [
+                load(["arg_tag", "arg", "rest_args_tag", "rest_args"], "args"),
+                match("param_tag", [(SYMS, [
+                    call(["arg_tag", "arg"], "eval", ["arg_tag", "arg", "args_env"]),
+                    err_if_("arg_tag", "arg"),
+                    store("ext_env", ["param_tag", "param", "arg_tag", "arg", "func_env"]),
+                    store("ext_fun", ["rest_params_tag", "rest_params", "body_tag", "body", "ext_env"]),
+                    call(["res_tag", "res"], "apply", ["fun_tag", "ext_fun", "rest_args_tag", "rest_args", "args_env"]),
+                    ret("res_tag", "res")])])] + err("IllegalBindingVar"))])] + err("ArgsNotList")
+
+    rest_var = [match("rest_params_tag", [
+        (TAG["Nil"], err("ParamInvalidRest")),
+        (TAG["Cons"], [
+            load(["param_tag", "param", "rest_params_tag", "rest_params"], "rest_params"),
+            match("param_tag", [(SYMS, [
+                match("rest_params_tag", [(TAG["Nil"], [
+                    call(["arg_tag", "arg"], "eval_list", ["args_tag", "args", "args_env"]),
+                    err_if_("arg_tag", "arg"),
+                    store("ext_env", ["param_tag", "param", "arg_tag", "arg", "func_env"]),
+                    store("ext_fun", ["rest_params_tag", "rest_params", "body_tag", "body", "ext_env"]),
+                    const("nil_tag", TAG["Nil"]), const("nil", 4242),
+                    call(["res_tag", "res"], "apply", ["fun_tag", "ext_fun", "nil_tag", "nil", "args_env"]),
+                    ret("res_tag", "res")])])] + err("ParamInvalidRest"))])] + err("IllegalBindingVar"))])] + err("ParamsNotList")
+    apply_stub = func("apply", ["head_tag", "head", "args_tag", "args", "args_env"], 2, [
+        const("err_tag", TAG["Err"]), const("fun_tag", TAG["Fun"]),
+        sub("head_not_fun", "head_tag", "fun_tag"),
+        if_("head_not_fun", err("ApplyNonFunc")),
+        load(["params_tag", "params", "body_tag", "body", "func_env"], "head"),
+        match("params_tag", [
+            (TAG["Nil"], [
+                call(["res_tag", "res"], "eval_begin", ["body_tag", "body", "func_env"]),
+                err_if_("res_tag", "res"),
+                match("args_tag", [
+                    (TAG["Nil"], [ret("res_tag", "res")]),
+                    (TAG["Cons"], [call(["app_res_tag", "app_res"], "apply", ["res_tag", "res", "args_tag", "args", "args_env"]),
+                                   ret("app_res_tag", "app_res")])])] + err("ArgsNotList")),
+            (TAG["Cons"], [
+                load(["param_tag", "param", "rest_params_tag", "rest_params"], "params"),
+                match("param_tag", [(SYMS, [
+                    const("rest_sym", 4444),
+                    sub("is_not_rest_sym", "param", "rest_sym"),
+                    if_("is_not_rest_sym", apply_block(), rest_var)])])] + apply_block())])] + err("ParamsNotList"), partial=True)
     eval_stub = func("eval", ["expr_tag", "expr", "env"], 2, [
         match("expr_tag", [
             ((TAG["Builtin"], TAG["Sym"], TAG["Coroutine"]), [
@@ -300,7 +351,6 @@ def lurk_eval_subset_toplevel():
             ], exhaustive=True)],
             [ret("one")])])
     # eval_direct.rs:1937-1956: `if !env {..}`, a 5-word load, `let y_tag_digest: [9] = (y_tag, y_digest)` (OpE::Slice)
-    from lurk_b200.lair import slice_
     env_lookup = func("env_lookup", [("x_tag_digest", 9), "env"], 2, [
         if_("env", [
             load(["y_tag", "y", "val_tag", "val", "tail_env"], "env"),
@@ -314,7 +364,6 @@ def lurk_eval_subset_toplevel():
             [const("err_tag", TAG["Err"]), const("err", ERR["UnboundVar"]), ret("err_tag", "err")])])
     # driver: an environment ((a . 7) (b . 9)) built in memory the way the evaluator lays it out -- entries
     # (sym_tag, sym_ptr, val_tag, val, tail_env), symbols as pointers to 8-word digests -- then env_lookup
-    from lurk_b200.lair import array, store
     env_demo = func("env_demo", ["x_tag", ("x_digest", 8)], 2, [
         array("da", list(range(1, 9))), store("pa", ["da"]),
         array("db", list(range(9, 17))), store("pb", ["db"]),
@@ -373,7 +422,6 @@ def lurk_eval_subset_toplevel():
                 ret("head_tag", "head")])])] + invalid_tail, partial=True)
     # eval_direct.rs:1614-1672 (eval_let), 1727-1751 (eval_letrec_bindings), 1753-1775 (eval_letrec); the callee
     # extend_env_with_mutuals is a stub here (the real one lives in lurk_b200/programs.py::lurk_data_toplevel)
-    from lurk_b200.lair import assert_eq
     mutuals_stub = func("extend_env_with_mutuals", ["binds_tag", "binds", "mutual_binds", "mutual_env"], 2,
                         [ret("binds_tag", "mutual_env")])
     inv2 = [ret("err_tag", "invalid_form")]

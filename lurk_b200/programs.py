@@ -165,6 +165,9 @@ def lurk_misc_toplevel():
                      big_num_lessthan, u64_demo], chips)
 
 
+LURK_DATA_SYMBOL_PTRS = {"nil": 1, "t": 2, "&rest": 3}   # what `preallocate` of lurk_data_toplevel stores first
+
+
 LURK_MISC_WIDTHS = {"hash3": 493, "hash4": 655, "hash5": 815, "u64_add": 53, "u64_sub": 53, "u64_mul": 85,
                     "u64_divrem": 166, "u64_lessthan": 44, "u64_iszero": 26, "digest_equal": 38,
                     "big_num_lessthan": 78}     # src/core/eval_direct.rs:2053-2063
@@ -183,7 +186,8 @@ def lurk_data_toplevel():
     T = dict(TAG, Nil=15, T=16)
     z = ZStore()
     nil_digest, t_digest = list(z.nil().digest), list(z.t().digest)
-    NIL_PTR, T_PTR = 1, 2
+    rest_digest = list(z.lurk_sym("&rest").digest)
+    NIL_PTR, T_PTR = 1, 2          # and &rest at 3 (LURK_DATA_SYMBOL_PTRS below)
     chips = [ChipInfo("hasher3", 24, 8, 457, 0, kind=1), ChipInfo("hasher4", 32, 8, 611, 0, kind=2),
              ChipInfo("hasher5", 40, 8, 763, 0, kind=3)]
     h3 = func("hash3", [("preimg", 24)], 8, [extern_call([("img", 8)], "hasher3", ["preimg"]), ret("img")], invertible=True)
@@ -264,12 +268,13 @@ def lurk_data_toplevel():
             (T["Env"], [if_("val", triple_out("tag", []), [array("digest", [0] * 8), ret("tag", "digest")])]),
         ], exhaustive=True)])
 
-    preallocate = func("preallocate", [], 2, [
+    preallocate = func("preallocate", [], 3, [
         array("nil_digest", nil_digest), store("nil_ptr", ["nil_digest"]),
         array("t_digest", t_digest), store("t_ptr", ["t_digest"]),
-        ret("nil_ptr", "t_ptr")])
+        array("rest_digest", rest_digest), store("rest_ptr", ["rest_digest"]),
+        ret("nil_ptr", "t_ptr", "rest_ptr")])
     data_roundtrip = func("data_roundtrip", [("tag_full", 8), ("digest", 8)], 9, [
-        call(["nil_ptr", "t_ptr"], "preallocate", []),
+        call(["nil_ptr", "t_ptr", "rest_ptr"], "preallocate", []),
         const("one", NIL_PTR), const("two", T_PTR),
         assert_eq("nil_ptr", "one"), assert_eq("t_ptr", "two"),
         call(["tag", "ptr"], "ingress", ["tag_full", "digest"]),
@@ -309,7 +314,7 @@ def lurk_data_toplevel():
                 ret("err_tag", "illegal_binding_var_err")])]),
         ret("err_tag", "invalid_form_err")])
     mutuals_demo = func("mutuals_demo", [("tag_full", 8), ("digest", 8)], 9, [
-        call(["nil_ptr", "t_ptr"], "preallocate", []),
+        call(["nil_ptr", "t_ptr", "rest_ptr"], "preallocate", []),
         call(["binds_tag", "binds"], "ingress", ["tag_full", "digest"]),
         const("empty_env", 0),
         call(["env_tag", "env"], "extend_env_with_mutuals", ["binds_tag", "binds", "binds", "empty_env"]),

@@ -176,7 +176,7 @@ TAG = dict(U64=0, Num=1, BigNum=2, Comm=3, Char=4, Str=5, Key=6, Fun=7, Builtin=
 ERR = dict(UnboundVar=0, InvalidForm=1, NotCons=12)
 
 
-def lurk_eval_subset_toplevel():
+def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
     """coerce_if_sym (eval_direct.rs:903-915), open_comm (:917-930), car_cdr (:932-977) and equal_inner (:1032-1115),
     statement for statement; `ingress`, `eval_builtin_expr` and `eval_coroutine_expr` are STUBS with the
     reference's signatures (e.g. fn ingress(tag_full: [8], digest: [8]): [2]) -- a func's layout depends on its own body and on
@@ -224,7 +224,7 @@ def lurk_eval_subset_toplevel():
                     err_if_("arg_tag", "arg"),
                     store("ext_env", ["param_tag", "param", "arg_tag", "arg", "func_env"]),
                     store("ext_fun", ["rest_params_tag", "rest_params", "body_tag", "body", "ext_env"]),
-                    const("nil_tag", TAG["Nil"]), const("nil", 4242),
+                    const("nil_tag", TAG["Nil"]), const("nil", nil_ptr),
                     call(["res_tag", "res"], "apply", ["fun_tag", "ext_fun", "nil_tag", "nil", "args_env"]),
                     ret("res_tag", "res")])])] + err("ParamInvalidRest"))])] + err("IllegalBindingVar"))])] + err("ParamsNotList")
     apply_stub = func("apply", ["head_tag", "head", "args_tag", "args", "args_env"], 2, [
@@ -243,7 +243,7 @@ def lurk_eval_subset_toplevel():
             (TAG["Cons"], [
                 load(["param_tag", "param", "rest_params_tag", "rest_params"], "params"),
                 match("param_tag", [(SYMS, [
-                    const("rest_sym", 4444),
+                    const("rest_sym", rest_ptr),
                     sub("is_not_rest_sym", "param", "rest_sym"),
                     if_("is_not_rest_sym", apply_block(), rest_var)])])] + apply_block())])] + err("ParamsNotList"), partial=True)
     eval_stub = func("eval", ["expr_tag", "expr", "env"], 2, [
@@ -291,7 +291,7 @@ def lurk_eval_subset_toplevel():
 
     invalid = [ret("err_tag", "invalid_form", "err_tag", "invalid_form")]
     car_cdr = func("car_cdr", ["rest_tag", "rest", "env"], 4, [
-        const("nil", 4242),                       # digests.lurk_symbol_ptr("nil"): a ZStore pointer, any constant here
+        const("nil", nil_ptr),                    # digests.lurk_symbol_ptr("nil"): the preallocated pointer
         const("nil_tag", TAG["Nil"]), const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]),
         const("invalid_form", ERR["InvalidForm"]),
         sub("rest_not_cons", "rest_tag", "cons_tag"),
@@ -376,7 +376,7 @@ def lurk_eval_subset_toplevel():
     # eval_direct.rs:979-1030, 1118-1182: three partial funcs around `eval` (names are re-bound the way the reference's
     # `let (head_tag, head) = call(eval, head_tag, head, env)` shadows them)
     err_if = lambda tag, val: match(tag, [(TAG["Err"], [ret(tag, val)])])      # `match x_tag { Tag::Err => return } ;`
-    t_or_nil = [if_("is_equal_inner", [const("t_tag", TAG["T"]), const("t", 4343), ret("t_tag", "t")]),
+    t_or_nil = [if_("is_equal_inner", [const("t_tag", TAG["T"]), const("t", t_ptr), ret("t_tag", "t")]),
                 ret("nil_tag", "is_equal_inner")]
     equal = func("equal", ["rest_tag", "rest", "env", "eval_first"], 2, [
         const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]), const("nil_tag", TAG["Nil"]),
@@ -481,3 +481,30 @@ def lurk_eval_subset_toplevel():
 def lurk_data_toplevel():
     from lurk_b200.programs import lurk_data_toplevel as u
     return u()
+
+
+def lurk_core_toplevel():
+    """The restated evaluator put together: data path (preallocate, ingress, egress, hash3/4/5, extend_env_with_mutuals:
+    lurk_b200/programs.py::lurk_data_toplevel) + evaluator core (eval, apply, eval_begin, eval_list, env_lookup, eval_let,
+    eval_letrec*, equal*, car_cdr, open_comm, coerce_if_sym: above, with the real preallocated pointers) -- everything
+    except the built-in operator family, whose two entry points answer (Err, Todo).  `lurk_eval_demo(expr)` =
+    preallocate, ingress, eval in the empty environment, egress: a builtin-free Lurk expression evaluated for real."""
+    from lurk_b200.lair import Toplevel, call, const, func, ret
+    from lurk_b200.programs import LURK_DATA_SYMBOL_PTRS as PTR, lurk_data_toplevel as data_toplevel
+    data = data_toplevel()
+    ev = lurk_eval_subset_toplevel(PTR["nil"], PTR["t"], PTR["&rest"])
+    take = lambda top, names: [f for f in top.funcs_e if f.name in names]
+    todo = [const("err_tag", TAG["Err"]), const("todo", 21), ret("err_tag", "todo")]            # EvalErr::Todo
+    stubs = [func("eval_builtin_expr", ["head", "rest_tag", "rest", "env"], 2, todo, partial=True),
+             func("eval_coroutine_expr", ["head", "args_tag", "args", "env"], 2, todo, partial=True)]
+    demo = func("lurk_eval_demo", [("tag_full", 8), ("digest", 8)], 9, [
+        call(["nil_ptr", "t_ptr", "rest_ptr"], "preallocate", []),
+        call(["tag", "ptr"], "ingress", ["tag_full", "digest"]),
+        const("empty_env", 0),
+        call(["res_tag", "res"], "eval", ["tag", "ptr", "empty_env"]),
+        call(["out_tag", ("out_digest", 8)], "egress", ["res_tag", "res"]),
+        ret("out_tag", "out_digest")], partial=True)
+    funcs = ([demo] + take(data, {"preallocate", "ingress", "egress", "hash3", "hash4", "hash5", "extend_env_with_mutuals"})
+             + take(ev, {"eval", "apply", "env_lookup", "eval_begin", "eval_list", "eval_let", "eval_letrec",
+                         "eval_letrec_bindings", "equal", "equal_inner", "car_cdr", "open_comm", "coerce_if_sym"}) + stubs)
+    return Toplevel(funcs, data.chips)

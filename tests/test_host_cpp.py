@@ -12,7 +12,7 @@ from lurk_b200.air import build_chip_vector, serialize_machine
 from lurk_b200.lair import DEPTH_W, FuncChip, Toplevel, call, func, ret
 
 TOPLEVELS = ["demo", "match", "inner_match", "not_eq", "if_many", "match_many", "assert", "equal_branch", "range",
-             "memory", "ackermann", "hash", "partial", "u64", "lurk_misc", "lurk_eval_subset", "lurk_data"]
+             "memory", "ackermann", "hash", "partial", "u64", "lurk_misc", "lurk_eval_subset", "lurk_data", "lurk_core"]
 
 
 @pytest.fixture(scope="module", autouse=True)

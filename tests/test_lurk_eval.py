@@ -1,0 +1,108 @@
+"""Builtin-free Lurk expressions evaluated by the restated evaluator (tests/lair_programs.py::lurk_core_toplevel: the
+reference's eval / apply / eval_begin / eval_list / env_lookup / ingress / egress, statement for statement): the
+expression is interned by the ZStore, ingressed, evaluated in the empty environment, egressed, and the result must be
+the ZPtr Lurk's semantics give.  Functions are written as literal Fun objects (the `lambda` builtin is not restated)."""
+import pytest
+
+import goldens
+from lurk_b200.execute import QueryRecord, execute_by_name
+from lurk_b200.zstore import TAG, ZStore
+
+ERR = dict(UnboundVar=0, ApplyNonFunc=3, ArgsNotList=7, Todo=21)
+
+
+def _cases(z):
+    x, y, r, rest = z.lurk_sym("x"), z.lurk_sym("y"), z.lurk_sym("r"), z.lurk_sym("&rest")
+    env0 = z.null(TAG["Env"])
+    fun = lambda params, body, env=env0: z.tuple110(TAG["Fun"], z.list(params), z.list(body), env)
+    second = fun([x, y], [y])                 # (lambda (x y) y)
+    err = lambda e: (TAG["Err"], [e] + [0] * 7)
+    zp = lambda p: (p.tag, list(p.digest))
+    return {
+        "a number evaluates to itself": (z.num(5), zp(z.num(5))),
+        "a string evaluates to itself": (z.string("hi"), zp(z.string("hi"))),
+        "nil evaluates to itself": (z.nil(), zp(z.nil())),
+        "unbound variable": (x, err(ERR["UnboundVar"])),
+        "saturated application": (z.list([second, z.num(5), z.u64(7)]), zp(z.u64(7))),
+        "the body is a sequence": (z.list([fun([x], [z.num(1), z.num(2), x]), z.num(9)]), zp(z.num(9))),
+        "undersaturated application returns a closure":
+            (z.list([second, z.num(5)]), zp(fun([y], [y], z.tuple110(TAG["Env"], x, z.num(5), env0)))),
+        "oversaturated application":                      # ((lambda (x) (lambda (y) y)) 1 2) with the inner one literal
+            (z.list([fun([x], [fun([y], [y])]), z.num(1), z.num(2)]), zp(z.num(2))),
+        "&rest collects the remaining arguments":
+            (z.list([fun([rest, r], [r]), z.num(1), z.num(2), z.num(3)]), zp(z.list([z.num(1), z.num(2), z.num(3)]))),
+        "nested application in an argument":
+            (z.list([second, z.num(0), z.list([second, z.num(1), z.string("ok")])]), zp(z.string("ok"))),
+        "applying a number": (z.list([z.num(5), z.num(1)]), err(ERR["ApplyNonFunc"])),
+        "an error in an argument propagates": (z.list([second, x, z.num(1)]), err(ERR["UnboundVar"])),
+        "a fixed point evaluates its body in the extended environment":    # Fix(body = f, binds = ((f 42)), env0)
+            (z.tuple110(TAG["Fix"], z.lurk_sym("f"), z.list([z.list([z.lurk_sym("f"), z.num(42)])]), env0), zp(z.num(42))),
+        "builtins are not restated yet": (z.list([z.builtin("cons"), z.num(1), z.num(2)]), err(ERR["Todo"])),
+    }
+
+
+CASE_NAMES = list(_cases(ZStore()).keys())
+
+
+def run(top, z, expr):
+    q = QueryRecord.new(top)
+    z.inject(q, top)
+    out = [int(v) for v in execute_by_name(top, "lurk_eval_demo", [expr.tag] + [0] * 7 + list(expr.digest), q)]
+    return q, (out[0], out[1:])
+
+
+@pytest.mark.parametrize("name", CASE_NAMES)
+def test_builtin_free_expressions_evaluate(name):
+    top = goldens.toplevel_for("lurk_core")
+    z = ZStore()
+    expr, want = _cases(z)[name]
+    _, got = run(top, z, expr)
+    assert got == (want[0], list(want[1])), name
+
+
+def _oracle_record(oracle, top, z, expr):
+    ot = oracle.OracleToplevel(top.serialize())
+    rec = oracle.OracleRecord(ot)
+    for name, width in (("hash3", 24), ("hash4", 32), ("hash5", 40)):
+        if z.hashes[width]:
+            rec.inject_inv_queries(top.func_by_name(name).index, [list(k) for k in z.hashes[width]],
+                                   [list(v) for v in z.hashes[width].values()])
+    f = top.func_by_name("lurk_eval_demo")
+    out = rec.execute(f.index, [expr.tag] + [0] * 7 + list(expr.digest), f.output_size)
+    return ot, rec, f, [int(v) for v in out]
+
+
+@pytest.mark.parametrize("name", ["saturated application", "&rest collects the remaining arguments"])
+def test_evaluation_proves_and_verifies_on_the_oracle(oracle, name):
+    from test_oracle_stark import oracle_machine
+    top = goldens.toplevel_for("lurk_core")
+    z = ZStore()
+    expr, want = _cases(z)[name]
+    ot, rec, f, out = _oracle_record(oracle, top, z, expr)
+    assert (out[0], out[1:]) == (want[0], list(want[1]))
+    _, om, _ = oracle_machine(oracle, top, "lurk_eval_demo")
+    proof = om.prove(rec)
+    assert om.verify(proof), om.last_error
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["saturated application", "&rest collects the remaining arguments",
+                                  "a fixed point evaluates its body in the extended environment"])
+def test_evaluation_proves_bit_exact_on_the_gpu(oracle, name):
+    # the whole path on a real Lurk evaluation: 23 func chips (partial funcs with depth provenance, preimages of
+    # hash4 / hash5, memory of four lengths), the GPU proof equal to the oracle's, accepted by the product verifier
+    import numpy as np
+    from lurk_b200.execute import Shard
+    from lurk_b200.machine import SphinxCoreOpts, new_machine
+    top = goldens.toplevel_for("lurk_core")
+    z = ZStore()
+    expr, want = _cases(z)[name]
+    m = new_machine(top, "lurk_eval_demo", opts=SphinxCoreOpts(num_queries=6, proof_of_work_bits=6))
+    pk, vk = m.setup()
+    q, got = run(top, z, expr)
+    assert got == (want[0], list(want[1]))
+    ot, rec, f, _ = _oracle_record(oracle, top, z, expr)
+    om = oracle.OracleMachine(ot, m.entry.index, m.blob, 6, 6)
+    proof = m.prove(pk, Shard.new(q))
+    assert np.array_equal(proof.words, om.prove(rec))
+    m.verify(vk, proof)

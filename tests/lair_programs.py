@@ -473,9 +473,23 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
         err_if("res_tag", "res"),
         call(["res_tag", "res"], "eval_begin", ["body_tag", "body", "ext_env"]),
         ret("res_tag", "res")], partial=True)
+    # lurk_main (eval_direct.rs:120-138): the entry point -- a call with no outputs, two ingresses, eval, egress
+    pre_stub = func("preallocate_symbols", [], 0, [ret()])
+    egress_stub = func("egress", ["tag", "val"], 9, [array("d", [0] * 8), ret("tag", "d")])
+    lurk_main = func("lurk_main", [("full_expr_tag", 8), ("expr_digest", 8), ("env_digest", 8)], 16, [
+        call([], "preallocate_symbols", []),
+        call(["expr_tag", "expr"], "ingress", ["full_expr_tag", "expr_digest"]),
+        array("padding", [0] * 7),
+        const("env_tag", TAG["Env"]),
+        slice_([("full_env_tag", 8)], ["env_tag", "padding"]),
+        call(["_env_tag", "env"], "ingress", ["full_env_tag", "env_digest"]),
+        call(["val_tag", "val"], "eval", ["expr_tag", "expr", "env"]),
+        call(["val_tag2", ("val_digest", 8)], "egress", ["val_tag", "val"]),
+        slice_([("full_val_tag", 8)], ["val_tag2", "padding"]),
+        ret("full_val_tag", "val_digest")], partial=True)
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
                      env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
-                     builtin_stub, coroutine_stub, apply_stub], chips)
+                     builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main], chips)
 
 
 def lurk_data_toplevel():

@@ -178,7 +178,7 @@ ERR = dict(UnboundVar=0, InvalidForm=1, NotCons=12)
 
 def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
     """coerce_if_sym (eval_direct.rs:903-915), open_comm (:917-930), car_cdr (:932-977) and equal_inner (:1032-1115),
-    statement for statement; `ingress`, `eval_builtin_expr` and `eval_coroutine_expr` are STUBS with the
+    statement for statement; `ingress` and `eval_builtin_expr` are STUBS with the
     reference's signatures (e.g. fn ingress(tag_full: [8], digest: [8]): [2]) -- a func's layout depends on its own body and on
     its callees' signatures only.  The reference pins the widths 9, 50, 61, 58 and, for env_lookup (:1937-1956), 52
     (eval_direct.rs:2044-2050)."""
@@ -194,7 +194,9 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
     def stub(name, params):
         return func(name, params, 2, [ret(params[0], params[1])], partial=True)
     builtin_stub = stub("eval_builtin_expr", ["head", "rest_tag", "rest", "env"])
-    coroutine_stub = stub("eval_coroutine_expr", ["head", "args_tag", "args", "env"])
+    # eval_coroutine_expr when the Lang has no coroutines (eval_direct.rs:196-222): never callable, not partial
+    coroutine_stub = func("eval_coroutine_expr", ["_head", "_args_tag", "_args", "_env"], 2, [
+        const("zero", 0), const("one", 1), assert_eq("zero", "one"), ret("zero", "zero")])
     # apply (eval_direct.rs:1777-1935), statement for statement ("&rest" and nil pointers: any constants here)
     E = dict(ApplyNonFunc=3, ParamsNotList=4, ParamInvalidRest=6, ArgsNotList=7, IllegalBindingVar=2)
     SYMS = (TAG["Sym"], TAG["Builtin"], TAG["Coroutine"])

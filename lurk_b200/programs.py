@@ -165,7 +165,6 @@ def lurk_misc_toplevel():
                      big_num_lessthan, u64_demo], chips)
 
 
-LURK_DATA_SYMBOL_PTRS = {"nil": 1, "t": 2, "&rest": 3}   # what `preallocate` of lurk_data_toplevel stores first
 
 
 LURK_MISC_WIDTHS = {"hash3": 493, "hash4": 655, "hash5": 815, "u64_add": 53, "u64_sub": 53, "u64_mul": 85,
@@ -173,21 +172,29 @@ LURK_MISC_WIDTHS = {"hash3": 493, "hash4": 655, "hash5": 815, "u64_add": 53, "u6
                     "big_num_lessthan": 78}     # src/core/eval_direct.rs:2053-2063
 
 
+# src/core/state.rs:270-316: the native symbols, in the order SymbolsDigests::new interns them (pointer = index + 1)
+LURK_SYMBOLS = ["nil", "t", "&rest"]
+BUILTIN_SYMBOLS = ["atom", "apply", "begin", "car", "cdr", "char", "commit", "comm", "bignum", "cons", "empty-env",
+                   "current-env", "bind", "env", "emit", "eval", "eq", "eqq", "type-eq", "type-eqq", "hide", "if", "lambda",
+                   "let", "letrec", "u64", "open", "quote", "secret", "strcons", "list", "+", "-", "*", "/", "%", "=", "<", ">",
+                   "<=", ">=", "breakpoint", "fail"]
+LURK_SYMBOL_PTRS = {name: i + 1 for i, name in enumerate(LURK_SYMBOLS + BUILTIN_SYMBOLS)}
+
+
 def lurk_data_toplevel():
     """Data in and out of the Lair memory, restated from src/core/ingress.rs:142-329: `ingress(tag_full, digest)`
     turns a content-addressed ZPtr into (tag, pointer) by walking the hash preimages (`preimg(hash4 / hash5, ..)`,
     fed by ZStore.inject) and storing the parts; `egress(tag, ptr)` hashes it back.  nil and t become the
     InternalTags 15 / 16 with the pointers of their preallocated digests (the reference's `preallocate_symbols`
-    stores every built-in symbol first; here `preallocate` stores nil and t, pointers 1 and 2).
-    `data_roundtrip` = preallocate, ingress, egress.  Widths pinned by the reference (eval_direct.rs:2051-2052):
+    stores every native symbol first: restated here too, nil = pointer 1, t = 2).
+    `data_roundtrip` = preallocate_symbols, ingress, egress.  Widths pinned by the reference (eval_direct.rs:2051-2052):
     ingress 104, egress 81."""
     from .lair import assert_eq, if_, preimg, range_u8, slice_
     from .zstore import TAG, ZStore
     T = dict(TAG, Nil=15, T=16)
     z = ZStore()
     nil_digest, t_digest = list(z.nil().digest), list(z.t().digest)
-    rest_digest = list(z.lurk_sym("&rest").digest)
-    NIL_PTR, T_PTR = 1, 2          # and &rest at 3 (LURK_DATA_SYMBOL_PTRS below)
+    NIL_PTR, T_PTR = LURK_SYMBOL_PTRS["nil"], LURK_SYMBOL_PTRS["t"]
     chips = [ChipInfo("hasher3", 24, 8, 457, 0, kind=1), ChipInfo("hasher4", 32, 8, 611, 0, kind=2),
              ChipInfo("hasher5", 40, 8, 763, 0, kind=3)]
     h3 = func("hash3", [("preimg", 24)], 8, [extern_call([("img", 8)], "hasher3", ["preimg"]), ret("img")], invertible=True)
@@ -268,15 +275,16 @@ def lurk_data_toplevel():
             (T["Env"], [if_("val", triple_out("tag", []), [array("digest", [0] * 8), ret("tag", "digest")])]),
         ], exhaustive=True)])
 
-    preallocate = func("preallocate", [], 3, [
-        array("nil_digest", nil_digest), store("nil_ptr", ["nil_digest"]),
-        array("t_digest", t_digest), store("t_ptr", ["t_digest"]),
-        array("rest_digest", rest_digest), store("rest_ptr", ["rest_digest"]),
-        ret("nil_ptr", "t_ptr", "rest_ptr")])
+    # preallocate_symbols (src/core/ingress.rs:114-140): every native symbol's digest is stored first, in the order of
+    # SymbolsDigests::new (ingress.rs:35-58: LURK_SYMBOLS then BUILTIN_SYMBOLS), so that its pointer is its index + 1;
+    # the func asserts exactly that.  No inputs, no outputs; width pinned at 188 (eval_direct.rs:2027).
+    pre_body = []
+    for name, ptr in LURK_SYMBOL_PTRS.items():
+        digest = z.lurk_sym(name).digest if name in LURK_SYMBOLS else z.builtin(name).digest
+        pre_body += [array("arr", list(digest)), store("ptr", ["arr"]), const("addr", ptr), assert_eq("ptr", "addr")]
+    preallocate = func("preallocate_symbols", [], 0, pre_body + [ret()])
     data_roundtrip = func("data_roundtrip", [("tag_full", 8), ("digest", 8)], 9, [
-        call(["nil_ptr", "t_ptr", "rest_ptr"], "preallocate", []),
-        const("one", NIL_PTR), const("two", T_PTR),
-        assert_eq("nil_ptr", "one"), assert_eq("t_ptr", "two"),
+        call([], "preallocate_symbols", []),
         call(["tag", "ptr"], "ingress", ["tag_full", "digest"]),
         call(["out_tag", ("out_digest", 8)], "egress", ["tag", "ptr"]),
         ret("out_tag", "out_digest")])
@@ -314,7 +322,7 @@ def lurk_data_toplevel():
                 ret("err_tag", "illegal_binding_var_err")])]),
         ret("err_tag", "invalid_form_err")])
     mutuals_demo = func("mutuals_demo", [("tag_full", 8), ("digest", 8)], 9, [
-        call(["nil_ptr", "t_ptr", "rest_ptr"], "preallocate", []),
+        call([], "preallocate_symbols", []),
         call(["binds_tag", "binds"], "ingress", ["tag_full", "digest"]),
         const("empty_env", 0),
         call(["env_tag", "env"], "extend_env_with_mutuals", ["binds_tag", "binds", "binds", "empty_env"]),

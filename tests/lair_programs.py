@@ -506,7 +506,7 @@ def lurk_core_toplevel():
     except the built-in operator family, whose two entry points answer (Err, Todo).  `lurk_eval_demo(expr)` =
     preallocate, ingress, eval in the empty environment, egress: a builtin-free Lurk expression evaluated for real."""
     from lurk_b200.lair import Toplevel, call, const, func, ret
-    from lurk_b200.programs import LURK_DATA_SYMBOL_PTRS as PTR, lurk_data_toplevel as data_toplevel
+    from lurk_b200.programs import LURK_SYMBOL_PTRS as PTR, lurk_data_toplevel as data_toplevel
     data = data_toplevel()
     ev = lurk_eval_subset_toplevel(PTR["nil"], PTR["t"], PTR["&rest"])
     take = lambda top, names: [f for f in top.funcs_e if f.name in names]
@@ -514,13 +514,13 @@ def lurk_core_toplevel():
     stubs = [func("eval_builtin_expr", ["head", "rest_tag", "rest", "env"], 2, todo, partial=True),
              func("eval_coroutine_expr", ["head", "args_tag", "args", "env"], 2, todo, partial=True)]
     demo = func("lurk_eval_demo", [("tag_full", 8), ("digest", 8)], 9, [
-        call(["nil_ptr", "t_ptr", "rest_ptr"], "preallocate", []),
+        call([], "preallocate_symbols", []),
         call(["tag", "ptr"], "ingress", ["tag_full", "digest"]),
         const("empty_env", 0),
         call(["res_tag", "res"], "eval", ["tag", "ptr", "empty_env"]),
         call(["out_tag", ("out_digest", 8)], "egress", ["res_tag", "res"]),
         ret("out_tag", "out_digest")], partial=True)
-    funcs = ([demo] + take(data, {"preallocate", "ingress", "egress", "hash3", "hash4", "hash5", "extend_env_with_mutuals"})
+    funcs = ([demo] + take(data, {"preallocate_symbols", "ingress", "egress", "hash3", "hash4", "hash5", "extend_env_with_mutuals"})
              + take(ev, {"eval", "apply", "env_lookup", "eval_begin", "eval_list", "eval_let", "eval_letrec",
                          "eval_letrec_bindings", "equal", "equal_inner", "car_cdr", "open_comm", "coerce_if_sym"}) + stubs)
     return Toplevel(funcs, data.chips)

@@ -22,7 +22,7 @@ def test_zstore_known_answers():
 
 def test_ingress_egress_have_the_reference_widths():
     top = goldens.toplevel_for("lurk_data")
-    for name, width in goldens.KNOWN_ANSWERS["lurk_data_widths"]["value"].items():
+    for name, width in goldens.KNOWN_ANSWERS["lurk_data_widths"]["value"].items():   # incl. preallocate_symbols = 188
         assert FuncChip.from_name(name, top).width() == width, name
 
 

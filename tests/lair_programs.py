@@ -475,6 +475,24 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
         err_if("res_tag", "res"),
         call(["res_tag", "res"], "eval_begin", ["body_tag", "body", "ext_env"]),
         ret("res_tag", "res")], partial=True)
+    # eval_binop_misc (eval_direct.rs:1359-1400): `cons` and `strcons`, keyed by the pointers of the preallocated symbols
+    from lurk_b200.programs import LURK_SYMBOL_PTRS as SYM
+    eval_binop_misc = func("eval_binop_misc", ["head", "exp1_tag", "exp1", "exp2_tag", "exp2", "env"], 2, [
+        const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]),
+        call(["val1_tag", "val1"], "eval", ["exp1_tag", "exp1", "env"]),
+        err_if("val1_tag", "val1"),
+        call(["val2_tag", "val2"], "eval", ["exp2_tag", "exp2", "env"]),
+        err_if("val2_tag", "val2"),
+        match("head", [
+            (SYM["cons"], [store("cons", ["val1_tag", "val1", "val2_tag", "val2"]), ret("cons_tag", "cons")]),
+            (SYM["strcons"], [
+                const("char_tag", TAG["Char"]), const("str_tag", TAG["Str"]),
+                store("strcons", ["val1_tag", "val1", "val2_tag", "val2"]),
+                sub("not_char", "val1_tag", "char_tag"),
+                sub("not_str", "val2_tag", "str_tag"),
+                if_("not_char", [const("err", 11), ret("err_tag", "err")]),       # EvalErr::NotChar
+                if_("not_str", [const("err", 13), ret("err_tag", "err")]),        # EvalErr::NotString
+                ret("str_tag", "strcons")])], exhaustive=True)], partial=True)
     # lurk_main (eval_direct.rs:120-138): the entry point -- a call with no outputs, two ingresses, eval, egress
     pre_stub = func("preallocate_symbols", [], 0, [ret()])
     egress_stub = func("egress", ["tag", "val"], 9, [array("d", [0] * 8), ret("tag", "d")])
@@ -491,7 +509,7 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
         ret("full_val_tag", "val_digest")], partial=True)
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
                      env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
-                     builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main], chips)
+                     builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main, eval_binop_misc], chips)
 
 
 def lurk_data_toplevel():

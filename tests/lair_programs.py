@@ -493,6 +493,33 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
                 if_("not_char", [const("err", 11), ret("err_tag", "err")]),       # EvalErr::NotChar
                 if_("not_str", [const("err", 13), ret("err_tag", "err")]),        # EvalErr::NotString
                 ret("str_tag", "strcons")])], exhaustive=True)], partial=True)
+    # eval_env_builtin (eval_direct.rs:835-881) and eval_apply_builtin (:883-902)
+    eval_env_builtin = func("eval_env_builtin", ["rest_tag", "rest", "env"], 2, [
+        const("env_tag", TAG["Env"]), const("err_tag", TAG["Err"]),
+        match("rest_tag", [
+            (TAG["Nil"], [const("env", 0), ret("env_tag", "env")]),
+            (TAG["Cons"], [
+                load(["head_tag", "head", "rest_tag", "rest"], "rest"),
+                call(["head_tag", "head"], "eval", ["head_tag", "head", "env"]),
+                match("head_tag", [
+                    (TAG["Cons"], [
+                        load(["sym_tag", "sym", "val_tag", "val"], "head"),
+                        match("sym_tag", [((TAG["Sym"], TAG["Builtin"], TAG["Coroutine"]), [
+                            call(["tail_env_tag", "tail_env"], "eval_env_builtin", ["rest_tag", "rest", "env"]),
+                            match("tail_env_tag", [
+                                (TAG["Env"], [store("env", ["sym_tag", "sym", "val_tag", "val", "tail_env"]), ret("env_tag", "env")]),
+                                (TAG["Err"], [ret("tail_env_tag", "tail_env")])], exhaustive=True)])]),
+                        const("err", 2), ret("err_tag", "err")]),                  # EvalErr::IllegalBindingVar
+                    (TAG["Err"], [ret("head_tag", "head")])]),
+                const("err", ERR["NotCons"]), ret("err_tag", "err")])]),
+        const("err", ERR["InvalidForm"]), ret("err_tag", "err")], partial=True)
+    eval_apply_builtin = func("eval_apply_builtin", ["fst_tag", "fst", "snd_tag", "snd", "env"], 2, [
+        call(["fst_tag", "fst"], "eval", ["fst_tag", "fst", "env"]),
+        err_if("fst_tag", "fst"),
+        call(["snd_tag", "snd"], "eval", ["snd_tag", "snd", "env"]),
+        err_if("snd_tag", "snd"),
+        call(["res_tag", "res"], "apply", ["fst_tag", "fst", "snd_tag", "snd", "env"]),
+        ret("res_tag", "res")], partial=True)
     # lurk_main (eval_direct.rs:120-138): the entry point -- a call with no outputs, two ingresses, eval, egress
     pre_stub = func("preallocate_symbols", [], 0, [ret()])
     egress_stub = func("egress", ["tag", "val"], 9, [array("d", [0] * 8), ret("tag", "d")])
@@ -509,7 +536,8 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
         ret("full_val_tag", "val_digest")], partial=True)
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
                      env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
-                     builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main, eval_binop_misc], chips)
+                     builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main, eval_binop_misc,
+                     eval_env_builtin, eval_apply_builtin], chips)
 
 
 def lurk_data_toplevel():

@@ -520,6 +520,32 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
         err_if("snd_tag", "snd"),
         call(["res_tag", "res"], "apply", ["fst_tag", "fst", "snd_tag", "snd", "env"]),
         ret("res_tag", "res")], partial=True)
+    # eval_bind_builtin (eval_direct.rs:774-828)
+    invf = [ret("err_tag", "invalid_form")]
+    eval_bind_builtin = func("eval_bind_builtin", ["rest_tag", "rest", "env"], 2, [
+        const("nil_tag", TAG["Nil"]), const("cons_tag", TAG["Cons"]), const("err_tag", TAG["Err"]),
+        const("invalid_form", ERR["InvalidForm"]),
+        sub("rest_not_cons", "rest_tag", "cons_tag"), if_("rest_not_cons", invf),
+        load(["fst_tag", "fst", "rest_tag", "rest"], "rest"),
+        sub("rest_not_cons", "rest_tag", "cons_tag"), if_("rest_not_cons", invf),
+        load(["snd_tag", "snd", "rest_tag", "rest"], "rest"),
+        sub("rest_not_cons", "rest_tag", "cons_tag"), if_("rest_not_cons", invf),
+        load(["trd_tag", "trd", "rest_tag", "_rest"], "rest"),
+        sub("rest_not_nil", "rest_tag", "nil_tag"), if_("rest_not_nil", invf),
+        call(["fst_tag", "fst"], "eval", ["fst_tag", "fst", "env"]),
+        match("fst_tag", [
+            ((TAG["Sym"], TAG["Builtin"], TAG["Coroutine"]), [
+                call(["snd_tag", "snd"], "eval", ["snd_tag", "snd", "env"]),
+                sub("not_err", "snd_tag", "err_tag"),
+                if_("not_err", [
+                    call(["trd_tag", "trd"], "eval", ["trd_tag", "trd", "env"]),
+                    match("trd_tag", [
+                        (TAG["Env"], [store("env2", ["fst_tag", "fst", "snd_tag", "snd", "trd"]), ret("trd_tag", "env2")]),
+                        (TAG["Err"], [ret("trd_tag", "trd")])]),
+                    const("err", 10), ret("err_tag", "err")],                      # EvalErr::NotEnv
+                    [ret("snd_tag", "snd")])]),
+            (TAG["Err"], [ret("fst_tag", "fst")])]),
+        const("err", 2), ret("err_tag", "err")], partial=True)                     # EvalErr::IllegalBindingVar
     # lurk_main (eval_direct.rs:120-138): the entry point -- a call with no outputs, two ingresses, eval, egress
     pre_stub = func("preallocate_symbols", [], 0, [ret()])
     egress_stub = func("egress", ["tag", "val"], 9, [array("d", [0] * 8), ret("tag", "d")])
@@ -537,7 +563,7 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
                      env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
                      builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main, eval_binop_misc,
-                     eval_env_builtin, eval_apply_builtin], chips)
+                     eval_env_builtin, eval_apply_builtin, eval_bind_builtin], chips)
 
 
 def lurk_data_toplevel():

@@ -546,6 +546,28 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
                     [ret("snd_tag", "snd")])]),
             (TAG["Err"], [ret("fst_tag", "fst")])]),
         const("err", 2), ret("err_tag", "err")], partial=True)                     # EvalErr::IllegalBindingVar
+    # eval_hide (eval_direct.rs:1564-1612): (hide secret value) -> commitment = hash3(secret ++ value.flatten())
+    eval_hide = func("eval_hide", ["rest_tag", "rest", "env"], 2, [
+        const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]), const("nil_tag", TAG["Nil"]),
+        const("invalid_form", ERR["InvalidForm"]),
+        sub("rest_not_cons", "rest_tag", "cons_tag"), if_("rest_not_cons", invf),
+        load(["exp1_tag", "exp1", "rest_tag", "rest"], "rest"),
+        sub("rest_not_cons", "rest_tag", "cons_tag"), if_("rest_not_cons", invf),
+        load(["exp2_tag", "exp2", "rest_tag", "_rest"], "rest"),
+        sub("rest_not_nil", "rest_tag", "nil_tag"), if_("rest_not_nil", invf),
+        call(["val1_tag", "val1"], "eval", ["exp1_tag", "exp1", "env"]),
+        err_if("val1_tag", "val1"),
+        call(["val2_tag", "val2"], "eval", ["exp2_tag", "exp2", "env"]),
+        err_if("val2_tag", "val2"),
+        match("val1_tag", [(TAG["BigNum"], [
+            load([("secret", 8)], "val1"),
+            call(["val2_tag", ("val2_digest", 8)], "egress", ["val2_tag", "val2"]),
+            array("padding", [0] * 7),
+            call([("comm_hash", 8)], "hash3", ["secret", "val2_tag", "padding", "val2_digest"]),
+            store("comm_ptr", ["comm_hash"]),
+            const("comm_tag", TAG["Comm"]),
+            ret("comm_tag", "comm_ptr")])]),
+        const("not_comm", 15), ret("err_tag", "not_comm")], partial=True)           # EvalErr::NotBigNum
     # lurk_main (eval_direct.rs:120-138): the entry point -- a call with no outputs, two ingresses, eval, egress
     pre_stub = func("preallocate_symbols", [], 0, [ret()])
     egress_stub = func("egress", ["tag", "val"], 9, [array("d", [0] * 8), ret("tag", "d")])
@@ -563,7 +585,7 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
                      env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
                      builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main, eval_binop_misc,
-                     eval_env_builtin, eval_apply_builtin, eval_bind_builtin], chips)
+                     eval_env_builtin, eval_apply_builtin, eval_bind_builtin, eval_hide], chips)
 
 
 def lurk_data_toplevel():

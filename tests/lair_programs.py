@@ -568,6 +568,30 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
             const("comm_tag", TAG["Comm"]),
             ret("comm_tag", "comm_ptr")])]),
         const("not_comm", 15), ret("err_tag", "not_comm")], partial=True)           # EvalErr::NotBigNum
+    # eval_opening_unop (eval_direct.rs:1502-1562): commit / open / secret
+    eval_opening_unop = func("eval_opening_unop", ["head", "rest_tag", "rest", "env"], 2, [
+        const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]), const("nil_tag", TAG["Nil"]),
+        const("invalid_form", ERR["InvalidForm"]),
+        sub("rest_not_cons", "rest_tag", "cons_tag"), if_("rest_not_cons", invf),
+        load(["expr_tag", "expr", "rest_tag", "_rest"], "rest"),
+        sub("rest_not_nil", "rest_tag", "nil_tag"), if_("rest_not_nil", invf),
+        call(["val_tag", "val"], "eval", ["expr_tag", "expr", "env"]),
+        err_if("val_tag", "val"),
+        match("head", [(SYM["commit"], [
+            call(["val_tag", ("val_digest", 8)], "egress", ["val_tag", "val"]),
+            array("padding", [0] * 7), const("zero", 0),
+            call([("comm_hash", 8)], "hash3", ["zero", "padding", "val_tag", "padding", "val_digest"]),
+            const("comm_tag", TAG["Comm"]),
+            store("comm_ptr", ["comm_hash"]),
+            ret("comm_tag", "comm_ptr")])]),
+        match("val_tag", [((TAG["Comm"], TAG["BigNum"]), [
+            load([("comm_hash", 8)], "val"),
+            preimg([("secret", 8), "tag", ("padding", 7), ("val_digest", 8)], "hash3", ["comm_hash"]),
+            match("head", [
+                (SYM["open"], [call(["tag", "ptr"], "ingress", ["tag", "padding", "val_digest"]), ret("tag", "ptr")]),
+                (SYM["secret"], [store("ptr", ["secret"]), const("big_num_tag", TAG["BigNum"]), ret("big_num_tag", "ptr")]),
+            ], exhaustive=True)])]),
+        const("cant_open", 16), ret("err_tag", "cant_open")], partial=True)          # EvalErr::CantOpen
     # lurk_main (eval_direct.rs:120-138): the entry point -- a call with no outputs, two ingresses, eval, egress
     pre_stub = func("preallocate_symbols", [], 0, [ret()])
     egress_stub = func("egress", ["tag", "val"], 9, [array("d", [0] * 8), ret("tag", "d")])
@@ -585,7 +609,8 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
     return Toplevel([hash3, eval_stub, ingress_stub, coerce_if_sym, open_comm, car_cdr, equal_inner, env_lookup,
                      env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
                      builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main, eval_binop_misc,
-                     eval_env_builtin, eval_apply_builtin, eval_bind_builtin, eval_hide], chips)
+                     eval_env_builtin, eval_apply_builtin, eval_bind_builtin, eval_hide,
+                     eval_opening_unop], chips)
 
 
 def lurk_data_toplevel():

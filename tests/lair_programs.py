@@ -592,6 +592,62 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
                 (SYM["secret"], [store("ptr", ["secret"]), const("big_num_tag", TAG["BigNum"]), ret("big_num_tag", "ptr")]),
             ], exhaustive=True)])]),
         const("cant_open", 16), ret("err_tag", "cant_open")], partial=True)          # EvalErr::CantOpen
+    # eval_binop_num (eval_direct.rs:1184-1356): arithmetic and comparisons on u64 / num / big-num pairs; its callees
+    # are the real pointer-taking funcs of src/core/misc.rs (lurk_b200/programs.py::lurk_misc_toplevel)
+    from lurk_b200.lair import add, div, match_many
+    from lurk_b200.programs import lurk_misc_toplevel
+    misc = [f for f in lurk_misc_toplevel().funcs_e if f.name in {
+        "u64_add", "u64_sub", "u64_mul", "u64_divrem", "u64_lessthan", "u64_iszero", "digest_equal", "big_num_lessthan"}]
+    T_ = [ret("t_tag", "t")]
+    NIL_ = [ret("nil_tag", "nil")]
+    def cmp(callee, a, b, yes, no):
+        return [call(["res"], callee, [a, b]), if_("res", yes), *no]
+    def u64_arith(callee):
+        return [call(["res"], callee, ["val1", "val2"]), ret("u64_tag", "res")]
+    eval_binop_num = func("eval_binop_num", ["head", "exp1_tag", "exp1", "exp2_tag", "exp2", "env"], 2, [
+        const("err_tag", TAG["Err"]), const("num_tag", TAG["Num"]), const("u64_tag", TAG["U64"]),
+        const("nil_tag", TAG["Nil"]), const("err_div_zero", 9),                          # EvalErr::DivByZero
+        const("t", t_ptr), const("nil", nil_ptr),
+        call(["val1_tag", "val1"], "eval", ["exp1_tag", "exp1", "env"]),
+        err_if("val1_tag", "val1"),
+        call(["val2_tag", "val2"], "eval", ["exp2_tag", "exp2", "env"]),
+        err_if("val2_tag", "val2"),
+        const("t_tag", TAG["T"]),
+        slice_([("tags", 2)], ["val1_tag", "val2_tag"]),
+        match_many("tags", [
+            ([TAG["U64"], TAG["U64"]], [match("head", [
+                (SYM["+"], u64_arith("u64_add")),
+                (SYM["-"], u64_arith("u64_sub")),
+                (SYM["*"], u64_arith("u64_mul")),
+                ((SYM["/"], SYM["%"]), [
+                    call(["is_zero"], "u64_iszero", ["val2"]),
+                    if_("is_zero", [ret("err_tag", "err_div_zero")]),
+                    call(["quot", "rem"], "u64_divrem", ["val1", "val2"]),
+                    match("head", [(SYM["/"], [ret("u64_tag", "quot")]), (SYM["%"], [ret("u64_tag", "rem")])], exhaustive=True)]),
+                (SYM["<"], cmp("u64_lessthan", "val1", "val2", T_, NIL_)),
+                (SYM[">="], cmp("u64_lessthan", "val1", "val2", NIL_, T_)),
+                (SYM[">"], cmp("u64_lessthan", "val2", "val1", T_, NIL_)),
+                (SYM["<="], cmp("u64_lessthan", "val2", "val1", NIL_, T_)),
+                (SYM["="], cmp("digest_equal", "val1", "val2", T_, NIL_)),
+            ], exhaustive=True)]),
+            ([TAG["Num"], TAG["Num"]], [match("head", [
+                (SYM["+"], [add("res", "val1", "val2"), ret("num_tag", "res")]),
+                (SYM["-"], [sub("res", "val1", "val2"), ret("num_tag", "res")]),
+                (SYM["*"], [mul("res", "val1", "val2"), ret("num_tag", "res")]),
+                (SYM["/"], [if_("val2", [div("res", "val1", "val2"), ret("num_tag", "res")], [ret("err_tag", "err_div_zero")])]),
+                (SYM["="], [sub("diff", "val1", "val2"), if_("diff", NIL_), *T_]),
+                ((SYM["%"], SYM["<"], SYM[">"], SYM["<="], SYM[">="]), [const("err", 14), ret("err_tag", "err")]),   # NotU64
+            ], exhaustive=True)]),
+            ([TAG["BigNum"], TAG["BigNum"]], [match("head", [
+                (SYM["<"], cmp("big_num_lessthan", "val1", "val2", T_, NIL_)),
+                (SYM[">="], cmp("big_num_lessthan", "val1", "val2", NIL_, T_)),
+                (SYM[">"], cmp("big_num_lessthan", "val2", "val1", T_, NIL_)),
+                (SYM["<="], cmp("big_num_lessthan", "val2", "val1", NIL_, T_)),
+                (SYM["="], cmp("digest_equal", "val2", "val1", T_, NIL_)),
+                ((SYM["+"], SYM["-"], SYM["*"], SYM["/"], SYM["%"]), [const("err", 8), ret("err_tag", "err")]),      # InvalidArg
+            ], exhaustive=True)]),
+        ]),
+        const("err", 8), ret("err_tag", "err")], partial=True)
     # lurk_main (eval_direct.rs:120-138): the entry point -- a call with no outputs, two ingresses, eval, egress
     pre_stub = func("preallocate_symbols", [], 0, [ret()])
     egress_stub = func("egress", ["tag", "val"], 9, [array("d", [0] * 8), ret("tag", "d")])
@@ -610,7 +666,7 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
                      env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
                      builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main, eval_binop_misc,
                      eval_env_builtin, eval_apply_builtin, eval_bind_builtin, eval_hide,
-                     eval_opening_unop], chips)
+                     eval_opening_unop, eval_binop_num] + misc, chips)
 
 
 def lurk_data_toplevel():

@@ -193,7 +193,105 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
     # reference's signatures
     def stub(name, params):
         return func(name, params, 2, [ret(params[0], params[1])], partial=True)
-    builtin_stub = stub("eval_builtin_expr", ["head", "rest_tag", "rest", "env"])
+    # eval_builtin_expr (eval_direct.rs:443-765): the dispatcher on the head symbol of a built-in form, statement for
+    # statement (the `breakpoint` pseudo-op, which has no effect on the trace, is left out); eval_unop is a stub
+    from lurk_b200.programs import LURK_SYMBOL_PTRS as SYM
+    inv_ = [ret("err_tag", "invalid_form")]
+    def need_cons():
+        return [sub("rest_not_cons", "rest_tag", "cons_tag"), if_("rest_not_cons", inv_)]
+    def need_nil():
+        return [sub("rest_not_nil", "rest_tag", "nil_tag"), if_("rest_not_nil", inv_)]
+    def errp(tag, val):
+        return match(tag, [(TAG["Err"], [ret(tag, val)])])
+    def fwd(callee, args):
+        return [call(["res_tag", "res"], callee, args), ret("res_tag", "res")]
+    two_args = (need_cons() + [load(["fst_tag", "fst", "rest_tag", "rest"], "rest")] + need_cons()
+                + [load(["snd_tag", "snd", "rest_tag", "_rest"], "rest")] + need_nil())
+    nil_or_t = lambda cond: [if_(cond, [const("nil", nil_ptr), ret("nil_tag", "nil")]),
+                             const("t_tag", TAG["T"]), const("t", t_ptr), ret("t_tag", "t")]
+    S = lambda *names: tuple(SYM[n] for n in names) if len(names) > 1 else SYM[names[0]]
+    builtin_stub = func("eval_builtin_expr", ["head", "rest_tag", "rest", "env"], 2, [
+        const("nil_tag", TAG["Nil"]), const("cons_tag", TAG["Cons"]), const("err_tag", TAG["Err"]),
+        const("invalid_form", ERR["InvalidForm"]),
+        match("head", [
+            (S("let", "letrec", "lambda"), need_cons() + [load(["fst_tag", "fst", "rest_tag", "rest"], "rest")] + need_cons() + [
+                match("head", [
+                    (S("let"), fwd("eval_let", ["fst_tag", "fst", "rest_tag", "rest", "env"])),
+                    (S("letrec"), fwd("eval_letrec", ["fst_tag", "fst", "rest_tag", "rest", "env"])),
+                    (S("lambda"), [const("res_tag", TAG["Fun"]), store("res", ["fst_tag", "fst", "rest_tag", "rest", "env"]),
+                                   ret("res_tag", "res")])], exhaustive=True)]),
+            (S("cons", "strcons", "type-eq", "type-eqq", "apply"), two_args + [
+                match("head", [
+                    (S("cons", "strcons"), fwd("eval_binop_misc", ["head", "fst_tag", "fst", "snd_tag", "snd", "env"])),
+                    (S("type-eq"), [
+                        call(["fst_tag", "fst"], "eval", ["fst_tag", "fst", "env"]), errp("fst_tag", "fst"),
+                        call(["snd_tag", "snd"], "eval", ["snd_tag", "snd", "env"]), errp("snd_tag", "snd"),
+                        call(["fst_tag"], "coerce_if_sym", ["fst_tag"]), call(["snd_tag"], "coerce_if_sym", ["snd_tag"]),
+                        sub("type_not_eq", "fst_tag", "snd_tag")] + nil_or_t("type_not_eq")),
+                    (S("type-eqq"), [
+                        call(["snd_tag", "snd"], "eval", ["snd_tag", "snd", "env"]), errp("snd_tag", "snd"),
+                        call(["fst_tag"], "coerce_if_sym", ["fst_tag"]), call(["snd_tag"], "coerce_if_sym", ["snd_tag"]),
+                        sub("type_not_eqq", "fst_tag", "snd_tag")] + nil_or_t("type_not_eqq")),
+                    (S("apply"), fwd("eval_apply_builtin", ["fst_tag", "fst", "snd_tag", "snd", "env"]))], exhaustive=True)]),
+            (S("list"), [call(["expr_tag", "expr"], "eval_list", ["rest_tag", "rest", "env"]), ret("expr_tag", "expr")]),
+            (S("+", "-", "*", "/", "%", "=", "<", ">", "<=", ">="),
+             two_args + fwd("eval_binop_num", ["head", "fst_tag", "fst", "snd_tag", "snd", "env"])),
+            (S("eval"), need_cons() + [
+                load(["expr_tag", "expr", "rest_tag", "rest"], "rest"),
+                match("rest_tag", [
+                    (TAG["Nil"], [
+                        call(["res_tag", "res"], "eval", ["expr_tag", "expr", "env"]), errp("res_tag", "res"),
+                        const("env", 0),
+                        call(["res_tag", "res"], "eval", ["res_tag", "res", "env"]), ret("res_tag", "res")]),
+                    (TAG["Cons"], [load(["env_expr_tag", "env_expr", "rest_tag", "_rest"], "rest")] + need_nil() + [
+                        call(["res_tag", "res"], "eval", ["expr_tag", "expr", "env"]), errp("res_tag", "res"),
+                        call(["env_tag", "new_env"], "eval", ["env_expr_tag", "env_expr", "env"]),
+                        match("env_tag", [
+                            (TAG["Err"], [ret("env_tag", "new_env")]),
+                            (TAG["Env"], [call(["res_tag", "res"], "eval", ["res_tag", "res", "new_env"]), ret("res_tag", "res")])]),
+                        const("err", 10), ret("err_tag", "err")])]),                              # EvalErr::NotEnv
+                const("not_env", 10), ret("err_tag", "not_env")]),
+            (S("quote"), need_cons() + [load(["expr_tag", "expr", "rest_tag", "_rest"], "rest")] + need_nil()
+             + [ret("expr_tag", "expr")]),
+            (S("begin"), [call(["expr_tag", "expr"], "eval_begin", ["rest_tag", "rest", "env"]), ret("expr_tag", "expr")]),
+            (S("current-env", "empty-env", "fail"), need_nil() + [
+                const("env_tag", TAG["Env"]),
+                match("head", [
+                    (S("current-env"), [ret("env_tag", "env")]),
+                    (S("empty-env"), [const("env", 0), ret("env_tag", "env")]),
+                    (S("fail"), [const("zero", 0), const("one", 1), assert_eq("zero", "one"), ret("zero", "zero")])],
+                      exhaustive=True)]),
+            (S("bind"), fwd("eval_bind_builtin", ["rest_tag", "rest", "env"])),
+            (S("env"), fwd("eval_env_builtin", ["rest_tag", "rest", "env"])),
+            (S("breakpoint"), [match("rest_tag", [
+                (TAG["Nil"], [const("nil", nil_ptr), ret("nil_tag", "nil")]),
+                (TAG["Cons"], [load(["expr_tag", "expr", "rest_tag", "_rest"], "rest")] + need_nil()
+                 + [call(["val_tag", "val"], "eval", ["expr_tag", "expr", "env"]), ret("val_tag", "val")])], exhaustive=True)]),
+            (S("if"), need_cons() + [load(["expr_tag", "expr", "rest_tag", "rest"], "rest")] + need_cons() + [
+                load(["t_branch_tag", "t_branch", "rest_tag", "rest"], "rest"),
+                match("rest_tag", [
+                    (TAG["Nil"], [
+                        call(["val_tag", "val"], "eval", ["expr_tag", "expr", "env"]),
+                        match("val_tag", [((TAG["Nil"], TAG["Err"]), [ret("val_tag", "val")])]),
+                        call(["res_tag", "res"], "eval", ["t_branch_tag", "t_branch", "env"]), ret("res_tag", "res")]),
+                    (TAG["Cons"], [load(["f_branch_tag", "f_branch", "rest_tag", "_rest"], "rest")] + need_nil() + [
+                        call(["val_tag", "val"], "eval", ["expr_tag", "expr", "env"]),
+                        match("val_tag", [
+                            (TAG["Nil"], [call(["res_tag", "res"], "eval", ["f_branch_tag", "f_branch", "env"]),
+                                          ret("res_tag", "res")]),
+                            (TAG["Err"], [ret("val_tag", "val")])]),
+                        call(["res_tag", "res"], "eval", ["t_branch_tag", "t_branch", "env"]), ret("res_tag", "res")])]),
+                ret("err_tag", "invalid_form")]),
+            (S("eq"), [const("one", 1), call([("res", 2)], "equal", ["rest_tag", "rest", "env", "one"]), ret("res")]),
+            (S("eqq"), [const("zero", 0), call([("res", 2)], "equal", ["rest_tag", "rest", "env", "zero"]), ret("res")]),
+            (S("hide"), fwd("eval_hide", ["rest_tag", "rest", "env"])),
+            (S("car", "cdr"), [
+                call(["car_tag", "car", "cdr_tag", "cdr"], "car_cdr", ["rest_tag", "rest", "env"]),
+                match("head", [(S("car"), [ret("car_tag", "car")]), (S("cdr"), [ret("cdr_tag", "cdr")])], exhaustive=True)]),
+            (S("u64", "char", "atom", "emit", "bignum", "comm"), fwd("eval_unop", ["head", "rest_tag", "rest", "env"])),
+            (S("commit", "open", "secret"), fwd("eval_opening_unop", ["head", "rest_tag", "rest", "env"])),
+        ], exhaustive=True)], partial=True)
+    unop_stub = stub("eval_unop", ["head", "rest_tag", "rest", "env"])
     # eval_coroutine_expr when the Lang has no coroutines (eval_direct.rs:196-222): never callable, not partial
     coroutine_stub = func("eval_coroutine_expr", ["_head", "_args_tag", "_args", "_env"], 2, [
         const("zero", 0), const("one", 1), assert_eq("zero", "one"), ret("zero", "zero")])
@@ -476,7 +574,6 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
         call(["res_tag", "res"], "eval_begin", ["body_tag", "body", "ext_env"]),
         ret("res_tag", "res")], partial=True)
     # eval_binop_misc (eval_direct.rs:1359-1400): `cons` and `strcons`, keyed by the pointers of the preallocated symbols
-    from lurk_b200.programs import LURK_SYMBOL_PTRS as SYM
     eval_binop_misc = func("eval_binop_misc", ["head", "exp1_tag", "exp1", "exp2_tag", "exp2", "env"], 2, [
         const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]),
         call(["val1_tag", "val1"], "eval", ["exp1_tag", "exp1", "env"]),
@@ -666,7 +763,7 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
                      env_demo, equal, eval_list, eval_begin, mutuals_stub, eval_let, eval_letrec_bindings, eval_letrec,
                      builtin_stub, coroutine_stub, apply_stub, pre_stub, egress_stub, lurk_main, eval_binop_misc,
                      eval_env_builtin, eval_apply_builtin, eval_bind_builtin, eval_hide,
-                     eval_opening_unop, eval_binop_num] + misc, chips)
+                     eval_opening_unop, eval_binop_num, unop_stub] + misc, chips)
 
 
 def lurk_data_toplevel():
@@ -677,17 +774,17 @@ def lurk_data_toplevel():
 def lurk_core_toplevel():
     """The restated evaluator put together: data path (preallocate, ingress, egress, hash3/4/5, extend_env_with_mutuals:
     lurk_b200/programs.py::lurk_data_toplevel) + evaluator core (eval, apply, eval_begin, eval_list, env_lookup, eval_let,
-    eval_letrec*, equal*, car_cdr, open_comm, coerce_if_sym: above, with the real preallocated pointers) -- everything
-    except the built-in operator family, whose two entry points answer (Err, Todo).  `lurk_eval_demo(expr)` =
-    preallocate, ingress, eval in the empty environment, egress: a builtin-free Lurk expression evaluated for real."""
+    eval_letrec*, equal*, car_cdr, open_comm, coerce_if_sym, eval_builtin_expr and the built-in operator family: above,
+    with the real preallocated pointers) -- 38 of the reference's 39 funcs; only eval_unop (u64 / char / atom / emit /
+    bignum / comm casts, needs the `emit` op) answers (Err, Todo).  `lurk_eval_demo(expr)` = preallocate_symbols,
+    ingress, eval in the empty environment, egress: Lurk programs evaluated for real."""
     from lurk_b200.lair import Toplevel, call, const, func, ret
     from lurk_b200.programs import LURK_SYMBOL_PTRS as PTR, lurk_data_toplevel as data_toplevel
     data = data_toplevel()
     ev = lurk_eval_subset_toplevel(PTR["nil"], PTR["t"], PTR["&rest"])
     take = lambda top, names: [f for f in top.funcs_e if f.name in names]
     todo = [const("err_tag", TAG["Err"]), const("todo", 21), ret("err_tag", "todo")]            # EvalErr::Todo
-    stubs = [func("eval_builtin_expr", ["head", "rest_tag", "rest", "env"], 2, todo, partial=True),
-             func("eval_coroutine_expr", ["head", "args_tag", "args", "env"], 2, todo, partial=True)]
+    stubs = [func("eval_unop", ["head", "rest_tag", "rest", "env"], 2, todo, partial=True)]      # needs `emit`: not restated
     demo = func("lurk_eval_demo", [("tag_full", 8), ("digest", 8)], 9, [
         call([], "preallocate_symbols", []),
         call(["tag", "ptr"], "ingress", ["tag_full", "digest"]),
@@ -697,5 +794,9 @@ def lurk_core_toplevel():
         ret("out_tag", "out_digest")], partial=True)
     funcs = ([demo] + take(data, {"preallocate_symbols", "ingress", "egress", "hash3", "hash4", "hash5", "extend_env_with_mutuals"})
              + take(ev, {"eval", "apply", "env_lookup", "eval_begin", "eval_list", "eval_let", "eval_letrec",
-                         "eval_letrec_bindings", "equal", "equal_inner", "car_cdr", "open_comm", "coerce_if_sym"}) + stubs)
-    return Toplevel(funcs, data.chips)
+                         "eval_letrec_bindings", "equal", "equal_inner", "car_cdr", "open_comm", "coerce_if_sym",
+                         "eval_builtin_expr", "eval_coroutine_expr", "eval_binop_num", "eval_binop_misc", "eval_env_builtin",
+                         "eval_apply_builtin", "eval_bind_builtin", "eval_hide", "eval_opening_unop",
+                         "u64_add", "u64_sub", "u64_mul", "u64_divrem", "u64_lessthan", "u64_iszero", "digest_equal",
+                         "big_num_lessthan"}) + stubs)
+    return Toplevel(funcs, ev.chips)

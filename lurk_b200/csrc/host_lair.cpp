@@ -74,6 +74,11 @@ St slice(const std::vector<Var>& outs, const std::vector<std::string>& inps) {
   s.names = inps;
   return s;
 }
+St emit(const std::vector<std::string>& xs) {
+  St s = mk(SK::Emit);
+  s.names = xs;
+  return s;
+}
 St ret(const std::vector<std::string>& vs) {
   St s = mk(SK::Return);
   s.names = vs;
@@ -344,6 +349,9 @@ std::unique_ptr<Block> compile_block(const Stmts& body, const Stmts& pre, Linker
         op.xs = flat(s.names);
         ops.push_back(op);
       } break;
+      case SK::Emit:
+        for (auto& v : s.names) ctx.get(v);   // must be bound; no bytecode
+        break;
       case SK::Slice: {   // pure re-linking (toplevel.rs OpE::Slice)
         const std::vector<uint32_t> vals = flat(s.names);
         if (out_size(s.outs) != vals.size()) bail("Var mismatch on slice");
@@ -650,7 +658,7 @@ struct Reader {
   St stmt() {
     St st;
     uint32_t k = u();
-    if (k > (uint32_t)SK::Slice) bail("bad statement kind in surface image");
+    if (k > (uint32_t)SK::Emit) bail("bad statement kind in surface image");
     st.kind = (SK)k;
     switch (st.kind) {
       case SK::Const: st.tgt = s(); st.value = u(); break;
@@ -665,7 +673,7 @@ struct Reader {
       case SK::Call: case SK::PreImg: case SK::ExternCall: st.outs = vars(); st.callee = s(); st.names = names(); break;
       case SK::Store: st.tgt = s(); st.names = names(); break;
       case SK::Load: st.outs = vars(); st.a = s(); break;
-      case SK::RangeU8: case SK::Return: st.names = names(); break;
+      case SK::RangeU8: case SK::Return: case SK::Emit: st.names = names(); break;
       case SK::Slice: st.outs = vars(); st.names = names(); break;
       case SK::If: {
         st.a = s();

@@ -40,7 +40,7 @@ struct St;
 using Stmts = std::vector<St>;
 enum class SK : uint32_t {
   Const, Array, Add, Sub, Mul, Div, Inv, Not, Eq, AssertEq, AssertNe, Contains, Call, PreImg, Store, Load,
-  ExternCall, RangeU8, Return, If, Match, MatchMany, Slice
+  ExternCall, RangeU8, Return, If, Match, MatchMany, Slice, Emit
 };
 struct Arm {
   std::vector<uint32_t> keys;  // Match: alternative scalar keys; MatchMany: one key tuple
@@ -80,6 +80,8 @@ St extern_call(const std::vector<Var>& outs, const std::string& chip, const std:
 St range_u8(const std::vector<std::string>& xs);
 // `let (x, y: [7]) = (a, b);` -- OpE::Slice (src/lair/expr.rs:141-143): rebinds the concatenated values, no bytecode
 St slice(const std::vector<Var>& outs, const std::vector<std::string>& inps);
+// `emit(x, ...)` -- OpE::Emit: no columns, no constraints; checked and compiled to nothing (see lurk_b200/lair.py::emit)
+St emit(const std::vector<std::string>& xs);
 St ret(const std::vector<std::string>& vs);
 St if_(const std::string& x, Stmts then);                 // the statements that follow form the else block
 St if_else(const std::string& x, Stmts then, Stmts else_);

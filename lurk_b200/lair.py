@@ -68,6 +68,12 @@ def store(ptr: str, vals: Sequence[str]) -> St: return St("store", (ptr, list(va
 def load(vals: Sequence[VarRef], ptr: str) -> St: return St("load", (list(vals), ptr))
 def extern_call(outs: Sequence[VarRef], name: str, inps: Sequence[str]) -> St: return St("extern_call", (list(outs), name, list(inps)))
 def range_u8(xs: Sequence[str]) -> St: return St("range_u8", (list(xs),))
+def emit(xs: Sequence[str]) -> St:
+    """`emit(x, ...)` -- OpE::Emit (src/lair/expr.rs:147-148): pushes values to QueryRecord::emitted while executing.  It has
+    no columns, no constraints and no place in the layout (air.rs:493, func_chip.rs:274, trace.rs:415), so traces and
+    proofs do not depend on it; here it is checked (the variables must be bound) and compiles to nothing -- the
+    `emitted` side channel of the REPL is not kept."""
+    return St("emit", (list(xs),))
 def slice_(outs: Sequence[VarRef], inps: Sequence[str]) -> St:
     """`let (x, y: [7]) = (a, b);` -- OpE::Slice (src/lair/expr.rs:141-143, macros.rs:247-268): rebinds the values of
     `inps`, concatenated, to the names `outs`; emits no bytecode."""
@@ -267,6 +273,9 @@ def _compile_block(stmts: List[St], pre_ops: List[St], ctx: _Linker) -> Block:
                 ctx.new(o)
         elif k == "range_u8":
             ops.append(Op("range_u8", ([j for v in a[0] for j in ctx.get(v)],)))
+        elif k == "emit":
+            for v in a[0]:
+                ctx.get(v)
         elif k == "slice":   # toplevel.rs OpE::Slice: pure re-linking
             flat = [j for v in a[1] for j in ctx.get(v)]
             assert sum(_vsize(o) for o in a[0]) == len(flat), "Var mismatch on slice"
@@ -502,7 +511,7 @@ class Toplevel:
 
         KIND = {"const": 0, "array": 1, "add": 2, "sub": 3, "mul": 4, "div": 5, "inv": 6, "not": 7, "eq": 8,
                 "assert_eq": 9, "assert_ne": 10, "contains": 11, "call": 12, "preimg": 13, "store": 14, "load": 15,
-                "extern_call": 16, "range_u8": 17, "return": 18, "if": 19, "match": 20, "match_many": 21, "slice": 22}
+                "extern_call": 16, "range_u8": 17, "return": 18, "if": 19, "match": 20, "match_many": 21, "slice": 22, "emit": 23}
 
         def vars_(vs) -> List[int]:
             out = [len(vs)]
@@ -538,7 +547,7 @@ class Toplevel:
                 out += [sid(a[0])] + names(a[1])
             elif k == "load":
                 out += vars_(a[0]) + [sid(a[1])]
-            elif k in ("range_u8", "return"):
+            elif k in ("range_u8", "return", "emit"):
                 out += names(a[0])
             elif k == "slice":
                 out += vars_(a[0]) + names(a[1])

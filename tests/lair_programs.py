@@ -291,7 +291,35 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
             (S("u64", "char", "atom", "emit", "bignum", "comm"), fwd("eval_unop", ["head", "rest_tag", "rest", "env"])),
             (S("commit", "open", "secret"), fwd("eval_opening_unop", ["head", "rest_tag", "rest", "env"])),
         ], exhaustive=True)], partial=True)
-    unop_stub = stub("eval_unop", ["head", "rest_tag", "rest", "env"])
+    # eval_unop (eval_direct.rs:1402-1500): atom / emit / u64 / char / bignum / comm
+    from lurk_b200.lair import emit
+    def cast(keep, convert, errcode):
+        return [match("val_tag", [(keep, [ret("val_tag", "val")]), convert]), const("err", errcode), ret("err_tag", "err")]
+    unop_stub = func("eval_unop", ["head", "rest_tag", "rest", "env"], 2, [
+        const("err_tag", TAG["Err"]), const("cons_tag", TAG["Cons"]), const("nil_tag", TAG["Nil"]),
+        const("invalid_form", ERR["InvalidForm"]),
+        sub("rest_not_cons", "rest_tag", "cons_tag"), if_("rest_not_cons", [ret("err_tag", "invalid_form")]),
+        load(["expr_tag", "expr", "rest_tag", "_rest"], "rest"),
+        sub("rest_not_nil", "rest_tag", "nil_tag"), if_("rest_not_nil", [ret("err_tag", "invalid_form")]),
+        call(["val_tag", "val"], "eval", ["expr_tag", "expr", "env"]),
+        match("val_tag", [(TAG["Err"], [ret("val_tag", "val")])]),
+        match("head", [
+            (SYM["atom"], [
+                sub("val_not_cons", "val_tag", "cons_tag"),
+                if_("val_not_cons", [const("t_tag", TAG["T"]), const("t", t_ptr), ret("t_tag", "t")]),
+                const("nil", nil_ptr), ret("nil_tag", "nil")]),
+            (SYM["emit"], [emit(["val_tag", "val"]), ret("val_tag", "val")]),
+            (SYM["u64"], cast(TAG["U64"], (TAG["Char"], [
+                load([("bytes", 4)], "val"), array("padding", [0] * 4), store("val", ["bytes", "padding"]),
+                const("val_tag", TAG["U64"]), ret("val_tag", "val")]), 18)),            # EvalErr::CantCastToU64
+            (SYM["char"], cast(TAG["Char"], (TAG["U64"], [
+                load([("bytes", 4), ("_ignored", 4)], "val"), store("val", ["bytes"]),
+                const("val_tag", TAG["Char"]), ret("val_tag", "val")]), 17)),           # EvalErr::CantCastToChar
+            (SYM["bignum"], cast(TAG["BigNum"], (TAG["Comm"], [const("big_num_tag", TAG["BigNum"]), ret("big_num_tag", "val")]), 19)),
+            (SYM["comm"], [match("val_tag", [
+                (TAG["BigNum"], [const("comm_tag", TAG["Comm"]), ret("comm_tag", "val")]),
+                (TAG["Comm"], [ret("val_tag", "val")])]), const("err", 20), ret("err_tag", "err")]),   # CantCastToComm
+        ], exhaustive=True)], partial=True)
     # eval_coroutine_expr when the Lang has no coroutines (eval_direct.rs:196-222): never callable, not partial
     coroutine_stub = func("eval_coroutine_expr", ["_head", "_args_tag", "_args", "_env"], 2, [
         const("zero", 0), const("one", 1), assert_eq("zero", "one"), ret("zero", "zero")])
@@ -775,16 +803,15 @@ def lurk_core_toplevel():
     """The restated evaluator put together: data path (preallocate, ingress, egress, hash3/4/5, extend_env_with_mutuals:
     lurk_b200/programs.py::lurk_data_toplevel) + evaluator core (eval, apply, eval_begin, eval_list, env_lookup, eval_let,
     eval_letrec*, equal*, car_cdr, open_comm, coerce_if_sym, eval_builtin_expr and the built-in operator family: above,
-    with the real preallocated pointers) -- 38 of the reference's 39 funcs; only eval_unop (u64 / char / atom / emit /
-    bignum / comm casts, needs the `emit` op) answers (Err, Todo).  `lurk_eval_demo(expr)` = preallocate_symbols,
+    with the real preallocated pointers) -- all 39 funcs of the reference's native Lurk toplevel (`emit` is accepted and
+    keeps no side channel; `breakpoint` is a no-op).  `lurk_eval_demo(expr)` = preallocate_symbols,
     ingress, eval in the empty environment, egress: Lurk programs evaluated for real."""
     from lurk_b200.lair import Toplevel, call, const, func, ret
     from lurk_b200.programs import LURK_SYMBOL_PTRS as PTR, lurk_data_toplevel as data_toplevel
     data = data_toplevel()
     ev = lurk_eval_subset_toplevel(PTR["nil"], PTR["t"], PTR["&rest"])
     take = lambda top, names: [f for f in top.funcs_e if f.name in names]
-    todo = [const("err_tag", TAG["Err"]), const("todo", 21), ret("err_tag", "todo")]            # EvalErr::Todo
-    stubs = [func("eval_unop", ["head", "rest_tag", "rest", "env"], 2, todo, partial=True)]      # needs `emit`: not restated
+    stubs = []
     demo = func("lurk_eval_demo", [("tag_full", 8), ("digest", 8)], 9, [
         call([], "preallocate_symbols", []),
         call(["tag", "ptr"], "ingress", ["tag_full", "digest"]),
@@ -796,7 +823,7 @@ def lurk_core_toplevel():
              + take(ev, {"eval", "apply", "env_lookup", "eval_begin", "eval_list", "eval_let", "eval_letrec",
                          "eval_letrec_bindings", "equal", "equal_inner", "car_cdr", "open_comm", "coerce_if_sym",
                          "eval_builtin_expr", "eval_coroutine_expr", "eval_binop_num", "eval_binop_misc", "eval_env_builtin",
-                         "eval_apply_builtin", "eval_bind_builtin", "eval_hide", "eval_opening_unop",
+                         "eval_apply_builtin", "eval_bind_builtin", "eval_hide", "eval_opening_unop", "eval_unop",
                          "u64_add", "u64_sub", "u64_mul", "u64_divrem", "u64_lessthan", "u64_iszero", "digest_equal",
                          "big_num_lessthan"}) + stubs)
     return Toplevel(funcs, ev.chips)

@@ -194,7 +194,7 @@ def lurk_eval_subset_toplevel(nil_ptr=4242, t_ptr=4343, rest_ptr=4444):
     def stub(name, params):
         return func(name, params, 2, [ret(params[0], params[1])], partial=True)
     # eval_builtin_expr (eval_direct.rs:443-765): the dispatcher on the head symbol of a built-in form, statement for
-    # statement (the `breakpoint` pseudo-op, which has no effect on the trace, is left out); eval_unop is a stub
+    # statement (the `breakpoint` pseudo-op, which has no effect on the trace, is left out)
     from lurk_b200.programs import LURK_SYMBOL_PTRS as SYM
     inv_ = [ret("err_tag", "invalid_form")]
     def need_cons():

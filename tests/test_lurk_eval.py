@@ -1,4 +1,4 @@
-"""Builtin-free Lurk expressions evaluated by the restated evaluator (tests/lair_programs.py::lurk_core_toplevel: the
+"""Builtin-free Lurk expressions evaluated by the restated evaluator (lurk_b200/lurk_eval.py::lurk_core_toplevel: the
 reference's eval / apply / eval_begin / eval_list / env_lookup / ingress / egress, statement for statement): the
 expression is interned by the ZStore, ingressed, evaluated in the empty environment, egressed, and the result must be
 the ZPtr Lurk's semantics give.  Functions are written as literal Fun objects (the `lambda` builtin is not restated)."""
@@ -188,3 +188,33 @@ def test_lurk_programs_prove_bit_exact_on_the_gpu(oracle, name):
     proof = m.prove(pk, Shard.new(q))
     assert np.array_equal(proof.words, om.prove(rec))
     m.verify(vk, proof)
+
+
+def _run_main(top, z, expr, env):
+    # lurk_main(full_expr_tag: [8], expr_digest: [8], env_digest: [8]): [16]  (eval_direct.rs:120-138)
+    q = QueryRecord.new(top)
+    z.inject(q, top)
+    args = [expr.tag] + [0] * 7 + list(expr.digest) + list(env.digest)
+    out = [int(v) for v in execute_by_name(top, "lurk_main", args, q)]
+    assert out[1:8] == [0] * 7
+    return q, (out[0], out[8:])
+
+
+def test_lurk_main_is_the_entry_point_of_the_packaged_toplevel():
+    # build_lurk_toplevel() (lurk_b200/lurk_eval.py): the reference's entry point takes the expression AND the environment
+    # by digest; run fib(10) in the empty environment and a variable in a two-binding environment through it
+    from lurk_b200.lurk_eval import build_lurk_toplevel
+    top = build_lurk_toplevel()
+    z = ZStore()
+    progs = {n: (e, w) for n, e, w in _programs(z)}
+    expr, want = progs["(letrec ((fib ...)) (fib 10)) = 55  [benches/fib.rs shape]"]
+    _, got = _run_main(top, z, expr, z.null(TAG["Env"]))
+    assert got == (want.tag, list(want.digest))
+    x, y = z.lurk_sym("x"), z.lurk_sym("y")
+    env = z.tuple110(TAG["Env"], x, z.num(7), z.tuple110(TAG["Env"], y, z.u64(9), z.null(TAG["Env"])))
+    for sym, val in ((x, z.num(7)), (y, z.u64(9))):
+        _, got = _run_main(top, z, sym, env)
+        assert got == (val.tag, list(val.digest))
+    plus = z.list([z.builtin("+"), x, z.num(35)])
+    _, got = _run_main(top, z, plus, env)
+    assert got == (TAG["Num"], list(z.num(42).digest))

@@ -118,3 +118,26 @@ def test_lurk_evaluator_funcs_have_the_reference_widths():
     for name, width in goldens.KNOWN_ANSWERS["lurk_eval_subset_widths"]["value"].items():
         assert FuncChip.from_name(name, top).width() == width, name
     assert np.array_equal(host.compile_toplevel(top.surface_image()), top.serialize_py())
+
+
+def test_the_assembled_lurk_toplevel_has_every_reference_width():
+    # build_lurk_toplevel (lurk_b200/lurk_eval.py; src/core/eval_direct.rs:29-118) assembled from the real funcs only --
+    # no stubs -- gives all 39 widths of the reference's test_widths (eval_direct.rs:2025-2063) in ONE toplevel, in the
+    # Python specification and through the C++ host layer alike
+    from lurk_b200 import host
+    from lurk_b200.lair import FuncChip
+    from lurk_b200.lurk_eval import build_lurk_toplevel
+    top = build_lurk_toplevel()
+    want = dict(lurk_main=97, preallocate_symbols=188, eval_coroutine_expr=10, eval=78, eval_builtin_expr=148,
+                eval_bind_builtin=110, eval_env_builtin=81, eval_apply_builtin=79, eval_opening_unop=97, eval_hide=115,
+                eval_unop=78, eval_binop_num=107, eval_binop_misc=70, eval_begin=68, eval_list=72, eval_let=94,
+                eval_letrec=66, extend_env_with_mutuals=54, eval_letrec_bindings=66, coerce_if_sym=9, open_comm=50,
+                equal=86, equal_inner=58, car_cdr=61, apply=114, env_lookup=52, ingress=104, egress=81, hash3=493,
+                hash4=655, hash5=815, u64_add=53, u64_sub=53, u64_mul=85, u64_divrem=166, u64_lessthan=44,
+                u64_iszero=26, digest_equal=38, big_num_lessthan=78)
+    assert len(want) == 39
+    assert {f.name for f in top.funcs_e} == set(want) | {"lurk_eval_demo"}
+    assert top.funcs_e[0].name == "lurk_main"
+    for name, width in want.items():
+        assert FuncChip.from_name(name, top).width() == width, name
+    assert np.array_equal(host.compile_toplevel(top.surface_image()), top.serialize_py())

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """benches/fib.rs for real: (letrec ((fib (lambda (n) (if (< n 2) n (+ (fib (- n 1)) (fib (- n 2))))))) (fib N)) evaluated by
-the restated Lurk evaluator (tests/lair_programs.py::lurk_core_toplevel, all 39 funcs of the reference's toplevel) and proved on the
+the restated Lurk evaluator (lurk_b200/lurk_eval.py::lurk_core_toplevel, all 39 funcs of the reference's toplevel) and proved on the
 GPU.  N = 95324 gives 2^20 rows of the `eval` chip (BASELINE configs[1]: "fib at 2^20 trace rows").
 
     python tools/lurk_fib_prove.py [--n 95324] [--steps 3]          one JSON line

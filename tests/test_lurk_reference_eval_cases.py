@@ -199,3 +199,54 @@ def test_reference_raw_eval_case(name):
     build, expected = RAW_CASES[name]
     z = ZStore()
     assert lurk_main(z, build(z), z.null(TAG["Env"])) == expected(z), name
+
+
+PROVE_CASES = ["(letrec ((sum (lambda (x &rest y) (if y (+ x (apply sum y)) x)))) (sum 1 2 3 4 5 6 7 8 9 10))",
+               "(hide (bignum (commit 321)) 123)", "(u64 'a')", f"(< #0x{BIG_A} #0x{BIG_B})"]
+
+
+def _oracle_main(oracle, top, z, expr):
+    ot = oracle.OracleToplevel(top.serialize())
+    rec = oracle.OracleRecord(ot)
+    for name, width in (("hash3", 24), ("hash4", 32), ("hash5", 40)):
+        if z.hashes[width]:
+            rec.inject_inv_queries(top.func_by_name(name).index, [list(k) for k in z.hashes[width]],
+                                   [list(v) for v in z.hashes[width].values()])
+    f = top.func_by_name("lurk_main")
+    out = rec.execute(f.index, [expr.tag] + [0] * 7 + list(expr.digest) + [0] * 8, f.output_size)
+    return ot, rec, [int(v) for v in out]
+
+
+@pytest.mark.parametrize("code", PROVE_CASES[:2])
+def test_reference_eval_case_on_the_oracle(oracle, code):
+    # the oracle's executor agrees with the native one on the full toplevel through lurk_main
+    z = ZStore()
+    expr = read(z, code)
+    want = dict(CASES)[code](z)
+    _, _, out = _oracle_main(oracle, toplevel(), z, expr)
+    assert (out[0], tuple(out[8:])) == (want.tag, want.digest)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("code", PROVE_CASES)
+def test_reference_eval_case_proves_bit_exact_on_the_gpu(oracle, code):
+    # the reference's path end to end: read, lurk_main over the full 40-func toplevel, GPU proof == oracle proof, verified
+    import numpy as np
+    from lurk_b200.execute import Shard
+    from lurk_b200.machine import SphinxCoreOpts, new_machine
+    top = toplevel()
+    z = ZStore()
+    expr = read(z, code)
+    want = dict(CASES)[code](z)
+    m = new_machine(top, "lurk_main", opts=SphinxCoreOpts(num_queries=6, proof_of_work_bits=6))
+    pk, vk = m.setup()
+    q = QueryRecord.new(top)
+    z.inject(q, top)
+    out = [int(v) for v in execute_by_name(top, "lurk_main", [expr.tag] + [0] * 7 + list(expr.digest) + [0] * 8, q)]
+    assert (out[0], tuple(out[8:])) == (want.tag, want.digest)
+    ot, rec, oout = _oracle_main(oracle, top, z, expr)
+    assert oout == out
+    om = oracle.OracleMachine(ot, m.entry.index, m.blob, 6, 6)
+    proof = m.prove(pk, Shard.new(q))
+    assert np.array_equal(proof.words, om.prove(rec))
+    m.verify(vk, proof)

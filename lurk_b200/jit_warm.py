@@ -1,4 +1,4 @@
-"""Fill the cubin cache of the compiled constraint programs (csrc/jit.cu) for the stock hasher programs.
+"""Fill the cubin cache of the compiled constraint programs (csrc/jit.cu) for the stock programs (hash / u64 / fib demos and the full Lurk toplevel).
 
     python -m lurk_b200.jit_warm
 
@@ -25,8 +25,10 @@ def precompile(toplevel, entry: str) -> dict:
 
 def stock_programs():
     from .lair import demo_toplevel
+    from .lurk_eval import build_lurk_toplevel
     from .programs import hash_toplevel, u64_toplevel
-    return [(hash_toplevel(), "cons_chain"), (u64_toplevel(), "factu"), (demo_toplevel(), "fib")]
+    return [(hash_toplevel(), "cons_chain"), (u64_toplevel(), "factu"), (demo_toplevel(), "fib"),
+            (build_lurk_toplevel(), "lurk_main")]      # the 41 chips behind tools/lurk_prove.py (benches/fib, lcs, sum)
 
 
 def main():

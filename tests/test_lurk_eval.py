@@ -169,7 +169,7 @@ def test_lurk_programs_evaluate(name):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["(letrec ((fib ...)) (fib 10)) = 55  [benches/fib.rs shape]", "(open (commit 123))"])
 def test_lurk_programs_prove_bit_exact_on_the_gpu(oracle, name):
-    # benches/fib.rs in miniature: the Lurk program is interned, ingressed, evaluated by the restated evaluator (38 func
+    # benches/fib.rs in miniature: the Lurk program is interned, ingressed, evaluated by the restated evaluator (39 func
     # chips, the u64 chipsets with their byte lookups, hash3/4/5 with preimages, partial funcs with depth provenance),
     # and the GPU proof equals the oracle's word for word and verifies
     import numpy as np

@@ -250,3 +250,19 @@ def test_reference_eval_case_proves_bit_exact_on_the_gpu(oracle, code):
     proof = m.prove(pk, Shard.new(q))
     assert np.array_equal(proof.words, om.prove(rec))
     m.verify(vk, proof)
+
+
+def test_reference_eval_case_proves_and_verifies_on_the_oracle(oracle):
+    # the CPU oracle prover on the full 41-chip machine behind lurk_main: prove, verify, and reject a tampered proof
+    from test_oracle_stark import oracle_machine
+    top = toplevel()
+    z = ZStore()
+    expr = read(z, "(u64 'a')")
+    ot, rec, out = _oracle_main(oracle, top, z, expr)
+    assert (out[0], tuple(out[8:])) == (TAG["U64"], z.u64(97).digest)
+    _, om, _ = oracle_machine(oracle, top, "lurk_main")      # public values: 24 inputs, 16 outputs, depth (partial func)
+    proof = om.prove(rec)
+    assert om.verify(proof), om.last_error
+    bad = proof.copy()
+    bad[len(bad) // 2] ^= 1
+    assert not om.verify(bad)

@@ -7,6 +7,9 @@ and verified.  One JSON line per program.
     python tools/lurk_prove.py --program lcs --arg 10        (leading characters of the reference's two strings)
     python tools/lurk_prove.py --program sum --arg 2000
     python tools/lurk_prove.py --exec-only ...                 rows per chip, no GPU
+
+The executor recurses as deep as the Lurk program does (100000 frames for the default fib / sum arguments): run under
+`ulimit -s unlimited`, as the measured lines in profiles/r1_lurk_bench_programs.jsonl were.
 """
 import argparse
 import json

@@ -118,7 +118,7 @@ void operand(std::string& o, uint32_t w, const ChipH& c, long local_def) {
       if (local_def >= 0) snprintf(buf, sizeof buf, "t%ld", local_def);
       else snprintf(buf, sizeof buf, "LSK_R(%u)", idx);
       break;
-    case 1: snprintf(buf, sizeof buf, "%uu", to_mont(c.consts[idx] % P)); break;   // Montgomery literal
+    case 1: snprintf(buf, sizeof buf, "%uu", to_mont(c.consts.at(idx) % P)); break;   // Montgomery literal
     case 2: snprintf(buf, sizeof buf, "LSK_ML(%u)", idx); break;
     case 3: snprintf(buf, sizeof buf, "LSK_MN(%u)", idx); break;
     case 4: snprintf(buf, sizeof buf, "LSK_PL(%u)", idx); break;
@@ -261,18 +261,45 @@ bool jit_eligible(const ChipH& c) {
   return c.code.size() / 4 >= min_instr;
 }
 
+// Cache entry = 48-byte header {magic, NVRTC version, key[2], payload length, payload checksum} + cubin.  The key is 128
+// bits over everything that decides the machine code: the generated sources, the two device headers and the compile
+// options; the header also names the NVRTC version that produced the entry, and an entry from another version is not
+// used when this process can load NVRTC (and so could tell).  An entry whose header, length or checksum does not match is a miss (it is
+// recompiled under LSK_JIT=1, otherwise the chip is interpreted): a stale, truncated or foreign file never runs.
+constexpr uint64_t JIT_CACHE_MAGIC = 0x4c534b514a495431ull;  // "LSKQJIT1"
+static const char* const JIT_OPTS[] = {"--gpu-architecture=sm_100a", "--std=c++17"};
+struct JitCacheHeader { uint64_t magic, nvrtc_version, key0, key1, length, checksum; };
+
 bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, std::string* how) {
   const std::string program_hdr = program_source(c), main_src = main_source(c);
-  uint64_t key = fnv1a(program_hdr);
-  key = fnv1a(main_src, key);
-  key = fnv1a(FIELD_CUH_SRC, key);
-  key = fnv1a(QUOTIENT_KERNEL_CUH_SRC, key);
-  char name[64];
-  snprintf(name, sizeof name, "/q_%016llx_sm100a.cubin", (unsigned long long)key);
+  int vmaj = 0, vmin = 0;
+  if (nvrtc().ok && nvrtc().Version) nvrtc().Version(&vmaj, &vmin);
+  const uint64_t rtc_version = (uint64_t)vmaj * 1000 + (uint64_t)vmin;   // 0: NVRTC not loadable here
+  uint64_t key[2];
+  for (int h = 0; h < 2; h++) {
+    uint64_t k = h ? 0x9e3779b97f4a7c15ull : 1469598103934665603ull;
+    for (const std::string& part : {program_hdr, main_src, std::string(FIELD_CUH_SRC), std::string(QUOTIENT_KERNEL_CUH_SRC),
+                                    std::string(JIT_OPTS[0]), std::string(JIT_OPTS[1])}) {
+      k = fnv1a(std::to_string(part.size()) + ":", k);
+      k = fnv1a(part, k);
+      if (h) k = (k ^ (k >> 29)) * 0xbf58476d1ce4e5b9ull;
+    }
+    key[h] = k;
+  }
+  char name[96];
+  snprintf(name, sizeof name, "/q_%016llx%016llx_sm100a.cubin", (unsigned long long)key[0], (unsigned long long)key[1]);
   const std::string dir = cache_dir(), path = dir + name;
-  if (read_file(path, cubin)) {
-    if (how) *how = "cache";
-    return true;
+  std::vector<char> file;
+  if (read_file(path, file) && file.size() > sizeof(JitCacheHeader)) {
+    JitCacheHeader hd;
+    memcpy(&hd, file.data(), sizeof hd);
+    const size_t n = file.size() - sizeof hd;
+    if (hd.magic == JIT_CACHE_MAGIC && (!rtc_version || hd.nvrtc_version == rtc_version) && hd.key0 == key[0] && hd.key1 == key[1] && hd.length == n &&
+        hd.checksum == fnv1a(std::string(file.data() + sizeof hd, n))) {
+      cubin.assign(file.begin() + sizeof hd, file.end());
+      if (how) *how = "cache";
+      return true;
+    }
   }
   if (!compile_on_miss) return false;
   if (!nvrtc().ok) fail(LSK_ERR_CUDA, "NVRTC (libnvrtc.so.12) could not be loaded");
@@ -281,8 +308,7 @@ bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, s
   const char* hdr_name[3] = {"field.cuh", "quotient_kernel.cuh", "lsk_program.cuh"};
   if (nvrtc().CreateProgram(&prog, main_src.c_str(), "lsk_quotient_jit.cu", 3, hdr_src, hdr_name) != 0)
     fail(LSK_ERR_CUDA, "nvrtcCreateProgram failed");
-  const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17"};
-  int rc = nvrtc().CompileProgram(prog, 2, opts);
+  int rc = nvrtc().CompileProgram(prog, 2, JIT_OPTS);
   if (rc != 0) {
     size_t n = 0;
     nvrtc().GetProgramLogSize(prog, &n);
@@ -296,7 +322,13 @@ bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, s
   cubin.resize(n);
   nvrtc().GetCUBIN(prog, cubin.data());
   nvrtc().DestroyProgram(&prog);
-  write_file(dir, path, cubin);
+  {
+    JitCacheHeader hd{JIT_CACHE_MAGIC, rtc_version, key[0], key[1], cubin.size(), fnv1a(std::string(cubin.data(), cubin.size()))};
+    std::vector<char> out(sizeof hd + cubin.size());
+    memcpy(out.data(), &hd, sizeof hd);
+    memcpy(out.data() + sizeof hd, cubin.data(), cubin.size());
+    write_file(dir, path, out);
+  }
   if (how) *how = "compiled";
   return true;
 }

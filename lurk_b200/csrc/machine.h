@@ -105,6 +105,17 @@ inline std::vector<ChipH> parse_machine_blob(const uint32_t* w, size_t n, uint32
       }
     }
     if (p != end) fail(LSK_ERR_ARG, "chip descriptor length mismatch");
+    // interaction operands are walked unchecked by the prover (perm_rows) and the verifier (eval_affine)
+    for (int s = 0; s < 2; s++)
+      for (auto& it : (s == 0 ? c.sends : c.receives)) {
+        auto check_affine = [&](const AffineH& a) {
+          for (auto& t : a.terms)
+            if (t[0] > 1 || t[1] >= (t[0] ? c.prep_width : c.width))
+              fail(LSK_ERR_ARG, "an interaction of chip %s references a column outside its trace", c.name.c_str());
+        };
+        check_affine(it.mult);
+        for (auto& v : it.values) check_affine(v);
+      }
     if (c.lqd != 1) fail(LSK_ERR_ARG, "only log_quotient_degree = 1 is supported (chip %s)", c.name.c_str());
     if (c.width > (1u << 20) || c.prep_width > (1u << 20) || c.n_regs > (1u << 20))
       fail(LSK_ERR_ARG, "implausible sizes in the descriptor of chip %s", c.name.c_str());

@@ -345,6 +345,16 @@ void verify_shard(const VerifyingKey& vk, const ShardProofV& sp, Challenger ch) 
     if (c.kind == CHIP_ENTRY) VCHECK(co.logn == 0 && sp.index == 0, "entrypoint shape");
     if (c.kind == CHIP_MEM) VCHECK(sp.index == 0, "memory chip outside shard 0");
   }
+  // The chip set of a shard is not the prover's choice (MachineAir::included, src/lair/lair_chip.rs:124-139): the
+  // Entrypoint -- the only chip that ties the public values to the computation (lair_chip.rs:166-191) -- and every
+  // memory table belong to shard 0 and to no other shard, the byte table to every shard (sphinx likewise insists on
+  // its "CPU" chip, which is why the byte chip carries that name: lair_chip.rs:90-92).  Func chips are present when
+  // they have rows; leaving one out only removes provides, which the cumulative-sum check then misses.
+  for (size_t i = 0; i < vk.chips.size(); i++) {
+    const ChipH& c = vk.chips[i];
+    const bool must = c.kind == CHIP_BYTES || (sp.index == 0 && (c.kind == CHIP_ENTRY || c.kind == CHIP_MEM));
+    VCHECK(!must || seen[i], "shard %u lacks the %s chip", sp.index, c.name.c_str());
+  }
   Ext chal_alpha = ch.sample_ext(), chal_beta = ch.sample_ext();
   ch.observe_n(sp.perm_root.data(), 8);
   Ext alpha = ch.sample_ext();
@@ -522,6 +532,7 @@ int lsk_vk_new(const uint32_t* blob, size_t n, const uint32_t prep_commit[8], in
   LSK_API_BEGIN
   if (!blob || !out || !prep_commit) fail(LSK_ERR_ARG, "null argument");
   auto vk = std::make_unique<lsk_vk>();
+  if (num_queries == 0 || num_queries > 1024 || pow_bits > 30) fail(LSK_ERR_ARG, "bad FRI parameters");
   vk->key.chips = parse_machine_blob(blob, n, &vk->key.num_pv);
   for (int k = 0; k < 8; k++) {
     if (prep_commit[k] >= P) fail(LSK_ERR_ARG, "non-canonical commitment");

@@ -202,24 +202,3 @@ def new_machine(toplevel: Toplevel, entry: Optional[str] = None, ctx: Optional[N
 def assemble_proof(shard_words: List[np.ndarray]) -> MachineProof:
     head = np.asarray([PROOF_MAGIC, len(shard_words)], dtype=np.uint32)
     return MachineProof(np.concatenate([head] + [N.u32(w) for w in shard_words]))
-
-
-def smoke_prove():
-    """One small prove on cuda:0 checked bit-for-bit against the CPU oracle (used by smoke())."""
-    from oracle import pyoracle
-    from .execute import QueryRecord, execute_by_name
-    from .lair import demo_toplevel
-    top = demo_toplevel()
-    opts = SphinxCoreOpts(num_queries=8, proof_of_work_bits=8)
-    m = new_machine(top, "fib", opts=opts)
-    pk, _ = m.setup()
-    q = QueryRecord.new(top)
-    execute_by_name(top, "fib", [300], q)
-    proof = m.prove(pk, Shard.new(q))
-    ot = pyoracle.OracleToplevel(top.serialize())
-    om = pyoracle.OracleMachine(ot, m.entry.index, m.blob, opts.num_queries, opts.proof_of_work_bits)
-    rec = pyoracle.OracleRecord(ot)
-    rec.execute(m.entry.index, [300], 1)
-    want = om.prove(rec)
-    assert np.array_equal(proof.words, want), "GPU proof != oracle proof"
-    assert om.verify(proof.words), om.last_error

@@ -27,6 +27,14 @@ void orc_machine_prep_commit(void* m, uint32_t* out8) {
   for (int i = 0; i < 8; i++) out8[i] = ((Machine*)m)->prep_commit.d[i].to_u32();
 }
 
+// negative tests: a prover that omits chips / claims public values it did not compute
+void orc_machine_forge_omit_kinds(void* m, uint32_t kind_mask) { ((Machine*)m)->forge_omit_kinds = kind_mask; }
+void orc_record_set_public_values(void* record, const uint32_t* pv, size_t n) {
+  auto& v = ((QueryRecord*)record)->public_values;
+  v.clear();
+  for (size_t i = 0; i < n; i++) v.push_back(Fp::from_u32(pv[i]));
+}
+
 // returns a malloc'd buffer of u32 words (free with orc_free)
 int orc_prove(void* m, void* record, uint32_t shard_size, uint32_t** out, size_t* out_len) {
   try {

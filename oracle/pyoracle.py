@@ -129,6 +129,11 @@ class OracleRecord:
         if rc:
             raise RuntimeError(_err())
 
+    def set_public_values(self, pv):
+        """Negative tests only: claim public values the record did not compute."""
+        v = _u32(list(pv))
+        lib().orc_record_set_public_values(ctypes.c_void_p(self.h), _vp(v), ctypes.c_size_t(len(v)))
+
     def num_queries(self, func):
         return lib().orc_num_queries(ctypes.c_void_p(self.h), func)
 
@@ -194,6 +199,11 @@ class OracleMachine:
         if getattr(self, "h", None):
             lib().orc_machine_free(ctypes.c_void_p(self.h))
 
+    def forge_omit_kinds(self, kind_mask):
+        """Negative tests only: prove as a dishonest prover that leaves out the chips of these kinds
+        (bit 0 func, 1 memory, 2 bytes, 3 entrypoint)."""
+        lib().orc_machine_forge_omit_kinds(ctypes.c_void_p(self.h), kind_mask)
+
     def prep_commit(self):
         out = np.zeros(8, dtype=np.uint32)
         lib().orc_machine_prep_commit(ctypes.c_void_p(self.h), _vp(out))
@@ -235,3 +245,68 @@ def merkle_root(mats):
     rc = lib().orc_merkle_root(ptrs, hs, ws, ctypes.c_size_t(n), _vp(out))
     assert rc == 0
     return out
+
+
+# ---- independent AIR / lookup checker (oracle/air_check.h) ----------------------------------------
+AIR_FUNC, AIR_MEM, AIR_BYTES, AIR_ENTRY = 0, 1, 2, 3
+
+
+class AirCheckError(AssertionError):
+    pass
+
+
+class TraceQueries:
+    """TraceQueries (src/air/debug.rs:26-116): the messages and memoset accesses of the traces checked so far."""
+
+    def __init__(self, top: OracleToplevel):
+        L = lib()
+        L.orc_tq_new.restype = ctypes.c_void_p
+        L.orc_air_last_error.restype = ctypes.c_char_p
+        self.top = top
+        self.h = L.orc_tq_new()
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_tq_free(ctypes.c_void_p(self.h))
+
+    def check(self, kind, index, main, prep=None, public_values=()):
+        """debug_constraints_collecting_queries (debug.rs:161-206): every constraint of every row must hold;
+        raises AirCheckError naming the first failing constraint and row."""
+        m = _u32(main)
+        assert m.ndim == 2
+        p = _u32(prep) if prep is not None else None
+        pv = _u32(list(public_values))
+        rc = lib().orc_air_check(ctypes.c_void_p(self.top.h), ctypes.c_void_p(self.h), kind, index, _vp(m),
+                                 ctypes.c_size_t(m.shape[0]), ctypes.c_size_t(m.shape[1]),
+                                 _vp(p) if p is not None else None, ctypes.c_size_t(p.shape[1] if p is not None else 0),
+                                 _vp(pv), ctypes.c_size_t(len(pv)))
+        if rc:
+            raise AirCheckError(lib().orc_air_last_error().decode())
+
+    def verify(self):
+        """TraceQueries::verify (debug.rs:91-107): sends == receives, every memoset chain closes."""
+        if lib().orc_tq_verify(ctypes.c_void_p(self.h)):
+            raise AirCheckError(lib().orc_air_last_error().decode())
+
+    def has_memoset_key(self, key) -> bool:
+        k = _u32(list(key))
+        return bool(lib().orc_tq_has_memoset_key(ctypes.c_void_p(self.h), _vp(k), ctypes.c_size_t(len(k))))
+
+    def counts(self):
+        out = (ctypes.c_uint64 * 3)()
+        lib().orc_tq_counts(ctypes.c_void_p(self.h), out)
+        return {"sends": out[0], "receives": out[1], "memoset_keys": out[2]}
+
+
+def air_cross_check(top: OracleToplevel, machine_blob, chip: int, nrows=3, seed=1):
+    """The captured chip vector ('MACH' blob) against the oracle's direct restatement of Air::eval on random rows:
+    -> (constraints, sends, receives) compared; raises AirCheckError on the first difference."""
+    L = lib()
+    L.orc_air_last_error.restype = ctypes.c_char_p
+    blob = _u32(machine_blob)
+    counts = (ctypes.c_uint32 * 3)()
+    rc = L.orc_air_cross_check(ctypes.c_void_p(top.h), _vp(blob), ctypes.c_size_t(len(blob)), chip, nrows,
+                               ctypes.c_uint64(seed), counts)
+    if rc:
+        raise AirCheckError(L.orc_air_last_error().decode())
+    return counts[0], counts[1], counts[2]

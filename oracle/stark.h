@@ -430,6 +430,9 @@ struct Machine {
   MerkleTree prep_tree;
   int prep_chip = -1;
   Digest prep_commit;
+  // TEST HOOK (negative tests of the verifiers only): a dishonest prover that leaves out every chip whose kind bit
+  // is set here, whatever MachineAir::included says
+  uint32_t forge_omit_kinds = 0;
 };
 
 static inline void machine_setup(Machine& m) {

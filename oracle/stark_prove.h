@@ -42,6 +42,7 @@ struct ShardData {
 };
 
 static inline bool chip_included(const Machine& m, const Chip& c, const QueryRecord& q, uint32_t shard, uint32_t ss) {
+  if ((m.forge_omit_kinds >> c.kind) & 1u) return false;
   switch (c.kind) {  // MachineAir::included, src/lair/lair_chip.rs:124-139
     case KIND_FUNC: return shard_func_range(q, c.index, shard, ss).len() > 0;
     case KIND_MEM: return shard == 0;
@@ -462,6 +463,7 @@ static inline ShardProof prove_shard(const Machine& m, const QueryRecord& q, Sha
 
 static inline std::vector<uint32_t> prove(const Machine& m, const QueryRecord& q, uint32_t shard_size) {
   uint32_t ns = num_shards(q, shard_size);
+  if (!ns && m.forge_omit_kinds) ns = 1;   // the forger proves a record in which nothing was executed
   if (!ns) throw std::runtime_error("empty record");
   Challenger ch;
   observe_machine(m, ch);
@@ -509,6 +511,15 @@ static inline void verify_shard(const Machine& m, const ShardProof& sp, Challeng
     VCHECK(co.quotient[0].size() == 4 && co.quotient[1].size() == 4, "quotient opening width");
     if (c.kind == KIND_BYTES) VCHECK(co.log_degree == 16, "byte table height");
     if (c.kind == KIND_ENTRY) VCHECK(co.log_degree == 0 && sp.shard_index == 0, "entrypoint shape");
+    if (c.kind == KIND_MEM) VCHECK(sp.shard_index == 0, "memory chip outside shard 0");
+  }
+  // MachineAir::included (src/lair/lair_chip.rs:124-139) is binding on the prover: Entrypoint and the memory tables
+  // in shard 0 only, the byte table ("CPU", lair_chip.rs:90-92) in every shard.  Without the Entrypoint nothing ties
+  // the public values to the computation.
+  for (size_t i = 0; i < m.chips.size(); i++) {
+    const Chip& c = m.chips[i];
+    bool must = c.kind == KIND_BYTES || (sp.shard_index == 0 && (c.kind == KIND_ENTRY || c.kind == KIND_MEM));
+    VCHECK(!must || seen[i], "a chip MachineAir::included demands is missing from the shard");
   }
   Ef chal_alpha = ch.sample_ext(), chal_beta = ch.sample_ext();
   ch.observe(sp.perm_commit);

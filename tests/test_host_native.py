@@ -209,3 +209,16 @@ def test_lurk_misc_u64_funcs_native_executor(oracle):
         q = QueryRecord.new(top)
         out = execute_by_name(top, "u64_demo", u64_bytes(a) + u64_bytes(b), q)
         assert [int(x) for x in out] == _u64_demo_expected(a, b)
+
+
+def test_the_package_never_imports_the_checker():
+    # oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may load it
+    import os
+    import re
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "lurk_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for name in files:
+            if name.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(dirpath, name), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), name
+                assert "liboracle" not in src and "pyoracle" not in src, name

@@ -102,3 +102,55 @@ def test_verifier_survives_hostile_input(oracle):
         k = int(rng.integers(2, n))
         bad[k:] = rng.integers(0, 2 ** 32, size=n - k, dtype=np.uint64).astype(np.uint32)
         rejected(bad)
+
+
+@pytest.mark.parametrize("omit", [0b1011, 0b1000, 0b0010, 0b0100], ids=["only-bytes", "no-entrypoint", "no-memory", "no-bytes"])
+def test_verifier_rejects_a_proof_without_the_chips_included_demands(oracle, omit):
+    # A dishonest prover that leaves out the Entrypoint (the only chip binding the public values, src/lair/lair_chip.rs:
+    # 166-191) can claim ANY public values: with an empty record and only the byte table, every LogUp sum is 0 and the
+    # quotient / FRI checks pass.  Both verifiers must insist on MachineAir::included (lair_chip.rs:124-139).
+    top = goldens.toplevel_for("demo")
+    ot, om, f = oracle_machine(oracle, top, "fib")
+    rec = oracle.OracleRecord(ot)
+    if omit == 0b1011:
+        rec.set_public_values([20, 19110])          # fib(20) is 6765
+    else:
+        rec.execute(f.index, [20], f.output_size)
+    om.forge_omit_kinds(omit)
+    proof = om.prove(rec)
+    om.forge_omit_kinds(0)
+    v = Verifier(top, "fib", VerifyingKey(om.prep_commit()), OPTS)
+    with pytest.raises(VerificationError, match="lacks the"):
+        v.verify(proof)
+    assert not om.verify(proof)
+    assert "included" in om.last_error
+
+
+def test_vk_new_validates_fri_parameters(oracle):
+    top = goldens.toplevel_for("demo")
+    ot, om, f = oracle_machine(oracle, top, "fib")
+    from lurk_b200._native import LurkStarkError
+    for nq, pb in ((0, 6), (2000, 6), (6, 31), (6, 40)):
+        with pytest.raises(LurkStarkError):
+            Verifier(top, "fib", VerifyingKey(om.prep_commit()), SphinxCoreOpts(nq, pb))
+
+
+def test_machine_blob_with_an_out_of_range_interaction_column_is_refused(oracle):
+    from lurk_b200 import host
+    from lurk_b200._native import LurkStarkError
+    top = goldens.toplevel_for("demo")
+    f = top.func_by_name("fib")
+    blob = np.asarray(host.chip_vector_blob(top.surface_image(), f.index), dtype=np.uint32)
+    _, om, _ = oracle_machine(oracle, top, "fib")
+    refused = 0
+    # an affine term is (is_prep, column, coefficient): find (0, col < width, coeff) triples of the entrypoint's
+    # interactions at the tail of its descriptor and push the column out of range
+    for i in range(3, len(blob) - 2):
+        bad = blob.copy()
+        if blob[i] == 0 and blob[i + 1] < 18 and blob[i + 2] == 1:
+            bad[i + 1] = 1 << 19
+            try:
+                Verifier(top, "fib", VerifyingKey(om.prep_commit()), OPTS, blob=bad)
+            except LurkStarkError:
+                refused += 1
+    assert refused > 10

@@ -39,8 +39,28 @@ def source(name: str, arg: int) -> str:
         return fib_source(arg)
     if name == "sum":
         return sum_source(arg)
-    if name == "lcs":        # arg = how many leading characters of the reference's two strings
-        return lcs_source(LCS_ARGS[0][:arg], LCS_ARGS[1][:arg])
+    if name == "lcs":        # arg = how many leading characters of the reference's two strings (repeated cyclically
+        a, b = LCS_ARGS      # beyond their 142 / 121 characters: the bench needs inputs for taller traces than the reference's)
+        return lcs_source((a * (arg // len(a) + 1))[:arg], (b * (arg // len(b) + 1))[:arg])
+    raise ValueError(name)
+
+
+# eval-chip rows (the tallest chip of all three programs) as a function of the argument, measured on the executor:
+# fib(n) -> 10 n + 4, sum over n elements -> 7 n + 9, lcs of two k-character prefixes ~ 21.2 k^2 (data dependent).
+LCS_ARG_FOR_LOG_ROWS = {14: 27, 16: 56, 18: 111, 19: 157, 20: 222, 21: 315, 22: 446}   # largest k whose trace fits 2^L rows (measured)
+
+
+def arg_for_rows(name: str, log_rows: int, shards: int = 1) -> int:
+    """The largest argument whose `eval` trace has at most shards * 2^log_rows rows."""
+    rows = shards << log_rows
+    if name == "fib":
+        return max((rows - 4) // 10, 0)
+    if name == "sum":
+        return max((rows - 9) // 7, 0)
+    if name == "lcs":
+        if shards == 1 and log_rows in LCS_ARG_FOR_LOG_ROWS:
+            return LCS_ARG_FOR_LOG_ROWS[log_rows]
+        return max(int((rows / 21.6) ** 0.5) - 3, 1)
     raise ValueError(name)
 
 

@@ -11,6 +11,9 @@
 //
 // This is the producer of the hot path's input; it is sequential by construction (memo table +
 // nonce order) and stays on the CPU exactly like the reference's.
+#include <pthread.h>
+#include <sys/mman.h>
+#include <exception>
 #include <cstring>
 #include <memory>
 
@@ -739,6 +742,50 @@ void lsk_record_free(lsk_record* r) {
   delete r;
 }
 
+// The executor recurses as deep as the Lair program does (a Lurk `(fib 100000)` nests ~10^6 Lair calls), far beyond a
+// default 8 MB thread stack: it runs on its own thread whose stack is a lazily committed reservation (LSK_EXEC_STACK_GB,
+// default 64 GB of address space; only the pages actually touched are ever backed).
+namespace {
+struct ExecJob {
+  Executor* ex;
+  uint32_t func;
+  const uint32_t* args;
+  uint32_t nargs;
+  std::vector<uint32_t>* out;
+  std::exception_ptr err;
+};
+void* exec_thread(void* arg) {
+  ExecJob* j = (ExecJob*)arg;
+  try {
+    j->ex->run(j->func, j->args, j->nargs, *j->out);
+  } catch (...) {
+    j->err = std::current_exception();
+  }
+  return nullptr;
+}
+void run_on_big_stack(ExecJob& job) {
+  size_t gb = 64;
+  if (const char* e = getenv("LSK_EXEC_STACK_GB")) gb = (size_t)std::max(1L, atol(e));
+  void* stack = MAP_FAILED;
+  size_t size = 0;
+  for (; gb >= 1 && stack == MAP_FAILED; gb /= 2) {
+    size = gb << 30;
+    stack = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_NORESERVE | MAP_STACK, -1, 0);
+  }
+  pthread_attr_t attr;
+  pthread_t th;
+  bool started = false;
+  if (stack != MAP_FAILED && pthread_attr_init(&attr) == 0) {
+    if (pthread_attr_setstack(&attr, stack, size) == 0 && pthread_create(&th, &attr, exec_thread, &job) == 0) started = true;
+    pthread_attr_destroy(&attr);
+  }
+  if (started) pthread_join(th, nullptr);
+  else exec_thread(&job);   // no reservation to be had: the caller's stack will have to do
+  if (stack != MAP_FAILED) munmap(stack, size);
+  if (job.err) std::rethrow_exception(job.err);
+}
+}  // namespace
+
 int lsk_execute(const lsk_program* p, lsk_record* r, uint32_t func, const uint32_t* args, size_t nargs, uint32_t* out,
                 size_t nout) {
   LSK_API_BEGIN
@@ -748,7 +795,8 @@ int lsk_execute(const lsk_program* p, lsk_record* r, uint32_t func, const uint32
   lsk::record_unpin(r);  // the tables are about to grow
   Executor ex(*p, *r);
   std::vector<uint32_t> o;
-  ex.run(func, args, (uint32_t)nargs, o);
+  ExecJob job{&ex, func, args, (uint32_t)nargs, &o, nullptr};
+  run_on_big_stack(job);
   if (o.size() != nout) fail(LSK_ERR_ARG, "output size mismatch");
   for (size_t i = 0; i < nout; i++) out[i] = o[i];
   return LSK_OK;

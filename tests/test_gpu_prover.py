@@ -500,3 +500,29 @@ def test_lurk_ingress_egress_proves_bit_exact(oracle, which):
     proof = m.prove(pk, Shard.new(q))
     assert np.array_equal(proof.words, om.prove(rec))
     m.verify(vk, proof)
+
+
+def test_fib_2pow20_proof_is_bit_exact_default_parameters(oracle):
+    # BASELINE configs[1] on the Lair fib at FULL size and sphinx's default FRI parameters: the GPU proof is word for
+    # word the CPU oracle's proof (the oracle needs ~6 s on 16 cores for it)
+    m, om, q, proof, want = _prove_both(oracle, demo_toplevel(), "fib", [[(1 << 20) - 1]], nq=100, pow_bits=16)
+    assert len(proof.words) == len(want)
+    assert np.array_equal(proof.words, want)
+
+
+@pytest.mark.parametrize("prog,arg", [("fib", 400), ("sum", 300), ("lcs", 12)])
+def test_lurk_bench_programs_prove_bit_exact(oracle, prog, arg):
+    # the reference's three benches (benches/fib.rs, sum.rs, lcs.rs) from source text through lurk_main on the 48-chip
+    # machine, thousands of `eval` rows, default FRI parameters: GPU proof == oracle proof, product verifier accepts
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from bench import CpuProver, Workload
+    wl = Workload("lurk-" + prog)
+    cp = CpuProver(wl)
+    _, want = cp.prove(cp.record(arg))
+    m = new_machine(wl.top, wl.entry)
+    pk, vk = m.setup()
+    q, _ = wl.record(arg)
+    proof = m.prove(pk, Shard.new(q))
+    assert np.array_equal(proof.words, want)
+    m.verify(vk, proof)

@@ -123,3 +123,57 @@ def test_u64_chip_traces_match_oracle(oracle):
         chip = FuncChip.from_name(fname, top)
         assert np.array_equal(chip.generate_trace(Shard.new(q)), rec.func_trace(chip.func.index)), fname
         assert np.array_equal(BytesChip().generate_trace(Shard.new(q)), rec.bytes_trace(0)), fname
+
+
+def test_fib_2pow20_trace_matches_oracle(oracle):
+    # BASELINE configs[1] at full size: 2^20 rows x 18 columns, GPU == oracle cell for cell
+    top = demo_toplevel()
+    n = (1 << 20) - 1
+    q = QueryRecord.new(top)
+    execute_by_name(top, "fib", [n], q)
+    trace = FuncChip.from_name("fib", top).generate_trace(Shard.new(q))
+    want = _oracle_rec(oracle, top, "fib", [n]).func_trace(1)
+    assert trace.shape == (1 << 20, 18)
+    assert np.array_equal(trace, want)
+
+
+def _gpu_record_satisfies_air(oracle, top, q, entry, ss):
+    """debug_chip_constraints_and_queries_with_sharding (src/air/debug.rs:119-158) on the GPU's traces, judged by the
+    oracle's independent restatement of every chip's Air::eval (oracle/air_check.h)."""
+    ot = oracle.OracleToplevel(top.serialize())
+    tq = oracle.TraceQueries(ot)
+    pv = list(q.expect_public_values())
+    cfg = ShardingConfig(ss)
+    prep = BytesChip().generate_preprocessed_trace()
+    for s in Shard(q, 0, cfg).shard(cfg):
+        if s.index == 0:
+            tq.check(oracle.AIR_ENTRY, entry.index, np.asarray([pv], dtype=np.uint32), public_values=pv)
+        for f in top.funcs:
+            if len(s.get_func_range(f.index)):
+                tq.check(oracle.AIR_FUNC, f.index, FuncChip(f, top).generate_trace(s))
+        if s.index == 0:
+            for i, ln in enumerate([2, 3, 4, 5, 6, 8]):
+                tq.check(oracle.AIR_MEM, i, MemChip(ln).generate_trace(s))
+        tq.check(oracle.AIR_BYTES, 0, BytesChip().generate_trace(s), prep=prep)
+    tq.verify()
+    return tq
+
+
+def test_gpu_traces_of_a_lurk_program_satisfy_the_independent_air(oracle):
+    # benches/fib.rs through lurk_main, every chip of the 48-chip machine, 2 shards
+    from lurk_b200.bench_programs import setup
+    from lurk_b200.lurk_eval import build_lurk_toplevel
+    top = build_lurk_toplevel()
+    inp, q, _ = setup("fib", 40, top)
+    execute_by_name(top, "lurk_main", inp, q)
+    tq = _gpu_record_satisfies_air(oracle, top, q, top.func_by_name("lurk_main"), 256)
+    assert tq.counts()["sends"] > 1000
+
+
+@pytest.mark.parametrize("tname,fname,args", [("demo", "fib", [300]), ("partial", "pmain", [300, 21]), ("hash", "cons_chain", [9]),
+                                              ("u64", "divrem", [255] * 8 + [1, 1] + [0] * 6), ("u64", "gcdu", [0, 0, 0, 1, 2, 3, 4, 5] + [0, 7, 0, 0, 9, 0, 0, 0])])
+def test_gpu_traces_satisfy_the_independent_air(oracle, tname, fname, args):
+    top = goldens.toplevel_for(tname)
+    q = QueryRecord.new(top)
+    execute_by_name(top, fname, args, q)
+    _gpu_record_satisfies_air(oracle, top, q, top.func_by_name(fname), 64)

@@ -93,6 +93,35 @@ int lsk_execute(const lsk_program* p, lsk_record* r, uint32_t func, const uint32
                 uint32_t* out, size_t nout);                        /* Toplevel::execute, execute.rs:376-392 */
 int lsk_inject_inv_queries(const lsk_program* p, lsk_record* r, uint32_t func, const uint32_t* inps,
                            const uint32_t* outs, size_t n);         /* execute.rs:299-319 */
+/* Importing a QueryRecord the caller's own executor produced -- the drop-in path behind the UNCHANGED Lurk
+ * evaluator: Rust keeps `toplevel.execute(...)` (src/lair/execute.rs:375-783) and hands the result over table by
+ * table.  lsk_record_import_func: QueryRecord::func_queries[func] (execute.rs:26-33,67-75) in insertion (= nonce)
+ * order -- args [n][in], output [n][out], provide [n][2] = (last_nonce, last_count) (src/air/builder.rs:135-148),
+ * requires as CSR pairs (prev_nonce, prev_count) with n + 1 offsets; for partial funcs depth [n] and
+ * depth_requires (CSR, n + 1 offsets), else NULL.  lsk_record_import_mem: mem_queries[mem_idx] (lengths
+ * 2,3,4,5,6,8; execute.rs:243-257) in insertion order, pointer = index + 1.  lsk_record_import_bytes: BytesRecord
+ * (src/gadgets/bytes/record.rs:14-110) as [65536][6][2] (nonce, count) per ByteInput and operation (range_u8,
+ * range_u16, less_than, and, xor, or); NULL = none.  lsk_record_import_public_values: execute.rs:383-391.
+ * Preimages no imported query produced (inject_inv_queries, execute.rs:299-319) go through lsk_inject_inv_queries.
+ * lsk_record_resolve then replays every row against the tables to find the callee / memory row of each Call,
+ * PreImg and Store -- the lookups src/lair/trace.rs:325-373 repeats per row at trace-generation time -- checking
+ * that every row returns its recorded output; afterwards the record is exactly what lsk_execute builds
+ * (tests/test_host_native.py holds the two equal table for table, tests/test_gpu_prover.py proof for proof). */
+int lsk_record_import_func(const lsk_program* p, lsk_record* r, uint32_t func, size_t n, const uint32_t* args,
+                           const uint32_t* outs, const uint32_t* provide, const uint32_t* req_off, const uint32_t* reqs,
+                           const uint32_t* depth, const uint32_t* dreq_off, const uint32_t* dreqs);
+int lsk_record_import_mem(lsk_record* r, uint32_t mem_idx, size_t n, const uint32_t* vals, const uint32_t* provide);
+int lsk_record_import_bytes(lsk_record* r, const uint32_t* records);
+int lsk_record_import_public_values(lsk_record* r, const uint32_t* pv, size_t n);
+int lsk_record_resolve(const lsk_program* p, lsk_record* r);
+/* the inverse of the imports (row-ordered tables: call lsk_record_finalize first).  sizes = {rows, require pairs,
+ * hints, depth-require pairs}; offset arrays receive rows + 1 entries; any output pointer may be NULL */
+int lsk_record_func_sizes(const lsk_record* r, uint32_t func, size_t sizes[4]);
+int lsk_record_export_func(const lsk_record* r, uint32_t func, uint32_t* args, uint32_t* outs, uint32_t* provide,
+                           uint32_t* req_off, uint32_t* reqs, uint32_t* hint_off, uint32_t* hints, uint32_t* depth,
+                           uint32_t* dreq_off, uint32_t* dreqs);
+int lsk_record_export_mem(const lsk_record* r, uint32_t mem_idx, uint32_t* vals, uint32_t* provide);
+int lsk_record_export_bytes(const lsk_record* r, uint32_t* records);
 size_t lsk_record_num_queries(const lsk_record* r, uint32_t func);
 size_t lsk_record_num_mem(const lsk_record* r, uint32_t mem_idx);
 size_t lsk_record_public_values(const lsk_record* r, uint32_t* out, size_t cap);

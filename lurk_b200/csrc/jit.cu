@@ -203,6 +203,83 @@ std::string program_source(const ChipH& c) {
   return body;
 }
 
+
+// ---- the chip's interactions (sends, then receives: the order of the device descriptor `inter`) as straight-line
+// code.  The interpreter (eval_interaction / eval_affine in quotient_kernel.cuh) walks a descriptor word by word and
+// multiplies every cell by its coefficient; here a coefficient of 1 is no product at all, -1 a subtraction, constants
+// are Montgomery literals, and the LogUp batches of two are unrolled.  Same field operations on the same reduced
+// values, hence the same words.  `V` supplies what a batch is used for: the permutation-trace row (perm_rows) or the
+// LogUp constraints of the quotient.
+void affine_source(std::string& o, const AffineH& a) {
+  std::string acc;
+  char buf[96];
+  const uint32_t cst = a.cst % P;
+  if (cst) {
+    snprintf(buf, sizeof buf, "%uu", to_mont(cst));
+    acc = buf;
+  }
+  for (auto& t : a.terms) {
+    snprintf(buf, sizeof buf, t[0] ? "LSK_CP(%u)" : "LSK_CM(%u)", t[1]);
+    const std::string cell = buf;
+    const uint32_t k = t[2] % P;
+    if (k == 0) continue;
+    if (k == 1) {
+      acc = acc.empty() ? cell : "fadd(" + acc + ", " + cell + ")";
+    } else if (k == P - 1) {
+      acc = acc.empty() ? "fneg(" + cell + ")" : "fsub(" + acc + ", " + cell + ")";
+    } else {
+      snprintf(buf, sizeof buf, "fmul(%s, %uu)", cell.c_str(), to_mont(k));
+      acc = acc.empty() ? std::string(buf) : "fadd(" + acc + ", " + buf + ")";
+    }
+  }
+  o += acc.empty() ? "0u" : acc;
+}
+std::string interactions_source(const ChipH& c) {
+  std::string o;
+  char buf[160];
+  const size_t nint = c.n_interactions();
+  snprintf(buf, sizeof buf, "#define LSK_JIT_NINT %zu\n", nint);
+  o += buf;
+  // one real function per interaction: NVVM's time grows much faster than linearly with the size of a basic block
+  // (cf. the chunks of program_source), and both kernels share the one copy
+  auto one = [&](size_t k) {
+    const bool recv = k >= c.sends.size();
+    const InteractionH& it = recv ? c.receives[k - c.sends.size()] : c.sends[k];
+    snprintf(buf, sizeof buf, "__device__ __noinline__ void lsk_int_%zu(const Cells& c, const Ext& alpha, const Ext* __restrict__ bp, "
+                              "Ext& r, uint32_t& m) {\n  m = ", k);
+    o += buf;
+    std::string m;
+    affine_source(m, it.mult);
+    o += recv ? "fneg(" + m + ")" : m;
+    snprintf(buf, sizeof buf, ";\n  r = eadd_base(alpha, %uu);\n", to_mont(it.kind % P));
+    o += buf;
+    for (size_t j = 0; j < it.values.size(); j++) {
+      std::string val;
+      affine_source(val, it.values[j]);
+      if (val == "0u") continue;   // adds beta^(j+1) * 0
+      snprintf(buf, sizeof buf, "  r = eadd(r, emul_base(bp[%zu], ", j);
+      o += buf;
+      o += val + "));\n";
+    }
+    o += "}\n";
+  };
+  for (size_t k = 0; k < nint; k++) one(k);
+  o += "template <class V>\n__device__ __forceinline__ void lsk_interactions(const Cells& c, const Ext& alpha, "
+       "const Ext* __restrict__ bp, V& v) {\n  Ext r0, r1;\n  uint32_t m0, m1;\n";
+  for (size_t b = 0; 2 * b < nint; b++) {
+    snprintf(buf, sizeof buf, "  lsk_int_%zu(c, alpha, bp, r0, m0);\n", 2 * b);
+    o += buf;
+    if (2 * b + 1 < nint) {
+      snprintf(buf, sizeof buf, "  lsk_int_%zu(c, alpha, bp, r1, m1);\n  v.pair(%zu, r0, m0, r1, m1);\n", 2 * b + 1, b);
+    } else {
+      snprintf(buf, sizeof buf, "  v.single(%zu, r0, m0);\n", b);
+    }
+    o += buf;
+  }
+  o += "}\n";
+  return o;
+}
+
 // the translation unit NVRTC compiles: three defines and the kernel header, which includes "lsk_program.cuh"
 std::string main_source(const ChipH& c) {
   uint32_t asserts = 0;
@@ -263,22 +340,19 @@ bool jit_eligible(const ChipH& c) {
 
 // Cache entry = 48-byte header {magic, NVRTC version, key[2], payload length, payload checksum} + cubin.  The key is 128
 // bits over everything that decides the machine code: the generated sources, the two device headers and the compile
-// options; the header also names the NVRTC version that produced the entry, and an entry from another version is not
-// used when this process can load NVRTC (and so could tell).  An entry whose header, length or checksum does not match is a miss (it is
+// options; the header also names the NVRTC version that produced the entry (informational: a cubin is self-contained
+// machine code, and the NVRTC a process happens to find -- torch ships its own -- says nothing about its validity).  An entry whose header, length or checksum does not match is a miss (it is
 // recompiled under LSK_JIT=1, otherwise the chip is interpreted): a stale, truncated or foreign file never runs.
 constexpr uint64_t JIT_CACHE_MAGIC = 0x4c534b514a495431ull;  // "LSKQJIT1"
 static const char* const JIT_OPTS[] = {"--gpu-architecture=sm_100a", "--std=c++17"};
 struct JitCacheHeader { uint64_t magic, nvrtc_version, key0, key1, length, checksum; };
 
 bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, std::string* how) {
-  const std::string program_hdr = program_source(c), main_src = main_source(c);
-  int vmaj = 0, vmin = 0;
-  if (nvrtc().ok && nvrtc().Version) nvrtc().Version(&vmaj, &vmin);
-  const uint64_t rtc_version = (uint64_t)vmaj * 1000 + (uint64_t)vmin;   // 0: NVRTC not loadable here
+  const std::string program_hdr = program_source(c), main_src = main_source(c), inter_hdr = interactions_source(c);
   uint64_t key[2];
   for (int h = 0; h < 2; h++) {
     uint64_t k = h ? 0x9e3779b97f4a7c15ull : 1469598103934665603ull;
-    for (const std::string& part : {program_hdr, main_src, std::string(FIELD_CUH_SRC), std::string(QUOTIENT_KERNEL_CUH_SRC),
+    for (const std::string& part : {program_hdr, inter_hdr, main_src, std::string(FIELD_CUH_SRC), std::string(QUOTIENT_KERNEL_CUH_SRC),
                                     std::string(JIT_OPTS[0]), std::string(JIT_OPTS[1])}) {
       k = fnv1a(std::to_string(part.size()) + ":", k);
       k = fnv1a(part, k);
@@ -294,19 +368,21 @@ bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, s
     JitCacheHeader hd;
     memcpy(&hd, file.data(), sizeof hd);
     const size_t n = file.size() - sizeof hd;
-    if (hd.magic == JIT_CACHE_MAGIC && (!rtc_version || hd.nvrtc_version == rtc_version) && hd.key0 == key[0] && hd.key1 == key[1] && hd.length == n &&
+    if (hd.magic == JIT_CACHE_MAGIC && hd.key0 == key[0] && hd.key1 == key[1] && hd.length == n &&
         hd.checksum == fnv1a(std::string(file.data() + sizeof hd, n))) {
       cubin.assign(file.begin() + sizeof hd, file.end());
       if (how) *how = "cache";
       return true;
     }
   }
+  if (getenv("LSK_JIT_DEBUG"))
+    fprintf(stderr, "[lsk jit] miss for chip %s: %s (%zu bytes read)\n", c.name.c_str(), path.c_str(), file.size());
   if (!compile_on_miss) return false;
   if (!nvrtc().ok) fail(LSK_ERR_CUDA, "NVRTC (libnvrtc.so.12) could not be loaded");
   void* prog = nullptr;
-  const char* hdr_src[3] = {FIELD_CUH_SRC, QUOTIENT_KERNEL_CUH_SRC, program_hdr.c_str()};
-  const char* hdr_name[3] = {"field.cuh", "quotient_kernel.cuh", "lsk_program.cuh"};
-  if (nvrtc().CreateProgram(&prog, main_src.c_str(), "lsk_quotient_jit.cu", 3, hdr_src, hdr_name) != 0)
+  const char* hdr_src[4] = {FIELD_CUH_SRC, QUOTIENT_KERNEL_CUH_SRC, program_hdr.c_str(), inter_hdr.c_str()};
+  const char* hdr_name[4] = {"field.cuh", "quotient_kernel.cuh", "lsk_program.cuh", "lsk_interactions.cuh"};
+  if (nvrtc().CreateProgram(&prog, main_src.c_str(), "lsk_quotient_jit.cu", 4, hdr_src, hdr_name) != 0)
     fail(LSK_ERR_CUDA, "nvrtcCreateProgram failed");
   int rc = nvrtc().CompileProgram(prog, 2, JIT_OPTS);
   if (rc != 0) {
@@ -323,6 +399,9 @@ bool jit_cubin(const ChipH& c, bool compile_on_miss, std::vector<char>& cubin, s
   nvrtc().GetCUBIN(prog, cubin.data());
   nvrtc().DestroyProgram(&prog);
   {
+    int vmaj = 0, vmin = 0;
+    if (nvrtc().Version) nvrtc().Version(&vmaj, &vmin);
+    const uint64_t rtc_version = (uint64_t)vmaj * 1000 + (uint64_t)vmin;
     JitCacheHeader hd{JIT_CACHE_MAGIC, rtc_version, key[0], key[1], cubin.size(), fnv1a(std::string(cubin.data(), cubin.size()))};
     std::vector<char> out(sizeof hd + cubin.size());
     memcpy(out.data(), &hd, sizeof hd);
@@ -344,6 +423,7 @@ JitKernel* jit_quotient(const ChipH& c) {
   k->smem_bytes = smem_bytes_for(c);
   int rc = driver().ModuleLoadData(&k->module, cubin.data());
   if (rc == 0) rc = driver().ModuleGetFunction(&k->function, k->module, "lsk_quotient_jit");
+  if (rc == 0) rc = driver().ModuleGetFunction(&k->perm_function, k->module, "lsk_perm_rows_jit");
   if (rc == 0 && k->smem_bytes > (48u << 10))
     rc = driver().FuncSetAttribute(k->function, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)k->smem_bytes);
   if (rc != 0) {
@@ -366,6 +446,15 @@ void jit_launch(lsk_ctx* ctx, const JitKernel* k, const QuotientArgs& a, const Q
   int rc = driver().LaunchKernel(k->function, div_up(nrows, JIT_THREADS), 1, 1, JIT_THREADS, 1, 1, k->smem_bytes, ctx->stream,
                                  params, nullptr);
   if (rc != 0) fail(LSK_ERR_CUDA, "cuLaunchKernel of a compiled constraint program failed (CUresult %d)", rc);
+}
+
+
+void jit_launch_perm(lsk_ctx* ctx, const JitKernel* k, const PermRowsArgs& a) {
+  const size_t nrows = a.row_end - a.row_begin;
+  void* params[] = {(void*)&a};
+  int rc = driver().LaunchKernel(k->perm_function, div_up(nrows, JIT_THREADS), 1, 1, JIT_THREADS, 1, 1, 0, ctx->stream, params,
+                                 nullptr);
+  if (rc != 0) fail(LSK_ERR_CUDA, "cuLaunchKernel of a compiled permutation-trace kernel failed (CUresult %d)", rc);
 }
 
 }  // namespace lsk

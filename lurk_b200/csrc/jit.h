@@ -15,6 +15,7 @@ constexpr size_t JIT_MIN_INSTR = 16;   // shorter programs are interpreted (the 
 struct JitKernel {
   void* module = nullptr;    // CUmodule
   void* function = nullptr;  // CUfunction of lsk_quotient_jit
+  void* perm_function = nullptr;  // CUfunction of lsk_perm_rows_jit (the chip's LogUp permutation-trace rows)
   uint32_t smem_bytes = 0;   // dynamic shared memory of a launch: the program's register file, or 0 (local memory)
 };
 
@@ -27,5 +28,6 @@ JitKernel* jit_quotient(const ChipH& c);
 void jit_free(JitKernel* k);
 void jit_launch(lsk_ctx* ctx, const JitKernel* k, const QuotientArgs& a, const QuotientConsts& qc, const uint32_t* inter,
                 uint32_t nint, uint32_t pw);
+void jit_launch_perm(lsk_ctx* ctx, const JitKernel* k, const PermRowsArgs& a);
 
 }  // namespace lsk

@@ -90,9 +90,14 @@ struct Executor {
   const uint32_t* w;
   std::vector<uint32_t> vals, req_stack, hint_stack, depth_stack;
   std::vector<Frame> frames;
+  // replay: the record is complete (imported from the caller's own executor, lsk_record_import_*); rows are re-run one
+  // by one only to find which callee / memory row each Call, PreImg and Store refers to (the hints); nothing else changes
+  bool replay = false;
+  uint32_t replay_sink[2] = {0, 0};
   Executor(const lsk_program& p, lsk_record& r) : prog(p), rec(r), w(p.words.data()) {}
 
-  static void new_lookup(uint32_t* provide, uint32_t nonce, std::vector<uint32_t>& reqs) {
+  void new_lookup(uint32_t* provide, uint32_t nonce, std::vector<uint32_t>& reqs) {
+    if (replay) return;
     reqs.push_back(provide[0]);
     reqs.push_back(provide[1]);
     provide[0] = nonce;
@@ -143,6 +148,7 @@ struct Executor {
     if (t.partial && rec.funcs[f.func].partial) depth_stack.push_back(t.depth[row]);  // execute.rs:510-512,751-753
   }
   uint32_t* byte_record(uint32_t i1, uint32_t i2, int slot) {  // BytesInputRecord field of ByteInput (i1, i2)
+    if (replay) return replay_sink;
     if (rec.bytes.empty()) rec.bytes.assign((size_t)65536 * 12, 0);
     rec.bytes_used = true;
     return &rec.bytes[(size_t)(i1 | (i2 << 8)) * 12 + 2 * slot];
@@ -215,6 +221,7 @@ struct Executor {
             if (!t.done[row]) fail(LSK_ERR_EXEC, "Loop detected");
             consume(callee, (uint32_t)row, false);
           } else {
+            if (replay) fail(LSK_ERR_EXEC, "imported record lacks a query of func %u that a row calls", callee);
             uint32_t r = insert_query(callee, inp, 0);
             push_frame(callee, r, inp, n, false);
           }
@@ -235,6 +242,7 @@ struct Executor {
             if (memcmp(&t.outs[(size_t)row * t.out], outv, t.out * 4)) fail(LSK_ERR_EXEC, "preimage output mismatch");
             consume(callee, (uint32_t)row, true);
           } else {
+            if (replay) fail(LSK_ERR_EXEC, "imported record lacks a query of func %u that a row takes the preimage of", callee);
             uint32_t r = insert_query(callee, inp.data(), 0);
             push_frame(callee, r, inp.data(), t.in, true);
           }
@@ -248,6 +256,7 @@ struct Executor {
           for (uint32_t i = 0; i < n; i++) v[i] = m[op[2 + i]];
           long row = mt.index.find(mt.vals.data(), n, v);
           if (row < 0) {
+            if (replay) fail(LSK_ERR_EXEC, "imported record lacks a memory slot that a row stores");
             row = (long)mt.rows();
             mt.vals.insert(mt.vals.end(), v, v + n);
             mt.provide.push_back(0);
@@ -382,9 +391,22 @@ struct Executor {
       uint32_t n = c[2];
       FuncTable& t = rec.funcs[f.func];
       if (n != t.out) fail(LSK_ERR_EXEC, "return arity mismatch");
-      if (t.done[f.nonce]) fail(LSK_ERR_EXEC, "output already set");
       uint32_t outv[64];
       for (uint32_t i = 0; i < n; i++) outv[i] = m[c[3 + i]];
+      if (replay) {
+        if (memcmp(&t.outs[(size_t)f.nonce * t.out], outv, n * 4))
+          fail(LSK_ERR_EXEC, "imported record: row %u of func %u does not return the recorded output", f.nonce, f.func);
+        t.hint_off[f.nonce] = (uint32_t)t.hints.size();
+        t.hints.insert(t.hints.end(), hint_stack.begin() + f.hint_base, hint_stack.end());
+        t.hint_len[f.nonce] = (uint32_t)(hint_stack.size() - f.hint_base);
+        hint_stack.resize(f.hint_base);
+        depth_stack.resize(f.depth_base);
+        vals.resize(f.map_base);
+        frames.pop_back();
+        if (!frames.empty()) fail(LSK_ERR_EXEC, "replay frame stack not empty");
+        return;
+      }
+      if (t.done[f.nonce]) fail(LSK_ERR_EXEC, "output already set");
       memcpy(&t.outs[(size_t)f.nonce * t.out], outv, n * 4);
       t.done[f.nonce] = 1;
       if (t.invertible) {  // execute.rs:690-692: inv_map.insert(out, inp) (later insert wins)
@@ -799,6 +821,194 @@ int lsk_execute(const lsk_program* p, lsk_record* r, uint32_t func, const uint32
   run_on_big_stack(job);
   if (o.size() != nout) fail(LSK_ERR_ARG, "output size mismatch");
   for (size_t i = 0; i < nout; i++) out[i] = o[i];
+  return LSK_OK;
+  LSK_API_END
+}
+
+
+// ---- importing a record produced elsewhere (the reference's own executor, src/lair/execute.rs:375-783) -----------------
+// QueryRecord::func_queries[func] in insertion (= nonce) order: args, output, provide, requires; depth and
+// depth_requires of partial funcs.  CSR offsets have n + 1 entries, in PAIRS (prev_nonce, prev_count).
+int lsk_record_import_func(const lsk_program* p, lsk_record* r, uint32_t func, size_t n, const uint32_t* args,
+                           const uint32_t* outs, const uint32_t* provide, const uint32_t* req_off, const uint32_t* reqs,
+                           const uint32_t* depth, const uint32_t* dreq_off, const uint32_t* dreqs) {
+  LSK_API_BEGIN
+  if (!p || !r || func >= p->nfuncs || (n && (!provide || !req_off))) fail(LSK_ERR_ARG, "bad argument");
+  FuncTable& t = r->funcs[func];
+  if (t.rows()) fail(LSK_ERR_ARG, "func %u already has queries", func);
+  if (n > 0xfffffffeull) fail(LSK_ERR_ARG, "too many queries");
+  if (n && ((t.in && !args) || (t.out && !outs) || (t.partial && (!depth || !dreq_off)))) fail(LSK_ERR_ARG, "missing table");
+  lsk::record_unpin(r);
+  auto canonical = [&](const uint32_t* v, size_t k, const char* what) {
+    for (size_t i = 0; i < k; i++)
+      if (v[i] >= Pq) fail(LSK_ERR_ARG, "non-canonical value in the %s of func %u", what, func);
+  };
+  if (n) {
+    canonical(args, n * t.in, "arguments");
+    canonical(outs, n * t.out, "outputs");
+    for (size_t i = 0; i < n; i++)
+      if (req_off[i] > req_off[i + 1]) fail(LSK_ERR_ARG, "require offsets of func %u are not monotone", func);
+    if (req_off[0] != 0) fail(LSK_ERR_ARG, "require offsets must start at 0");
+    if (req_off[n] && !reqs) fail(LSK_ERR_ARG, "missing require records");
+  }
+  t.args.assign(args, args + n * t.in);
+  t.outs.assign(outs, outs + n * t.out);
+  t.done.assign(n, 1);
+  t.provide.assign(provide, provide + 2 * n);
+  t.req_off.assign(req_off, req_off + n);
+  t.req_len.resize(n);
+  for (size_t i = 0; i < n; i++) t.req_len[i] = req_off[i + 1] - req_off[i];
+  t.reqs.assign(reqs, reqs + (n ? 2 * (size_t)req_off[n] : 0));
+  t.hint_off.assign(n, 0);
+  t.hint_len.assign(n, 0);
+  t.hints.clear();
+  if (t.partial) {
+    for (size_t i = 0; i < n; i++)
+      if (dreq_off[i] > dreq_off[i + 1]) fail(LSK_ERR_ARG, "depth-require offsets of func %u are not monotone", func);
+    t.depth.assign(depth, depth + n);
+    t.dreq_off.assign(dreq_off, dreq_off + n);
+    t.dreq_len.resize(n);
+    for (size_t i = 0; i < n; i++) t.dreq_len[i] = dreq_off[i + 1] - dreq_off[i];
+    t.dreqs.assign(dreqs, dreqs + (n ? 2 * (size_t)dreq_off[n] : 0));
+  }
+  t.row_ordered = true;
+  t.completed = n;
+  t.index = HashIndex();
+  for (size_t i = 0; i < n; i++) {
+    if (t.index.find(t.args.data(), t.in, &t.args[i * t.in]) >= 0) fail(LSK_ERR_ARG, "func %u: two queries with the same arguments", func);
+    t.index.insert_new(t.args.data(), t.in, (uint32_t)i);
+  }
+  if (t.invertible)   // execute.rs:690-692: every finished query also feeds the inverse map (a later one wins)
+    for (size_t i = 0; i < n; i++) {
+      const uint32_t* o = &t.outs[i * t.out];
+      long iv = t.inv_index.find(t.inv_outs.data(), t.out, o);
+      if (iv >= 0) {
+        memcpy(&t.inv_inps[(size_t)iv * t.in], &t.args[i * t.in], t.in * 4);
+      } else {
+        uint32_t slot = (uint32_t)t.inv_index.used;
+        t.inv_outs.insert(t.inv_outs.end(), o, o + t.out);
+        t.inv_inps.insert(t.inv_inps.end(), t.args.begin() + i * t.in, t.args.begin() + (i + 1) * t.in);
+        t.inv_index.insert_new(t.inv_outs.data(), t.out, slot);
+      }
+    }
+  return LSK_OK;
+  LSK_API_END
+}
+// QueryRecord::mem_queries[mem_idx] in insertion order (pointer = index + 1): values and provide records
+int lsk_record_import_mem(lsk_record* r, uint32_t mem_idx, size_t n, const uint32_t* vals, const uint32_t* provide) {
+  LSK_API_BEGIN
+  if (!r || mem_idx >= NUM_MEM_TABLES || (n && (!vals || !provide))) fail(LSK_ERR_ARG, "bad argument");
+  MemTable& mt = r->mems[mem_idx];
+  if (mt.rows()) fail(LSK_ERR_ARG, "memory table %u already has entries", mem_idx);
+  lsk::record_unpin(r);
+  for (size_t i = 0; i < n * mt.len; i++)
+    if (vals[i] >= Pq) fail(LSK_ERR_ARG, "non-canonical value in memory table %u", mem_idx);
+  mt.vals.assign(vals, vals + n * mt.len);
+  mt.provide.assign(provide, provide + 2 * n);
+  mt.index = HashIndex();
+  for (size_t i = 0; i < n; i++) {
+    if (mt.index.find(mt.vals.data(), mt.len, &mt.vals[i * mt.len]) >= 0) fail(LSK_ERR_ARG, "memory table %u: duplicate entry", mem_idx);
+    mt.index.insert_new(mt.vals.data(), mt.len, (uint32_t)i);
+  }
+  return LSK_OK;
+  LSK_API_END
+}
+// BytesRecord (src/gadgets/bytes/record.rs:14-110): for each of the 65536 ByteInputs the provide records
+// (nonce, count) of range_u8, range_u16, less_than, and, xor, or -- [65536][6][2] words; NULL / all zero = no byte lookups
+int lsk_record_import_bytes(lsk_record* r, const uint32_t* records) {
+  LSK_API_BEGIN
+  if (!r) fail(LSK_ERR_ARG, "null record");
+  lsk::record_unpin(r);
+  r->bytes.clear();
+  r->bytes_used = false;
+  if (records) {
+    bool any = false;
+    for (size_t i = 0; i < (size_t)65536 * 12 && !any; i++) any = records[i] != 0;
+    if (any) {
+      r->bytes.assign(records, records + (size_t)65536 * 12);
+      r->bytes_used = true;
+    }
+  }
+  return LSK_OK;
+  LSK_API_END
+}
+int lsk_record_import_public_values(lsk_record* r, const uint32_t* pv, size_t n) {
+  LSK_API_BEGIN
+  if (!r || (n && !pv)) fail(LSK_ERR_ARG, "bad argument");
+  for (size_t i = 0; i < n; i++)
+    if (pv[i] >= Pq) fail(LSK_ERR_ARG, "non-canonical public value");
+  r->public_values.assign(pv, pv + n);
+  return LSK_OK;
+  LSK_API_END
+}
+// The hints the trace kernels gather through (record.h): replays every imported row against the imported tables --
+// the lookups the reference repeats at trace-generation time (src/lair/trace.rs:325-373) -- and checks on the way that
+// each row returns its recorded output.  Must follow the imports (and lsk_inject_inv_queries, for preimages that no
+// imported query produced); afterwards the record is what lsk_execute would have built.
+int lsk_record_resolve(const lsk_program* p, lsk_record* r) {
+  LSK_API_BEGIN
+  if (!p || !r) fail(LSK_ERR_ARG, "null argument");
+  lsk::record_unpin(r);
+  Executor ex(*p, *r);
+  ex.replay = true;
+  std::vector<uint32_t> out;
+  for (uint32_t f = 0; f < p->nfuncs; f++) {
+    FuncTable& t = r->funcs[f];
+    t.hints.clear();
+    for (size_t row = 0; row < t.rows(); row++) {
+      std::vector<uint32_t> a(t.args.begin() + row * t.in, t.args.begin() + (row + 1) * t.in);
+      ex.push_frame(f, (uint32_t)row, a.data(), t.in, false);
+      while (!ex.frames.empty()) ex.step(out);
+    }
+  }
+  return LSK_OK;
+  LSK_API_END
+}
+// ---- exporting (tests; the inverse of the imports) ---------------------------------------------------------------------
+// sizes = {rows, require pairs, hints, depth-require pairs}
+int lsk_record_func_sizes(const lsk_record* r, uint32_t func, size_t sizes[4]) {
+  LSK_API_BEGIN
+  if (!r || func >= r->funcs.size() || !sizes) fail(LSK_ERR_ARG, "bad argument");
+  const FuncTable& t = r->funcs[func];
+  sizes[0] = t.rows(); sizes[1] = t.reqs.size() / 2; sizes[2] = t.hints.size(); sizes[3] = t.dreqs.size() / 2;
+  return LSK_OK;
+  LSK_API_END
+}
+// row-ordered tables (call lsk_record_finalize first); offsets get rows + 1 entries; any pointer may be NULL
+int lsk_record_export_func(const lsk_record* r, uint32_t func, uint32_t* args, uint32_t* outs, uint32_t* provide,
+                           uint32_t* req_off, uint32_t* reqs, uint32_t* hint_off, uint32_t* hints, uint32_t* depth,
+                           uint32_t* dreq_off, uint32_t* dreqs) {
+  LSK_API_BEGIN
+  if (!r || func >= r->funcs.size()) fail(LSK_ERR_ARG, "bad argument");
+  const FuncTable& t = r->funcs[func];
+  if (!t.row_ordered) fail(LSK_ERR_ARG, "export needs row-ordered tables: call lsk_record_finalize");
+  const size_t n = t.rows();
+  auto cp = [](uint32_t* dst, const std::vector<uint32_t>& v) { if (dst && !v.empty()) memcpy(dst, v.data(), v.size() * 4); };
+  cp(args, t.args); cp(outs, t.outs); cp(provide, t.provide); cp(reqs, t.reqs); cp(hints, t.hints);
+  if (req_off) { cp(req_off, t.req_off); req_off[n] = (uint32_t)(t.reqs.size() / 2); }
+  if (hint_off) { cp(hint_off, t.hint_off); hint_off[n] = (uint32_t)t.hints.size(); }
+  if (t.partial) {
+    cp(depth, t.depth); cp(dreqs, t.dreqs);
+    if (dreq_off) { cp(dreq_off, t.dreq_off); dreq_off[n] = (uint32_t)(t.dreqs.size() / 2); }
+  }
+  return LSK_OK;
+  LSK_API_END
+}
+int lsk_record_export_mem(const lsk_record* r, uint32_t mem_idx, uint32_t* vals, uint32_t* provide) {
+  LSK_API_BEGIN
+  if (!r || mem_idx >= NUM_MEM_TABLES) fail(LSK_ERR_ARG, "bad argument");
+  const MemTable& mt = r->mems[mem_idx];
+  if (vals && !mt.vals.empty()) memcpy(vals, mt.vals.data(), mt.vals.size() * 4);
+  if (provide && !mt.provide.empty()) memcpy(provide, mt.provide.data(), mt.provide.size() * 4);
+  return LSK_OK;
+  LSK_API_END
+}
+// [65536][6][2] words (all zero when the record has no byte lookups)
+int lsk_record_export_bytes(const lsk_record* r, uint32_t* records) {
+  LSK_API_BEGIN
+  if (!r || !records) fail(LSK_ERR_ARG, "bad argument");
+  if (r->bytes.empty()) memset(records, 0, (size_t)65536 * 12 * 4);
+  else memcpy(records, r->bytes.data(), (size_t)65536 * 12 * 4);
   return LSK_OK;
   LSK_API_END
 }

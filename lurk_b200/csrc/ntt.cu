@@ -17,6 +17,8 @@
 // instead of 12 shared-memory round trips.  Twiddles are (w, floor(w 2^32 / p)) pairs so every
 // twiddle product is a Shoup multiplication (3 multiply-pipe instructions on constants instead of
 // the 3 + 2 of a Montgomery product); the level-packed table w_{2^s}^k is 32 KB and L1-resident.
+#include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <vector>
@@ -438,28 +440,45 @@ void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, 
   unsigned tt = logn - LOG_BLOCK;
   unsigned blocks = 1u << tt;
   if (ncols > 65535) fail(LSK_ERR_ARG, "too many columns");
-  const double cells = (double)((size_t)1 << logn) * ncols;
-  {
-    ProfScope ps(ctx, PT_LDE_K1, 1, 8.0 * cells);
-    lde_k1_kernel<<<dim3(blocks, ncols), K13_THREADS, 0, st>>>(in, in_stride, out, out_stride, t->tw_inv.p);
-  }
   // tile = 2^t blocks x 2^c low indices = 2^12 .. 2^14 elements (c = 4 up to t = 10, then 3, 2), two
   // copies in shared memory (coefficients + work), 16 elements per thread
   unsigned log_tile = tt <= 8 ? 12 : (tt <= 10 ? tt + 4 : 14);
   unsigned c = log_tile - tt;
-  dim3 grid(BLOCK_ELEMS >> c, ncols);
   size_t smem = 2 * ((size_t)1 << log_tile) * sizeof(uint32_t);
-  {
-    ProfScope ps(ctx, PT_LDE_K2, 1, 12.0 * cells);
-    K2Args a{out, out_stride, logn, c, t->tw_fwd.p, t->tw_inv.p, bg->lo_f.p, bg->hi_f.p, bg->lo_i.p, bg->hi_i.p,
-             sc->a.p, sc->b.p};
-    if (log_tile == 12) lde_k2_kernel<256><<<grid, 256, smem, st>>>(a);
-    else if (log_tile == 13) lde_k2_kernel<512><<<grid, 512, smem, st>>>(a);
-    else lde_k2_kernel<1024><<<grid, 1024, smem, st>>>(a);
-  }
-  {
-    ProfScope ps(ctx, PT_LDE_K3, 1, 16.0 * cells);
-    lde_k3_kernel<<<dim3(2 * blocks, ncols), K13_THREADS, 0, st>>>(out, out_stride, t->tw_fwd.p);
+  // Column chunking (LSK_LDE_L2_MB, default off).  The three passes of a column exchange 4N + 8N + 8N bytes through
+  // `out`; run over a chunk of columns whose 12N-byte footprints fit the L2 together, K2 and K3 find what the previous
+  // pass wrote still on chip.  MEASURED AND REJECTED (B200, Lurk fib 2^20, 80 MB chunks): K1+K2+K3 19.4 ms against 16.3 ms
+  // with all columns per launch -- the passes are bound by instruction issue / the multiply pipe (ncu: K2 executes ~310
+  // instructions per element, fmaheavy 68 % busy, math_pipe_throttle the top stall, DRAM at 0.9 TB/s), not by HBM, and
+  // the smaller grids only add partial waves.  profiles/r02_ncu_lde.csv.
+  static const size_t l2_budget = [] {
+    const char* e = getenv("LSK_LDE_L2_MB");
+    return (size_t)(e ? std::max(0L, atol(e)) : 0) << 20;
+  }();
+  const size_t col_bytes = (size_t)12 << logn;
+  const uint32_t chunk = l2_budget ? (uint32_t)std::min<size_t>(ncols, std::max<size_t>(1, l2_budget / col_bytes)) : ncols;
+  for (uint32_t c0 = 0; c0 < ncols; c0 += chunk) {
+    const uint32_t nc = std::min(chunk, ncols - c0);
+    const uint32_t* cin = in + (size_t)c0 * in_stride;
+    uint32_t* cout = out + (size_t)c0 * out_stride;
+    const double cells = (double)((size_t)1 << logn) * nc;
+    {
+      ProfScope ps(ctx, PT_LDE_K1, 1, 8.0 * cells);
+      lde_k1_kernel<<<dim3(blocks, nc), K13_THREADS, 0, st>>>(cin, in_stride, cout, out_stride, t->tw_inv.p);
+    }
+    dim3 grid(BLOCK_ELEMS >> c, nc);
+    {
+      ProfScope ps(ctx, PT_LDE_K2, 1, 12.0 * cells);
+      K2Args a{cout, out_stride, logn, c, t->tw_fwd.p, t->tw_inv.p, bg->lo_f.p, bg->hi_f.p, bg->lo_i.p, bg->hi_i.p,
+               sc->a.p, sc->b.p};
+      if (log_tile == 12) lde_k2_kernel<256><<<grid, 256, smem, st>>>(a);
+      else if (log_tile == 13) lde_k2_kernel<512><<<grid, 512, smem, st>>>(a);
+      else lde_k2_kernel<1024><<<grid, 1024, smem, st>>>(a);
+    }
+    {
+      ProfScope ps(ctx, PT_LDE_K3, 1, 16.0 * cells);
+      lde_k3_kernel<<<dim3(2 * blocks, nc), K13_THREADS, 0, st>>>(cout, out_stride, t->tw_fwd.p);
+    }
   }
   LSK_CUDA(cudaGetLastError());
 }

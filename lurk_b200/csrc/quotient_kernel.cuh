@@ -33,6 +33,17 @@ struct QuotientArgs {
 struct QuotientConsts {
   uint32_t g, w2n, wn_inv, zh[2], inv_zh[2];
 };
+struct PermRowsArgs {   // LogUp permutation-trace rows of one chip (stark_kernels.cu::perm_rows_kernel and its compiled form)
+  const uint32_t* main; size_t mstride;
+  const uint32_t* prep; size_t pstride;
+  unsigned logn;
+  Ext alpha;
+  const Ext* beta_pows;
+  uint32_t* perm; size_t perm_stride;
+  size_t row_begin, row_end;
+  uint32_t scatter;       // row sums to natural order (for the scan) or left in storage order
+  Ext* rowsum_out;
+};
 
 // ---- device helpers shared with the LogUp trace kernel ---------------------------------------------------------
 struct Cells {  // local-row view of a chip's main + preprocessed matrices
@@ -90,6 +101,8 @@ LSK_D void quotient_row_setup(const QuotientArgs& a, const QuotientConsts& qc, s
   q.sel[1] = fmul(zh, fmul(inv, xm1));  // is_last
   q.sel[2] = xml;                       // is_transition
 }
+LSK_D void quotient_row_tail(const QuotientArgs& a, const QuotientConsts& qc, const QuotientRow& q, Ext ac, uint32_t cj,
+                             const Ext& sum_local, const Ext& sum_next, uint32_t pw, bool live);
 // LogUp constraints (sphinx eval_permutation_constraints) on top of the folded AIR constraints `ac` (the first
 // `ci` alpha powers are spent), division by the vanishing polynomial, store
 LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, const QuotientRow& q, Ext ac, uint32_t ci,
@@ -117,6 +130,10 @@ LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, 
     sum_local = eadd(sum_local, pl);
     sum_next = eadd(sum_next, load_ext_cols(a.perm, a.permstride, 4 * b, q.rn));
   }
+  quotient_row_tail(a, qc, q, ac, cj, sum_local, sum_next, pw, live);
+}
+LSK_D void quotient_row_tail(const QuotientArgs& a, const QuotientConsts& qc, const QuotientRow& q, Ext ac, uint32_t cj,
+                             const Ext& sum_local, const Ext& sum_next, uint32_t pw, bool live) {
   Ext phi_local = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), q.r);
   Ext phi_next = load_ext_cols(a.perm, a.permstride, 4 * (pw - 1), q.rn);
   ac = eadd(ac, emul(a.apow[a.n_total - 1 - (cj++)], emul_base(esub(esub(phi_next, phi_local), sum_next), q.sel[2])));
@@ -170,6 +187,61 @@ LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, 
   acc = eadd(acc, Ext{{mont_reduce(acc_reduce64(lsk_s0)), mont_reduce(acc_reduce64(lsk_s1)),               \
                        mont_reduce(acc_reduce64(lsk_s2)), mont_reduce(acc_reduce64(lsk_s3))}})
 #include "lsk_program.cuh"
+// "lsk_interactions.cuh" (jit.cu::interactions_source): lsk_interactions<V>(cells, alpha, beta_pows, v) evaluates the
+// chip's interactions as straight-line code and hands every LogUp batch to v.pair(b, r0, m0, r1, m1) / v.single(b, r0, m0)
+#define LSK_CM(i) c.main[(size_t)(i) * c.mstride + c.r]
+#define LSK_CP(i) c.prep[(size_t)(i) * c.pstride + c.r]
+#include "lsk_interactions.cuh"
+// the batch bodies are real calls: inlined into every one of a chip's 10-30 batches they multiply NVVM's work (the
+// 41 chips of the Lurk machine took 19 minutes to compile that way, 40 s like this) for no measurable gain
+__device__ __noinline__ Ext lsk_perm_pair(const Ext& r0, uint32_t m0, const Ext& r1, uint32_t m1) {
+  const Ext num = eadd(emul_base(r1, m0), emul_base(r0, m1));
+  return (m0 | m1) ? emul(num, einv(emul(r0, r1))) : ext_zero();
+}
+__device__ __noinline__ Ext lsk_perm_single(const Ext& r0, uint32_t m0) { return m0 ? emul_base(einv(r0), m0) : ext_zero(); }
+__device__ __noinline__ Ext lsk_quot_pair(const Ext& pl, const Ext& r0, uint32_t m0, const Ext& r1, uint32_t m1) {
+  return esub(emul(emul(pl, r0), r1), eadd(emul_base(r1, m0), emul_base(r0, m1)));
+}
+__device__ __noinline__ Ext lsk_fold(const Ext& ac, const Ext& ap, const Ext& x) { return eadd(ac, emul(ap, x)); }
+struct LskQuotientBatches {   // quotient_row_finish's loop body
+  const QuotientArgs& a;
+  const QuotientRow& q;
+  Ext ac, sum_local, sum_next;
+  uint32_t cj;
+  LSK_D void fold(uint32_t b, const Ext& pl, const Ext& diff) {
+    ac = lsk_fold(ac, a.apow[a.n_total - 1 - (cj++)], diff);
+    sum_local = eadd(sum_local, pl);
+    sum_next = eadd(sum_next, load_ext_cols(a.perm, a.permstride, 4 * b, q.rn));
+  }
+  LSK_D void pair(uint32_t b, const Ext& r0, uint32_t m0, const Ext& r1, uint32_t m1) {
+    const Ext pl = load_ext_cols(a.perm, a.permstride, 4 * b, q.r);
+    fold(b, pl, lsk_quot_pair(pl, r0, m0, r1, m1));
+  }
+  LSK_D void single(uint32_t b, const Ext& r0, uint32_t m0) {
+    const Ext pl = load_ext_cols(a.perm, a.permstride, 4 * b, q.r);
+    fold(b, pl, esub(emul(pl, r0), ext_from_base(m0)));
+  }
+};
+struct LskPermBatches {       // perm_rows_kernel's loop body
+  const PermRowsArgs& a;
+  size_t r;
+  Ext rowsum;
+  LSK_D void put(uint32_t b, const Ext& v) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) a.perm[(size_t)(4 * b + k) * a.perm_stride + r] = v.c[k];
+    rowsum = eadd(rowsum, v);
+  }
+  LSK_D void pair(uint32_t b, const Ext& r0, uint32_t m0, const Ext& r1, uint32_t m1) { put(b, lsk_perm_pair(r0, m0, r1, m1)); }
+  LSK_D void single(uint32_t b, const Ext& r0, uint32_t m0) { put(b, lsk_perm_single(r0, m0)); }
+};
+extern "C" __global__ void __launch_bounds__(256) lsk_perm_rows_jit(PermRowsArgs a) {
+  const size_t r = a.row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (r >= a.row_end) return;
+  const Cells cells{a.main, a.mstride, a.prep, a.pstride, r};
+  LskPermBatches v{a, r, ext_zero()};
+  lsk_interactions(cells, a.alpha, a.beta_pows, v);
+  a.rowsum_out[a.scatter ? bitrev32((uint32_t)r, a.logn) : r] = v.rowsum;
+}
 extern "C" __global__ void __launch_bounds__(256) lsk_quotient_jit(QuotientArgs a, QuotientConsts qc,
                                                                    const uint32_t* __restrict__ inter, uint32_t nint,
                                                                    uint32_t pw) {
@@ -190,7 +262,10 @@ extern "C" __global__ void __launch_bounds__(256) lsk_quotient_jit(QuotientArgs 
   LSK_R(0) = 0;
   Ext acc = ext_zero();
   lsk_program(R, acc, a, q);
-  quotient_row_finish(a, qc, q, acc, LSK_JIT_ASSERTS, inter, nint, pw, live);
+  const Cells cells{a.main, a.mstride, a.prep, a.pstride, q.r};
+  LskQuotientBatches v{a, q, acc, ext_zero(), ext_zero(), LSK_JIT_ASSERTS};
+  lsk_interactions(cells, a.chal_alpha, a.beta_pows, v);
+  quotient_row_tail(a, qc, q, v.ac, v.cj, v.sum_local, v.sum_next, pw, live);
 }
 #else
 // ---- interpreted form.  ROWS rows per thread (rows t, t + 256, ... of the CTA's slab, so every access stays

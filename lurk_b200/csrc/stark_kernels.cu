@@ -126,6 +126,11 @@ void perm_trace_dev(lsk_ctx* ctx, const ChipDev& chip, const uint32_t* main, siz
   if (split) sums_pos.alloc(ctx, n);
   {
     ProfScope ps(ctx, PT_PERM_ROWS, 1, (double)(e - b) * (4.0 * (chip.width + chip.prep_width) + 16.0 * chip.pw));
+    if (chip.jit) {   // the chip's interactions compiled to straight-line code (jit.cu)
+      PermRowsArgs pa{main, mstride, prep, pstride, logn, chal_alpha, beta_pows_dev, perm_out, perm_stride, b, e,
+                      split ? 0u : 1u, split ? sums_pos.p : scratch};
+      jit_launch_perm(ctx, chip.jit.get(), pa);
+    } else
     perm_rows_kernel<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(chip.inter.p, chip.nint, main, mstride, prep, pstride,
                                                                   logn, chal_alpha, beta_pows_dev, perm_out, perm_stride,
                                                                   b, e, !split, split ? sums_pos.p : scratch);

@@ -87,6 +87,67 @@ class QueryRecord:
     def device_bytes(self) -> int:
         return N.lib().lsk_record_device_bytes(self.h)
 
+    # -- tables in and out: the form in which a record made by another executor (the reference's own
+    #    `toplevel.execute`, src/lair/execute.rs:375-783) crosses the C ABI ---------------------------------------
+    def export_tables(self) -> dict:
+        """Every table of the record as numpy arrays: {"funcs": {index: {...}}, "mems": {idx: {...}}, "bytes", "public_values"}.
+        Row-ordered (finalize() is called)."""
+        self.finalize()
+        L = N.lib()
+        funcs = {}
+        for f in self.toplevel.funcs:
+            sz = (ctypes.c_size_t * 4)()
+            N.check(L.lsk_record_func_sizes(self.h, f.index, sz))
+            n, nreq, nhint, ndreq = (int(x) for x in sz)
+            if not n:
+                continue
+            t = {"args": np.zeros((n, f.input_size), np.uint32), "outs": np.zeros((n, f.output_size), np.uint32),
+                 "provide": np.zeros((n, 2), np.uint32), "req_off": np.zeros(n + 1, np.uint32),
+                 "reqs": np.zeros((nreq, 2), np.uint32), "hint_off": np.zeros(n + 1, np.uint32),
+                 "hints": np.zeros(nhint, np.uint32)}
+            if f.partial:
+                t.update(depth=np.zeros(n, np.uint32), dreq_off=np.zeros(n + 1, np.uint32), dreqs=np.zeros((ndreq, 2), np.uint32))
+            p = lambda k: N.vp(t[k]) if k in t and t[k].size else None
+            N.check(L.lsk_record_export_func(self.h, f.index, p("args"), p("outs"), p("provide"), p("req_off"), p("reqs"),
+                                             p("hint_off"), p("hints"), p("depth"), p("dreq_off"), p("dreqs")))
+            funcs[f.index] = t
+        mems = {}
+        for i, ln in enumerate(MEM_TABLE_SIZES):
+            n = self.num_mem(i)
+            if n:
+                m = {"vals": np.zeros((n, ln), np.uint32), "provide": np.zeros((n, 2), np.uint32)}
+                N.check(L.lsk_record_export_mem(self.h, i, N.vp(m["vals"]), N.vp(m["provide"])))
+                mems[i] = m
+        b = np.zeros((65536, 6, 2), np.uint32)
+        N.check(L.lsk_record_export_bytes(self.h, N.vp(b)))
+        return {"funcs": funcs, "mems": mems, "bytes": b, "public_values": self.expect_public_values()}
+
+    @classmethod
+    def from_tables(cls, toplevel: Toplevel, tables: dict, inv_queries=()) -> "QueryRecord":
+        """A record imported table by table (lsk_record_import_* + lsk_record_resolve): what a Rust shim does with the
+        reference's QueryRecord.  The "hint" tables are NOT read: resolve recomputes them.  inv_queries: [(func name,
+        [(preimage, image), ...])] for preimages that no imported query produced (inject_inv_queries)."""
+        q = cls(toplevel)
+        L = N.lib()
+        for idx, t in tables["funcs"].items():
+            g = lambda k: N.vp(N.u32(t[k])) if k in t and np.size(t[k]) else None
+            keep = {k: N.u32(v) for k, v in t.items()}      # keep the contiguous copies alive across the call
+            p = lambda k: N.vp(keep[k]) if k in keep and keep[k].size else None
+            N.check(L.lsk_record_import_func(q.program.h, q.h, idx, ctypes.c_size_t(len(keep["provide"])), p("args"), p("outs"),
+                                             p("provide"), N.vp(keep["req_off"]), p("reqs"), p("depth"),
+                                             N.vp(keep["dreq_off"]) if "dreq_off" in keep else None, p("dreqs")))
+        for i, m in tables["mems"].items():
+            v, pr = N.u32(m["vals"]), N.u32(m["provide"])
+            N.check(L.lsk_record_import_mem(q.h, i, ctypes.c_size_t(len(pr)), N.vp(v), N.vp(pr)))
+        b = N.u32(tables["bytes"])
+        N.check(L.lsk_record_import_bytes(q.h, N.vp(b)))
+        pv = N.u32(tables["public_values"])
+        N.check(L.lsk_record_import_public_values(q.h, N.vp(pv), ctypes.c_size_t(len(pv))))
+        for name, pairs in inv_queries:
+            q.inject_inv_queries(name, toplevel, pairs)
+        N.check(L.lsk_record_resolve(q.program.h, q.h))
+        return q
+
 
 def execute(toplevel: Toplevel, func: Func, args, queries: QueryRecord) -> np.ndarray:
     """Toplevel::execute (src/lair/execute.rs:376-392)"""

@@ -526,3 +526,26 @@ def test_lurk_bench_programs_prove_bit_exact(oracle, prog, arg):
     proof = m.prove(pk, Shard.new(q))
     assert np.array_equal(proof.words, want)
     m.verify(vk, proof)
+
+
+def test_an_imported_record_proves_like_the_executed_one():
+    # the drop-in path behind an unchanged evaluator: the record crosses the C ABI as tables (lsk_record_import_*),
+    # lsk_record_resolve finds the hints, and the proof is the proof of the natively executed record
+    from lurk_b200.bench_programs import source
+    from lurk_b200.lurk_eval import build_lurk_toplevel
+    from lurk_b200.reader import read
+    from lurk_b200.zstore import ZStore
+    top = build_lurk_toplevel()
+    z = ZStore()
+    e = read(z, source("fib", 30))
+    q = QueryRecord.new(top)
+    z.inject(q, top)
+    execute_by_name(top, "lurk_main", [e.tag] + [0] * 7 + list(e.digest) + [0] * 8, q)
+    inv = [(name, list(z.hashes[w].items())) for name, w in (("hash3", 24), ("hash4", 32), ("hash5", 40)) if z.hashes[w]]
+    q2 = QueryRecord.from_tables(top, q.export_tables(), inv)
+    m = new_machine(top, "lurk_main", opts=SphinxCoreOpts(num_queries=6, proof_of_work_bits=6))
+    pk, vk = m.setup()
+    a = m.prove(pk, Shard.new(q))
+    b = m.prove(pk, Shard.new(q2))
+    assert np.array_equal(a.words, b.words)
+    m.verify(vk, b)

@@ -222,3 +222,84 @@ def test_the_package_never_imports_the_checker():
                 src = open(os.path.join(dirpath, name), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), name
                 assert "liboracle" not in src and "pyoracle" not in src, name
+
+
+def _roundtrip_tables(top, entry, args, setup=None):
+    import numpy as np
+    from lurk_b200.execute import QueryRecord, execute_by_name
+    q = QueryRecord.new(top)
+    inv = setup(q) if setup else ()
+    execute_by_name(top, entry, args, q)
+    tables = q.export_tables()
+    q2 = QueryRecord.from_tables(top, tables, inv)
+    t2 = q2.export_tables()
+    assert set(tables["funcs"]) == set(t2["funcs"]) and set(tables["mems"]) == set(t2["mems"])
+    for idx, t in tables["funcs"].items():
+        for k, v in t.items():
+            assert np.array_equal(v, t2["funcs"][idx][k]), (idx, k)      # the HINTS included: resolve recomputed them
+    for i, m in tables["mems"].items():
+        for k, v in m.items():
+            assert np.array_equal(v, t2["mems"][i][k]), (i, k)
+    assert np.array_equal(tables["bytes"], t2["bytes"])
+    assert np.array_equal(tables["public_values"], t2["public_values"])
+    return tables, q2
+
+
+@pytest.mark.parametrize("tname,fname,args", [("demo", "fib", [200]), ("demo", "even", [33]), ("memory", "test", []),
+                                              ("partial", "pmain", [300, 21]), ("range", "range_test", [100, 12, 64]),
+                                              ("u64", "divrem", [255] * 8 + [1, 1] + [0] * 6), ("hash", "cons_chain", [9]),
+                                              ("ackermann", "ackermann", [2, 12])])
+def test_an_imported_record_equals_the_executed_one(tname, fname, args):
+    # lsk_record_import_* + lsk_record_resolve: the drop-in path for a QueryRecord made by the reference's own executor
+    import goldens
+    tables, _ = _roundtrip_tables(goldens.toplevel_for(tname), fname, args)
+    assert any(t["hints"].size for t in tables["funcs"].values()) or tname in ("range", "u64")
+
+
+def test_an_imported_lurk_record_equals_the_executed_one():
+    # a Lurk evaluation through lurk_main: 17 func tables, 2 memories, byte lookups, injected hash preimages
+    from lurk_b200.bench_programs import source
+    from lurk_b200.lurk_eval import build_lurk_toplevel
+    from lurk_b200.reader import read
+    from lurk_b200.zstore import ZStore
+    top = build_lurk_toplevel()
+    z = ZStore()
+    e = read(z, source("fib", 25))
+    inv = [(name, list(z.hashes[w].items())) for name, w in (("hash3", 24), ("hash4", 32), ("hash5", 40)) if z.hashes[w]]
+
+    def setup(q):
+        z.inject(q, top)
+        return inv
+    tables, _ = _roundtrip_tables(top, "lurk_main", [e.tag] + [0] * 7 + list(e.digest) + [0] * 8, setup)
+    assert len(tables["funcs"]) >= 15
+
+
+def test_import_refuses_inconsistent_tables():
+    import numpy as np
+    from lurk_b200._native import LurkStarkError
+    from lurk_b200.execute import QueryRecord, execute_by_name
+    from lurk_b200.lair import demo_toplevel
+    top = demo_toplevel()
+    q = QueryRecord.new(top)
+    execute_by_name(top, "fib", [30], q)
+    tables = q.export_tables()
+    fib = top.func_by_name("fib").index
+    for mutate in ("output", "missing-row", "duplicate", "non-canonical", "offsets"):
+        t = {k: v.copy() for k, v in tables["funcs"][fib].items()}
+        if mutate == "output":
+            t["outs"][7, 0] = (int(t["outs"][7, 0]) + 1) % 2013265921      # resolve: the row does not return that
+        elif mutate == "missing-row":
+            n = len(t["provide"]) - 1                                        # drop fib(0): fib(2) calls a query that is not there
+            t = {"args": t["args"][:n], "outs": t["outs"][:n], "provide": t["provide"][:n], "req_off": t["req_off"][:n + 1],
+                 "reqs": t["reqs"][:int(t["req_off"][n])]}
+        elif mutate == "duplicate":
+            t["args"][3] = t["args"][4]
+        elif mutate == "non-canonical":
+            t["args"][3, 0] = 2013265921
+        else:
+            t["req_off"][5] = t["req_off"][6] + 1
+        funcs = dict(tables["funcs"])
+        funcs[fib] = t
+        bad = dict(tables, funcs=funcs)
+        with pytest.raises(LurkStarkError):
+            QueryRecord.from_tables(top, bad)

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """One or two proves of a workload, for running under ncu / compute-sanitizer:
-    python tools/prove_once.py [fib|cons|u64] [log_rows] [repeats]"""
+    python tools/prove_once.py [fib|cons|u64|lurk-fib|lurk-lcs|lurk-sum] [log_rows] [repeats]"""
 import os
 import sys
 
@@ -14,14 +14,15 @@ repeats = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 if workload == "u64":
     from lurk_b200.programs import u64_toplevel
     top, entry, arg = u64_toplevel(), "factu", [20] + [0] * 7
+    q = QueryRecord.new(top)
+    execute_by_name(top, entry, arg, q)
 else:
-    from bench import workload_program
-    top, entry = workload_program(workload)
-    arg = [(1 << log_rows) - 1]
+    from bench import Workload
+    wl = Workload(workload)
+    top, entry = wl.top, wl.entry
+    q, _ = wl.record(wl.arg_for(log_rows))
 m = new_machine(top, entry)
 pk, vk = m.setup()
-q = QueryRecord.new(top)
-execute_by_name(top, entry, arg, q)
 for _ in range(repeats):
     proof = m.prove(pk, Shard(q, 0, ShardingConfig(1 << max(log_rows, 10))))
 m.verify(vk, proof)

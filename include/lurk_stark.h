@@ -206,6 +206,30 @@ int lsk_coset_lde(lsk_ctx* ctx, const uint32_t* rows, size_t h, size_t w, int sh
 int lsk_merkle_root(lsk_ctx* ctx, const uint32_t* const* mats, const size_t* hs, const size_t* ws, size_t nmats,
                     uint32_t out8[8]);
 
+/* A8 / A10 / A12, one stage at a time: the third-party pieces sphinx's prover runs between the
+ * commitments, exposed so that each can be held against the oracle on its own.  `chip` indexes the machine's chip
+ * vector (build_lair_chip_vector order, src/lair/lair_chip.rs:196-212); matrices are row-major canonical with
+ * NATURAL row order on the trace domain; extension elements are 4 canonical words.
+ *   lsk_perm_trace: sphinx `generate_permutation_trace` for one chip -- per row and batch of two interactions
+ *     sum +-mult / (alpha + kind + sum_k beta^(k+1) value_k), last column = running sum; perm_rows_out is
+ *     h x 4*pw (pw = lsk_machine_chip_perm_width), cum_sum_out the chip's cumulative sum.
+ *   lsk_quotient: `quotient_values`: Air::eval (src/lair/lair_chip.rs:156-194) + the LogUp constraints folded with
+ *     powers of `alpha` on the 2h-point quotient domain g*H_2h, divided by the vanishing polynomial; inputs are the
+ *     main and permutation traces on the trace domain (extended inside), output 2h x 4 in commitment (bit-reversed) order.
+ *   lsk_fri_prove: TwoAdicFriPcs's FRI on ONE vector of 2^log_n extension values (commitment order): commit phase
+ *     (arity-2 folds, one Merkle commitment per layer, the transcript step on the device), final constant, proof-of-
+ *     work witness, query indices and openings.  challenger_state = the DuplexChallenger's 16 sponge words with an
+ *     empty input buffer.  Words: nlayers, roots[nlayers][8], final_poly[4], pow_witness, nqueries, then per query:
+ *     index, per layer { sibling[4], pathlen, digests[pathlen][8] }.  Free with lsk_proof_free. */
+int lsk_machine_chip_perm_width(const lsk_machine* m, uint32_t chip);
+int lsk_perm_trace(lsk_machine* m, uint32_t chip, const uint32_t* main_rows, size_t h, const uint32_t chal_alpha[4],
+                   const uint32_t chal_beta[4], uint32_t* perm_rows_out, uint32_t cum_sum_out[4]);
+int lsk_quotient(lsk_machine* m, uint32_t chip, const uint32_t* main_rows, const uint32_t* perm_rows, size_t h,
+                 const uint32_t* public_values, const uint32_t cum_sum[4], const uint32_t chal_alpha[4],
+                 const uint32_t chal_beta[4], const uint32_t alpha[4], uint32_t* quot_out);
+int lsk_fri_prove(lsk_ctx* ctx, const uint32_t* vals, uint32_t log_n, const uint32_t challenger_state[16], uint32_t num_queries,
+                  uint32_t pow_bits, uint32_t** words, size_t* len);
+
 /* ---- C++ host layer (csrc/host_lair.h, host_air.cpp): what the reference does in Rust before it can call the
  * prover -- Toplevel::new (expand + compile the `func!` definitions, src/lair/toplevel.rs), FuncChip layout
  * (src/lair/func_chip.rs:90-277) and Chip::new's symbolic run of every Air::eval (src/lair/lair_chip.rs:

@@ -245,8 +245,8 @@ std::string interactions_source(const ChipH& c) {
   auto one = [&](size_t k) {
     const bool recv = k >= c.sends.size();
     const InteractionH& it = recv ? c.receives[k - c.sends.size()] : c.sends[k];
-    snprintf(buf, sizeof buf, "__device__ __noinline__ void lsk_int_%zu(const Cells& c, const Ext& alpha, const Ext* __restrict__ bp, "
-                              "Ext& r, uint32_t& m) {\n  m = ", k);
+    snprintf(buf, sizeof buf, "__device__ __noinline__ LskInt lsk_int_%zu(const Cells c, const Ext alpha, const Ext* __restrict__ bp) "
+                              "{\n  Ext r;\n  const uint32_t m = ", k);
     o += buf;
     std::string m;
     affine_source(m, it.mult);
@@ -257,22 +257,23 @@ std::string interactions_source(const ChipH& c) {
       std::string val;
       affine_source(val, it.values[j]);
       if (val == "0u") continue;   // adds beta^(j+1) * 0
-      snprintf(buf, sizeof buf, "  r = eadd(r, emul_base(bp[%zu], ", j);
+      snprintf(buf, sizeof buf, "  r = eadd(r, emul_base(ldg_ext(bp + %zu), ", j);
       o += buf;
       o += val + "));\n";
     }
-    o += "}\n";
+    o += "  return LskInt{r, m};\n}\n";
   };
+  o += "struct LskInt { Ext r; uint32_t m; };\n";
   for (size_t k = 0; k < nint; k++) one(k);
   o += "template <class V>\n__device__ __forceinline__ void lsk_interactions(const Cells& c, const Ext& alpha, "
-       "const Ext* __restrict__ bp, V& v) {\n  Ext r0, r1;\n  uint32_t m0, m1;\n";
+       "const Ext* __restrict__ bp, V& v) {\n";
   for (size_t b = 0; 2 * b < nint; b++) {
-    snprintf(buf, sizeof buf, "  lsk_int_%zu(c, alpha, bp, r0, m0);\n", 2 * b);
+    snprintf(buf, sizeof buf, "  {\n    const LskInt i0 = lsk_int_%zu(c, alpha, bp);\n", 2 * b);
     o += buf;
     if (2 * b + 1 < nint) {
-      snprintf(buf, sizeof buf, "  lsk_int_%zu(c, alpha, bp, r1, m1);\n  v.pair(%zu, r0, m0, r1, m1);\n", 2 * b + 1, b);
+      snprintf(buf, sizeof buf, "    const LskInt i1 = lsk_int_%zu(c, alpha, bp);\n    v.pair(%zu, i0.r, i0.m, i1.r, i1.m);\n  }\n", 2 * b + 1, b);
     } else {
-      snprintf(buf, sizeof buf, "  v.single(%zu, r0, m0);\n", b);
+      snprintf(buf, sizeof buf, "    v.single(%zu, i0.r, i0.m);\n  }\n", b);
     }
     o += buf;
   }

@@ -295,6 +295,70 @@ __global__ void __launch_bounds__(K13_THREADS) lde_k3_kernel(uint32_t* __restric
     reinterpret_cast<uint4*>(p)[t * 4 + k] = make_uint4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
 }
 
+
+// K3 with the tile staged by a bulk-asynchronous copy (cp.async.bulk + mbarrier: the 1-D form of TMA, SASS UBLKCP):
+// persistent CTAs, two 16 KB input buffers; while the CTA transforms tile i the copy engine fetches tile i + 1, so the
+// loads that lde_k3_kernel waits for (ncu: long_scoreboard is its top stall) are off the critical path.  Selected
+// with LSK_LDE_BULK=1; measured against the plain kernel in DESIGN.md section 10.
+LSK_D uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__global__ void __launch_bounds__(K13_THREADS) lde_k3_bulk_kernel(uint32_t* __restrict__ out, size_t out_stride, unsigned tiles_per_col,
+                                                                   unsigned ntiles, const uint2* __restrict__ tw_fwd) {
+  extern __shared__ __align__(128) uint32_t k3b_smem[];   // in[2][4096] ++ s[K13_SMEM]: 50 KB, above the static limit
+  uint32_t(*in)[BLOCK_ELEMS] = reinterpret_cast<uint32_t(*)[BLOCK_ELEMS]>(k3b_smem);
+  uint32_t* s = k3b_smem + 2 * BLOCK_ELEMS;
+  __shared__ __align__(8) uint64_t bar[2];
+  const unsigned t = threadIdx.x, hi = t >> 4, lo = t & 15;
+  auto tile_ptr = [&](unsigned tile) { return out + (size_t)(tile / tiles_per_col) * out_stride + (size_t)(tile % tiles_per_col) * BLOCK_ELEMS; };
+  auto issue = [&](unsigned tile, unsigned b) {   // one thread: arm the barrier with the byte count, start the copy
+    const uint32_t bytes = BLOCK_ELEMS * 4;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&bar[b])), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(in[b])),
+                 "l"(tile_ptr(tile)), "r"(bytes), "r"(smem_u32(&bar[b]))
+                 : "memory");
+  };
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[0])));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar[1])));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (t == 0 && blockIdx.x < ntiles) issue(blockIdx.x, 0);
+  unsigned it = 0;
+  for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+    const unsigned b = it & 1, parity = (it >> 1) & 1;
+    if (t == 0 && tile + gridDim.x < ntiles) issue(tile + gridDim.x, b ^ 1);
+    {  // wait for this tile's bytes
+      uint32_t done = 0;
+      while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(smem_u32(&bar[b])), "r"(parity)
+                     : "memory");
+    }
+    uint32_t* p = tile_ptr(tile);
+    uint32_t x[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = in[b][j * 256 + t];
+    dif_local<4>(x, 8, t, tw_fwd);
+#pragma unroll
+    for (int j = 0; j < 16; j++) s[pad16(j * 256 + t)] = x[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = s[pad16(hi * 256 + j * 16 + lo)];
+    dif_local<4>(x, 4, lo, tw_fwd);
+#pragma unroll
+    for (int j = 0; j < 16; j++) s[pad16(hi * 256 + j * 16 + lo)] = x[j];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 16; j++) x[j] = s[pad16(t * 16 + j)];
+    dif_local<4>(x, 0, 0, tw_fwd);
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      reinterpret_cast<uint4*>(p)[t * 4 + k] = make_uint4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+    __syncthreads();   // `s` and in[b] are free again (in[b] is refilled by the copy issued in the next iteration)
+  }
+}
+
 // K2: the middle pass over a tile of 2^t blocks (q) x 2^c consecutive low indices (lo), element (q, lo)
 // at shared index (q << c) | lo.  The size-2^t transforms over q run as ceil(t/4) register passes of
 // 2^r (r <= 4) elements each; the first DIT pass reads global memory (applying the inverse inter-pass
@@ -391,7 +455,9 @@ __global__ void __launch_bounds__(NT, 768 / NT > 0 ? 768 / NT : 1) lde_k2_kernel
   }
 }
 
+constexpr size_t K3B_SMEM_BYTES = (2 * BLOCK_ELEMS + K13_SMEM) * sizeof(uint32_t);
 void init_ntt_kernels() {
+  LSK_CUDA(cudaFuncSetAttribute(lde_k3_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3B_SMEM_BYTES));
   LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
   LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
   LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
@@ -477,6 +543,12 @@ void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, 
     }
     {
       ProfScope ps(ctx, PT_LDE_K3, 1, 16.0 * cells);
+      static const bool bulk = [] { const char* e = getenv("LSK_LDE_BULK"); return e && e[0] == '1'; }();
+      if (bulk) {
+        const unsigned ntiles = 2 * blocks * nc;
+        lde_k3_bulk_kernel<<<std::min(ntiles, 148u * 4u), K13_THREADS, K3B_SMEM_BYTES, st>>>(cout, out_stride, 2 * blocks, ntiles,
+                                                                                             t->tw_fwd.p);
+      } else
       lde_k3_kernel<<<dim3(2 * blocks, nc), K13_THREADS, 0, st>>>(cout, out_stride, t->tw_fwd.p);
     }
   }

@@ -720,11 +720,28 @@ __global__ void import_rows_kernel(const uint32_t* __restrict__ rows, size_t h, 
   size_t dr = bitrev ? bitrev32((uint32_t)r, logh) : r;
   out[c * h + dr] = to_mont(rows[i]);
 }
-__global__ void export_rows_kernel(const uint32_t* __restrict__ cols, size_t h, uint32_t w, uint32_t* __restrict__ rows) {
+__global__ void export_rows_kernel(const uint32_t* __restrict__ cols, size_t h, uint32_t w, uint32_t* __restrict__ rows,
+                                   unsigned logh = 0, bool bitrev = false) {
   size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= h * w) return;
   size_t r = i / w, c = i % w;
-  rows[i] = from_mont(cols[c * h + r]);
+  rows[i] = from_mont(cols[c * h + (bitrev ? bitrev32((uint32_t)r, logh) : r)]);
+}
+static Ext ext_from_canonical(const uint32_t* w) {
+  Ext e;
+  for (int k = 0; k < 4; k++) {
+    if (w[k] >= P) fail(LSK_ERR_ARG, "non-canonical extension element");
+    e.c[k] = to_mont(w[k]);
+  }
+  return e;
+}
+static void upload_ext_pows(lsk_ctx* ctx, const Ext& base, size_t n, bool from_one, DevBuf<Ext>& dev) {
+  std::vector<Ext> host(std::max<size_t>(n, 1));
+  Ext p = from_one ? ext_one() : base;
+  for (auto& x : host) x = p, p = emul(p, base);
+  dev.alloc(ctx, host.size());
+  dev.upload(host.data(), host.size());
+  LSK_CUDA(cudaStreamSynchronize(ctx->stream));   // `host` dies with this call
 }
 
 void record_unpin(lsk_record* r) {
@@ -971,6 +988,209 @@ int lsk_merkle_root(lsk_ctx* ctx, const uint32_t* const* mats, const size_t* hs,
   MerkleTreeDev tree;
   merkle_commit_dev(ctx, refs, tree);
   merkle_root_host(ctx, tree, out8);
+  return LSK_OK;
+  LSK_API_END
+}
+
+
+// ---- A8 / A10 / A12 as stages: the third-party pieces behind machine.prove, one at a time, so that a
+// mismatch with the oracle can be localised without bisecting a whole proof ---------------------------------------
+int lsk_machine_chip_perm_width(const lsk_machine* m, uint32_t chip) {
+  return (m && chip < m->chips.size()) ? (int)m->chips[chip].perm_width() : -1;
+}
+static const ChipH& stage_chip(const lsk_machine* m, uint32_t chip, size_t h, const uint32_t* main_rows) {
+  if (!m || !main_rows || chip >= m->chips.size() || !h || (h & (h - 1)) || h > ((size_t)1 << 24)) fail(LSK_ERR_ARG, "bad argument");
+  const ChipH& c = m->chips[chip];
+  if (c.prep_width && h != 65536) fail(LSK_ERR_ARG, "the byte chip's traces have 65536 rows");
+  return c;
+}
+int lsk_perm_trace(lsk_machine* m, uint32_t chip, const uint32_t* main_rows, size_t h, const uint32_t chal_alpha[4],
+                   const uint32_t chal_beta[4], uint32_t* perm_rows_out, uint32_t cum_sum_out[4]) {
+  LSK_API_BEGIN
+  const ChipH& c = stage_chip(m, chip, h, main_rows);
+  if (!chal_alpha || !chal_beta || !perm_rows_out || !cum_sum_out) fail(LSK_ERR_ARG, "null argument");
+  lsk_ctx* ctx = m->ctx;
+  LSK_CUDA(cudaSetDevice(ctx->device));
+  const unsigned logn = log2_exact(h);
+  const uint32_t pcols = 4 * (uint32_t)c.perm_width();
+  DevBuf<uint32_t> d_rows(ctx, h * c.width), tr(ctx, h * c.width), perm(ctx, h * pcols), d_out(ctx, h * pcols);
+  d_rows.upload(main_rows, h * c.width);
+  import_rows_kernel<<<div_up(h * c.width, 256), 256, 0, ctx->stream>>>(d_rows.p, h, c.width, logn, true, tr.p);
+  DevBuf<Ext> d_beta, scratch(ctx, h), cum(ctx, 1);
+  upload_ext_pows(ctx, ext_from_canonical(chal_beta), c.max_values(), false, d_beta);
+  perm_trace_dev(ctx, m->dchips[chip], tr.p, h, c.prep_width ? m->prep_trace.p : nullptr, h, logn, ext_from_canonical(chal_alpha),
+                 d_beta.p, perm.p, h, scratch.p, cum.p);
+  export_rows_kernel<<<div_up(h * pcols, 256), 256, 0, ctx->stream>>>(perm.p, h, pcols, d_out.p, logn, true);
+  LSK_CUDA(cudaGetLastError());
+  d_out.download(perm_rows_out, h * pcols);
+  Ext hc;
+  cum.download(&hc, 1);
+  LSK_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int k = 0; k < 4; k++) cum_sum_out[k] = from_mont(hc.c[k]);
+  return LSK_OK;
+  LSK_API_END
+}
+int lsk_quotient(lsk_machine* m, uint32_t chip, const uint32_t* main_rows, const uint32_t* perm_rows, size_t h,
+                 const uint32_t* public_values, const uint32_t cum_sum[4], const uint32_t chal_alpha[4],
+                 const uint32_t chal_beta[4], const uint32_t alpha[4], uint32_t* quot_out) {
+  LSK_API_BEGIN
+  const ChipH& c = stage_chip(m, chip, h, main_rows);
+  if (!perm_rows || !cum_sum || !chal_alpha || !chal_beta || !alpha || !quot_out || (m->num_pv && !public_values))
+    fail(LSK_ERR_ARG, "null argument");
+  lsk_ctx* ctx = m->ctx;
+  LSK_CUDA(cudaSetDevice(ctx->device));
+  const unsigned logn = log2_exact(h);
+  const uint32_t pcols = 4 * (uint32_t)c.perm_width();
+  const size_t n2 = 2 * h;
+  DevBuf<uint32_t> d_rows(ctx, h * std::max<size_t>(c.width, pcols)), tr(ctx, h * c.width), pm(ctx, h * pcols);
+  DevBuf<uint32_t> main_lde(ctx, n2 * c.width), perm_lde(ctx, n2 * pcols), qv(ctx, n2 * 4), d_out(ctx, n2 * 4);
+  d_rows.upload(main_rows, h * c.width);
+  import_rows_kernel<<<div_up(h * c.width, 256), 256, 0, ctx->stream>>>(d_rows.p, h, c.width, logn, true, tr.p);
+  LSK_CUDA(cudaStreamSynchronize(ctx->stream));
+  d_rows.upload(perm_rows, h * pcols);
+  import_rows_kernel<<<div_up(h * pcols, 256), 256, 0, ctx->stream>>>(d_rows.p, h, pcols, logn, true, pm.p);
+  lde_dev(ctx, tr.p, h, main_lde.p, n2, logn, c.width, LdeShift::Trace);
+  lde_dev(ctx, pm.p, h, perm_lde.p, n2, logn, pcols, LdeShift::Trace);
+  DevBuf<Ext> d_beta, d_alpha, d_cum(ctx, 1);
+  upload_ext_pows(ctx, ext_from_canonical(chal_beta), c.max_values(), false, d_beta);
+  const uint32_t n_total = (uint32_t)(c.n_constraints + c.n_perm_constraints());
+  upload_ext_pows(ctx, ext_from_canonical(alpha), n_total, true, d_alpha);
+  Ext hc = ext_from_canonical(cum_sum);
+  d_cum.upload(&hc, 1);
+  std::vector<uint32_t> pv(std::max<size_t>(1, m->num_pv), 0);
+  for (uint32_t k = 0; k < m->num_pv; k++) {
+    if (public_values[k] >= P) fail(LSK_ERR_ARG, "non-canonical public value");
+    pv[k] = to_mont(public_values[k]);
+  }
+  DevBuf<uint32_t> d_pv(ctx, pv.size());
+  d_pv.upload(pv.data(), pv.size());
+  QuotientArgs a{};
+  a.main = main_lde.p; a.mstride = n2;
+  a.prep = c.prep_width ? m->prep_lde.p : nullptr; a.pstride = n2;
+  a.perm = perm_lde.p; a.permstride = n2;
+  a.pv = d_pv.p;
+  a.apow = d_alpha.p;
+  a.n_total = n_total;
+  a.beta_pows = d_beta.p;
+  a.cum_sum = d_cum.p;
+  a.chal_alpha = ext_from_canonical(chal_alpha);
+  a.logn = logn;
+  a.out = qv.p; a.ostride = n2;
+  quotient_dev(ctx, m->dchips[chip], a);
+  export_rows_kernel<<<div_up(n2 * 4, 256), 256, 0, ctx->stream>>>(qv.p, n2, 4, d_out.p);
+  LSK_CUDA(cudaGetLastError());
+  d_out.download(quot_out, n2 * 4);
+  LSK_CUDA(cudaStreamSynchronize(ctx->stream));
+  return LSK_OK;
+  LSK_API_END
+}
+int lsk_fri_prove(lsk_ctx* ctx, const uint32_t* vals, uint32_t log_n, const uint32_t challenger_state[16], uint32_t num_queries,
+                  uint32_t pow_bits, uint32_t** words, size_t* len) {
+  LSK_API_BEGIN
+  if (!ctx || !vals || !challenger_state || !words || !len || log_n < 2 || log_n > 25 || !num_queries || num_queries > 1024 ||
+      pow_bits > 30)
+    fail(LSK_ERR_ARG, "bad argument");
+  LSK_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  static const HostPerm16 perm;
+  Challenger ch(&perm);
+  for (int k = 0; k < 16; k++) {
+    if (challenger_state[k] >= P) fail(LSK_ERR_ARG, "non-canonical challenger state");
+    ch.state[k] = to_mont(challenger_state[k]);
+  }
+  const size_t n = (size_t)1 << log_n;
+  const unsigned log_max = log_n, nlayers = log_max - LOG_BLOWUP;
+  std::vector<DevBuf<Ext>> fri_vals(nlayers + 1);
+  std::vector<MerkleTreeDev> fri_trees(nlayers);
+  {
+    std::vector<Ext> h(n);
+    for (size_t i = 0; i < n; i++) h[i] = ext_from_canonical(vals + 4 * i);
+    fri_vals[0].alloc(ctx, n);
+    fri_vals[0].upload(h.data(), n);
+    LSK_CUDA(cudaStreamSynchronize(st));
+  }
+  DevBuf<uint32_t> d_chal(ctx, 16), d_roots(ctx, 8 * (size_t)nlayers);
+  DevBuf<Ext> d_betas(ctx, nlayers);
+  d_chal.upload(ch.state, 16);
+  for (unsigned li = 0; li < nlayers; li++) {
+    unsigned lfh = log_max - 1 - li;
+    FriChallenge fc{d_chal.p, d_betas.p + li, d_roots.p + 8 * (size_t)li};
+    if (lfh <= FRI_TAIL_LOG) {
+      std::vector<Ext*> v;
+      std::vector<const Ext*> add;
+      for (unsigned j = 0; j <= lfh; j++) {
+        if (j) fri_vals[li + j].alloc(ctx, (size_t)2 << (lfh - j));
+        v.push_back(fri_vals[li + j].p);
+        if (j < lfh) add.push_back(nullptr);
+      }
+      fri_commit_tail_dev(ctx, lfh, v.data(), &fri_trees[li], add.data(), fc);
+      break;
+    }
+    merkle_commit_fri_layer_dev(ctx, (const uint32_t*)fri_vals[li].p, lfh, fri_trees[li], fc);
+    fri_vals[li + 1].alloc(ctx, (size_t)1 << lfh);
+    fri_fold_dev(ctx, fri_vals[li].p, lfh, d_betas.p + li, nullptr, fri_vals[li + 1].p);
+  }
+  Ext fin[2];
+  std::vector<uint32_t> h_roots(8 * (size_t)nlayers);
+  fri_vals[nlayers].download(fin, 2);
+  d_roots.download(h_roots.data(), h_roots.size());
+  LSK_CUDA(cudaStreamSynchronize(st));
+  std::vector<uint32_t> W;
+  W.push_back(nlayers);
+  for (unsigned li = 0; li < nlayers; li++) {
+    for (int k = 0; k < 8; k++) {
+      ch.observe(h_roots[8 * li + k]);
+      W.push_back(from_mont(h_roots[8 * li + k]));
+    }
+    ch.sample_ext();
+  }
+  if (!ext_eq(fin[0], fin[1])) fail(LSK_ERR_EXEC, "the folded vector is not constant: the input is not a low-degree codeword");
+  for (int k = 0; k < 4; k++) W.push_back(from_mont(fin[0].c[k]));
+  ch.observe(fin[0]);
+  uint32_t state_c[16], pend_c[8];
+  for (int k = 0; k < 16; k++) state_c[k] = from_mont(ch.state[k]);
+  for (size_t k = 0; k < ch.in.size(); k++) pend_c[k] = from_mont(ch.in[k]);
+  uint32_t pow_witness = grind_dev(ctx, state_c, pend_c, (unsigned)ch.in.size(), pow_bits);
+  if (!ch.check_witness(pow_bits, to_mont(pow_witness))) fail(LSK_ERR_EXEC, "device grinding returned a bad witness");
+  W.push_back(pow_witness);
+  W.push_back(num_queries);
+  // one query: index, then per layer the sibling value and the Merkle path of the pair's row
+  std::vector<QuerySeg> segs;
+  uint32_t wpq = 0;
+  auto data = [&](const uint32_t* p, uint64_t stride, uint32_t count, uint32_t shift, uint32_t xor1, uint32_t mul) {
+    segs.push_back(QuerySeg{p, stride, count, wpq, shift, xor1, mul, 0, 0, QSEG_ALL});
+    wpq += count;
+  };
+  auto lit = [&](uint32_t v) {
+    segs.push_back(QuerySeg{nullptr, 0, 1, wpq, 0, 0, 0, v, 0, QSEG_ALL});
+    wpq += 1;
+  };
+  for (unsigned li = 0; li < nlayers; li++) {
+    const MerkleTreeDev& t = fri_trees[li];
+    data((const uint32_t*)fri_vals[li].p, 1, 4, li, 1, 4);
+    lit(t.log_max);
+    for (unsigned l = 0; l < t.log_max; l++) data(t.layer(l), 1, 8, li + 1 + l, 1, 8);
+  }
+  std::vector<uint32_t> indices(num_queries);
+  for (auto& ix : indices) ix = ch.sample_bits(log_max);
+  std::vector<uint32_t> gathered((size_t)num_queries * wpq);
+  {
+    DevBuf<QuerySeg> d_segs(ctx, segs.size());
+    DevBuf<uint32_t> d_idx(ctx, indices.size()), d_out(ctx, gathered.size());
+    d_segs.upload(segs.data(), segs.size());
+    d_idx.upload(indices.data(), indices.size());
+    query_assemble_dev(ctx, d_segs.p, (uint32_t)segs.size(), d_idx.p, num_queries, wpq, d_out.p);
+    d_out.download(gathered.data(), gathered.size());
+    LSK_CUDA(cudaStreamSynchronize(st));
+  }
+  for (uint32_t q = 0; q < num_queries; q++) {
+    W.push_back(indices[q]);
+    W.insert(W.end(), gathered.begin() + (size_t)q * wpq, gathered.begin() + (size_t)(q + 1) * wpq);
+  }
+  *words = (uint32_t*)malloc(W.size() * 4 + 4);
+  if (!*words) fail(LSK_ERR_ARG, "out of memory");
+  memcpy(*words, W.data(), W.size() * 4);
+  *len = W.size();
   return LSK_OK;
   LSK_API_END
 }

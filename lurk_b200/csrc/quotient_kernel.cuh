@@ -73,6 +73,10 @@ LSK_D void eval_interaction(const uint32_t* __restrict__& s, const Cells& c, con
     rlc = eadd(rlc, emul_base(beta_pows[v], val));
   }
 }
+LSK_D Ext ldg_ext(const Ext* __restrict__ p) {   // 16-byte aligned (arrays of Ext in device buffers)
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+  return Ext{{v.x, v.y, v.z, v.w}};
+}
 LSK_D Ext load_ext_cols(const uint32_t* __restrict__ m, size_t stride, uint32_t first_col, size_t r) {
   Ext e;
 #pragma unroll
@@ -154,11 +158,14 @@ LSK_D void quotient_row_tail(const QuotientArgs& a, const QuotientConsts& qc, co
 #else
 #define LSK_R(i) R[i]
 #endif
-#define LSK_ML(i) a.main[(size_t)(i) * a.mstride + q.r]
-#define LSK_MN(i) a.main[(size_t)(i) * a.mstride + q.rn]
-#define LSK_PL(i) a.prep[(size_t)(i) * a.pstride + q.r]
-#define LSK_PN(i) a.prep[(size_t)(i) * a.pstride + q.rn]
-#define LSK_PV(i) a.pv[i]
+// trace cells, public values and challenge powers are read-only for the whole launch: __ldg makes the loads
+// LDG.CONSTANT -- through the argument structs they were GENERIC loads (LD.E), which the compiler must keep in order with
+// every store to the register file / the stack and cannot hoist (ncu: long_scoreboard was the top stall)
+#define LSK_ML(i) __ldg(a.main + ((size_t)(i) * a.mstride + q.r))
+#define LSK_MN(i) __ldg(a.main + ((size_t)(i) * a.mstride + q.rn))
+#define LSK_PL(i) __ldg(a.prep + ((size_t)(i) * a.pstride + q.r))
+#define LSK_PN(i) __ldg(a.prep + ((size_t)(i) * a.pstride + q.rn))
+#define LSK_PV(i) __ldg(a.pv + (i))
 #define LSK_SEL(i) q.sel[i]
 // constraints of one chunk: sum_i alpha^(n_total-1-ci) * v_i as four 64-bit sums of raw products, each kept below
 // P * 2^32 (what mont_reduce accepts) by one conditional subtraction per term; reduced once when the chunk ends
@@ -167,7 +174,7 @@ LSK_D void quotient_row_tail(const QuotientArgs& a, const QuotientConsts& qc, co
 // (P * 2^32 + 2 P^2 < 2^64): jit.cu alternates them; LSK_ASSERT_END reduces whatever is pending
 #define LSK_ASSERT_A(ci, v)                                \
   {                                                        \
-    const Ext lsk_ap = a.apow[a.n_total - 1 - (ci)];       \
+    const Ext lsk_ap = ldg_ext(a.apow + (a.n_total - 1 - (ci))); \
     const uint32_t lsk_x = (v);                            \
     lsk_s0 += (uint64_t)lsk_ap.c[0] * lsk_x;               \
     lsk_s1 += (uint64_t)lsk_ap.c[1] * lsk_x;               \
@@ -176,7 +183,7 @@ LSK_D void quotient_row_tail(const QuotientArgs& a, const QuotientConsts& qc, co
   }
 #define LSK_ASSERT_B(ci, v)                                             \
   {                                                                     \
-    const Ext lsk_ap = a.apow[a.n_total - 1 - (ci)];                    \
+    const Ext lsk_ap = ldg_ext(a.apow + (a.n_total - 1 - (ci)));        \
     const uint32_t lsk_x = (v);                                         \
     lsk_s0 = acc_reduce64(lsk_s0 + (uint64_t)lsk_ap.c[0] * lsk_x);      \
     lsk_s1 = acc_reduce64(lsk_s1 + (uint64_t)lsk_ap.c[1] * lsk_x);      \
@@ -189,27 +196,27 @@ LSK_D void quotient_row_tail(const QuotientArgs& a, const QuotientConsts& qc, co
 #include "lsk_program.cuh"
 // "lsk_interactions.cuh" (jit.cu::interactions_source): lsk_interactions<V>(cells, alpha, beta_pows, v) evaluates the
 // chip's interactions as straight-line code and hands every LogUp batch to v.pair(b, r0, m0, r1, m1) / v.single(b, r0, m0)
-#define LSK_CM(i) c.main[(size_t)(i) * c.mstride + c.r]
-#define LSK_CP(i) c.prep[(size_t)(i) * c.pstride + c.r]
+#define LSK_CM(i) __ldg(c.main + ((size_t)(i) * c.mstride + c.r))
+#define LSK_CP(i) __ldg(c.prep + ((size_t)(i) * c.pstride + c.r))
 #include "lsk_interactions.cuh"
 // the batch bodies are real calls: inlined into every one of a chip's 10-30 batches they multiply NVVM's work (the
 // 41 chips of the Lurk machine took 19 minutes to compile that way, 40 s like this) for no measurable gain
-__device__ __noinline__ Ext lsk_perm_pair(const Ext& r0, uint32_t m0, const Ext& r1, uint32_t m1) {
+__device__ __noinline__ Ext lsk_perm_pair(Ext r0, uint32_t m0, Ext r1, uint32_t m1) {
   const Ext num = eadd(emul_base(r1, m0), emul_base(r0, m1));
   return (m0 | m1) ? emul(num, einv(emul(r0, r1))) : ext_zero();
 }
-__device__ __noinline__ Ext lsk_perm_single(const Ext& r0, uint32_t m0) { return m0 ? emul_base(einv(r0), m0) : ext_zero(); }
-__device__ __noinline__ Ext lsk_quot_pair(const Ext& pl, const Ext& r0, uint32_t m0, const Ext& r1, uint32_t m1) {
+__device__ __noinline__ Ext lsk_perm_single(Ext r0, uint32_t m0) { return m0 ? emul_base(einv(r0), m0) : ext_zero(); }
+__device__ __noinline__ Ext lsk_quot_pair(Ext pl, Ext r0, uint32_t m0, Ext r1, uint32_t m1) {
   return esub(emul(emul(pl, r0), r1), eadd(emul_base(r1, m0), emul_base(r0, m1)));
 }
-__device__ __noinline__ Ext lsk_fold(const Ext& ac, const Ext& ap, const Ext& x) { return eadd(ac, emul(ap, x)); }
+__device__ __noinline__ Ext lsk_fold(Ext ac, Ext ap, Ext x) { return eadd(ac, emul(ap, x)); }
 struct LskQuotientBatches {   // quotient_row_finish's loop body
   const QuotientArgs& a;
   const QuotientRow& q;
   Ext ac, sum_local, sum_next;
   uint32_t cj;
   LSK_D void fold(uint32_t b, const Ext& pl, const Ext& diff) {
-    ac = lsk_fold(ac, a.apow[a.n_total - 1 - (cj++)], diff);
+    ac = lsk_fold(ac, ldg_ext(a.apow + (a.n_total - 1 - (cj++))), diff);
     sum_local = eadd(sum_local, pl);
     sum_next = eadd(sum_next, load_ext_cols(a.perm, a.permstride, 4 * b, q.rn));
   }

@@ -99,4 +99,109 @@ int orc_merkle_root(const uint32_t* const* mats, const size_t* hs, const size_t*
     return -1;
   }
 }
+// ---- A8 / A10 / A12 one stage at a time (counterparts of lsk_perm_trace / lsk_quotient / lsk_fri_prove) ----------
+static Ef ef_from(const uint32_t* w) {
+  Ef e;
+  for (int k = 0; k < 4; k++) e.c[k] = Fp::from_u32(w[k]);
+  return e;
+}
+int orc_chip_perm_width(void* m, uint32_t chip) { return (int)((Machine*)m)->chips.at(chip).perm_width(); }
+// main: h x w row-major canonical, natural rows -> perm: h x 4*pw, cum[4]
+int orc_perm_trace(void* mp, uint32_t chip, const uint32_t* main, size_t h, const uint32_t* alpha, const uint32_t* beta,
+                   uint32_t* perm_out, uint32_t* cum_out) {
+  try {
+    Machine& m = *(Machine*)mp;
+    const Chip& c = m.chips.at(chip);
+    std::vector<Fp> v(h * c.width);
+    for (size_t i = 0; i < v.size(); i++) v[i] = Fp::from_u32(main[i]);
+    Mat mm = from_row_major(v, h, c.width);
+    Ef cum;
+    Mat perm = permutation_trace(c, mm, c.prep_width ? &m.prep_trace : nullptr, ef_from(alpha), ef_from(beta), &cum);
+    for (size_t r = 0; r < h; r++)
+      for (size_t k = 0; k < perm.w; k++) perm_out[r * perm.w + k] = perm.at(r, k).to_u32();
+    for (int k = 0; k < 4; k++) cum_out[k] = cum.c[k].to_u32();
+    return 0;
+  } catch (std::exception& e) {
+    g_serr = e.what();
+    return -1;
+  }
+}
+// quotient values on g*H_2h in commitment (bit-reversed) order: 2h x 4
+int orc_quotient(void* mp, uint32_t chip, const uint32_t* main, const uint32_t* perm, size_t h, const uint32_t* pv,
+                 const uint32_t* cum, const uint32_t* chal_alpha, const uint32_t* chal_beta, const uint32_t* alpha,
+                 uint32_t* out) {
+  try {
+    Machine& m = *(Machine*)mp;
+    const Chip& c = m.chips.at(chip);
+    size_t pcols = 4 * c.perm_width();
+    std::vector<Fp> a(h * c.width), b(h * pcols), pvs(m.num_pv);
+    for (size_t i = 0; i < a.size(); i++) a[i] = Fp::from_u32(main[i]);
+    for (size_t i = 0; i < b.size(); i++) b[i] = Fp::from_u32(perm[i]);
+    for (size_t i = 0; i < pvs.size(); i++) pvs[i] = Fp::from_u32(pv[i]);
+    Mat main_lde = coset_lde(from_row_major(a, h, c.width)), perm_lde = coset_lde(from_row_major(b, h, pcols));
+    std::vector<Ef> q = quotient_values(c, log2_strict(h), main_lde, perm_lde, c.prep_width ? &m.prep_lde : nullptr, pvs,
+                                        ef_from(cum), ef_from(chal_alpha), ef_from(chal_beta), ef_from(alpha));
+    for (size_t r = 0; r < q.size(); r++)
+      for (int k = 0; k < 4; k++) out[4 * r + k] = q[r].c[k].to_u32();
+    return 0;
+  } catch (std::exception& e) {
+    g_serr = e.what();
+    return -1;
+  }
+}
+// FRI on one vector (2^log_n extension values, commitment order) from a given DuplexChallenger sponge state; the word
+// image of lsk_fri_prove (include/lurk_stark.h)
+int orc_fri_prove(const uint32_t* vals, uint32_t log_n, const uint32_t* state, uint32_t num_queries, uint32_t pow_bits,
+                  uint32_t** out, size_t* out_len) {
+  try {
+    size_t n = (size_t)1 << log_n;
+    std::vector<Ef> cur(n);
+    for (size_t i = 0; i < n; i++) cur[i] = ef_from(vals + 4 * i);
+    Challenger ch;
+    for (int k = 0; k < 16; k++) ch.state[k] = Fp::from_u32(state[k]);
+    std::vector<std::vector<Ef>> layer_vals;
+    std::vector<Mat> layer_mats;
+    std::vector<MerkleTree> trees;
+    layer_mats.reserve(log_n);
+    trees.reserve(log_n);
+    std::vector<uint32_t> W;
+    W.push_back(log_n - 1);
+    for (unsigned lfh = log_n - 1;; lfh--) {
+      layer_vals.push_back(cur);
+      layer_mats.push_back(fri_layer_matrix(cur));
+      trees.push_back(merkle_commit({&layer_mats.back()}));
+      Digest root = trees.back().root();
+      for (Fp x : root.d) W.push_back(x.to_u32());
+      ch.observe(root);
+      cur = fri_fold(cur, ch.sample_ext());
+      if (lfh == 1) break;
+    }
+    for (size_t i = 1; i < cur.size(); i++)
+      if (cur[i] != cur[0]) throw std::runtime_error("the folded vector is not constant");
+    for (Fp x : cur[0].c) W.push_back(x.to_u32());
+    ch.observe(cur[0]);
+    W.push_back(ch.grind(pow_bits).to_u32());
+    W.push_back(num_queries);
+    for (uint32_t q = 0; q < num_queries; q++) {
+      size_t index = ch.sample_bits(log_n);
+      W.push_back((uint32_t)index);
+      for (size_t li = 0; li < trees.size(); li++) {
+        size_t pos = index >> li;
+        const Ef& sib = layer_vals[li][pos ^ 1];
+        for (Fp x : sib.c) W.push_back(x.to_u32());
+        BatchOpening op = merkle_open(trees[li], pos >> 1);
+        W.push_back((uint32_t)op.path.size());
+        for (auto& d : op.path)
+          for (Fp x : d.d) W.push_back(x.to_u32());
+      }
+    }
+    *out = (uint32_t*)malloc(W.size() * 4 + 4);
+    memcpy(*out, W.data(), W.size() * 4);
+    *out_len = W.size();
+    return 0;
+  } catch (std::exception& e) {
+    g_serr = e.what();
+    return -1;
+  }
+}
 }  // extern "C"

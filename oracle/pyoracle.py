@@ -310,3 +310,44 @@ def air_cross_check(top: OracleToplevel, machine_blob, chip: int, nrows=3, seed=
     if rc:
         raise AirCheckError(L.orc_air_last_error().decode())
     return counts[0], counts[1], counts[2]
+
+
+# ---- stage-level counterparts of lsk_perm_trace / lsk_quotient / lsk_fri_prove ----------------------------------
+def chip_perm_width(machine: OracleMachine, chip: int) -> int:
+    return lib().orc_chip_perm_width(ctypes.c_void_p(machine.h), chip)
+
+
+def perm_trace(machine: OracleMachine, chip: int, main, alpha, beta):
+    """sphinx generate_permutation_trace for one chip: -> (h x 4*pw matrix, cumulative sum[4])"""
+    m = _u32(main)
+    pw = chip_perm_width(machine, chip)
+    out = np.zeros((m.shape[0], 4 * pw), dtype=np.uint32)
+    cum = np.zeros(4, dtype=np.uint32)
+    a, b = _u32(alpha), _u32(beta)
+    rc = lib().orc_perm_trace(ctypes.c_void_p(machine.h), chip, _vp(m), ctypes.c_size_t(m.shape[0]), _vp(a), _vp(b), _vp(out), _vp(cum))
+    if rc:
+        raise RuntimeError(lib().orc_stark_last_error().decode())
+    return out, cum
+
+
+def quotient(machine: OracleMachine, chip: int, main, perm, pv, cum, chal_alpha, chal_beta, alpha):
+    """quotient values on g*H_2h in commitment order: (2h x 4)"""
+    m, p = _u32(main), _u32(perm)
+    out = np.zeros((2 * m.shape[0], 4), dtype=np.uint32)
+    args = [_u32(x) for x in (pv if len(pv) else [0], cum, chal_alpha, chal_beta, alpha)]
+    rc = lib().orc_quotient(ctypes.c_void_p(machine.h), chip, _vp(m), _vp(p), ctypes.c_size_t(m.shape[0]), *[_vp(x) for x in args], _vp(out))
+    if rc:
+        raise RuntimeError(lib().orc_stark_last_error().decode())
+    return out
+
+
+def fri_prove(vals, log_n, state, num_queries, pow_bits):
+    v, s = _u32(vals), _u32(state)
+    out = ctypes.POINTER(ctypes.c_uint32)()
+    n = ctypes.c_size_t()
+    rc = lib().orc_fri_prove(_vp(v), log_n, _vp(s), num_queries, pow_bits, ctypes.byref(out), ctypes.byref(n))
+    if rc:
+        raise RuntimeError(lib().orc_stark_last_error().decode())
+    arr = np.ctypeslib.as_array(out, shape=(n.value,)).copy()
+    lib().orc_free(out)
+    return arr

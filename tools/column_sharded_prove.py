@@ -29,7 +29,7 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    from bench import workload_program
+    from bench import Workload
     from lurk_b200 import _native as N
     from lurk_b200.execute import QueryRecord, Shard, ShardingConfig, execute_by_name
     from lurk_b200.machine import new_machine
@@ -45,7 +45,8 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
 
     def setup(workload, n_arg, shard_size=None):
-        top, entry = workload_program(workload)
+        wl = Workload(workload)
+        top, entry = wl.top, wl.entry
         m = new_machine(top, entry, ctx=ctx)
         pk, vk = m.setup()
         q = QueryRecord.new(top)

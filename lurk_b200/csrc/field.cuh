@@ -131,10 +131,7 @@ LSK_HD uint32_t two_adic_generator(unsigned bits) {
   for (unsigned i = bits; i < 27; i++) g = fsqr(g);
   return g;
 }
-LSK_HD uint32_t fmul11(uint32_t a) {
-  uint32_t a2 = fdbl(a), a4 = fdbl(a2), a8 = fdbl(a4);
-  return fadd(fadd(a8, a2), a);
-}
+LSK_HD uint32_t fmul11(uint32_t a) { return mont_reduce((uint64_t)a * 939524073u); }   // 11 in Montgomery form (M11)
 
 // ---- quartic extension ------------------------------------------------------------------------
 struct __align__(16) Ext {
@@ -160,27 +157,63 @@ LSK_HD Ext eadd_base(const Ext& a, uint32_t b) { return Ext{{fadd(a.c[0], b), a.
 LSK_HD Ext esub_base(const Ext& a, uint32_t b) { return Ext{{fsub(a.c[0], b), a.c[1], a.c[2], a.c[3]}}; }
 
 // Schoolbook product with the 64-bit partial sums reduced once per coefficient: each a_i*b_j is
-// < 2^62, so up to four of them (pre-scaled where x^4 = 11 folds back) are accumulated modulo
-// P*2^32 before a single Montgomery reduction.
-LSK_HD uint64_t acc_reduce64(uint64_t x) {  // keep x < P * 2^32 so mont_reduce stays in range
+// < P^2 < 2^62, so the products of one coefficient are accumulated modulo M = P*2^32 (the bound mont_reduce
+// accepts) before a single Montgomery reduction.  acc_reduce64 takes x < 2M: M has a zero low word, so the
+// conditional subtraction only touches the HIGH word -- one VIADDMNMX on the device, where the 64-bit compare /
+// subtract / select the portable form compiles to is six instructions (cuobjdump, sm_100a).
+constexpr uint32_t M11 = 939524073u;  // 11 in Montgomery form: the non-residue W of x^4 = W
+LSK_HD uint64_t acc_reduce64(uint64_t x) {  // x < 2 * P * 2^32  ->  x mod P * 2^32
+#if defined(__CUDA_ARCH__)
+  const uint32_t hi = (uint32_t)(x >> 32);
+  return ((uint64_t)min(hi, hi - P) << 32) | (uint32_t)x;
+#else
   const uint64_t M = (uint64_t)P << 32;
   return x >= M ? x - M : x;
+#endif
 }
+// The part of the product that wraps around x^4 = 11 is reduced to a field element h and re-enters the low
+// coefficient's 64-bit sum as the raw product h * M11 (one more IMAD.WIDE) instead of three doublings and two
+// additions of reduced values: 19 wide products, 7 Montgomery reductions and 6 one-instruction corrections per
+// extension product.
 LSK_HD Ext emul(const Ext& a, const Ext& b) {
-  // high part folded with W = 11: compute t_k = sum_{i+j=k+4} a_i b_j as field elements first
-  uint32_t h0 = mont_reduce(acc_reduce64(acc_reduce64((uint64_t)a.c[1] * b.c[3] + (uint64_t)a.c[2] * b.c[2]) +
-                                         (uint64_t)a.c[3] * b.c[1]));
-  uint32_t h1 = mont_reduce(acc_reduce64((uint64_t)a.c[2] * b.c[3] + (uint64_t)a.c[3] * b.c[2]));
-  uint32_t h2 = fmul(a.c[3], b.c[3]);
-  uint32_t l0 = fmul(a.c[0], b.c[0]);
-  uint32_t l1 = mont_reduce(acc_reduce64((uint64_t)a.c[0] * b.c[1] + (uint64_t)a.c[1] * b.c[0]));
-  uint32_t l2 = mont_reduce(acc_reduce64(acc_reduce64((uint64_t)a.c[0] * b.c[2] + (uint64_t)a.c[1] * b.c[1]) +
-                                         (uint64_t)a.c[2] * b.c[0]));
-  uint32_t l3 = mont_reduce(acc_reduce64(
-      acc_reduce64(acc_reduce64((uint64_t)a.c[0] * b.c[3] + (uint64_t)a.c[1] * b.c[2]) + (uint64_t)a.c[2] * b.c[1]) +
+  const uint32_t h0 = mont_reduce(acc_reduce64(acc_reduce64((uint64_t)a.c[1] * b.c[3] + (uint64_t)a.c[2] * b.c[2]) +
+                                               (uint64_t)a.c[3] * b.c[1]));
+  const uint32_t h1 = mont_reduce((uint64_t)a.c[2] * b.c[3] + (uint64_t)a.c[3] * b.c[2]);   // 2 P^2 < P * 2^32
+  const uint32_t h2 = fmul(a.c[3], b.c[3]);
+  const uint32_t c0 = mont_reduce((uint64_t)a.c[0] * b.c[0] + (uint64_t)h0 * M11);
+  const uint32_t c1 = mont_reduce(acc_reduce64((uint64_t)a.c[0] * b.c[1] + (uint64_t)a.c[1] * b.c[0] + (uint64_t)h1 * M11));
+  const uint32_t c2 = mont_reduce(acc_reduce64(
+      acc_reduce64((uint64_t)a.c[0] * b.c[2] + (uint64_t)a.c[1] * b.c[1] + (uint64_t)a.c[2] * b.c[0]) + (uint64_t)h2 * M11));
+  const uint32_t c3 = mont_reduce(acc_reduce64(
+      acc_reduce64((uint64_t)a.c[0] * b.c[3] + (uint64_t)a.c[1] * b.c[2] + (uint64_t)a.c[2] * b.c[1]) +
       (uint64_t)a.c[3] * b.c[0]));
-  return Ext{{fadd(l0, fmul11(h0)), fadd(l1, fmul11(h1)), fadd(l2, fmul11(h2)), l3}};
+  return Ext{{c0, c1, c2, c3}};
 }
+// sum_k a_k * b_k of extension elements a_k by base elements b_k (random linear combinations: LogUp messages, folded
+// constraints, openings) as four 64-bit sums of raw products.  add() leaves a sum below M + P^2, add_reduce() takes
+// such a sum back below M (M + 2 P^2 < 2M), so the two alternate; value() reduces once.  Same field elements as
+// eadd(acc, emul_base(a, b)) term by term, at 4 IMAD.WIDE + 2 corrections per term instead of 4 Montgomery products
+// + 4 modular additions (32 instructions).
+struct ExtAcc {
+  uint64_t s[4];
+  LSK_HD void add(const Ext& a, uint32_t b) {          // precondition: every s < M
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) s[k] += (uint64_t)a.c[k] * b;
+  }
+  LSK_HD void add_reduce(const Ext& a, uint32_t b) {   // precondition: every s < M + P^2
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; k++) s[k] = acc_reduce64(s[k] + (uint64_t)a.c[k] * b);
+  }
+  LSK_HD Ext value() const {
+    return Ext{{mont_reduce(acc_reduce64(s[0])), mont_reduce(acc_reduce64(s[1])), mont_reduce(acc_reduce64(s[2])),
+                mont_reduce(acc_reduce64(s[3]))}};
+  }
+};
+LSK_HD ExtAcc ext_acc_zero() { return ExtAcc{{0, 0, 0, 0}}; }
 LSK_HD Ext esqr(const Ext& a) { return emul(a, a); }
 
 // 1/a via the tower F[y]/(y^2-11) -> F[x]/(x^2-y): a = A + xB, 1/a = (A - xB)/(A^2 - yB^2).

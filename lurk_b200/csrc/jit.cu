@@ -236,7 +236,7 @@ void affine_source(std::string& o, const AffineH& a) {
 }
 std::string interactions_source(const ChipH& c) {
   std::string o;
-  char buf[160];
+  char buf[256];
   const size_t nint = c.n_interactions();
   snprintf(buf, sizeof buf, "#define LSK_JIT_NINT %zu\n", nint);
   o += buf;
@@ -246,21 +246,25 @@ std::string interactions_source(const ChipH& c) {
     const bool recv = k >= c.sends.size();
     const InteractionH& it = recv ? c.receives[k - c.sends.size()] : c.sends[k];
     snprintf(buf, sizeof buf, "__device__ __noinline__ LskInt lsk_int_%zu(const Cells c, const Ext alpha, const Ext* __restrict__ bp) "
-                              "{\n  Ext r;\n  const uint32_t m = ", k);
+                              "{\n  ExtAcc s = ext_acc_zero();\n  const uint32_t m = ", k);
     o += buf;
     std::string m;
     affine_source(m, it.mult);
     o += recv ? "fneg(" + m + ")" : m;
-    snprintf(buf, sizeof buf, ";\n  r = eadd_base(alpha, %uu);\n", to_mont(it.kind % P));
-    o += buf;
+    o += ";\n";
+    // sum_j beta^(j+1) * value_j as four 64-bit sums of raw products (ExtAcc, field.cuh): add / add_reduce alternate
+    bool pending = false;
     for (size_t j = 0; j < it.values.size(); j++) {
       std::string val;
       affine_source(val, it.values[j]);
       if (val == "0u") continue;   // adds beta^(j+1) * 0
-      snprintf(buf, sizeof buf, "  r = eadd(r, emul_base(ldg_ext(bp + %zu), ", j);
+      snprintf(buf, sizeof buf, "  s.%s(ldg_ext(bp + %zu), ", pending ? "add_reduce" : "add", j);
+      pending = !pending;
       o += buf;
-      o += val + "));\n";
+      o += val + ");\n";
     }
+    snprintf(buf, sizeof buf, "  const Ext r = eadd(eadd_base(alpha, %uu), s.value());\n", to_mont(it.kind % P));
+    o += buf;
     o += "  return LskInt{r, m};\n}\n";
   };
   o += "struct LskInt { Ext r; uint32_t m; };\n";

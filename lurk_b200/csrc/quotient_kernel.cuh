@@ -67,11 +67,19 @@ LSK_D void eval_interaction(const uint32_t* __restrict__& s, const Cells& c, con
   s += 3;
   m = eval_affine(s, c);
   if (sign) m = fneg(m);
-  rlc = eadd_base(alpha, kind);
+  ExtAcc sum = ext_acc_zero();
   for (uint32_t v = 0; v < nv; v++) {
     uint32_t val = eval_affine(s, c);
-    rlc = eadd(rlc, emul_base(beta_pows[v], val));
+    sum.add_reduce(beta_pows[v], val);
   }
+  rlc = eadd(eadd_base(alpha, kind), sum.value());
+}
+// a * x + b * y for extension a, b and base x, y (the numerator of a LogUp batch of two)
+LSK_D Ext emul_base2(const Ext& a, uint32_t x, const Ext& b, uint32_t y) {
+  ExtAcc s = ext_acc_zero();
+  s.add(a, x);
+  s.add_reduce(b, y);
+  return s.value();
 }
 LSK_D Ext ldg_ext(const Ext* __restrict__ p) {   // 16-byte aligned (arrays of Ext in device buffers)
   const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
@@ -125,7 +133,7 @@ LSK_D void quotient_row_finish(const QuotientArgs& a, const QuotientConsts& qc, 
       uint32_t m1;
       eval_interaction(s, cells, a.chal_alpha, a.beta_pows, r1, m1);
       lhs = emul(emul(pl, r0), r1);
-      rhs = eadd(emul_base(r1, m0), emul_base(r0, m1));
+      rhs = emul_base2(r1, m0, r0, m1);
     } else {
       lhs = emul(pl, r0);
       rhs = ext_from_base(m0);
@@ -201,13 +209,8 @@ LSK_D void quotient_row_tail(const QuotientArgs& a, const QuotientConsts& qc, co
 #include "lsk_interactions.cuh"
 // the batch bodies are real calls: inlined into every one of a chip's 10-30 batches they multiply NVVM's work (the
 // 41 chips of the Lurk machine took 19 minutes to compile that way, 40 s like this) for no measurable gain
-__device__ __noinline__ Ext lsk_perm_pair(Ext r0, uint32_t m0, Ext r1, uint32_t m1) {
-  const Ext num = eadd(emul_base(r1, m0), emul_base(r0, m1));
-  return (m0 | m1) ? emul(num, einv(emul(r0, r1))) : ext_zero();
-}
-__device__ __noinline__ Ext lsk_perm_single(Ext r0, uint32_t m0) { return m0 ? emul_base(einv(r0), m0) : ext_zero(); }
 __device__ __noinline__ Ext lsk_quot_pair(Ext pl, Ext r0, uint32_t m0, Ext r1, uint32_t m1) {
-  return esub(emul(emul(pl, r0), r1), eadd(emul_base(r1, m0), emul_base(r0, m1)));
+  return esub(emul(emul(pl, r0), r1), emul_base2(r1, m0, r0, m1));
 }
 __device__ __noinline__ Ext lsk_fold(Ext ac, Ext ap, Ext x) { return eadd(ac, emul(ap, x)); }
 struct LskQuotientBatches {   // quotient_row_finish's loop body
@@ -229,23 +232,60 @@ struct LskQuotientBatches {   // quotient_row_finish's loop body
     fold(b, pl, esub(emul(pl, r0), ext_from_base(m0)));
   }
 };
-struct LskPermBatches {       // perm_rows_kernel's loop body
+// perm_rows_kernel's loop body, with the inversions of up to four consecutive batches shared (Montgomery's trick: one
+// einv -- ~85 base products, 62 of them a dependent chain -- and 3 (n - 1) extension products instead of n einv).  The
+// values are the same field elements; only a denominator that is exactly zero (probability 2^-124 per batch) would
+// behave differently from the one-inversion-per-batch form, which maps 1/0 to 0.
+constexpr uint32_t LSK_PERM_GROUP = 4;
+__device__ __noinline__ Ext lsk_perm_flush(const PermRowsArgs& a, size_t r, uint32_t b0, uint32_t n, const Ext* __restrict__ den,
+                                           const Ext* __restrict__ num) {
+  Ext pre[LSK_PERM_GROUP];
+  pre[0] = den[0];
+  for (uint32_t i = 1; i < n; i++) pre[i] = emul(pre[i - 1], den[i]);
+  Ext inv = einv(pre[n - 1]), rowsum = ext_zero();
+  for (uint32_t i = n; i-- > 0;) {
+    const Ext v = emul(num[i], i ? emul(inv, pre[i - 1]) : inv);
+    if (i) inv = emul(inv, den[i]);
+#pragma unroll
+    for (int k = 0; k < 4; k++) a.perm[(size_t)(4 * (b0 + i) + k) * a.perm_stride + r] = v.c[k];
+    rowsum = eadd(rowsum, v);
+  }
+  return rowsum;
+}
+__device__ __noinline__ void lsk_perm_zero(const PermRowsArgs& a, size_t r, uint32_t b0, uint32_t n) {
+  for (uint32_t i = 0; i < 4 * n; i++) a.perm[(size_t)(4 * b0 + i) * a.perm_stride + r] = 0u;
+}
+struct LskPermBatches {
   const PermRowsArgs& a;
   size_t r;
   Ext rowsum;
-  LSK_D void put(uint32_t b, const Ext& v) {
-#pragma unroll
-    for (int k = 0; k < 4; k++) a.perm[(size_t)(4 * b + k) * a.perm_stride + r] = v.c[k];
-    rowsum = eadd(rowsum, v);
+  Ext den[LSK_PERM_GROUP], num[LSK_PERM_GROUP];
+  uint32_t any;   // OR of the multiplicities of the open group: a group of padding rows costs no inversion at all
+  LSK_D void close(uint32_t b) {
+    const uint32_t slot = b % LSK_PERM_GROUP;
+    if (slot + 1 != LSK_PERM_GROUP && b + 1 != (LSK_JIT_NINT + 1) / 2) return;
+    if (any) rowsum = eadd(rowsum, lsk_perm_flush(a, r, b - slot, slot + 1, den, num));
+    else lsk_perm_zero(a, r, b - slot, slot + 1);
+    any = 0;
   }
-  LSK_D void pair(uint32_t b, const Ext& r0, uint32_t m0, const Ext& r1, uint32_t m1) { put(b, lsk_perm_pair(r0, m0, r1, m1)); }
-  LSK_D void single(uint32_t b, const Ext& r0, uint32_t m0) { put(b, lsk_perm_single(r0, m0)); }
+  LSK_D void pair(uint32_t b, const Ext& r0, uint32_t m0, const Ext& r1, uint32_t m1) {
+    den[b % LSK_PERM_GROUP] = emul(r0, r1);
+    num[b % LSK_PERM_GROUP] = emul_base2(r1, m0, r0, m1);
+    any |= m0 | m1;
+    close(b);
+  }
+  LSK_D void single(uint32_t b, const Ext& r0, uint32_t m0) {
+    den[b % LSK_PERM_GROUP] = r0;
+    num[b % LSK_PERM_GROUP] = ext_from_base(m0);
+    any |= m0;
+    close(b);
+  }
 };
 extern "C" __global__ void __launch_bounds__(256) lsk_perm_rows_jit(PermRowsArgs a) {
   const size_t r = a.row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
   if (r >= a.row_end) return;
   const Cells cells{a.main, a.mstride, a.prep, a.pstride, r};
-  LskPermBatches v{a, r, ext_zero()};
+  LskPermBatches v{a, r, ext_zero(), {}, {}, 0u};
   lsk_interactions(cells, a.alpha, a.beta_pows, v);
   a.rowsum_out[a.scatter ? bitrev32((uint32_t)r, a.logn) : r] = v.rowsum;
 }

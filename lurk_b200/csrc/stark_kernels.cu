@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) perm_rows_kernel(const uint32_t* __restri
       Ext r1;
       uint32_t m1;
       eval_interaction(s, cells, alpha, beta_pows, r1, m1);
-      Ext num = eadd(emul_base(r1, m0), emul_base(r0, m1));
+      Ext num = emul_base2(r1, m0, r0, m1);
       v = (m0 | m1) ? emul(num, einv(emul(r0, r1))) : ext_zero();
     } else {
       v = m0 ? emul_base(einv(r0), m0) : ext_zero();
@@ -223,7 +223,7 @@ struct OpenGroup { uint32_t mat, c0; };
 // products kept below P * 2^32 (one conditional subtraction per term, one Montgomery reduction at the end: a third
 // of the multiply-pipe work of a Montgomery product per term); rows are predicated, not broken out of, so the
 // loop unrolls and the loads of two rows are in flight together.
-__global__ void __launch_bounds__(256) open_partial_batch_kernel(const OpenMat* __restrict__ mats,
+__global__ void __launch_bounds__(256, 2) open_partial_batch_kernel(const OpenMat* __restrict__ mats,
                                                                   const OpenGroup* __restrict__ groups, size_t n,
                                                                   const Ext* __restrict__ wts0, const Ext* __restrict__ wts1,
                                                                   Ext* __restrict__ partial, uint32_t nchunks) {

@@ -8,8 +8,16 @@ zstore.rs:112-133); compound data is hashed with the Poseidon2 hashers (zstore.r
 where flatten() = [tag, 0 x 7] ++ digest.  The store remembers every preimage it hashed (`hashes3/4/5`): the
 Lair funcs `ingress` / `open_comm` recover data from digests through `preimg(hash4, ..)`, so the preimages are
 injected into the QueryRecord as inverse queries before execution (`QueryRecord::inject_inv_queries`,
-src/lair/execute.rs; `inject` below).  Hashing runs on the host, one preimage after another, exactly where the
-reference does it (`lsk_poseidon2_hash_host`); the GPU batch hash (`lsk_poseidon2_hash`) is for bulk data.
+src/lair/execute.rs; `inject` below).  Interning one datum hashes on the host, one preimage after another, exactly where
+the reference does it (`lsk_poseidon2_hash_host`).
+
+Batch interning: `defer_*` builds the same data as a DAG of pending nodes without hashing anything,
+and `resolve` hashes it level by level -- level k holds the nodes whose children are all known after level k - 1, i.e.
+one batch of independent preimages per hasher width.  A batch of at least `gpu_min_batch` preimages goes through the
+GPU kernel (`lsk_poseidon2_hash`, one launch per level and width), smaller ones through the host hasher: a list is a
+chain of dependent conses (every level one node wide -- the GPU's ~25 us per dependent hash loses to 0.7 us on a CPU
+core), a wide structure (many sublists, a tree, a batch of independent expressions) has levels thousands wide.  The
+digests and the preimage tables are identical to one-by-one interning either way (tests/test_zstore.py).
 """
 from __future__ import annotations
 
@@ -20,6 +28,7 @@ from typing import Dict, Iterable, List, Sequence, Tuple
 import numpy as np
 
 from . import _native as N
+from typing import Optional, Union
 
 P = 2013265921
 # src/core/tag.rs:23-39
@@ -48,11 +57,26 @@ def _digest_from_field(f: int) -> Tuple[int, ...]:
     return (f % P,) + (0,) * 7
 
 
+class Deferred:
+    """A compound datum whose digest is not known yet: `kind` 11 (tuple11), 110 (tuple110) or 3 (hide); children are
+    ZPtrs or other Deferred nodes.  `ZStore.resolve` fills in `zptr`."""
+    __slots__ = ("tag", "kind", "children", "secret", "level", "zptr")
+
+    def __init__(self, tag: int, kind: int, children, secret=None):
+        self.tag, self.kind, self.children, self.secret = tag, kind, tuple(children), secret
+        self.level = 1 + max((c.level for c in self.children if isinstance(c, Deferred)), default=0)
+        self.zptr: Optional[ZPtr] = None
+
+
+Node = Union[ZPtr, Deferred]
+
+
 class ZStore:
     def __init__(self):
         self.hashes: Dict[int, Dict[Tuple[int, ...], Tuple[int, ...]]] = {24: {}, 32: {}, 40: {}}
         self._str: Dict[str, ZPtr] = {}
         self._sym: Dict[Tuple[str, ...], ZPtr] = {}
+        self.gpu_batches = 0         # launches of the GPU batch hasher issued by hash_many / resolve
 
     # ---- hashing (zstore.rs:305-333) ---------------------------------------------------------------------------
     def hash(self, preimg: Sequence[int]) -> Tuple[int, ...]:
@@ -63,6 +87,95 @@ class ZStore:
             N.check(N.lib().lsk_poseidon2_hash_host(len(pre), N.vp(N.u32(pre)), ctypes.c_size_t(1), N.vp(out)))
             table[pre] = tuple(int(x) for x in out)
         return table[pre]
+
+    def hash_many(self, width: int, preimgs: np.ndarray, ctx=None, gpu_min_batch: int = 256) -> np.ndarray:
+        """Digests of a batch of independent preimages, (n, width) -> (n, 8); remembered like `hash` remembers them.
+        n >= gpu_min_batch with a context: one GPU launch (lsk_poseidon2_hash); otherwise the host hasher."""
+        pre = np.ascontiguousarray(preimgs, dtype=np.uint32).reshape(-1, width)
+        out = np.empty((len(pre), 8), dtype=np.uint32)
+        if len(pre) == 0:
+            return out
+        if ctx is not None and len(pre) >= gpu_min_batch:
+            N.check(N.lib().lsk_poseidon2_hash(ctx.h, width, N.vp(pre), ctypes.c_size_t(len(pre)), N.vp(out)))
+            self.gpu_batches += 1
+        else:
+            N.check(N.lib().lsk_poseidon2_hash_host(width, N.vp(pre), ctypes.c_size_t(len(pre)), N.vp(out)))
+        table = self.hashes[width]
+        for row, dig in zip(pre.tolist(), out.tolist()):
+            table[tuple(row)] = tuple(dig)
+        return out
+
+    # ---- batch interning (SURVEY.md 8 f.4; zstore.rs:305-349 level by level) ------------------------------------
+    def defer_tuple11(self, tag: int, a: Node, b: Node) -> Deferred: return Deferred(tag, 11, (a, b))
+    def defer_tuple110(self, tag: int, a: Node, b: Node, c: Node) -> Deferred: return Deferred(tag, 110, (a, b, c))
+    def defer_cons(self, a: Node, b: Node) -> Deferred: return Deferred(TAG["Cons"], 11, (a, b))
+    def defer_hide(self, secret: Sequence[int], payload: Node) -> Deferred:
+        assert len(secret) == 8
+        return Deferred(TAG["Comm"], 3, (payload,), tuple(int(x) for x in secret))
+
+    def defer_list(self, xs: Iterable[Node]) -> Node:
+        z: Node = self.nil()
+        for x in reversed(list(xs)):
+            z = self.defer_cons(x, z)
+        return z
+
+    def defer_data(self, obj) -> Node:
+        """Nested Python lists / ints / strs / ZPtrs as Lurk data: a list becomes a proper list, an int a u64, a str a
+        string (interned at once: a string is a chain)."""
+        if isinstance(obj, (ZPtr, Deferred)):
+            return obj
+        if isinstance(obj, int):
+            return self.u64(obj)
+        if isinstance(obj, str):
+            return self.string(obj)
+        return self.defer_list([self.defer_data(x) for x in obj])
+
+    def resolve(self, roots: Sequence[Node], ctx=None, gpu_min_batch: int = 256) -> List[ZPtr]:
+        """Hash every pending node under `roots`, one batch per (level, width); -> the roots as ZPtrs."""
+        pending: Dict[int, Deferred] = {}
+        stack = [r for r in roots if isinstance(r, Deferred)]
+        while stack:
+            d = stack.pop()
+            if d.zptr is not None or id(d) in pending:
+                continue
+            pending[id(d)] = d
+            stack.extend(c for c in d.children if isinstance(c, Deferred))
+        by_level: Dict[int, List[Deferred]] = {}
+        for d in pending.values():
+            by_level.setdefault(d.level, []).append(d)
+        flat = lambda c: (c if isinstance(c, ZPtr) else c.zptr)
+        for level in sorted(by_level):
+            groups: Dict[int, List[Deferred]] = {24: [], 32: [], 40: []}
+            for d in by_level[level]:
+                groups[{3: 24, 11: 32, 110: 40}[d.kind]].append(d)
+            for width, nodes in groups.items():
+                if not nodes:
+                    continue
+                rows = []
+                for d in nodes:
+                    ch = [flat(c) for c in d.children]
+                    if d.kind == 3:
+                        rows.append(list(d.secret) + ch[0].flatten())
+                    elif d.kind == 11:
+                        rows.append(ch[0].flatten() + ch[1].flatten())
+                    else:
+                        rows.append(ch[0].flatten() + ch[1].flatten() + list(ch[2].digest))
+                pre = np.asarray(rows, dtype=np.uint32)
+                table = self.hashes[width]
+                # what the store already knows is not hashed again (the reference's hashes3/4/5 caches); duplicates
+                # inside the batch are hashed once
+                uniq: Dict[Tuple[int, ...], int] = {}
+                todo = []
+                for row in rows:
+                    t = tuple(row)
+                    if t not in table and t not in uniq:
+                        uniq[t] = len(todo)
+                        todo.append(row)
+                if todo:
+                    self.hash_many(width, np.asarray(todo, dtype=np.uint32), ctx, gpu_min_batch)
+                for d, row in zip(nodes, rows):
+                    d.zptr = ZPtr(d.tag, table[tuple(row)])
+        return [flat(r) for r in roots]
 
     # ---- atoms ----------------------------------------------------------------------------------------------------
     @staticmethod

@@ -100,3 +100,58 @@ def test_extend_env_with_mutuals_builds_the_letrec_environment(oracle):
         z.inject(q, top)
         out = [int(v) for v in execute_by_name(top, "mutuals_demo", [bad.tag] + [0] * 7 + list(bad.digest), q)]
         assert out == [TAG["Err"], err] + [0] * 7
+
+
+# ---- batch interning (zstore.rs:305-349 hashed level by level) -------------------------------------
+def _intern_directly(z, obj):
+    if isinstance(obj, int):
+        return z.u64(obj)
+    if isinstance(obj, str):
+        return z.string(obj)
+    return z.list([_intern_directly(z, x) for x in obj])
+
+
+def _wide_data(n):
+    # n sublists: every level of the cons DAG is ~n nodes wide; shared tails and repeated strings exercise the caches
+    return [[i, i % 7, [3 * i, "ab"], "shared"] for i in range(n)]
+
+
+def test_deferred_interning_equals_one_by_one_interning():
+    a, b = ZStore(), ZStore()
+    want = _intern_directly(a, _wide_data(40))
+    got = b.resolve([b.defer_data(_wide_data(40))])[0]
+    assert got == want
+    assert a.hashes == b.hashes                     # the same preimages are remembered, each once
+    assert b.gpu_batches == 0                       # no context given: host hasher only
+    # functions / environments (hash5) and commitments (hash3), resolved together with their children
+    env = b.defer_tuple110(TAG["Env"], b.lurk_sym("x"), b.defer_list([b.u64(1), b.u64(2)]), b.null(TAG["Env"]))
+    comm = b.defer_hide([0] * 8, env)
+    zenv, zcomm = b.resolve([env, comm])
+    lst = a.list([a.u64(1), a.u64(2)])
+    assert zenv == a.tuple110(TAG["Env"], a.lurk_sym("x"), lst, a.null(TAG["Env"]))
+    assert zcomm == a.commit(zenv)
+    assert b.resolve([]) == [] and b.resolve([a.u64(5)]) == [a.u64(5)]
+
+
+def test_deferred_levels_are_the_dependency_depth():
+    z = ZStore()
+    chain = z.defer_list([z.u64(i) for i in range(10)])
+    assert chain.level == 10                        # a list is a chain: ten levels, one node each
+    wide = z.defer_list([z.defer_list([z.u64(i)]) for i in range(10)])
+    assert wide.children[0].level == 1 and wide.level == 11   # the ten sublists are one level; the spine is a chain
+
+
+@pytest.mark.gpu
+def test_deferred_interning_on_the_gpu_equals_the_host():
+    from lurk_b200 import _native as N
+    ctx = N.default_context()
+    a, b = ZStore(), ZStore()
+    want = _intern_directly(a, _wide_data(600))
+    got = b.resolve([b.defer_data(_wide_data(600))], ctx=ctx, gpu_min_batch=64)[0]
+    assert got == want and a.hashes == b.hashes
+    assert b.gpu_batches >= 3                       # the wide levels went through lsk_poseidon2_hash
+    # KAT-1 (zstore.rs:1008-1019) through the batch path: commitments of 300 numbers, 123 among them
+    c = ZStore()
+    comms = c.resolve([c.defer_hide([0] * 8, c.num(i)) for i in range(300)], ctx=ctx, gpu_min_batch=64)
+    assert c.gpu_batches == 1
+    assert comms[123].to_biguint() == 0xaa8db8504fa55b480f3da7a75f3480174f28d683f4c3ac451b7cee488d2fe

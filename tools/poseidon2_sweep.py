@@ -78,7 +78,11 @@ def main():
             n = n_total // world                      # this rank's slice
             if n == 0:
                 continue
-            x = splitmix_inputs(torch, n, w, dev, first_row=rank * n)
+            # generated in slabs of 2^20 rows: the int64 temporaries of a 2^28-row slab would not fit beside the inputs
+            x = torch.empty((n, w), dtype=torch.int32, device=dev)
+            for r0 in range(0, n, 1 << 20):
+                r1 = min(n, r0 + (1 << 20))
+                x[r0:r1] = splitmix_inputs(torch, r1 - r0, w, dev, first_row=rank * n + r0)
             out = torch.empty((n, 8), dtype=torch.int32, device=dev)
             torch.cuda.synchronize()
             with torch.cuda.stream(stream):

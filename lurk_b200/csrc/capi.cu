@@ -38,6 +38,9 @@ int lsk_ctx_create(int device, lsk_ctx** out) {
   auto* ctx = new lsk_ctx;
   ctx->device = device;
   LSK_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  LSK_CUDA(cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+  LSK_CUDA(cudaEventCreateWithFlags(&ctx->side_fork, cudaEventDisableTiming));
+  LSK_CUDA(cudaEventCreateWithFlags(&ctx->side_join, cudaEventDisableTiming));
   cudaDeviceProp prop;
   LSK_CUDA(cudaGetDeviceProperties(&prop, device));
   ctx->sm_count = prop.multiProcessorCount;
@@ -58,6 +61,10 @@ void lsk_ctx_destroy(lsk_ctx* ctx) {
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   ctx->pool.trim();
   cudaStreamDestroy(ctx->stream);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
+  if (ctx->side_join) cudaEventDestroy(ctx->side_join);
   ctx->stream = nullptr;
   // objects that still own device buffers (a machine freed after its context) release into this pool later:
   // keep the (small) context object alive for them rather than leave them a dangling pointer

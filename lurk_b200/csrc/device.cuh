@@ -110,6 +110,10 @@ struct lsk_ctx {
   int device = 0;
   lsk::Comm* comm = nullptr;    // device group of a column-sharded prove (comm.cuh); null: this GPU works alone
   cudaStream_t stream = nullptr;
+  cudaStream_t side = nullptr;      // second stream: the single-CTA launches of a shard's tiny chips run beside the big ones
+  cudaEvent_t side_fork = nullptr, side_join = nullptr;
+  void* pinned = nullptr;           // page-locked host scratch (pinned_scratch): results the host consumes while kernels run
+  size_t pinned_bytes = 0;
   int sm_count = 148;
   lsk::MemPool pool;
   void* ntt_tables = nullptr;   // lsk::NttTables (ntt.cu): twiddle / coset-scale tables, built lazily per size
@@ -117,6 +121,49 @@ struct lsk_ctx {
 };
 
 namespace lsk {
+// page-locked host scratch of at least `bytes`, owned by the context (valid until the next call asks for more)
+inline void* pinned_scratch(lsk_ctx* ctx, size_t bytes) {
+  if (bytes > ctx->pinned_bytes) {
+    if (ctx->pinned) {
+      cudaStreamSynchronize(ctx->stream);
+      cudaFreeHost(ctx->pinned);
+      ctx->pinned = nullptr;
+      ctx->pinned_bytes = 0;
+    }
+    size_t want = bytes + bytes / 2;
+    if (cudaHostAlloc(&ctx->pinned, want, cudaHostAllocDefault) != cudaSuccess) lsk::fail(LSK_ERR_CUDA, "cudaHostAlloc(%zu) failed", want);
+    ctx->pinned_bytes = want;
+  }
+  return ctx->pinned;
+}
+// Work queued between fork() and join() on ctx->side runs concurrently with what the main stream does in between.
+// While `active`, ctx->stream IS the side stream (every helper launches on ctx->stream), so the caller brackets exactly
+// the calls that should go there.  The memory pool is ordered by the main stream only: nothing a side-stream kernel
+// touches may be released before join().
+struct SideStream {
+  lsk_ctx* ctx;
+  cudaStream_t main;
+  bool forked = false;
+  explicit SideStream(lsk_ctx* c) : ctx(c), main(c->stream) {}
+  void enter() {   // subsequent launches go to the side stream (after everything queued on the main stream so far)
+    if (!forked) {
+      cudaEventRecord(ctx->side_fork, main);
+      cudaStreamWaitEvent(ctx->side, ctx->side_fork, 0);
+      forked = true;
+    }
+    ctx->stream = ctx->side;
+  }
+  void leave() { ctx->stream = main; }
+  void join() {    // the main stream waits for the side stream's work
+    ctx->stream = main;
+    if (forked) {
+      cudaEventRecord(ctx->side_join, ctx->side);
+      cudaStreamWaitEvent(main, ctx->side_join, 0);
+      forked = false;
+    }
+  }
+  ~SideStream() { join(); }
+};
 struct ProfScope {
   lsk_ctx* ctx;
   int tag;
@@ -126,7 +173,9 @@ struct ProfScope {
     p.launches[t] += nlaunch;
     p.bytes[t] += algorithmic_bytes;
     p.work[t] += work;
-    if (p.timing) {
+    // launches on the side stream overlap the main stream's: they are counted, not timed (their events would span
+    // whatever the main stream ran meanwhile and the per-kernel times would no longer add up to the step)
+    if (p.timing && ctx->stream != ctx->side) {
       a = p.get();
       b = p.get();
       cudaEventRecord(a, ctx->stream);

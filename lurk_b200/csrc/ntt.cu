@@ -6,9 +6,15 @@
 // permutation pass.  For N <= 2^12 one CTA does the whole column in shared memory.  Larger N is
 // split Bailey-style at bit 12, N = 2^12 * 2^t:
 //   K1  DIT stages 1..12 on contiguous 4096-blocks                      (4R + 4W bytes / element)
-//   K2  per group of 2^c consecutive low indices: inter-pass twiddle, DIT over the 2^t blocks ->
-//       coefficients (shared memory), then for both cosets: scale, DIF over the blocks,
-//       inter-pass twiddle, store                                        (4R + 8W)
+//   K2  per group of 2^c consecutive low indices: DIT stages 13..logn across the 2^t blocks ->
+//       coefficients (shared memory), then for both cosets: scale, DIF stages logn..13 across the
+//       blocks, store                                                    (4R + 8W)
+//       These are the ordinary stages of the size-N transform (stage s pairs elements 2^(s-1) apart with
+//       w_{2^s}^k, k = index mod 2^(s-1)), so no separate inter-pass (Bailey) twiddle exists: their twiddles
+//       depend on the low index as well as on the block and come from one level-packed table of N entries
+//       (w_{2^s}^k at 2^(s-1) + k, shared by every size up to N, read through the L2).  Round 1 split the
+//       transform Bailey-style and paid two more table products per element at every global load and store
+//       of K2 (22 Shoup products per element for N = 2^20; now 16).
 //   K3  DIF stages 12..1 on contiguous 4096-blocks of both cosets        (8R + 8W)
 // i.e. 36 B of HBM traffic per input element against the 12 B algorithmic minimum (4 read, 8
 // written).  Butterflies run radix-16 in REGISTERS: a thread owns the 16 elements that differ in four
@@ -35,13 +41,13 @@ constexpr unsigned BLOCK_ELEMS = 1u << LOG_BLOCK;
 // every table entry is a Shoup pair {c, floor(c * 2^32 / p)} of a plain residue c
 struct NttTables {
   DevBuf<uint2> tw_fwd, tw_inv;
-  struct Big {  // per logn > 12
-    DevBuf<uint2> lo_f, hi_f, lo_i, hi_i;  // W_N^(+-x), x < 4096; W_N^(+-4096 y), y < N / 4096
-  };
+  // level-packed twiddles of the stages above 12, w_{2^s}^(+-k) at 2^(s-1) + k for 13 <= s <= big_log (entries below
+  // 2^12 unused): a prefix of the table of any larger size, so one table serves every logn <= big_log
+  DevBuf<uint2> big_f, big_i;
+  unsigned big_log = 0;
   struct Scale {  // per (logn, kind): a[j][lo] = s_j^lo / N (lo < min(N, 4096)); b[j][k2] = s_j^(4096 k2)
     DevBuf<uint2> a, b;
   };
-  std::map<unsigned, std::unique_ptr<Big>> big;
   std::map<std::pair<unsigned, int>, std::unique_ptr<Scale>> scale;
 };
 
@@ -80,21 +86,30 @@ void ntt_ctx_destroy(lsk_ctx* ctx) {
   ctx->ntt_tables = nullptr;
 }
 
-static NttTables::Big* big_tables(lsk_ctx* ctx, unsigned logn) {
+// T[idx] for idx in [2^12, 2^logn): level s = floor(log2 idx) + 1, k = idx - 2^(s-1), entry = Shoup pair of w_{2^s}^(+-k)
+__global__ void big_twiddle_fill_kernel(uint2* __restrict__ t, unsigned logn, bool inverse) {
+  const size_t idx = ((size_t)1 << LOG_BLOCK) + (size_t)blockIdx.x * 256 + threadIdx.x;
+  if (idx >> logn) return;
+  const unsigned s = 64 - __clzll((unsigned long long)idx);
+  const size_t k = idx - ((size_t)1 << (s - 1));
+  uint32_t w = two_adic_generator(s);
+  if (inverse) w = finv(w);
+  const uint32_t c = from_mont(fpow(w, k));
+  t[idx] = make_uint2(c, (uint32_t)(((uint64_t)c << 32) / P));
+}
+static void big_tables(lsk_ctx* ctx, unsigned logn) {
   NttTables* t = tables(ctx);
-  auto it = t->big.find(logn);
-  if (it != t->big.end()) return it->second.get();
-  auto b = std::make_unique<NttTables::Big>();
-  uint32_t w = two_adic_generator(logn), wi = finv(w);
-  size_t nhi = (size_t)1 << (logn - LOG_BLOCK);
-  auto lo_f = powers(w, BLOCK_ELEMS), lo_i = powers(wi, BLOCK_ELEMS);
-  auto hi_f = powers(fpow(w, BLOCK_ELEMS), nhi), hi_i = powers(fpow(wi, BLOCK_ELEMS), nhi);
-  b->lo_f.alloc(ctx, BLOCK_ELEMS); b->lo_f.upload(lo_f.data(), BLOCK_ELEMS);
-  b->lo_i.alloc(ctx, BLOCK_ELEMS); b->lo_i.upload(lo_i.data(), BLOCK_ELEMS);
-  b->hi_f.alloc(ctx, nhi); b->hi_f.upload(hi_f.data(), nhi);
-  b->hi_i.alloc(ctx, nhi); b->hi_i.upload(hi_i.data(), nhi);
-  LSK_CUDA(cudaStreamSynchronize(ctx->stream));  // the host vectors die here
-  return (t->big[logn] = std::move(b)).get();
+  if (logn <= t->big_log) return;
+  // buffers of the old (smaller) table go back to the pool; the pool is stream-ordered, so kernels already queued keep
+  // reading valid memory until they have run
+  DevBuf<uint2> f(ctx, (size_t)1 << logn), inv(ctx, (size_t)1 << logn);
+  const size_t n = ((size_t)1 << logn) - BLOCK_ELEMS;
+  big_twiddle_fill_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(f.p, logn, false);
+  big_twiddle_fill_kernel<<<div_up(n, 256), 256, 0, ctx->stream>>>(inv.p, logn, true);
+  LSK_CUDA(cudaGetLastError());
+  t->big_f = std::move(f);
+  t->big_i = std::move(inv);
+  t->big_log = logn;
 }
 
 static NttTables::Scale* scale_tables(lsk_ctx* ctx, unsigned logn, LdeShift kind) {
@@ -154,6 +169,41 @@ LSK_D void dif_local(uint32_t (&x)[1 << R], unsigned s0, unsigned low, const uin
       uint32_t a = x[j0], c = x[j1];
       x[j0] = fadd(a, c);
       x[j1] = shoup(fsub(a, c), __ldg(tw + H + low + (kl << s0)));
+    }
+  }
+}
+
+// The same register passes for the stages ABOVE 12 (K2): x[jj] is the element of block q = (high << (s0 + R)) | (jj << s0)
+// | low at low index glo; stage 12 + s0 + u pairs blocks differing in bit s0 + u - 1 with the twiddle w_{2^s}^k,
+// k = ((q mod 2^(s0+u-1)) << 12) | glo -- the level-packed index of the small passes shifted left by 12, plus glo.
+template <int R>
+LSK_D void dit_local_big(uint32_t (&x)[1 << R], unsigned s0, unsigned low, unsigned glo, const uint2* __restrict__ big) {
+#pragma unroll
+  for (int u = 1; u <= R; u++) {
+    const unsigned h = 1u << (u - 1), H = 1u << (s0 + u - 1);
+#pragma unroll
+    for (unsigned b = 0; b < (1u << (R - 1)); b++) {
+      const unsigned kl = b & (h - 1);
+      const unsigned j0 = ((b >> (u - 1)) << u) | kl, j1 = j0 + h;
+      uint32_t v = shoup(x[j1], __ldg(big + (((H + low + (kl << s0)) << LOG_BLOCK) | glo)));
+      uint32_t a = x[j0];
+      x[j0] = fadd(a, v);
+      x[j1] = fsub(a, v);
+    }
+  }
+}
+template <int R>
+LSK_D void dif_local_big(uint32_t (&x)[1 << R], unsigned s0, unsigned low, unsigned glo, const uint2* __restrict__ big) {
+#pragma unroll
+  for (int u = R; u >= 1; u--) {
+    const unsigned h = 1u << (u - 1), H = 1u << (s0 + u - 1);
+#pragma unroll
+    for (unsigned b = 0; b < (1u << (R - 1)); b++) {
+      const unsigned kl = b & (h - 1);
+      const unsigned j0 = ((b >> (u - 1)) << u) | kl, j1 = j0 + h;
+      uint32_t a = x[j0], c = x[j1];
+      x[j0] = fadd(a, c);
+      x[j1] = shoup(fsub(a, c), __ldg(big + (((H + low + (kl << s0)) << LOG_BLOCK) | glo)));
     }
   }
 }
@@ -360,107 +410,114 @@ __global__ void __launch_bounds__(K13_THREADS) lde_k3_bulk_kernel(uint32_t* __re
 }
 
 // K2: the middle pass over a tile of 2^t blocks (q) x 2^c consecutive low indices (lo), element (q, lo)
-// at shared index (q << c) | lo.  The size-2^t transforms over q run as ceil(t/4) register passes of
-// 2^r (r <= 4) elements each; the first DIT pass reads global memory (applying the inverse inter-pass
-// twiddle W_N^(-bitrev_t(q) * lo)), the last DIF pass of each coset writes it (forward twiddle).
+// at shared index (q << c) | lo.  Stages 13..logn over q run as ceil(t/4) register passes of 2^r (r <= 4)
+// elements each; the first DIT pass reads global memory, the last DIF pass of each coset writes it.
 struct K2Args {
   uint32_t* out;
   size_t out_stride;
-  unsigned logn, c;
-  const uint2 *tw_fwd, *tw_inv, *lo_f, *hi_f, *lo_i, *hi_i, *scale_a, *scale_b;
+  const uint2 *big_f, *big_i, *scale_a, *scale_b;
 };
 enum { K2_GLOBAL = 0, K2_COEF = 1, K2_WORK = 2 };
-template <int R, bool DIF>
+// Everything about a launch is fixed by T = logn - 12, so the kernel is instantiated per T (12 instances): tile shape,
+// pass plan, loop trip counts, shifts and masks are compile-time constants (round 1 decoded them at run time: ~310
+// instructions per element, a third of them index arithmetic).
+template <int T>
+struct K2Plan {
+  static constexpr int LOG_TILE = T <= 8 ? 12 : (T <= 10 ? T + 4 : 14);   // 2^T blocks x 2^C low indices
+  static constexpr int C = LOG_TILE - T;
+  static constexpr int THREADS = 1 << (LOG_TILE - 4);                     // 16 elements per thread
+  static constexpr int NP = (T + 3) / 4, BASE = T / NP, REM = T % NP;     // passes as even as possible (10 -> 4, 3, 3)
+  static constexpr int r(int p) { return BASE + (p < REM ? 1 : 0); }
+  static constexpr int s0(int p) { return p * BASE + (p < REM ? p : REM); }
+};
+template <int T, int R, int S0, bool DIF, int SRC, int DST>
 LSK_D void k2_pass(const K2Args& a, uint32_t* __restrict__ col, uint32_t* __restrict__ coef, uint32_t* __restrict__ work,
-                   unsigned t, unsigned s0, int src, int dst, int coset) {
-  const unsigned c = a.c, cmask = (1u << c) - 1, lo_base = blockIdx.x << c;
-  const unsigned nitems = 1u << (t - R + c);
-  const size_t n = (size_t)1 << a.logn;
-  for (unsigned it = threadIdx.x; it < nitems; it += blockDim.x) {
-    const unsigned lo = it & cmask, rest = it >> c;
-    const unsigned ql = rest & ((1u << s0) - 1), qh = rest >> s0;
-    const unsigned qbase = (qh << (s0 + R)) | ql, glo = lo_base + lo;
-    uint32_t x[1 << R];
-    if (src == K2_GLOBAL) {
+                   int coset) {
+  using Pl = K2Plan<T>;
+  constexpr unsigned c = Pl::C, cmask = (1u << c) - 1;
+  constexpr unsigned nitems = 1u << (T - R + c);
+  constexpr size_t n = (size_t)1 << (T + LOG_BLOCK);
+  const unsigned lo_base = blockIdx.x << c;
 #pragma unroll
-      for (int jj = 0; jj < (1 << R); jj++) {
-        const unsigned q = qbase | (jj << s0);
-        const unsigned ex = bitrev32(q, t) * glo;
-        uint32_t v = col[((size_t)q << LOG_BLOCK) | glo];
-        x[jj] = shoup(shoup(v, __ldg(a.lo_i + (ex & (BLOCK_ELEMS - 1)))), __ldg(a.hi_i + (ex >> LOG_BLOCK)));
-      }
-    } else if (src == K2_COEF && DIF) {  // first DIF pass of a coset: coefficient m = q * 4096 + lo times s_j^m / N
+  for (unsigned it0 = 0; it0 < nitems; it0 += Pl::THREADS) {
+    const unsigned it = it0 + threadIdx.x;
+    const unsigned lo = it & cmask, rest = it >> c;
+    const unsigned ql = rest & ((1u << S0) - 1), qh = rest >> S0;
+    const unsigned qbase = (qh << (S0 + R)) | ql, glo = lo_base + lo;
+    uint32_t x[1 << R];
+    if (SRC == K2_GLOBAL) {
+#pragma unroll
+      for (int jj = 0; jj < (1 << R); jj++) x[jj] = col[((size_t)(qbase | (jj << S0)) << LOG_BLOCK) | glo];
+    } else if (SRC == K2_COEF && DIF) {  // first DIF pass of a coset: coefficient m = q * 4096 + lo times s_j^m / N
       const uint2 sa = __ldg(a.scale_a + coset * BLOCK_ELEMS + glo);
 #pragma unroll
       for (int jj = 0; jj < (1 << R); jj++) {
-        const unsigned q = qbase | (jj << s0);
-        x[jj] = shoup(shoup(coef[(q << c) | lo], sa), __ldg(a.scale_b + ((size_t)coset << t) + q));
+        const unsigned q = qbase | (jj << S0);
+        x[jj] = shoup(shoup(coef[(q << c) | lo], sa), __ldg(a.scale_b + ((size_t)coset << T) + q));
       }
     } else {
-      const uint32_t* sp = src == K2_COEF ? coef : work;
+      const uint32_t* sp = SRC == K2_COEF ? coef : work;
 #pragma unroll
-      for (int jj = 0; jj < (1 << R); jj++) x[jj] = sp[((qbase | (jj << s0)) << c) | lo];
+      for (int jj = 0; jj < (1 << R); jj++) x[jj] = sp[((qbase | (jj << S0)) << c) | lo];
     }
-    if (DIF) dif_local<R>(x, s0, ql, a.tw_fwd);
-    else dit_local<R>(x, s0, ql, a.tw_inv);
-    if (dst == K2_GLOBAL) {
+    if (DIF) dif_local_big<R>(x, S0, ql, glo, a.big_f);
+    else dit_local_big<R>(x, S0, ql, glo, a.big_i);
+    if (DST == K2_GLOBAL) {
 #pragma unroll
-      for (int jj = 0; jj < (1 << R); jj++) {
-        const unsigned q = qbase | (jj << s0);
-        const unsigned ex = bitrev32(q, t) * glo;
-        uint32_t v = shoup(shoup(x[jj], __ldg(a.lo_f + (ex & (BLOCK_ELEMS - 1)))), __ldg(a.hi_f + (ex >> LOG_BLOCK)));
-        col[(size_t)coset * n + (((size_t)q << LOG_BLOCK) | glo)] = v;
-      }
+      for (int jj = 0; jj < (1 << R); jj++)
+        col[(size_t)coset * n + (((size_t)(qbase | (jj << S0)) << LOG_BLOCK) | glo)] = x[jj];
     } else {
-      uint32_t* dp = dst == K2_COEF ? coef : work;
+      uint32_t* dp = DST == K2_COEF ? coef : work;
 #pragma unroll
-      for (int jj = 0; jj < (1 << R); jj++) dp[((qbase | (jj << s0)) << c) | lo] = x[jj];
+      for (int jj = 0; jj < (1 << R); jj++) dp[((qbase | (jj << S0)) << c) | lo] = x[jj];
     }
   }
 }
-template <bool DIF>
-LSK_D void k2_pass_r(unsigned r, const K2Args& a, uint32_t* col, uint32_t* coef, uint32_t* work, unsigned t, unsigned s0,
-                     int src, int dst, int coset) {
-  switch (r) {
-    case 1: k2_pass<1, DIF>(a, col, coef, work, t, s0, src, dst, coset); break;
-    case 2: k2_pass<2, DIF>(a, col, coef, work, t, s0, src, dst, coset); break;
-    case 3: k2_pass<3, DIF>(a, col, coef, work, t, s0, src, dst, coset); break;
-    default: k2_pass<4, DIF>(a, col, coef, work, t, s0, src, dst, coset); break;
-  }
-}
-template <int NT>
-__global__ void __launch_bounds__(NT, 768 / NT > 0 ? 768 / NT : 1) lde_k2_kernel(K2Args a) {
-  extern __shared__ uint32_t smem[];
-  const unsigned t = a.logn - LOG_BLOCK;
-  uint32_t* coef = smem;
-  uint32_t* work = smem + ((size_t)1 << (t + a.c));
-  uint32_t* col = a.out + (size_t)blockIdx.y * a.out_stride;
-  // pass plan: ceil(t / 4) passes, sizes as even as possible (t = 10 -> 4, 3, 3)
-  const unsigned np = (t + 3) / 4, base = t / np, rem = t % np;
-  unsigned s0 = 0;
-  for (unsigned p = 0; p < np; p++) {  // DIT: stages 1 .. t
-    const unsigned r = base + (p < rem ? 1u : 0u);
-    k2_pass_r<false>(r, a, col, coef, work, t, s0, p == 0 ? K2_GLOBAL : K2_COEF, K2_COEF, 0);
-    s0 += r;
+template <int T, int P>
+LSK_D void k2_dit_passes(const K2Args& a, uint32_t* col, uint32_t* coef, uint32_t* work) {   // stages 13 .. logn
+  using Pl = K2Plan<T>;
+  if constexpr (P < Pl::NP) {
+    k2_pass<T, Pl::r(P), Pl::s0(P), false, P == 0 ? K2_GLOBAL : K2_COEF, K2_COEF>(a, col, coef, work, 0);
     __syncthreads();
+    k2_dit_passes<T, P + 1>(a, col, coef, work);
   }
-  for (int coset = 0; coset < 2; coset++) {  // DIF: stages t .. 1
-    unsigned top = t;
-    for (unsigned p = np; p-- > 0;) {
-      const unsigned r = base + (p < rem ? 1u : 0u);
-      top -= r;
-      k2_pass_r<true>(r, a, col, coef, work, t, top, p == np - 1 ? K2_COEF : K2_WORK, p == 0 ? K2_GLOBAL : K2_WORK, coset);
-      __syncthreads();
-    }
+}
+template <int T, int P>
+LSK_D void k2_dif_passes(const K2Args& a, uint32_t* col, uint32_t* coef, uint32_t* work, int coset) {   // stages logn .. 13
+  using Pl = K2Plan<T>;
+  if constexpr (P >= 0) {
+    k2_pass<T, Pl::r(P), Pl::s0(P), true, P == Pl::NP - 1 ? K2_COEF : K2_WORK, P == 0 ? K2_GLOBAL : K2_WORK>(a, col, coef, work,
+                                                                                                         coset);
+    __syncthreads();
+    k2_dif_passes<T, P - 1>(a, col, coef, work, coset);
   }
+}
+// 256-thread tiles: two resident CTAs per SM (128 registers, next to no spilling in the fully unrolled passes) measured
+// faster than three (80 registers, 192 B of spills at T = 8): 5.39 vs 5.97 ms for the LDEs of a Lurk fib 2^20 prove.
+template <int T>
+__global__ void __launch_bounds__(K2Plan<T>::THREADS, K2Plan<T>::THREADS == 256 ? 2 : 1) lde_k2_kernel(K2Args a) {
+  extern __shared__ uint32_t smem[];
+  uint32_t* coef = smem;
+  uint32_t* work = smem + ((size_t)1 << K2Plan<T>::LOG_TILE);
+  uint32_t* col = a.out + (size_t)blockIdx.y * a.out_stride;
+  k2_dit_passes<T, 0>(a, col, coef, work);
+  for (int coset = 0; coset < 2; coset++) k2_dif_passes<T, K2Plan<T>::NP - 1>(a, col, coef, work, coset);
+}
+template <int T>
+static void k2_set_smem() {
+  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (2 * 4) << K2Plan<T>::LOG_TILE));
+}
+template <int T>
+static void k2_launch(const K2Args& a, uint32_t nc, cudaStream_t st) {
+  using Pl = K2Plan<T>;
+  lde_k2_kernel<T><<<dim3(BLOCK_ELEMS >> Pl::C, nc), Pl::THREADS, (2 * 4) << Pl::LOG_TILE, st>>>(a);
 }
 
 constexpr size_t K3B_SMEM_BYTES = (2 * BLOCK_ELEMS + K13_SMEM) * sizeof(uint32_t);
 void init_ntt_kernels() {
   LSK_CUDA(cudaFuncSetAttribute(lde_k3_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K3B_SMEM_BYTES));
-  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 4096 * 4));
-  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 8192 * 4));
-  LSK_CUDA(cudaFuncSetAttribute(lde_k2_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 16384 * 4));
+  k2_set_smem<1>(); k2_set_smem<2>(); k2_set_smem<3>(); k2_set_smem<4>(); k2_set_smem<5>(); k2_set_smem<6>();
+  k2_set_smem<7>(); k2_set_smem<8>(); k2_set_smem<9>(); k2_set_smem<10>(); k2_set_smem<11>(); k2_set_smem<12>();
 }
 
 void lde_flush(lsk_ctx* ctx, LdeBatch& batch) {
@@ -502,15 +559,12 @@ void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, 
     LSK_CUDA(cudaGetLastError());
     return;
   }
-  NttTables::Big* bg = big_tables(ctx, logn);
+  big_tables(ctx, logn);
   unsigned tt = logn - LOG_BLOCK;
   unsigned blocks = 1u << tt;
   if (ncols > 65535) fail(LSK_ERR_ARG, "too many columns");
-  // tile = 2^t blocks x 2^c low indices = 2^12 .. 2^14 elements (c = 4 up to t = 10, then 3, 2), two
-  // copies in shared memory (coefficients + work), 16 elements per thread
-  unsigned log_tile = tt <= 8 ? 12 : (tt <= 10 ? tt + 4 : 14);
-  unsigned c = log_tile - tt;
-  size_t smem = 2 * ((size_t)1 << log_tile) * sizeof(uint32_t);
+  // tile = 2^t blocks x 2^c low indices = 2^12 .. 2^14 elements (K2Plan), two copies in shared memory
+  // (coefficients + work), 16 elements per thread
   // Column chunking (LSK_LDE_L2_MB, default off).  The three passes of a column exchange 4N + 8N + 8N bytes through
   // `out`; run over a chunk of columns whose 12N-byte footprints fit the L2 together, K2 and K3 find what the previous
   // pass wrote still on chip.  MEASURED AND REJECTED (B200, Lurk fib 2^20, 80 MB chunks): K1+K2+K3 19.4 ms against 16.3 ms
@@ -532,14 +586,23 @@ void lde_dev(lsk_ctx* ctx, const uint32_t* in, size_t in_stride, uint32_t* out, 
       ProfScope ps(ctx, PT_LDE_K1, 1, 8.0 * cells);
       lde_k1_kernel<<<dim3(blocks, nc), K13_THREADS, 0, st>>>(cin, in_stride, cout, out_stride, t->tw_inv.p);
     }
-    dim3 grid(BLOCK_ELEMS >> c, nc);
     {
       ProfScope ps(ctx, PT_LDE_K2, 1, 12.0 * cells);
-      K2Args a{cout, out_stride, logn, c, t->tw_fwd.p, t->tw_inv.p, bg->lo_f.p, bg->hi_f.p, bg->lo_i.p, bg->hi_i.p,
-               sc->a.p, sc->b.p};
-      if (log_tile == 12) lde_k2_kernel<256><<<grid, 256, smem, st>>>(a);
-      else if (log_tile == 13) lde_k2_kernel<512><<<grid, 512, smem, st>>>(a);
-      else lde_k2_kernel<1024><<<grid, 1024, smem, st>>>(a);
+      K2Args a{cout, out_stride, t->big_f.p, t->big_i.p, sc->a.p, sc->b.p};
+      switch (tt) {
+        case 1: k2_launch<1>(a, nc, st); break;
+        case 2: k2_launch<2>(a, nc, st); break;
+        case 3: k2_launch<3>(a, nc, st); break;
+        case 4: k2_launch<4>(a, nc, st); break;
+        case 5: k2_launch<5>(a, nc, st); break;
+        case 6: k2_launch<6>(a, nc, st); break;
+        case 7: k2_launch<7>(a, nc, st); break;
+        case 8: k2_launch<8>(a, nc, st); break;
+        case 9: k2_launch<9>(a, nc, st); break;
+        case 10: k2_launch<10>(a, nc, st); break;
+        case 11: k2_launch<11>(a, nc, st); break;
+        default: k2_launch<12>(a, nc, st); break;
+      }
     }
     {
       ProfScope ps(ctx, PT_LDE_K3, 1, 16.0 * cells);

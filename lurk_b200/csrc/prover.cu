@@ -339,20 +339,40 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   std::vector<MatRef> refs;
   LdeBatch small_ldes;
   std::vector<DevBuf<uint32_t>> small_perms;  // natural-domain traces of queued small LDEs, alive until the flush
-  for (size_t i = 0; i < nchips; i++) {
-    const ChipH& c = m.chips[sd.chip_ids[i]];
-    const ChipDev& d = m.dchips[sd.chip_ids[i]];
-    size_t n = (size_t)1 << sd.logn[i];
-    uint32_t pcols = 4 * d.pw;
-    DevBuf<uint32_t> perm(ctx, n * pcols);
-    perm_lde[i].alloc(ctx, 2 * n * pcols);
-    perm_trace_dev(ctx, d, sd.main[i].p, n, c.prep_width ? m.prep_trace.p : nullptr, n, sd.logn[i], chal_alpha, d_beta.p,
-                   perm.p, n, scratch.p, cums.p + i);
-    lde_matrix(ctx, perm.p, n, perm_lde[i].p, 2 * n, sd.logn[i], pcols, LdeShift::Trace, &small_ldes);
-    refs.push_back(MatRef{perm_lde[i].p, 2 * n, sd.logn[i] + 1, pcols});
-    if (sd.logn[i] <= 12) small_perms.push_back(std::move(perm));
-    sd.main[i].release();  // the natural-domain trace is not needed past this point
-  }
+  // A shard of a Lurk machine has a dozen chips with a handful of rows (hash3/5, the u64 chips, ...): their
+  // permutation-trace and quotient launches are ONE CTA walking a long straight-line program (0.05-0.5 ms each, 3.5 ms
+  // per prove) while 147 SMs idle.  They go to the context's side stream and run beside the big chips' launches; their
+  // LDEs are queued anyway (lde_flush), after the join.  Not in a device group (one stream orders the collectives).
+  const bool use_side = !comm_active(ctx) && !getenv("LSK_NO_SIDE_STREAM");
+  constexpr unsigned SIDE_MAX_LOG = 8;
+  SideStream side(ctx);
+  DevBuf<Ext> scratch_side(ctx, (size_t)1 << SIDE_MAX_LOG);
+  std::vector<DevBuf<uint32_t>> side_inputs;   // buffers side-stream kernels read: released only after the join
+  // the tiny chips first: the side stream waits (once) for what the main stream has queued so far, and every buffer its
+  // kernels use comes from the pool as it stood then
+  refs.resize(nchips);
+  for (int pass = 0; pass < 2; pass++)
+    for (size_t i = 0; i < nchips; i++) {
+      const bool on_side = use_side && sd.logn[i] <= SIDE_MAX_LOG;
+      if (on_side != (pass == 0)) continue;
+      const ChipH& c = m.chips[sd.chip_ids[i]];
+      const ChipDev& d = m.dchips[sd.chip_ids[i]];
+      size_t n = (size_t)1 << sd.logn[i];
+      uint32_t pcols = 4 * d.pw;
+      DevBuf<uint32_t> perm(ctx, n * pcols);
+      perm_lde[i].alloc(ctx, 2 * n * pcols);
+      if (on_side) side.enter();
+      perm_trace_dev(ctx, d, sd.main[i].p, n, c.prep_width ? m.prep_trace.p : nullptr, n, sd.logn[i], chal_alpha, d_beta.p,
+                     perm.p, n, on_side ? scratch_side.p : scratch.p, cums.p + i);
+      if (on_side) side.leave();
+      lde_matrix(ctx, perm.p, n, perm_lde[i].p, 2 * n, sd.logn[i], pcols, LdeShift::Trace, &small_ldes);
+      refs[i] = MatRef{perm_lde[i].p, 2 * n, sd.logn[i] + 1, pcols};
+      if (sd.logn[i] <= 12) small_perms.push_back(std::move(perm));
+      if (on_side) side_inputs.push_back(std::move(sd.main[i]));
+      else sd.main[i].release();  // the natural-domain trace is not needed past this point
+    }
+  side.join();
+  side_inputs.clear();
   lde_flush(ctx, small_ldes);
   small_perms.clear();
   pt.mark("perm trace + LDE");
@@ -378,35 +398,42 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     DevBuf<uint32_t> qv(ctx, 2 * max_n * 4);
     LdeBatch small_ldes;
     std::vector<DevBuf<uint32_t>> small_qv;  // quotient values of the queued small LDEs
-    for (size_t i = 0; i < nchips; i++) {
-      const ChipH& c = m.chips[sd.chip_ids[i]];
-      const ChipDev& d = m.dchips[sd.chip_ids[i]];
-      size_t n = (size_t)1 << sd.logn[i];
-      uint32_t* qvp = qv.p;
-      if (sd.logn[i] <= 12) {
-        small_qv.emplace_back(ctx, 2 * n * 4);
-        qvp = small_qv.back().p;
+    refs.resize(2 * nchips);
+    for (int pass = 0; pass < 2; pass++)
+      for (size_t i = 0; i < nchips; i++) {
+        const bool on_side = use_side && sd.logn[i] <= SIDE_MAX_LOG;   // tiny chips first, on the side stream (see above)
+        if (on_side != (pass == 0)) continue;
+        const ChipH& c = m.chips[sd.chip_ids[i]];
+        const ChipDev& d = m.dchips[sd.chip_ids[i]];
+        size_t n = (size_t)1 << sd.logn[i];
+        uint32_t* qvp = qv.p;
+        if (sd.logn[i] <= 12) {
+          small_qv.emplace_back(ctx, 2 * n * 4);
+          qvp = small_qv.back().p;
+        }
+        QuotientArgs a{};
+        a.main = sd.main_lde[i].p; a.mstride = 2 * n;
+        a.prep = c.prep_width ? m.prep_lde.p : nullptr; a.pstride = 2 * n;
+        a.perm = perm_lde[i].p; a.permstride = 2 * n;
+        a.pv = d_pv.p;
+        a.apow = d_alpha.p;
+        a.n_total = (uint32_t)(c.n_constraints + c.n_perm_constraints());
+        a.beta_pows = d_beta.p;
+        a.cum_sum = cums.p + i;
+        a.chal_alpha = chal_alpha;
+        a.logn = sd.logn[i];
+        a.out = qvp; a.ostride = 2 * n;
+        if (on_side) side.enter();
+        quotient_dev(ctx, d, a);
+        if (on_side) side.leave();
+        for (int j = 0; j < 2; j++) {
+          quot_lde[2 * i + j].alloc(ctx, 2 * n * 4);
+          lde_matrix(ctx, qvp + (size_t)j * n, 2 * n, quot_lde[2 * i + j].p, 2 * n, sd.logn[i], 4,
+                     j ? LdeShift::QuotChunk1 : LdeShift::QuotChunk0, &small_ldes);
+          refs[2 * i + j] = MatRef{quot_lde[2 * i + j].p, 2 * n, sd.logn[i] + 1, 4};
+        }
       }
-      QuotientArgs a{};
-      a.main = sd.main_lde[i].p; a.mstride = 2 * n;
-      a.prep = c.prep_width ? m.prep_lde.p : nullptr; a.pstride = 2 * n;
-      a.perm = perm_lde[i].p; a.permstride = 2 * n;
-      a.pv = d_pv.p;
-      a.apow = d_alpha.p;
-      a.n_total = (uint32_t)(c.n_constraints + c.n_perm_constraints());
-      a.beta_pows = d_beta.p;
-      a.cum_sum = cums.p + i;
-      a.chal_alpha = chal_alpha;
-      a.logn = sd.logn[i];
-      a.out = qvp; a.ostride = 2 * n;
-      quotient_dev(ctx, d, a);
-      for (int j = 0; j < 2; j++) {
-        quot_lde[2 * i + j].alloc(ctx, 2 * n * 4);
-        lde_matrix(ctx, qvp + (size_t)j * n, 2 * n, quot_lde[2 * i + j].p, 2 * n, sd.logn[i], 4,
-                   j ? LdeShift::QuotChunk1 : LdeShift::QuotChunk0, &small_ldes);
-        refs.push_back(MatRef{quot_lde[2 * i + j].p, 2 * n, sd.logn[i] + 1, 4});
-      }
-    }
+    side.join();
     lde_flush(ctx, small_ldes);
   }
   pt.mark("quotient + LDE");
@@ -422,16 +449,26 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   // layout of `opened` per chip: prep | main | perm | quot0 | quot1, each as [col][point]
   struct OpenOff { size_t prep, main, perm, quot[2]; };
   std::vector<OpenOff> oo(nchips);
-  size_t nopen = 0;
+  // round-major (all preprocessed, all main, all permutation, all quotient values): the order the transcript observes
+  // them in, so that a round's values are one contiguous range that can leave the device as soon as it is complete
+  size_t nopen = 0, round_end[3];
+  for (size_t i = 0; i < nchips; i++) oo[i].prep = nopen, nopen += 2 * m.chips[sd.chip_ids[i]].prep_width;
+  for (size_t i = 0; i < nchips; i++) oo[i].main = nopen, nopen += 2 * m.chips[sd.chip_ids[i]].width;
+  round_end[0] = nopen;
+  for (size_t i = 0; i < nchips; i++) oo[i].perm = nopen, nopen += 2 * 4 * m.chips[sd.chip_ids[i]].perm_width();
+  round_end[1] = nopen;
   for (size_t i = 0; i < nchips; i++) {
-    const ChipH& c = m.chips[sd.chip_ids[i]];
-    oo[i].prep = nopen; nopen += 2 * c.prep_width;
-    oo[i].main = nopen; nopen += 2 * c.width;
-    oo[i].perm = nopen; nopen += 2 * 4 * c.perm_width();
     oo[i].quot[0] = nopen; nopen += 8;
     oo[i].quot[1] = nopen; nopen += 8;
   }
+  round_end[2] = nopen;
   DevBuf<Ext> opened(ctx, nopen);
+  Ext* h_open = (Ext*)pinned_scratch(ctx, (nopen + nchips) * sizeof(Ext));   // page-locked: the copies below are asynchronous
+  Ext* h_cums = h_open + nopen;
+  struct Events {
+    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
+    ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
+  } open_done;
   const bool grouped = comm_active(ctx);
   if (grouped) opened.zero();   // every value is computed by exactly one rank and summed over the group
   {
@@ -445,6 +482,35 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       v.push_back(OpenMat{sd.main_lde[i].p, n2, c.width, (uint32_t)oo[i].main, 0});
       v.push_back(OpenMat{perm_lde[i].p, n2, 4 * (uint32_t)c.perm_width(), (uint32_t)oo[i].perm, 0});
       for (int j = 0; j < 2; j++) v.push_back(OpenMat{quot_lde[2 * i + j].p, n2, 4, (uint32_t)oo[i].quot[j], 1});
+    }
+    if (!grouped) {
+      // Weights of every height first, then the openings round by round (preprocessed + main, permutation, quotient);
+      // each round's values are copied out behind its kernels.  The host feeds a round to the transcript -- 7 000
+      // dependent Poseidon2 permutations for a Lurk shard, ~5 ms on a core -- while the device computes the next one.
+      std::map<unsigned, std::pair<DevBuf<Ext>, DevBuf<Ext>>> wts;
+      for (auto& kv : by_logn) {
+        auto& w = wts[kv.first];
+        w.first.alloc(ctx, (size_t)1 << kv.first);
+        w.second.alloc(ctx, (size_t)1 << kv.first);
+        bary_weights_dev(ctx, kv.first, zeta, w.first.p);
+        bary_weights_dev(ctx, kv.first, emul_base(zeta, two_adic_generator(kv.first)), w.second.p);
+      }
+      size_t lo = 0;
+      for (int r = 0; r < 3; r++) {
+        const size_t hi = round_end[r];
+        for (auto& kv : by_logn) {
+          std::vector<OpenMat> part;
+          for (auto& om : kv.second)
+            if (om.out_off >= lo && om.out_off < hi) part.push_back(om);
+          open_batch_dev(ctx, part, kv.first, wts[kv.first].first.p, wts[kv.first].second.p, opened.p);
+        }
+        if (hi > lo) LSK_CUDA(cudaMemcpyAsync(h_open + lo, opened.p + lo, (hi - lo) * sizeof(Ext), cudaMemcpyDeviceToHost, st));
+        if (r == 2) LSK_CUDA(cudaMemcpyAsync(h_cums, cums.p, nchips * sizeof(Ext), cudaMemcpyDeviceToHost, st));
+        LSK_CUDA(cudaEventCreateWithFlags(&open_done.e[r], cudaEventDisableTiming));
+        LSK_CUDA(cudaEventRecord(open_done.e[r], st));
+        lo = hi;
+      }
+      by_logn.clear();
     }
     for (auto& kv : by_logn) {
       const unsigned logn = kv.first;
@@ -480,20 +546,21 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       // the weight buffers are freed stream-ordered after the kernels that read them
     }
   }
-  if (grouped) comm_allreduce_u32(ctx, (uint32_t*)opened.p, 4 * nopen);
-  std::vector<Ext> h_open(nopen), h_cums(nchips);
-  opened.download(h_open.data(), nopen);
-  cums.download(h_cums.data(), nchips);
-  LSK_CUDA(cudaStreamSynchronize(st));
+  if (grouped) {
+    comm_allreduce_u32(ctx, (uint32_t*)opened.p, 4 * nopen);
+    opened.download(h_open, nopen);
+    cums.download(h_cums, nchips);
+    LSK_CUDA(cudaStreamSynchronize(st));
+  }
   m.last_d2h += (nopen + nchips) * sizeof(Ext);
   pt.mark("openings");
 
   // rounds in the order the PCS sees them: preprocessed, main, permutation, quotient
   struct RoundMat { const uint32_t* p; size_t stride; unsigned lh; uint32_t w, npoints; size_t open_off; };
-  struct Round { const MerkleTreeDev* tree; std::vector<RoundMat> mats; };
+  struct Round { const MerkleTreeDev* tree; std::vector<RoundMat> mats; int wait; };   // wait: open_done event of its values
   std::vector<Round> rounds;
   {
-    Round rp{&m.prep_tree, {}}, rm{&sd.main_tree, {}}, rperm{&perm_tree, {}}, rq{&quot_tree, {}};
+    Round rp{&m.prep_tree, {}, 0}, rm{&sd.main_tree, {}, 0}, rperm{&perm_tree, {}, 1}, rq{&quot_tree, {}, 2};
     for (size_t i = 0; i < nchips; i++) {
       const ChipH& c = m.chips[sd.chip_ids[i]];
       size_t n2 = (size_t)2 << sd.logn[i];
@@ -508,10 +575,13 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     rounds.push_back(std::move(rperm));
     rounds.push_back(std::move(rq));
   }
-  for (auto& rd : rounds)
+  for (auto& rd : rounds) {
+    if (open_done.e[rd.wait]) LSK_CUDA(cudaEventSynchronize(open_done.e[rd.wait]));
     for (auto& mt : rd.mats)
       for (uint32_t p = 0; p < mt.npoints; p++)
         for (uint32_t c = 0; c < mt.w; c++) ch.observe(h_open[mt.open_off + 2 * c + p]);
+  }
+  if (open_done.e[2]) LSK_CUDA(cudaEventSynchronize(open_done.e[2]));   // (the cumulative sums ride behind the last round)
   Ext fri_alpha = ch.sample_ext();
 
   // ---- reduced openings per LDE height

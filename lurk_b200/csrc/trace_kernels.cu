@@ -446,19 +446,38 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
   h2d_bytes = 0;
   const bool sliced = shard_size != 0 && record_row_ordered(rec);
   // words [first, first + count) of v; the returned pointer is biased by -first so that v's own indices work
-  // In a device group (comm.cuh) every rank holds the same host record, but only rank 0 of the group sends the
-  // large tables over PCIe; the others receive them over NVLink (one NCCL group of broadcasts at the end).
+  // In a device group (comm.cuh) every rank holds the same host record.  The large tables are laid out in ONE device
+  // arena; rank r copies only the r-th 1/G of the arena over its own PCIe link and a single all-gather over NVLink fills
+  // in the rest -- G links share the upload instead of every rank (or a leader) pushing the whole record.
   const bool grouped = comm_active(ctx);
-  std::vector<std::pair<void*, size_t>> from_leader;
+  struct Piece { size_t off; const uint32_t* src; size_t count; };
+  std::vector<Piece> pieces;
+  uint32_t* arena = nullptr;
+  size_t arena_off = 0, arena_per = 0;
+  if (grouped) {
+    size_t total = 0;
+    auto add = [&](const std::vector<uint32_t>& v) { total += v.size() + 4; };
+    for (const FuncTable& t : rec.funcs) {
+      add(t.args); add(t.outs); add(t.provide); add(t.req_off); add(t.reqs); add(t.hint_off); add(t.hints);
+      add(t.depth); add(t.dreq_off); add(t.dreqs);
+    }
+    for (const MemTable& m : rec.mems) { add(m.vals); add(m.provide); }
+    const size_t g = (size_t)ctx->comm->size;
+    arena_per = ((total + g - 1) / g + 3) & ~(size_t)3;
+    bufs.emplace_back(ctx, arena_per * g);
+    arena = bufs.back().p;
+  }
   auto up_range = [&](const std::vector<uint32_t>& v, size_t first, size_t count) -> const uint32_t* {
     if (!count) return nullptr;
-    bufs.emplace_back(ctx, count);
-    const bool shared = grouped && count * 4 >= (64u << 10);
-    if (!shared || ctx->comm->rank == 0) {
-      LSK_CUDA(cudaMemcpyAsync(bufs.back().p, v.data() + first, count * 4, cudaMemcpyHostToDevice, ctx->stream));
-      h2d_bytes += count * 4;
+    if (grouped && count * 4 >= (64u << 10)) {
+      const size_t off = arena_off;
+      arena_off += (count + 3) & ~(size_t)3;
+      pieces.push_back({off, v.data() + first, count});
+      return arena + off - first;
     }
-    if (shared) from_leader.emplace_back(bufs.back().p, count * 4);
+    bufs.emplace_back(ctx, count);
+    LSK_CUDA(cudaMemcpyAsync(bufs.back().p, v.data() + first, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    h2d_bytes += count * 4;
     return bufs.back().p - first;
   };
   auto up = [&](const std::vector<uint32_t>& v) { return up_range(v, 0, v.size()); };
@@ -500,7 +519,16 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
     d.len = m.len; d.rows = (uint32_t)m.rows();
     h_mems.push_back(d);
   }
-  if (grouped) comm_broadcast_many(ctx, from_leader, 0);
+  if (grouped && arena_off) {
+    const size_t b = (size_t)ctx->comm->rank * arena_per, e = b + arena_per;   // this rank's words of the arena
+    for (const Piece& pc : pieces) {
+      const size_t lo = std::max(b, pc.off), hi = std::min(e, pc.off + pc.count);
+      if (lo >= hi) continue;
+      LSK_CUDA(cudaMemcpyAsync(arena + lo, pc.src + (lo - pc.off), (hi - lo) * 4, cudaMemcpyHostToDevice, ctx->stream));
+      h2d_bytes += (hi - lo) * 4;
+    }
+    comm_allgather(ctx, arena, arena_per * 4);
+  }
   funcs.alloc(ctx, h_funcs.size());
   if (!h_funcs.empty()) funcs.upload(h_funcs.data(), h_funcs.size());
   mems.alloc(ctx, h_mems.size());

@@ -294,6 +294,7 @@ static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record
     sd->main_lde.push_back(std::move(lde));
   }
   if (refs.empty()) fail(LSK_ERR_ARG, "shard %u has no chips", shard);
+  drec.wait_all(ctx);   // tables of funcs without rows in this shard included: nothing of the upload outlives this point
   lde_flush(ctx, small_ldes);
   pt.mark("trace + main LDE");
   merkle_commit_dev(ctx, refs, sd->main_tree);

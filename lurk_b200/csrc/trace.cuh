@@ -30,6 +30,27 @@ struct DeviceRecord {
   std::vector<DevFuncTable> h_funcs;
   std::vector<DevMemTable> h_mems;
   size_t h2d_bytes = 0;
+  // Outside a device group the tables travel on the context's side stream, in two waves: first what every trace kernel
+  // may gather from (outputs, depths, arguments of invertible funcs, memory values, descriptors), then func by func the
+  // per-row tables only that func's own trace reads.  A trace launch waits for `common_ready` and its func's event, so
+  // trace generation and the LDE of the first chips run while the tables of the later ones are still crossing PCIe.
+  cudaEvent_t common_ready = nullptr, all_ready = nullptr;
+  std::vector<cudaEvent_t> func_ready;
+  void wait_common(lsk_ctx* ctx) const { if (common_ready) cudaStreamWaitEvent(ctx->stream, common_ready, 0); }
+  void wait_func(lsk_ctx* ctx, uint32_t f) const {
+    wait_common(ctx);
+    if (f < func_ready.size() && func_ready[f]) cudaStreamWaitEvent(ctx->stream, func_ready[f], 0);
+  }
+  void wait_all(lsk_ctx* ctx) const { if (all_ready) cudaStreamWaitEvent(ctx->stream, all_ready, 0); }
+  DeviceRecord() = default;
+  DeviceRecord(const DeviceRecord&) = delete;
+  DeviceRecord& operator=(const DeviceRecord&) = delete;
+  ~DeviceRecord() {
+    if (all_ready) cudaEventSynchronize(all_ready);   // no copy may still be writing the buffers about to be released
+    for (cudaEvent_t e : func_ready) if (e) cudaEventDestroy(e);
+    if (common_ready) cudaEventDestroy(common_ready);
+    if (all_ready) cudaEventDestroy(all_ready);
+  }
   // shard_size == 0: the whole record.  Otherwise, if the record is row-ordered (lsk_record_finalize), only
   // what proving `shard` touches: the per-row tables of its row range (device pointers are biased so that
   // kernels keep indexing by absolute row) plus the tables other rows gather from (outputs, depths,

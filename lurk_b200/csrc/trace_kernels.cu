@@ -467,6 +467,11 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
     bufs.emplace_back(ctx, arena_per * g);
     arena = bufs.back().p;
   }
+  // copies are collected first (tag: -1 = read by any trace kernel, f = read by func f's own trace only) and issued in
+  // waves below
+  struct Copy { uint32_t* dst; const uint32_t* src; size_t count; int tag; };
+  std::vector<Copy> copies;
+  int tag = -1;
   auto up_range = [&](const std::vector<uint32_t>& v, size_t first, size_t count) -> const uint32_t* {
     if (!count) return nullptr;
     if (grouped && count * 4 >= (64u << 10)) {
@@ -476,7 +481,7 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
       return arena + off - first;
     }
     bufs.emplace_back(ctx, count);
-    LSK_CUDA(cudaMemcpyAsync(bufs.back().p, v.data() + first, count * 4, cudaMemcpyHostToDevice, ctx->stream));
+    copies.push_back({bufs.back().p, v.data() + first, count, tag});
     h2d_bytes += count * 4;
     return bufs.back().p - first;
   };
@@ -488,9 +493,13 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
     size_t s = 0, e = n;
     if (sliced) s = std::min(n, (size_t)shard * shard_size), e = std::min(n, (size_t)(shard + 1) * shard_size);
     const size_t cnt = e - s;
+    const int self = (int)h_funcs.size();
+    tag = -1;
     d.outs = up(t.outs);
     d.depth = up(t.depth);
+    tag = t.invertible ? -1 : self;   // arguments are gathered by other funcs' rows only through `preimg` of an invertible func
     d.args = t.invertible || !sliced ? up(t.args) : up_range(t.args, s * t.in, cnt * t.in);
+    tag = self;
     d.provide = up_range(t.provide, 2 * s, 2 * cnt);
     d.req_off = up_range(t.req_off, s, cnt);
     d.hint_off = up_range(t.hint_off, s, cnt);
@@ -512,6 +521,7 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
     h_funcs.push_back(d);
   }
   h_mems.clear();
+  tag = -1;
   for (const MemTable& m : rec.mems) {
     DevMemTable d{};
     d.vals = up(m.vals);
@@ -529,19 +539,47 @@ void DeviceRecord::upload(lsk_ctx* ctx, const lsk_program& prog, const lsk_recor
     }
     comm_allgather(ctx, arena, arena_per * 4);
   }
+  // the copy stream: the side stream (behind everything the main stream has queued: the pool may hand out blocks that
+  // earlier kernels still use), or the main stream itself inside a device group
+  const bool async_up = !grouped && ctx->side && !getenv("LSK_NO_SIDE_STREAM");
+  cudaStream_t cs = async_up ? ctx->side : ctx->stream;
+  if (async_up) {
+    LSK_CUDA(cudaEventRecord(ctx->side_fork, ctx->stream));
+    LSK_CUDA(cudaStreamWaitEvent(cs, ctx->side_fork, 0));
+  }
+  auto h2d = [&](void* dst, const void* src, size_t bytes) {
+    LSK_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, cs));
+  };
   funcs.alloc(ctx, h_funcs.size());
-  if (!h_funcs.empty()) funcs.upload(h_funcs.data(), h_funcs.size());
+  if (!h_funcs.empty()) h2d(funcs.p, h_funcs.data(), h_funcs.size() * sizeof(DevFuncTable));
   mems.alloc(ctx, h_mems.size());
-  mems.upload(h_mems.data(), h_mems.size());
+  h2d(mems.p, h_mems.data(), h_mems.size() * sizeof(DevMemTable));
   program.alloc(ctx, prog.words.size());
-  program.upload(prog.words.data(), prog.words.size());
+  h2d(program.p, prog.words.data(), prog.words.size() * 4);
   if (rec.bytes_used && (!sliced || shard == 0)) {  // the byte table's main trace is non-empty in shard 0 only
     bytes.alloc(ctx, rec.bytes.size());
-    bytes.upload(rec.bytes.data(), rec.bytes.size());
+    h2d(bytes.p, rec.bytes.data(), rec.bytes.size() * 4);
     h2d_bytes += rec.bytes.size() * 4;
   } else {
     bytes.release();
   }
+  auto event = [&](cudaEvent_t& e) {
+    if (!e) LSK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    LSK_CUDA(cudaEventRecord(e, cs));
+  };
+  for (const Copy& c : copies)
+    if (c.tag < 0) h2d(c.dst, c.src, c.count * 4);
+  event(common_ready);
+  func_ready.resize(h_funcs.size(), nullptr);
+  size_t at = 0;   // copies are in func order
+  for (size_t f = 0; f < h_funcs.size(); f++) {
+    bool any = false;
+    for (; at < copies.size() && copies[at].tag <= (int)f; at++)
+      if (copies[at].tag == (int)f) h2d(copies[at].dst, copies[at].src, copies[at].count * 4), any = true;
+    if (any) event(func_ready[f]);
+    else if (func_ready[f]) cudaEventDestroy(func_ready[f]), func_ready[f] = nullptr;
+  }
+  event(all_ready);
 }
 
 void func_trace_dev(lsk_ctx* ctx, const lsk_program& prog, const DeviceRecord& drec, uint32_t func, uint32_t row_start,
@@ -550,6 +588,7 @@ void func_trace_dev(lsk_ctx* ctx, const lsk_program& prog, const DeviceRecord& d
   uint32_t width = prog.width(func);
   LSK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)height * width * 4, ctx->stream));
   if (!height) return;
+  drec.wait_func(ctx, func);   // the tables this trace reads may still be on their way (DeviceRecord::upload)
   uint32_t log_h = log2_exact(height);
   unsigned grid = div_up(height, 128);
   const uint32_t* w = drec.program.p;
@@ -581,6 +620,7 @@ void mem_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, uint32_t mem_idx, uin
   const DevMemTable& mt = drec.h_mems[mem_idx];
   LSK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)height * (4 + mt.len) * 4, ctx->stream));
   if (!mt.rows) return;
+  drec.wait_common(ctx);
   uint32_t log_h = log2_exact(height);
   ProfScope ps(ctx, PT_TRACE, 1, 8.0 * mt.rows * (4 + mt.len));
   if (layout == TraceLayout::ColMajorBitrevMont)
@@ -593,6 +633,7 @@ void mem_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, uint32_t mem_idx, uin
 void bytes_trace_dev(lsk_ctx* ctx, const DeviceRecord& drec, bool real, TraceLayout layout, uint32_t* d_out) {
   LSK_CUDA(cudaMemsetAsync(d_out, 0, (size_t)65536 * 13 * 4, ctx->stream));
   if (!real || !drec.bytes.p) return;
+  drec.wait_common(ctx);
   ProfScope ps(ctx, PT_TRACE, 1, 65536.0 * 25 * 4);
   if (layout == TraceLayout::ColMajorBitrevMont)
     bytes_trace_kernel<true><<<65536 / 256, 256, 0, ctx->stream>>>(drec.bytes.p, d_out);

@@ -447,6 +447,26 @@ def test_compiled_constraint_programs_match_the_interpreter(monkeypatch):
     m1.verify(m1.setup()[1], compiled)
 
 
+def test_side_stream_does_not_change_the_proof(monkeypatch):
+    # prover.cu / trace_kernels.cu: the record tables travel on the context's second stream in waves (trace kernels wait on
+    # per-func events), and the permutation-row / quotient launches of chips with a handful of rows run there beside the
+    # tall chips.  Same record, second stream on and off (LSK_NO_SIDE_STREAM=1: everything on one stream): the same words,
+    # repeatedly (a race would show up as a differing or rejected proof).
+    from lurk_b200.programs import hash_toplevel
+    top = hash_toplevel()
+    q = QueryRecord.new(top)
+    execute_by_name(top, "cons_chain", [700], q)          # hash3/4/5 and helper chips of a few rows next to a tall chip
+    m = new_machine(top, "cons_chain")
+    pk, vk = m.setup()
+    monkeypatch.setenv("LSK_NO_SIDE_STREAM", "1")
+    one_stream = m.prove(pk, Shard.new(q))
+    monkeypatch.delenv("LSK_NO_SIDE_STREAM")
+    for _ in range(4):
+        two_streams = m.prove(pk, Shard.new(q))
+        assert np.array_equal(one_stream.words, two_streams.words)
+    m.verify(vk, two_streams)
+
+
 @pytest.mark.parametrize("a,b", [(10**18 + 7, 12345), (123456789, 0)])
 def test_lurk_misc_u64_funcs_prove_bit_exact(oracle, a, b):
     # src/core/misc.rs:32-128 (pointer-taking u64 / big-num / digest_equal funcs; widths pinned by the reference,

@@ -35,6 +35,16 @@ constexpr uint32_t R2 = 1172168163u;        // 2^64 mod P
 constexpr uint32_t GEN = 31u;               // multiplicative generator (coset shift)
 constexpr uint32_t TWO_ADIC_GEN_27 = 0x1a427a41u;  // 31^((p-1)/2^27)
 
+// Pipe placement of the PLAIN additions (tools/perm_variants.cu).  ptxas emits a + b either as IADD3 (ALU pipe) or as
+// IMAD.IADD (multiply pipe) by its own balancing; on B200 the multiply pipe is the bound of every hashing kernel, so
+// LSK_ALU_ADD forces chosen additions onto the ALU pipe by writing them as min(a + b, g_lsk_ones): an add + min pair with
+// an operand ptxas cannot fold (a __constant__ it does not know the value of), which it fuses into one VIADDMNMX.
+// bit 0: fadd, bit 1: fsub, bit 2: the high-word subtraction of mont_reduce.
+#if defined(__CUDACC__) && !defined(__CUDACC_RTC__) && defined(LSK_ALU_ADD)
+static __constant__ uint32_t g_lsk_ones = 0xffffffffu;
+#define LSK_ALU_PLUS(a, b) min((uint32_t)((a) + (b)), g_lsk_ones)
+#define LSK_ALU_MINUS(a, b) min((uint32_t)((a) - (b)), g_lsk_ones)
+#endif
 LSK_HD uint32_t mont_reduce(uint64_t x) {
   uint32_t t = (uint32_t)x * PINV;
 #if defined(__CUDA_ARCH__)
@@ -43,7 +53,11 @@ LSK_HD uint32_t mont_reduce(uint64_t x) {
   uint32_t hu = (uint32_t)(((uint64_t)t * P) >> 32);
 #endif
   uint32_t hx = (uint32_t)(x >> 32);
+#if defined(__CUDA_ARCH__) && defined(LSK_ALU_PLUS) && (LSK_ALU_ADD & 4)
+  uint32_t r = LSK_ALU_MINUS(hx, hu);
+#else
   uint32_t r = hx - hu;
+#endif
 #if defined(__CUDA_ARCH__)
   return min(r, r + P);  // r wrapped iff hx < hu; one fused add+min (VIADDMNMX) on the ALU pipe
 #else
@@ -59,7 +73,11 @@ LSK_HD uint32_t mont_reduce(uint64_t x) {
 // ~19 k pipe-cycles per width-16 permutation per warp, are the roofline of every hashing kernel.
 LSK_HD uint32_t fmul(uint32_t a, uint32_t b) { return mont_reduce((uint64_t)a * b); }
 LSK_HD uint32_t fadd(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__) && defined(LSK_ALU_PLUS) && (LSK_ALU_ADD & 1)
+  uint32_t s = LSK_ALU_PLUS(a, b);
+#else
   uint32_t s = a + b;
+#endif
 #if defined(__CUDA_ARCH__)
   return min(s, s - P);
 #else
@@ -67,7 +85,11 @@ LSK_HD uint32_t fadd(uint32_t a, uint32_t b) {
 #endif
 }
 LSK_HD uint32_t fsub(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__) && defined(LSK_ALU_PLUS) && (LSK_ALU_ADD & 2)
+  uint32_t s = LSK_ALU_MINUS(a, b);
+#else
   uint32_t s = a - b;
+#endif
 #if defined(__CUDA_ARCH__)
   return min(s, s + P);
 #else

@@ -61,7 +61,7 @@ void lsk_ctx_destroy(lsk_ctx* ctx) {
   for (auto e : ctx->prof.pool) cudaEventDestroy(e);
   ctx->pool.trim();
   cudaStreamDestroy(ctx->stream);
-  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (void* h : ctx->pinned) if (h) cudaFreeHost(h);
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->side_fork) cudaEventDestroy(ctx->side_fork);
   if (ctx->side_join) cudaEventDestroy(ctx->side_join);

@@ -112,8 +112,8 @@ struct lsk_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t side = nullptr;      // second stream: the single-CTA launches of a shard's tiny chips run beside the big ones
   cudaEvent_t side_fork = nullptr, side_join = nullptr;
-  void* pinned = nullptr;           // page-locked host scratch (pinned_scratch): results the host consumes while kernels run
-  size_t pinned_bytes = 0;
+  void* pinned[2] = {nullptr, nullptr};   // page-locked host scratch (pinned_scratch): results the host consumes while kernels run
+  size_t pinned_bytes[2] = {0, 0};
   int sm_count = 148;
   lsk::MemPool pool;
   void* ntt_tables = nullptr;   // lsk::NttTables (ntt.cu): twiddle / coset-scale tables, built lazily per size
@@ -121,20 +121,21 @@ struct lsk_ctx {
 };
 
 namespace lsk {
-// page-locked host scratch of at least `bytes`, owned by the context (valid until the next call asks for more)
-inline void* pinned_scratch(lsk_ctx* ctx, size_t bytes) {
-  if (bytes > ctx->pinned_bytes) {
-    if (ctx->pinned) {
+// page-locked host scratch `slot` of at least `bytes`, owned by the context (valid until a later call asks for more in the
+// same slot)
+inline void* pinned_scratch(lsk_ctx* ctx, int slot, size_t bytes) {
+  if (bytes > ctx->pinned_bytes[slot]) {
+    if (ctx->pinned[slot]) {
       cudaStreamSynchronize(ctx->stream);
-      cudaFreeHost(ctx->pinned);
-      ctx->pinned = nullptr;
-      ctx->pinned_bytes = 0;
+      cudaFreeHost(ctx->pinned[slot]);
+      ctx->pinned[slot] = nullptr;
+      ctx->pinned_bytes[slot] = 0;
     }
     size_t want = bytes + bytes / 2;
-    if (cudaHostAlloc(&ctx->pinned, want, cudaHostAllocDefault) != cudaSuccess) lsk::fail(LSK_ERR_CUDA, "cudaHostAlloc(%zu) failed", want);
-    ctx->pinned_bytes = want;
+    if (cudaHostAlloc(&ctx->pinned[slot], want, cudaHostAllocDefault) != cudaSuccess) lsk::fail(LSK_ERR_CUDA, "cudaHostAlloc(%zu) failed", want);
+    ctx->pinned_bytes[slot] = want;
   }
-  return ctx->pinned;
+  return ctx->pinned[slot];
 }
 // Work queued between fork() and join() on ctx->side runs concurrently with what the main stream does in between.
 // While `active`, ctx->stream IS the side stream (every helper launches on ctx->stream), so the caller brackets exactly

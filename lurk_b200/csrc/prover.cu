@@ -464,7 +464,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   }
   round_end[2] = nopen;
   DevBuf<Ext> opened(ctx, nopen);
-  Ext* h_open = (Ext*)pinned_scratch(ctx, (nopen + nchips) * sizeof(Ext));   // page-locked: the copies below are asynchronous
+  Ext* h_open = (Ext*)pinned_scratch(ctx, 0, (nopen + nchips) * sizeof(Ext));   // page-locked: the copies below are asynchronous
   Ext* h_cums = h_open + nopen;
   struct Events {
     cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
@@ -721,21 +721,22 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   }
   std::vector<uint32_t> indices(m.num_queries);
   for (auto& ix : indices) ix = ch.sample_bits(log_max);
-  std::vector<uint32_t> gathered((size_t)m.num_queries * wpq);
-  {
-    DevBuf<QuerySeg> d_segs(ctx, segs.size());
-    DevBuf<uint32_t> d_idx(ctx, indices.size()), d_out(ctx, gathered.size());
-    d_segs.upload(segs.data(), segs.size());
-    d_idx.upload(indices.data(), indices.size());
-    query_assemble_dev(ctx, d_segs.p, (uint32_t)segs.size(), d_idx.p, m.num_queries, wpq, d_out.p);
-    if (grouped) comm_allreduce_u32(ctx, d_out.p, gathered.size());
-    d_out.download(gathered.data(), gathered.size());
-    LSK_CUDA(cudaStreamSynchronize(st));
-    m.last_d2h += gathered.size() * 4;
-  }
+  // the query words (the bulk of the proof: 100 queries x ~6.5 k words for a Lurk shard) are assembled on the device and
+  // land in page-locked memory while the host writes the head of the shard proof
+  const size_t ngathered = (size_t)m.num_queries * wpq;
+  uint32_t* gathered = (uint32_t*)pinned_scratch(ctx, 1, ngathered * 4);
+  DevBuf<QuerySeg> d_segs(ctx, segs.size());
+  DevBuf<uint32_t> d_idx(ctx, indices.size()), d_out(ctx, ngathered);
+  d_segs.upload(segs.data(), segs.size());
+  d_idx.upload(indices.data(), indices.size());
+  query_assemble_dev(ctx, d_segs.p, (uint32_t)segs.size(), d_idx.p, m.num_queries, wpq, d_out.p);
+  if (grouped) comm_allreduce_u32(ctx, d_out.p, ngathered);
+  d_out.download(gathered, ngathered);
+  m.last_d2h += ngathered * 4;
 
   pt.mark("queries");
   // ---- serialise (word-for-word the oracle's / verifier's layout, canonical values)
+  W.reserve(W.size() + 64 + 4 * nopen + 16 * nchips + m.num_pv + 8 * (size_t)nlayers + ngathered);
   W.push_back(sd.shard);
   for (int k = 0; k < 8; k++) W.push_back(sd.main_root[k]);
   for (int k = 0; k < 8; k++) W.push_back(perm_root[k]);
@@ -767,7 +768,8 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   push_ext(W, final_poly);
   W.push_back(pow_witness);
   W.push_back(m.num_queries);
-  W.insert(W.end(), gathered.begin(), gathered.end());
+  LSK_CUDA(cudaStreamSynchronize(st));   // the query words have arrived (segs / indices stay alive until here)
+  W.insert(W.end(), gathered, gathered + ngathered);
   pt.mark("serialise");
 }
 

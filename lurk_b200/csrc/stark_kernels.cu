@@ -5,6 +5,7 @@
 // reads 128 contiguous bytes of each column) and are HBM-bound; the per-row scalar work (one
 // extension-field inversion, a few dozen modmuls) rides under the loads.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "fri.cuh"
@@ -341,6 +342,7 @@ void open_batch_dev(lsk_ctx* ctx, const std::vector<OpenMat>& mats, unsigned log
 }
 
 // ---- FRI: reduced openings, fold, grind --------------------------------------------------------------------
+template <int COLS>   // columns per loop iteration (each pair of columns shares one conditional subtraction)
 __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* __restrict__ mats, uint32_t nmats,
                                                                unsigned lh, uint32_t g, uint32_t w, Ext z0, Ext z1,
                                                                const Ext* __restrict__ apow, size_t row_begin,
@@ -355,8 +357,21 @@ __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* _
     uint64_t s0 = 0, s1 = 0, s2 = 0, s3 = 0;   // raw 64-bit products below P * 2^32, one reduction per matrix
     const uint32_t* p = m.p + r;
     uint32_t c = 0;
-#pragma unroll 2
-    for (; c + 2 <= m.w; c += 2) {   // two terms per conditional subtraction (acc + 2 products < 2^64)
+    for (; c + COLS <= m.w; c += COLS) {   // the loads of COLS columns in flight together
+      uint32_t v[COLS];
+#pragma unroll
+      for (int k = 0; k < COLS; k++) v[k] = __ldg(p + (size_t)(c + k) * m.stride);
+#pragma unroll
+      for (int k = 0; k < COLS; k += 2) {   // two terms per conditional subtraction (acc + 2 products < 2^64)
+        const Ext ap = apow[c + k], aq = apow[c + k + 1];
+        s0 = acc_reduce64(s0 + (uint64_t)ap.c[0] * v[k] + (uint64_t)aq.c[0] * v[k + 1]);
+        s1 = acc_reduce64(s1 + (uint64_t)ap.c[1] * v[k] + (uint64_t)aq.c[1] * v[k + 1]);
+        s2 = acc_reduce64(s2 + (uint64_t)ap.c[2] * v[k] + (uint64_t)aq.c[2] * v[k + 1]);
+        s3 = acc_reduce64(s3 + (uint64_t)ap.c[3] * v[k] + (uint64_t)aq.c[3] * v[k + 1]);
+      }
+    }
+#pragma unroll 1
+    for (; c + 2 <= m.w; c += 2) {
       const Ext ap = apow[c], aq = apow[c + 1];
       const uint32_t v = p[(size_t)c * m.stride], u = p[(size_t)(c + 1) * m.stride];
       s0 = acc_reduce64(s0 + (uint64_t)ap.c[0] * v + (uint64_t)aq.c[0] * u);
@@ -391,7 +406,14 @@ void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats
   {
     ProfScope ps(ctx, PT_REDUCE_OPEN, 1, algorithmic_bytes * (double)(e - b) / (double)n);
     Ext z1 = emul_base(zeta, two_adic_generator(lh - 1));
-    reduce_openings_kernel<<<div_up(e - b, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
+    static const int cols = [] { const char* e = getenv("LSK_RO_COLS"); return e ? atoi(e) : 8; }();
+    if (cols >= 8) reduce_openings_kernel<8><<<div_up(e - b, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
+                                                                        two_adic_generator(lh), zeta, z1, alpha_pows_dev,
+                                                                        b, e, ro);
+    else if (cols >= 4) reduce_openings_kernel<4><<<div_up(e - b, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
+                                                                        two_adic_generator(lh), zeta, z1, alpha_pows_dev,
+                                                                        b, e, ro);
+    else reduce_openings_kernel<2><<<div_up(e - b, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
                                                                         two_adic_generator(lh), zeta, z1, alpha_pows_dev,
                                                                         b, e, ro);
     LSK_CUDA(cudaGetLastError());

@@ -406,7 +406,9 @@ void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats
   {
     ProfScope ps(ctx, PT_REDUCE_OPEN, 1, algorithmic_bytes * (double)(e - b) / (double)n);
     Ext z1 = emul_base(zeta, two_adic_generator(lh - 1));
-    static const int cols = [] { const char* e = getenv("LSK_RO_COLS"); return e ? atoi(e) : 8; }();
+    // columns in flight per loop iteration, measured on B200 (Lurk fib 2^20, ms per prove): 2 -> 3.50, 4 -> 2.76, 8 -> 3.42
+    // (round 1's loop, two columns and generic loads: 4.27); LSK_RO_COLS overrides
+    static const int cols = [] { const char* e = getenv("LSK_RO_COLS"); return e ? atoi(e) : 4; }();
     if (cols >= 8) reduce_openings_kernel<8><<<div_up(e - b, 256), 256, 0, ctx->stream>>>(mats_dev, nmats, lh, to_mont(GEN),
                                                                         two_adic_generator(lh), zeta, z1, alpha_pows_dev,
                                                                         b, e, ro);

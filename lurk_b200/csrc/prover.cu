@@ -466,9 +466,13 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   DevBuf<Ext> opened(ctx, nopen);
   Ext* h_open = (Ext*)pinned_scratch(ctx, 0, (nopen + nchips) * sizeof(Ext));   // page-locked: the copies below are asynchronous
   Ext* h_cums = h_open + nopen;
-  struct Events {
-    cudaEvent_t e[3] = {nullptr, nullptr, nullptr};
-    ~Events() { for (auto x : e) if (x) cudaEventDestroy(x); }
+  struct Events {   // (round, log height) -> its values have reached the host
+    std::map<std::pair<int, unsigned>, cudaEvent_t> by_group;
+    cudaEvent_t last = nullptr;
+    ~Events() {
+      for (auto& kv : by_group) cudaEventDestroy(kv.second);
+      if (last) cudaEventDestroy(last);
+    }
   } open_done;
   const bool grouped = comm_active(ctx);
   if (grouped) opened.zero();   // every value is computed by exactly one rank and summed over the group
@@ -496,21 +500,33 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
         bary_weights_dev(ctx, kv.first, zeta, w.first.p);
         bary_weights_dev(ctx, kv.first, emul_base(zeta, two_adic_generator(kv.first)), w.second.p);
       }
+      // per round, tallest chips first = the order the transcript observes them in; one event per (round, height)
       size_t lo = 0;
       for (int r = 0; r < 3; r++) {
         const size_t hi = round_end[r];
-        for (auto& kv : by_logn) {
+        for (auto kv = by_logn.rbegin(); kv != by_logn.rend(); ++kv) {
           std::vector<OpenMat> part;
-          for (auto& om : kv.second)
+          for (auto& om : kv->second)
             if (om.out_off >= lo && om.out_off < hi) part.push_back(om);
-          open_batch_dev(ctx, part, kv.first, wts[kv.first].first.p, wts[kv.first].second.p, opened.p);
+          if (part.empty()) continue;
+          open_batch_dev(ctx, part, kv->first, wts[kv->first].first.p, wts[kv->first].second.p, opened.p);
+          // the group's values: runs of adjacent matrices ([col][point] pairs, 2 w values each)
+          std::sort(part.begin(), part.end(), [](const OpenMat& a, const OpenMat& b) { return a.out_off < b.out_off; });
+          for (size_t i = 0; i < part.size();) {
+            size_t b0 = part[i].out_off, e0 = b0 + 2 * (size_t)part[i].w;
+            for (i++; i < part.size() && part[i].out_off == e0; i++) e0 += 2 * (size_t)part[i].w;
+            LSK_CUDA(cudaMemcpyAsync(h_open + b0, opened.p + b0, (e0 - b0) * sizeof(Ext), cudaMemcpyDeviceToHost, st));
+          }
+          cudaEvent_t ev = nullptr;
+          LSK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+          LSK_CUDA(cudaEventRecord(ev, st));
+          open_done.by_group[{r, kv->first}] = ev;
         }
-        if (hi > lo) LSK_CUDA(cudaMemcpyAsync(h_open + lo, opened.p + lo, (hi - lo) * sizeof(Ext), cudaMemcpyDeviceToHost, st));
-        if (r == 2) LSK_CUDA(cudaMemcpyAsync(h_cums, cums.p, nchips * sizeof(Ext), cudaMemcpyDeviceToHost, st));
-        LSK_CUDA(cudaEventCreateWithFlags(&open_done.e[r], cudaEventDisableTiming));
-        LSK_CUDA(cudaEventRecord(open_done.e[r], st));
         lo = hi;
       }
+      LSK_CUDA(cudaMemcpyAsync(h_cums, cums.p, nchips * sizeof(Ext), cudaMemcpyDeviceToHost, st));
+      LSK_CUDA(cudaEventCreateWithFlags(&open_done.last, cudaEventDisableTiming));
+      LSK_CUDA(cudaEventRecord(open_done.last, st));
       by_logn.clear();
     }
     for (auto& kv : by_logn) {
@@ -577,12 +593,18 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     rounds.push_back(std::move(rq));
   }
   for (auto& rd : rounds) {
-    if (open_done.e[rd.wait]) LSK_CUDA(cudaEventSynchronize(open_done.e[rd.wait]));
-    for (auto& mt : rd.mats)
+    unsigned waited = ~0u;
+    for (auto& mt : rd.mats) {
+      if (mt.lh - 1 != waited) {   // matrices come tallest first: one wait per height
+        auto ev = open_done.by_group.find({rd.wait, mt.lh - 1});
+        if (ev != open_done.by_group.end()) LSK_CUDA(cudaEventSynchronize(ev->second));
+        waited = mt.lh - 1;
+      }
       for (uint32_t p = 0; p < mt.npoints; p++)
         for (uint32_t c = 0; c < mt.w; c++) ch.observe(h_open[mt.open_off + 2 * c + p]);
+    }
   }
-  if (open_done.e[2]) LSK_CUDA(cudaEventSynchronize(open_done.e[2]));   // (the cumulative sums ride behind the last round)
+  if (open_done.last) LSK_CUDA(cudaEventSynchronize(open_done.last));   // (the cumulative sums ride behind the last group)
   Ext fri_alpha = ch.sample_ext();
 
   // ---- reduced openings per LDE height

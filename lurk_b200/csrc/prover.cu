@@ -468,9 +468,11 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   Ext* h_cums = h_open + nopen;
   struct Events {   // (round, log height) -> its values have reached the host
     std::map<std::pair<int, unsigned>, cudaEvent_t> by_group;
+    cudaEvent_t by_round[3] = {nullptr, nullptr, nullptr};   // device group: a round arrives as a whole
     cudaEvent_t last = nullptr;
     ~Events() {
       for (auto& kv : by_group) cudaEventDestroy(kv.second);
+      for (cudaEvent_t e : by_round) if (e) cudaEventDestroy(e);
       if (last) cudaEventDestroy(last);
     }
   } open_done;
@@ -488,86 +490,77 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       v.push_back(OpenMat{perm_lde[i].p, n2, 4 * (uint32_t)c.perm_width(), (uint32_t)oo[i].perm, 0});
       for (int j = 0; j < 2; j++) v.push_back(OpenMat{quot_lde[2 * i + j].p, n2, 4, (uint32_t)oo[i].quot[j], 1});
     }
-    if (!grouped) {
-      // Weights of every height first, then the openings round by round (preprocessed + main, permutation, quotient);
-      // each round's values are copied out behind its kernels.  The host feeds a round to the transcript -- 7 000
-      // dependent Poseidon2 permutations for a Lurk shard, ~5 ms on a core -- while the device computes the next one.
-      std::map<unsigned, std::pair<DevBuf<Ext>, DevBuf<Ext>>> wts;
-      for (auto& kv : by_logn) {
-        auto& w = wts[kv.first];
-        w.first.alloc(ctx, (size_t)1 << kv.first);
-        w.second.alloc(ctx, (size_t)1 << kv.first);
-        bary_weights_dev(ctx, kv.first, zeta, w.first.p);
-        bary_weights_dev(ctx, kv.first, emul_base(zeta, two_adic_generator(kv.first)), w.second.p);
-      }
-      // per round, tallest chips first = the order the transcript observes them in; one event per (round, height)
-      size_t lo = 0;
-      for (int r = 0; r < 3; r++) {
-        const size_t hi = round_end[r];
-        for (auto kv = by_logn.rbegin(); kv != by_logn.rend(); ++kv) {
-          std::vector<OpenMat> part;
-          for (auto& om : kv->second)
-            if (om.out_off >= lo && om.out_off < hi) part.push_back(om);
-          if (part.empty()) continue;
-          open_batch_dev(ctx, part, kv->first, wts[kv->first].first.p, wts[kv->first].second.p, opened.p);
-          // the group's values: runs of adjacent matrices ([col][point] pairs, 2 w values each)
-          std::sort(part.begin(), part.end(), [](const OpenMat& a, const OpenMat& b) { return a.out_off < b.out_off; });
-          for (size_t i = 0; i < part.size();) {
-            size_t b0 = part[i].out_off, e0 = b0 + 2 * (size_t)part[i].w;
-            for (i++; i < part.size() && part[i].out_off == e0; i++) e0 += 2 * (size_t)part[i].w;
-            LSK_CUDA(cudaMemcpyAsync(h_open + b0, opened.p + b0, (e0 - b0) * sizeof(Ext), cudaMemcpyDeviceToHost, st));
-          }
-          cudaEvent_t ev = nullptr;
-          LSK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-          LSK_CUDA(cudaEventRecord(ev, st));
-          open_done.by_group[{r, kv->first}] = ev;
-        }
-        lo = hi;
-      }
-      LSK_CUDA(cudaMemcpyAsync(h_cums, cums.p, nchips * sizeof(Ext), cudaMemcpyDeviceToHost, st));
-      LSK_CUDA(cudaEventCreateWithFlags(&open_done.last, cudaEventDisableTiming));
-      LSK_CUDA(cudaEventRecord(open_done.last, st));
-      by_logn.clear();
-    }
+    // Weights of every height first (in a device group the tall ones are a collective: every rank calls), then the
+    // openings round by round (preprocessed + main, permutation, quotient), tallest chips first = the order the
+    // transcript observes them in.  Each (round, height) group's values are copied to page-locked memory behind its
+    // kernels: the host feeds them to the transcript -- 7 000 dependent Poseidon2 permutations for a Lurk shard, ~5 ms
+    // on a core -- while the device computes the next group.  In a device group every value is computed by one rank
+    // (tall matrices: a block of the concatenated column list per rank; the rest: rank 0) and a round is summed over the
+    // group before it leaves the device.
+    std::map<unsigned, std::pair<DevBuf<Ext>, DevBuf<Ext>>> wts;
     for (auto& kv : by_logn) {
-      const unsigned logn = kv.first;
-      const size_t n = (size_t)1 << logn;
-      if (grouped) {
-        // tall matrices: this rank's block of the concatenated column list; the rest: rank 0 alone
+      auto& w = wts[kv.first];
+      w.first.alloc(ctx, (size_t)1 << kv.first);
+      w.second.alloc(ctx, (size_t)1 << kv.first);
+      bary_weights_dev(ctx, kv.first, zeta, w.first.p);
+      bary_weights_dev(ctx, kv.first, emul_base(zeta, two_adic_generator(kv.first)), w.second.p);
+    }
+    auto new_event = [&]() {
+      cudaEvent_t ev = nullptr;
+      LSK_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+      LSK_CUDA(cudaEventRecord(ev, st));
+      return ev;
+    };
+    size_t lo = 0;
+    for (int r = 0; r < 3; r++) {
+      const size_t hi = round_end[r];
+      for (auto kv = by_logn.rbegin(); kv != by_logn.rend(); ++kv) {
+        const unsigned logn = kv->first;
+        std::vector<OpenMat> part;
+        for (auto& om : kv->second)
+          if (om.out_off >= lo && om.out_off < hi) part.push_back(om);
+        if (part.empty()) continue;
         std::vector<OpenMat> mine;
-        if (comm_splits(ctx, logn + 1)) {
+        if (!grouped) {
+          mine = part;
+        } else if (comm_splits(ctx, logn + 1)) {
           size_t total = 0, b, e, at = 0;
-          for (auto& om : kv.second) total += om.w;
+          for (auto& om : part) total += om.w;
           comm_range(ctx, total, &b, &e);
-          for (auto& om : kv.second) {
-            const size_t lo = std::max(b, at), hi = std::min(e, at + om.w);
-            if (lo < hi) {
-              OpenMat part = om;
-              part.p += (lo - at) * om.stride;
-              part.w = (uint32_t)(hi - lo);
-              part.out_off += 2 * (uint32_t)(lo - at);
-              mine.push_back(part);
+          for (auto& om : part) {
+            const size_t l2 = std::max(b, at), h2 = std::min(e, at + om.w);
+            if (l2 < h2) {
+              OpenMat piece = om;
+              piece.p += (l2 - at) * om.stride;
+              piece.w = (uint32_t)(h2 - l2);
+              piece.out_off += 2 * (uint32_t)(l2 - at);
+              mine.push_back(piece);
             }
             at += om.w;
           }
         } else if (ctx->comm->rank == 0) {
-          mine = kv.second;
+          mine = part;
         }
-        kv.second.swap(mine);
-        if (kv.second.empty() && !comm_splits(ctx, logn)) continue;   // (split weights are a collective)
+        open_batch_dev(ctx, mine, logn, wts[logn].first.p, wts[logn].second.p, opened.p);
+        if (grouped) continue;   // the round leaves the device as a whole, after the all-reduce below
+        // the group's values: runs of adjacent matrices ([col][point] pairs, 2 w values each)
+        std::sort(part.begin(), part.end(), [](const OpenMat& a, const OpenMat& b) { return a.out_off < b.out_off; });
+        for (size_t i = 0; i < part.size();) {
+          size_t b0 = part[i].out_off, e0 = b0 + 2 * (size_t)part[i].w;
+          for (i++; i < part.size() && part[i].out_off == e0; i++) e0 += 2 * (size_t)part[i].w;
+          LSK_CUDA(cudaMemcpyAsync(h_open + b0, opened.p + b0, (e0 - b0) * sizeof(Ext), cudaMemcpyDeviceToHost, st));
+        }
+        open_done.by_group[{r, logn}] = new_event();
       }
-      DevBuf<Ext> w0(ctx, n), w1(ctx, n);
-      bary_weights_dev(ctx, logn, zeta, w0.p);
-      bary_weights_dev(ctx, logn, emul_base(zeta, two_adic_generator(logn)), w1.p);
-      open_batch_dev(ctx, kv.second, logn, w0.p, w1.p, opened.p);
-      // the weight buffers are freed stream-ordered after the kernels that read them
+      if (grouped && hi > lo) {
+        comm_allreduce_u32(ctx, (uint32_t*)(opened.p + lo), 4 * (hi - lo));
+        LSK_CUDA(cudaMemcpyAsync(h_open + lo, opened.p + lo, (hi - lo) * sizeof(Ext), cudaMemcpyDeviceToHost, st));
+        open_done.by_round[r] = new_event();
+      }
+      lo = hi;
     }
-  }
-  if (grouped) {
-    comm_allreduce_u32(ctx, (uint32_t*)opened.p, 4 * nopen);
-    opened.download(h_open, nopen);
-    cums.download(h_cums, nchips);
-    LSK_CUDA(cudaStreamSynchronize(st));
+    LSK_CUDA(cudaMemcpyAsync(h_cums, cums.p, nchips * sizeof(Ext), cudaMemcpyDeviceToHost, st));
+    open_done.last = new_event();
   }
   m.last_d2h += (nopen + nchips) * sizeof(Ext);
   pt.mark("openings");
@@ -598,6 +591,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       if (mt.lh - 1 != waited) {   // matrices come tallest first: one wait per height
         auto ev = open_done.by_group.find({rd.wait, mt.lh - 1});
         if (ev != open_done.by_group.end()) LSK_CUDA(cudaEventSynchronize(ev->second));
+        else if (open_done.by_round[rd.wait]) LSK_CUDA(cudaEventSynchronize(open_done.by_round[rd.wait]));
         waited = mt.lh - 1;
       }
       for (uint32_t p = 0; p < mt.npoints; p++)

@@ -33,9 +33,22 @@ LSK_D void store_digest(uint32_t* p, const uint32_t* d) {
 //   if `children`: node = compress(children[0], children[1]); with a row digest present the result
 //   is compress(node, row digest) (mixed-height injection).
 // Result in st[0..8).
+//   `rowdig` (tail levels, see tail_rows_kernel): the row digest was computed beforehand -- no sponge steps here.
 LSK_D void merkle_digest(const uint32_t* const* __restrict__ cols, uint32_t ncols, size_t r,
                          const uint32_t* __restrict__ packed_row, const uint32_t* __restrict__ children,
-                         uint32_t (&st)[16]) {
+                         uint32_t (&st)[16], const uint32_t* __restrict__ rowdig = nullptr) {
+  if (rowdig) {
+    if (!children) {
+      load_digest(rowdig, st);
+      return;
+    }
+    load_digest(children, st);
+    load_digest(children + 8, st + 8);
+    p2_permute<16>(st);
+    load_digest(rowdig, st + 8);
+    p2_permute<16>(st);
+    return;
+  }
   const uint32_t nabs = packed_row ? 1u : (ncols + 7) / 8;
   const uint32_t total = nabs + (children ? (nabs ? 2u : 1u) : 0u);
   uint32_t rd[8];
@@ -70,8 +83,14 @@ LSK_D void merkle_digest(const uint32_t* const* __restrict__ cols, uint32_t ncol
 // the same ncols / packed / children-ness.
 LSK_D uint32_t merkle_digest_coop(const uint32_t* const* __restrict__ cols, uint32_t ncols, size_t r,
                                   const uint32_t* __restrict__ packed_row, const uint32_t* __restrict__ children,
-                                  const Coop16& k, unsigned lane) {
+                                  const Coop16& k, unsigned lane, const uint32_t* __restrict__ rowdig = nullptr) {
   const unsigned g = lane & 15;
+  if (rowdig) {   // the row digest was computed beforehand (tail_rows_kernel)
+    if (!children) return g < 8 ? rowdig[g] : 0u;
+    uint32_t s = coop16_permute(children[g], k, lane);
+    if (g >= 8) s = rowdig[g - 8];
+    return coop16_permute(s, k, lane);
+  }
   const uint32_t nabs = packed_row ? 1u : (ncols + 7) / 8;
   const uint32_t total = nabs + (children ? (nabs ? 2u : 1u) : 0u);
   uint32_t s = 0, rd = 0;
@@ -110,6 +129,7 @@ struct SubtreeArgs {
   uint32_t off[ST_LEVELS + 1];           // digest offsets of layers l0 .. l0 + levels
   uint32_t inj_first[ST_LEVELS + 1];     // column-list range of the height group of layer l0 + k
   uint32_t inj_ncols[ST_LEVELS + 1];     // (k = 0: the leaf group in LEAF mode)
+  const uint32_t* rowdig;                // digests of the injected rows, laid out like `nodes` (tail_rows_kernel), or null
   FriChallenge fc;                       // set on the launch that produces a FRI layer's root
 };
 enum { ST_NODES = 0, ST_LEAVES = 1, ST_FRI_LEAVES = 2 };
@@ -125,7 +145,8 @@ template <int MODE>
 LSK_D void subtree_build(uint32_t* __restrict__ nodes, const uint32_t* const* __restrict__ cols,
                          const uint32_t* __restrict__ fri_vals, uint32_t levels, uint32_t log_in,
                          const uint32_t* __restrict__ off, const uint32_t* __restrict__ inj_first,
-                         const uint32_t* __restrict__ inj_ncols, size_t in0, const Coop16& ck, uint32_t* sdig) {
+                         const uint32_t* __restrict__ inj_ncols, size_t in0, const Coop16& ck, uint32_t* sdig,
+                         const uint32_t* __restrict__ rowdig = nullptr) {
   const uint32_t nin = 1u << log_in;
   const unsigned lane = threadIdx.x & 31;
   const uint32_t k0 = MODE == ST_NODES ? 1u : 0u;
@@ -137,6 +158,7 @@ LSK_D void subtree_build(uint32_t* __restrict__ nodes, const uint32_t* const* __
     const bool packed = MODE == ST_FRI_LEAVES && k == 0;
     const uint32_t ncols = packed || !inj_ncols ? 0u : inj_ncols[k];
     const uint32_t* const* gcols = inj_first ? cols + inj_first[k] : cols;
+    const uint32_t* rd_layer = rowdig && ncols ? rowdig + (size_t)off[k] * 8 : nullptr;
     uint32_t* scur = sdig + (k & 1) * (512 * 8);
     const uint32_t* sprev = sdig + ((k - 1) & 1) * (512 * 8);
     if (cnt <= COOP_MAX) {
@@ -146,7 +168,8 @@ LSK_D void subtree_build(uint32_t* __restrict__ nodes, const uint32_t* const* __
         const uint32_t t = t0 + (lane >> 4), tc = t < cnt ? t : cnt - 1;
         const size_t i = (in0 >> k) + tc;
         const uint32_t* children = !k ? nullptr : (k > k0 ? sprev + 16 * tc : prev + 16 * i);
-        uint32_t s = merkle_digest_coop(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr, children, ck, lane);
+        uint32_t s = merkle_digest_coop(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr, children, ck, lane,
+                                        rd_layer ? rd_layer + i * 8 : nullptr);
         if (t < cnt && (lane & 15) < 8) {
           layer[i * 8 + (lane & 15)] = s;
           scur[t * 8 + (lane & 15)] = s;
@@ -158,7 +181,7 @@ LSK_D void subtree_build(uint32_t* __restrict__ nodes, const uint32_t* const* __
         const size_t i = (in0 >> k) + t;
         const uint32_t* children = !k ? nullptr : (k > k0 ? sprev + 16 * t : prev + 16 * i);
         uint32_t st[16];
-        merkle_digest(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr, children, st);
+        merkle_digest(gcols, ncols, i, packed ? fri_vals + i * 8 : nullptr, children, st, rd_layer ? rd_layer + i * 8 : nullptr);
         store_digest(layer + i * 8, st);
         store_digest(scur + t * 8, st);
       }
@@ -187,7 +210,7 @@ __global__ void __launch_bounds__(ST_THREADS) merkle_subtree_kernel(SubtreeArgs 
   const Coop16 ck = coop16_load(threadIdx.x & 31);
   __shared__ __align__(16) uint32_t sdig[2 * 512 * 8];
   subtree_build<MODE>(a.nodes, a.cols, a.fri_vals, a.levels, a.log_in, a.off, a.inj_first, a.inj_ncols,
-                      (size_t)blockIdx.x << a.log_in, ck, sdig);
+                      (size_t)blockIdx.x << a.log_in, ck, sdig, a.rowdig);
   if (a.fc.chal && blockIdx.x == 0 && threadIdx.x < 32) fri_challenge(a.fc, a.nodes + (size_t)a.off[a.levels] * 8, ck);
 }
 
@@ -226,6 +249,32 @@ __global__ void __launch_bounds__(ST_THREADS) fri_tail_kernel(FriTailArgs a) {
     }
     __syncthreads();
   }
+}
+
+// Row digests of everything injected into the TAIL of a tree, in one launch.  A Lurk shard has wide chips with a handful
+// of rows (hash3/4/5: 493-815 columns): inside the tail such a row is a chain of ~100 dependent permutations, and the
+// levels were walked one after another (1.4 ms for the main commitment of a Lurk fib shard, 1.0 of it one 128-node
+// level on a single SM).  Here every injected row of every tail level is a half-warp job (16 lanes per permutation)
+// spread over the machine, so the chains of different levels and rows run side by side; the tail then only compresses.
+struct TailRowJob { uint32_t first_col, ncols, nrows, off; };   // column-list range, rows of the level, digest offset
+constexpr int TAIL_ROWS_THREADS = 128;   // 8 half-warps per CTA: many CTAs, few chains per SM
+__global__ void __launch_bounds__(TAIL_ROWS_THREADS) tail_rows_kernel(const uint32_t* const* __restrict__ cols,
+                                                                      const TailRowJob* __restrict__ jobs, uint32_t njobs,
+                                                                      uint32_t* __restrict__ rowdig) {
+  const unsigned lane = threadIdx.x & 31;
+  const Coop16 ck = coop16_load(lane);
+  // global warp index -> (job, pair of rows): both half-warps of a warp work on the SAME job (the permutation's shuffles
+  // are warp-wide, so the two halves must run the same number of permutations); jobs are few, a linear walk is cheap.
+  // A half-warp past the end of its job recomputes the job's last row and does not store.
+  uint32_t w = (blockIdx.x * TAIL_ROWS_THREADS + threadIdx.x) >> 5;
+  uint32_t j = 0;
+  while (j + 1 < njobs && w >= (jobs[j].nrows + 1) / 2) w -= (jobs[j].nrows + 1) / 2, j++;
+  const TailRowJob job = jobs[j];
+  const uint32_t hw = 2 * w + (lane >> 4);
+  const bool live = hw < job.nrows;
+  const uint32_t row = live ? hw : job.nrows - 1;
+  uint32_t s = merkle_digest_coop(cols + job.first_col, job.ncols, row, nullptr, nullptr, ck, lane);
+  if (live && (lane & 15) < 8) rowdig[((size_t)job.off + row) * 8 + (lane & 15)] = s;
 }
 
 // Throughput-bound part of a tree: one thread per leaf / per node, one launch per layer.
@@ -334,6 +383,36 @@ static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std:
     comm_allgather(ctx, tree.nodes.p + tree.layer_off[l0] * 8, n / ctx->comm->size * 32);
     tree.dist_layers = l0;
   }
+  // row digests of everything injected into the tail, all levels at once (tail_rows_kernel)
+  DevBuf<uint32_t> rowdig;
+  uint32_t* rowdig_biased = nullptr;
+  DevBuf<TailRowJob> d_jobs;
+  if (leaf_mode == ST_LEAVES) {
+    std::vector<TailRowJob> jobs;
+    uint32_t nwarps = 0, longest = 0;
+    const unsigned lfirst = first ? 0 : l0 + 1;
+    // the buffer covers the tail layers only; the pointer handed to the kernels is biased so that layer offsets of the
+    // whole tree index it
+    const size_t base = lfirst <= tree.log_max ? tree.layer_off[lfirst] : 0;
+    for (unsigned l = lfirst; l <= tree.log_max; l++) {
+      if (!groups[l].second) continue;
+      const uint32_t nrows = 1u << (tree.log_max - l);
+      jobs.push_back(TailRowJob{groups[l].first, groups[l].second, nrows, (uint32_t)tree.layer_off[l]});
+      nwarps += (nrows + 1) / 2;
+      longest = std::max(longest, groups[l].second);
+    }
+    if (!jobs.empty() && longest > 16) {   // worth a launch once some row is a chain of more than two permutations
+      rowdig.alloc(ctx, tree.nodes.n - base * 8);
+      rowdig_biased = rowdig.p - base * 8;
+      d_jobs.alloc(ctx, jobs.size());
+      d_jobs.upload(jobs.data(), jobs.size());
+      double perms = 0, bytes = 0;
+      for (auto& j : jobs) perms += (double)j.nrows * ((j.ncols + 7) / 8), bytes += (double)j.nrows * (4.0 * j.ncols + 32.0);
+      ProfScope ps(ctx, PT_MERKLE_TOP, 1, bytes);
+      tail_rows_kernel<<<div_up((size_t)nwarps * 32, TAIL_ROWS_THREADS), TAIL_ROWS_THREADS, 0, st>>>(tree.colptrs.p, d_jobs.p,
+                                                                                                   (uint32_t)jobs.size(), rowdig_biased);
+    }
+  }
   // latency-bound tail (or a whole small tree): subtree launches
   while (first || l0 < tree.log_max) {
     unsigned log_nodes = tree.log_max - l0;  // log2(nodes of layer l0)
@@ -342,6 +421,7 @@ static void build_tree(lsk_ctx* ctx, MerkleTreeDev& tree, const std::vector<std:
     a.nodes = tree.nodes.p;
     a.cols = tree.colptrs.p;
     a.fri_vals = fri_vals;
+    a.rowdig = rowdig_biased;
     a.l0 = l0;
     a.levels = log_in;
     a.log_in = log_in;

@@ -614,10 +614,8 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
       for (auto& mt : rd.mats) {
         ReduceMat rmat{};
         rmat.p = mt.p; rmat.stride = mt.stride; rmat.w = mt.w; rmat.npoints = mt.npoints;
+        rmat.open_off = (uint32_t)mt.open_off;   // y[p] = sum_c alpha^c opened[open_off + 2 c + p]: reduce_y_dev
         for (uint32_t p = 0; p < mt.npoints; p++) {
-          Ext y = ext_zero();
-          for (uint32_t c = 0; c < mt.w; c++) y = eadd(y, emul(h_fri[c], h_open[mt.open_off + 2 * c + p]));
-          rmat.y[p] = y;
           rmat.off[p] = alpha_off[mt.lh];
           alpha_off[mt.lh] = emul(alpha_off[mt.lh], h_fri[mt.w]);
         }
@@ -631,6 +629,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
     ro[lh].alloc(ctx, (size_t)1 << lh);
     ro_desc[lh].alloc(ctx, by_height[lh].size());
     ro_desc[lh].upload(by_height[lh].data(), by_height[lh].size());
+    reduce_y_dev(ctx, ro_desc[lh].p, (uint32_t)by_height[lh].size(), opened.p, d_fri.p);
     double bytes = 16.0 * (double)((size_t)1 << lh);
     for (auto& rmat : by_height[lh]) bytes += 4.0 * rmat.w * (double)((size_t)1 << lh);
     reduce_openings_dev(ctx, ro_desc[lh].p, (uint32_t)by_height[lh].size(), lh, zeta, d_fri.p, ro[lh].p, bytes);

@@ -342,6 +342,37 @@ void open_batch_dev(lsk_ctx* ctx, const std::vector<OpenMat>& mats, unsigned log
 }
 
 // ---- FRI: reduced openings, fold, grind --------------------------------------------------------------------
+__global__ void __launch_bounds__(128) reduce_y_kernel(ReduceMat* __restrict__ mats, const Ext* __restrict__ opened,
+                                                       const Ext* __restrict__ apow) {
+  __shared__ Ext red[2][4];
+  ReduceMat& m = mats[blockIdx.x];
+  Ext acc[2] = {ext_zero(), ext_zero()};
+  for (uint32_t c = threadIdx.x; c < m.w; c += 128) {
+    const Ext a = apow[c];
+    acc[0] = eadd(acc[0], emul(a, opened[m.open_off + 2 * c]));
+    if (m.npoints > 1) acc[1] = eadd(acc[1], emul(a, opened[m.open_off + 2 * c + 1]));
+  }
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int p = 0; p < 2; p++) {
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      uint32_t v = acc[p].c[e];
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) v = fadd(v, __shfl_xor_sync(0xffffffffu, v, d));
+      if (lane == 0) red[p][warp].c[e] = v;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) m.y[threadIdx.x] = eadd(eadd(red[threadIdx.x][0], red[threadIdx.x][1]), eadd(red[threadIdx.x][2], red[threadIdx.x][3]));
+}
+void reduce_y_dev(lsk_ctx* ctx, ReduceMat* mats_dev, uint32_t nmats, const Ext* opened_dev, const Ext* alpha_pows_dev) {
+  if (!nmats) return;
+  ProfScope ps(ctx, PT_REDUCE_OPEN, 1, 0.0);
+  reduce_y_kernel<<<nmats, 128, 0, ctx->stream>>>(mats_dev, opened_dev, alpha_pows_dev);
+  LSK_CUDA(cudaGetLastError());
+}
+
 template <int COLS>   // columns per loop iteration (each pair of columns shares one conditional subtraction)
 __global__ void __launch_bounds__(256) reduce_openings_kernel(const ReduceMat* __restrict__ mats, uint32_t nmats,
                                                                unsigned lh, uint32_t g, uint32_t w, Ext z0, Ext z1,

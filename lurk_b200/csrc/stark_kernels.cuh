@@ -54,11 +54,15 @@ struct ReduceMat {  // one opened matrix of LDE height 2^lh
   const uint32_t* p;
   uint64_t stride;
   uint32_t w, npoints;
+  uint32_t open_off, pad_;   // the matrix's opened values: opened[open_off + 2 c + p] (reduce_y_dev fills y from them)
   Ext y[2];    // sum_c alpha^c * opened_value_p[c]
   Ext off[2];  // alpha offset of (matrix, point)
 };
 // ro[r] = sum over mats, points of off * (y - sum_c alpha^c m[r][c]) / (z_p - x_r), x_r = g * w_{2^lh}^bitrev(r),
 // z_0 = zeta, z_1 = zeta * w_{2^(lh-1)}
+// y[p] of every matrix of the array from the opened values on the device (one CTA per matrix): the ~14 k extension
+// products of a Lurk shard that the host used to do while the device waited
+void reduce_y_dev(lsk_ctx* ctx, ReduceMat* mats_dev, uint32_t nmats, const Ext* opened_dev, const Ext* alpha_pows_dev);
 void reduce_openings_dev(lsk_ctx* ctx, const ReduceMat* mats_dev, uint32_t nmats, unsigned lh, Ext zeta,
                          const Ext* alpha_pows_dev, Ext* ro, double algorithmic_bytes);
 // out[i] = (1/2 + t) cur[2i] + (1/2 - t) cur[2i+1] (+ add[i]),  t = beta / (2 * w_{2^(logh+1)}^bitrev(i))

@@ -303,12 +303,40 @@ static std::unique_ptr<ShardState> commit_shard(lsk_machine& m, const lsk_record
   return sd;
 }
 
-static void push_ext(std::vector<uint32_t>& w, const Ext& e) {
+// The proof under construction: words in a malloc'd buffer that is handed to the caller as it is (lsk_proof_free =
+// free) -- a std::vector would be copied once more, and fresh pages faulted in twice, for the 2.6 MB of a Lurk shard proof.
+struct ProofWords {
+  uint32_t* p = nullptr;
+  size_t n = 0, cap = 0;
+  ProofWords() = default;
+  ProofWords(const ProofWords&) = delete;
+  ProofWords& operator=(const ProofWords&) = delete;
+  ~ProofWords() { free(p); }
+  void reserve(size_t want) {
+    if (want <= cap) return;
+    size_t c = std::max<size_t>(want, cap * 2 + 64);
+    uint32_t* q = (uint32_t*)realloc(p, c * sizeof(uint32_t));
+    if (!q) fail(LSK_ERR_ARG, "out of memory");
+    p = q, cap = c;
+  }
+  void push_back(uint32_t v) {
+    if (n == cap) reserve(n + 1);
+    p[n++] = v;
+  }
+  void append(const uint32_t* src, size_t count) {
+    reserve(n + count);
+    memcpy(p + n, src, count * sizeof(uint32_t));
+    n += count;
+  }
+  size_t size() const { return n; }
+  uint32_t* release() { uint32_t* q = p; p = nullptr; n = cap = 0; return q; }
+};
+static void push_ext(ProofWords& w, const Ext& e) {
   for (int k = 0; k < 4; k++) w.push_back(from_mont(e.c[k]));
 }
 
 // ---- phase 2: everything after the main commitment --------------------------------------------------------
-static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, Challenger ch, std::vector<uint32_t>& W) {
+static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, Challenger ch, ProofWords& W) {
   lsk_ctx* ctx = m.ctx;
   cudaStream_t st = ctx->stream;
   const size_t nchips = sd.chip_ids.size();
@@ -784,7 +812,7 @@ static void prove_shard(lsk_machine& m, const lsk_record& rec, ShardState& sd, C
   W.push_back(pow_witness);
   W.push_back(m.num_queries);
   LSK_CUDA(cudaStreamSynchronize(st));   // the query words have arrived (segs / indices stay alive until here)
-  W.insert(W.end(), gathered, gathered + ngathered);
+  W.append(gathered, ngathered);
   pt.mark("serialise");
 }
 
@@ -958,12 +986,10 @@ int lsk_shard_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard, const
   m->pending.erase(it);
   Challenger ch = initial_challenger(*m);
   for (uint32_t s = 0; s < nshards; s++) observe_shard(*m, ch, all_roots + 8 * s, rec->public_values.data());
-  std::vector<uint32_t> W;
+  ProofWords W;
   prove_shard(*m, *rec, *sd, ch, W);
-  *words = (uint32_t*)malloc(W.size() * 4 + 4);
-  if (!*words) fail(LSK_ERR_ARG, "out of memory");
-  memcpy(*words, W.data(), W.size() * 4);
   *len = W.size();
+  *words = W.release();
   return LSK_OK;
   LSK_API_END
 }
@@ -1021,17 +1047,15 @@ int lsk_prove(lsk_machine* m, const lsk_record* rec, uint32_t shard_size, uint32
     shards.push_back(commit_shard(*m, *rec, s, shard_size, true));
     observe_shard(*m, ch, shards.back()->main_root, rec->public_values.data());
   }
-  std::vector<uint32_t> W;
+  ProofWords W;
   W.push_back(PROOF_MAGIC);
   W.push_back(ns);
   for (uint32_t s = 0; s < ns; s++) {
     prove_shard(*m, *rec, *shards[s], ch, W);
     shards[s].reset();
   }
-  *words = (uint32_t*)malloc(W.size() * 4 + 4);
-  if (!*words) fail(LSK_ERR_ARG, "out of memory");
-  memcpy(*words, W.data(), W.size() * 4);
   *len = W.size();
+  *words = W.release();
   return LSK_OK;
   LSK_API_END
 }

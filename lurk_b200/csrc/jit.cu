@@ -100,6 +100,20 @@ uint32_t smem_bytes_for(const ChipH& c) {
   const size_t bytes = (size_t)(c.n_regs ? c.n_regs : 1u) * JIT_THREADS * 4;
   return bytes <= (96u << 10) ? (uint32_t)bytes : 0u;   // at least two CTAs per SM
 }
+// threads per CTA of the compiled quotient kernel (LSK_JIT_QTHREADS overrides, for tuning; part of the source, hence of the
+// cache key)
+uint32_t quotient_threads(const ChipH& c) {
+  if (const char* e = getenv("LSK_JIT_QTHREADS")) {
+    long v = atol(e);
+    if (v >= 64 && v <= 1024 && v % 32 == 0) return (uint32_t)v;
+  }
+  // measured on B200 (quotient kernels per prove, ms): Lurk fib 2^20 256 -> 12.5, 512 -> 16.5, 768 -> 12.4; Lurk lcs 2^22
+  // 256 -> 67.7, 512 -> 83.9, 768 -> 59.6.  768 threads = one CTA per SM at 80 registers: a single instruction stream per SM
+  // (256: three CTAs at different places of the megabyte-sized program; 512: one CTA, a third fewer warps).  The hasher
+  // chips are the exception: their programs keep 40-70 values alive across chunks and want the 86 registers a 256-thread
+  // CTA may have (hash4 chip at 2^20 rows: 7.2 ms at 256 threads, 8.4 at 768)
+  return c.n_regs > 16 ? 256 : 768;
+}
 // statements per __noinline__ chunk (LSK_JIT_CHUNK overrides, for tuning; part of the source, hence of the cache key)
 uint32_t chunk_size() {
   if (const char* e = getenv("LSK_JIT_CHUNK")) {
@@ -289,11 +303,11 @@ std::string interactions_source(const ChipH& c) {
 std::string main_source(const ChipH& c) {
   uint32_t asserts = 0;
   for (size_t i = 0; i < c.code.size(); i += 4) asserts += c.code[i] == COP_ASSERT;
-  char buf[200];
+  char buf[256];
   snprintf(buf, sizeof buf,
            "#define LSK_JIT_PROGRAM 1\n#define LSK_JIT_REGS %u\n#define LSK_JIT_ASSERTS %u\n#define LSK_JIT_SMEM %u\n"
-           "#include \"quotient_kernel.cuh\"\n",
-           c.n_regs ? c.n_regs : 1u, asserts, smem_bytes_for(c) ? 1u : 0u);
+           "#define LSK_JIT_QTHREADS %u\n#include \"quotient_kernel.cuh\"\n",
+           c.n_regs ? c.n_regs : 1u, asserts, smem_bytes_for(c) ? 1u : 0u, smem_bytes_for(c) ? 256u : quotient_threads(c));
   return buf;
 }
 
@@ -426,6 +440,7 @@ JitKernel* jit_quotient(const ChipH& c) {
   if (!driver().ok) fail(LSK_ERR_CUDA, "libcuda.so.1 could not be loaded for a compiled constraint program");
   auto k = new JitKernel;
   k->smem_bytes = smem_bytes_for(c);
+  k->qthreads = k->smem_bytes ? 256u : quotient_threads(c);
   int rc = driver().ModuleLoadData(&k->module, cubin.data());
   if (rc == 0) rc = driver().ModuleGetFunction(&k->function, k->module, "lsk_quotient_jit");
   if (rc == 0) rc = driver().ModuleGetFunction(&k->perm_function, k->module, "lsk_perm_rows_jit");
@@ -450,7 +465,7 @@ void jit_launch(lsk_ctx* ctx, const JitKernel* k, const QuotientArgs& a, const Q
   void* params[] = {(void*)&a, (void*)&qc, (void*)&inter, (void*)&nint, (void*)&pw};
   // (a two-rows-per-thread variant -- every chunk run for row A, then, instructions cached, for row B -- was measured
   // and removed: quotient 13.7 -> 17.9 ms on Lurk fib 2^20, 68.8 -> 95.8 ms on lcs 2^22)
-  int rc = driver().LaunchKernel(k->function, div_up(nrows, JIT_THREADS), 1, 1, JIT_THREADS, 1, 1, k->smem_bytes, ctx->stream,
+  int rc = driver().LaunchKernel(k->function, div_up(nrows, k->qthreads), 1, 1, k->qthreads, 1, 1, k->smem_bytes, ctx->stream,
                                  params, nullptr);
   if (rc != 0) fail(LSK_ERR_CUDA, "cuLaunchKernel of a compiled constraint program failed (CUresult %d)", rc);
 }

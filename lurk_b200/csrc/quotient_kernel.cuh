@@ -289,13 +289,19 @@ extern "C" __global__ void __launch_bounds__(256) lsk_perm_rows_jit(PermRowsArgs
   lsk_interactions(cells, a.alpha, a.beta_pows, v);
   a.rowsum_out[a.scatter ? bitrev32((uint32_t)r, a.logn) : r] = v.rowsum;
 }
-extern "C" __global__ void __launch_bounds__(256) lsk_quotient_jit(QuotientArgs a, QuotientConsts qc,
+// threads per CTA of the compiled quotient (jit.cu defines it; LSK_JIT_QTHREADS in the environment at compile time).  The
+// warps of a CTA walk the straight-line program in step (a barrier per chunk), so a larger CTA means fewer instruction
+// streams per SM.
+#ifndef LSK_JIT_QTHREADS
+#define LSK_JIT_QTHREADS 768
+#endif
+extern "C" __global__ void __launch_bounds__(LSK_JIT_QTHREADS) lsk_quotient_jit(QuotientArgs a, QuotientConsts qc,
                                                                    const uint32_t* __restrict__ inter, uint32_t nint,
                                                                    uint32_t pw) {
   // no early exit: the chunks are separated by __syncthreads() so that the warps of a CTA walk the (megabyte-sized,
   // straight-line) program together and share what the instruction cache fetched -- ncu showed "no instruction"
   // as the second stall reason without it.  Threads past the end recompute a valid row and do not store.
-  size_t row = a.row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
+  size_t row = a.row_begin + (size_t)blockIdx.x * LSK_JIT_QTHREADS + threadIdx.x;
   const bool live = row < a.row_end;
   if (!live) row = a.row_begin;
   QuotientRow q;

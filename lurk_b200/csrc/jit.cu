@@ -114,6 +114,15 @@ uint32_t quotient_threads(const ChipH& c) {
   // CTA may have (hash4 chip at 2^20 rows: 7.2 ms at 256 threads, 8.4 at 768)
   return c.n_regs > 16 ? 256 : 768;
 }
+uint32_t perm_threads() {   // threads per CTA of the compiled permutation-row kernel (LSK_JIT_PTHREADS: tuning)
+  if (const char* e = getenv("LSK_JIT_PTHREADS")) {
+    long v = atol(e);
+    if (v >= 64 && v <= 1024 && v % 32 == 0) return (uint32_t)v;
+  }
+  // measured on B200 (permutation-row kernels per prove, ms): Lurk fib 2^20 256 -> 5.36, 512 -> 4.85, 768 -> 4.91; Lurk
+  // lcs 2^22 256 -> 37.2, 512 -> 28.9, 768 -> 24.7 (the same one-instruction-stream-per-SM effect as the quotient's)
+  return 768;
+}
 // statements per __noinline__ chunk (LSK_JIT_CHUNK overrides, for tuning; part of the source, hence of the cache key)
 uint32_t chunk_size() {
   if (const char* e = getenv("LSK_JIT_CHUNK")) {
@@ -306,8 +315,9 @@ std::string main_source(const ChipH& c) {
   char buf[256];
   snprintf(buf, sizeof buf,
            "#define LSK_JIT_PROGRAM 1\n#define LSK_JIT_REGS %u\n#define LSK_JIT_ASSERTS %u\n#define LSK_JIT_SMEM %u\n"
-           "#define LSK_JIT_QTHREADS %u\n#include \"quotient_kernel.cuh\"\n",
-           c.n_regs ? c.n_regs : 1u, asserts, smem_bytes_for(c) ? 1u : 0u, smem_bytes_for(c) ? 256u : quotient_threads(c));
+           "#define LSK_JIT_QTHREADS %u\n#define LSK_JIT_PTHREADS %u\n#include \"quotient_kernel.cuh\"\n",
+           c.n_regs ? c.n_regs : 1u, asserts, smem_bytes_for(c) ? 1u : 0u, smem_bytes_for(c) ? 256u : quotient_threads(c),
+           perm_threads());
   return buf;
 }
 
@@ -441,6 +451,7 @@ JitKernel* jit_quotient(const ChipH& c) {
   auto k = new JitKernel;
   k->smem_bytes = smem_bytes_for(c);
   k->qthreads = k->smem_bytes ? 256u : quotient_threads(c);
+  k->pthreads = perm_threads();
   int rc = driver().ModuleLoadData(&k->module, cubin.data());
   if (rc == 0) rc = driver().ModuleGetFunction(&k->function, k->module, "lsk_quotient_jit");
   if (rc == 0) rc = driver().ModuleGetFunction(&k->perm_function, k->module, "lsk_perm_rows_jit");
@@ -474,7 +485,7 @@ void jit_launch(lsk_ctx* ctx, const JitKernel* k, const QuotientArgs& a, const Q
 void jit_launch_perm(lsk_ctx* ctx, const JitKernel* k, const PermRowsArgs& a) {
   const size_t nrows = a.row_end - a.row_begin;
   void* params[] = {(void*)&a};
-  int rc = driver().LaunchKernel(k->perm_function, div_up(nrows, JIT_THREADS), 1, 1, JIT_THREADS, 1, 1, 0, ctx->stream, params,
+  int rc = driver().LaunchKernel(k->perm_function, div_up(nrows, k->pthreads), 1, 1, k->pthreads, 1, 1, 0, ctx->stream, params,
                                  nullptr);
   if (rc != 0) fail(LSK_ERR_CUDA, "cuLaunchKernel of a compiled permutation-trace kernel failed (CUresult %d)", rc);
 }

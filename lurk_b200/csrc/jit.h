@@ -17,6 +17,7 @@ struct JitKernel {
   void* function = nullptr;  // CUfunction of lsk_quotient_jit
   void* perm_function = nullptr;  // CUfunction of lsk_perm_rows_jit (the chip's LogUp permutation-trace rows)
   uint32_t qthreads = 768;   // threads per CTA the quotient kernel was compiled for
+  uint32_t pthreads = 768;   // ... and the permutation-row kernel
   uint32_t smem_bytes = 0;   // dynamic shared memory of a launch: the program's register file, or 0 (local memory)
 };
 

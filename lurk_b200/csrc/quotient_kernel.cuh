@@ -281,8 +281,11 @@ struct LskPermBatches {
     close(b);
   }
 };
-extern "C" __global__ void __launch_bounds__(256) lsk_perm_rows_jit(PermRowsArgs a) {
-  const size_t r = a.row_begin + (size_t)blockIdx.x * 256 + threadIdx.x;
+#ifndef LSK_JIT_PTHREADS
+#define LSK_JIT_PTHREADS 256
+#endif
+extern "C" __global__ void __launch_bounds__(LSK_JIT_PTHREADS) lsk_perm_rows_jit(PermRowsArgs a) {
+  const size_t r = a.row_begin + (size_t)blockIdx.x * LSK_JIT_PTHREADS + threadIdx.x;
   if (r >= a.row_end) return;
   const Cells cells{a.main, a.mstride, a.prep, a.pstride, r};
   LskPermBatches v{a, r, ext_zero(), {}, {}, 0u};

@@ -365,6 +365,11 @@ def run_ours(args):
     wl = Workload(args.workload)
     top, entry = wl.top, wl.entry
     m = new_machine(top, entry, ctx=ctx)
+    if rank == 0 and wl.name.startswith("lurk") and int(N.lib().lsk_machine_jit_chips(m.h)) == 0:
+        # a Lurk machine without compiled constraint programs proves correctly but ~25 % slower (every chip interpreted):
+        # the cubin cache is stale -- an edit of field.cuh / quotient_kernel.cuh invalidates it; build() refills it
+        print("bench.py: WARNING: no compiled constraint programs in lurk_b200/jit_cache for this library; run "
+              "`python -m lurk_b200.jit_warm` (or __graft_entry__.build())", file=sys.stderr, flush=True)
     pk, vk = m.setup()
     K = args.shards_per_gpu
     column = args.partition == "column"   # every shard is proved by a GROUP of ranks together
